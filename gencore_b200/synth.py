@@ -347,8 +347,10 @@ def make_fixed_batch(cfg: FixedConfig, seed: int, n_pairs: Optional[int] = None,
     else:
         contigs, genome = genome_cache
     # ---- molecules
-    n_mol = max(1, int(round(n_target / cfg.depth)))
+    n_mol = int(n_target / cfg.depth * 1.25) + 64
     fam = 1 + rng.poisson(max(cfg.depth - 1.0, 0.0), n_mol).astype(np.int64)
+    while fam.sum() < n_target:
+        fam = np.concatenate([fam, 1 + rng.poisson(max(cfg.depth - 1.0, 0.0), n_mol).astype(np.int64)])
     csum = np.cumsum(fam)
     n_mol = int(np.searchsorted(csum, n_target, side="left")) + 1
     fam = fam[:n_mol]

@@ -98,3 +98,27 @@ def assert_matches_reference(batch: Batch, res: Result, ref_pairs, ref_out, ref_
                  "post_cluster", "post_multi_cluster", "post_sscs", "post_dcs"):
         assert getattr(st, name) == int(ref_stats[name]), f"stats {name}: {getattr(st, name)} vs {int(ref_stats[name])}"
     np.testing.assert_array_equal(st.pre_hist, ref_stats["pre_hist"], err_msg="stats pre_hist")
+
+
+# ----------------------------------------------------------------------------- golden fixtures (tests/golden/*.npz)
+
+def save_golden(path, batch, genome, contigs, opt, ref_pairs, ref_out, ref_stats, n_ref):
+    import ctypes
+    qn = np.asarray([bytes(q) for q in batch.qnames], dtype="S")
+    np.savez_compressed(
+        path, cluster_pair_off=batch.cluster_pair_off, cluster_ref=batch.cluster_ref, cluster_flags=batch.cluster_flags,
+        umi=batch.umi, reads=batch.reads, cigar=batch.cigar, payload=batch.payload, qnames=qn, nm=batch.nm,
+        umi_prefix=np.asarray(batch.umi_prefix), packed4=genome.packed4, contig_off=genome.contig_off,
+        contig_len=genome.contig_len, names=np.asarray(genome.names),
+        opt=np.frombuffer(ctypes.string_at(ctypes.addressof(opt), ctypes.sizeof(opt)), np.uint8),
+        ref_pairs=ref_pairs, ref_out=ref_out, ref_stats=np.asarray([ref_stats]), n_ref=np.asarray(n_ref))
+
+
+def load_golden(path):
+    from gencore_b200.abi import Genome, Options
+    z = np.load(path, allow_pickle=False)
+    batch = Batch(z["cluster_pair_off"], z["cluster_ref"], z["cluster_flags"], z["umi"], z["reads"], z["cigar"], z["payload"],
+                  list(z["qnames"]), z["nm"], str(z["umi_prefix"]))
+    genome = Genome(z["packed4"], z["contig_off"], z["contig_len"], [str(x) for x in z["names"]])
+    opt = Options.from_buffer_copy(z["opt"].tobytes())
+    return batch, genome, opt, z["ref_pairs"], z["ref_out"], z["ref_stats"][0], int(z["n_ref"])
