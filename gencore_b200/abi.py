@@ -88,7 +88,7 @@ assert GROUP_RESULT.itemsize == 72
 
 class BatchStruct(C.Structure):
     _fields_ = [
-        ("n_clusters", C.c_int32), ("n_pairs", C.c_int32), ("umi_words", C.c_int32), ("reserved", C.c_int32),
+        ("n_clusters", C.c_int32), ("n_pairs", C.c_int32), ("umi_words", C.c_int32), ("max_cluster_bytes", C.c_int32),
         ("cluster_pair_off", C.c_void_p), ("cluster_ref", C.c_void_p), ("cluster_flags", C.c_void_p),
         ("umi", C.c_void_p), ("reads", C.c_void_p), ("cigar", C.c_void_p), ("n_cigar_ops", C.c_int64),
         ("payload", C.c_void_p), ("payload_bytes", C.c_int64),
@@ -176,11 +176,24 @@ class Batch:
     def as_struct(self) -> BatchStruct:
         """Struct of HOST pointers (the arrays must stay alive while it is used)."""
         return BatchStruct(
-            self.n_clusters, self.n_pairs, self.umi_words, 0,
+            self.n_clusters, self.n_pairs, self.umi_words, self.max_cluster_bytes(),
             self.cluster_pair_off.ctypes.data, self.cluster_ref.ctypes.data, self.cluster_flags.ctypes.data,
             self.umi.ctypes.data, self.reads.ctypes.data, self.cigar.ctypes.data, len(self.cigar),
             self.payload.ctypes.data, len(self.payload),
         )
+
+    def cluster_slab_bounds(self) -> np.ndarray:
+        """int64 [n_clusters+1]: payload byte range of each cluster (see the header's layout rule)."""
+        first = self.reads["data_off"][0::2]
+        b = np.empty(self.n_clusters + 1, np.int64)
+        b[:-1] = first[self.cluster_pair_off[:-1]]
+        b[-1] = len(self.payload)
+        return b
+
+    def max_cluster_bytes(self) -> int:
+        if self.n_clusters == 0:
+            return 0
+        return int(min(np.diff(self.cluster_slab_bounds()).max(), 2**31 - 1))
 
     def algorithmic_bytes(self) -> dict:
         """SURVEY §8(d) payload-only byte counts for the vote kernel (input side)."""
@@ -231,7 +244,7 @@ def encode_umi(umi: str, words: int) -> np.ndarray:
         raise ValueError(f"UMI {umi!r} longer than {16 * words}")
     out = np.zeros(words, np.uint64)
     for k, ch in enumerate(umi):
-        out[k >> 4] |= np.uint64(UMI_CODE[ch] << (4 * (k & 15)))
+        out[k >> 4] |= np.uint64(UMI_CODE[ch] << (60 - 4 * (k & 15)))
     return out
 
 

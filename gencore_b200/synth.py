@@ -409,7 +409,7 @@ def make_fixed_batch(cfg: FixedConfig, seed: int, n_pairs: Optional[int] = None,
             fields[ei[ok], ej[ok]] = rng.integers(1, 5, int(ok.sum()), dtype=np.uint8)
         umi = np.zeros((N, words), np.uint64)
         for j in range(nfield):
-            umi[:, j >> 4] |= fields[:, j].astype(np.uint64) << np.uint64(4 * (j & 15))
+            umi[:, j >> 4] |= fields[:, j].astype(np.uint64) << np.uint64(60 - 4 * (j & 15))
         umi_chars = np.frombuffer(b"?ACGT_", np.uint8)[fields]
     # ---- reads: slot 2p = left, 2p+1 = right
     goff = np.concatenate([[0], np.cumsum([len(c) for c in contigs])[:-1]]).astype(np.int64)

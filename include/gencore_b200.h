@@ -23,14 +23,18 @@
  *   bases    BAM 4-bit codes, two per byte, EVEN index in the HIGH nibble (bam_get_seq layout).
  *   quals    raw phred bytes (bam_get_qual layout).
  *   payload  one record per read: l_qseq qual bytes at data_off, then the packed bases at
- *            data_off + GCB_ALIGN4(l_qseq).  Records of one cluster are contiguous and the
- *            cluster's first record starts on a 16-byte boundary (so one TMA bulk copy stages
- *            a whole cluster).
- *   UMI      `umi_words` little-endian u64 per pair; character k of the UMI string is the 4-bit
- *            field at bits [4k,4k+4) of word k/16: A=1 C=2 G=3 T=4 _=5, 0 = past the end.  (The
- *            reference's getUMI, bamutil.cpp:23-112, can only produce these five characters.)
- *            With this code umiDiff (cluster.cpp:41-53) is the number of differing fields, and
- *            big-endian field order is std::string order.
+ *            data_off + GCB_ALIGN4(l_qseq).  Records are laid out in read-slot order; those of one
+ *            cluster are contiguous and the cluster's first record starts on a 16-byte boundary,
+ *            so cluster c's slab is [reads[2*off[c]].data_off, reads[2*off[c+1]].data_off) (the
+ *            last one ends at payload_bytes) and one TMA bulk copy stages a whole cluster.  Every
+ *            pair has its side-0 read (Cluster::addRead always fills mLeft first, cluster.cpp:260).
+ *   UMI      `umi_words` u64 per pair; character k of the UMI string is the 4-bit field at bits
+ *            [60-4*(k%16), 64-4*(k%16)) of word k/16 (first character in the MOST significant
+ *            nibble): A=1 C=2 G=3 T=4 _=5, 0 = past the end.  (The reference's getUMI,
+ *            bamutil.cpp:23-112, can only produce these five characters.)  With this code umiDiff
+ *            (cluster.cpp:41-53) is the number of differing fields, and comparing the words as
+ *            unsigned integers, word 0 first, is std::string order (the map<string,int> order of
+ *            cluster.cpp:57-76).
  *   genome   the reference's own packing (fastareader.cpp:139-152): A=1 T=2 C=3 G=4 other=0,
  *            EVEN index in the LOW nibble, one byte string per contig.
  */
@@ -95,7 +99,7 @@ typedef struct gcb_batch {
     int32_t n_clusters;
     int32_t n_pairs;
     int32_t umi_words;               /* 1..GCB_MAX_UMI_WORDS */
-    int32_t reserved;
+    int32_t max_cluster_bytes;       /* hint: largest cluster slab in payload bytes, 0 = unknown */
     const int32_t *cluster_pair_off; /* [n_clusters+1]; pairs of cluster c are [off[c], off[c+1]) in the
                                         iteration order of Cluster::mPairs (map<string qname+pad>, cluster.h:45) */
     const int32_t *cluster_ref;      /* [n_clusters] genome contig index for the cluster's tid, or -1 when

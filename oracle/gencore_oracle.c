@@ -120,7 +120,7 @@ int gco_encode_umi(const char *umi, uint64_t *words, int n_words) {
     for (int k = 0; k < len; k++) {
         int code = umi_char_code(umi[k]);
         if (!code) return -1;
-        words[k >> 4] |= (uint64_t)code << (4 * (k & 15));
+        words[k >> 4] |= (uint64_t)code << (60 - 4 * (k & 15));
     }
     return len;
 }
@@ -128,7 +128,7 @@ int gco_encode_umi(const char *umi, uint64_t *words, int n_words) {
 static void decode_umi(const uint64_t *words, int n_words, char *out) {
     int k = 0;
     for (; k < 16 * n_words; k++) {
-        int code = (int)((words[k >> 4] >> (4 * (k & 15))) & 0xF);
+        int code = (int)((words[k >> 4] >> (60 - 4 * (k & 15))) & 0xF);
         if (!code) break;
         out[k] = UMI_CODE_CHAR[code & 7];
     }
@@ -639,7 +639,7 @@ static int duplex_merge_bam(W *w, int s1, int s2) {
 /* field-wise compare of two UMI codes == std::string compare of the UMIs */
 static int umi_cmp(const uint64_t *a, const uint64_t *b, int nw) {
     for (int k = 0; k < 16 * nw; k++) {
-        int fa = (int)((a[k >> 4] >> (4 * (k & 15))) & 0xF), fb = (int)((b[k >> 4] >> (4 * (k & 15))) & 0xF);
+        int fa = (int)((a[k >> 4] >> (60 - 4 * (k & 15))) & 0xF), fb = (int)((b[k >> 4] >> (60 - 4 * (k & 15))) & 0xF);
         if (fa != fb) return fa < fb ? -1 : 1;
     }
     return 0;
@@ -664,7 +664,7 @@ static void cluster_by_umi(W *w, int c, gcb_result *res, int64_t *out_cursor, in
     int hasUMI = 0;
     for (int i = 0; i < n; i++) {
         const uint64_t *u = b->umi + (size_t)(p0 + i) * nw;
-        if (u[0] & 0xF) hasUMI = 1;
+        if (u[0] >> 60) hasUMI = 1;
         rep[i] = i;
         for (int j = 0; j < i; j++)
             if (umi_cmp(u, b->umi + (size_t)(p0 + j) * nw, nw) == 0) { rep[i] = rep[j]; break; }

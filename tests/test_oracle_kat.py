@@ -49,10 +49,11 @@ def test_umi_code_is_string_order_and_hamming(oracle):
     for a, b in itertools.product(umis, umis):
         ca, cb = encode_umi(a, 2), encode_umi(b, 2)
         assert np.array_equal(ca, oracle.encode_umi(a, 2))
-        fa = [(int(ca[k >> 4]) >> (4 * (k & 15))) & 15 for k in range(32)]
-        fb = [(int(cb[k >> 4]) >> (4 * (k & 15))) & 15 for k in range(32)]
+        fa = [(int(ca[k >> 4]) >> (60 - 4 * (k & 15))) & 15 for k in range(32)]
+        fb = [(int(cb[k >> 4]) >> (60 - 4 * (k & 15))) & 15 for k in range(32)]
         assert sum(x != y for x, y in zip(fa, fb)) == oracle.umi_diff(a, b), (a, b)
         assert (fa < fb) == (a < b) and (fa == fb) == (a == b), (a, b)
+        assert ((int(ca[0]), int(ca[1])) < (int(cb[0]), int(cb[1]))) == (a < b), (a, b)
 
 
 def test_kat_against_compiled_reference(oracle, have_reference):
