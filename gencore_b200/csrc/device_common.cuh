@@ -2,45 +2,49 @@
 // Reference semantics are cited as file:line under /root/reference/src.
 #pragma once
 
-#include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "gencore_b200.h"
-
-#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
-#error "gencore_b200 is written for sm_100a (B200) only"
-#endif
+#include "simt.h"
 
 namespace gcb {
 
 constexpr int WARP = 32;
 constexpr unsigned FULL = 0xffffffffu;
 
-// ---- workspace that lives in the context and carries state between the four kernels
+// ---- workspace that lives in the context and carries state between the kernels of one batch
 struct PairOverlap {   // Pair::computeScore's overlap window (pair.cpp:103-119), one per pair
-    int16_t left_start;   // first overlapped index in the left read
-    int16_t right_start;  // first overlapped index in the right read
-    int16_t cmp_len;      // overlapped length (may be <= 0)
-    int16_t valid;        // 1: both mates present and both have an M block (scores are quality-derived)
+    int32_t left_start;   // first overlapped index in the left read
+    int32_t right_start;  // first overlapped index in the right read
+    int32_t cmp_len;      // overlapped length (may be <= 0)
+    int32_t valid;        // 1: both mates present and both have an M block (scores depend on quality)
 };
 
 struct Workspace {
-    int32_t *members;         // [n_pairs] pair indices of each cluster, grouped by UMI family (stable)
-    int32_t *group_start;     // [n_pairs] slot-indexed: offset (within the batch) of the family's first member
-    int32_t *umi_count;       // [n_pairs] multiplicity of each pair's UMI inside its cluster
-    int32_t *right_ref_pos;   // [2*n_pairs] BamUtil::getRightRefPos per read
-    uint8_t *vote_flags;      // [2*n_pairs] VOTE_* per read
-    uint8_t *side_mode;       // [2*n_pairs] slot*2+side: leftReadMode used for that side's vote
-    uint8_t *cluster_has_umi; // [n_clusters]
-    PairOverlap *overlap;     // [n_pairs]
+    int32_t *members;           // [n_pairs] pair indices, cluster by cluster, families contiguous, map order inside
+    int32_t *group_off;         // [n_pairs] slot-indexed: index into members of the family's first pair
+    int32_t *scratch;           // [2*n_pairs] per read slot: containedBy counts (group.cpp:196-233) / duplex stack
+    int32_t *right_ref_pos;     // [2*n_pairs] BamUtil::getRightRefPos per read slot
+    uint8_t *vote_flags;        // [2*n_pairs] VOTE_* per read slot
+    uint8_t *side_mode;         // [2*n_pairs] index slot*2+side: SIDE_*
+    uint8_t *cluster_has_umi;   // [n_clusters] cluster.cpp:57-65 hasUMI
+    PairOverlap *overlap;       // [n_pairs]
+    int64_t *slab_off;          // [n_clusters+1] payload byte offset of each cluster's slab
     int64_t *cluster_out_bytes; // [n_clusters] bytes of consensus records the cluster emits
-    int64_t *cluster_out_off;   // [n_clusters] exclusive scan of the above
-    int64_t *scan_tiles;        // scratch of the scan
+    int64_t *cluster_out_off;   // [n_clusters] exclusive prefix of the above inside its scan block
+    int64_t *scan_block;        // [n_scan_blocks+1] exclusive prefix over scan blocks; last = total
     int32_t *error_flag;        // [1] sticky gcb_status raised by a kernel
 };
 
 constexpr uint8_t VOTE_PARTICIPATES = 1;  // read is in makeConsensus' `reads` (group.cpp:287-313)
 constexpr uint8_t VOTE_LENDIFF0 = 2;      // lenDiff forced to 0 (group.cpp:344-347)
+
+constexpr uint8_t SIDE_NONE = 0;   // consensusMergeBam returned NULL for this side
+constexpr uint8_t SIDE_LEFT = 1;   // vote with left-aligned column indexing (leftReadMode)
+constexpr uint8_t SIDE_RIGHT = 2;  // vote with right-aligned column indexing
+constexpr uint8_t SIDE_COPY = 3;   // single pair without mRight: record passes through (group.cpp:73-77)
+
+constexpr int SCAN_BLOCK = 2048;   // clusters per block of the output-offset scan
 
 struct GenomeView {
     const uint8_t *packed4;
@@ -50,18 +54,18 @@ struct GenomeView {
 };
 
 // ---- CIGAR helpers ------------------------------------------------------------------------
-__device__ __forceinline__ int cig_op(uint32_t c) { return (int)(c & 0xF); }
-__device__ __forceinline__ int cig_len(uint32_t c) { return (int)(c >> 4); }
+GCB_HD int cig_op(uint32_t c) { return (int)(c & 0xF); }
+GCB_HD int cig_len(uint32_t c) { return (int)(c >> 4); }
 // bamutil.cpp:290-291 as bit masks over the op code (ops >= 10 consume nothing)
-__device__ __forceinline__ int query_consum(int op) { return (0x193 >> op) & 1; }  // M I S = X
-__device__ __forceinline__ int ref_consum(int op) { return (0x18D >> op) & 1; }    // M D N = X
+GCB_HD int query_consum(int op) { return (0x193 >> op) & 1; }  // M I S = X
+GCB_HD int ref_consum(int op) { return (0x18D >> op) & 1; }    // M D N = X
 constexpr int OP_MATCH = 0, OP_INS = 1, OP_SOFT_CLIP = 4, OP_HARD_CLIP = 5;
 
 // BamUtil::getRefOffset, bamutil.cpp:293-314
-__device__ __forceinline__ int get_ref_offset(const uint32_t *__restrict__ cig, int n, int bampos) {
+GCB_HD int get_ref_offset(const uint32_t *cig, int n, int bampos) {
     int ref = 0, query = 0;
     for (int i = 0; i < n; i++) {
-        uint32_t v = __ldg(cig + i);
+        uint32_t v = cig[i];
         int op = cig_op(v), len = cig_len(v);
         query += len * query_consum(op);
         ref += len * ref_consum(op);
@@ -74,10 +78,10 @@ __device__ __forceinline__ int get_ref_offset(const uint32_t *__restrict__ cig, 
 }
 
 // BamUtil::getMOffsetAndLen, bamutil.cpp:316-336
-__device__ __forceinline__ void get_m_offset_and_len(const uint32_t *__restrict__ cig, int n, int &off, int &len) {
+GCB_HD void get_m_offset_and_len(const uint32_t *cig, int n, int &off, int &len) {
     int query = 0;
     for (int i = 0; i < n; i++) {
-        uint32_t v = __ldg(cig + i);
+        uint32_t v = cig[i];
         int op = cig_op(v);
         if (op == OP_MATCH) { off = query; len = cig_len(v); return; }
         query += cig_len(v) * query_consum(op);
@@ -87,28 +91,24 @@ __device__ __forceinline__ void get_m_offset_and_len(const uint32_t *__restrict_
 }
 
 // bam_cigar2rlen (used by BamUtil::getRightRefPos, bamutil.cpp:379-383)
-__device__ __forceinline__ int cigar_ref_len(const uint32_t *__restrict__ cig, int n) {
+GCB_HD int cigar_ref_len(const uint32_t *cig, int n) {
     int l = 0;
-    for (int i = 0; i < n; i++) {
-        uint32_t v = __ldg(cig + i);
-        l += cig_len(v) * ref_consum(cig_op(v));
-    }
+    for (int i = 0; i < n; i++) l += cig_len(cig[i]) * ref_consum(cig_op(cig[i]));
     return l;
 }
 
 // BamUtil::isPartOf, bamutil.cpp:204-255
-__device__ __forceinline__ bool is_part_of(const uint32_t *__restrict__ cp, int np, const uint32_t *__restrict__ cw, int nw,
-                                           bool is_left) {
+GCB_HD bool is_part_of(const uint32_t *cp, int np, const uint32_t *cw, int nw, bool is_left) {
     if (nw < np) return false;
     for (int i = 0; i < np; i++) {
-        uint32_t vp = __ldg(is_left ? cp + i : cp + (np - i - 1));
-        uint32_t vw = __ldg(is_left ? cw + i : cw + (nw - i - 1));
+        uint32_t vp = is_left ? cp[i] : cp[np - i - 1];
+        uint32_t vw = is_left ? cw[i] : cw[nw - i - 1];
         if (cig_op(vp) != cig_op(vw)) return false;
         if (cig_len(vp) > cig_len(vw)) return false;
         if (cig_len(vp) < cig_len(vw)) {
             if (i != np - 1) {
                 if (i != np - 2) return false;
-                uint32_t vn = __ldg(is_left ? cp + i + 1 : cp + (np - i - 2));
+                uint32_t vn = is_left ? cp[i + 1] : cp[np - i - 2];
                 if (cig_op(vn) != OP_HARD_CLIP) return false;
             }
         }
@@ -116,67 +116,138 @@ __device__ __forceinline__ bool is_part_of(const uint32_t *__restrict__ cp, int 
     return true;
 }
 
+// BamUtil::getCigar string equality (bamutil.cpp:191-202): op CHARACTER + length; bam_cigar_opchr maps
+// every op code >= 10 to '?', so those compare equal
+GCB_HD bool same_cigar_string(const uint32_t *a, int na, const uint32_t *b, int nb) {
+    if (na != nb) return false;
+    for (int k = 0; k < na; k++) {
+        int oa = cig_op(a[k]), ob = cig_op(b[k]);
+        if (oa >= 10) oa = 10;
+        if (ob >= 10) ob = 10;
+        if (oa != ob || cig_len(a[k]) != cig_len(b[k])) return false;
+    }
+    return true;
+}
+
 // ---- UMI code helpers (see the header's encoding conventions) -------------------------------
 // number of differing 4-bit fields == Cluster::umiDiff (cluster.cpp:41-53)
-__device__ __forceinline__ int umi_diff_word(uint64_t a, uint64_t b) {
+GCB_HD int nibble_diff64(uint64_t a, uint64_t b) {
     uint64_t x = a ^ b;
     x |= x >> 1;
     x |= x >> 2;
-    return __popcll(x & 0x1111111111111111ull);
+    x &= 0x1111111111111111ull;
+#ifdef __CUDA_ARCH__
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
 }
 
-template <int W>
 struct Umi {
-    uint64_t w[W];
-    __device__ __forceinline__ void load(const uint64_t *__restrict__ p) {
-#pragma unroll
-        for (int k = 0; k < W; k++) w[k] = __ldg(p + k);
-    }
-    __device__ __forceinline__ int diff(const Umi &o) const {
-        int d = 0;
-#pragma unroll
-        for (int k = 0; k < W; k++) d += umi_diff_word(w[k], o.w[k]);
-        return d;
-    }
-    __device__ __forceinline__ bool equal(const Umi &o) const {
-        bool e = true;
-#pragma unroll
-        for (int k = 0; k < W; k++) e &= (w[k] == o.w[k]);
-        return e;
-    }
-    // std::string operator< on the decoded UMIs
-    __device__ __forceinline__ bool less(const Umi &o) const {
-#pragma unroll
-        for (int k = 0; k < W; k++) {
-            if (w[k] != o.w[k]) return w[k] < o.w[k];
-        }
-        return false;
-    }
-    __device__ __forceinline__ bool empty() const { return (w[0] >> 60) == 0; }
+    uint64_t w[GCB_MAX_UMI_WORDS];
 };
+GCB_HD Umi umi_load(const uint64_t *p, int nw) {
+    Umi u;
+#pragma unroll
+    for (int k = 0; k < GCB_MAX_UMI_WORDS; k++) u.w[k] = k < nw ? p[k] : 0ull;
+    return u;
+}
+GCB_HD int umi_diff(const Umi &a, const Umi &b) {
+    int d = 0;
+#pragma unroll
+    for (int k = 0; k < GCB_MAX_UMI_WORDS; k++) d += nibble_diff64(a.w[k], b.w[k]);
+    return d;
+}
+GCB_HD bool umi_equal(const Umi &a, const Umi &b) {
+    bool e = true;
+#pragma unroll
+    for (int k = 0; k < GCB_MAX_UMI_WORDS; k++) e = e && (a.w[k] == b.w[k]);
+    return e;
+}
+// std::string operator< on the decoded UMIs (MSB-first fields: plain unsigned word order)
+GCB_HD bool umi_less(const Umi &a, const Umi &b) {
+#pragma unroll
+    for (int k = 0; k < GCB_MAX_UMI_WORDS; k++)
+        if (a.w[k] != b.w[k]) return a.w[k] < b.w[k];
+    return false;
+}
+GCB_HD int umi_field(const Umi &u, int k) { return (int)((u.w[k >> 4] >> (60 - 4 * (k & 15))) & 0xF); }
+constexpr int UMI_UNDERSCORE = 5;
 
-// nibble k (0 = first character) of a UMI code held in global memory
-__device__ __forceinline__ int umi_field(const uint64_t *__restrict__ u, int k) {
-    return (int)((__ldg(u + (k >> 4)) >> (60 - 4 * (k & 15))) & 0xF);
+// Cluster::isDuplex (cluster.cpp:246-258) on the 4-bit code.  util.h:59-88 split(): leading '_' are
+// skipped, then every '_' ends a part and the text after the last '_' is always a part (possibly
+// empty); both UMIs must have exactly two parts, swapped.
+struct UmiParts { int n, b0, e0, b1, e1; };
+GCB_HD UmiParts umi_split(const Umi &u) {
+    UmiParts p = {0, 0, 0, 0, 0};
+    int len = 0;
+    while (len < 16 * GCB_MAX_UMI_WORDS && umi_field(u, len) != 0) len++;
+    if (len == 0) return p;
+    int pos = 0;
+    while (pos < len && umi_field(u, pos) == UMI_UNDERSCORE) pos++;
+    if (pos >= len) return p;
+    for (;;) {
+        int sep = -1;
+        for (int k = pos; k < len; k++)
+            if (umi_field(u, k) == UMI_UNDERSCORE) { sep = k; break; }
+        int end = sep >= 0 ? sep : len;
+        if (p.n == 0) { p.b0 = pos; p.e0 = end; }
+        else if (p.n == 1) { p.b1 = pos; p.e1 = end; }
+        p.n++;
+        if (sep < 0) break;
+        pos = sep + 1;
+    }
+    return p;
+}
+GCB_HD bool umi_is_duplex(const Umi &a, const Umi &b) {
+    UmiParts pa = umi_split(a), pb = umi_split(b);
+    if (pa.n != 2 || pb.n != 2) return false;
+    int a0 = pa.e0 - pa.b0, a1 = pa.e1 - pa.b1, c0 = pb.e0 - pb.b0, c1 = pb.e1 - pb.b1;
+    if (a0 != c1 || a1 != c0) return false;
+    for (int k = 0; k < a0; k++)
+        if (umi_field(a, pa.b0 + k) != umi_field(b, pb.b1 + k)) return false;
+    for (int k = 0; k < a1; k++)
+        if (umi_field(a, pa.b1 + k) != umi_field(b, pb.b0 + k)) return false;
+    return true;
 }
 
 // ---- sequence helpers ------------------------------------------------------------------------
-__device__ __forceinline__ int base_at(const uint8_t *seq, int i) {  // bam_get_seq nibble order
+GCB_HD int base_at(const uint8_t *seq, int i) {  // bam_get_seq nibble order
     uint8_t b = seq[i >> 1];
     return (i & 1) ? (b & 0xF) : (b >> 4);
 }
+// BamUtil::fourbits2base (bamutil.cpp:149-165) as a class id: A C G T keep their code, the rest are 'N'
+GCB_HD int base_letter(int code) { return (code == 1 || code == 2 || code == 4 || code == 8) ? code : 15; }
 
-// Pair::qual2score, pair.cpp:77-86
-__device__ __forceinline__ int qual2score(const gcb_options &o, int q) {
-    if (o.high_quality <= q) return o.score_high;
-    if (o.moderate_quality <= q) return o.score_moderate;
-    if (o.low_quality <= q) return o.score_low;
-    return o.score_bad;
+GCB_HD int sc8(int v) { return (int)(signed char)v; }  // the reference keeps scores in `char`
+
+// Pair::qual2score, pair.cpp:77-86 (returns `char`)
+GCB_HD int qual2score(const gcb_options &o, int q) {
+    if (o.high_quality <= q) return sc8(o.score_high);
+    if (o.moderate_quality <= q) return sc8(o.score_moderate);
+    if (o.low_quality <= q) return sc8(o.score_low);
+    return sc8(o.score_bad);
 }
 
 // record size of a read of l bases in a payload
-__device__ __forceinline__ int64_t record_bytes(int l) { return GCB_ALIGN4(l) + GCB_ALIGN4((l + 1) >> 1); }
+GCB_HD int64_t record_bytes(int l) { return (int64_t)GCB_ALIGN4(l) + GCB_ALIGN4((l + 1) >> 1); }
 
+#ifndef GCB_SIMT_CHECK
 __device__ __forceinline__ void raise_error(int32_t *flag, int code) { atomicCAS(flag, 0, code); }
+#else
+inline void raise_error(int32_t *flag, int code) { if (*flag == 0) *flag = code; }
+#endif
+
+// ---- warp helpers ---------------------------------------------------------------------------------
+GCB_DEV int lane_id() { return (int)(threadIdx.x & 31); }
+GCB_DEV int warp_sum(int v) { return __reduce_add_sync(FULL, v); }
+GCB_DEV int warp_min(int v) { return __reduce_min_sync(FULL, v); }
+GCB_DEV int warp_max(int v) { return __reduce_max_sync(FULL, v); }
+GCB_DEV Umi umi_shfl(const Umi &u, int src) {
+    Umi r;
+#pragma unroll
+    for (int k = 0; k < GCB_MAX_UMI_WORDS; k++) r.w[k] = __shfl_sync(FULL, u.w[k], src);
+    return r;
+}
 
 }  // namespace gcb

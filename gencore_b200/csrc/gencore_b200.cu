@@ -1,0 +1,333 @@
+// gencore_b200.cu — the C ABI of libgencore_b200.so (include/gencore_b200.h) and the launch sequence
+// of one batch.  Host code only sizes buffers, moves bytes and launches; all arithmetic of the
+// reference's hot path lives in the kernels:
+//   umi_group_kernel -> select_template_kernel -> scan_local/scan_blocks -> score_vote_kernel -> duplex_kernel
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "k_duplex.cuh"
+#include "k_group_select.cuh"
+#include "k_score_vote.cuh"
+
+using namespace gcb;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct gcb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    gcb_options opt;
+    char err[256] = {0};
+    int64_t launches = 0;
+    // genome
+    GenomeView genome = {nullptr, nullptr, nullptr, 0};
+    DevBuf g_packed, g_off, g_len;
+    // workspace (grow-only)
+    DevBuf w_members, w_group_off, w_scratch, w_rrp, w_flags, w_mode, w_hasumi, w_overlap, w_slab, w_cob, w_coo, w_scan, w_err, w_tiles;
+    // device mirror of a host batch / result (gcb_consensus_batch)
+    DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
+    DevBuf d_pair_group, d_ngroups, d_groups, d_out, d_out_bytes;
+};
+
+namespace {
+
+int fail(gcb_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
+    if (ctx) {
+        if (e != cudaSuccess) snprintf(ctx->err, sizeof ctx->err, "%s: %s", what, cudaGetErrorString(e));
+        else snprintf(ctx->err, sizeof ctx->err, "%s", what);
+    }
+    return code;
+}
+
+#define GCB_CUDA(ctx, call)                                              \
+    do {                                                                 \
+        cudaError_t e_ = (call);                                         \
+        if (e_ != cudaSuccess) return fail((ctx), GCB_ERR_CUDA, #call, e_); \
+    } while (0)
+
+int reserve(gcb_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return GCB_OK;
+    if (b.p) GCB_CUDA(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    GCB_CUDA(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return GCB_OK;
+}
+
+void release(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t n_tiles, Workspace &ws, int32_t *&tile_first) {
+    int rc;
+    const int64_t n_scan = (n_clusters + SCAN_BLOCK - 1) / SCAN_BLOCK;
+#define GCB_RES(buf, bytes) if ((rc = reserve(ctx, ctx->buf, (size_t)(bytes))) != GCB_OK) return rc
+    GCB_RES(w_members, n_pairs * 4);
+    GCB_RES(w_group_off, n_pairs * 4);
+    GCB_RES(w_scratch, n_pairs * 8);
+    GCB_RES(w_rrp, n_pairs * 8);
+    GCB_RES(w_flags, n_pairs * 2);
+    GCB_RES(w_mode, n_pairs * 2);
+    GCB_RES(w_hasumi, n_clusters);
+    GCB_RES(w_overlap, n_pairs * sizeof(PairOverlap));
+    GCB_RES(w_slab, (n_clusters + 1) * 8);
+    GCB_RES(w_cob, n_clusters * 8);
+    GCB_RES(w_coo, n_clusters * 8);
+    GCB_RES(w_scan, (n_scan + 1) * 8);
+    GCB_RES(w_err, 4);
+    GCB_RES(w_tiles, (n_tiles + 1) * 4);
+#undef GCB_RES
+    ws.members = (int32_t *)ctx->w_members.p;
+    ws.group_off = (int32_t *)ctx->w_group_off.p;
+    ws.scratch = (int32_t *)ctx->w_scratch.p;
+    ws.right_ref_pos = (int32_t *)ctx->w_rrp.p;
+    ws.vote_flags = (uint8_t *)ctx->w_flags.p;
+    ws.side_mode = (uint8_t *)ctx->w_mode.p;
+    ws.cluster_has_umi = (uint8_t *)ctx->w_hasumi.p;
+    ws.overlap = (PairOverlap *)ctx->w_overlap.p;
+    ws.slab_off = (int64_t *)ctx->w_slab.p;
+    ws.cluster_out_bytes = (int64_t *)ctx->w_cob.p;
+    ws.cluster_out_off = (int64_t *)ctx->w_coo.p;
+    ws.scan_block = (int64_t *)ctx->w_scan.p;
+    ws.error_flag = (int32_t *)ctx->w_err.p;
+    tile_first = (int32_t *)ctx->w_tiles.p;
+    return GCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gcb_abi_version(void) { return GCB_ABI_VERSION; }
+
+void gcb_default_options(gcb_options *o) {  // Options::Options, options.cpp:4-40
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->duplex_mismatch_threshold = 2;
+    o->cluster_size_req = 1;
+    o->base_score_req = 6;
+    o->high_quality = 30;
+    o->moderate_quality = 20;
+    o->low_quality = 15;
+    o->score_high = 8;
+    o->score_moderate = 6;
+    o->score_low = 4;
+    o->score_bad = 2;
+    o->skip_low_complexity_cluster_threshold = 1000;
+    o->score_percent_req = 0.8;
+}
+
+int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
+    if (!out) return GCB_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return GCB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GCB_ERR_NO_DEVICE;
+    if (prop.major != 10) return GCB_ERR_NO_DEVICE;  // the kernels exist for sm_100a only; there is no other path
+    gcb_ctx *ctx = new (std::nothrow) gcb_ctx();
+    if (!ctx) return GCB_ERR_ARG;
+    ctx->device = device;
+    if (opt) ctx->opt = *opt;
+    else gcb_default_options(&ctx->opt);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return GCB_ERR_CUDA;
+    }
+    if (cudaFuncSetAttribute(score_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return GCB_ERR_CUDA;
+    }
+    *out = ctx;
+    return GCB_OK;
+}
+
+void gcb_destroy(gcb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
+                     &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
+                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
+                     &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
+                     &ctx->d_out, &ctx->d_out_bytes};
+    for (DevBuf *b : all) release(*b);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *gcb_last_error(const gcb_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+int gcb_set_reference_device(gcb_ctx *ctx, const uint8_t *packed4_dev, int64_t packed_bytes, const int64_t *contig_off,
+                             const int64_t *contig_len, int32_t n_contigs) {
+    if (!ctx || n_contigs < 0 || (n_contigs > 0 && (!packed4_dev || !contig_off || !contig_len)) || packed_bytes < 0)
+        return fail(ctx, GCB_ERR_ARG, "gcb_set_reference_device: bad argument");
+    GCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->genome = {nullptr, nullptr, nullptr, 0};
+    if (n_contigs == 0) return GCB_OK;
+    int rc;
+    if ((rc = reserve(ctx, ctx->g_off, (size_t)n_contigs * 8)) != GCB_OK) return rc;
+    if ((rc = reserve(ctx, ctx->g_len, (size_t)n_contigs * 8)) != GCB_OK) return rc;
+    GCB_CUDA(ctx, cudaMemcpyAsync(ctx->g_off.p, contig_off, (size_t)n_contigs * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GCB_CUDA(ctx, cudaMemcpyAsync(ctx->g_len.p, contig_len, (size_t)n_contigs * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->genome.packed4 = packed4_dev;
+    ctx->genome.contig_off = (const int64_t *)ctx->g_off.p;
+    ctx->genome.contig_len = (const int64_t *)ctx->g_len.p;
+    ctx->genome.n_contigs = n_contigs;
+    return GCB_OK;
+}
+
+int gcb_set_reference(gcb_ctx *ctx, const uint8_t *packed4, int64_t packed_bytes, const int64_t *contig_off, const int64_t *contig_len,
+                      int32_t n_contigs) {
+    if (!ctx || n_contigs < 0 || (n_contigs > 0 && !packed4) || packed_bytes < 0)
+        return fail(ctx, GCB_ERR_ARG, "gcb_set_reference: bad argument");
+    GCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_contigs == 0) {
+        ctx->genome = {nullptr, nullptr, nullptr, 0};
+        return GCB_OK;
+    }
+    int rc;
+    if ((rc = reserve(ctx, ctx->g_packed, (size_t)packed_bytes)) != GCB_OK) return rc;
+    GCB_CUDA(ctx, cudaMemcpyAsync(ctx->g_packed.p, packed4, (size_t)packed_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return gcb_set_reference_device(ctx, (const uint8_t *)ctx->g_packed.p, packed_bytes, contig_off, contig_len, n_contigs);
+}
+
+int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result *result, uint32_t stages, void *stream_) {
+    if (!ctx || !batch || !result) return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch_device: null argument");
+    if (batch->n_clusters < 0 || batch->n_pairs < 0 || batch->umi_words < 1 || batch->umi_words > GCB_MAX_UMI_WORDS ||
+        batch->payload_bytes < 0 || (batch->payload_bytes & 15) || ((uintptr_t)batch->payload & 15) || ((uintptr_t)result->out_payload & 3))
+        return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch_device: bad sizes or alignment (payload 16 B, payload_bytes % 16, out_payload 4 B)");
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+    GCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n_tiles = (batch->payload_bytes + TILE_WINDOW - 1) / TILE_WINDOW;
+    Workspace ws;
+    int32_t *tile_first = nullptr;
+    int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, ws, tile_first);
+    if (rc != GCB_OK) return rc;
+    BatchView b = {batch->n_clusters, batch->n_pairs, batch->umi_words, batch->cluster_pair_off, batch->cluster_ref, batch->cluster_flags,
+                   batch->umi, batch->reads, batch->cigar, batch->payload, batch->payload_bytes};
+    ResultView r = {result->pair_group, result->cluster_n_groups, result->groups, result->out_payload, result->out_capacity, result->out_bytes};
+    if (batch->n_clusters == 0) {
+        if (stages & GCB_STAGE_SELECT_TEMPLATE) GCB_CUDA(ctx, cudaMemsetAsync(result->out_bytes, 0, 8, stream));
+        GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, stream));
+        return GCB_OK;
+    }
+    const int warps_per_cta = GROUP_THREADS / WARP;
+    const unsigned grid_clusters = (unsigned)((batch->n_clusters + warps_per_cta - 1) / warps_per_cta);
+    if (stages & GCB_STAGE_UMI_GROUP) {
+        GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, stream));
+        GCB_LAUNCH(umi_group_kernel, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, (int32_t)TILE_WINDOW, tile_first,
+                   (int32_t)n_tiles);
+        ctx->launches++;
+    }
+    if (stages & GCB_STAGE_SELECT_TEMPLATE) {
+        const int32_t n_scan = (int32_t)((batch->n_clusters + SCAN_BLOCK - 1) / SCAN_BLOCK);
+        GCB_CUDA(ctx, cudaMemsetAsync(result->groups, 0, sizeof(gcb_group_result) * (size_t)batch->n_pairs, stream));
+        GCB_LAUNCH(select_template_kernel, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->opt);
+        GCB_LAUNCH(scan_local_kernel, dim3((unsigned)n_scan), dim3(SCAN_THREADS), 0, stream, ws, batch->n_clusters);
+        GCB_LAUNCH(scan_blocks_kernel, dim3(1), dim3(WARP), 0, stream, ws, n_scan, result->out_bytes, result->out_capacity);
+        ctx->launches += 3;
+    }
+    if ((stages & GCB_STAGE_SCORE_VOTE) && n_tiles > 0) {
+        GCB_LAUNCH(score_vote_kernel, dim3((unsigned)n_tiles), dim3(VOTE_THREADS), VOTE_SMEM, stream, b, r, ws, ctx->genome, ctx->opt,
+                   (const int32_t *)tile_first);
+        ctx->launches++;
+    }
+    if (stages & GCB_STAGE_DUPLEX) {
+        GCB_LAUNCH(duplex_kernel, dim3((unsigned)((batch->n_clusters + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream,
+                   b, r, ws, ctx->opt);
+        ctx->launches++;
+    }
+    GCB_CUDA(ctx, cudaGetLastError());
+    return GCB_OK;
+}
+
+int gcb_batch_status(gcb_ctx *ctx, void *stream_) {
+    if (!ctx) return GCB_ERR_ARG;
+    if (!ctx->w_err.p) return GCB_OK;
+    cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+    int32_t flag = 0;
+    GCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GCB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->w_err.p, 4, cudaMemcpyDeviceToHost, stream));
+    GCB_CUDA(ctx, cudaStreamSynchronize(stream));
+    if (flag != GCB_OK) fail(ctx, flag, flag == GCB_ERR_CAPACITY ? "out_payload too small" : "malformed batch");
+    return flag;
+}
+
+int gcb_consensus_batch(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *hr) {
+    if (!ctx || !hb || !hr) return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch: null argument");
+    if (hb->n_clusters < 0 || hb->n_pairs < 0 || hb->payload_bytes < 0 || hb->n_cigar_ops < 0 || hr->out_capacity < 0)
+        return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch: negative size");
+    GCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t nc = (size_t)hb->n_clusters, np = (size_t)hb->n_pairs;
+    int rc;
+#define GCB_UP(buf, src, bytes)                                                                         \
+    if ((rc = reserve(ctx, ctx->buf, (bytes))) != GCB_OK) return rc;                                    \
+    if ((bytes) > 0) GCB_CUDA(ctx, cudaMemcpyAsync(ctx->buf.p, (src), (bytes), cudaMemcpyHostToDevice, st))
+    GCB_UP(d_pair_off, hb->cluster_pair_off, (nc + 1) * 4);
+    GCB_UP(d_cref, hb->cluster_ref, nc * 4);
+    GCB_UP(d_cflags, hb->cluster_flags, nc);
+    GCB_UP(d_umi, hb->umi, np * (size_t)hb->umi_words * 8);
+    GCB_UP(d_reads, hb->reads, 2 * np * sizeof(gcb_read_desc));
+    GCB_UP(d_cigar, hb->cigar, (size_t)hb->n_cigar_ops * 4);
+    GCB_UP(d_payload, hb->payload, (size_t)hb->payload_bytes);
+#undef GCB_UP
+    if ((rc = reserve(ctx, ctx->d_pair_group, np * 4)) != GCB_OK) return rc;
+    if ((rc = reserve(ctx, ctx->d_ngroups, nc * 4)) != GCB_OK) return rc;
+    if ((rc = reserve(ctx, ctx->d_groups, np * sizeof(gcb_group_result))) != GCB_OK) return rc;
+    if ((rc = reserve(ctx, ctx->d_out, (size_t)hr->out_capacity)) != GCB_OK) return rc;
+    if ((rc = reserve(ctx, ctx->d_out_bytes, 8)) != GCB_OK) return rc;
+    gcb_batch db = *hb;
+    db.cluster_pair_off = (const int32_t *)ctx->d_pair_off.p;
+    db.cluster_ref = (const int32_t *)ctx->d_cref.p;
+    db.cluster_flags = (const uint8_t *)ctx->d_cflags.p;
+    db.umi = (const uint64_t *)ctx->d_umi.p;
+    db.reads = (const gcb_read_desc *)ctx->d_reads.p;
+    db.cigar = (const uint32_t *)ctx->d_cigar.p;
+    db.payload = (const uint8_t *)ctx->d_payload.p;
+    gcb_result dr;
+    dr.pair_group = (int32_t *)ctx->d_pair_group.p;
+    dr.cluster_n_groups = (int32_t *)ctx->d_ngroups.p;
+    dr.groups = (gcb_group_result *)ctx->d_groups.p;
+    dr.out_payload = (uint8_t *)ctx->d_out.p;
+    dr.out_capacity = hr->out_capacity;
+    dr.out_bytes = (int64_t *)ctx->d_out_bytes.p;
+    if ((rc = gcb_consensus_batch_device(ctx, &db, &dr, GCB_STAGE_ALL, st)) != GCB_OK) return rc;
+    if (np > 0) {
+        GCB_CUDA(ctx, cudaMemcpyAsync(hr->pair_group, dr.pair_group, np * 4, cudaMemcpyDeviceToHost, st));
+        GCB_CUDA(ctx, cudaMemcpyAsync(hr->groups, dr.groups, np * sizeof(gcb_group_result), cudaMemcpyDeviceToHost, st));
+    }
+    if (nc > 0) GCB_CUDA(ctx, cudaMemcpyAsync(hr->cluster_n_groups, dr.cluster_n_groups, nc * 4, cudaMemcpyDeviceToHost, st));
+    GCB_CUDA(ctx, cudaMemcpyAsync(hr->out_bytes, dr.out_bytes, 8, cudaMemcpyDeviceToHost, st));
+    int32_t flag = 0;
+    GCB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->w_err.p, 4, cudaMemcpyDeviceToHost, st));
+    GCB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (flag != GCB_OK) return fail(ctx, flag, flag == GCB_ERR_CAPACITY ? "out_payload too small" : "malformed batch");
+    const int64_t used = *hr->out_bytes;
+    if (used > 0) {
+        GCB_CUDA(ctx, cudaMemcpyAsync(hr->out_payload, dr.out_payload, (size_t)used, cudaMemcpyDeviceToHost, st));
+        GCB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return GCB_OK;
+}
+
+int64_t gcb_launch_count(const gcb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// k_duplex.cuh — the tail of Cluster::clusterByUMI (cluster.cpp:102-188): duplex partner search,
+// Cluster::duplexMerge / duplexMergeBam (cluster.cpp:190-244) on the consensus records the vote
+// kernel wrote, and the SSCS / DCS / dropped verdict of every family.  One thread per cluster: the
+// partner search is a sequential stack walk in the reference and its order decides who pairs up.
+#pragma once
+
+#include "k_group_select.cuh"
+
+namespace gcb {
+
+constexpr int DUPLEX_THREADS = 128;
+
+// cluster.cpp:200-244 on two consensus records in out_payload.  The byte-equality shortcut advances
+// i by two from either parity, so after a handled mismatch the walk can stay on odd indices and skip
+// the high nibbles of the following differing bytes; reproduced literally.
+GCB_DEV int duplex_merge_records(uint8_t *rec1, int len1, uint8_t *rec2, int len2) {
+    int diff = len1 > len2 ? len1 - len2 : len2 - len1;
+    const int len = min(len1, len2);
+    uint8_t *qual1 = rec1, *qual2 = rec2;
+    uint8_t *seq1 = rec1 + GCB_ALIGN4(len1), *seq2 = rec2 + GCB_ALIGN4(len2);
+    for (int i = 0; i < len; i++) {
+        const uint8_t a = seq1[i >> 1], c = seq2[i >> 1];
+        if (a == c) {
+            i++;
+            continue;
+        }
+        const int b1 = (i & 1) ? (a & 0xF) : (a >> 4), b2 = (i & 1) ? (c & 0xF) : (c >> 4);
+        if (base_letter(b1) != base_letter(b2)) {
+            diff++;
+            qual1[i] = 0;
+            qual2[i] = 0;
+            if (i & 1) {
+                seq1[i >> 1] = (uint8_t)(a | 0x0F);
+                seq2[i >> 1] = (uint8_t)(c | 0x0F);
+            } else {
+                seq1[i >> 1] = (uint8_t)(a | 0xF0);
+                seq2[i >> 1] = (uint8_t)(c | 0xF0);
+            }
+        }
+    }
+    return diff;
+}
+
+__global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o) {
+    const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= b.n_clusters) return;
+    const int p0 = b.cluster_pair_off[c];
+    const int G = r.cluster_n_groups[c];
+    const int nw = b.umi_words;
+    gcb_group_result *gr = r.groups + p0;
+
+    if (!(ws.cluster_has_umi[c] && !o.disable_duplex)) {  // cluster.cpp:169-183
+        for (int g = 0; g < G; g++)
+            gr[g].status = (!o.duplex_only && gr[g].merge_reads >= o.cluster_size_req) ? GCB_GROUP_SSCS : GCB_GROUP_DROPPED;
+        return;
+    }
+    // cluster.cpp:119-168: pop from the back, pair with the first family (in creation order) whose UMI is the swap
+    int32_t *alive = ws.scratch + 2 * (int64_t)p0;  // G <= pairs of the cluster
+    int nalive = G;
+    for (int g = 0; g < G; g++) alive[g] = g;
+    while (nalive > 0) {
+        const int g1 = alive[--nalive];
+        gcb_group_result *r1 = gr + g1;
+        const Umi u1 = r1->umi_pair >= 0 ? umi_load(b.umi + (int64_t)r1->umi_pair * nw, nw) : umi_load(b.umi, 0);
+        bool found = false;
+        for (int i = 0; i < nalive; i++) {
+            const int g2 = alive[i];
+            gcb_group_result *r2 = gr + g2;
+            const Umi u2 = r2->umi_pair >= 0 ? umi_load(b.umi + (int64_t)r2->umi_pair * nw, nw) : umi_load(b.umi, 0);
+            if (!umi_is_duplex(u1, u2)) continue;
+            found = true;
+            int diff = 0;  // Cluster::duplexMerge, cluster.cpp:190-198
+            for (int s = 0; s < 2; s++) {
+                const int t1 = r1->tmpl_read[s], t2 = r2->tmpl_read[s];
+                if (t1 < 0 || t2 < 0) continue;
+                const int l1 = b.reads[t1].l_qseq, l2 = b.reads[t2].l_qseq;
+                if (r1->out_off[s] + record_bytes(l1) > r.out_capacity || r2->out_off[s] + record_bytes(l2) > r.out_capacity) continue;
+                diff += duplex_merge_records(r.out_payload + r1->out_off[s], l1, r.out_payload + r2->out_off[s], l2);
+            }
+            r1->duplex_partner = g2;
+            r1->duplex_diff = diff;
+            r2->duplex_partner = g1;
+            r2->duplex_diff = diff;
+            r2->status = GCB_GROUP_DUPLEX_PARTNER;
+            if (diff <= o.duplex_mismatch_threshold) {
+                if (r1->merge_reads + r2->merge_reads >= o.cluster_size_req) {
+                    r1->status = GCB_GROUP_DCS;
+                    r1->reverse_merge_reads = r2->merge_reads;  // Pair::setDuplex
+                } else {
+                    r1->status = GCB_GROUP_DUPLEX_SMALL;
+                }
+            } else {
+                r1->status = GCB_GROUP_DUPLEX_DIFF;
+            }
+            for (int k = i; k + 1 < nalive; k++) alive[k] = alive[k + 1];
+            nalive--;
+            break;
+        }
+        if (!found) r1->status = (!o.duplex_only && r1->merge_reads >= o.cluster_size_req) ? GCB_GROUP_SSCS : GCB_GROUP_DROPPED;
+    }
+}
+
+}  // namespace gcb

@@ -1,0 +1,406 @@
+// k_group_select.cuh — the two descriptor-only kernels that run before the vote:
+//   umi_group_kernel        Cluster::clusterByUMI's grouping loop        cluster.cpp:55-100
+//   select_template_kernel  Group::consensusMerge / consensusMergeBam    group.cpp:68-318 (everything but makeConsensus)
+// Both give one warp to one cluster; they read UMIs, read descriptors and CIGARs only (the payload
+// is touched only by the >1000-pair low-complexity probe).
+#pragma once
+
+#include "device_common.cuh"
+
+namespace gcb {
+
+struct BatchView {  // gcb_batch with device pointers
+    int32_t n_clusters, n_pairs, umi_words;
+    const int32_t *cluster_pair_off;
+    const int32_t *cluster_ref;
+    const uint8_t *cluster_flags;
+    const uint64_t *umi;
+    const gcb_read_desc *reads;
+    const uint32_t *cigar;
+    const uint8_t *payload;
+    int64_t payload_bytes;
+};
+
+struct ResultView {  // gcb_result with device pointers
+    int32_t *pair_group;
+    int32_t *cluster_n_groups;
+    gcb_group_result *groups;
+    uint8_t *out_payload;
+    int64_t out_capacity;
+    int64_t *out_bytes;
+};
+
+constexpr int GROUP_THREADS = 128;  // 4 clusters per CTA
+
+// ------------------------------------------------------------------------------------------------
+// cluster.cpp:55-100.  umiCount (a map<string,int>) becomes a per-pair multiplicity; each round takes
+// the lexicographically first UMI of maximal count among the pairs still unassigned and absorbs every
+// unassigned pair within `thr` of it, in map (= pair) order.  Counts never need decrementing: pairs
+// carrying the same UMI are always absorbed together.
+__global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, ResultView r, Workspace ws, int32_t tile_window,
+                                                                   int32_t *tile_first, int32_t n_tiles) {
+    const int lane = lane_id();
+    const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    if (c >= b.n_clusters) return;
+    const int p0 = b.cluster_pair_off[c], p1 = b.cluster_pair_off[c + 1], n = p1 - p0;
+    const int nw = b.umi_words;
+    const int thr = b.cluster_flags[c] >> GCB_CLUSTER_UMI_THR_SHIFT;
+
+    if (lane == 0) {
+        // slab bounds of this cluster and the vote kernel's tile directory: tile t owns the clusters
+        // whose slab starts inside [t*window, (t+1)*window)
+        const int64_t s = p0 < b.n_pairs ? b.reads[2 * (int64_t)p0].data_off : b.payload_bytes;
+        ws.slab_off[c] = s;
+        int64_t t_lo = 0;
+        if (c > 0) {
+            const int pp = b.cluster_pair_off[c - 1];
+            const int64_t prev = pp < b.n_pairs ? b.reads[2 * (int64_t)pp].data_off : b.payload_bytes;
+            t_lo = prev / tile_window + 1;
+        }
+        for (int64_t t = t_lo; t <= s / tile_window && t <= n_tiles; t++) tile_first[t] = c;
+        if (c == b.n_clusters - 1) {
+            ws.slab_off[c + 1] = b.payload_bytes;
+            for (int64_t t = s / tile_window + 1; t <= n_tiles; t++) tile_first[t] = b.n_clusters;
+        }
+    }
+
+    // multiplicity of every pair's UMI inside the cluster (cluster.cpp:57-65)
+    bool has = false;
+    for (int i = lane; i < n; i += WARP) {
+        const Umi u = umi_load(b.umi + (int64_t)(p0 + i) * nw, nw);
+        has |= (u.w[0] >> 60) != 0;
+        int cnt = 0;
+        for (int j = 0; j < n; j++) cnt += umi_equal(u, umi_load(b.umi + (int64_t)(p0 + j) * nw, nw)) ? 1 : 0;
+        ws.scratch[2 * (int64_t)(p0 + i)] = cnt;
+        r.pair_group[p0 + i] = -1;
+    }
+    has = __any_sync(FULL, has);
+    if (lane == 0) ws.cluster_has_umi[c] = has ? 1 : 0;
+
+    int filled = 0, g = 0;
+    while (filled < n) {  // cluster.cpp:66-100
+        int best_cnt = -1;
+        Umi best = umi_load(b.umi, 0);
+        for (int i = lane; i < n; i += WARP) {
+            if (r.pair_group[p0 + i] >= 0) continue;
+            const int cnt = ws.scratch[2 * (int64_t)(p0 + i)];
+            const Umi u = umi_load(b.umi + (int64_t)(p0 + i) * nw, nw);
+            if (cnt > best_cnt || (cnt == best_cnt && umi_less(u, best))) { best_cnt = cnt; best = u; }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            const int oc = __shfl_xor_sync(FULL, best_cnt, off);
+            Umi ou;
+#pragma unroll
+            for (int k = 0; k < GCB_MAX_UMI_WORDS; k++) ou.w[k] = __shfl_xor_sync(FULL, best.w[k], off);
+            if (oc > best_cnt || (oc == best_cnt && oc >= 0 && umi_less(ou, best))) { best_cnt = oc; best = ou; }
+        }
+        const int start = filled;
+        for (int base = 0; base < n; base += WARP) {
+            const int i = base + lane;
+            bool absorb = false;
+            if (i < n && r.pair_group[p0 + i] < 0)
+                absorb = umi_diff(umi_load(b.umi + (int64_t)(p0 + i) * nw, nw), best) <= thr;
+            const unsigned m = __ballot_sync(FULL, absorb);
+            if (absorb) {
+                ws.members[p0 + filled + __popc(m & ((1u << lane) - 1u))] = p0 + i;
+                r.pair_group[p0 + i] = g;
+            }
+            filled += __popc(m);
+        }
+        if (lane == 0) ws.group_off[p0 + g] = p0 + start;
+        if (filled == start) {  // cannot happen (the top UMI is within 0 of itself); never spin on bad input
+            if (lane == 0) raise_error(ws.error_flag, GCB_ERR_MALFORMED);
+            break;
+        }
+        g++;
+    }
+    if (lane == 0) r.cluster_n_groups[c] = g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// group.cpp:136-313 for one side of one family: returns the template's read slot (or -1) and fills
+// vote_flags / side_mode for the vote kernel.  Called by a whole warp; the result is warp-uniform.
+GCB_DEV int side_select(const BatchView &b, const Workspace &ws, const gcb_options &o, int mb, int m, int side, int slot) {
+    const int lane = lane_id();
+    const bool isLeft = side == 0;
+    const int thr = o.skip_low_complexity_cluster_threshold;
+#define GCB_SLOT(k) (2 * ws.members[mb + (k)] + side)
+#define GCB_HAVE(k) (b.reads[GCB_SLOT(k)].l_qseq >= 0)
+#define GCB_CIG(s) (b.cigar + b.reads[s].cigar_off)
+
+    if (m > thr) {  // group.cpp:142-175: many distinct CIGARs + a low-complexity first read => skip the side
+        int distinct = 0, first_k = 0x7FFFFFFF;
+        for (int k = lane; k < m; k += WARP) {
+            if (!GCB_HAVE(k)) continue;
+            first_k = min(first_k, k);
+            const int sk = GCB_SLOT(k);
+            bool seen = false;
+            for (int j = 0; j < k && !seen; j++) {
+                if (!GCB_HAVE(j)) continue;
+                const int sj = GCB_SLOT(j);
+                seen = same_cigar_string(GCB_CIG(sj), b.reads[sj].n_cigar, GCB_CIG(sk), b.reads[sk].n_cigar);
+            }
+            if (!seen) distinct++;
+        }
+        distinct = warp_sum(distinct);
+        first_k = warp_min(first_k);
+        if ((double)distinct > m * 0.1 && first_k != 0x7FFFFFFF) {
+            const gcb_read_desc rd = b.reads[GCB_SLOT(first_k)];
+            const uint8_t *seq = b.payload + rd.data_off + GCB_ALIGN4(rd.l_qseq);
+            int dn = 0;
+            for (int i = lane; i < rd.l_qseq - 1; i += WARP)
+                if (base_letter(base_at(seq, i)) != base_letter(base_at(seq, i + 1))) dn++;
+            dn = warp_sum(dn);
+            if ((double)dn < rd.l_qseq * 0.5) return -1;
+        }
+    }
+
+    bool leftReadMode = isLeft;
+    if (!isLeft) {  // group.cpp:177-194: every right read starts at the same position => left-aligned columns
+        int lo = 0x7FFFFFFF, hi = -0x7FFFFFFF;
+        for (int k = lane; k < m; k += WARP) {
+            if (!GCB_HAVE(k)) continue;
+            const int pos = b.reads[GCB_SLOT(k)].pos;
+            lo = min(lo, pos);
+            hi = max(hi, pos);
+        }
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (lo >= hi) leftReadMode = true;  // all equal, or no read at all
+    }
+
+    // group.cpp:196-233: containedBy[i] = 1 + #{j : read i is part of read j}
+    int first_big = 0x7FFFFFFF;
+    for (int k = lane; k < m; k += WARP) {
+        int cnt = 0;
+        if (GCB_HAVE(k)) {
+            cnt = 1;
+            const int si = GCB_SLOT(k);
+            const uint32_t *ci = GCB_CIG(si);
+            const int ni = b.reads[si].n_cigar;
+            const int rrp = ws.right_ref_pos[si];
+            for (int j = 0; j < m; j++) {
+                if (j == k || !GCB_HAVE(j)) continue;
+                const int sj = GCB_SLOT(j);
+                if (!isLeft && rrp != ws.right_ref_pos[sj]) continue;
+                if (is_part_of(ci, ni, GCB_CIG(sj), b.reads[sj].n_cigar, leftReadMode)) cnt++;
+            }
+            if (m > thr && cnt >= m / 2) first_big = min(first_big, k);
+        }
+        ws.scratch[2 * (int64_t)(mb + k) + side] = cnt;
+    }
+    first_big = warp_min(first_big);  // group.cpp:231-232: the scan stops there, later entries stay 0
+
+    // group.cpp:235-261: most contained, ties -> strictly shorter read, else first in map order
+    int best_cnt = -1, best_len = 0, best_k = 0x7FFFFFFF;
+    for (int k = lane; k < m; k += WARP) {
+        const int cnt = k > first_big ? 0 : ws.scratch[2 * (int64_t)(mb + k) + side];
+        const int len = GCB_HAVE(k) ? b.reads[GCB_SLOT(k)].l_qseq : 0;
+        if (cnt > best_cnt || (cnt == best_cnt && len < best_len)) { best_cnt = cnt; best_len = len; best_k = k; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const int oc = __shfl_xor_sync(FULL, best_cnt, off), ol = __shfl_xor_sync(FULL, best_len, off),
+                  ok = __shfl_xor_sync(FULL, best_k, off);
+        if (oc > best_cnt || (oc == best_cnt && (ol < best_len || (ol == best_len && ok < best_k)))) {
+            best_cnt = oc; best_len = ol; best_k = ok;
+        }
+    }
+    if ((double)best_cnt < m * 0.4 && m != 1) return -1;  // group.cpp:264
+    if (!GCB_HAVE(best_k)) return -1;                     // group.cpp:270-285
+    const int out = GCB_SLOT(best_k);
+    const gcb_read_desc od = b.reads[out];
+
+    // group.cpp:287-313 (who votes) and 339-349 (whose length difference is ignored)
+    for (int k = lane; k < m; k += WARP) {
+        if (!GCB_HAVE(k)) continue;
+        const int sk = GCB_SLOT(k);
+        uint8_t f = 0;
+        if (k == best_k) f = VOTE_PARTICIPATES;
+        else {
+            const gcb_read_desc rd = b.reads[sk];
+            if (is_part_of(GCB_CIG(out), od.n_cigar, GCB_CIG(sk), rd.n_cigar, leftReadMode)) {
+                f = VOTE_PARTICIPATES;
+                if (rd.l_qseq != od.l_qseq && rd.pos == od.pos && is_part_of(GCB_CIG(out), od.n_cigar, GCB_CIG(sk), rd.n_cigar, true))
+                    f |= VOTE_LENDIFF0;
+            }
+        }
+        ws.vote_flags[sk] = f;
+    }
+    if (lane == 0) ws.side_mode[2 * (int64_t)slot + side] = leftReadMode ? SIDE_LEFT : SIDE_RIGHT;
+    return out;
+#undef GCB_SLOT
+#undef GCB_HAVE
+#undef GCB_CIG
+}
+
+// group.cpp:68-134 per family of the cluster + the per-pair overlap windows of pair.cpp:103-119
+__global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o) {
+    const int lane = lane_id();
+    const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    if (c >= b.n_clusters) return;
+    const int p0 = b.cluster_pair_off[c], p1 = b.cluster_pair_off[c + 1], n = p1 - p0;
+    const int G = r.cluster_n_groups[c];
+    const bool crossContig = (b.cluster_flags[c] & GCB_CLUSTER_CROSS_CONTIG) != 0;
+
+    for (int i = lane; i < n; i += WARP) {
+        const int64_t pair = p0 + i;
+        const gcb_read_desc L = b.reads[2 * pair], R = b.reads[2 * pair + 1];
+        if (L.l_qseq >= 0) ws.right_ref_pos[2 * pair] = L.pos < 0 ? -1 : L.pos + cigar_ref_len(b.cigar + L.cigar_off, L.n_cigar);
+        if (R.l_qseq >= 0) ws.right_ref_pos[2 * pair + 1] = R.pos < 0 ? -1 : R.pos + cigar_ref_len(b.cigar + R.cigar_off, R.n_cigar);
+        ws.vote_flags[2 * pair] = 0;
+        ws.vote_flags[2 * pair + 1] = 0;
+        PairOverlap ov = {0, 0, 0, 0};
+        if (L.l_qseq >= 0 && R.l_qseq >= 0) {  // pair.cpp:103-119
+            int lo, ll, ro, rl;
+            get_m_offset_and_len(b.cigar + L.cigar_off, L.n_cigar, lo, ll);
+            get_m_offset_and_len(b.cigar + R.cigar_off, R.n_cigar, ro, rl);
+            if (ll > 0 && rl > 0) {
+                const int posDis = R.pos - L.pos;
+                ov.valid = 1;
+                if (posDis >= 0) {
+                    ov.left_start = lo + posDis;
+                    ov.right_start = ro;
+                    ov.cmp_len = min(ll - posDis, rl);
+                } else {
+                    ov.left_start = lo;
+                    ov.right_start = ro - posDis;
+                    ov.cmp_len = min(ll, rl + posDis);
+                }
+            }
+        }
+        ws.overlap[pair] = ov;
+    }
+    __syncwarp();
+
+    int64_t out_rel = 0;
+    for (int g = 0; g < G; g++) {
+        const int slot = p0 + g;
+        const int mb = ws.group_off[slot];
+        const int me = g + 1 < G ? ws.group_off[slot + 1] : p1;
+        const int m = me - mb;
+        gcb_group_result gr;
+        gr.out_off[0] = gr.out_off[1] = -1;
+        gr.tmpl_read[0] = gr.tmpl_read[1] = -1;
+        gr.qname_donor[0] = gr.qname_donor[1] = -1;
+        gr.diff[0] = gr.diff[1] = 0;
+        gr.mismatch_inc[0] = gr.mismatch_inc[1] = 0;
+        gr.merge_reads = m;
+        gr.reverse_merge_reads = 0;
+        gr.status = 0;
+        gr.duplex_partner = -1;
+        gr.duplex_diff = 0;
+        gr.umi_pair = -1;
+        const int first = ws.members[mb];
+        uint8_t mode0 = SIDE_NONE;
+        if (m == 1 && b.reads[2 * (int64_t)first + 1].l_qseq < 0) {  // group.cpp:73-77: passes through untouched
+            gr.merge_reads = 1;
+            if (b.reads[2 * (int64_t)first].l_qseq >= 0) {
+                gr.tmpl_read[0] = 2 * first;
+                mode0 = SIDE_COPY;
+            }
+            gr.umi_pair = first;
+            if (lane == 0) {
+                ws.side_mode[2 * (int64_t)slot] = mode0;
+                ws.side_mode[2 * (int64_t)slot + 1] = SIDE_NONE;
+            }
+        } else {
+            int nameToCopy = -1;  // group.cpp:79-99: shortest padded qname among the left reads, first in map order
+            if (crossContig) {
+                long long key = 0x7FFFFFFFFFFFFFFFll;
+                for (int k = lane; k < m; k += WARP) {
+                    const int sl = 2 * ws.members[mb + k];
+                    if (b.reads[sl].l_qseq < 0) continue;
+                    const long long kk = ((long long)b.reads[sl].l_qname << 32) | (unsigned)k;
+                    key = kk < key ? kk : key;
+                }
+                for (int off = 16; off > 0; off >>= 1) {
+                    const long long ok = __shfl_xor_sync(FULL, key, off);
+                    key = ok < key ? ok : key;
+                }
+                if (key != 0x7FFFFFFFFFFFFFFFll) nameToCopy = 2 * ws.members[mb + (int)(key & 0xFFFFFFFFll)];
+            }
+            if (lane == 0) {
+                ws.side_mode[2 * (int64_t)slot] = SIDE_NONE;
+                ws.side_mode[2 * (int64_t)slot + 1] = SIDE_NONE;
+            }
+            __syncwarp();
+            const int left = side_select(b, ws, o, mb, m, 0, slot);
+            const int right = side_select(b, ws, o, mb, m, 1, slot);
+            gr.tmpl_read[0] = left;
+            gr.tmpl_read[1] = right;
+            int name_slot;
+            if (crossContig) {  // group.cpp:109-113
+                if (left >= 0 && nameToCopy >= 0 && nameToCopy != left) gr.qname_donor[0] = nameToCopy;
+                name_slot = left >= 0 ? (nameToCopy >= 0 ? nameToCopy : left) : right;
+            } else if (left >= 0 && right >= 0) {  // group.cpp:114-123
+                if (b.reads[left].l_qname <= b.reads[right].l_qname) { gr.qname_donor[1] = left; name_slot = left; }
+                else { gr.qname_donor[0] = right; name_slot = right; }
+            } else {
+                name_slot = left >= 0 ? left : right;
+            }
+            gr.umi_pair = name_slot >= 0 ? name_slot / 2 : -1;  // Pair::setLeft/setRight, pair.cpp:188-216
+        }
+        for (int s = 0; s < 2; s++) {
+            if (gr.tmpl_read[s] < 0) continue;
+            gr.out_off[s] = out_rel;  // cluster-relative; the vote kernel rebases it after the scan
+            out_rel += record_bytes(b.reads[gr.tmpl_read[s]].l_qseq);
+        }
+        if (lane == 0) r.groups[slot] = gr;
+    }
+    if (lane == 0) ws.cluster_out_bytes[c] = out_rel;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive scan of cluster_out_bytes in two launches (block-local prefix, then the block totals).
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = SCAN_BLOCK / SCAN_THREADS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_local_kernel(Workspace ws, int32_t n_clusters) {
+    __shared__ int64_t warp_tot[SCAN_THREADS / WARP];
+    const int lane = lane_id(), warp = (int)(threadIdx.x >> 5);
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int64_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = base + k < n_clusters ? ws.cluster_out_bytes[base + k] : 0;
+        sum += v[k];
+    }
+    int64_t incl = sum;
+    for (int off = 1; off < WARP; off <<= 1) {
+        const int64_t t = __shfl_up_sync(FULL, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == WARP - 1) warp_tot[warp] = incl;
+    __syncthreads();
+    int64_t pre = incl - sum;
+    for (int w = 0; w < warp; w++) pre += warp_tot[w];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n_clusters) ws.cluster_out_off[base + k] = pre;
+        pre += v[k];
+    }
+    if (threadIdx.x == SCAN_THREADS - 1) ws.scan_block[blockIdx.x] = pre;
+}
+
+__global__ void __launch_bounds__(WARP) scan_blocks_kernel(Workspace ws, int32_t n_blocks, int64_t *out_bytes, int64_t out_capacity) {
+    const int lane = lane_id();
+    int64_t carry = 0;
+    for (int base = 0; base < n_blocks; base += WARP) {
+        const int i = base + lane;
+        const int64_t v = i < n_blocks ? ws.scan_block[i] : 0;
+        int64_t incl = v;
+        for (int off = 1; off < WARP; off <<= 1) {
+            const int64_t t = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (i < n_blocks) ws.scan_block[i] = carry + incl - v;
+        carry += __shfl_sync(FULL, incl, WARP - 1);
+    }
+    if (lane == 0) {
+        ws.scan_block[n_blocks] = carry;
+        *out_bytes = carry;
+        if (carry > out_capacity) raise_error(ws.error_flag, GCB_ERR_CAPACITY);
+    }
+}
+
+}  // namespace gcb

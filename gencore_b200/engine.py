@@ -1,0 +1,132 @@
+"""Host-side mirror of the reference's seam for the hot path.
+
+The reference's in-process seam is `Cluster::clusterByUMI(umiDiffThreshold, preStats, postStats,
+crossContig)` called cluster by cluster from gencore.cpp:355 and gencore.cpp:409.  `ConsensusEngine`
+is that call batched: `cluster_by_umi(batch)` hands a packed batch of clusters to the CUDA library
+(libgencore_b200.so, C ABI in include/gencore_b200.h) and returns what the reference's Pair objects
+would hold.  There is no CPU path: without the compiled library or without an sm_100 device the
+constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .abi import (GCB_ABI_VERSION, GCB_ERR_NO_DEVICE, GCB_OK, STAGE_ALL, Batch, BatchStruct, Genome, Options, Result,
+                  ResultStruct)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(HERE, "csrc", "libgencore_b200.so")
+
+# every symbol include/gencore_b200.h declares
+ABI_SYMBOLS = ["gcb_abi_version", "gcb_default_options", "gcb_create", "gcb_destroy", "gcb_last_error", "gcb_set_reference",
+               "gcb_set_reference_device", "gcb_consensus_batch", "gcb_consensus_batch_device", "gcb_batch_status",
+               "gcb_launch_count"]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"gencore_b200: status {code}: {msg}")
+        self.code = code
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    path = path or DEFAULT_LIB
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} is missing: build it with `python -m gencore_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.gcb_abi_version.restype = C.c_int
+    lib.gcb_default_options.argtypes = [C.c_void_p]
+    lib.gcb_create.restype = C.c_int
+    lib.gcb_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.gcb_destroy.argtypes = [C.c_void_p]
+    lib.gcb_last_error.restype = C.c_char_p
+    lib.gcb_last_error.argtypes = [C.c_void_p]
+    lib.gcb_set_reference.restype = C.c_int
+    lib.gcb_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.gcb_set_reference_device.restype = C.c_int
+    lib.gcb_set_reference_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.gcb_consensus_batch.restype = C.c_int
+    lib.gcb_consensus_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gcb_consensus_batch_device.restype = C.c_int
+    lib.gcb_consensus_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.gcb_batch_status.restype = C.c_int
+    lib.gcb_batch_status.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gcb_launch_count.restype = C.c_int64
+    lib.gcb_launch_count.argtypes = [C.c_void_p]
+    if lib.gcb_abi_version() != GCB_ABI_VERSION:
+        raise RuntimeError(f"{path}: ABI version {lib.gcb_abi_version()} != {GCB_ABI_VERSION}")
+    return lib
+
+
+class ConsensusEngine:
+    """One context on one GPU.  `options` are the Options fields the hot path reads."""
+
+    def __init__(self, options: Optional[Options] = None, device: int = 0, lib_path: Optional[str] = None):
+        self.lib = load_library(lib_path)
+        self.options = options or Options.default()
+        self.device = device
+        self._ctx = C.c_void_p()
+        rc = self.lib.gcb_create(C.byref(self.options), device, C.byref(self._ctx))
+        if rc == GCB_ERR_NO_DEVICE:
+            raise EngineError(rc, "no sm_100 (B200) device: the consensus engine has no CPU path")
+        if rc != GCB_OK:
+            raise EngineError(rc, "gcb_create failed")
+        self._genome_keepalive = None
+
+    # -- lifecycle
+    def close(self) -> None:
+        if self._ctx:
+            self.lib.gcb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        if rc != GCB_OK:
+            raise EngineError(rc, (self.lib.gcb_last_error(self._ctx) or b"").decode())
+
+    # -- Reference::instance()->getData (reference.cpp:33-71)
+    def set_reference(self, genome: Optional[Genome]) -> None:
+        if genome is None:
+            self._check(self.lib.gcb_set_reference(self._ctx, None, 0, None, None, 0))
+            return
+        self._check(self.lib.gcb_set_reference(self._ctx, genome.packed4.ctypes.data, len(genome.packed4), genome.contig_off.ctypes.data,
+                                               genome.contig_len.ctypes.data, len(genome.contig_len)))
+
+    def set_reference_device(self, packed4_ptr: int, packed_bytes: int, contig_off: np.ndarray, contig_len: np.ndarray, keepalive=None) -> None:
+        """The packed genome already lives on the device (e.g. after an NCCL broadcast)."""
+        self._genome_keepalive = keepalive
+        self._check(self.lib.gcb_set_reference_device(self._ctx, packed4_ptr, packed_bytes, contig_off.ctypes.data,
+                                                      contig_len.ctypes.data, len(contig_len)))
+
+    # -- Cluster::clusterByUMI over a batch of clusters, host buffers in and out
+    def cluster_by_umi(self, batch: Batch, result: Optional[Result] = None) -> Result:
+        res = result or Result.allocate(batch)
+        bs, rs = batch.as_struct(), res.as_struct()
+        self._check(self.lib.gcb_consensus_batch(self._ctx, C.byref(bs), C.byref(rs)))
+        return res
+
+    # -- same with every buffer resident on the device (pointers are integers, e.g. torch .data_ptr())
+    def cluster_by_umi_device(self, bs: BatchStruct, rs: ResultStruct, stages: int = STAGE_ALL, stream: int = 0) -> None:
+        self._check(self.lib.gcb_consensus_batch_device(self._ctx, C.byref(bs), C.byref(rs), stages, C.c_void_p(stream)))
+
+    def batch_status(self, stream: int = 0) -> int:
+        return self.lib.gcb_batch_status(self._ctx, C.c_void_p(stream))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.gcb_launch_count(self._ctx))

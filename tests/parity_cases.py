@@ -1,0 +1,98 @@
+"""The batches every implementation of the hot path is compared on (SIMT-check build on CPU, CUDA build on
+the B200): golden fixtures from the reference, the hand-built quirk batch under every option set, random
+ragged batches, >1000-pair families, the fixed-length BASELINE.json shapes, and degenerate inputs."""
+from __future__ import annotations
+
+import dataclasses
+import glob
+import os
+
+import numpy as np
+
+import cases
+from gencore_b200 import synth
+from gencore_b200.abi import READ_DESC, Batch, Options
+from parity import load_golden
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+
+
+def golden_case(path):
+    batch, genome, opt, *_ = load_golden(path)
+    return batch, genome, opt
+
+
+def edge_case(optname):
+    batch, genome, _ = cases.edge_batch()
+    return batch, genome, cases.OPTION_SETS[optname]
+
+
+def ragged_case(seed, umi, n_clusters=60):
+    batch, genome, _ = synth.make_ragged_batch(100 + seed, n_clusters=n_clusters, umi=umi, err=0.02 if seed % 2 else 0.005)
+    return batch, genome, list(cases.OPTION_SETS.values())[seed % len(cases.OPTION_SETS)]
+
+
+def fixed_case(name, n_pairs, contig_len=200_000):
+    cfg = synth.CONFIGS[name]
+    small = dataclasses.replace(cfg, contig_len=contig_len, n_contigs=min(cfg.n_contigs, 2))
+    batch, genome, _ = synth.make_fixed_batch(small, seed=20261017, n_pairs=n_pairs, with_qnames=False)
+    return batch, genome, Options.default(cluster_size_req=cfg.supporting_reads)
+
+
+def deep_case():
+    batch, genome, _ = cases.deep_batch()
+    return batch, genome, Options.default()
+
+
+def low_complexity_case():
+    batch, genome, _ = cases.low_complexity_batch()
+    return batch, genome, Options.default()
+
+
+def no_reference_case():
+    batch, _genome, _ = synth.make_ragged_batch(5, n_clusters=40, umi="single")
+    return batch, None, Options.default()
+
+
+def empty_case():
+    batch = Batch(np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros((0, 1), np.uint64),
+                  np.zeros(0, READ_DESC), np.zeros(1, np.uint32), np.zeros(16, np.uint8), [], np.zeros(0, np.uint8), "")
+    return batch, None, Options.default()
+
+
+def tiny_reads_case():
+    """Reads of 1..9 bases, odd lengths, mates missing: record padding and the nibble tail."""
+    from gencore_b200.synth import BatchBuilder, SynthCluster, SynthPair, SynthRead
+    rng = np.random.Generator(np.random.PCG64(3))
+    contigs, genome = synth.random_genome(rng, [400])
+    bb = BatchBuilder(1, "UMI")
+    for c in range(12):
+        prs = []
+        for i in range(1 + c % 4):
+            l = 1 + (c + i) % 9
+            pos = 10 + 20 * c
+            left = SynthRead(pos, f"{l}M", bytes(contigs[0][pos:pos + l]), rng.integers(2, 41, l).astype(np.uint8), 12)
+            right = None
+            if (c + i) % 3:
+                right = SynthRead(pos + 3, f"{l}M", bytes(contigs[0][pos + 3:pos + 3 + l]), rng.integers(2, 41, l).astype(np.uint8), -12)
+            prs.append(SynthPair(b"t%d_%d:UMI_ACGT" % (c, i), "ACGT", left, right))
+        bb.add(SynthCluster(0, prs))
+    return bb.build(), genome, Options.default()
+
+
+def small_cases():
+    """(id, thunk) for the cases cheap enough for the CPU SIMT interpreter."""
+    out = [("golden_" + os.path.basename(p)[:-4], (lambda p=p: golden_case(p))) for p in GOLDEN]
+    out += [("edge_" + n, (lambda n=n: edge_case(n))) for n in cases.OPTION_SETS]
+    out += [(f"ragged_{umi}_{seed}", (lambda s=seed, u=umi: ragged_case(s, u, 30))) for seed in range(4) for umi in ("none", "single", "duplex")]
+    out += [("deep_1100", deep_case), ("low_complexity", low_complexity_case), ("no_reference", no_reference_case),
+            ("empty", empty_case), ("tiny_reads", tiny_reads_case)]
+    out += [(f"{n}_1500", (lambda n=n: fixed_case(n, 1500))) for n in ("cfg1", "cfg2", "cfg3", "cfg4")]
+    return out
+
+
+def gpu_cases():
+    out = small_cases()
+    out += [(f"ragged_{umi}_{seed}_big", (lambda s=seed, u=umi: ragged_case(s, u, 400))) for seed in range(4, 8) for umi in ("none", "single", "duplex")]
+    out += [(f"{n}_40k", (lambda n=n: fixed_case(n, 40_000, 2_000_000))) for n in ("cfg1", "cfg2", "cfg3", "cfg4")]
+    return out

@@ -1,0 +1,348 @@
+// simt_check.h — a small single-threaded SIMT interpreter for CPU-only CI.  TEST INFRASTRUCTURE ONLY.
+//
+// The kernels under gencore_b200/csrc/ are compiled a second time by g++ with -DGCB_SIMT_CHECK
+// (tests/simt_check/build.py) against this header: every CUDA thread of a block becomes a ucontext
+// fiber, __syncthreads()/warp collectives are rendezvous points between fibers, blocks run one
+// after another, and the CUDA runtime calls the host side makes become malloc/memcpy.  That lets the
+// parity tests drive the real kernel source against the oracle on a box without a GPU; it proves
+// nothing about races, alignment or speed (the `-m gpu` tests and compute-sanitizer do that) and it
+// is never loaded by the product package.
+#pragma once
+
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+namespace simt {
+
+constexpr int kWarp = 32;
+constexpr size_t kStackBytes = 256 * 1024;
+
+struct Fiber {
+    ucontext_t ctx;
+    char *stack = nullptr;
+    bool done = true;
+};
+
+struct WarpState {
+    uint64_t xchg[2][kWarp];
+    int parity = 0;       // which xchg buffer the next collective uses
+    int arrived = 0;
+    unsigned generation = 0;
+    int live = 0;
+};
+
+struct State {
+    std::vector<Fiber> fibers;
+    std::vector<WarpState> warps;
+    ucontext_t sched;
+    int cur = -1;
+    int nthreads = 0;
+    int live = 0;
+    int bar_arrived = 0;
+    unsigned bar_generation = 0;
+    uint64_t progress = 0;
+    std::vector<uint8_t> smem;
+    const std::function<void()> *body = nullptr;
+    uint64_t launches = 0;
+};
+
+inline State &st() {
+    static State s;
+    return s;
+}
+
+}  // namespace simt
+
+inline uint3 threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
+
+namespace simt {
+
+inline uint8_t *dyn_smem() { return st().smem.data(); }
+
+inline void yield() {
+    State &s = st();
+    swapcontext(&s.fibers[s.cur].ctx, &s.sched);
+}
+
+inline void trampoline() {
+    State &s = st();
+    (*s.body)();
+    int me = s.cur;
+    s.fibers[me].done = true;
+    s.live--;
+    s.warps[me / kWarp].live--;
+    s.progress++;
+    swapcontext(&s.fibers[me].ctx, &s.sched);
+}
+
+inline void run_block(int nthreads, const std::function<void()> &body) {
+    State &s = st();
+    if ((int)s.fibers.size() < nthreads) s.fibers.resize(nthreads);
+    s.warps.assign((nthreads + kWarp - 1) / kWarp, WarpState());
+    s.nthreads = nthreads;
+    s.live = nthreads;
+    s.bar_arrived = 0;
+    s.body = &body;
+    for (int t = 0; t < nthreads; t++) {
+        Fiber &f = s.fibers[t];
+        if (!f.stack) f.stack = (char *)malloc(kStackBytes);
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = kStackBytes;
+        f.ctx.uc_link = &s.sched;
+        makecontext(&f.ctx, (void (*)())trampoline, 0);
+        f.done = false;
+        s.warps[t / kWarp].live++;
+    }
+    while (s.live > 0) {
+        uint64_t before = s.progress;
+        for (int t = 0; t < nthreads; t++) {
+            if (s.fibers[t].done) continue;
+            s.cur = t;
+            threadIdx.x = (unsigned)t;
+            threadIdx.y = threadIdx.z = 0;
+            swapcontext(&s.sched, &s.fibers[t].ctx);
+        }
+        if (s.live > 0 && s.progress == before) {
+            fprintf(stderr, "simt_check: deadlock in block %u (%d threads alive, none can advance)\n", blockIdx.x, s.live);
+            abort();
+        }
+    }
+}
+
+inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body) {
+    State &s = st();
+    if (block.x % kWarp != 0 || block.y != 1 || block.z != 1 || grid.y != 1 || grid.z != 1) {
+        fprintf(stderr, "simt_check: unsupported launch shape\n");
+        abort();
+    }
+    s.launches++;
+    if (s.smem.size() < smem_bytes + 128) s.smem.resize(smem_bytes + 128);
+    blockDim = block;
+    gridDim = grid;
+    for (unsigned b = 0; b < grid.x; b++) {
+        blockIdx.x = b;
+        blockIdx.y = blockIdx.z = 0;
+        run_block((int)block.x, body);
+    }
+}
+
+// ---- rendezvous primitives
+inline void block_barrier() {
+    State &s = st();
+    unsigned gen = s.bar_generation;
+    s.bar_arrived++;
+    for (;;) {
+        if (s.bar_generation != gen) return;
+        if (s.bar_arrived >= s.live) {  // exited threads count as arrived (CUDA semantics)
+            s.bar_arrived = 0;
+            s.bar_generation++;
+            s.progress++;
+            return;
+        }
+        yield();
+    }
+}
+
+inline void warp_barrier() {
+    State &s = st();
+    WarpState &w = s.warps[s.cur / kWarp];
+    unsigned gen = w.generation;
+    w.arrived++;
+    for (;;) {
+        if (w.generation != gen) return;
+        if (w.arrived >= w.live) {
+            if (w.live != kWarp) {
+                fprintf(stderr, "simt_check: warp collective after %d lanes of the warp exited\n", kWarp - w.live);
+                abort();
+            }
+            w.arrived = 0;
+            w.generation++;
+            s.progress++;
+            return;
+        }
+        yield();
+    }
+}
+
+inline int lane() { return st().cur % kWarp; }
+
+// every lane publishes v, gets the whole vector back
+inline const uint64_t *exchange(uint64_t v) {
+    State &s = st();
+    WarpState &w = s.warps[s.cur / kWarp];
+    int p = w.parity;
+    w.xchg[p][s.cur % kWarp] = v;
+    warp_barrier();
+    // the last arriver flips parity for the next collective; all lanes of this one still read buffer p
+    if (w.parity == p) w.parity = p ^ 1;  // flipped once per collective, by the first lane released
+    return w.xchg[p];
+}
+
+inline void check_full(unsigned mask) {
+    if (mask != 0xffffffffu) {
+        fprintf(stderr, "simt_check: only full-mask warp collectives are supported (mask %08x)\n", mask);
+        abort();
+    }
+}
+
+template <typename T>
+inline uint64_t to_bits(T v) {
+    static_assert(sizeof(T) <= 8, "collective operand too wide");
+    uint64_t b = 0;
+    memcpy(&b, &v, sizeof(T));
+    return b;
+}
+template <typename T>
+inline T from_bits(uint64_t b) {
+    T v;
+    memcpy(&v, &b, sizeof(T));
+    return v;
+}
+
+}  // namespace simt
+
+// ---- CUDA device intrinsics used by the kernels ---------------------------------------------------
+inline void __syncthreads() { simt::block_barrier(); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) {
+    simt::check_full(mask);
+    simt::warp_barrier();
+}
+template <typename T>
+inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
+    simt::check_full(mask);
+    (void)width;
+    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    return simt::from_bits<T>(x[src & 31]);
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
+    simt::check_full(mask);
+    (void)width;
+    int l = simt::lane();
+    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    return simt::from_bits<T>(x[(l ^ lanemask) & 31]);
+}
+template <typename T>
+inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32) {
+    simt::check_full(mask);
+    (void)width;
+    int l = simt::lane();
+    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    int src = l + (int)delta;
+    return simt::from_bits<T>(x[src < 32 ? src : l]);
+}
+template <typename T>
+inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
+    simt::check_full(mask);
+    (void)width;
+    int l = simt::lane();
+    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    int src = l - (int)delta;
+    return simt::from_bits<T>(x[src >= 0 ? src : l]);
+}
+inline unsigned __ballot_sync(unsigned mask, int pred) {
+    simt::check_full(mask);
+    const uint64_t *x = simt::exchange(pred ? 1 : 0);
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) r |= (unsigned)(x[i] & 1) << i;
+    return r;
+}
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
+inline int __reduce_add_sync(unsigned mask, int v) {
+    simt::check_full(mask);
+    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    int r = 0;
+    for (int i = 0; i < 32; i++) r += simt::from_bits<int>(x[i]);
+    return r;
+}
+inline int __reduce_min_sync(unsigned mask, int v) {
+    simt::check_full(mask);
+    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    int r = simt::from_bits<int>(x[0]);
+    for (int i = 1; i < 32; i++) r = std::min(r, simt::from_bits<int>(x[i]));
+    return r;
+}
+inline int __reduce_max_sync(unsigned mask, int v) {
+    simt::check_full(mask);
+    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    int r = simt::from_bits<int>(x[0]);
+    for (int i = 1; i < 32; i++) r = std::max(r, simt::from_bits<int>(x[i]));
+    return r;
+}
+
+template <typename T>
+inline T __ldg(const T *p) { return *p; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (unsigned)(v >> (shift & 31));
+}
+using std::max;
+using std::min;
+
+template <typename T>
+inline T atomicAdd(T *p, T v) { T old = *p; *p = old + v; return old; }
+template <typename T>
+inline T atomicMax(T *p, T v) { T old = *p; if (v > old) *p = v; return old; }
+template <typename T>
+inline T atomicCAS(T *p, T cmp, T v) { T old = *p; if (old == cmp) *p = v; return old; }
+inline void __threadfence() {}
+
+// ---- the slice of the CUDA runtime the host side uses -----------------------------------------------
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+constexpr cudaError_t cudaSuccess = 0;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+struct cudaDeviceProp { int major, minor, multiProcessorCount; char name[64]; size_t sharedMemPerBlockOptin; };
+inline cudaError_t cudaMalloc(void **p, size_t n) { *p = aligned_alloc(256, (n + 255) & ~(size_t)255); return *p ? 0 : 2; }
+inline cudaError_t cudaFree(void *p) { free(p); return 0; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return 0; }
+constexpr unsigned cudaStreamNonBlocking = 1;
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaGetLastError() { return 0; }
+inline cudaError_t cudaSetDevice(int) { return 0; }
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return 0; }
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
+    memset(p, 0, sizeof *p);
+    p->major = 10;
+    p->minor = 0;
+    p->multiProcessorCount = 4;
+    p->sharedMemPerBlockOptin = 227 * 1024;
+    strcpy(p->name, "simt_check");
+    return 0;
+}
+inline const char *cudaGetErrorString(cudaError_t) { return "simt_check"; }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }

@@ -1,0 +1,102 @@
+"""Parity tests proper: the CUDA library (gencore_b200/csrc/libgencore_b200.so) through its C ABI on a
+B200 against the oracle, bit-exact, on the shared case list; then size-independent properties at
+BASELINE.json's bench size."""
+import numpy as np
+import pytest
+
+import parity_cases
+from gencore_b200.abi import GROUP_DCS, GROUP_SSCS, STAGE_ALL, Options, Result
+from gencore_b200.hoststats import group_slots
+from parity import assert_results_equal
+
+pytestmark = pytest.mark.gpu
+
+CASES = parity_cases.gpu_cases()
+
+
+@pytest.fixture(scope="module")
+def engine_cls():
+    import torch
+    assert torch.cuda.is_available(), "the gpu tests need a CUDA device"
+    from gencore_b200.engine import ConsensusEngine
+    return ConsensusEngine
+
+
+@pytest.mark.parametrize("name,thunk", CASES, ids=[c[0] for c in CASES])
+def test_cuda_matches_oracle_host_buffers(engine_cls, oracle, name, thunk):
+    batch, genome, opt = thunk()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        res = eng.cluster_by_umi(batch)
+        assert eng.launches > 0 or batch.n_clusters == 0
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
+
+
+@pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "deep_1100"])
+def test_cuda_matches_oracle_device_buffers(engine_cls, oracle, name):
+    import torch
+    from gencore_b200.device import DeviceBatch, DeviceResult
+    batch, genome, opt = dict(CASES)[name]()
+    dev = torch.device("cuda:0")
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        db = DeviceBatch.from_host(batch, dev)
+        dr = DeviceResult.allocate(batch.n_pairs, batch.n_clusters, len(batch.payload), dev)
+        torch.cuda.synchronize()
+        for _ in range(2):  # the second run must give the same answer (no state leaks between batches)
+            eng.cluster_by_umi_device(db.struct, dr.struct, STAGE_ALL, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert eng.batch_status() == 0
+            res = dr.to_host()
+            assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
+
+
+def test_capacity_error_is_reported(engine_cls):
+    from gencore_b200.abi import GCB_ERR_CAPACITY
+    from gencore_b200.engine import EngineError
+    batch, genome, opt = parity_cases.fixed_case("cfg2", 1500)
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        small = Result.allocate(batch, out_capacity=64)
+        with pytest.raises(EngineError) as ei:
+            eng.cluster_by_umi(batch, small)
+        assert ei.value.code == GCB_ERR_CAPACITY
+
+
+def test_full_size_properties(engine_cls, oracle):
+    """cfg2 at the bench size (1M pairs): properties that need no oracle run, plus an oracle check on a slice."""
+    from gencore_b200 import synth
+    batch, genome, _ = synth.make_fixed_batch(synth.CONFIGS["cfg2"], seed=20261019, n_pairs=1_000_000, with_qnames=False)
+    opt = Options.default()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        res = eng.cluster_by_umi(batch)
+        res2 = eng.cluster_by_umi(batch)
+    # determinism
+    assert np.array_equal(res.groups, res2.groups) and np.array_equal(res.out_payload[:res.out_bytes[0]], res2.out_payload[:res2.out_bytes[0]])
+    slots = group_slots(batch, res)
+    g = res.groups[slots]
+    # every pair is in exactly one family and family sizes add up
+    assert (res.pair_group >= 0).all()
+    assert int(g["merge_reads"].sum()) == batch.n_pairs
+    # no UMI pair is a duplex here, every family survives with -s 1
+    assert ((g["status"] == GROUP_SSCS) | (g["status"] == GROUP_DCS)).all()
+    # consensus records tile the output exactly, in order
+    l = batch.reads["l_qseq"][np.maximum(g["tmpl_read"], 0)].astype(np.int64)
+    sz = np.where(g["tmpl_read"] >= 0, ((l + 3) & ~3) + (((l + 1) // 2 + 3) & ~3), 0)
+    offs = g["out_off"].reshape(-1)[(g["tmpl_read"] >= 0).reshape(-1)]
+    assert np.array_equal(offs, np.concatenate([[0], np.cumsum(sz.reshape(-1)[sz.reshape(-1) > 0])[:-1]]))
+    assert int(res.out_bytes[0]) == int(sz.sum())
+    # consensus of a family whose reads all agree is the template itself (idempotence): vote again over the output
+    # -> checked through the oracle on the first 2000 clusters
+    c1 = 2000
+    p1 = int(batch.cluster_pair_off[c1])
+    from gencore_b200.abi import Batch
+    sub = Batch(batch.cluster_pair_off[:c1 + 1].copy(), batch.cluster_ref[:c1].copy(), batch.cluster_flags[:c1].copy(), batch.umi[:p1].copy(),
+                batch.reads[:2 * p1].copy(), batch.cigar, batch.payload[:int(batch.reads["data_off"][2 * p1])].copy(), None, None, batch.umi_prefix)
+    ref = oracle.consensus(sub, genome, opt)
+    nslots = group_slots(sub, ref)
+    assert np.array_equal(res.cluster_n_groups[:c1], ref.cluster_n_groups)
+    for name in ref.groups.dtype.names:
+        assert np.array_equal(res.groups[nslots][name], ref.groups[nslots][name]), name
+    assert np.array_equal(res.out_payload[:ref.out_bytes[0]], ref.out_payload[:ref.out_bytes[0]])
