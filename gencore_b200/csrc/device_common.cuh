@@ -20,6 +20,39 @@ struct PairOverlap {   // Pair::computeScore's overlap window (pair.cpp:103-119)
     int32_t valid;        // 1: both mates present and both have an M block (scores depend on quality)
 };
 
+// One read as the tiled vote kernel sees it (16 bytes, staged into shared memory by a bulk copy).
+// Offsets are in 4-byte units relative to the cluster's slab.  own_l == 0: the read does not vote.
+struct VoteRead {
+    uint16_t own_off4;   // record of this read
+    uint16_t mate_off4;  // record of its mate (valid with VR_OVERLAP)
+    int16_t own_l;       // l_qseq of this read, 0 = no vote
+    int16_t mate_l;
+    int16_t shift;       // readpos = column + shift (group.cpp:377-379)
+    int16_t ov_own;      // overlap window of Pair::computeScore (pair.cpp:108-119) clipped to this read:
+    int16_t ov_mate;     //   own index ov_own + k pairs with mate index ov_mate + k, 0 <= k < ov_len
+    int16_t ov_len;      //   VR_NO_OVERLAP_INFO: pair without mate or M block, the moderate score everywhere (pair.cpp:92,99)
+};
+constexpr int VR_NO_OVERLAP_INFO = -1;
+
+// One (family, side) for the tiled vote kernel (16 bytes).
+struct FsDesc {
+    uint16_t mb_rel;   // members index of the family's first pair, relative to the cluster's first pair
+    uint16_t m;        // pairs in the family
+    uint16_t l_out;    // template l_qseq
+    uint16_t len;      // columns that are voted (group.cpp:354-360)
+    uint16_t tmpl_k;   // template = k-th member of the family
+    uint8_t mode;      // SIDE_*
+    uint8_t flags;     // FS_*
+    uint32_t out_rel;  // consensus record offset relative to the cluster's output
+};
+constexpr uint8_t FS_NOFIT = 1;  // some field does not fit its 16 bits: the tile goes to the generic kernel
+
+struct TileDir {
+    int32_t c0;      // first cluster of the tile
+    int32_t p0;      // its first pair
+    int64_t slab0;   // payload offset of its slab
+};
+
 struct Workspace {
     int32_t *members;           // [n_pairs] pair indices, cluster by cluster, families contiguous, map order inside
     int32_t *group_off;         // [n_pairs] slot-indexed: index into members of the family's first pair
@@ -34,6 +67,13 @@ struct Workspace {
     int64_t *cluster_out_off;   // [n_clusters] exclusive prefix of the above inside its scan block
     int64_t *scan_block;        // [n_scan_blocks+1] exclusive prefix over scan blocks; last = total
     int32_t *error_flag;        // [1] sticky gcb_status raised by a kernel
+    VoteRead *vote_reads;       // [2*n_pairs] what the tiled vote kernel needs of every read, family-side runs:
+                                //   the family whose pairs are members[mb..mb+m) owns entries [2*mb, 2*mb+m) for side 0
+                                //   and [2*mb+m, 2*mb+2m) for side 1, in members order
+    FsDesc *fs_desc;            // [2*n_pairs] index 2*slot+side: one family-side's vote parameters (mode NONE = nothing)
+    TileDir *tile_dir;          // [n_tiles+1] first cluster / pair / slab byte of every vote tile
+    int32_t *generic_tiles;     // [n_tiles] tiles the tiled vote kernel handed to the generic kernel
+    int32_t *generic_count;     // [1]
 };
 
 constexpr uint8_t VOTE_PARTICIPATES = 1;  // read is in makeConsensus' `reads` (group.cpp:287-313)

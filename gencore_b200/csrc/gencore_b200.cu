@@ -1,7 +1,8 @@
 // gencore_b200.cu — the C ABI of libgencore_b200.so (include/gencore_b200.h) and the launch sequence
 // of one batch.  Host code only sizes buffers, moves bytes and launches; all arithmetic of the
 // reference's hot path lives in the kernels:
-//   umi_group_kernel -> select_template_kernel -> scan_local/scan_blocks -> score_vote_kernel -> duplex_kernel
+//   umi_group_kernel -> select_template_kernel -> scan_local/scan_blocks -> vote_tiled_kernel
+//   (-> score_vote_kernel for the tiles that do not fit the tiled kernel's tables) -> duplex_kernel
 #include <stdio.h>
 #include <string.h>
 
@@ -10,6 +11,7 @@
 #include "k_duplex.cuh"
 #include "k_group_select.cuh"
 #include "k_score_vote.cuh"
+#include "k_vote_tiled.cuh"
 
 using namespace gcb;
 
@@ -33,6 +35,7 @@ struct gcb_ctx {
     DevBuf g_packed, g_off, g_len;
     // workspace (grow-only)
     DevBuf w_members, w_group_off, w_scratch, w_rrp, w_flags, w_mode, w_hasumi, w_overlap, w_slab, w_cob, w_coo, w_scan, w_err, w_tiles;
+    DevBuf w_vr, w_fs, w_gtiles, w_gcount;
     // device mirror of a host batch / result (gcb_consensus_batch)
     DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
     DevBuf d_pair_group, d_ngroups, d_groups, d_out, d_out_bytes;
@@ -72,7 +75,38 @@ void release(DevBuf &b) {
     b.cap = 0;
 }
 
-int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t n_tiles, Workspace &ws, int32_t *&tile_first) {
+// Tile geometry of the tiled vote kernel for one batch: the payload window whose clusters form a tile and
+// the staging buffer that holds the largest such tile (window + the largest cluster), chosen so that as
+// many CTAs as possible share an SM's 227 KB of shared memory.
+struct TilePlan {
+    int32_t window, slab_cap, smem;
+};
+TilePlan plan_tiles(int32_t max_cluster_bytes) {
+    const int32_t KB = 1024, budget = 227 * KB, tables = VT_OFF_SLAB + 1 * KB;  // + the 1 KB per-CTA reserve
+    int32_t maxc = max_cluster_bytes > 0 ? ((max_cluster_bytes + 127) & ~127) : 16 * KB;
+    TilePlan p;
+    if (32 * KB + maxc + tables <= budget / 3) p.window = 32 * KB;
+    else if (24 * KB + maxc + tables <= budget / 2) p.window = 24 * KB;
+    else p.window = 32 * KB;
+    p.slab_cap = p.window + maxc;
+    if (p.slab_cap > VT_MAX_SLAB) p.slab_cap = VT_MAX_SLAB;
+    if (p.slab_cap + tables > budget) p.slab_cap = (budget - tables) & ~127;
+    p.smem = VT_OFF_SLAB + p.slab_cap;
+    return p;
+}
+
+// group.cpp:421-427 holds for a column whose reads all agree and whose best quality is >= moderateQuality
+// without looking at the scores iff every score such a column can see is positive and the best read's is >= -c
+int32_t fast_path_implied(const gcb_options &o) {
+    const int sh = (signed char)o.score_high, sm = (signed char)o.score_moderate, sl = (signed char)o.score_low, sb = (signed char)o.score_bad;
+    const int mn = sh < sm ? (sh < sl ? (sh < sb ? sh : sb) : (sl < sb ? sl : sb)) : (sm < sl ? (sm < sb ? sm : sb) : (sl < sb ? sl : sb));
+    if (mn <= 0 || mn + 4 > 127) return 0;
+    if (sh < o.base_score_req || sm < o.base_score_req || mn + 4 < o.base_score_req) return 0;
+    if (o.moderate_quality < 0 || o.moderate_quality > 255) return 0;
+    return 1;
+}
+
+int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t n_tiles, Workspace &ws) {
     int rc;
     const int64_t n_scan = (n_clusters + SCAN_BLOCK - 1) / SCAN_BLOCK;
 #define GCB_RES(buf, bytes) if ((rc = reserve(ctx, ctx->buf, (size_t)(bytes))) != GCB_OK) return rc
@@ -89,7 +123,11 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_coo, n_clusters * 8);
     GCB_RES(w_scan, (n_scan + 1) * 8);
     GCB_RES(w_err, 4);
-    GCB_RES(w_tiles, (n_tiles + 1) * 4);
+    GCB_RES(w_tiles, (n_tiles + 1) * sizeof(TileDir));
+    GCB_RES(w_vr, 2 * n_pairs * sizeof(VoteRead));
+    GCB_RES(w_fs, 2 * n_pairs * sizeof(FsDesc));
+    GCB_RES(w_gtiles, (n_tiles + 1) * 4);
+    GCB_RES(w_gcount, 4);
 #undef GCB_RES
     ws.members = (int32_t *)ctx->w_members.p;
     ws.group_off = (int32_t *)ctx->w_group_off.p;
@@ -104,7 +142,11 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     ws.cluster_out_off = (int64_t *)ctx->w_coo.p;
     ws.scan_block = (int64_t *)ctx->w_scan.p;
     ws.error_flag = (int32_t *)ctx->w_err.p;
-    tile_first = (int32_t *)ctx->w_tiles.p;
+    ws.tile_dir = (TileDir *)ctx->w_tiles.p;
+    ws.vote_reads = (VoteRead *)ctx->w_vr.p;
+    ws.fs_desc = (FsDesc *)ctx->w_fs.p;
+    ws.generic_tiles = (int32_t *)ctx->w_gtiles.p;
+    ws.generic_count = (int32_t *)ctx->w_gcount.p;
     return GCB_OK;
 }
 
@@ -148,7 +190,8 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
         delete ctx;
         return GCB_ERR_CUDA;
     }
-    if (cudaFuncSetAttribute(score_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(score_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(vote_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
         return GCB_ERR_CUDA;
@@ -163,7 +206,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
-                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
+                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
                      &ctx->d_out, &ctx->d_out_bytes};
     for (DevBuf *b : all) release(*b);
@@ -215,10 +258,10 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
         return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch_device: bad sizes or alignment (payload 16 B, payload_bytes % 16, out_payload 4 B)");
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : ctx->stream;
     GCB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int64_t n_tiles = (batch->payload_bytes + TILE_WINDOW - 1) / TILE_WINDOW;
+    const TilePlan plan = plan_tiles(batch->max_cluster_bytes);
+    const int64_t n_tiles = (batch->payload_bytes + plan.window - 1) / plan.window;
     Workspace ws;
-    int32_t *tile_first = nullptr;
-    int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, ws, tile_first);
+    int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, ws);
     if (rc != GCB_OK) return rc;
     BatchView b = {batch->n_clusters, batch->n_pairs, batch->umi_words, batch->cluster_pair_off, batch->cluster_ref, batch->cluster_flags,
                    batch->umi, batch->reads, batch->cigar, batch->payload, batch->payload_bytes};
@@ -232,8 +275,7 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
     const unsigned grid_clusters = (unsigned)((batch->n_clusters + warps_per_cta - 1) / warps_per_cta);
     if (stages & GCB_STAGE_UMI_GROUP) {
         GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, stream));
-        GCB_LAUNCH(umi_group_kernel, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, (int32_t)TILE_WINDOW, tile_first,
-                   (int32_t)n_tiles);
+        GCB_LAUNCH(umi_group_kernel, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window, (int32_t)n_tiles);
         ctx->launches++;
     }
     if (stages & GCB_STAGE_SELECT_TEMPLATE) {
@@ -245,9 +287,12 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
         ctx->launches += 3;
     }
     if ((stages & GCB_STAGE_SCORE_VOTE) && n_tiles > 0) {
-        GCB_LAUNCH(score_vote_kernel, dim3((unsigned)n_tiles), dim3(VOTE_THREADS), VOTE_SMEM, stream, b, r, ws, ctx->genome, ctx->opt,
-                   (const int32_t *)tile_first);
-        ctx->launches++;
+        GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
+        GCB_LAUNCH(vote_tiled_kernel, dim3((unsigned)n_tiles), dim3(VT_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
+                   plan.slab_cap, fast_path_implied(ctx->opt));
+        const unsigned generic_grid = (unsigned)(n_tiles < 2 * 148 ? n_tiles : 2 * 148);
+        GCB_LAUNCH(score_vote_kernel, dim3(generic_grid), dim3(VOTE_THREADS), VOTE_SMEM, stream, b, r, ws, ctx->genome, ctx->opt);
+        ctx->launches += 2;
     }
     if (stages & GCB_STAGE_DUPLEX) {
         GCB_LAUNCH(duplex_kernel, dim3((unsigned)((batch->n_clusters + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream,
@@ -329,5 +374,15 @@ int gcb_consensus_batch(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *hr) {
 }
 
 int64_t gcb_launch_count(const gcb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+#ifdef GCB_SIMT_CHECK
+// tests only (CPU SIMT-check build): which vote path the tiles and columns took
+void gcb_simt_counters(int64_t *out, int reset) {
+    for (int k = 0; k < 4; k++) {
+        out[k] = g_simt_counters[k];
+        if (reset) g_simt_counters[k] = 0;
+    }
+}
+#endif
 
 }  // extern "C"

@@ -38,7 +38,7 @@ constexpr int GROUP_THREADS = 128;  // 4 clusters per CTA
 // unassigned pair within `thr` of it, in map (= pair) order.  Counts never need decrementing: pairs
 // carrying the same UMI are always absorbed together.
 __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, ResultView r, Workspace ws, int32_t tile_window,
-                                                                   int32_t *tile_first, int32_t n_tiles) {
+                                                                   int32_t n_tiles) {
     const int lane = lane_id();
     const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
     if (c >= b.n_clusters) return;
@@ -57,10 +57,12 @@ __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, R
             const int64_t prev = pp < b.n_pairs ? b.reads[2 * (int64_t)pp].data_off : b.payload_bytes;
             t_lo = prev / tile_window + 1;
         }
-        for (int64_t t = t_lo; t <= s / tile_window && t <= n_tiles; t++) tile_first[t] = c;
+        const TileDir here = {c, p0, s};
+        for (int64_t t = t_lo; t <= s / tile_window && t <= n_tiles; t++) ws.tile_dir[t] = here;
         if (c == b.n_clusters - 1) {
             ws.slab_off[c + 1] = b.payload_bytes;
-            for (int64_t t = s / tile_window + 1; t <= n_tiles; t++) tile_first[t] = b.n_clusters;
+            const TileDir end = {b.n_clusters, p1, b.payload_bytes};
+            for (int64_t t = s / tile_window + 1; t <= n_tiles; t++) ws.tile_dir[t] = end;
         }
     }
 
@@ -120,8 +122,62 @@ __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, R
 // ------------------------------------------------------------------------------------------------
 // group.cpp:136-313 for one side of one family: returns the template's read slot (or -1) and fills
 // vote_flags / side_mode for the vote kernel.  Called by a whole warp; the result is warp-uniform.
-GCB_DEV int side_select(const BatchView &b, const Workspace &ws, const gcb_options &o, int mb, int m, int side, int slot) {
+struct SideChoice {
+    int out;     // template read slot, -1 = NULL
+    int k;       // its index in the family
+    int len;     // voted columns (group.cpp:354-360)
+    bool fits;   // every VoteRead field fits its 16 bits
+};
+
+// The VoteRead of read slot sk (see device_common.cuh); `fits` is cleared when a field overflows.
+GCB_DEV VoteRead make_vote_read(const BatchView &b, const Workspace &ws, int64_t slab0, int sk, int side, uint8_t f, int l_out, bool left_mode,
+                                bool &fits) {
+    VoteRead v = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!(f & VOTE_PARTICIPATES)) return v;
+    const gcb_read_desc rd = b.reads[sk];
+    const int64_t off = rd.data_off - slab0;
+    const int d = (f & VOTE_LENDIFF0) ? 0 : rd.l_qseq - l_out;  // group.cpp:339-349
+    const int shift = left_mode ? 0 : d;
+    if (off < 0 || (off >> 2) > 0xFFFF || rd.l_qseq > 0x7FFF || shift < -0x8000 || shift > 0x7FFF) {
+        fits = false;
+        return v;
+    }
+    v.own_off4 = (uint16_t)(off >> 2);
+    v.own_l = (int16_t)rd.l_qseq;
+    v.shift = (int16_t)shift;
+    v.ov_len = VR_NO_OVERLAP_INFO;
+    const PairOverlap ov = ws.overlap[sk >> 1];
+    if (ov.valid) {
+        const gcb_read_desc md = b.reads[sk ^ 1];
+        const int64_t moff = md.data_off - slab0;
+        int64_t own = side == 0 ? ov.left_start : ov.right_start;
+        int64_t mate = side == 0 ? ov.right_start : ov.left_start;
+        int64_t len = ov.cmp_len;
+        const int64_t a = own > 0 ? own : 0;
+        const int64_t e = own + len < rd.l_qseq ? own + len : rd.l_qseq;
+        if (len > 0 && e > a) {  // the window clipped to this read's own indices
+            mate += a - own;
+            own = a;
+            len = e - a;
+        } else {
+            own = mate = len = 0;
+        }
+        if (moff < 0 || (moff >> 2) > 0xFFFF || md.l_qseq > 0x7FFF || mate < -0x8000 || mate > 0x7FFF) {
+            fits = false;
+            return v;
+        }
+        v.mate_off4 = (uint16_t)(moff >> 2);
+        v.mate_l = (int16_t)md.l_qseq;
+        v.ov_own = (int16_t)own;
+        v.ov_mate = (int16_t)mate;
+        v.ov_len = (int16_t)len;
+    }
+    return v;
+}
+
+GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gcb_options &o, int mb, int m, int side, int slot, int64_t slab0) {
     const int lane = lane_id();
+    const SideChoice none = {-1, 0, 0, true};
     const bool isLeft = side == 0;
     const int thr = o.skip_low_complexity_cluster_threshold;
 #define GCB_SLOT(k) (2 * ws.members[mb + (k)] + side)
@@ -151,7 +207,7 @@ GCB_DEV int side_select(const BatchView &b, const Workspace &ws, const gcb_optio
             for (int i = lane; i < rd.l_qseq - 1; i += WARP)
                 if (base_letter(base_at(seq, i)) != base_letter(base_at(seq, i + 1))) dn++;
             dn = warp_sum(dn);
-            if ((double)dn < rd.l_qseq * 0.5) return -1;
+            if ((double)dn < rd.l_qseq * 0.5) return none;
         }
     }
 
@@ -205,14 +261,21 @@ GCB_DEV int side_select(const BatchView &b, const Workspace &ws, const gcb_optio
             best_cnt = oc; best_len = ol; best_k = ok;
         }
     }
-    if ((double)best_cnt < m * 0.4 && m != 1) return -1;  // group.cpp:264
-    if (!GCB_HAVE(best_k)) return -1;                     // group.cpp:270-285
+    if ((double)best_cnt < m * 0.4 && m != 1) return none;  // group.cpp:264
+    if (!GCB_HAVE(best_k)) return none;                     // group.cpp:270-285
     const int out = GCB_SLOT(best_k);
     const gcb_read_desc od = b.reads[out];
 
     // group.cpp:287-313 (who votes) and 339-349 (whose length difference is ignored)
+    bool fits = true;
+    int mn = od.l_qseq;
+    VoteRead *vr = ws.vote_reads + 2 * (int64_t)mb + (int64_t)side * m;
     for (int k = lane; k < m; k += WARP) {
-        if (!GCB_HAVE(k)) continue;
+        const VoteRead zero = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (!GCB_HAVE(k)) {
+            vr[k] = zero;
+            continue;
+        }
         const int sk = GCB_SLOT(k);
         uint8_t f = 0;
         if (k == best_k) f = VOTE_PARTICIPATES;
@@ -225,9 +288,16 @@ GCB_DEV int side_select(const BatchView &b, const Workspace &ws, const gcb_optio
             }
         }
         ws.vote_flags[sk] = f;
+        if (f & VOTE_PARTICIPATES) mn = min(mn, b.reads[sk].l_qseq);
+        vr[k] = make_vote_read(b, ws, slab0, sk, side, f, od.l_qseq, leftReadMode, fits);
     }
     if (lane == 0) ws.side_mode[2 * (int64_t)slot + side] = leftReadMode ? SIDE_LEFT : SIDE_RIGHT;
-    return out;
+    SideChoice ch;
+    ch.out = out;
+    ch.k = best_k;
+    ch.len = od.n_cigar == 0 ? warp_min(mn) : od.l_qseq;  // group.cpp:354-360: no CIGAR => only the shortest read's columns
+    ch.fits = __all_sync(FULL, fits);
+    return ch;
 #undef GCB_SLOT
 #undef GCB_HAVE
 #undef GCB_CIG
@@ -272,6 +342,12 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
     }
     __syncwarp();
 
+    const int64_t slab0 = ws.slab_off[c];
+    for (int i = G + lane; i < n; i += WARP) {  // slots that hold no family
+        const FsDesc nofs = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0};
+        ws.fs_desc[2 * (int64_t)(p0 + i)] = nofs;
+        ws.fs_desc[2 * (int64_t)(p0 + i) + 1] = nofs;
+    }
     int64_t out_rel = 0;
     for (int g = 0; g < G; g++) {
         const int slot = p0 + g;
@@ -292,11 +368,20 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
         gr.umi_pair = -1;
         const int first = ws.members[mb];
         uint8_t mode0 = SIDE_NONE;
+        SideChoice ch[2] = {{-1, 0, 0, true}, {-1, 0, 0, true}};
         if (m == 1 && b.reads[2 * (int64_t)first + 1].l_qseq < 0) {  // group.cpp:73-77: passes through untouched
             gr.merge_reads = 1;
             if (b.reads[2 * (int64_t)first].l_qseq >= 0) {
                 gr.tmpl_read[0] = 2 * first;
                 mode0 = SIDE_COPY;
+                ch[0].out = 2 * first;
+                ch[0].len = b.reads[2 * (int64_t)first].l_qseq;
+                const VoteRead v = make_vote_read(b, ws, slab0, 2 * first, 0, VOTE_PARTICIPATES, ch[0].len, true, ch[0].fits);
+                if (lane == 0) {
+                    const VoteRead zero = {0, 0, 0, 0, 0, 0, 0, 0};
+                    ws.vote_reads[2 * (int64_t)mb] = v;
+                    ws.vote_reads[2 * (int64_t)mb + 1] = zero;
+                }
             }
             gr.umi_pair = first;
             if (lane == 0) {
@@ -324,8 +409,9 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
                 ws.side_mode[2 * (int64_t)slot + 1] = SIDE_NONE;
             }
             __syncwarp();
-            const int left = side_select(b, ws, o, mb, m, 0, slot);
-            const int right = side_select(b, ws, o, mb, m, 1, slot);
+            ch[0] = side_select(b, ws, o, mb, m, 0, slot, slab0);
+            ch[1] = side_select(b, ws, o, mb, m, 1, slot, slab0);
+            const int left = ch[0].out, right = ch[1].out;
             gr.tmpl_read[0] = left;
             gr.tmpl_read[1] = right;
             int name_slot;
@@ -340,10 +426,23 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
             }
             gr.umi_pair = name_slot >= 0 ? name_slot / 2 : -1;  // Pair::setLeft/setRight, pair.cpp:188-216
         }
+        __syncwarp();
         for (int s = 0; s < 2; s++) {
-            if (gr.tmpl_read[s] < 0) continue;
-            gr.out_off[s] = out_rel;  // cluster-relative; the vote kernel rebases it after the scan
-            out_rel += record_bytes(b.reads[gr.tmpl_read[s]].l_qseq);
+            FsDesc fd = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0};
+            if (gr.tmpl_read[s] >= 0) {
+                const int l_out = b.reads[gr.tmpl_read[s]].l_qseq;
+                gr.out_off[s] = out_rel;  // cluster-relative; the vote kernel rebases it after the scan
+                fd.mb_rel = (uint16_t)(mb - p0);
+                fd.m = (uint16_t)m;
+                fd.l_out = (uint16_t)l_out;
+                fd.len = (uint16_t)ch[s].len;
+                fd.tmpl_k = (uint16_t)ch[s].k;
+                fd.mode = s == 0 && mode0 == SIDE_COPY ? SIDE_COPY : ws.side_mode[2 * (int64_t)slot + s];
+                fd.out_rel = (uint32_t)out_rel;
+                if (!ch[s].fits || mb - p0 > 0xFFFF || m > 0xFFFF || l_out > 0x7FFF || out_rel > 0xFFFFFFFFll) fd.flags |= FS_NOFIT;
+                out_rel += record_bytes(l_out);
+            }
+            if (lane == 0) ws.fs_desc[2 * (int64_t)slot + s] = fd;
         }
         if (lane == 0) r.groups[slot] = gr;
     }

@@ -1,12 +1,14 @@
-// k_score_vote.cuh — the hot kernel: Pair::computeScore (pair.cpp:88-172) fused with
-// Group::makeConsensus (group.cpp:320-579).
+// k_score_vote.cuh — the GENERIC vote kernel: Pair::computeScore (pair.cpp:88-172) fused with
+// Group::makeConsensus (group.cpp:320-579) for the tiles the tiled kernel (k_vote_tiled.cuh) cannot
+// take: clusters larger than its staging buffer, tiles with more pairs than its tables hold, fields
+// that overflow its 16-bit table slots.  It has no size limits at all.
 //
 // Work decomposition
-//   CTA   = one tile of consecutive clusters: the clusters whose slab starts inside a window of
-//           TILE_WINDOW payload bytes.  Their slabs are one contiguous byte range, staged into
-//           shared memory with a single bulk asynchronous copy (cp.async.bulk -> UBLKCP) that
-//           completes on an mbarrier.  A cluster larger than the staging buffer is voted straight
-//           from global memory by the same code (generic pointers).
+//   CTA   = loops over the tiles listed in ws.generic_tiles.  A tile's clusters are one contiguous
+//           byte range of the payload; runs of clusters that fit the staging buffer are staged
+//           into shared memory with a single bulk asynchronous copy (cp.async.bulk -> UBLKCP)
+//           that completes on an mbarrier.  A cluster larger than the staging buffer is voted
+//           straight from global memory by the same code (generic pointers).
 //   warp  = one cluster at a time (dynamic counter); inside it one (family, side) after another.
 //   lane  = one column of the template per pass of 32 columns.
 // Scores are never materialised: each (column, read) recomputes the overlap score and the rewritten
@@ -19,7 +21,6 @@
 namespace gcb {
 
 constexpr int VOTE_THREADS = 128;
-constexpr int TILE_WINDOW = 16 * 1024;  // payload bytes whose clusters form one tile
 constexpr int SLAB_CAP = 40 * 1024;     // staging buffer; tile overflow is handled by sub-tiling
 constexpr int VOTE_SMEM = SLAB_CAP + 64;
 
@@ -434,8 +435,7 @@ GCB_DEV void vote_family_side(const BatchView &b, const ResultView &r, const Wor
     }
 }
 
-__global__ void __launch_bounds__(VOTE_THREADS) score_vote_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o,
-                                                                  const int32_t *tile_first) {
+__global__ void __launch_bounds__(VOTE_THREADS) score_vote_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o) {
     GCB_DYN_SMEM(smem);
     uint64_t *bar = (uint64_t *)smem;
     int *counter = (int *)(smem + 8);
@@ -443,11 +443,13 @@ __global__ void __launch_bounds__(VOTE_THREADS) score_vote_kernel(BatchView b, R
     uint8_t *slab = smem + 64;
     const int lane = lane_id();
     const int tid = (int)threadIdx.x;
-    const int c0 = tile_first[blockIdx.x], c1 = tile_first[blockIdx.x + 1];
-    if (c0 >= c1) return;
     if (tid == 0) tile_barrier_init(bar);
     __syncthreads();
     uint32_t parity = 0;
+    const int n_generic = *ws.generic_count;
+    for (int gi = (int)blockIdx.x; gi < n_generic; gi += (int)gridDim.x) {
+    const int tile = ws.generic_tiles[gi];
+    const int c0 = ws.tile_dir[tile].c0, c1 = ws.tile_dir[tile + 1].c0;
     int cs = c0;
     while (cs < c1) {
         // the longest run of clusters starting at cs whose slabs fit the staging buffer
@@ -488,6 +490,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) score_vote_kernel(BatchView b, R
         }
         __syncthreads();
         cs = ce;
+    }
     }
 }
 

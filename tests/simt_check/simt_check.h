@@ -304,6 +304,27 @@ inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return (unsigned)(v >> (shift & 31));
 }
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (unsigned)((v << (shift & 31)) >> 32);
+}
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    uint64_t v = ((uint64_t)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
+inline unsigned __vmaxu4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= std::max((a >> (8 * i)) & 0xFFu, (b >> (8 * i)) & 0xFFu) << (8 * i);
+    return r;
+}
+inline unsigned __vcmpgeu4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++)
+        if (((a >> (8 * i)) & 0xFFu) >= ((b >> (8 * i)) & 0xFFu)) r |= 0xFFu << (8 * i);
+    return r;
+}
 using std::max;
 using std::min;
 
@@ -311,6 +332,8 @@ template <typename T>
 inline T atomicAdd(T *p, T v) { T old = *p; *p = old + v; return old; }
 template <typename T>
 inline T atomicMax(T *p, T v) { T old = *p; if (v > old) *p = v; return old; }
+template <typename T>
+inline T atomicXor(T *p, T v) { T old = *p; *p = old ^ v; return old; }
 template <typename T>
 inline T atomicCAS(T *p, T cmp, T v) { T old = *p; if (old == cmp) *p = v; return old; }
 inline void __threadfence() {}

@@ -1,6 +1,7 @@
 """The kernel source itself (gencore_b200/csrc/*.cu*), compiled by g++ against the SIMT interpreter in
 tests/simt_check/, executed on the CPU and compared bit-for-bit with the oracle.  This is a check of the
 kernels' LOGIC on a box without a GPU; the same comparisons run on the real library in test_gpu_parity.py."""
+import ctypes
 import os
 import sys
 
@@ -12,6 +13,7 @@ from parity import assert_results_equal
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt_check"))
 
 CASES = parity_cases.small_cases()
+COVERAGE = {}
 
 
 @pytest.fixture(scope="module")
@@ -24,7 +26,24 @@ def simt_lib():
 def test_kernels_match_oracle_under_simt_check(simt_lib, oracle, name, thunk):
     from gencore_b200.engine import ConsensusEngine
     batch, genome, opt = thunk()
+    cnt = (ctypes.c_int64 * 4)()
     with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
         eng.set_reference(genome)
+        eng.lib.gcb_simt_counters(cnt, 1)
         res = eng.cluster_by_umi(batch)
+        eng.lib.gcb_simt_counters(cnt, 1)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
+    tiled, generic, cols, slow = list(cnt)
+    COVERAGE[name] = (tiled, generic, cols, slow)
+    if name in ("deep_1100", "low_complexity"):
+        assert generic > 0, "the >1000-pair clusters must take the generic kernel"
+    elif batch.n_pairs > 0:
+        assert tiled > 0 and generic == 0, (tiled, generic)
+    if name.startswith(("cfg1", "cfg2", "cfg3")):
+        assert 0 < slow < 0.2 * cols, "the fixed-length shapes must mostly take the fast columns"
+
+
+def test_both_column_paths_are_exercised():
+    assert COVERAGE, "runs after the parametrised cases"
+    assert sum(v[2] - v[3] for v in COVERAGE.values()) > 0 and sum(v[3] for v in COVERAGE.values()) > 0
+    print({k: v for k, v in COVERAGE.items()})
