@@ -203,17 +203,21 @@ def b200_arm(args):
 
     db = DeviceBatch.from_host(batch, dev)
     dr = DeviceResult.allocate(batch.n_pairs, batch.n_clusters, len(batch.payload) // 4 + 4096, dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # the kernels are launched on this (non-default) stream and the CUDA events are recorded on it
+    tstream = torch.cuda.Stream(device=dev)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    torch.cuda.synchronize()
     stages = [STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_SCORE_VOTE, STAGE_DUPLEX]
     names = ["umi_group", "select_template+scan", "score_vote", "duplex"]
 
     def step(events=None):
         for k, st in enumerate(stages):
             if events is not None:
-                events[k].record()
+                events[k].record(tstream)
             eng.cluster_by_umi_device(db.struct, dr.struct, st, stream)
         if events is not None:
-            events[len(stages)].record()
+            events[len(stages)].record(tstream)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -228,10 +232,10 @@ def b200_arm(args):
     barrier()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record()
+    t_start.record(tstream)
     for k in range(args.steps):
         step(evs[k])
-    t_end.record()
+    t_end.record(tstream)
     barrier()
     launches = eng.launches - launches0
     total_ms = t_start.elapsed_time(t_end)

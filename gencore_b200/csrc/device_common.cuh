@@ -22,7 +22,7 @@ struct PairOverlap {   // Pair::computeScore's overlap window (pair.cpp:103-119)
 
 // One read as the tiled vote kernel sees it (16 bytes, staged into shared memory by a bulk copy).
 // Offsets are in 4-byte units relative to the cluster's slab.  own_l == 0: the read does not vote.
-struct VoteRead {
+struct __align__(16) VoteRead {
     uint16_t own_off4;   // record of this read
     uint16_t mate_off4;  // record of its mate (valid with VR_OVERLAP)
     int16_t own_l;       // l_qseq of this read, 0 = no vote
@@ -35,7 +35,7 @@ struct VoteRead {
 constexpr int VR_NO_OVERLAP_INFO = -1;
 
 // One (family, side) for the tiled vote kernel (16 bytes).
-struct FsDesc {
+struct __align__(16) FsDesc {
     uint16_t mb_rel;   // members index of the family's first pair, relative to the cluster's first pair
     uint16_t m;        // pairs in the family
     uint16_t l_out;    // template l_qseq
@@ -47,7 +47,7 @@ struct FsDesc {
 };
 constexpr uint8_t FS_NOFIT = 1;  // some field does not fit its 16 bits: the tile goes to the generic kernel
 
-struct TileDir {
+struct __align__(16) TileDir {
     int32_t c0;      // first cluster of the tile
     int32_t p0;      // its first pair
     int64_t slab0;   // payload offset of its slab

@@ -43,7 +43,7 @@ static_assert(VT_OFF_FS % 16 == 0 && VT_OFF_VR % 16 == 0, "bulk copy destination
 constexpr int VT_MAX_SLAB = 200 * 1024;  // cbase4 / out4 are 16-bit counts of 4-byte units
 
 // FsDesc rewritten in place for the tile (still 16 bytes)
-struct FsTile {
+struct __align__(16) FsTile {
     uint16_t ent0;    // first VoteRead of this family side in the tile's table
     uint16_t m;
     uint16_t l_out;
@@ -486,12 +486,16 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
                 mq1 = __vmaxu4(mq1, q1);
                 dis |= (be ^ tbe) & nib_range(a, z);
                 if (v.ov_len > 0) {  // pair.cpp:133-170: a base that differs from its mate's is never a fast column
-                    const int dm = (int)v.ov_mate - (int)v.ov_own;
-                    const int oa = max(a, max((int)v.ov_own - rp0, -dm - rp0));
-                    const int oz = min(z, min((int)v.ov_own + (int)v.ov_len - rp0, (int)v.mate_l - dm - rp0));
+                    // chunk column k pairs own index rp0+k with mate index k - y.  (Written with subtractions only:
+                    // ptxas 12.9 dropped the negation when it folded max(a, max(x, -t)) into one VIMNMX3 on sm_100a —
+                    // the PTX was right, the SASS and the B200 were not; profiles/r01_notes.md has the listing.)
+                    const int x = (int)v.ov_own - rp0;   // first chunk column inside the overlap window
+                    const int y = x - (int)v.ov_mate;    // first chunk column whose mate index is >= 0
+                    const int oa = max(max(a, x), y);
+                    const int oz = min(min(z, x + (int)v.ov_len), y + (int)v.mate_l);
                     if (oz > oa) {
                         const uint8_t *mrec = cb + 4 * (int)v.mate_off4;
-                        const uint32_t mbe = fetch8b(mrec + GCB_ALIGN4(v.mate_l), GCB_ALIGN4((v.mate_l + 1) >> 1), rp0 + dm);
+                        const uint32_t mbe = fetch8b(mrec + GCB_ALIGN4(v.mate_l), GCB_ALIGN4((v.mate_l + 1) >> 1), 0 - y);
                         dis |= (be ^ mbe) & nib_range(oa, oz);
                     }
                 }
