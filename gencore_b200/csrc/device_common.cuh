@@ -34,7 +34,7 @@ struct __align__(16) VoteRead {
 };
 constexpr int VR_NO_OVERLAP_INFO = -1;
 
-// One (family, side) for the tiled vote kernel (16 bytes).
+// One (family, side) for the tiled vote kernel (32 bytes, index 2*slot+side).
 struct __align__(16) FsDesc {
     uint16_t mb_rel;   // members index of the family's first pair, relative to the cluster's first pair
     uint16_t m;        // pairs in the family
@@ -44,8 +44,15 @@ struct __align__(16) FsDesc {
     uint8_t mode;      // SIDE_*
     uint8_t flags;     // FS_*
     uint32_t out_rel;  // consensus record offset relative to the cluster's output
+    int32_t pos;       // template core.pos
+    int32_t tmpl;      // template read slot
+    uint32_t reserved[2];
 };
-constexpr uint8_t FS_NOFIT = 1;  // some field does not fit its 16 bits: the tile goes to the generic kernel
+constexpr uint8_t FS_NOFIT = 1;         // some field does not fit its 16 bits: the tile goes to the generic kernel
+constexpr uint8_t FS_REF_OK = 2;        // group.cpp:362-367 + reference.cpp:33-71: the vote may consult the reference
+constexpr uint8_t FS_SIMPLE_CIGAR = 4;  // template CIGAR is one M/=/X op covering the read: BamUtil::getRefOffset(i) == i
+constexpr uint8_t FS_UNIFORM = 8;       // (set by the vote kernel) every voter has the template's geometry
+constexpr uint16_t VR_NO_VOTE = 0xFFFFu;  // VoteRead.own_off4 of a read that does not vote
 
 struct __align__(16) TileDir {
     int32_t c0;      // first cluster of the tile

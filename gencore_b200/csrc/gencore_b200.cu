@@ -82,7 +82,7 @@ struct TilePlan {
     int32_t window, slab_cap, smem;
 };
 TilePlan plan_tiles(int32_t max_cluster_bytes) {
-    const int32_t KB = 1024, budget = 227 * KB, tables = VT_OFF_SLAB + 1 * KB;  // + the 1 KB per-CTA reserve
+    const int32_t KB = 1024, budget = 227 * KB, tables = VT_OFF_SLAB + VT_SLAB_SLACK + 1 * KB;  // + the 1 KB per-CTA reserve
     int32_t maxc = max_cluster_bytes > 0 ? ((max_cluster_bytes + 127) & ~127) : 16 * KB;
     TilePlan p;
     if (32 * KB + maxc + tables <= budget / 3) p.window = 32 * KB;
@@ -91,7 +91,7 @@ TilePlan plan_tiles(int32_t max_cluster_bytes) {
     p.slab_cap = p.window + maxc;
     if (p.slab_cap > VT_MAX_SLAB) p.slab_cap = VT_MAX_SLAB;
     if (p.slab_cap + tables > budget) p.slab_cap = (budget - tables) & ~127;
-    p.smem = VT_OFF_SLAB + p.slab_cap;
+    p.smem = VT_OFF_SLAB + p.slab_cap + VT_SLAB_SLACK;
     return p;
 }
 
@@ -281,7 +281,7 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
     if (stages & GCB_STAGE_SELECT_TEMPLATE) {
         const int32_t n_scan = (int32_t)((batch->n_clusters + SCAN_BLOCK - 1) / SCAN_BLOCK);
         GCB_CUDA(ctx, cudaMemsetAsync(result->groups, 0, sizeof(gcb_group_result) * (size_t)batch->n_pairs, stream));
-        GCB_LAUNCH(select_template_kernel, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->opt);
+        GCB_LAUNCH(select_template_kernel, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
         GCB_LAUNCH(scan_local_kernel, dim3((unsigned)n_scan), dim3(SCAN_THREADS), 0, stream, ws, batch->n_clusters);
         GCB_LAUNCH(scan_blocks_kernel, dim3(1), dim3(WARP), 0, stream, ws, n_scan, result->out_bytes, result->out_capacity);
         ctx->launches += 3;
@@ -378,7 +378,7 @@ int64_t gcb_launch_count(const gcb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 #ifdef GCB_SIMT_CHECK
 // tests only (CPU SIMT-check build): which vote path the tiles and columns took
 void gcb_simt_counters(int64_t *out, int reset) {
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 6; k++) {
         out[k] = g_simt_counters[k];
         if (reset) g_simt_counters[k] = 0;
     }

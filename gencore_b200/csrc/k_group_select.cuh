@@ -132,13 +132,13 @@ struct SideChoice {
 // The VoteRead of read slot sk (see device_common.cuh); `fits` is cleared when a field overflows.
 GCB_DEV VoteRead make_vote_read(const BatchView &b, const Workspace &ws, int64_t slab0, int sk, int side, uint8_t f, int l_out, bool left_mode,
                                 bool &fits) {
-    VoteRead v = {0, 0, 0, 0, 0, 0, 0, 0};
+    VoteRead v = {VR_NO_VOTE, 0, 0, 0, 0, 0, 0, 0};
     if (!(f & VOTE_PARTICIPATES)) return v;
     const gcb_read_desc rd = b.reads[sk];
     const int64_t off = rd.data_off - slab0;
     const int d = (f & VOTE_LENDIFF0) ? 0 : rd.l_qseq - l_out;  // group.cpp:339-349
     const int shift = left_mode ? 0 : d;
-    if (off < 0 || (off >> 2) > 0xFFFF || rd.l_qseq > 0x7FFF || shift < -0x8000 || shift > 0x7FFF) {
+    if (off < 0 || (off >> 2) >= VR_NO_VOTE || rd.l_qseq > 0x7FFF || shift < -0x8000 || shift > 0x7FFF) {
         fits = false;
         return v;
     }
@@ -271,7 +271,7 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
     int mn = od.l_qseq;
     VoteRead *vr = ws.vote_reads + 2 * (int64_t)mb + (int64_t)side * m;
     for (int k = lane; k < m; k += WARP) {
-        const VoteRead zero = {0, 0, 0, 0, 0, 0, 0, 0};
+        const VoteRead zero = {VR_NO_VOTE, 0, 0, 0, 0, 0, 0, 0};
         if (!GCB_HAVE(k)) {
             vr[k] = zero;
             continue;
@@ -304,7 +304,7 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
 }
 
 // group.cpp:68-134 per family of the cluster + the per-pair overlap windows of pair.cpp:103-119
-__global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o) {
+__global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o) {
     const int lane = lane_id();
     const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
     if (c >= b.n_clusters) return;
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
 
     const int64_t slab0 = ws.slab_off[c];
     for (int i = G + lane; i < n; i += WARP) {  // slots that hold no family
-        const FsDesc nofs = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0};
+        const FsDesc nofs = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, {0, 0}};
         ws.fs_desc[2 * (int64_t)(p0 + i)] = nofs;
         ws.fs_desc[2 * (int64_t)(p0 + i) + 1] = nofs;
     }
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
                 ch[0].len = b.reads[2 * (int64_t)first].l_qseq;
                 const VoteRead v = make_vote_read(b, ws, slab0, 2 * first, 0, VOTE_PARTICIPATES, ch[0].len, true, ch[0].fits);
                 if (lane == 0) {
-                    const VoteRead zero = {0, 0, 0, 0, 0, 0, 0, 0};
+                    const VoteRead zero = {VR_NO_VOTE, 0, 0, 0, 0, 0, 0, 0};
                     ws.vote_reads[2 * (int64_t)mb] = v;
                     ws.vote_reads[2 * (int64_t)mb + 1] = zero;
                 }
@@ -428,9 +428,24 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
         }
         __syncwarp();
         for (int s = 0; s < 2; s++) {
-            FsDesc fd = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0};
+            FsDesc fd = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, {0, 0}};
             if (gr.tmpl_read[s] >= 0) {
-                const int l_out = b.reads[gr.tmpl_read[s]].l_qseq;
+                const gcb_read_desc od = b.reads[gr.tmpl_read[s]];
+                const int l_out = od.l_qseq;
+                fd.pos = od.pos;
+                fd.tmpl = gr.tmpl_read[s];
+                const uint32_t *ocig = b.cigar + od.cigar_off;
+                if (od.isize != 0 && gv.packed4) {  // group.cpp:362-367 + reference.cpp:33-71
+                    const int contig = b.cluster_ref[c];
+                    if (contig >= 0 && contig < gv.n_contigs) {
+                        const int64_t span = (int64_t)get_ref_offset(ocig, od.n_cigar, ch[s].len - 1) + 1;
+                        if ((int64_t)od.pos + span < gv.contig_len[contig]) fd.flags |= FS_REF_OK;
+                    }
+                }
+                if (od.n_cigar == 1) {
+                    const int op = cig_op(ocig[0]);
+                    if (query_consum(op) && ref_consum(op) && cig_len(ocig[0]) >= l_out) fd.flags |= FS_SIMPLE_CIGAR;
+                }
                 gr.out_off[s] = out_rel;  // cluster-relative; the vote kernel rebases it after the scan
                 fd.mb_rel = (uint16_t)(mb - p0);
                 fd.m = (uint16_t)m;

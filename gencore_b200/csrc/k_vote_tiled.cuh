@@ -1,22 +1,25 @@
 // k_vote_tiled.cuh — the hot kernel: Pair::computeScore (pair.cpp:88-172) fused with
-// Group::makeConsensus (group.cpp:320-579), eight template columns per thread.
+// Group::makeConsensus (group.cpp:320-579), sixteen template columns per lane.
 //
 // Work decomposition
-//   CTA    = one tile: the consecutive clusters whose slab starts inside a window of the payload.
-//            Three bulk asynchronous copies (cp.async.bulk -> UBLKCP, one mbarrier) stage the tile's
-//            payload slab, its VoteRead table and its FsDesc table into shared memory; nothing else
-//            of the batch is read on the common path.
-//   thread = one item = eight consecutive columns of one (family, side): two 32-bit words of
-//            qualities and one 32-bit word of 4-bit bases per read, compared and reduced with
-//            SIMD-in-word arithmetic (no per-base loop, no warp shuffles).
-// A column is FAST when every voting read shows the template's base there, no read disagrees with its
-// mate inside the pair overlap, and the best quality reaches moderateQuality.  With the options for
-// which that implies topScore >= baseScoreReq (`implied`, true for the reference's defaults) such a
-// column is exactly group.cpp:421-427: second bin empty, only the quality (the maximum) is written.
-// Every other column is SLOW: it is queued and decided by slow_column(), a literal per-read,
-// per-bin restatement of group.cpp:376-525 that shares column_top()/column_arbitrate() with the
-// generic kernel.  Tiles that do not fit the tables (huge clusters, thousands of tiny reads) are
-// handed to score_vote_kernel (k_score_vote.cuh) through ws.generic_tiles.
+//   CTA    = one tile: the consecutive clusters whose slab starts inside a window of the payload.  Two bulk
+//            asynchronous copies (cp.async.bulk -> UBLKCP, one mbarrier) stage the tile's payload slab and
+//            its VoteRead table in shared memory while the threads fetch the tile's FsDesc entries.
+//   warp   = one bundle of family sides at a time (dynamic counter): L lanes per family side, L = the
+//            tile's widest record in 16-column chunks, so three 150-base family sides share a warp.
+//   lane   = sixteen consecutive columns of one family side: four 32-bit words of qualities and two words
+//            of 4-bit bases per read, reduced with SIMD-in-word arithmetic; no per-base loop, no shuffles.
+// A column is FAST when every voting read shows the template's base there, no read disagrees with its mate
+// inside the pair overlap, and the best quality reaches moderateQuality.  With options for which that
+// implies topScore >= baseScoreReq (`implied`, true for the reference's defaults) such a column is exactly
+// group.cpp:421-427: second bin empty, only the quality (the maximum) is written.  Every other column is
+// SLOW: it is queued, its reads are histogrammed into the sixteen bins of group.cpp:376-393 by eight
+// threads per column (shared-memory atomics) and one thread per column then applies group.cpp:395-525
+// through column_top()/column_arbitrate(), the same functions the generic kernel uses.
+// Families whose voters all share the template's geometry (same length, no column shift, same overlap
+// window: every fixed-length library) run a loop whose masks are hoisted out (FS_UNIFORM).
+// Tiles that do not fit the tables (huge clusters, reads longer than 512, 16-bit field overflow) are handed
+// to score_vote_kernel (k_score_vote.cuh) through ws.generic_tiles.
 #pragma once
 
 #include "k_score_vote.cuh"
@@ -24,41 +27,53 @@
 namespace gcb {
 
 constexpr int VT_THREADS = 256;
-constexpr int VT_MAX_PAIRS = VT_THREADS;  // pair positions of a tile: one thread each in the prologue
-constexpr int VT_SLOW_CAP = 1024;         // queued slow columns; more are decided inline by their owner
+constexpr int VT_WARPS = VT_THREADS / WARP;
+constexpr int VT_MAX_PAIRS = VT_THREADS;     // pair positions of a tile (one thread each in the prologue)
+constexpr int VT_MAX_FS = 256;               // family sides of a tile
+constexpr int VT_SLOW_CAP = 512;             // queued slow columns; more are decided inline by their owner
+constexpr int VT_BIN_COLS = VT_THREADS / 8;  // slow columns histogrammed per pass (eight threads each)
+constexpr int VT_CHUNK = 16;                 // columns per lane
 
 // shared-memory map (bytes)
 constexpr int VT_OFF_BAR = 0;
 constexpr int VT_OFF_NSLOW = 8;
 constexpr int VT_OFF_NOFIT = 12;
-constexpr int VT_OFF_WSUM = 16;                                   // 8 warp totals of the chunk scan
-constexpr int VT_OFF_CPO = 64;                                    // int32[VT_MAX_PAIRS + 2]
-constexpr int VT_OFF_CHUNK0 = VT_OFF_CPO + 4 * (VT_MAX_PAIRS + 2 + 14);   // uint32[2*VT_MAX_PAIRS + 1]
-constexpr int VT_OFF_ACC = VT_OFF_CHUNK0 + 4 * (2 * VT_MAX_PAIRS + 4);    // int32[2*VT_MAX_PAIRS]
-constexpr int VT_OFF_SLOW = VT_OFF_ACC + 4 * 2 * VT_MAX_PAIRS;            // uint32[VT_SLOW_CAP]
-constexpr int VT_OFF_FS = VT_OFF_SLOW + 4 * VT_SLOW_CAP;                  // FsDesc/FsTile[2*VT_MAX_PAIRS]
-constexpr int VT_OFF_VR = VT_OFF_FS + 16 * 2 * VT_MAX_PAIRS;              // VoteRead[2*VT_MAX_PAIRS]
+constexpr int VT_OFF_NFS = 16;
+constexpr int VT_OFF_NEXT = 20;
+constexpr int VT_OFF_LMAX = 24;
+constexpr int VT_OFF_WSUM = 32;                                  // VT_WARPS warp totals of the compaction scan
+constexpr int VT_OFF_CPO = 64;                                   // int32[VT_MAX_PAIRS + 2]
+constexpr int VT_OFF_ACC = VT_OFF_CPO + 4 * (VT_MAX_PAIRS + 8);  // int32[VT_MAX_FS]
+constexpr int VT_OFF_SLOW = VT_OFF_ACC + 4 * VT_MAX_FS;          // uint32[VT_SLOW_CAP]
+constexpr int VT_OFF_BINS = VT_OFF_SLOW + 4 * VT_SLOW_CAP;       // int32[VT_BIN_COLS][16][4]
+constexpr int VT_OFF_FT = VT_OFF_BINS + 4 * VT_BIN_COLS * 64;    // FsTile[VT_MAX_FS]
+constexpr int VT_OFF_VR = VT_OFF_FT + 32 * VT_MAX_FS;            // VoteRead[2*VT_MAX_PAIRS]
 constexpr int VT_OFF_SLAB = (VT_OFF_VR + 16 * 2 * VT_MAX_PAIRS + 127) & ~127;
-static_assert(VT_OFF_FS % 16 == 0 && VT_OFF_VR % 16 == 0, "bulk copy destinations are 16-byte aligned");
+constexpr int VT_SLAB_SLACK = 64;  // the hoisted loop reads whole words past a record's end (masked afterwards)
+static_assert(VT_OFF_FT % 16 == 0 && VT_OFF_VR % 16 == 0 && VT_OFF_BINS % 16 == 0, "16-byte aligned tables");
 constexpr int VT_MAX_SLAB = 200 * 1024;  // cbase4 / out4 are 16-bit counts of 4-byte units
 
-// FsDesc rewritten in place for the tile (still 16 bytes)
+// a family side as the tile sees it (shared memory only)
 struct __align__(16) FsTile {
-    uint16_t ent0;    // first VoteRead of this family side in the tile's table
+    uint16_t ent0;      // first VoteRead of this family side in the tile's table
     uint16_t m;
     uint16_t l_out;
     uint16_t len;
     uint16_t tmpl_k;
     uint8_t mode;
     uint8_t flags;
-    uint16_t cbase4;  // the cluster's slab inside the staged tile, 4-byte units
-    uint16_t out4;    // consensus record relative to the tile's first output byte, 4-byte units
+    uint16_t cbase4;    // the cluster's slab inside the staged tile, 4-byte units
+    uint16_t out4;      // consensus record relative to the tile's first output byte, 4-byte units
+    int64_t ref_nib0;   // nibble index of the template's pos in the packed genome (FS_REF_OK)
+    int32_t ref_limit;  // contig length - pos: reference offsets below it exist
+    int32_t tmpl;       // template read slot; its low bit is the side
 };
-static_assert(sizeof(FsTile) == 16 && sizeof(FsDesc) == 16 && sizeof(VoteRead) == 16, "table entries are 16 bytes");
+static_assert(sizeof(FsTile) == 32 && sizeof(FsDesc) == 32 && sizeof(VoteRead) == 16, "table entry sizes");
 
-// coverage counters of the CPU SIMT-check build (tests only): tiled tiles, generic tiles, fast columns, slow columns
+// coverage counters of the CPU SIMT-check build (tests only): tiled tiles, generic tiles, voted columns, slow columns,
+// uniform family sides, non-uniform family sides
 #ifdef GCB_SIMT_CHECK
-inline int64_t g_simt_counters[4] = {0, 0, 0, 0};
+inline int64_t g_simt_counters[6] = {0, 0, 0, 0, 0, 0};
 #define GCB_COUNT(k, n) (g_simt_counters[k] += (n))
 #else
 #define GCB_COUNT(k, n) ((void)0)
@@ -79,47 +94,49 @@ inline void tile_copy(void *dst, const void *src, uint32_t bytes, uint64_t *) { 
 #endif
 
 // ---- SIMD-in-word helpers ------------------------------------------------------------------------------
+// Bases travel as big-endian nibble words: column k of an 8-column word sits in bits 28-4k..31-4k.
+// Qualities stay little-endian: column k of a 4-column word is byte k.
 GCB_DEV uint32_t bswap32(uint32_t w) { return __byte_perm(w, 0, 0x0123); }
-// columns [a, b) of a chunk, 0 <= a <= b <= 8, as a mask over the big-endian nibble word (column k = bits 28-4k..31-4k)
-GCB_DEV uint32_t nib_range(int a, int b) {
-    const uint32_t hi = a >= 8 ? 0u : (0xFFFFFFFFu >> (4 * a));
-    const uint32_t lo = b >= 8 ? 0u : (0xFFFFFFFFu >> (4 * b));
-    return hi & ~lo;
+GCB_DEV int clamp_int(int v, int lo, int hi) { return min(max(v, lo), hi); }
+// columns >= s of an 8-column nibble word (s is clamped to 0..8)
+GCB_DEV uint32_t nib_ge(int s) { return __funnelshift_rc(0xFFFFFFFFu, 0u, 4u * (unsigned)clamp_int(s, 0, 8)); }
+// columns [a, z) of an 8-column nibble word
+GCB_DEV uint32_t nib_range(int a, int z) { return nib_ge(a) & ~nib_ge(z); }
+// a nibble mask (all-ones or all-zero nibbles) widened to the byte masks of its columns 0-3 and 4-7
+GCB_DEV uint32_t bytes_lo(uint32_t nm) { return __byte_perm(nm, nm << 4, 0xEAFB); }
+GCB_DEV uint32_t bytes_hi(uint32_t nm) { return __byte_perm(nm, nm << 4, 0xC8D9); }
+// byte flags (0xFF / 0x00) of columns 0-3 (a) and 4-7 (b) narrowed to a nibble mask
+GCB_DEV uint32_t nibs_of_bytes(uint32_t a, uint32_t b) {
+    return (__byte_perm(a, b, 0x0246) & 0xF0F0F0F0u) | (__byte_perm(a, b, 0x1357) & 0x0F0F0F0Fu);
 }
-// bytes [a, b) of a little-endian word, arguments clamped to 0..4
-GCB_DEV uint32_t byte_range(int a, int b) {
-    a = max(a, 0);
-    b = min(b, 4);
-    if (b <= a) return 0u;
-    const uint32_t lo = 0xFFFFFFFFu << (8 * a);  // a <= 3 here
-    const uint32_t hi = b >= 4 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu << (8 * b));
-    return lo & hi;
-}
-// eight qualities at read positions rp0..rp0+7 of a record whose quality area holds qbytes bytes; outside reads as 0
-GCB_DEV void fetch8q(const uint8_t *rec, int qbytes, int rp0, uint32_t &q0, uint32_t &q1) {
+// one word of a record area of nw words, outside reads as 0
+GCB_DEV uint32_t word_or_zero(const uint32_t *p, int w, int nw) { return (unsigned)w < (unsigned)nw ? p[w] : 0u; }
+
+// sixteen qualities at read positions rp0..rp0+15 (any alignment, any sign); positions outside the area read as 0
+GCB_DEV void fetch16q(const uint8_t *rec, int qbytes, int rp0, uint32_t q[4]) {
     const uint32_t *p = (const uint32_t *)rec;
     const int nw = qbytes >> 2, w0 = rp0 >> 2;
     const unsigned sh = (unsigned)(rp0 & 3) * 8u;
-    const uint32_t a = (unsigned)w0 < (unsigned)nw ? p[w0] : 0u;
-    const uint32_t c = (unsigned)(w0 + 1) < (unsigned)nw ? p[w0 + 1] : 0u;
-    const uint32_t d = (unsigned)(w0 + 2) < (unsigned)nw ? p[w0 + 2] : 0u;
-    q0 = __funnelshift_r(a, c, sh);
-    q1 = __funnelshift_r(c, d, sh);
+    uint32_t w[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) w[k] = word_or_zero(p, w0 + k, nw);
+#pragma unroll
+    for (int k = 0; k < 4; k++) q[k] = __funnelshift_r(w[k], w[k + 1], sh);
 }
-// eight base codes at read positions rp0..rp0+7 as a big-endian nibble word; seq area holds sbytes bytes
-GCB_DEV uint32_t fetch8b(const uint8_t *seq, int sbytes, int rp0) {
+// sixteen base codes at read positions rp0..rp0+15 as two big-endian nibble words
+GCB_DEV void fetch16b(const uint8_t *seq, int sbytes, int rp0, uint32_t &b0, uint32_t &b1) {
     const uint32_t *p = (const uint32_t *)seq;
     const int nw = sbytes >> 2, w0 = rp0 >> 3;
     const unsigned sh = (unsigned)(rp0 & 7) * 4u;
-    const uint32_t a = (unsigned)w0 < (unsigned)nw ? bswap32(p[w0]) : 0u;
-    const uint32_t c = (unsigned)(w0 + 1) < (unsigned)nw ? bswap32(p[w0 + 1]) : 0u;
-    return __funnelshift_l(c, a, sh);
+    const uint32_t a = bswap32(word_or_zero(p, w0, nw)), c = bswap32(word_or_zero(p, w0 + 1, nw)), d = bswap32(word_or_zero(p, w0 + 2, nw));
+    b0 = __funnelshift_l(c, a, sh);
+    b1 = __funnelshift_l(d, c, sh);
 }
 
 // base, rewritten quality and score of one read at template column i: pair.cpp:88-172 for one base,
 // from the staged tables (the same function of the same bytes as fetch_base in k_score_vote.cuh)
 GCB_DEV bool fetch_ent(const uint8_t *cb, const VoteRead &v, int i, int side, const gcb_options &o, int &base, int &qual, int &score) {
-    if (v.own_l == 0) return false;
+    if (v.own_off4 == VR_NO_VOTE || v.own_l == 0) return false;
     const int rp = i + v.shift;
     if (rp < 0 || rp >= v.own_l) return false;
     const uint8_t *q = cb + 4 * (int)v.own_off4;
@@ -156,17 +173,13 @@ GCB_DEV bool fetch_ent(const uint8_t *cb, const VoteRead &v, int i, int side, co
 
 struct TileCtx {
     const BatchView *b;
-    const ResultView *r;
-    const Workspace *ws;
     const GenomeView *gv;
     const gcb_options *o;
     const uint8_t *slab;
     const VoteRead *vr;
     const FsTile *ft;
-    const int32_t *cpo;  // cluster_pair_off[c0 .. c1]
     int32_t *acc;
-    uint8_t *out0;       // out_payload + the tile's first output byte
-    int c0, nc, p0;
+    uint8_t *out0;  // out_payload + the tile's first output byte
 };
 
 // cluster (relative to c0) that owns pair position `pos`
@@ -180,15 +193,27 @@ GCB_DEV int cluster_of(const int32_t *cpo, int nc, int pos) {
     return lo - 1;
 }
 
-// One column decided the long way: group.cpp:376-525.  Thread-local.
-GCB_DEV void slow_column(const TileCtx &t, int f, int col) {
+// group.cpp:376-393 for one read of one slow column: its vote goes into the column's sixteen bins
+// {count, sum of scores, sum of qualities, best quality}
+GCB_DEV void slow_histogram(const TileCtx &t, const FsTile &ft, int col, int e, int32_t *bins) {
+    int base, qual, score;
+    if (!fetch_ent(t.slab + 4 * (int)ft.cbase4, t.vr[ft.ent0 + e], col, ft.tmpl & 1, *t.o, base, qual, score)) return;
+    int32_t *bin = bins + 4 * base;
+    atomicAdd(bin, 1);
+    atomicAdd(bin + 1, score);
+    atomicAdd(bin + 2, qual);
+    atomicMax(bin + 3, qual);
+}
+
+// group.cpp:395-525 for one slow column whose bins are complete.  Thread-local.
+GCB_DEV void slow_decide(const TileCtx &t, int f, int col, const int32_t *bins) {
     const gcb_options &o = *t.o;
     const FsTile ft = t.ft[f];
-    const int side = f & 1, slot = t.p0 + (f >> 1);
+    const int side = ft.tmpl & 1;
     const uint8_t *cb = t.slab + 4 * (int)ft.cbase4;
     const VoteRead *ents = t.vr + ft.ent0;
     const VoteRead tv = ents[ft.tmpl_k];
-    const int l_out = ft.l_out, qbytes = GCB_ALIGN4(l_out);
+    const int qbytes = GCB_ALIGN4(ft.l_out);
     uint8_t *out = t.out0 + 4 * (int64_t)ft.out4;
     int obase = 0, oqual = 0, sc;
     fetch_ent(cb, tv, col, side, o, obase, oqual, sc);
@@ -196,74 +221,45 @@ GCB_DEV void slow_column(const TileCtx &t, int f, int col) {
         out[col] = (uint8_t)oqual;
         return;
     }
-    SparseBins bins;
-    bins.init();
-    for (int e = 0; e < ft.m; e++) {
-        int base, qual, score;
-        if (fetch_ent(cb, ents[e], col, side, o, base, qual, score)) bins.add(base, qual, score);
-    }
     VoteBin obs[16];
-    int nobs = 0, total = bins.total;
-    if (bins.overflow) {  // four or more distinct codes: full histogram
-        int cnt[16], scs[16], qls[16], mxq[16];
-        for (int k = 0; k < 16; k++) cnt[k] = scs[k] = qls[k] = mxq[k] = 0;
-        total = 0;
-        for (int e = 0; e < ft.m; e++) {
-            int base, qual, score;
-            if (!fetch_ent(cb, ents[e], col, side, o, base, qual, score)) continue;
-            cnt[base]++;
-            scs[base] += score;
-            qls[base] += qual;
-            mxq[base] = max(mxq[base], qual);
-            total += score;
+    int nobs = 0, total = 0;
+    for (int k = 0; k < 16; k++) {
+        const int cnt = bins[4 * k];
+        if (cnt > 0) {
+            obs[nobs].base = k; obs[nobs].cnt = cnt; obs[nobs].score = bins[4 * k + 1]; obs[nobs].qual = bins[4 * k + 2]; obs[nobs].maxq = bins[4 * k + 3];
+            total += obs[nobs].score;
+            nobs++;
         }
-        for (int k = 0; k < 16; k++)
-            if (cnt[k] > 0) {
-                obs[nobs].base = k; obs[nobs].cnt = cnt[k]; obs[nobs].score = scs[k]; obs[nobs].qual = qls[k]; obs[nobs].maxq = mxq[k];
-                nobs++;
-            }
-    } else {
-        for (int k = 0; k < 3; k++)
-            if (bins.s[k].base >= 0) obs[nobs++] = bins.s[k];
     }
     const ColumnTop top = column_top(o, obs, nobs, total);
-    int new_base = obase, new_qual;
+    int new_qual;
     if (top.fast) {
         new_qual = top.top.maxq;  // group.cpp:422-426: the base is NOT written
     } else {
         int ref4 = 0;
-        const int tmpl = t.r->groups[slot].tmpl_read[side];
-        const gcb_read_desc od = t.b->reads[tmpl];
-        if (od.isize != 0 && t.gv->packed4) {  // group.cpp:362-367 + reference.cpp:33-71, group.cpp:430-439
-            const int c = t.c0 + cluster_of(t.cpo, t.nc, slot);
-            const int contig = t.b->cluster_ref[c];
-            if (contig >= 0 && contig < t.gv->n_contigs) {
-                const uint32_t *ocig = t.b->cigar + od.cigar_off;
-                const int64_t span = (int64_t)get_ref_offset(ocig, od.n_cigar, ft.len - 1) + 1;
-                const int64_t clen = t.gv->contig_len[contig];
-                if ((int64_t)od.pos + span < clen) {
-                    const int refpos = get_ref_offset(ocig, od.n_cigar, col);
-                    const int64_t gp = (int64_t)od.pos + refpos;
-                    if (refpos >= 0 && gp < clen) {
-                        const uint8_t two = t.gv->packed4[t.gv->contig_off[contig] + (gp >> 1)];
-                        ref4 = genome_nibble_to_bam((gp & 1) ? (two >> 4) : (two & 0xF));
-                    }
-                }
+        if (ft.flags & FS_REF_OK) {  // group.cpp:430-439
+            int refpos = col;
+            if (!(ft.flags & FS_SIMPLE_CIGAR)) {
+                const gcb_read_desc od = t.b->reads[ft.tmpl];
+                refpos = get_ref_offset(t.b->cigar + od.cigar_off, od.n_cigar, col);
+            }
+            if (refpos >= 0 && refpos < ft.ref_limit) {
+                const int64_t nib = ft.ref_nib0 + refpos;
+                const uint8_t two = t.gv->packed4[nib >> 1];
+                ref4 = genome_nibble_to_bam((nib & 1) ? (two >> 4) : (two & 0xF));
             }
         }
         int rbq = 0;
         bool any_high = false;
         if (top.need_ref && ref4 != 0) {
-            int rmax = 0;
-            for (int k = 0; k < nobs; k++)
-                if (obs[k].base == ref4) rmax = obs[k].maxq;
+            const int rmax = bins[4 * ref4] > 0 ? bins[4 * ref4 + 3] : 0;
             if (rmax >= 128) {  // `char refBaseQual` wraps: the scan order matters (group.cpp:474-490): template first
                 int tb, tq, ts;
                 if (fetch_ent(cb, tv, col, side, o, tb, tq, ts) && tb == ref4) {
                     if (tq > rbq) rbq = sc8(tq);
                     if (tq >= o.high_quality) any_high = true;
                 }
-                for (int e = 0; e < ft.m; e++) {
+                for (int e = 0; e < (int)ft.m; e++) {
                     int base, qual, score;
                     if (e == ft.tmpl_k || !fetch_ent(cb, ents[e], col, side, o, base, qual, score) || base != ref4) continue;
                     if (qual > rbq) rbq = sc8(qual);
@@ -275,22 +271,37 @@ GCB_DEV void slow_column(const TileCtx &t, int f, int col) {
             }
         }
         const ColumnOut co = column_arbitrate(o, top, ref4, rbq, any_high);
-        int d_diff = 0, d_mm = 0;
         if (obase != co.base) {  // group.cpp:509-524
-            new_base = co.base;
-            d_diff = 1;
+            int d_mm = 0;
             if (ref4 != 0) {
                 if (obase == ref4) d_mm = 1;
                 else if (co.base == ref4) d_mm = -1;
             }
-            atomicAdd(t.acc + f, d_diff + d_mm * 65536);
+            atomicAdd(t.acc + f, 1 + d_mm * 65536);
             const int byte = col >> 1;
-            const unsigned delta = ((unsigned)(obase ^ new_base) & 0xFu) << ((col & 1) ? 0 : 4);
+            const unsigned delta = ((unsigned)(obase ^ co.base) & 0xFu) << ((col & 1) ? 0 : 4);
             atomicXor((unsigned *)(out + qbytes + (byte & ~3)), delta << (8 * (byte & 3)));
         }
         new_qual = co.qual;
     }
     out[col] = (uint8_t)new_qual;
+}
+
+// a slow column decided by its owner alone (queue overflow): the histogram lives in local memory
+GCB_DEV void slow_inline(const TileCtx &t, int f, int col) {
+    int32_t bins[64];
+    for (int k = 0; k < 64; k++) bins[k] = 0;
+    const FsTile ft = t.ft[f];
+    if (col < (int)ft.len)
+        for (int e = 0; e < (int)ft.m; e++) {
+            int base, qual, score;
+            if (!fetch_ent(t.slab + 4 * (int)ft.cbase4, t.vr[ft.ent0 + e], col, ft.tmpl & 1, *t.o, base, qual, score)) continue;
+            bins[4 * base]++;
+            bins[4 * base + 1] += score;
+            bins[4 * base + 2] += qual;
+            bins[4 * base + 3] = max(bins[4 * base + 3], qual);
+        }
+    slow_decide(t, f, col, bins);
 }
 
 // group.cpp:538-566: more than five new mismatches => the record keeps the template's bases and (rewritten) qualities
@@ -303,7 +314,7 @@ GCB_DEV void rollback_record(const TileCtx &t, int f) {
     const uint8_t *tseq = cb + 4 * (int)tv.own_off4 + qbytes;
     for (int col = 0; col < l_out; col++) {
         int base, qual, sc;
-        fetch_ent(cb, tv, col, f & 1, *t.o, base, qual, sc);
+        fetch_ent(cb, tv, col, ft.tmpl & 1, *t.o, base, qual, sc);
         out[col] = (uint8_t)qual;
     }
     for (int k = 0; k < (l_out + 1) >> 1; k++) out[qbytes + k] = tseq[k];
@@ -315,14 +326,17 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
     uint64_t *bar = (uint64_t *)(smem + VT_OFF_BAR);
     int *s_nslow = (int *)(smem + VT_OFF_NSLOW);
     int *s_nofit = (int *)(smem + VT_OFF_NOFIT);
+    int *s_nfs = (int *)(smem + VT_OFF_NFS);
+    int *s_next = (int *)(smem + VT_OFF_NEXT);
+    int *s_lmax = (int *)(smem + VT_OFF_LMAX);
     uint32_t *s_wsum = (uint32_t *)(smem + VT_OFF_WSUM);
     int32_t *s_cpo = (int32_t *)(smem + VT_OFF_CPO);
-    uint32_t *s_chunk0 = (uint32_t *)(smem + VT_OFF_CHUNK0);
     int32_t *s_acc = (int32_t *)(smem + VT_OFF_ACC);
     uint32_t *s_slow = (uint32_t *)(smem + VT_OFF_SLOW);
-    FsDesc *s_fd = (FsDesc *)(smem + VT_OFF_FS);
-    FsTile *s_ft = (FsTile *)(smem + VT_OFF_FS);
+    int32_t *s_bins = (int32_t *)(smem + VT_OFF_BINS);
+    FsTile *s_ft = (FsTile *)(smem + VT_OFF_FT);
     VoteRead *s_vr = (VoteRead *)(smem + VT_OFF_VR);
+    const uint32_t *s_vr32 = (const uint32_t *)(smem + VT_OFF_VR);
     uint8_t *slab = smem + VT_OFF_SLAB;
 
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -343,62 +357,46 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
         tile_barrier_init(bar);
         *s_nslow = 0;
         *s_nofit = 0;
+        *s_next = 0;
+        *s_lmax = 1;
     }
     __syncthreads();
     if (tid == 0) {
         const uint32_t tb = 32u * (uint32_t)NP;
-        tile_expect(bar, (uint32_t)slab_bytes + 2u * tb);
+        tile_expect(bar, (uint32_t)slab_bytes + tb);
         if (slab_bytes > 0) tile_copy(slab, b.payload + t0.slab0, (uint32_t)slab_bytes, bar);
         tile_copy(s_vr, ws.vote_reads + 2 * (int64_t)P0, tb, bar);
-        tile_copy(s_fd, ws.fs_desc + 2 * (int64_t)P0, tb, bar);
+    }
+    // ---- prologue: one thread per pair position = per possible family slot
+    FsDesc fd[2];
+    fd[0].mode = fd[1].mode = SIDE_NONE;
+    fd[0].flags = fd[1].flags = 0;
+    if (tid < NP) {
+        fd[0] = ws.fs_desc[2 * (int64_t)(P0 + tid)];
+        fd[1] = ws.fs_desc[2 * (int64_t)(P0 + tid) + 1];
     }
     for (int i = tid; i <= NC; i += VT_THREADS) s_cpo[i] = b.cluster_pair_off[c0 + i];
     const int64_t out_base0 = ws.scan_block[c0 / SCAN_BLOCK] + ws.cluster_out_off[c0];
     __syncthreads();
-
-    // ---- prologue: one thread per pair position = per possible family slot
-    int ci = 0;
-    int64_t c_slab = 0, c_out = 0;
-    if (tid < NP) {
-        ci = cluster_of(s_cpo, NC, P0 + tid);
+    const bool live0 = fd[0].mode != SIDE_NONE, live1 = fd[1].mode != SIDE_NONE;
+    int pos_rel = 0;
+    int64_t c_slab = 0, c_out = 0, ref_off = 0, ref_len = 0;
+    if (live0 || live1) {
+        const int ci = cluster_of(s_cpo, NC, P0 + tid);
         const int c = c0 + ci;
+        pos_rel = s_cpo[ci] - P0;
         c_slab = ws.slab_off[c] - t0.slab0;
         c_out = ws.scan_block[c / SCAN_BLOCK] + ws.cluster_out_off[c] - out_base0;
-        s_acc[2 * tid] = 0;
-        s_acc[2 * tid + 1] = 0;
-    }
-    tile_wait(bar, 0);
-    uint32_t nch[2] = {0u, 0u};
-    if (tid < NP) {
-        for (int side = 0; side < 2; side++) {
-            const FsDesc fd = s_fd[2 * tid + side];
-            FsTile ft;
-            ft.ent0 = (uint16_t)(2 * (s_cpo[ci] - P0 + (int)fd.mb_rel) + side * (int)fd.m);
-            ft.m = fd.m;
-            ft.l_out = fd.l_out;
-            ft.len = fd.len;
-            ft.tmpl_k = fd.tmpl_k;
-            ft.mode = fd.mode;
-            ft.flags = fd.flags;
-            ft.cbase4 = (uint16_t)(c_slab >> 2);
-            const int64_t orel = c_out + fd.out_rel;
-            ft.out4 = (uint16_t)(orel >> 2);
-            if (fd.mode != SIDE_NONE) {
-                if ((fd.flags & FS_NOFIT) || (orel >> 2) > 0xFFFF) *s_nofit = 1;
-                const int l = fd.l_out;
-                if (out_base0 + orel + record_bytes(l) > r.out_capacity) {
-                    raise_error(ws.error_flag, GCB_ERR_CAPACITY);
-                    ft.mode = SIDE_NONE;
-                } else {
-                    nch[side] = (uint32_t)max((GCB_ALIGN4(l) + 7) >> 3, GCB_ALIGN4((l + 1) >> 1) >> 2);
-                }
-            }
-            s_ft[2 * tid + side] = ft;
+        if ((fd[0].flags | fd[1].flags) & FS_REF_OK) {
+            const int contig = b.cluster_ref[c];
+            ref_off = gv.contig_off[contig];
+            ref_len = gv.contig_len[contig];
         }
     }
-    // exclusive scan of the chunk counts over the family sides of the tile
+    // compact index of the live family sides (exclusive scan of the live counts)
+    int fidx0;
     {
-        const uint32_t mine = nch[0] + nch[1];
+        const uint32_t mine = (live0 ? 1u : 0u) + (live1 ? 1u : 0u);
         uint32_t incl = mine;
         for (int off = 1; off < WARP; off <<= 1) {
             const uint32_t v = __shfl_up_sync(FULL, incl, off);
@@ -408,14 +406,51 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
         __syncthreads();
         uint32_t pre = incl - mine;
         for (int w = 0; w < warp; w++) pre += s_wsum[w];
-        if (tid < NP) {
-            s_chunk0[2 * tid] = pre;
-            s_chunk0[2 * tid + 1] = pre + nch[0];
+        fidx0 = (int)pre;
+        if (tid == VT_THREADS - 1) {
+            *s_nfs = (int)(pre + mine);
+            if (pre + mine > (uint32_t)VT_MAX_FS) *s_nofit = 1;
         }
-        if (tid == VT_THREADS - 1) s_chunk0[2 * NP] = pre + mine;
-        __syncthreads();
     }
-    if (*s_nofit) {  // a field overflowed its table slot: the generic kernel takes the tile
+    {
+        int lneed = 1, fidx = fidx0;
+        for (int side = 0; side < 2; side++) {
+            if (fd[side].mode == SIDE_NONE) continue;
+            const FsDesc d = fd[side];
+            FsTile ft;
+            ft.ent0 = (uint16_t)(2 * (pos_rel + (int)d.mb_rel) + side * (int)d.m);
+            ft.m = d.m;
+            ft.l_out = d.l_out;
+            ft.len = d.len;
+            ft.tmpl_k = d.tmpl_k;
+            ft.mode = d.mode;
+            ft.flags = d.flags;
+            ft.cbase4 = (uint16_t)(c_slab >> 2);
+            const int64_t orel = c_out + d.out_rel;
+            ft.out4 = (uint16_t)(orel >> 2);
+            ft.ref_nib0 = 2 * ref_off + d.pos;
+            const int64_t lim = ref_len - d.pos;
+            ft.ref_limit = (int32_t)(lim > 0x7FFFFFFF ? 0x7FFFFFFF : (lim < 0 ? 0 : lim));
+            ft.tmpl = d.tmpl;
+            const int l = d.l_out;
+            const int chunks = max((GCB_ALIGN4(l) + 15) >> 4, (GCB_ALIGN4((l + 1) >> 1) + 7) >> 3);
+            if ((d.flags & FS_NOFIT) || (orel >> 2) > 0xFFFF || chunks > WARP) *s_nofit = 1;
+            if (out_base0 + orel + record_bytes(l) > r.out_capacity) {
+                raise_error(ws.error_flag, GCB_ERR_CAPACITY);
+                ft.mode = SIDE_NONE;  // keeps its place in the table but is never voted
+            }
+            lneed = max(lneed, min(chunks, WARP));
+            if (fidx < VT_MAX_FS) {
+                s_ft[fidx] = ft;
+                s_acc[fidx] = 0;
+            }
+            fidx++;
+        }
+        if (lneed > 1) atomicMax(s_lmax, lneed);
+    }
+    tile_wait(bar, 0);
+    __syncthreads();
+    if (*s_nofit) {  // the generic kernel takes the tile
         if (tid == 0) {
             ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = (int32_t)blockIdx.x;
             GCB_COUNT(1, 1);
@@ -423,123 +458,223 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
         return;
     }
     if (tid == 0) GCB_COUNT(0, 1);
+    const int nfs = *s_nfs;
+    // does every voter of the family side share the template's geometry?  (one thread per family side)
+    for (int f = tid; f < nfs; f += VT_THREADS) {
+        const FsTile ft = s_ft[f];
+        if (ft.mode == SIDE_NONE || ft.mode == SIDE_COPY) continue;
+        const VoteRead tv = s_vr[ft.ent0 + ft.tmpl_k];
+        bool uni = ft.len == ft.l_out && tv.shift == 0 && (int)tv.own_l == (int)ft.l_out;
+        for (int e = 0; e < (int)ft.m && uni; e++) {
+            const VoteRead v = s_vr[ft.ent0 + e];
+            if (v.own_off4 == VR_NO_VOTE) continue;
+            uni = v.own_l == tv.own_l && v.shift == 0 && v.ov_len == tv.ov_len &&
+                  (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l));
+        }
+        if (uni) s_ft[f].flags = ft.flags | FS_UNIFORM;
+        GCB_COUNT(uni ? 4 : 5, 1);
+    }
+    __syncthreads();
 
     TileCtx t;
-    t.b = &b; t.r = &r; t.ws = &ws; t.gv = &gv; t.o = &o;
-    t.slab = slab; t.vr = s_vr; t.ft = s_ft; t.cpo = s_cpo; t.acc = s_acc;
+    t.b = &b; t.gv = &gv; t.o = &o;
+    t.slab = slab; t.vr = s_vr; t.ft = s_ft; t.acc = s_acc;
     t.out0 = r.out_payload + out_base0;
-    t.c0 = c0; t.nc = NC; t.p0 = P0;
 
     const uint32_t mod4 = 0x01010101u * (uint32_t)(o.moderate_quality & 0xFF);
-    const int nfs = 2 * NP;
-    const int total = (int)s_chunk0[nfs];
-    for (int item = tid; item < total; item += VT_THREADS) {
-        int f = 0;
-        {
-            int hi = nfs;  // last f with chunk0[f] <= item
-            while (hi - f > 1) {
-                const int mid = (f + hi) >> 1;
-                if ((int)s_chunk0[mid] <= item) f = mid;
-                else hi = mid;
-            }
-        }
-        const FsTile ft = s_ft[f];
-        const int j = item - (int)s_chunk0[f];
-        const int col0 = 8 * j;
+    const int L = *s_lmax;   // lanes per family side
+    const int S = WARP / L;  // family sides per bundle
+    const int nb = (nfs + S - 1) / S;
+    const int sub = lane / L, j = lane - sub * L;
+    const int col0 = VT_CHUNK * j;
+    for (;;) {
+        int bundle = 0;
+        if (lane == 0) bundle = atomicAdd(s_next, 1);
+        bundle = __shfl_sync(FULL, bundle, 0);
+        if (bundle >= nb) break;
+        const int f = bundle * S + sub;
+        FsTile ft;
+        ft.ent0 = 0; ft.m = 0; ft.l_out = 0; ft.len = 0; ft.tmpl_k = 0; ft.mode = SIDE_NONE; ft.flags = 0; ft.cbase4 = 0; ft.out4 = 0;
+        if (sub < S && f < nfs) ft = s_ft[f];
         const int l_out = ft.l_out, len = ft.len;
         const int qbytes = GCB_ALIGN4(l_out), sbytes = GCB_ALIGN4((l_out + 1) >> 1);
+        const bool mine = ft.mode != SIDE_NONE && col0 < max(qbytes, 2 * sbytes);  // this lane owns words of the record
+        const int m = mine && ft.mode != SIDE_COPY ? (int)ft.m : 0;
+        const int mmax = __reduce_max_sync(FULL, m);
         const uint8_t *cb = slab + 4 * (int)ft.cbase4;
+        const uint32_t *ent32 = s_vr32 + 4 * (int)ft.ent0;
         const VoteRead *ents = s_vr + ft.ent0;
-        const uint8_t *trec = cb + 4 * (int)ents[ft.tmpl_k].own_off4;
-        const uint32_t tbe = 4 * j < sbytes ? bswap32(*(const uint32_t *)(trec + qbytes + 4 * j)) : 0u;
-        const int nv = min(max(l_out - col0, 0), 8);                           // columns of the record in this chunk
-        const int nk = min(max(2 * ((l_out + 1) >> 1) - col0, 0), 8);         // nibbles the record keeps (odd tail included)
-        const uint32_t qm0 = byte_range(0, nv), qm1 = byte_range(0, nv - 4);
-        uint32_t oq0, oq1, inline_slow = 0u;
-        if (ft.mode == SIDE_COPY) {  // group.cpp:73-77: the record itself
-            oq0 = col0 < qbytes ? *(const uint32_t *)(trec + col0) : 0u;
-            oq1 = col0 + 4 < qbytes ? *(const uint32_t *)(trec + col0 + 4) : 0u;
+        VoteRead tv = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t tq[4] = {0u, 0u, 0u, 0u}, tbe0 = 0u, tbe1 = 0u;
+        if (mine) {
+            tv = ents[ft.tmpl_k];
+            const uint8_t *trec = cb + 4 * (int)tv.own_off4;
+            const uint32_t *tp = (const uint32_t *)trec;
+#pragma unroll
+            for (int k = 0; k < 4; k++) tq[k] = word_or_zero(tp, (col0 >> 2) + k, qbytes >> 2);
+            const uint32_t *sp = (const uint32_t *)(trec + qbytes);
+            tbe0 = bswap32(word_or_zero(sp, 2 * j, sbytes >> 2));
+            tbe1 = bswap32(word_or_zero(sp, 2 * j + 1, sbytes >> 2));
+        }
+        uint32_t mq[4] = {0u, 0u, 0u, 0u}, dis0 = 0u, dis1 = 0u;
+        const int nvote = clamp_int(len - col0, 0, VT_CHUNK);  // voted columns of this chunk
+        if (ft.flags & FS_UNIFORM) {
+            // hoisted geometry: every voter is read at the template's columns and meets its mate at the same offset
+            const int x = (int)tv.ov_own - col0;
+            const int y = x - (int)tv.ov_mate;
+            const int oa = max(max(0, x), y), oz = min(min(nvote, x + (int)tv.ov_len), y + (int)tv.mate_l);
+            const bool has_ov = tv.ov_len > 0 && oz > oa;
+            const uint32_t om0 = has_ov ? nib_range(oa, oz) : 0u, om1 = has_ov ? nib_range(oa - 8, oz - 8) : 0u;
+            const int mqb = GCB_ALIGN4(tv.mate_l), mnw = GCB_ALIGN4((tv.mate_l + 1) >> 1) >> 2;
+            const int ms = 0 - y, mw0 = ms >> 3;
+            const unsigned msh = (unsigned)(ms & 7) * 4u;
+            const bool p0 = has_ov && (unsigned)mw0 < (unsigned)mnw, p1 = has_ov && (unsigned)(mw0 + 1) < (unsigned)mnw,
+                       p2 = has_ov && (unsigned)(mw0 + 2) < (unsigned)mnw;
+            const int qoff = col0, soff = qbytes + 8 * j, moff = mqb + 4 * mw0;
+            for (int e = 0; e < mmax; e++) {
+                if (e >= m) continue;
+                const uint32_t w = ent32[4 * e];
+                if ((w & 0xFFFFu) == VR_NO_VOTE) continue;
+                const uint8_t *rec = cb + 4 * (int)(w & 0xFFFFu);
+                const uint32_t *qp = (const uint32_t *)(rec + qoff);
+                mq[0] = __vmaxu4(mq[0], qp[0]);
+                mq[1] = __vmaxu4(mq[1], qp[1]);
+                mq[2] = __vmaxu4(mq[2], qp[2]);
+                mq[3] = __vmaxu4(mq[3], qp[3]);
+                const uint32_t *sp = (const uint32_t *)(rec + soff);
+                const uint32_t be0 = bswap32(sp[0]), be1 = bswap32(sp[1]);
+                dis0 |= be0 ^ tbe0;
+                dis1 |= be1 ^ tbe1;
+                if (has_ov) {  // pair.cpp:133-170: a base that differs from its mate's is never a fast column
+                    const uint32_t *mp = (const uint32_t *)(cb + 4 * (int)(w >> 16) + moff);
+                    const uint32_t a = p0 ? bswap32(mp[0]) : 0u, c = p1 ? bswap32(mp[1]) : 0u, d = p2 ? bswap32(mp[2]) : 0u;
+                    dis0 |= (be0 ^ __funnelshift_l(c, a, msh)) & om0;
+                    dis1 |= (be1 ^ __funnelshift_l(d, c, msh)) & om1;
+                }
+            }
+            // the loop read whole words: keep the voted columns only
+            const uint32_t vm0 = nib_range(0, nvote), vm1 = nib_range(0, nvote - 8);
+            dis0 &= vm0;
+            dis1 &= vm1;
+            mq[0] &= bytes_lo(vm0);
+            mq[1] &= bytes_hi(vm0);
+            mq[2] &= bytes_lo(vm1);
+            mq[3] &= bytes_hi(vm1);
         } else {
-            uint32_t mq0 = 0u, mq1 = 0u, dis = 0u;
-            for (int e = 0; e < (int)ft.m; e++) {
+            for (int e = 0; e < mmax; e++) {
+                if (e >= m) continue;
                 const VoteRead v = ents[e];
-                if (v.own_l == 0) continue;
+                if (v.own_off4 == VR_NO_VOTE || v.own_l == 0) continue;
                 const int rp0 = col0 + v.shift;
-                const int a = max(0, -rp0), z = min(8, min((int)v.own_l - rp0, len - col0));
+                const int a = max(0, 0 - rp0), z = min(nvote, (int)v.own_l - rp0);
                 if (z <= a) continue;
                 const uint8_t *rec = cb + 4 * (int)v.own_off4;
                 const int rq = GCB_ALIGN4(v.own_l);
-                uint32_t q0, q1, be;
-                if (v.shift == 0) {
-                    q0 = *(const uint32_t *)(rec + col0);
-                    q1 = col0 + 4 < rq ? *(const uint32_t *)(rec + col0 + 4) : 0u;
-                    be = bswap32(*(const uint32_t *)(rec + rq + 4 * j));
-                } else {
-                    fetch8q(rec, rq, rp0, q0, q1);
-                    be = fetch8b(rec + rq, GCB_ALIGN4((v.own_l + 1) >> 1), rp0);
-                }
-                if (a != 0 || z != 8) {
-                    q0 &= byte_range(a, z);
-                    q1 &= byte_range(a - 4, z - 4);
-                }
-                mq0 = __vmaxu4(mq0, q0);
-                mq1 = __vmaxu4(mq1, q1);
-                dis |= (be ^ tbe) & nib_range(a, z);
-                if (v.ov_len > 0) {  // pair.cpp:133-170: a base that differs from its mate's is never a fast column
+                uint32_t q[4], be0, be1;
+                fetch16q(rec, rq, rp0, q);
+                fetch16b(rec + rq, GCB_ALIGN4((v.own_l + 1) >> 1), rp0, be0, be1);
+                const uint32_t vm0 = nib_range(a, z), vm1 = nib_range(a - 8, z - 8);
+                mq[0] = __vmaxu4(mq[0], q[0] & bytes_lo(vm0));
+                mq[1] = __vmaxu4(mq[1], q[1] & bytes_hi(vm0));
+                mq[2] = __vmaxu4(mq[2], q[2] & bytes_lo(vm1));
+                mq[3] = __vmaxu4(mq[3], q[3] & bytes_hi(vm1));
+                dis0 |= (be0 ^ tbe0) & vm0;
+                dis1 |= (be1 ^ tbe1) & vm1;
+                if (v.ov_len > 0) {
                     // chunk column k pairs own index rp0+k with mate index k - y.  (Written with subtractions only:
                     // ptxas 12.9 dropped the negation when it folded max(a, max(x, -t)) into one VIMNMX3 on sm_100a —
                     // the PTX was right, the SASS and the B200 were not; profiles/r01_notes.md has the listing.)
-                    const int x = (int)v.ov_own - rp0;   // first chunk column inside the overlap window
-                    const int y = x - (int)v.ov_mate;    // first chunk column whose mate index is >= 0
+                    const int x = (int)v.ov_own - rp0;  // first chunk column inside the overlap window
+                    const int y = x - (int)v.ov_mate;   // first chunk column whose mate index is >= 0
                     const int oa = max(max(a, x), y);
                     const int oz = min(min(z, x + (int)v.ov_len), y + (int)v.mate_l);
                     if (oz > oa) {
                         const uint8_t *mrec = cb + 4 * (int)v.mate_off4;
-                        const uint32_t mbe = fetch8b(mrec + GCB_ALIGN4(v.mate_l), GCB_ALIGN4((v.mate_l + 1) >> 1), 0 - y);
-                        dis |= (be ^ mbe) & nib_range(oa, oz);
+                        uint32_t mb0, mb1;
+                        fetch16b(mrec + GCB_ALIGN4(v.mate_l), GCB_ALIGN4((v.mate_l + 1) >> 1), 0 - y, mb0, mb1);
+                        dis0 |= (be0 ^ mb0) & nib_range(oa, oz);
+                        dis1 |= (be1 ^ mb1) & nib_range(oa - 8, oz - 8);
                     }
-                }
-            }
-            oq0 = mq0;
-            oq1 = mq1;
-            GCB_COUNT(2, min(max(len - col0, 0), 8));
-            // which columns are not fast
-            const int nvote = min(max(len - col0, 0), 8);
-            const uint32_t vq0 = byte_range(0, nvote), vq1 = byte_range(0, nvote - 4);
-            const bool all_fast = implied && len == l_out && dis == 0u && ((__vcmpgeu4(mq0, mod4) & vq0) == vq0) &&
-                                  ((__vcmpgeu4(mq1, mod4) & vq1) == vq1);
-            if (!all_fast) {
-                const int ncheck = (implied && len == l_out) ? nvote : nv;  // without `implied` (or with unvoted columns) every column is slow
-                for (int k = 0; k < ncheck; k++) {
-                    bool slow = !(implied && len == l_out);
-                    if (!slow) {
-                        const uint32_t q = ((k < 4 ? mq0 : mq1) >> (8 * (k & 3))) & 0xFFu;
-                        slow = ((dis >> (28 - 4 * k)) & 0xFu) != 0u || (int)q < o.moderate_quality;
-                    }
-                    if (!slow) continue;
-                    GCB_COUNT(3, 1);
-                    const int idx = atomicAdd(s_nslow, 1);
-                    if (idx < VT_SLOW_CAP) s_slow[idx] = ((uint32_t)f << 16) | (uint32_t)(col0 + k);
-                    else inline_slow |= 1u << k;  // queue full: this thread owns the chunk's words and decides the column itself
                 }
             }
         }
+        if (!mine) continue;
+        // ---- what the record gets: qualities = the maxima (fast columns), bases = the template's
+        const int nv = clamp_int(l_out - col0, 0, VT_CHUNK);                  // columns of the record in this chunk
+        const int nk = clamp_int(2 * ((l_out + 1) >> 1) - col0, 0, VT_CHUNK);  // nibbles the record keeps (odd tail included)
+        const uint32_t rm0 = nib_range(0, nv), rm1 = nib_range(0, nv - 8);
+        uint32_t oq[4];
+        uint32_t slow0 = 0u, slow1 = 0u;
+        if (ft.mode == SIDE_COPY) {  // group.cpp:73-77: the record itself
+#pragma unroll
+            for (int k = 0; k < 4; k++) oq[k] = tq[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) oq[k] = mq[k];
+            GCB_COUNT(2, nvote);
+            if (implied && len == l_out) {
+                const uint32_t lowq0 = nibs_of_bytes(~__vcmpgeu4(mq[0], mod4), ~__vcmpgeu4(mq[1], mod4));
+                const uint32_t lowq1 = nibs_of_bytes(~__vcmpgeu4(mq[2], mod4), ~__vcmpgeu4(mq[3], mod4));
+                slow0 = (dis0 | lowq0) & nib_range(0, nvote);
+                slow1 = (dis1 | lowq1) & nib_range(0, nvote - 8);
+            } else {  // without `implied`, or with columns that are not voted, every column of the record is slow
+                slow0 = rm0;
+                slow1 = rm1;
+            }
+        }
         uint8_t *out = t.out0 + 4 * (int64_t)ft.out4;
-        if (col0 < qbytes) *(uint32_t *)(out + col0) = oq0 & qm0;
-        if (col0 + 4 < qbytes) *(uint32_t *)(out + col0 + 4) = oq1 & qm1;
-        if (4 * j < sbytes) *(uint32_t *)(out + qbytes + 4 * j) = bswap32(tbe & nib_range(0, nk));
-        for (int k = 0; inline_slow != 0u; k++, inline_slow >>= 1)
-            if (inline_slow & 1u) slow_column(t, f, col0 + k);
+        {
+            const uint32_t qm[4] = {bytes_lo(rm0), bytes_hi(rm0), bytes_lo(rm1), bytes_hi(rm1)};
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (col0 + 4 * k < qbytes) *(uint32_t *)(out + col0 + 4 * k) = oq[k] & qm[k];
+            if (8 * j < sbytes) *(uint32_t *)(out + qbytes + 8 * j) = bswap32(tbe0 & nib_range(0, nk));
+            if (8 * j + 4 < sbytes) *(uint32_t *)(out + qbytes + 8 * j + 4) = bswap32(tbe1 & nib_range(0, nk - 8));
+        }
+        // queue the slow columns (one or two per family side of a clean library)
+        for (int wsel = 0; wsel < 2; wsel++) {
+            uint32_t sm = wsel ? slow1 : slow0;
+            while (sm != 0u) {
+                const int k = __clz((int)sm) >> 2;
+                sm &= ~(0xF0000000u >> (4 * k));
+                const int col = col0 + 8 * wsel + k;
+                GCB_COUNT(3, 1);
+                const int idx = atomicAdd(s_nslow, 1);
+                if (idx < VT_SLOW_CAP) s_slow[idx] = ((uint32_t)f << 16) | (uint32_t)col;
+                else slow_inline(t, f, col);  // queue full: this lane owns the chunk's words
+            }
+        }
     }
     __syncthreads();
+    // ---- slow columns: eight threads histogram one column, then one thread decides it
     {
         const int n = min(*s_nslow, VT_SLOW_CAP);
-        for (int i = tid; i < n; i += VT_THREADS) slow_column(t, (int)(s_slow[i] >> 16), (int)(s_slow[i] & 0xFFFFu));
+        for (int base = 0; base < n; base += VT_BIN_COLS) {
+            const int cnt = min(VT_BIN_COLS, n - base);
+            for (int k = tid; k < cnt * 64; k += VT_THREADS) s_bins[k] = 0;
+            __syncthreads();
+            const int ci = tid >> 3, sub8 = tid & 7;
+            if (ci < cnt) {
+                const uint32_t code = s_slow[base + ci];
+                const int col = (int)(code & 0xFFFFu);
+                const FsTile ft = s_ft[code >> 16];
+                if (col < (int)ft.len)
+                    for (int e = sub8; e < (int)ft.m; e += 8) slow_histogram(t, ft, col, e, s_bins + 64 * ci);
+            }
+            __syncthreads();
+            if (tid < cnt) {
+                const uint32_t code = s_slow[base + tid];
+                slow_decide(t, (int)(code >> 16), (int)(code & 0xFFFFu), s_bins + 64 * tid);
+            }
+            __syncthreads();
+        }
     }
-    __syncthreads();
-    if (tid < NP) {  // per family side: diff, mismatchInc, rollback, absolute output offset
+    // ---- per family side: diff, mismatchInc, rollback, absolute output offset
+    if (tid < NP) {
+        int fidx = fidx0;
         for (int side = 0; side < 2; side++) {
-            const int f = 2 * tid + side;
+            if (fd[side].mode == SIDE_NONE) continue;
+            const int f = fidx++;
             const FsTile ft = s_ft[f];
             if (ft.mode == SIDE_NONE) continue;
             const int acc = s_acc[f];

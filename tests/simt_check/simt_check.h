@@ -311,8 +311,17 @@ inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
 inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
     uint64_t v = ((uint64_t)y << 32) | x;
     unsigned r = 0;
-    for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    for (int i = 0; i < 4; i++) {
+        unsigned sel = (s >> (4 * i)) & 0xF;
+        unsigned byte = (unsigned)((v >> (8 * (sel & 7))) & 0xFF);
+        if (sel & 8) byte = (byte & 0x80) ? 0xFFu : 0u;  // sign-replicate mode
+        r |= byte << (8 * i);
+    }
     return r;
+}
+inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned shift) {
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return shift >= 32 ? hi : (unsigned)(v >> shift);
 }
 inline unsigned __vmaxu4(unsigned a, unsigned b) {
     unsigned r = 0;

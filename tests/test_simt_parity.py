@@ -26,21 +26,24 @@ def simt_lib():
 def test_kernels_match_oracle_under_simt_check(simt_lib, oracle, name, thunk):
     from gencore_b200.engine import ConsensusEngine
     batch, genome, opt = thunk()
-    cnt = (ctypes.c_int64 * 4)()
+    cnt = (ctypes.c_int64 * 6)()
     with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
         eng.set_reference(genome)
         eng.lib.gcb_simt_counters(cnt, 1)
         res = eng.cluster_by_umi(batch)
         eng.lib.gcb_simt_counters(cnt, 1)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
-    tiled, generic, cols, slow = list(cnt)
-    COVERAGE[name] = (tiled, generic, cols, slow)
+    tiled, generic, cols, slow, uni, nonuni = list(cnt)
+    COVERAGE[name] = (tiled, generic, cols, slow, uni, nonuni)
     if name in ("deep_1100", "low_complexity"):
         assert generic > 0, "the >1000-pair clusters must take the generic kernel"
     elif batch.n_pairs > 0:
         assert tiled > 0 and generic == 0, (tiled, generic)
     if name.startswith(("cfg1", "cfg2", "cfg3")):
         assert 0 < slow < 0.2 * cols, "the fixed-length shapes must mostly take the fast columns"
+        assert uni > 0 and nonuni == 0, "fixed-length families are uniform"
+    if name.startswith("ragged") and "_3" not in name:
+        assert nonuni > 0
 
 
 def test_both_column_paths_are_exercised():
