@@ -34,24 +34,26 @@ struct __align__(16) VoteRead {
 };
 constexpr int VR_NO_OVERLAP_INFO = -1;
 
-// One (family, side) for the tiled vote kernel (32 bytes, index 2*slot+side).
+// One (family, side) for the tiled vote kernel (32 bytes, index 2*slot+side); self-contained, so that the
+// vote kernel needs no cluster lookup before it can place the family side in its tile.
 struct __align__(16) FsDesc {
-    uint16_t mb_rel;   // members index of the family's first pair, relative to the cluster's first pair
+    int32_t mb;        // members index of the family's first pair
     uint16_t m;        // pairs in the family
     uint16_t l_out;    // template l_qseq
     uint16_t len;      // columns that are voted (group.cpp:354-360)
     uint16_t tmpl_k;   // template = k-th member of the family
     uint8_t mode;      // SIDE_*
     uint8_t flags;     // FS_*
+    uint16_t reserved;
     uint32_t out_rel;  // consensus record offset relative to the cluster's output
-    int32_t pos;       // template core.pos
-    int32_t tmpl;      // template read slot
-    uint32_t reserved[2];
+    int32_t c;         // cluster
+    int64_t ref_nib0;  // FS_REF_OK: nibble index in the packed genome of the template's core.pos
 };
 constexpr uint8_t FS_NOFIT = 1;         // some field does not fit its 16 bits: the tile goes to the generic kernel
 constexpr uint8_t FS_REF_OK = 2;        // group.cpp:362-367 + reference.cpp:33-71: the vote may consult the reference
 constexpr uint8_t FS_SIMPLE_CIGAR = 4;  // template CIGAR is one M/=/X op covering the read: BamUtil::getRefOffset(i) == i
-constexpr uint8_t FS_UNIFORM = 8;       // (set by the vote kernel) every voter has the template's geometry
+constexpr uint8_t FS_UNIFORM = 8;       // every voter has the template's geometry: same length, no shift, same overlap window
+constexpr uint8_t FS_SIDE1 = 0x80;      // (set by the vote kernel) this is the right-hand side of the pairs
 constexpr uint16_t VR_NO_VOTE = 0xFFFFu;  // VoteRead.own_off4 of a read that does not vote
 
 struct __align__(16) TileDir {
@@ -98,6 +100,7 @@ struct GenomeView {
     const int64_t *contig_off;
     const int64_t *contig_len;
     int32_t n_contigs;
+    int64_t packed_bytes;
 };
 
 // ---- CIGAR helpers ------------------------------------------------------------------------

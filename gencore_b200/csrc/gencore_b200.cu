@@ -31,7 +31,7 @@ struct gcb_ctx {
     char err[256] = {0};
     int64_t launches = 0;
     // genome
-    GenomeView genome = {nullptr, nullptr, nullptr, 0};
+    GenomeView genome = {nullptr, nullptr, nullptr, 0, 0};
     DevBuf g_packed, g_off, g_len;
     // workspace (grow-only)
     DevBuf w_members, w_group_off, w_scratch, w_rrp, w_flags, w_mode, w_hasumi, w_overlap, w_slab, w_cob, w_coo, w_scan, w_err, w_tiles;
@@ -221,7 +221,7 @@ int gcb_set_reference_device(gcb_ctx *ctx, const uint8_t *packed4_dev, int64_t p
     if (!ctx || n_contigs < 0 || (n_contigs > 0 && (!packed4_dev || !contig_off || !contig_len)) || packed_bytes < 0)
         return fail(ctx, GCB_ERR_ARG, "gcb_set_reference_device: bad argument");
     GCB_CUDA(ctx, cudaSetDevice(ctx->device));
-    ctx->genome = {nullptr, nullptr, nullptr, 0};
+    ctx->genome = {nullptr, nullptr, nullptr, 0, 0};
     if (n_contigs == 0) return GCB_OK;
     int rc;
     if ((rc = reserve(ctx, ctx->g_off, (size_t)n_contigs * 8)) != GCB_OK) return rc;
@@ -233,6 +233,7 @@ int gcb_set_reference_device(gcb_ctx *ctx, const uint8_t *packed4_dev, int64_t p
     ctx->genome.contig_off = (const int64_t *)ctx->g_off.p;
     ctx->genome.contig_len = (const int64_t *)ctx->g_len.p;
     ctx->genome.n_contigs = n_contigs;
+    ctx->genome.packed_bytes = packed_bytes;
     return GCB_OK;
 }
 
@@ -242,7 +243,7 @@ int gcb_set_reference(gcb_ctx *ctx, const uint8_t *packed4, int64_t packed_bytes
         return fail(ctx, GCB_ERR_ARG, "gcb_set_reference: bad argument");
     GCB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n_contigs == 0) {
-        ctx->genome = {nullptr, nullptr, nullptr, 0};
+        ctx->genome = {nullptr, nullptr, nullptr, 0, 0};
         return GCB_OK;
     }
     int rc;

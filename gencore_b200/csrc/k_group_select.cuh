@@ -127,6 +127,7 @@ struct SideChoice {
     int k;       // its index in the family
     int len;     // voted columns (group.cpp:354-360)
     bool fits;   // every VoteRead field fits its 16 bits
+    bool uniform;  // every voter shares the template's geometry (FS_UNIFORM)
 };
 
 // The VoteRead of read slot sk (see device_common.cuh); `fits` is cleared when a field overflows.
@@ -177,7 +178,7 @@ GCB_DEV VoteRead make_vote_read(const BatchView &b, const Workspace &ws, int64_t
 
 GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gcb_options &o, int mb, int m, int side, int slot, int64_t slab0) {
     const int lane = lane_id();
-    const SideChoice none = {-1, 0, 0, true};
+    const SideChoice none = {-1, 0, 0, true, false};
     const bool isLeft = side == 0;
     const int thr = o.skip_low_complexity_cluster_threshold;
 #define GCB_SLOT(k) (2 * ws.members[mb + (k)] + side)
@@ -297,6 +298,18 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
     ch.k = best_k;
     ch.len = od.n_cigar == 0 ? warp_min(mn) : od.l_qseq;  // group.cpp:354-360: no CIGAR => only the shortest read's columns
     ch.fits = __all_sync(FULL, fits);
+    // FS_UNIFORM: every voter is as long as the template, is read at the template's columns and meets its mate
+    // through the same overlap window (true for every family of a fixed-length library)
+    __syncwarp();
+    const VoteRead tv = vr[best_k];
+    bool uni = ch.len == od.l_qseq && tv.shift == 0 && tv.own_l == od.l_qseq;
+    for (int k = lane; k < m; k += WARP) {
+        const VoteRead v = vr[k];
+        if (v.own_off4 == VR_NO_VOTE) continue;
+        uni = uni && v.own_l == tv.own_l && v.shift == 0 && v.ov_len == tv.ov_len &&
+              (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l));
+    }
+    ch.uniform = __all_sync(FULL, uni);
     return ch;
 #undef GCB_SLOT
 #undef GCB_HAVE
@@ -344,7 +357,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
 
     const int64_t slab0 = ws.slab_off[c];
     for (int i = G + lane; i < n; i += WARP) {  // slots that hold no family
-        const FsDesc nofs = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, {0, 0}};
+        const FsDesc nofs = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, 0};
         ws.fs_desc[2 * (int64_t)(p0 + i)] = nofs;
         ws.fs_desc[2 * (int64_t)(p0 + i) + 1] = nofs;
     }
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
         gr.umi_pair = -1;
         const int first = ws.members[mb];
         uint8_t mode0 = SIDE_NONE;
-        SideChoice ch[2] = {{-1, 0, 0, true}, {-1, 0, 0, true}};
+        SideChoice ch[2] = {{-1, 0, 0, true, false}, {-1, 0, 0, true, false}};
         if (m == 1 && b.reads[2 * (int64_t)first + 1].l_qseq < 0) {  // group.cpp:73-77: passes through untouched
             gr.merge_reads = 1;
             if (b.reads[2 * (int64_t)first].l_qseq >= 0) {
@@ -428,18 +441,20 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
         }
         __syncwarp();
         for (int s = 0; s < 2; s++) {
-            FsDesc fd = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, {0, 0}};
+            FsDesc fd = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, 0};
             if (gr.tmpl_read[s] >= 0) {
                 const gcb_read_desc od = b.reads[gr.tmpl_read[s]];
                 const int l_out = od.l_qseq;
-                fd.pos = od.pos;
-                fd.tmpl = gr.tmpl_read[s];
+                fd.c = c;
                 const uint32_t *ocig = b.cigar + od.cigar_off;
                 if (od.isize != 0 && gv.packed4) {  // group.cpp:362-367 + reference.cpp:33-71
                     const int contig = b.cluster_ref[c];
                     if (contig >= 0 && contig < gv.n_contigs) {
                         const int64_t span = (int64_t)get_ref_offset(ocig, od.n_cigar, ch[s].len - 1) + 1;
-                        if ((int64_t)od.pos + span < gv.contig_len[contig]) fd.flags |= FS_REF_OK;
+                        if ((int64_t)od.pos + span < gv.contig_len[contig]) {
+                            fd.flags |= FS_REF_OK;
+                            fd.ref_nib0 = 2 * gv.contig_off[contig] + od.pos;
+                        }
                     }
                 }
                 if (od.n_cigar == 1) {
@@ -447,14 +462,15 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
                     if (query_consum(op) && ref_consum(op) && cig_len(ocig[0]) >= l_out) fd.flags |= FS_SIMPLE_CIGAR;
                 }
                 gr.out_off[s] = out_rel;  // cluster-relative; the vote kernel rebases it after the scan
-                fd.mb_rel = (uint16_t)(mb - p0);
+                fd.mb = mb;
                 fd.m = (uint16_t)m;
+                if (ch[s].uniform) fd.flags |= FS_UNIFORM;
                 fd.l_out = (uint16_t)l_out;
                 fd.len = (uint16_t)ch[s].len;
                 fd.tmpl_k = (uint16_t)ch[s].k;
                 fd.mode = s == 0 && mode0 == SIDE_COPY ? SIDE_COPY : ws.side_mode[2 * (int64_t)slot + s];
                 fd.out_rel = (uint32_t)out_rel;
-                if (!ch[s].fits || mb - p0 > 0xFFFF || m > 0xFFFF || l_out > 0x7FFF || out_rel > 0xFFFFFFFFll) fd.flags |= FS_NOFIT;
+                if (!ch[s].fits || m > 0xFFFF || l_out > 0x7FFF || out_rel > 0xFFFFFFFFll) fd.flags |= FS_NOFIT;
                 out_rel += record_bytes(l_out);
             }
             if (lane == 0) ws.fs_desc[2 * (int64_t)slot + s] = fd;

@@ -42,8 +42,7 @@ constexpr int VT_OFF_NFS = 16;
 constexpr int VT_OFF_NEXT = 20;
 constexpr int VT_OFF_LMAX = 24;
 constexpr int VT_OFF_WSUM = 32;                                  // VT_WARPS warp totals of the compaction scan
-constexpr int VT_OFF_CPO = 64;                                   // int32[VT_MAX_PAIRS + 2]
-constexpr int VT_OFF_ACC = VT_OFF_CPO + 4 * (VT_MAX_PAIRS + 8);  // int32[VT_MAX_FS]
+constexpr int VT_OFF_ACC = 64;                                   // int32[VT_MAX_FS]
 constexpr int VT_OFF_SLOW = VT_OFF_ACC + 4 * VT_MAX_FS;          // uint32[VT_SLOW_CAP]
 constexpr int VT_OFF_BINS = VT_OFF_SLOW + 4 * VT_SLOW_CAP;       // int32[VT_BIN_COLS][16][4]
 constexpr int VT_OFF_FT = VT_OFF_BINS + 4 * VT_BIN_COLS * 64;    // FsTile[VT_MAX_FS]
@@ -65,8 +64,8 @@ struct __align__(16) FsTile {
     uint16_t cbase4;    // the cluster's slab inside the staged tile, 4-byte units
     uint16_t out4;      // consensus record relative to the tile's first output byte, 4-byte units
     int64_t ref_nib0;   // nibble index of the template's pos in the packed genome (FS_REF_OK)
-    int32_t ref_limit;  // contig length - pos: reference offsets below it exist
-    int32_t tmpl;       // template read slot; its low bit is the side
+    int32_t slot;       // the family's group slot (result row)
+    int32_t reserved;
 };
 static_assert(sizeof(FsTile) == 32 && sizeof(FsDesc) == 32 && sizeof(VoteRead) == 16, "table entry sizes");
 
@@ -96,6 +95,17 @@ inline void tile_copy(void *dst, const void *src, uint32_t bytes, uint64_t *) { 
 // ---- SIMD-in-word helpers ------------------------------------------------------------------------------
 // Bases travel as big-endian nibble words: column k of an 8-column word sits in bits 28-4k..31-4k.
 // Qualities stay little-endian: column k of a 4-column word is byte k.
+// PTX prmt.b32 in its default mode: a selector nibble with bit 3 set replicates the SIGN of the selected byte
+// (the __byte_perm intrinsic masks that bit off, so it cannot be used for the mask widening below)
+#ifndef GCB_SIMT_CHECK
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+#else
+inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return ::simt::prmt(a, b, sel); }
+#endif
 GCB_DEV uint32_t bswap32(uint32_t w) { return __byte_perm(w, 0, 0x0123); }
 GCB_DEV int clamp_int(int v, int lo, int hi) { return min(max(v, lo), hi); }
 // columns >= s of an 8-column nibble word (s is clamped to 0..8)
@@ -103,8 +113,8 @@ GCB_DEV uint32_t nib_ge(int s) { return __funnelshift_rc(0xFFFFFFFFu, 0u, 4u * (
 // columns [a, z) of an 8-column nibble word
 GCB_DEV uint32_t nib_range(int a, int z) { return nib_ge(a) & ~nib_ge(z); }
 // a nibble mask (all-ones or all-zero nibbles) widened to the byte masks of its columns 0-3 and 4-7
-GCB_DEV uint32_t bytes_lo(uint32_t nm) { return __byte_perm(nm, nm << 4, 0xEAFB); }
-GCB_DEV uint32_t bytes_hi(uint32_t nm) { return __byte_perm(nm, nm << 4, 0xC8D9); }
+GCB_DEV uint32_t bytes_lo(uint32_t nm) { return prmt(nm, nm << 4, 0xEAFBu); }
+GCB_DEV uint32_t bytes_hi(uint32_t nm) { return prmt(nm, nm << 4, 0xC8D9u); }
 // byte flags (0xFF / 0x00) of columns 0-3 (a) and 4-7 (b) narrowed to a nibble mask
 GCB_DEV uint32_t nibs_of_bytes(uint32_t a, uint32_t b) {
     return (__byte_perm(a, b, 0x0246) & 0xF0F0F0F0u) | (__byte_perm(a, b, 0x1357) & 0x0F0F0F0Fu);
@@ -173,6 +183,7 @@ GCB_DEV bool fetch_ent(const uint8_t *cb, const VoteRead &v, int i, int side, co
 
 struct TileCtx {
     const BatchView *b;
+    const ResultView *r;
     const GenomeView *gv;
     const gcb_options *o;
     const uint8_t *slab;
@@ -181,23 +192,13 @@ struct TileCtx {
     int32_t *acc;
     uint8_t *out0;  // out_payload + the tile's first output byte
 };
-
-// cluster (relative to c0) that owns pair position `pos`
-GCB_DEV int cluster_of(const int32_t *cpo, int nc, int pos) {
-    int lo = 0, hi = nc;  // first index in (0, nc] whose offset is > pos; cpo[nc] > pos always
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (cpo[mid] > pos) hi = mid;
-        else lo = mid + 1;
-    }
-    return lo - 1;
-}
+GCB_DEV int fs_side(const FsTile &ft) { return (ft.flags & FS_SIDE1) ? 1 : 0; }
 
 // group.cpp:376-393 for one read of one slow column: its vote goes into the column's sixteen bins
 // {count, sum of scores, sum of qualities, best quality}
 GCB_DEV void slow_histogram(const TileCtx &t, const FsTile &ft, int col, int e, int32_t *bins) {
     int base, qual, score;
-    if (!fetch_ent(t.slab + 4 * (int)ft.cbase4, t.vr[ft.ent0 + e], col, ft.tmpl & 1, *t.o, base, qual, score)) return;
+    if (!fetch_ent(t.slab + 4 * (int)ft.cbase4, t.vr[ft.ent0 + e], col, fs_side(ft), *t.o, base, qual, score)) return;
     int32_t *bin = bins + 4 * base;
     atomicAdd(bin, 1);
     atomicAdd(bin + 1, score);
@@ -209,7 +210,7 @@ GCB_DEV void slow_histogram(const TileCtx &t, const FsTile &ft, int col, int e, 
 GCB_DEV void slow_decide(const TileCtx &t, int f, int col, const int32_t *bins) {
     const gcb_options &o = *t.o;
     const FsTile ft = t.ft[f];
-    const int side = ft.tmpl & 1;
+    const int side = fs_side(ft);
     const uint8_t *cb = t.slab + 4 * (int)ft.cbase4;
     const VoteRead *ents = t.vr + ft.ent0;
     const VoteRead tv = ents[ft.tmpl_k];
@@ -240,11 +241,11 @@ GCB_DEV void slow_decide(const TileCtx &t, int f, int col, const int32_t *bins) 
         if (ft.flags & FS_REF_OK) {  // group.cpp:430-439
             int refpos = col;
             if (!(ft.flags & FS_SIMPLE_CIGAR)) {
-                const gcb_read_desc od = t.b->reads[ft.tmpl];
+                const gcb_read_desc od = t.b->reads[t.r->groups[ft.slot].tmpl_read[side]];
                 refpos = get_ref_offset(t.b->cigar + od.cigar_off, od.n_cigar, col);
             }
-            if (refpos >= 0 && refpos < ft.ref_limit) {
-                const int64_t nib = ft.ref_nib0 + refpos;
+            const int64_t nib = ft.ref_nib0 + refpos;
+            if (refpos >= 0 && nib >= 0 && (nib >> 1) < t.gv->packed_bytes) {  // the bound only guards malformed CIGARs
                 const uint8_t two = t.gv->packed4[nib >> 1];
                 ref4 = genome_nibble_to_bam((nib & 1) ? (two >> 4) : (two & 0xF));
             }
@@ -295,7 +296,7 @@ GCB_DEV void slow_inline(const TileCtx &t, int f, int col) {
     if (col < (int)ft.len)
         for (int e = 0; e < (int)ft.m; e++) {
             int base, qual, score;
-            if (!fetch_ent(t.slab + 4 * (int)ft.cbase4, t.vr[ft.ent0 + e], col, ft.tmpl & 1, *t.o, base, qual, score)) continue;
+            if (!fetch_ent(t.slab + 4 * (int)ft.cbase4, t.vr[ft.ent0 + e], col, fs_side(ft), *t.o, base, qual, score)) continue;
             bins[4 * base]++;
             bins[4 * base + 1] += score;
             bins[4 * base + 2] += qual;
@@ -314,13 +315,36 @@ GCB_DEV void rollback_record(const TileCtx &t, int f) {
     const uint8_t *tseq = cb + 4 * (int)tv.own_off4 + qbytes;
     for (int col = 0; col < l_out; col++) {
         int base, qual, sc;
-        fetch_ent(cb, tv, col, ft.tmpl & 1, *t.o, base, qual, sc);
+        fetch_ent(cb, tv, col, fs_side(ft), *t.o, base, qual, sc);
         out[col] = (uint8_t)qual;
     }
     for (int k = 0; k < (l_out + 1) >> 1; k++) out[qbytes + k] = tseq[k];
 }
 
-__global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o,
+// what a lane needs to know about its sixteen columns of a record of l_out bases of which `len` are voted
+struct ChunkMasks {
+    uint32_t vn0, vn1;   // voted columns, nibble masks of columns 0-7 and 8-15
+    uint32_t vb[4];      // voted columns, byte masks of the four quality words
+    uint32_t rb[4];      // columns of the record (l_out), byte masks
+    uint32_t kn0, kn1;   // nibbles the record keeps: its columns plus the odd tail nibble
+    int nvote;
+};
+GCB_DEV ChunkMasks make_masks(int l_out, int len, int col0) {
+    ChunkMasks c;
+    c.nvote = clamp_int(len - col0, 0, VT_CHUNK);
+    c.vn0 = nib_range(0, c.nvote);
+    c.vn1 = nib_range(0, c.nvote - 8);
+    c.vb[0] = bytes_lo(c.vn0); c.vb[1] = bytes_hi(c.vn0); c.vb[2] = bytes_lo(c.vn1); c.vb[3] = bytes_hi(c.vn1);
+    const int nv = clamp_int(l_out - col0, 0, VT_CHUNK);
+    const uint32_t rn0 = nib_range(0, nv), rn1 = nib_range(0, nv - 8);
+    c.rb[0] = bytes_lo(rn0); c.rb[1] = bytes_hi(rn0); c.rb[2] = bytes_lo(rn1); c.rb[3] = bytes_hi(rn1);
+    const int nk = clamp_int(2 * ((l_out + 1) >> 1) - col0, 0, VT_CHUNK);
+    c.kn0 = nib_range(0, nk);
+    c.kn1 = nib_range(0, nk - 8);
+    return c;
+}
+
+__global__ void __launch_bounds__(VT_THREADS, 3) vote_tiled_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o,
                                                                 int32_t slab_cap, int32_t implied) {
     GCB_DYN_SMEM(smem);
     uint64_t *bar = (uint64_t *)(smem + VT_OFF_BAR);
@@ -330,22 +354,21 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
     int *s_next = (int *)(smem + VT_OFF_NEXT);
     int *s_lmax = (int *)(smem + VT_OFF_LMAX);
     uint32_t *s_wsum = (uint32_t *)(smem + VT_OFF_WSUM);
-    int32_t *s_cpo = (int32_t *)(smem + VT_OFF_CPO);
     int32_t *s_acc = (int32_t *)(smem + VT_OFF_ACC);
     uint32_t *s_slow = (uint32_t *)(smem + VT_OFF_SLOW);
     int32_t *s_bins = (int32_t *)(smem + VT_OFF_BINS);
     FsTile *s_ft = (FsTile *)(smem + VT_OFF_FT);
     VoteRead *s_vr = (VoteRead *)(smem + VT_OFF_VR);
-    const uint32_t *s_vr32 = (const uint32_t *)(smem + VT_OFF_VR);
     uint8_t *slab = smem + VT_OFF_SLAB;
+#define GCB_LDS32(off) (*(const uint32_t *)(smem + (off)))
 
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const TileDir t0 = ws.tile_dir[blockIdx.x], t1 = ws.tile_dir[blockIdx.x + 1];
     const int c0 = t0.c0, c1 = t1.c0;
     if (c0 >= c1) return;
-    const int P0 = t0.p0, NP = t1.p0 - t0.p0, NC = c1 - c0;
+    const int P0 = t0.p0, NP = t1.p0 - t0.p0;
     const int64_t slab_bytes = t1.slab0 - t0.slab0;
-    if (NP > VT_MAX_PAIRS || NC > VT_MAX_PAIRS || slab_bytes > slab_cap) {  // not a tile for this kernel
+    if (NP > VT_MAX_PAIRS || slab_bytes > slab_cap) {  // not a tile for this kernel
         if (tid == 0) {
             ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = (int32_t)blockIdx.x;
             GCB_COUNT(1, 1);
@@ -367,31 +390,22 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
         if (slab_bytes > 0) tile_copy(slab, b.payload + t0.slab0, (uint32_t)slab_bytes, bar);
         tile_copy(s_vr, ws.vote_reads + 2 * (int64_t)P0, tb, bar);
     }
-    // ---- prologue: one thread per pair position = per possible family slot
+    // ---- prologue: one thread per pair position = per possible family slot; FsDesc is self-contained
     FsDesc fd[2];
     fd[0].mode = fd[1].mode = SIDE_NONE;
-    fd[0].flags = fd[1].flags = 0;
+    fd[0].c = fd[1].c = c0;
     if (tid < NP) {
         fd[0] = ws.fs_desc[2 * (int64_t)(P0 + tid)];
         fd[1] = ws.fs_desc[2 * (int64_t)(P0 + tid) + 1];
     }
-    for (int i = tid; i <= NC; i += VT_THREADS) s_cpo[i] = b.cluster_pair_off[c0 + i];
     const int64_t out_base0 = ws.scan_block[c0 / SCAN_BLOCK] + ws.cluster_out_off[c0];
-    __syncthreads();
+    for (int k = tid; k < VT_BIN_COLS * 64; k += VT_THREADS) s_bins[k] = 0;  // the first pass of slow columns finds clean bins
     const bool live0 = fd[0].mode != SIDE_NONE, live1 = fd[1].mode != SIDE_NONE;
-    int pos_rel = 0;
-    int64_t c_slab = 0, c_out = 0, ref_off = 0, ref_len = 0;
+    int64_t c_slab = 0, c_out = 0;
     if (live0 || live1) {
-        const int ci = cluster_of(s_cpo, NC, P0 + tid);
-        const int c = c0 + ci;
-        pos_rel = s_cpo[ci] - P0;
+        const int c = live0 ? fd[0].c : fd[1].c;
         c_slab = ws.slab_off[c] - t0.slab0;
         c_out = ws.scan_block[c / SCAN_BLOCK] + ws.cluster_out_off[c] - out_base0;
-        if ((fd[0].flags | fd[1].flags) & FS_REF_OK) {
-            const int contig = b.cluster_ref[c];
-            ref_off = gv.contig_off[contig];
-            ref_len = gv.contig_len[contig];
-        }
     }
     // compact index of the live family sides (exclusive scan of the live counts)
     int fidx0;
@@ -412,26 +426,25 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
             if (pre + mine > (uint32_t)VT_MAX_FS) *s_nofit = 1;
         }
     }
-    {
+    if (live0 || live1) {
         int lneed = 1, fidx = fidx0;
         for (int side = 0; side < 2; side++) {
             if (fd[side].mode == SIDE_NONE) continue;
             const FsDesc d = fd[side];
             FsTile ft;
-            ft.ent0 = (uint16_t)(2 * (pos_rel + (int)d.mb_rel) + side * (int)d.m);
+            ft.ent0 = (uint16_t)(2 * (d.mb - P0) + side * (int)d.m);
             ft.m = d.m;
             ft.l_out = d.l_out;
             ft.len = d.len;
             ft.tmpl_k = d.tmpl_k;
             ft.mode = d.mode;
-            ft.flags = d.flags;
+            ft.flags = (uint8_t)(d.flags | (side ? FS_SIDE1 : 0));
             ft.cbase4 = (uint16_t)(c_slab >> 2);
             const int64_t orel = c_out + d.out_rel;
             ft.out4 = (uint16_t)(orel >> 2);
-            ft.ref_nib0 = 2 * ref_off + d.pos;
-            const int64_t lim = ref_len - d.pos;
-            ft.ref_limit = (int32_t)(lim > 0x7FFFFFFF ? 0x7FFFFFFF : (lim < 0 ? 0 : lim));
-            ft.tmpl = d.tmpl;
+            ft.ref_nib0 = d.ref_nib0;
+            ft.slot = P0 + tid;
+            ft.reserved = 0;
             const int l = d.l_out;
             const int chunks = max((GCB_ALIGN4(l) + 15) >> 4, (GCB_ALIGN4((l + 1) >> 1) + 7) >> 3);
             if ((d.flags & FS_NOFIT) || (orel >> 2) > 0xFFFF || chunks > WARP) *s_nofit = 1;
@@ -459,25 +472,9 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
     }
     if (tid == 0) GCB_COUNT(0, 1);
     const int nfs = *s_nfs;
-    // does every voter of the family side share the template's geometry?  (one thread per family side)
-    for (int f = tid; f < nfs; f += VT_THREADS) {
-        const FsTile ft = s_ft[f];
-        if (ft.mode == SIDE_NONE || ft.mode == SIDE_COPY) continue;
-        const VoteRead tv = s_vr[ft.ent0 + ft.tmpl_k];
-        bool uni = ft.len == ft.l_out && tv.shift == 0 && (int)tv.own_l == (int)ft.l_out;
-        for (int e = 0; e < (int)ft.m && uni; e++) {
-            const VoteRead v = s_vr[ft.ent0 + e];
-            if (v.own_off4 == VR_NO_VOTE) continue;
-            uni = v.own_l == tv.own_l && v.shift == 0 && v.ov_len == tv.ov_len &&
-                  (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l));
-        }
-        if (uni) s_ft[f].flags = ft.flags | FS_UNIFORM;
-        GCB_COUNT(uni ? 4 : 5, 1);
-    }
-    __syncthreads();
 
     TileCtx t;
-    t.b = &b; t.gv = &gv; t.o = &o;
+    t.b = &b; t.r = &r; t.gv = &gv; t.o = &o;
     t.slab = slab; t.vr = s_vr; t.ft = s_ft; t.acc = s_acc;
     t.out0 = r.out_payload + out_base0;
 
@@ -487,6 +484,8 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
     const int nb = (nfs + S - 1) / S;
     const int sub = lane / L, j = lane - sub * L;
     const int col0 = VT_CHUNK * j;
+    const int common_l = s_ft[0].l_out;  // the masks of the tile's usual record length are computed once
+    const ChunkMasks cm_common = make_masks(common_l, common_l, col0);
     for (;;) {
         int bundle = 0;
         if (lane == 0) bundle = atomicAdd(s_next, 1);
@@ -501,83 +500,77 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
         const bool mine = ft.mode != SIDE_NONE && col0 < max(qbytes, 2 * sbytes);  // this lane owns words of the record
         const int m = mine && ft.mode != SIDE_COPY ? (int)ft.m : 0;
         const int mmax = __reduce_max_sync(FULL, m);
-        const uint8_t *cb = slab + 4 * (int)ft.cbase4;
-        const uint32_t *ent32 = s_vr32 + 4 * (int)ft.ent0;
-        const VoteRead *ents = s_vr + ft.ent0;
+        const int cb = VT_OFF_SLAB + 4 * (int)ft.cbase4;  // byte offsets into the CTA's shared memory
+        const int ento = VT_OFF_VR + 16 * (int)ft.ent0;
         VoteRead tv = {0, 0, 0, 0, 0, 0, 0, 0};
-        uint32_t tq[4] = {0u, 0u, 0u, 0u}, tbe0 = 0u, tbe1 = 0u;
+        uint32_t tbe0 = 0u, tbe1 = 0u;
+        int trec = cb;
         if (mine) {
-            tv = ents[ft.tmpl_k];
-            const uint8_t *trec = cb + 4 * (int)tv.own_off4;
-            const uint32_t *tp = (const uint32_t *)trec;
-#pragma unroll
-            for (int k = 0; k < 4; k++) tq[k] = word_or_zero(tp, (col0 >> 2) + k, qbytes >> 2);
-            const uint32_t *sp = (const uint32_t *)(trec + qbytes);
-            tbe0 = bswap32(word_or_zero(sp, 2 * j, sbytes >> 2));
-            tbe1 = bswap32(word_or_zero(sp, 2 * j + 1, sbytes >> 2));
+            tv = s_vr[ft.ent0 + ft.tmpl_k];
+            trec = cb + 4 * (int)tv.own_off4;
+            if (8 * j < sbytes) tbe0 = bswap32(GCB_LDS32(trec + qbytes + 8 * j));
+            if (8 * j + 4 < sbytes) tbe1 = bswap32(GCB_LDS32(trec + qbytes + 8 * j + 4));
         }
-        uint32_t mq[4] = {0u, 0u, 0u, 0u}, dis0 = 0u, dis1 = 0u;
-        const int nvote = clamp_int(len - col0, 0, VT_CHUNK);  // voted columns of this chunk
+        ChunkMasks cm = cm_common;
+        if (l_out != common_l || len != l_out) cm = make_masks(l_out, len, col0);
+        if (mine && j == 0 && ft.mode != SIDE_COPY) GCB_COUNT((ft.flags & FS_UNIFORM) ? 4 : 5, 1);
+        // per-column maxima live in 16-bit lanes (VIMNMX.U16x2 is native, a per-byte maximum is seven instructions):
+        // mo[k] tracks bytes 1 and 3 of quality word k in the high byte of each half, me[k] bytes 0 and 2 (word << 8)
+        uint32_t mo[4] = {0u, 0u, 0u, 0u}, me[4] = {0u, 0u, 0u, 0u}, dis0 = 0u, dis1 = 0u;
         if (ft.flags & FS_UNIFORM) {
             // hoisted geometry: every voter is read at the template's columns and meets its mate at the same offset
             const int x = (int)tv.ov_own - col0;
             const int y = x - (int)tv.ov_mate;
-            const int oa = max(max(0, x), y), oz = min(min(nvote, x + (int)tv.ov_len), y + (int)tv.mate_l);
+            const int oa = max(max(0, x), y), oz = min(min(cm.nvote, x + (int)tv.ov_len), y + (int)tv.mate_l);
             const bool has_ov = tv.ov_len > 0 && oz > oa;
             const uint32_t om0 = has_ov ? nib_range(oa, oz) : 0u, om1 = has_ov ? nib_range(oa - 8, oz - 8) : 0u;
-            const int mqb = GCB_ALIGN4(tv.mate_l), mnw = GCB_ALIGN4((tv.mate_l + 1) >> 1) >> 2;
+            const int mnw = GCB_ALIGN4((tv.mate_l + 1) >> 1) >> 2;
             const int ms = 0 - y, mw0 = ms >> 3;
             const unsigned msh = (unsigned)(ms & 7) * 4u;
             const bool p0 = has_ov && (unsigned)mw0 < (unsigned)mnw, p1 = has_ov && (unsigned)(mw0 + 1) < (unsigned)mnw,
                        p2 = has_ov && (unsigned)(mw0 + 2) < (unsigned)mnw;
-            const int qoff = col0, soff = qbytes + 8 * j, moff = mqb + 4 * mw0;
+            const int qoff = cb + col0, soff = cb + qbytes + 8 * j, moff = cb + GCB_ALIGN4(tv.mate_l) + 4 * mw0;
             for (int e = 0; e < mmax; e++) {
                 if (e >= m) continue;
-                const uint32_t w = ent32[4 * e];
+                const uint32_t w = GCB_LDS32(ento + 16 * e);
                 if ((w & 0xFFFFu) == VR_NO_VOTE) continue;
-                const uint8_t *rec = cb + 4 * (int)(w & 0xFFFFu);
-                const uint32_t *qp = (const uint32_t *)(rec + qoff);
-                mq[0] = __vmaxu4(mq[0], qp[0]);
-                mq[1] = __vmaxu4(mq[1], qp[1]);
-                mq[2] = __vmaxu4(mq[2], qp[2]);
-                mq[3] = __vmaxu4(mq[3], qp[3]);
-                const uint32_t *sp = (const uint32_t *)(rec + soff);
-                const uint32_t be0 = bswap32(sp[0]), be1 = bswap32(sp[1]);
+                const int ro = (int)((w << 2) & 0x3FFFCu);
+                const uint32_t q0 = GCB_LDS32(qoff + ro), q1 = GCB_LDS32(qoff + ro + 4), q2 = GCB_LDS32(qoff + ro + 8), q3 = GCB_LDS32(qoff + ro + 12);
+                mo[0] = __vmaxu2(mo[0], q0); me[0] = __vmaxu2(me[0], q0 << 8);
+                mo[1] = __vmaxu2(mo[1], q1); me[1] = __vmaxu2(me[1], q1 << 8);
+                mo[2] = __vmaxu2(mo[2], q2); me[2] = __vmaxu2(me[2], q2 << 8);
+                mo[3] = __vmaxu2(mo[3], q3); me[3] = __vmaxu2(me[3], q3 << 8);
+                const uint32_t be0 = bswap32(GCB_LDS32(soff + ro)), be1 = bswap32(GCB_LDS32(soff + ro + 4));
                 dis0 |= be0 ^ tbe0;
                 dis1 |= be1 ^ tbe1;
                 if (has_ov) {  // pair.cpp:133-170: a base that differs from its mate's is never a fast column
-                    const uint32_t *mp = (const uint32_t *)(cb + 4 * (int)(w >> 16) + moff);
-                    const uint32_t a = p0 ? bswap32(mp[0]) : 0u, c = p1 ? bswap32(mp[1]) : 0u, d = p2 ? bswap32(mp[2]) : 0u;
+                    const int mo_ = moff + (int)((w >> 14) & 0x3FFFCu);
+                    const uint32_t a = p0 ? bswap32(GCB_LDS32(mo_)) : 0u, c = p1 ? bswap32(GCB_LDS32(mo_ + 4)) : 0u,
+                                   d = p2 ? bswap32(GCB_LDS32(mo_ + 8)) : 0u;
                     dis0 |= (be0 ^ __funnelshift_l(c, a, msh)) & om0;
                     dis1 |= (be1 ^ __funnelshift_l(d, c, msh)) & om1;
                 }
             }
-            // the loop read whole words: keep the voted columns only
-            const uint32_t vm0 = nib_range(0, nvote), vm1 = nib_range(0, nvote - 8);
-            dis0 &= vm0;
-            dis1 &= vm1;
-            mq[0] &= bytes_lo(vm0);
-            mq[1] &= bytes_hi(vm0);
-            mq[2] &= bytes_lo(vm1);
-            mq[3] &= bytes_hi(vm1);
         } else {
             for (int e = 0; e < mmax; e++) {
                 if (e >= m) continue;
-                const VoteRead v = ents[e];
+                const VoteRead v = s_vr[ft.ent0 + e];
                 if (v.own_off4 == VR_NO_VOTE || v.own_l == 0) continue;
                 const int rp0 = col0 + v.shift;
-                const int a = max(0, 0 - rp0), z = min(nvote, (int)v.own_l - rp0);
+                const int a = max(0, 0 - rp0), z = min(cm.nvote, (int)v.own_l - rp0);
                 if (z <= a) continue;
-                const uint8_t *rec = cb + 4 * (int)v.own_off4;
+                const uint8_t *rec = smem + cb + 4 * (int)v.own_off4;
                 const int rq = GCB_ALIGN4(v.own_l);
                 uint32_t q[4], be0, be1;
                 fetch16q(rec, rq, rp0, q);
                 fetch16b(rec + rq, GCB_ALIGN4((v.own_l + 1) >> 1), rp0, be0, be1);
                 const uint32_t vm0 = nib_range(a, z), vm1 = nib_range(a - 8, z - 8);
-                mq[0] = __vmaxu4(mq[0], q[0] & bytes_lo(vm0));
-                mq[1] = __vmaxu4(mq[1], q[1] & bytes_hi(vm0));
-                mq[2] = __vmaxu4(mq[2], q[2] & bytes_lo(vm1));
-                mq[3] = __vmaxu4(mq[3], q[3] & bytes_hi(vm1));
+                q[0] &= bytes_lo(vm0); q[1] &= bytes_hi(vm0); q[2] &= bytes_lo(vm1); q[3] &= bytes_hi(vm1);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    mo[k] = __vmaxu2(mo[k], q[k]);
+                    me[k] = __vmaxu2(me[k], q[k] << 8);
+                }
                 dis0 |= (be0 ^ tbe0) & vm0;
                 dis1 |= (be1 ^ tbe1) & vm1;
                 if (v.ov_len > 0) {
@@ -589,7 +582,7 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
                     const int oa = max(max(a, x), y);
                     const int oz = min(min(z, x + (int)v.ov_len), y + (int)v.mate_l);
                     if (oz > oa) {
-                        const uint8_t *mrec = cb + 4 * (int)v.mate_off4;
+                        const uint8_t *mrec = smem + cb + 4 * (int)v.mate_off4;
                         uint32_t mb0, mb1;
                         fetch16b(mrec + GCB_ALIGN4(v.mate_l), GCB_ALIGN4((v.mate_l + 1) >> 1), 0 - y, mb0, mb1);
                         dis0 |= (be0 ^ mb0) & nib_range(oa, oz);
@@ -600,37 +593,33 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
         }
         if (!mine) continue;
         // ---- what the record gets: qualities = the maxima (fast columns), bases = the template's
-        const int nv = clamp_int(l_out - col0, 0, VT_CHUNK);                  // columns of the record in this chunk
-        const int nk = clamp_int(2 * ((l_out + 1) >> 1) - col0, 0, VT_CHUNK);  // nibbles the record keeps (odd tail included)
-        const uint32_t rm0 = nib_range(0, nv), rm1 = nib_range(0, nv - 8);
         uint32_t oq[4];
         uint32_t slow0 = 0u, slow1 = 0u;
         if (ft.mode == SIDE_COPY) {  // group.cpp:73-77: the record itself
 #pragma unroll
-            for (int k = 0; k < 4; k++) oq[k] = tq[k];
+            for (int k = 0; k < 4; k++) oq[k] = col0 + 4 * k < qbytes ? GCB_LDS32(trec + col0 + 4 * k) : 0u;
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) oq[k] = mq[k];
-            GCB_COUNT(2, nvote);
+            for (int k = 0; k < 4; k++) oq[k] = prmt(mo[k], me[k], 0x3715u) & cm.vb[k];  // (the hoisted loop read whole words)
+            dis0 &= cm.vn0;
+            dis1 &= cm.vn1;
+            GCB_COUNT(2, cm.nvote);
             if (implied && len == l_out) {
-                const uint32_t lowq0 = nibs_of_bytes(~__vcmpgeu4(mq[0], mod4), ~__vcmpgeu4(mq[1], mod4));
-                const uint32_t lowq1 = nibs_of_bytes(~__vcmpgeu4(mq[2], mod4), ~__vcmpgeu4(mq[3], mod4));
-                slow0 = (dis0 | lowq0) & nib_range(0, nvote);
-                slow1 = (dis1 | lowq1) & nib_range(0, nvote - 8);
+                const uint32_t lowq0 = nibs_of_bytes(~__vcmpgeu4(oq[0], mod4), ~__vcmpgeu4(oq[1], mod4));
+                const uint32_t lowq1 = nibs_of_bytes(~__vcmpgeu4(oq[2], mod4), ~__vcmpgeu4(oq[3], mod4));
+                slow0 = (dis0 | lowq0) & cm.vn0;
+                slow1 = (dis1 | lowq1) & cm.vn1;
             } else {  // without `implied`, or with columns that are not voted, every column of the record is slow
-                slow0 = rm0;
-                slow1 = rm1;
+                slow0 = nibs_of_bytes(cm.rb[0], cm.rb[1]);
+                slow1 = nibs_of_bytes(cm.rb[2], cm.rb[3]);
             }
         }
         uint8_t *out = t.out0 + 4 * (int64_t)ft.out4;
-        {
-            const uint32_t qm[4] = {bytes_lo(rm0), bytes_hi(rm0), bytes_lo(rm1), bytes_hi(rm1)};
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (col0 + 4 * k < qbytes) *(uint32_t *)(out + col0 + 4 * k) = oq[k] & qm[k];
-            if (8 * j < sbytes) *(uint32_t *)(out + qbytes + 8 * j) = bswap32(tbe0 & nib_range(0, nk));
-            if (8 * j + 4 < sbytes) *(uint32_t *)(out + qbytes + 8 * j + 4) = bswap32(tbe1 & nib_range(0, nk - 8));
-        }
+        for (int k = 0; k < 4; k++)
+            if (col0 + 4 * k < qbytes) *(uint32_t *)(out + col0 + 4 * k) = oq[k] & cm.rb[k];
+        if (8 * j < sbytes) *(uint32_t *)(out + qbytes + 8 * j) = bswap32(tbe0 & cm.kn0);
+        if (8 * j + 4 < sbytes) *(uint32_t *)(out + qbytes + 8 * j + 4) = bswap32(tbe1 & cm.kn1);
         // queue the slow columns (one or two per family side of a clean library)
         for (int wsel = 0; wsel < 2; wsel++) {
             uint32_t sm = wsel ? slow1 : slow0;
@@ -651,8 +640,10 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
         const int n = min(*s_nslow, VT_SLOW_CAP);
         for (int base = 0; base < n; base += VT_BIN_COLS) {
             const int cnt = min(VT_BIN_COLS, n - base);
-            for (int k = tid; k < cnt * 64; k += VT_THREADS) s_bins[k] = 0;
-            __syncthreads();
+            if (base > 0) {
+                for (int k = tid; k < cnt * 64; k += VT_THREADS) s_bins[k] = 0;
+                __syncthreads();
+            }
             const int ci = tid >> 3, sub8 = tid & 7;
             if (ci < cnt) {
                 const uint32_t code = s_slow[base + ci];
@@ -670,7 +661,7 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
         }
     }
     // ---- per family side: diff, mismatchInc, rollback, absolute output offset
-    if (tid < NP) {
+    if (live0 || live1) {
         int fidx = fidx0;
         for (int side = 0; side < 2; side++) {
             if (fd[side].mode == SIDE_NONE) continue;
@@ -686,6 +677,7 @@ __global__ void __launch_bounds__(VT_THREADS) vote_tiled_kernel(BatchView b, Res
             gr->out_off[side] = out_base0 + 4 * (int64_t)ft.out4;
         }
     }
+#undef GCB_LDS32
 }
 
 }  // namespace gcb

@@ -308,17 +308,22 @@ inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return (unsigned)((v << (shift & 31)) >> 32);
 }
-inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+namespace simt {
+// PTX prmt.b32, default mode: selector nibble bit 3 replicates the sign of the selected byte
+inline unsigned prmt(unsigned x, unsigned y, unsigned s) {
     uint64_t v = ((uint64_t)y << 32) | x;
     unsigned r = 0;
     for (int i = 0; i < 4; i++) {
         unsigned sel = (s >> (4 * i)) & 0xF;
         unsigned byte = (unsigned)((v >> (8 * (sel & 7))) & 0xFF);
-        if (sel & 8) byte = (byte & 0x80) ? 0xFFu : 0u;  // sign-replicate mode
+        if (sel & 8) byte = (byte & 0x80) ? 0xFFu : 0u;
         r |= byte << (8 * i);
     }
     return r;
 }
+}  // namespace simt
+// the CUDA intrinsic uses only three bits of every selector nibble (measured on the B200: no sign mode)
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) { return simt::prmt(x, y, s & 0x7777u); }
 inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned shift) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return shift >= 32 ? hi : (unsigned)(v >> shift);
@@ -327,6 +332,9 @@ inline unsigned __vmaxu4(unsigned a, unsigned b) {
     unsigned r = 0;
     for (int i = 0; i < 4; i++) r |= std::max((a >> (8 * i)) & 0xFFu, (b >> (8 * i)) & 0xFFu) << (8 * i);
     return r;
+}
+inline unsigned __vmaxu2(unsigned a, unsigned b) {
+    return std::max(a & 0xFFFFu, b & 0xFFFFu) | (std::max(a >> 16, b >> 16) << 16);
 }
 inline unsigned __vcmpgeu4(unsigned a, unsigned b) {
     unsigned r = 0;
