@@ -106,6 +106,21 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 #else
 inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return ::simt::prmt(a, b, sel); }
 #endif
+// a 32-bit word of the CTA's shared memory at `addr` + IMM, where addr is a shared-window address (hot loop only:
+// it keeps the address arithmetic in 32 bits and the immediate in the instruction)
+#ifndef GCB_SIMT_CHECK
+template <int IMM>
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+__device__ __forceinline__ uint32_t smem_base(const void *smem) { return smem_u32(smem); }
+#else
+template <int IMM>
+inline uint32_t lds32(uint32_t addr) { return *(const uint32_t *)(::simt::dyn_smem() + addr + IMM); }
+inline uint32_t smem_base(const void *) { return 0u; }
+#endif
 GCB_DEV uint32_t bswap32(uint32_t w) { return __byte_perm(w, 0, 0x0123); }
 GCB_DEV int clamp_int(int v, int lo, int hi) { return min(max(v, lo), hi); }
 // columns >= s of an 8-column nibble word (s is clamped to 0..8)
@@ -206,8 +221,8 @@ GCB_DEV void slow_histogram(const TileCtx &t, const FsTile &ft, int col, int e, 
     atomicMax(bin + 3, qual);
 }
 
-// group.cpp:395-525 for one slow column whose bins are complete.  Thread-local.
-GCB_DEV void slow_decide(const TileCtx &t, int f, int col, const int32_t *bins) {
+// group.cpp:419-525 for one slow column once its top and second bins are known.  Thread-local.
+GCB_DEV void slow_finish(const TileCtx &t, int f, int col, ColumnTop &top, int total, const int32_t *bins) {
     const gcb_options &o = *t.o;
     const FsTile ft = t.ft[f];
     const int side = fs_side(ft);
@@ -216,27 +231,13 @@ GCB_DEV void slow_decide(const TileCtx &t, int f, int col, const int32_t *bins) 
     const VoteRead tv = ents[ft.tmpl_k];
     const int qbytes = GCB_ALIGN4(ft.l_out);
     uint8_t *out = t.out0 + 4 * (int64_t)ft.out4;
-    int obase = 0, oqual = 0, sc;
-    fetch_ent(cb, tv, col, side, o, obase, oqual, sc);
-    if (col >= ft.len) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
-        out[col] = (uint8_t)oqual;
-        return;
-    }
-    VoteBin obs[16];
-    int nobs = 0, total = 0;
-    for (int k = 0; k < 16; k++) {
-        const int cnt = bins[4 * k];
-        if (cnt > 0) {
-            obs[nobs].base = k; obs[nobs].cnt = cnt; obs[nobs].score = bins[4 * k + 1]; obs[nobs].qual = bins[4 * k + 2]; obs[nobs].maxq = bins[4 * k + 3];
-            total += obs[nobs].score;
-            nobs++;
-        }
-    }
-    const ColumnTop top = column_top(o, obs, nobs, total);
+    column_rules(o, top, total);
     int new_qual;
     if (top.fast) {
         new_qual = top.top.maxq;  // group.cpp:422-426: the base is NOT written
     } else {
+        int obase = 0, oqual = 0, sc;
+        fetch_ent(cb, tv, col, side, o, obase, oqual, sc);
         int ref4 = 0;
         if (ft.flags & FS_REF_OK) {  // group.cpp:430-439
             int refpos = col;
@@ -286,6 +287,82 @@ GCB_DEV void slow_decide(const TileCtx &t, int f, int col, const int32_t *bins) 
         new_qual = co.qual;
     }
     out[col] = (uint8_t)new_qual;
+}
+
+// beyond the voted columns the record keeps what it held (rewritten qualities)
+GCB_DEV void slow_unvoted(const TileCtx &t, int f, int col) {
+    const FsTile ft = t.ft[f];
+    int obase = 0, oqual = 0, sc;
+    fetch_ent(t.slab + 4 * (int)ft.cbase4, t.vr[ft.ent0 + ft.tmpl_k], col, fs_side(ft), *t.o, obase, oqual, sc);
+    (t.out0 + 4 * (int64_t)ft.out4)[col] = (uint8_t)oqual;
+}
+
+// group.cpp:395-417 over complete bins, thread-local (queue overflow path)
+GCB_DEV void slow_decide(const TileCtx &t, int f, int col, const int32_t *bins) {
+    if (col >= (int)t.ft[f].len) {
+        slow_unvoted(t, f, col);
+        return;
+    }
+    VoteBin obs[16];
+    int nobs = 0, total = 0;
+    for (int k = 0; k < 16; k++) {
+        const int cnt = bins[4 * k];
+        if (cnt > 0) {
+            obs[nobs].base = k; obs[nobs].cnt = cnt; obs[nobs].score = bins[4 * k + 1]; obs[nobs].qual = bins[4 * k + 2]; obs[nobs].maxq = bins[4 * k + 3];
+            total += obs[nobs].score;
+            nobs++;
+        }
+    }
+    ColumnTop top = column_top(*t.o, obs, nobs, total);
+    slow_finish(t, f, col, top, total, bins);
+}
+
+// The (score, quality sum, code) order of group.cpp:395-417 as one integer: the scans walk the sixteen bins,
+// replace on a larger score or an equal score and a not-smaller quality sum, so they return the lexicographic
+// maximum with ties going to the larger code; empty bins take part with (0, 0).
+GCB_DEV unsigned long long bin_key(int score, int qual, int code) {
+    return ((unsigned long long)(unsigned)(score + (1 << 23)) << 28) | ((unsigned long long)(unsigned)qual << 4) | (unsigned)code;
+}
+GCB_DEV unsigned long long max_u64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+GCB_DEV unsigned long long min_u64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+
+// One slow column by the eight lanes of an octet: group.cpp:376-393 (histogram, lanes stride the reads), then
+// the two scans of group.cpp:395-417 as a top-2 reduction of the sixteen bin keys (two bins per lane, three
+// shuffle steps), then lane 0 of the octet applies the rules.  Every lane of the warp must call it.
+GCB_DEV void slow_octet(const TileCtx &t, bool active, int f, int col, int32_t *bins, int sub8) {
+    FsTile ft;
+    ft.m = 0; ft.len = 0; ft.ent0 = 0; ft.cbase4 = 0; ft.flags = 0;
+    if (active) ft = t.ft[f];
+    const bool voted = active && col < (int)ft.len;
+    int4 *b4 = (int4 *)bins;
+    const int4 zero = {0, 0, 0, 0};
+    b4[2 * sub8] = zero;
+    b4[2 * sub8 + 1] = zero;
+    __syncwarp();
+    if (voted)
+        for (int e = sub8; e < (int)ft.m; e += 8) slow_histogram(t, ft, col, e, bins);
+    __syncwarp();
+    const int4 x0 = b4[2 * sub8], x1 = b4[2 * sub8 + 1];  // {count, sum of scores, sum of qualities, best quality}
+    const unsigned long long k0 = bin_key(x0.y, x0.z, 2 * sub8), k1 = bin_key(x1.y, x1.z, 2 * sub8 + 1);
+    unsigned long long top = max_u64(k0, k1), sec = min_u64(k0, k1);
+    int total = x0.y + x1.y;
+    for (int off = 1; off < 8; off <<= 1) {
+        const unsigned long long ot = __shfl_xor_sync(FULL, top, off), os = __shfl_xor_sync(FULL, sec, off);
+        total += __shfl_xor_sync(FULL, total, off);
+        sec = max_u64(min_u64(top, ot), max_u64(sec, os));
+        top = max_u64(top, ot);
+    }
+    if (!active || sub8 != 0) return;
+    if (!voted) {
+        slow_unvoted(t, f, col);
+        return;
+    }
+    const int tb = (int)(top & 0xF), sb = (int)(sec & 0xF);
+    const int4 T = b4[tb], S = b4[sb];
+    ColumnTop ct;
+    ct.top.base = tb; ct.top.cnt = T.x; ct.top.score = T.y; ct.top.qual = T.z; ct.top.maxq = T.w;
+    ct.sec.base = sb; ct.sec.cnt = S.x; ct.sec.score = S.y; ct.sec.qual = S.z; ct.sec.maxq = S.w;
+    slow_finish(t, f, col, ct, total, bins);
 }
 
 // a slow column decided by its owner alone (queue overflow): the histogram lives in local memory
@@ -399,7 +476,6 @@ __global__ void __launch_bounds__(VT_THREADS, 3) vote_tiled_kernel(BatchView b, 
         fd[1] = ws.fs_desc[2 * (int64_t)(P0 + tid) + 1];
     }
     const int64_t out_base0 = ws.scan_block[c0 / SCAN_BLOCK] + ws.cluster_out_off[c0];
-    for (int k = tid; k < VT_BIN_COLS * 64; k += VT_THREADS) s_bins[k] = 0;  // the first pass of slow columns finds clean bins
     const bool live0 = fd[0].mode != SIDE_NONE, live1 = fd[1].mode != SIDE_NONE;
     int64_t c_slab = 0, c_out = 0;
     if (live0 || live1) {
@@ -479,10 +555,12 @@ __global__ void __launch_bounds__(VT_THREADS, 3) vote_tiled_kernel(BatchView b, 
     t.out0 = r.out_payload + out_base0;
 
     const uint32_t mod4 = 0x01010101u * (uint32_t)(o.moderate_quality & 0xFF);
-    const int L = *s_lmax;   // lanes per family side
-    const int S = WARP / L;  // family sides per bundle
-    const int nb = (nfs + S - 1) / S;
-    const int sub = lane / L, j = lane - sub * L;
+    const uint32_t sbase = smem_base(smem);
+    // (divisions of small numbers by multiply-and-shift: exact for numerators below 2^16 / divisor)
+    const int L = *s_lmax;                              // lanes per family side, 1..32
+    const int S = (int)((32u * ((65535u / (unsigned)L) + 1u)) >> 16);  // family sides per bundle = 32 / L
+    const int nb = (int)(((unsigned)(nfs + S - 1) * ((65535u / (unsigned)S) + 1u)) >> 16);
+    const int sub = (int)(((unsigned)lane * ((65535u / (unsigned)L) + 1u)) >> 16), j = lane - sub * L;
     const int col0 = VT_CHUNK * j;
     const int common_l = s_ft[0].l_out;  // the masks of the tile's usual record length are computed once
     const ChunkMasks cm_common = make_masks(common_l, common_l, col0);
@@ -529,24 +607,26 @@ __global__ void __launch_bounds__(VT_THREADS, 3) vote_tiled_kernel(BatchView b, 
             const unsigned msh = (unsigned)(ms & 7) * 4u;
             const bool p0 = has_ov && (unsigned)mw0 < (unsigned)mnw, p1 = has_ov && (unsigned)(mw0 + 1) < (unsigned)mnw,
                        p2 = has_ov && (unsigned)(mw0 + 2) < (unsigned)mnw;
-            const int qoff = cb + col0, soff = cb + qbytes + 8 * j, moff = cb + GCB_ALIGN4(tv.mate_l) + 4 * mw0;
-            for (int e = 0; e < mmax; e++) {
+            const uint32_t qbase = sbase + (uint32_t)(cb + col0), sdelta = (uint32_t)(qbytes - col0 + 8 * j),
+                           mbase = sbase + (uint32_t)(cb + GCB_ALIGN4(tv.mate_l) + 4 * mw0);
+            uint32_t ea = sbase + (uint32_t)ento;
+            for (int e = 0; e < mmax; e++, ea += 16) {
                 if (e >= m) continue;
-                const uint32_t w = GCB_LDS32(ento + 16 * e);
+                const uint32_t w = lds32<0>(ea);
                 if ((w & 0xFFFFu) == VR_NO_VOTE) continue;
-                const int ro = (int)((w << 2) & 0x3FFFCu);
-                const uint32_t q0 = GCB_LDS32(qoff + ro), q1 = GCB_LDS32(qoff + ro + 4), q2 = GCB_LDS32(qoff + ro + 8), q3 = GCB_LDS32(qoff + ro + 12);
+                const uint32_t qa = qbase + ((w & 0xFFFFu) << 2), sa = qa + sdelta;
+                const uint32_t q0 = lds32<0>(qa), q1 = lds32<4>(qa), q2 = lds32<8>(qa), q3 = lds32<12>(qa);
+                const uint32_t be0 = bswap32(lds32<0>(sa)), be1 = bswap32(lds32<4>(sa));
                 mo[0] = __vmaxu2(mo[0], q0); me[0] = __vmaxu2(me[0], q0 << 8);
                 mo[1] = __vmaxu2(mo[1], q1); me[1] = __vmaxu2(me[1], q1 << 8);
                 mo[2] = __vmaxu2(mo[2], q2); me[2] = __vmaxu2(me[2], q2 << 8);
                 mo[3] = __vmaxu2(mo[3], q3); me[3] = __vmaxu2(me[3], q3 << 8);
-                const uint32_t be0 = bswap32(GCB_LDS32(soff + ro)), be1 = bswap32(GCB_LDS32(soff + ro + 4));
                 dis0 |= be0 ^ tbe0;
                 dis1 |= be1 ^ tbe1;
                 if (has_ov) {  // pair.cpp:133-170: a base that differs from its mate's is never a fast column
-                    const int mo_ = moff + (int)((w >> 14) & 0x3FFFCu);
-                    const uint32_t a = p0 ? bswap32(GCB_LDS32(mo_)) : 0u, c = p1 ? bswap32(GCB_LDS32(mo_ + 4)) : 0u,
-                                   d = p2 ? bswap32(GCB_LDS32(mo_ + 8)) : 0u;
+                    const uint32_t ma = mbase + ((w >> 16) << 2);
+                    const uint32_t a = p0 ? bswap32(lds32<0>(ma)) : 0u, c = p1 ? bswap32(lds32<4>(ma)) : 0u,
+                                   d = p2 ? bswap32(lds32<8>(ma)) : 0u;
                     dis0 |= (be0 ^ __funnelshift_l(c, a, msh)) & om0;
                     dis1 |= (be1 ^ __funnelshift_l(d, c, msh)) & om1;
                 }
@@ -635,31 +715,18 @@ __global__ void __launch_bounds__(VT_THREADS, 3) vote_tiled_kernel(BatchView b, 
         }
     }
     __syncthreads();
-    // ---- slow columns: eight threads histogram one column, then one thread decides it
+    // ---- slow columns: one octet (eight lanes) per column, thirty-two columns per pass; an octet owns its bins
     {
         const int n = min(*s_nslow, VT_SLOW_CAP);
+        const int ci = tid >> 3, sub8 = tid & 7;
         for (int base = 0; base < n; base += VT_BIN_COLS) {
-            const int cnt = min(VT_BIN_COLS, n - base);
-            if (base > 0) {
-                for (int k = tid; k < cnt * 64; k += VT_THREADS) s_bins[k] = 0;
-                __syncthreads();
-            }
-            const int ci = tid >> 3, sub8 = tid & 7;
-            if (ci < cnt) {
-                const uint32_t code = s_slow[base + ci];
-                const int col = (int)(code & 0xFFFFu);
-                const FsTile ft = s_ft[code >> 16];
-                if (col < (int)ft.len)
-                    for (int e = sub8; e < (int)ft.m; e += 8) slow_histogram(t, ft, col, e, s_bins + 64 * ci);
-            }
-            __syncthreads();
-            if (tid < cnt) {
-                const uint32_t code = s_slow[base + tid];
-                slow_decide(t, (int)(code >> 16), (int)(code & 0xFFFFu), s_bins + 64 * tid);
-            }
-            __syncthreads();
+            const bool active = base + ci < n;
+            const uint32_t code = active ? s_slow[base + ci] : 0u;
+            slow_octet(t, active, (int)(code >> 16), (int)(code & 0xFFFFu), s_bins + 64 * ci, sub8);
+            __syncwarp();
         }
     }
+    __syncthreads();
     // ---- per family side: diff, mismatchInc, rollback, absolute output offset
     if (live0 || live1) {
         int fidx = fidx0;

@@ -31,6 +31,31 @@ struct ColumnTop {
     bool need_ref;       // needToCheckRef after group.cpp:421-467
 };
 
+// group.cpp:419-467: what the top and second bins imply.  `r.top` / `r.sec` are filled in; sets r.fast / r.need_ref.
+GCB_HD void column_rules(const gcb_options &o, ColumnTop &r, int total) {
+    const int topScore = r.top.score, topNum = r.top.cnt, topQual = r.top.maxq, secNum = r.sec.cnt;
+    r.fast = false;
+    r.need_ref = false;
+    if (secNum == 0) {
+        if (topScore >= o.base_score_req && topQual >= o.moderate_quality) {
+            r.fast = true;
+            return;
+        }
+        r.need_ref = true;
+    }
+    if (secNum == 1) {  // group.cpp:442-457; quals[secBase] is a sum of one quality here
+        if (r.sec.qual <= o.low_quality) {
+            if (topNum < 2 && topQual < o.high_quality) r.need_ref = true;
+        } else {
+            if (topNum < 3 || topQual < o.high_quality) r.need_ref = true;
+        }
+    }
+    if (secNum > 1) {  // group.cpp:460-464
+        if ((double)topScore < o.score_percent_req * (double)total || topQual < o.moderate_quality) r.need_ref = true;
+    }
+    if (topScore < o.base_score_req || topQual <= o.low_quality) r.need_ref = true;
+}
+
 // group.cpp:395-467.  obs[0..nobs) are the distinct observed codes (cnt >= 1), total = totalScore.
 GCB_HD ColumnTop column_top(const gcb_options &o, const VoteBin *obs, int nobs, int total) {
     // the two largest codes nobody voted for
@@ -57,27 +82,7 @@ GCB_HD ColumnTop column_top(const gcb_options &o, const VoteBin *obs, int nobs, 
     if (topk == -2 && e2.base >= 0 && bin_beats(e2, r.sec)) r.sec = e2;
     // sixteen codes all observed and only one of them... cannot leave sec unset: nobs + free codes = 16 >= 2
 
-    const int topScore = r.top.score, topNum = r.top.cnt, topQual = r.top.maxq, secNum = r.sec.cnt;
-    r.fast = false;
-    r.need_ref = false;
-    if (secNum == 0) {
-        if (topScore >= o.base_score_req && topQual >= o.moderate_quality) {
-            r.fast = true;
-            return r;
-        }
-        r.need_ref = true;
-    }
-    if (secNum == 1) {  // group.cpp:442-457; quals[secBase] is a sum of one quality here
-        if (r.sec.qual <= o.low_quality) {
-            if (topNum < 2 && topQual < o.high_quality) r.need_ref = true;
-        } else {
-            if (topNum < 3 || topQual < o.high_quality) r.need_ref = true;
-        }
-    }
-    if (secNum > 1) {  // group.cpp:460-464
-        if ((double)topScore < o.score_percent_req * (double)total || topQual < o.moderate_quality) r.need_ref = true;
-    }
-    if (topScore < o.base_score_req || topQual <= o.low_quality) r.need_ref = true;
+    column_rules(o, r, total);
     return r;
 }
 
