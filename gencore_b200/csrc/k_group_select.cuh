@@ -212,54 +212,75 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
         }
     }
 
-    bool leftReadMode = isLeft;
-    if (!isLeft) {  // group.cpp:177-194: every right read starts at the same position => left-aligned columns
-        int lo = 0x7FFFFFFF, hi = -0x7FFFFFFF;
-        for (int k = lane; k < m; k += WARP) {
-            if (!GCB_HAVE(k)) continue;
-            const int pos = b.reads[GCB_SLOT(k)].pos;
-            lo = min(lo, pos);
-            hi = max(hi, pos);
+    // Shortcut for the usual family: every read present, one identical CIGAR op, same length, same position.
+    // Then every read is part of every other (bamutil.cpp:204-255 on equal CIGARs), the counts tie at m, the lengths
+    // tie, so the template is the first read in map order, every read votes, and right reads share their position
+    // (left-aligned columns).  Exactly what the general code below computes, without its O(m^2) CIGAR walks.
+    bool same = m <= thr;
+    {
+        const gcb_read_desc r0 = b.reads[GCB_SLOT(0)];
+        same = same && r0.l_qseq >= 0 && r0.n_cigar == 1;
+        const uint32_t c0w = same ? b.cigar[r0.cigar_off] : 0u;
+        for (int k = lane; k < m && same; k += WARP) {
+            const gcb_read_desc rk = b.reads[GCB_SLOT(k)];
+            same = rk.l_qseq == r0.l_qseq && rk.n_cigar == 1 && rk.pos == r0.pos && b.cigar[rk.cigar_off] == c0w;
         }
-        lo = warp_min(lo);
-        hi = warp_max(hi);
-        if (lo >= hi) leftReadMode = true;  // all equal, or no read at all
+        same = __all_sync(FULL, same);
     }
-
-    // group.cpp:196-233: containedBy[i] = 1 + #{j : read i is part of read j}
-    int first_big = 0x7FFFFFFF;
-    for (int k = lane; k < m; k += WARP) {
-        int cnt = 0;
-        if (GCB_HAVE(k)) {
-            cnt = 1;
-            const int si = GCB_SLOT(k);
-            const uint32_t *ci = GCB_CIG(si);
-            const int ni = b.reads[si].n_cigar;
-            const int rrp = ws.right_ref_pos[si];
-            for (int j = 0; j < m; j++) {
-                if (j == k || !GCB_HAVE(j)) continue;
-                const int sj = GCB_SLOT(j);
-                if (!isLeft && rrp != ws.right_ref_pos[sj]) continue;
-                if (is_part_of(ci, ni, GCB_CIG(sj), b.reads[sj].n_cigar, leftReadMode)) cnt++;
+    bool leftReadMode = true;
+    int best_cnt = m, best_k = 0;
+    if (!same) {
+        leftReadMode = isLeft;
+        if (!isLeft) {  // group.cpp:177-194: every right read starts at the same position => left-aligned columns
+            int lo = 0x7FFFFFFF, hi = -0x7FFFFFFF;
+            for (int k = lane; k < m; k += WARP) {
+                if (!GCB_HAVE(k)) continue;
+                const int pos = b.reads[GCB_SLOT(k)].pos;
+                lo = min(lo, pos);
+                hi = max(hi, pos);
             }
-            if (m > thr && cnt >= m / 2) first_big = min(first_big, k);
+            lo = warp_min(lo);
+            hi = warp_max(hi);
+            if (lo >= hi) leftReadMode = true;  // all equal, or no read at all
         }
-        ws.scratch[2 * (int64_t)(mb + k) + side] = cnt;
-    }
-    first_big = warp_min(first_big);  // group.cpp:231-232: the scan stops there, later entries stay 0
 
-    // group.cpp:235-261: most contained, ties -> strictly shorter read, else first in map order
-    int best_cnt = -1, best_len = 0, best_k = 0x7FFFFFFF;
-    for (int k = lane; k < m; k += WARP) {
-        const int cnt = k > first_big ? 0 : ws.scratch[2 * (int64_t)(mb + k) + side];
-        const int len = GCB_HAVE(k) ? b.reads[GCB_SLOT(k)].l_qseq : 0;
-        if (cnt > best_cnt || (cnt == best_cnt && len < best_len)) { best_cnt = cnt; best_len = len; best_k = k; }
-    }
-    for (int off = 16; off > 0; off >>= 1) {
-        const int oc = __shfl_xor_sync(FULL, best_cnt, off), ol = __shfl_xor_sync(FULL, best_len, off),
-                  ok = __shfl_xor_sync(FULL, best_k, off);
-        if (oc > best_cnt || (oc == best_cnt && (ol < best_len || (ol == best_len && ok < best_k)))) {
-            best_cnt = oc; best_len = ol; best_k = ok;
+        // group.cpp:196-233: containedBy[i] = 1 + #{j : read i is part of read j}
+        int first_big = 0x7FFFFFFF;
+        for (int k = lane; k < m; k += WARP) {
+            int cnt = 0;
+            if (GCB_HAVE(k)) {
+                cnt = 1;
+                const int si = GCB_SLOT(k);
+                const uint32_t *ci = GCB_CIG(si);
+                const int ni = b.reads[si].n_cigar;
+                const int rrp = ws.right_ref_pos[si];
+                for (int j = 0; j < m; j++) {
+                    if (j == k || !GCB_HAVE(j)) continue;
+                    const int sj = GCB_SLOT(j);
+                    if (!isLeft && rrp != ws.right_ref_pos[sj]) continue;
+                    if (is_part_of(ci, ni, GCB_CIG(sj), b.reads[sj].n_cigar, leftReadMode)) cnt++;
+                }
+                if (m > thr && cnt >= m / 2) first_big = min(first_big, k);
+            }
+            ws.scratch[2 * (int64_t)(mb + k) + side] = cnt;
+        }
+        first_big = warp_min(first_big);  // group.cpp:231-232: the scan stops there, later entries stay 0
+
+        // group.cpp:235-261: most contained, ties -> strictly shorter read, else first in map order
+        int best_len = 0;
+        best_cnt = -1;
+        best_k = 0x7FFFFFFF;
+        for (int k = lane; k < m; k += WARP) {
+            const int cnt = k > first_big ? 0 : ws.scratch[2 * (int64_t)(mb + k) + side];
+            const int len = GCB_HAVE(k) ? b.reads[GCB_SLOT(k)].l_qseq : 0;
+            if (cnt > best_cnt || (cnt == best_cnt && len < best_len)) { best_cnt = cnt; best_len = len; best_k = k; }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            const int oc = __shfl_xor_sync(FULL, best_cnt, off), ol = __shfl_xor_sync(FULL, best_len, off),
+                      ok = __shfl_xor_sync(FULL, best_k, off);
+            if (oc > best_cnt || (oc == best_cnt && (ol < best_len || (ol == best_len && ok < best_k)))) {
+                best_cnt = oc; best_len = ol; best_k = ok;
+            }
         }
     }
     if ((double)best_cnt < m * 0.4 && m != 1) return none;  // group.cpp:264
@@ -279,7 +300,7 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
         }
         const int sk = GCB_SLOT(k);
         uint8_t f = 0;
-        if (k == best_k) f = VOTE_PARTICIPATES;
+        if (k == best_k || same) f = VOTE_PARTICIPATES;
         else {
             const gcb_read_desc rd = b.reads[sk];
             if (is_part_of(GCB_CIG(out), od.n_cigar, GCB_CIG(sk), rd.n_cigar, leftReadMode)) {
@@ -356,10 +377,9 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
     __syncwarp();
 
     const int64_t slab0 = ws.slab_off[c];
-    for (int i = G + lane; i < n; i += WARP) {  // slots that hold no family
-        const FsDesc nofs = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, 0};
-        ws.fs_desc[2 * (int64_t)(p0 + i)] = nofs;
-        ws.fs_desc[2 * (int64_t)(p0 + i) + 1] = nofs;
+    for (int i = G + lane; i < n; i += WARP) {  // slots that hold no family: the vote kernel reads side_mode to know
+        ws.side_mode[2 * (int64_t)(p0 + i)] = SIDE_NONE;
+        ws.side_mode[2 * (int64_t)(p0 + i) + 1] = SIDE_NONE;
     }
     int64_t out_rel = 0;
     for (int g = 0; g < G; g++) {

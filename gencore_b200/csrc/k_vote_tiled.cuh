@@ -236,8 +236,8 @@ GCB_DEV void slow_finish(const TileCtx &t, int f, int col, ColumnTop &top, int t
     if (top.fast) {
         new_qual = top.top.maxq;  // group.cpp:422-426: the base is NOT written
     } else {
-        int obase = 0, oqual = 0, sc;
-        fetch_ent(cb, tv, col, side, o, obase, oqual, sc);
+        // the record's base before the vote: the template's own (pair.cpp rewrites qualities, never bases)
+        const int obase = base_at(cb + 4 * (int)tv.own_off4 + qbytes, col);
         int ref4 = 0;
         if (ft.flags & FS_REF_OK) {  // group.cpp:430-439
             int refpos = col;
@@ -471,9 +471,12 @@ __global__ void __launch_bounds__(VT_THREADS, 3) vote_tiled_kernel(BatchView b, 
     FsDesc fd[2];
     fd[0].mode = fd[1].mode = SIDE_NONE;
     fd[0].c = fd[1].c = c0;
-    if (tid < NP) {
+    if (tid < NP) {  // slots that hold no family carry SIDE_NONE in side_mode and garbage in fs_desc
+        const uint16_t modes = *(const uint16_t *)(ws.side_mode + 2 * (int64_t)(P0 + tid));
         fd[0] = ws.fs_desc[2 * (int64_t)(P0 + tid)];
         fd[1] = ws.fs_desc[2 * (int64_t)(P0 + tid) + 1];
+        if ((modes & 0xFF) == SIDE_NONE) fd[0].mode = SIDE_NONE;
+        if ((modes >> 8) == SIDE_NONE) fd[1].mode = SIDE_NONE;
     }
     const int64_t out_base0 = ws.scan_block[c0 / SCAN_BLOCK] + ws.cluster_out_off[c0];
     const bool live0 = fd[0].mode != SIDE_NONE, live1 = fd[1].mode != SIDE_NONE;
