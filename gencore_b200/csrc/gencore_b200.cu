@@ -15,6 +15,9 @@
 
 using namespace gcb;
 
+constexpr int GCB_MAX_CHUNKS = 16;
+constexpr int64_t GCB_CHUNK_BYTES = 48ll << 20;  // payload per pipeline chunk of gcb_consensus_batch
+
 namespace {
 
 struct DevBuf {
@@ -39,6 +42,12 @@ struct gcb_ctx {
     // device mirror of a host batch / result (gcb_consensus_batch)
     DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
     DevBuf d_pair_group, d_ngroups, d_groups, d_out, d_out_bytes;
+    // gcb_consensus_batch pipelines chunks of clusters: copies in, kernels and copies out run on three streams
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t ev_in[GCB_MAX_CHUNKS] = {nullptr}, ev_done[GCB_MAX_CHUNKS] = {nullptr}, ev_out[GCB_MAX_CHUNKS] = {nullptr};
+    int64_t *h_totals = nullptr;  // pinned: cumulative consensus bytes after every chunk
+    int32_t *h_flag = nullptr;    // pinned: the device error flag
+    int64_t chunk_bytes = GCB_CHUNK_BYTES;
 };
 
 namespace {
@@ -79,15 +88,16 @@ void release(DevBuf &b) {
 // the staging buffer that holds the largest such tile (window + the largest cluster), chosen so that as
 // many CTAs as possible share an SM's 227 KB of shared memory.
 struct TilePlan {
-    int32_t window, slab_cap, smem;
+    int32_t window, window_shift, slab_cap, smem;
 };
 TilePlan plan_tiles(int32_t max_cluster_bytes) {
     const int32_t KB = 1024, budget = 227 * KB, tables = VT_OFF_SLAB + VT_SLAB_SLACK + 1 * KB;  // + the 1 KB per-CTA reserve
     int32_t maxc = max_cluster_bytes > 0 ? ((max_cluster_bytes + 127) & ~127) : 16 * KB;
     TilePlan p;
-    if (32 * KB + maxc + tables <= budget / 3) p.window = 32 * KB;
-    else if (24 * KB + maxc + tables <= budget / 2) p.window = 24 * KB;
-    else p.window = 32 * KB;
+    if (32 * KB + maxc + tables <= budget / 3) p.window_shift = 15;       // three CTAs per SM
+    else if (16 * KB + maxc + tables <= budget / 2) p.window_shift = 14;  // two
+    else p.window_shift = 15;
+    p.window = 1 << p.window_shift;
     p.slab_cap = p.window + maxc;
     if (p.slab_cap > VT_MAX_SLAB) p.slab_cap = VT_MAX_SLAB;
     if (p.slab_cap + tables > budget) p.slab_cap = (budget - tables) & ~127;
@@ -118,16 +128,16 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_mode, n_pairs * 2);
     GCB_RES(w_hasumi, n_clusters);
     GCB_RES(w_overlap, n_pairs * sizeof(PairOverlap));
-    GCB_RES(w_slab, (n_clusters + 1) * 8);
+    GCB_RES(w_slab, (n_clusters + GCB_MAX_CHUNKS + 1) * 8);
     GCB_RES(w_cob, n_clusters * 8);
     GCB_RES(w_coo, n_clusters * 8);
-    GCB_RES(w_scan, (n_scan + 1) * 8);
+    GCB_RES(w_scan, (n_scan + 2 * GCB_MAX_CHUNKS + 1) * 8);
     GCB_RES(w_err, 4);
-    GCB_RES(w_tiles, (n_tiles + 1) * sizeof(TileDir));
+    GCB_RES(w_tiles, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * sizeof(TileDir));
     GCB_RES(w_vr, 2 * n_pairs * sizeof(VoteRead));
     GCB_RES(w_fs, 2 * n_pairs * sizeof(FsDesc));
-    GCB_RES(w_gtiles, (n_tiles + 1) * 4);
-    GCB_RES(w_gcount, 4);
+    GCB_RES(w_gtiles, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * 4);
+    GCB_RES(w_gcount, 4 * GCB_MAX_CHUNKS);
 #undef GCB_RES
     ws.members = (int32_t *)ctx->w_members.p;
     ws.group_off = (int32_t *)ctx->w_group_off.p;
@@ -147,6 +157,79 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     ws.fs_desc = (FsDesc *)ctx->w_fs.p;
     ws.generic_tiles = (int32_t *)ctx->w_gtiles.p;
     ws.generic_count = (int32_t *)ctx->w_gcount.p;
+    return GCB_OK;
+}
+
+// A contiguous run of clusters processed as one unit (the whole batch, or one pipeline chunk of it).
+struct ViewRange {
+    int32_t c0, c1;        // clusters
+    int32_t p0, p1;        // pairs
+    int64_t s0, s1;        // payload bytes
+    int64_t tile_base;     // first entry of this view in tile_dir / generic_tiles
+    int64_t scan_base;     // first entry of this view in scan_block
+    int32_t index;         // chunk number (generic_count slot)
+};
+
+// The kernels of the path over one view.  Every array of `batch` / `result` is a device pointer to the WHOLE
+// batch; per-pair arrays are indexed absolutely, per-cluster arrays are rebased to the view here.
+int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result, const Workspace &ws0, const TilePlan &plan,
+                  const ViewRange &v, uint32_t stages, cudaStream_t stream, const int64_t *carry_in, int64_t *total_out) {
+    const int32_t nc = v.c1 - v.c0;
+    const int64_t n_tiles = (v.s1 - v.s0 + plan.window - 1) / plan.window;
+    BatchView b = {nc, v.p1, batch.umi_words, batch.cluster_pair_off + v.c0, batch.cluster_ref + v.c0, batch.cluster_flags + v.c0,
+                   batch.umi, batch.reads, batch.cigar, batch.payload, v.s1, v.s0};
+    ResultView r = {result.pair_group, result.cluster_n_groups + v.c0, result.groups, result.out_payload, result.out_capacity, total_out};
+    Workspace ws = ws0;
+    ws.cluster_has_umi += v.c0;
+    ws.slab_off += v.c0 + v.index;  // every view writes one entry past its last cluster
+    ws.cluster_out_bytes += v.c0;
+    ws.cluster_out_off += v.c0;
+    ws.scan_block += v.scan_base;
+    ws.tile_dir += v.tile_base;
+    ws.generic_tiles += v.tile_base;
+    ws.generic_count += v.index;
+    if (nc == 0) {
+        if (stages & GCB_STAGE_SELECT_TEMPLATE) {
+            if (carry_in) GCB_CUDA(ctx, cudaMemcpyAsync(total_out, carry_in, 8, cudaMemcpyDeviceToDevice, stream));
+            else GCB_CUDA(ctx, cudaMemsetAsync(total_out, 0, 8, stream));
+        }
+        return GCB_OK;
+    }
+    const int warps_per_cta = GROUP_THREADS / WARP;
+    const unsigned grid_clusters = (unsigned)((nc + warps_per_cta - 1) / warps_per_cta);
+    if (stages & GCB_STAGE_UMI_GROUP) {
+        if (batch.umi_words == 1)
+            GCB_LAUNCH(umi_group_kernel<1>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles);
+        else if (batch.umi_words == 2)
+            GCB_LAUNCH(umi_group_kernel<2>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles);
+        else if (batch.umi_words == 3)
+            GCB_LAUNCH(umi_group_kernel<3>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles);
+        else
+            GCB_LAUNCH(umi_group_kernel<4>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles);
+        ctx->launches++;
+    }
+    if (stages & GCB_STAGE_SELECT_TEMPLATE) {
+        const int32_t n_scan = (int32_t)((nc + SCAN_BLOCK - 1) / SCAN_BLOCK);
+        GCB_CUDA(ctx, cudaMemsetAsync(result.groups + v.p0, 0, sizeof(gcb_group_result) * (size_t)(v.p1 - v.p0), stream));
+        GCB_LAUNCH(select_template_kernel, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
+        GCB_LAUNCH(scan_local_kernel, dim3((unsigned)n_scan), dim3(SCAN_THREADS), 0, stream, ws, nc);
+        GCB_LAUNCH(scan_blocks_kernel, dim3(1), dim3(WARP), 0, stream, ws, n_scan, total_out, result.out_capacity, carry_in);
+        ctx->launches += 3;
+    }
+    if ((stages & GCB_STAGE_SCORE_VOTE) && n_tiles > 0) {
+        GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
+        GCB_LAUNCH(vote_tiled_kernel, dim3((unsigned)n_tiles), dim3(VT_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
+                   plan.slab_cap, fast_path_implied(ctx->opt));
+        const unsigned generic_grid = (unsigned)(n_tiles < 2 * 148 ? n_tiles : 2 * 148);
+        GCB_LAUNCH(score_vote_kernel, dim3(generic_grid), dim3(VOTE_THREADS), VOTE_SMEM, stream, b, r, ws, ctx->genome, ctx->opt);
+        ctx->launches += 2;
+    }
+    if (stages & GCB_STAGE_DUPLEX) {
+        GCB_LAUNCH(duplex_kernel, dim3((unsigned)((nc + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream, b, r, ws,
+                   ctx->opt);
+        ctx->launches++;
+    }
+    GCB_CUDA(ctx, cudaGetLastError());
     return GCB_OK;
 }
 
@@ -190,10 +273,21 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
         delete ctx;
         return GCB_ERR_CUDA;
     }
+    bool ok = cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMallocHost((void **)&ctx->h_totals, 8 * (GCB_MAX_CHUNKS + 1)) == cudaSuccess &&
+              cudaMallocHost((void **)&ctx->h_flag, 8) == cudaSuccess;
+    for (int k = 0; ok && k < GCB_MAX_CHUNKS; k++)
+        ok = cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_out[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        gcb_destroy(ctx);
+        return GCB_ERR_CUDA;
+    }
     if (cudaFuncSetAttribute(score_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(vote_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-        cudaStreamDestroy(ctx->stream);
-        delete ctx;
+        gcb_destroy(ctx);
         return GCB_ERR_CUDA;
     }
     *out = ctx;
@@ -210,7 +304,16 @@ void gcb_destroy(gcb_ctx *ctx) {
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
                      &ctx->d_out, &ctx->d_out_bytes};
     for (DevBuf *b : all) release(*b);
-    cudaStreamDestroy(ctx->stream);
+    for (int k = 0; k < GCB_MAX_CHUNKS; k++) {
+        if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
+        if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]);
+        if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
+    }
+    if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
+    if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -264,44 +367,9 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
     Workspace ws;
     int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, ws);
     if (rc != GCB_OK) return rc;
-    BatchView b = {batch->n_clusters, batch->n_pairs, batch->umi_words, batch->cluster_pair_off, batch->cluster_ref, batch->cluster_flags,
-                   batch->umi, batch->reads, batch->cigar, batch->payload, batch->payload_bytes};
-    ResultView r = {result->pair_group, result->cluster_n_groups, result->groups, result->out_payload, result->out_capacity, result->out_bytes};
-    if (batch->n_clusters == 0) {
-        if (stages & GCB_STAGE_SELECT_TEMPLATE) GCB_CUDA(ctx, cudaMemsetAsync(result->out_bytes, 0, 8, stream));
-        GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, stream));
-        return GCB_OK;
-    }
-    const int warps_per_cta = GROUP_THREADS / WARP;
-    const unsigned grid_clusters = (unsigned)((batch->n_clusters + warps_per_cta - 1) / warps_per_cta);
-    if (stages & GCB_STAGE_UMI_GROUP) {
-        GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, stream));
-        GCB_LAUNCH(umi_group_kernel, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window, (int32_t)n_tiles);
-        ctx->launches++;
-    }
-    if (stages & GCB_STAGE_SELECT_TEMPLATE) {
-        const int32_t n_scan = (int32_t)((batch->n_clusters + SCAN_BLOCK - 1) / SCAN_BLOCK);
-        GCB_CUDA(ctx, cudaMemsetAsync(result->groups, 0, sizeof(gcb_group_result) * (size_t)batch->n_pairs, stream));
-        GCB_LAUNCH(select_template_kernel, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
-        GCB_LAUNCH(scan_local_kernel, dim3((unsigned)n_scan), dim3(SCAN_THREADS), 0, stream, ws, batch->n_clusters);
-        GCB_LAUNCH(scan_blocks_kernel, dim3(1), dim3(WARP), 0, stream, ws, n_scan, result->out_bytes, result->out_capacity);
-        ctx->launches += 3;
-    }
-    if ((stages & GCB_STAGE_SCORE_VOTE) && n_tiles > 0) {
-        GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
-        GCB_LAUNCH(vote_tiled_kernel, dim3((unsigned)n_tiles), dim3(VT_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
-                   plan.slab_cap, fast_path_implied(ctx->opt));
-        const unsigned generic_grid = (unsigned)(n_tiles < 2 * 148 ? n_tiles : 2 * 148);
-        GCB_LAUNCH(score_vote_kernel, dim3(generic_grid), dim3(VOTE_THREADS), VOTE_SMEM, stream, b, r, ws, ctx->genome, ctx->opt);
-        ctx->launches += 2;
-    }
-    if (stages & GCB_STAGE_DUPLEX) {
-        GCB_LAUNCH(duplex_kernel, dim3((unsigned)((batch->n_clusters + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream,
-                   b, r, ws, ctx->opt);
-        ctx->launches++;
-    }
-    GCB_CUDA(ctx, cudaGetLastError());
-    return GCB_OK;
+    const ViewRange whole = {0, batch->n_clusters, 0, batch->n_pairs, 0, batch->payload_bytes, 0, 0, 0};
+    if (stages & GCB_STAGE_UMI_GROUP) GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, stream));
+    return launch_stages(ctx, *batch, *result, ws, plan, whole, stages, stream, nullptr, result->out_bytes);
 }
 
 int gcb_batch_status(gcb_ctx *ctx, void *stream_) {
@@ -318,28 +386,26 @@ int gcb_batch_status(gcb_ctx *ctx, void *stream_) {
 
 int gcb_consensus_batch(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *hr) {
     if (!ctx || !hb || !hr) return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch: null argument");
-    if (hb->n_clusters < 0 || hb->n_pairs < 0 || hb->payload_bytes < 0 || hb->n_cigar_ops < 0 || hr->out_capacity < 0)
-        return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch: negative size");
+    if (hb->n_clusters < 0 || hb->n_pairs < 0 || hb->payload_bytes < 0 || hb->n_cigar_ops < 0 || hr->out_capacity < 0 ||
+        hb->umi_words < 1 || hb->umi_words > GCB_MAX_UMI_WORDS || (hb->payload_bytes & 15))
+        return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch: bad size");
     GCB_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     const size_t nc = (size_t)hb->n_clusters, np = (size_t)hb->n_pairs;
     int rc;
-#define GCB_UP(buf, src, bytes)                                                                         \
-    if ((rc = reserve(ctx, ctx->buf, (bytes))) != GCB_OK) return rc;                                    \
-    if ((bytes) > 0) GCB_CUDA(ctx, cudaMemcpyAsync(ctx->buf.p, (src), (bytes), cudaMemcpyHostToDevice, st))
-    GCB_UP(d_pair_off, hb->cluster_pair_off, (nc + 1) * 4);
-    GCB_UP(d_cref, hb->cluster_ref, nc * 4);
-    GCB_UP(d_cflags, hb->cluster_flags, nc);
-    GCB_UP(d_umi, hb->umi, np * (size_t)hb->umi_words * 8);
-    GCB_UP(d_reads, hb->reads, 2 * np * sizeof(gcb_read_desc));
-    GCB_UP(d_cigar, hb->cigar, (size_t)hb->n_cigar_ops * 4);
-    GCB_UP(d_payload, hb->payload, (size_t)hb->payload_bytes);
-#undef GCB_UP
-    if ((rc = reserve(ctx, ctx->d_pair_group, np * 4)) != GCB_OK) return rc;
-    if ((rc = reserve(ctx, ctx->d_ngroups, nc * 4)) != GCB_OK) return rc;
-    if ((rc = reserve(ctx, ctx->d_groups, np * sizeof(gcb_group_result))) != GCB_OK) return rc;
-    if ((rc = reserve(ctx, ctx->d_out, (size_t)hr->out_capacity)) != GCB_OK) return rc;
-    if ((rc = reserve(ctx, ctx->d_out_bytes, 8)) != GCB_OK) return rc;
+#define GCB_RESERVE(buf, bytes) if ((rc = reserve(ctx, ctx->buf, (bytes))) != GCB_OK) return rc
+    GCB_RESERVE(d_pair_off, (nc + 1) * 4);
+    GCB_RESERVE(d_cref, nc * 4);
+    GCB_RESERVE(d_cflags, nc);
+    GCB_RESERVE(d_umi, np * (size_t)hb->umi_words * 8);
+    GCB_RESERVE(d_reads, 2 * np * sizeof(gcb_read_desc));
+    GCB_RESERVE(d_cigar, (size_t)hb->n_cigar_ops * 4);
+    GCB_RESERVE(d_payload, (size_t)hb->payload_bytes);
+    GCB_RESERVE(d_pair_group, np * 4);
+    GCB_RESERVE(d_ngroups, nc * 4);
+    GCB_RESERVE(d_groups, np * sizeof(gcb_group_result));
+    GCB_RESERVE(d_out, (size_t)hr->out_capacity);
+    GCB_RESERVE(d_out_bytes, 8 * (GCB_MAX_CHUNKS + 1));
+#undef GCB_RESERVE
     gcb_batch db = *hb;
     db.cluster_pair_off = (const int32_t *)ctx->d_pair_off.p;
     db.cluster_ref = (const int32_t *)ctx->d_cref.p;
@@ -355,22 +421,104 @@ int gcb_consensus_batch(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *hr) {
     dr.out_payload = (uint8_t *)ctx->d_out.p;
     dr.out_capacity = hr->out_capacity;
     dr.out_bytes = (int64_t *)ctx->d_out_bytes.p;
-    if ((rc = gcb_consensus_batch_device(ctx, &db, &dr, GCB_STAGE_ALL, st)) != GCB_OK) return rc;
-    if (np > 0) {
-        GCB_CUDA(ctx, cudaMemcpyAsync(hr->pair_group, dr.pair_group, np * 4, cudaMemcpyDeviceToHost, st));
-        GCB_CUDA(ctx, cudaMemcpyAsync(hr->groups, dr.groups, np * sizeof(gcb_group_result), cudaMemcpyDeviceToHost, st));
+    int64_t *d_totals = (int64_t *)ctx->d_out_bytes.p;  // [k]: consensus bytes emitted by chunks 0..k
+
+    // ---- chunks of clusters of about GCB_CHUNK_BYTES of payload each: while chunk k is voted, chunk k+1 is on its
+    // way in and chunk k-1 on its way out (three streams; PCIe is full duplex)
+    auto slab_start = [&](int32_t c) -> int64_t {  // same rule as umi_group_kernel
+        const int32_t p = hb->cluster_pair_off[c];
+        return p < hb->n_pairs ? hb->reads[2 * (int64_t)p].data_off : hb->payload_bytes;
+    };
+    int K = (int)((hb->payload_bytes + ctx->chunk_bytes - 1) / ctx->chunk_bytes);
+    if (K > GCB_MAX_CHUNKS) K = GCB_MAX_CHUNKS;
+    if (K < 1) K = 1;
+    if ((int64_t)K > (int64_t)nc) K = nc > 0 ? (int)nc : 1;
+    const TilePlan plan = plan_tiles(hb->max_cluster_bytes);
+    ViewRange view[GCB_MAX_CHUNKS];
+    {
+        int32_t c_prev = 0;
+        int64_t tiles = 0, scans = 0;
+        for (int k = 0; k < K; k++) {
+            int32_t c_end = (int32_t)nc;
+            if (k + 1 < K) {  // first cluster whose slab starts at or after the target byte
+                const int64_t target = hb->payload_bytes / K * (k + 1);
+                int32_t lo = c_prev, hi = (int32_t)nc;
+                while (lo < hi) {
+                    const int32_t mid = lo + (hi - lo) / 2;
+                    if (slab_start(mid) < target) lo = mid + 1;
+                    else hi = mid;
+                }
+                c_end = lo;
+            }
+            ViewRange &v = view[k];
+            v.c0 = c_prev;
+            v.c1 = c_end;
+            v.p0 = nc ? hb->cluster_pair_off[v.c0] : 0;
+            v.p1 = nc ? hb->cluster_pair_off[v.c1] : 0;
+            v.s0 = v.c0 < (int32_t)nc ? slab_start(v.c0) : hb->payload_bytes;
+            v.s1 = v.c1 < (int32_t)nc ? slab_start(v.c1) : hb->payload_bytes;
+            if (k == 0) v.s0 = 0;
+            v.tile_base = tiles;
+            v.scan_base = scans;
+            v.index = k;
+            tiles += (v.s1 - v.s0 + plan.window - 1) / plan.window + 1;
+            scans += (v.c1 - v.c0 + SCAN_BLOCK - 1) / SCAN_BLOCK + 1;
+            c_prev = c_end;
+        }
     }
-    if (nc > 0) GCB_CUDA(ctx, cudaMemcpyAsync(hr->cluster_n_groups, dr.cluster_n_groups, nc * 4, cudaMemcpyDeviceToHost, st));
-    GCB_CUDA(ctx, cudaMemcpyAsync(hr->out_bytes, dr.out_bytes, 8, cudaMemcpyDeviceToHost, st));
-    int32_t flag = 0;
-    GCB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->w_err.p, 4, cudaMemcpyDeviceToHost, st));
-    GCB_CUDA(ctx, cudaStreamSynchronize(st));
+    Workspace ws;
+    if ((rc = reserve_workspace(ctx, hb->n_pairs, hb->n_clusters, (hb->payload_bytes + plan.window - 1) / plan.window, ws)) != GCB_OK) return rc;
+    cudaStream_t sc = ctx->stream, sin = ctx->h2d, sout = ctx->d2h;
+    GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, sc));
+    for (int k = 0; k < K; k++) {
+        const ViewRange &v = view[k];
+        const size_t vc = (size_t)(v.c1 - v.c0), vp = (size_t)(v.p1 - v.p0);
+#define GCB_UP(buf, src, off, bytes, elem)                                                                                   \
+    if ((bytes) > 0)                                                                                                         \
+    GCB_CUDA(ctx, cudaMemcpyAsync((char *)ctx->buf.p + (size_t)(off) * (elem), (const char *)(src) + (size_t)(off) * (elem), (bytes), \
+                                  cudaMemcpyHostToDevice, sin))
+        if (k == 0) GCB_UP(d_cigar, hb->cigar, 0, (size_t)hb->n_cigar_ops * 4, 4);
+        GCB_UP(d_pair_off, hb->cluster_pair_off, v.c0, (vc + 1) * 4, 4);
+        GCB_UP(d_cref, hb->cluster_ref, v.c0, vc * 4, 4);
+        GCB_UP(d_cflags, hb->cluster_flags, v.c0, vc, 1);
+        GCB_UP(d_umi, hb->umi, (size_t)v.p0 * hb->umi_words, vp * hb->umi_words * 8, 8);
+        GCB_UP(d_reads, hb->reads, 2 * (size_t)v.p0, 2 * vp * sizeof(gcb_read_desc), sizeof(gcb_read_desc));
+        GCB_UP(d_payload, hb->payload, v.s0, (size_t)(v.s1 - v.s0), 1);
+#undef GCB_UP
+        GCB_CUDA(ctx, cudaEventRecord(ctx->ev_in[k], sin));
+        GCB_CUDA(ctx, cudaStreamWaitEvent(sc, ctx->ev_in[k], 0));
+        if ((rc = launch_stages(ctx, db, dr, ws, plan, v, GCB_STAGE_ALL, sc, k ? d_totals + (k - 1) : nullptr, d_totals + k)) != GCB_OK) return rc;
+        GCB_CUDA(ctx, cudaEventRecord(ctx->ev_done[k], sc));
+        GCB_CUDA(ctx, cudaStreamWaitEvent(sout, ctx->ev_done[k], 0));
+        if (vp > 0) {
+            GCB_CUDA(ctx, cudaMemcpyAsync(hr->pair_group + v.p0, dr.pair_group + v.p0, vp * 4, cudaMemcpyDeviceToHost, sout));
+            GCB_CUDA(ctx, cudaMemcpyAsync(hr->groups + v.p0, dr.groups + v.p0, vp * sizeof(gcb_group_result), cudaMemcpyDeviceToHost, sout));
+        }
+        if (vc > 0) GCB_CUDA(ctx, cudaMemcpyAsync(hr->cluster_n_groups + v.c0, dr.cluster_n_groups + v.c0, vc * 4, cudaMemcpyDeviceToHost, sout));
+        GCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_totals + k, d_totals + k, 8, cudaMemcpyDeviceToHost, sout));
+        GCB_CUDA(ctx, cudaEventRecord(ctx->ev_out[k], sout));
+    }
+    // consensus records: the size of every chunk's share is known only on the device
+    int64_t done = 0;
+    for (int k = 0; k < K; k++) {
+        GCB_CUDA(ctx, cudaEventSynchronize(ctx->ev_out[k]));
+        int64_t upto = ctx->h_totals[k];
+        if (upto > hr->out_capacity) upto = hr->out_capacity;  // (the error flag below reports it)
+        if (upto > done) GCB_CUDA(ctx, cudaMemcpyAsync(hr->out_payload + done, dr.out_payload + done, (size_t)(upto - done), cudaMemcpyDeviceToHost, sout));
+        if (upto > done) done = upto;
+    }
+    GCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_flag, ws.error_flag, 4, cudaMemcpyDeviceToHost, sout));
+    GCB_CUDA(ctx, cudaStreamSynchronize(sout));
+    GCB_CUDA(ctx, cudaStreamSynchronize(sc));
+    *hr->out_bytes = ctx->h_totals[K - 1];
+    const int32_t flag = *ctx->h_flag;
     if (flag != GCB_OK) return fail(ctx, flag, flag == GCB_ERR_CAPACITY ? "out_payload too small" : "malformed batch");
-    const int64_t used = *hr->out_bytes;
-    if (used > 0) {
-        GCB_CUDA(ctx, cudaMemcpyAsync(hr->out_payload, dr.out_payload, (size_t)used, cudaMemcpyDeviceToHost, st));
-        GCB_CUDA(ctx, cudaStreamSynchronize(st));
-    }
+    return GCB_OK;
+}
+
+int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes) {
+    if (!ctx || bytes < 16) return GCB_ERR_ARG;
+    ctx->chunk_bytes = bytes;
     return GCB_OK;
 }
 

@@ -18,7 +18,8 @@ struct BatchView {  // gcb_batch with device pointers
     const gcb_read_desc *reads;
     const uint32_t *cigar;
     const uint8_t *payload;
-    int64_t payload_bytes;
+    int64_t payload_bytes;   // end of this view's payload (absolute offset)
+    int64_t payload_origin;  // start of this view's payload: vote tiles are windows counted from here
 };
 
 struct ResultView {  // gcb_result with device pointers
@@ -33,18 +34,54 @@ struct ResultView {  // gcb_result with device pointers
 constexpr int GROUP_THREADS = 128;  // 4 clusters per CTA
 
 // ------------------------------------------------------------------------------------------------
+// UMIs of NW 64-bit words held in registers (the kernel is instantiated for 1, 2 and GCB_MAX_UMI_WORDS words:
+// sixteen characters fit one word, a duplex UMI of 8+1+8 needs two)
+template <int NW>
+struct UmiT {
+    uint64_t w[NW];
+};
+template <int NW>
+GCB_DEV UmiT<NW> umit_load(const uint64_t *p) {
+    UmiT<NW> u;
+#pragma unroll
+    for (int k = 0; k < NW; k++) u.w[k] = p[k];
+    return u;
+}
+template <int NW>
+GCB_DEV bool umit_equal(const UmiT<NW> &a, const UmiT<NW> &b) {
+    bool e = true;
+#pragma unroll
+    for (int k = 0; k < NW; k++) e = e && a.w[k] == b.w[k];
+    return e;
+}
+template <int NW>
+GCB_DEV bool umit_less(const UmiT<NW> &a, const UmiT<NW> &b) {  // std::string order of the decoded UMIs
+#pragma unroll
+    for (int k = 0; k < NW; k++)
+        if (a.w[k] != b.w[k]) return a.w[k] < b.w[k];
+    return false;
+}
+template <int NW>
+GCB_DEV int umit_diff(const UmiT<NW> &a, const UmiT<NW> &b) {  // Cluster::umiDiff, cluster.cpp:41-53
+    int d = 0;
+#pragma unroll
+    for (int k = 0; k < NW; k++) d += nibble_diff64(a.w[k], b.w[k]);
+    return d;
+}
+
 // cluster.cpp:55-100.  umiCount (a map<string,int>) becomes a per-pair multiplicity; each round takes
 // the lexicographically first UMI of maximal count among the pairs still unassigned and absorbs every
 // unassigned pair within `thr` of it, in map (= pair) order.  Counts never need decrementing: pairs
-// carrying the same UMI are always absorbed together.
-__global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, ResultView r, Workspace ws, int32_t tile_window,
+// carrying the same UMI are always absorbed together.  `window_shift`: the vote tile window is 1 << window_shift.
+template <int NW>
+__global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, ResultView r, Workspace ws, int32_t window_shift,
                                                                    int32_t n_tiles) {
     const int lane = lane_id();
     const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
     if (c >= b.n_clusters) return;
     const int p0 = b.cluster_pair_off[c], p1 = b.cluster_pair_off[c + 1], n = p1 - p0;
-    const int nw = b.umi_words;
     const int thr = b.cluster_flags[c] >> GCB_CLUSTER_UMI_THR_SHIFT;
+    const uint64_t *umi = b.umi + (int64_t)p0 * NW;
 
     if (lane == 0) {
         // slab bounds of this cluster and the vote kernel's tile directory: tile t owns the clusters
@@ -55,24 +92,24 @@ __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, R
         if (c > 0) {
             const int pp = b.cluster_pair_off[c - 1];
             const int64_t prev = pp < b.n_pairs ? b.reads[2 * (int64_t)pp].data_off : b.payload_bytes;
-            t_lo = prev / tile_window + 1;
+            t_lo = ((prev - b.payload_origin) >> window_shift) + 1;
         }
         const TileDir here = {c, p0, s};
-        for (int64_t t = t_lo; t <= s / tile_window && t <= n_tiles; t++) ws.tile_dir[t] = here;
+        for (int64_t t = t_lo; t <= ((s - b.payload_origin) >> window_shift) && t <= n_tiles; t++) ws.tile_dir[t] = here;
         if (c == b.n_clusters - 1) {
             ws.slab_off[c + 1] = b.payload_bytes;
             const TileDir end = {b.n_clusters, p1, b.payload_bytes};
-            for (int64_t t = s / tile_window + 1; t <= n_tiles; t++) ws.tile_dir[t] = end;
+            for (int64_t t = ((s - b.payload_origin) >> window_shift) + 1; t <= n_tiles; t++) ws.tile_dir[t] = end;
         }
     }
 
     // multiplicity of every pair's UMI inside the cluster (cluster.cpp:57-65)
     bool has = false;
     for (int i = lane; i < n; i += WARP) {
-        const Umi u = umi_load(b.umi + (int64_t)(p0 + i) * nw, nw);
+        const UmiT<NW> u = umit_load<NW>(umi + (int64_t)i * NW);
         has |= (u.w[0] >> 60) != 0;
         int cnt = 0;
-        for (int j = 0; j < n; j++) cnt += umi_equal(u, umi_load(b.umi + (int64_t)(p0 + j) * nw, nw)) ? 1 : 0;
+        for (int j = 0; j < n; j++) cnt += umit_equal<NW>(u, umit_load<NW>(umi + (int64_t)j * NW)) ? 1 : 0;
         ws.scratch[2 * (int64_t)(p0 + i)] = cnt;
         r.pair_group[p0 + i] = -1;
     }
@@ -82,26 +119,27 @@ __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, R
     int filled = 0, g = 0;
     while (filled < n) {  // cluster.cpp:66-100
         int best_cnt = -1;
-        Umi best = umi_load(b.umi, 0);
+        UmiT<NW> best;
+#pragma unroll
+        for (int k = 0; k < NW; k++) best.w[k] = 0ull;
         for (int i = lane; i < n; i += WARP) {
             if (r.pair_group[p0 + i] >= 0) continue;
             const int cnt = ws.scratch[2 * (int64_t)(p0 + i)];
-            const Umi u = umi_load(b.umi + (int64_t)(p0 + i) * nw, nw);
-            if (cnt > best_cnt || (cnt == best_cnt && umi_less(u, best))) { best_cnt = cnt; best = u; }
+            const UmiT<NW> u = umit_load<NW>(umi + (int64_t)i * NW);
+            if (cnt > best_cnt || (cnt == best_cnt && umit_less<NW>(u, best))) { best_cnt = cnt; best = u; }
         }
         for (int off = 16; off > 0; off >>= 1) {
             const int oc = __shfl_xor_sync(FULL, best_cnt, off);
-            Umi ou;
+            UmiT<NW> ou;
 #pragma unroll
-            for (int k = 0; k < GCB_MAX_UMI_WORDS; k++) ou.w[k] = __shfl_xor_sync(FULL, best.w[k], off);
-            if (oc > best_cnt || (oc == best_cnt && oc >= 0 && umi_less(ou, best))) { best_cnt = oc; best = ou; }
+            for (int k = 0; k < NW; k++) ou.w[k] = __shfl_xor_sync(FULL, best.w[k], off);
+            if (oc > best_cnt || (oc == best_cnt && oc >= 0 && umit_less<NW>(ou, best))) { best_cnt = oc; best = ou; }
         }
         const int start = filled;
         for (int base = 0; base < n; base += WARP) {
             const int i = base + lane;
             bool absorb = false;
-            if (i < n && r.pair_group[p0 + i] < 0)
-                absorb = umi_diff(umi_load(b.umi + (int64_t)(p0 + i) * nw, nw), best) <= thr;
+            if (i < n && r.pair_group[p0 + i] < 0) absorb = umit_diff<NW>(umit_load<NW>(umi + (int64_t)i * NW), best) <= thr;
             const unsigned m = __ballot_sync(FULL, absorb);
             if (absorb) {
                 ws.members[p0 + filled + __popc(m & ((1u << lane) - 1u))] = p0 + i;
@@ -532,9 +570,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_local_kernel(Workspace ws, 
     if (threadIdx.x == SCAN_THREADS - 1) ws.scan_block[blockIdx.x] = pre;
 }
 
-__global__ void __launch_bounds__(WARP) scan_blocks_kernel(Workspace ws, int32_t n_blocks, int64_t *out_bytes, int64_t out_capacity) {
+// `carry_in`: bytes emitted by the views that precede this one in out_payload (NULL = none)
+__global__ void __launch_bounds__(WARP) scan_blocks_kernel(Workspace ws, int32_t n_blocks, int64_t *out_bytes, int64_t out_capacity,
+                                                           const int64_t *carry_in) {
     const int lane = lane_id();
-    int64_t carry = 0;
+    int64_t carry = carry_in ? *carry_in : 0;
     for (int base = 0; base < n_blocks; base += WARP) {
         const int i = base + lane;
         const int64_t v = i < n_blocks ? ws.scan_block[i] : 0;

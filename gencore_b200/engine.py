@@ -24,7 +24,7 @@ DEFAULT_LIB = os.path.join(HERE, "csrc", "libgencore_b200.so")
 # every symbol include/gencore_b200.h declares
 ABI_SYMBOLS = ["gcb_abi_version", "gcb_default_options", "gcb_create", "gcb_destroy", "gcb_last_error", "gcb_set_reference",
                "gcb_set_reference_device", "gcb_consensus_batch", "gcb_consensus_batch_device", "gcb_batch_status",
-               "gcb_launch_count"]
+               "gcb_launch_count", "gcb_set_chunk_bytes"]
 
 
 class EngineError(RuntimeError):
@@ -55,6 +55,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gcb_consensus_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     lib.gcb_batch_status.restype = C.c_int
     lib.gcb_batch_status.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gcb_set_chunk_bytes.restype = C.c_int
+    lib.gcb_set_chunk_bytes.argtypes = [C.c_void_p, C.c_int64]
     lib.gcb_launch_count.restype = C.c_int64
     lib.gcb_launch_count.argtypes = [C.c_void_p]
     if lib.gcb_abi_version() != GCB_ABI_VERSION:
@@ -123,6 +125,10 @@ class ConsensusEngine:
     # -- same with every buffer resident on the device (pointers are integers, e.g. torch .data_ptr())
     def cluster_by_umi_device(self, bs: BatchStruct, rs: ResultStruct, stages: int = STAGE_ALL, stream: int = 0) -> None:
         self._check(self.lib.gcb_consensus_batch_device(self._ctx, C.byref(bs), C.byref(rs), stages, C.c_void_p(stream)))
+
+    def set_chunk_bytes(self, nbytes: int) -> None:
+        """Payload bytes per pipeline chunk of cluster_by_umi (tuning only: results do not depend on it)."""
+        self._check(self.lib.gcb_set_chunk_bytes(self._ctx, nbytes))
 
     def batch_status(self, stream: int = 0) -> int:
         return self.lib.gcb_batch_status(self._ctx, C.c_void_p(stream))

@@ -190,6 +190,10 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
  * synchronises the stream. */
 int gcb_batch_status(gcb_ctx *ctx, void *stream);
 
+/* Tuning knob of gcb_consensus_batch: payload bytes per pipeline chunk (default 48 MiB; at most 16 chunks per call,
+ * chunks are whole clusters).  Results do not depend on it. */
+int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes);
+
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t gcb_launch_count(const gcb_ctx *ctx);
 

@@ -54,6 +54,15 @@ def no_reference_case():
     return batch, None, Options.default()
 
 
+def wide_umi_case(words):
+    """A duplex batch whose UMI array is widened to `words` u64 per pair (zero fields = past the end of the string):
+    the 3- and 4-word instantiations of the grouping kernel."""
+    batch, genome, opt = ragged_case(2, "duplex", 30)
+    umi = np.zeros((batch.n_pairs, words), np.uint64)
+    umi[:, :batch.umi.shape[1]] = batch.umi
+    return dataclasses.replace(batch, umi=umi), genome, opt
+
+
 def empty_case():
     batch = Batch(np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros((0, 1), np.uint64),
                   np.zeros(0, READ_DESC), np.zeros(1, np.uint32), np.zeros(16, np.uint8), [], np.zeros(0, np.uint8), "")
@@ -86,7 +95,8 @@ def small_cases():
     out += [("edge_" + n, (lambda n=n: edge_case(n))) for n in cases.OPTION_SETS]
     out += [(f"ragged_{umi}_{seed}", (lambda s=seed, u=umi: ragged_case(s, u, 30))) for seed in range(4) for umi in ("none", "single", "duplex")]
     out += [("deep_1100", deep_case), ("low_complexity", low_complexity_case), ("no_reference", no_reference_case),
-            ("empty", empty_case), ("tiny_reads", tiny_reads_case)]
+            ("empty", empty_case), ("tiny_reads", tiny_reads_case),
+            ("wide_umi_3", lambda: wide_umi_case(3)), ("wide_umi_4", lambda: wide_umi_case(4))]
     out += [(f"{n}_1500", (lambda n=n: fixed_case(n, 1500))) for n in ("cfg1", "cfg2", "cfg3", "cfg4")]
     return out
 

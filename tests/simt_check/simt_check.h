@@ -370,6 +370,15 @@ inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = n
 constexpr unsigned cudaStreamNonBlocking = 1;
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+typedef void *cudaEvent_t;
+constexpr unsigned cudaEventDisableTiming = 2;
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = (void *)1; return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
+inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = malloc(n); return *p ? 0 : 2; }
+inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
 inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDevice(int *d) { *d = 0; return 0; }

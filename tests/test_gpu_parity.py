@@ -51,6 +51,17 @@ def test_cuda_matches_oracle_device_buffers(engine_cls, oracle, name):
             assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 
 
+@pytest.mark.parametrize("name", ["cfg3_40k", "ragged_duplex_5_big", "deep_1100", "cfg4_40k"])
+@pytest.mark.parametrize("chunk", [1 << 14, 1 << 18, 1 << 21])
+def test_pipeline_chunks_do_not_change_results(engine_cls, oracle, name, chunk):
+    batch, genome, opt = dict(CASES)[name]()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        eng.set_chunk_bytes(chunk)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} chunk {chunk}")
+
+
 def test_capacity_error_is_reported(engine_cls):
     from gencore_b200.abi import GCB_ERR_CAPACITY
     from gencore_b200.engine import EngineError

@@ -50,3 +50,16 @@ def test_both_column_paths_are_exercised():
     assert COVERAGE, "runs after the parametrised cases"
     assert sum(v[2] - v[3] for v in COVERAGE.values()) > 0 and sum(v[3] for v in COVERAGE.values()) > 0
     print({k: v for k, v in COVERAGE.items()})
+
+
+@pytest.mark.parametrize("name", ["cfg3_1500", "ragged_duplex_1", "deep_1100", "golden_cfg4_600"])
+@pytest.mark.parametrize("chunk", [1 << 12, 1 << 15, 1 << 17])
+def test_pipeline_chunks_do_not_change_results(simt_lib, oracle, name, chunk):
+    """gcb_consensus_batch splits a batch into chunks of clusters that overlap copies and kernels; force many small chunks."""
+    from gencore_b200.engine import ConsensusEngine
+    batch, genome, opt = dict(CASES)[name]()
+    with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
+        eng.set_reference(genome)
+        eng.set_chunk_bytes(chunk)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} chunk {chunk}")
