@@ -11,6 +11,7 @@
 #include "k_duplex.cuh"
 #include "k_group_select.cuh"
 #include "k_score_vote.cuh"
+#include "k_umi_extract.cuh"
 #include "k_vote_tiled.cuh"
 
 using namespace gcb;
@@ -42,6 +43,7 @@ struct gcb_ctx {
     // device mirror of a host batch / result (gcb_consensus_batch)
     DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
     DevBuf d_pair_group, d_ngroups, d_groups, d_out, d_out_bytes;
+    DevBuf u_names, u_off, u_out, u_status;  // gcb_extract_umi
     // gcb_consensus_batch pipelines chunks of clusters: copies in, kernels and copies out run on three streams
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaEvent_t ev_in[GCB_MAX_CHUNKS] = {nullptr}, ev_done[GCB_MAX_CHUNKS] = {nullptr}, ev_out[GCB_MAX_CHUNKS] = {nullptr};
@@ -302,7 +304,7 @@ void gcb_destroy(gcb_ctx *ctx) {
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
                      &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
-                     &ctx->d_out, &ctx->d_out_bytes};
+                     &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status};
     for (DevBuf *b : all) release(*b);
     for (int k = 0; k < GCB_MAX_CHUNKS; k++) {
         if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
@@ -513,6 +515,36 @@ int gcb_consensus_batch(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *hr) {
     *hr->out_bytes = ctx->h_totals[K - 1];
     const int32_t flag = *ctx->h_flag;
     if (flag != GCB_OK) return fail(ctx, flag, flag == GCB_ERR_CAPACITY ? "out_payload too small" : "malformed batch");
+    return GCB_OK;
+}
+
+int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, int32_t n, const char *prefix, int32_t umi_words,
+                    uint64_t *out_umi, uint8_t *status) {
+    if (!ctx || n < 0 || umi_words < 1 || umi_words > GCB_MAX_UMI_WORDS || (n > 0 && (!names || !name_off || !out_umi || !status)))
+        return fail(ctx, GCB_ERR_ARG, "gcb_extract_umi: bad argument");
+    UmiPrefix pf;
+    memset(&pf, 0, sizeof pf);
+    const size_t plen = prefix ? strlen(prefix) : 0;
+    if (plen >= UMI_MAX_PREFIX) return fail(ctx, GCB_ERR_ARG, "gcb_extract_umi: prefix longer than 31 characters");
+    if (plen) memcpy(pf.s, prefix, plen);
+    pf.len = (int32_t)plen;
+    if (n == 0) return GCB_OK;
+    GCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)name_off[n];
+    int rc;
+    if ((rc = reserve(ctx, ctx->u_names, bytes)) != GCB_OK || (rc = reserve(ctx, ctx->u_off, ((size_t)n + 1) * 8)) != GCB_OK ||
+        (rc = reserve(ctx, ctx->u_out, (size_t)n * umi_words * 8)) != GCB_OK || (rc = reserve(ctx, ctx->u_status, (size_t)n)) != GCB_OK)
+        return rc;
+    cudaStream_t st = ctx->stream;
+    if (bytes) GCB_CUDA(ctx, cudaMemcpyAsync(ctx->u_names.p, names, bytes, cudaMemcpyHostToDevice, st));
+    GCB_CUDA(ctx, cudaMemcpyAsync(ctx->u_off.p, name_off, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+    GCB_LAUNCH(umi_extract_kernel, dim3((unsigned)((n + UMI_EXTRACT_THREADS - 1) / UMI_EXTRACT_THREADS)), dim3(UMI_EXTRACT_THREADS), 0, st,
+               (const char *)ctx->u_names.p, (const int64_t *)ctx->u_off.p, n, pf, umi_words, (uint64_t *)ctx->u_out.p, (uint8_t *)ctx->u_status.p);
+    ctx->launches++;
+    GCB_CUDA(ctx, cudaGetLastError());
+    GCB_CUDA(ctx, cudaMemcpyAsync(out_umi, ctx->u_out.p, (size_t)n * umi_words * 8, cudaMemcpyDeviceToHost, st));
+    GCB_CUDA(ctx, cudaMemcpyAsync(status, ctx->u_status.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    GCB_CUDA(ctx, cudaStreamSynchronize(st));
     return GCB_OK;
 }
 

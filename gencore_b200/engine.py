@@ -24,7 +24,7 @@ DEFAULT_LIB = os.path.join(HERE, "csrc", "libgencore_b200.so")
 # every symbol include/gencore_b200.h declares
 ABI_SYMBOLS = ["gcb_abi_version", "gcb_default_options", "gcb_create", "gcb_destroy", "gcb_last_error", "gcb_set_reference",
                "gcb_set_reference_device", "gcb_consensus_batch", "gcb_consensus_batch_device", "gcb_batch_status",
-               "gcb_launch_count", "gcb_set_chunk_bytes"]
+               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi"]
 
 
 class EngineError(RuntimeError):
@@ -55,6 +55,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gcb_consensus_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     lib.gcb_batch_status.restype = C.c_int
     lib.gcb_batch_status.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gcb_extract_umi.restype = C.c_int
+    lib.gcb_extract_umi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.gcb_set_chunk_bytes.restype = C.c_int
     lib.gcb_set_chunk_bytes.argtypes = [C.c_void_p, C.c_int64]
     lib.gcb_launch_count.restype = C.c_int64
@@ -125,6 +127,19 @@ class ConsensusEngine:
     # -- same with every buffer resident on the device (pointers are integers, e.g. torch .data_ptr())
     def cluster_by_umi_device(self, bs: BatchStruct, rs: ResultStruct, stages: int = STAGE_ALL, stream: int = 0) -> None:
         self._check(self.lib.gcb_consensus_batch_device(self._ctx, C.byref(bs), C.byref(rs), stages, C.c_void_p(stream)))
+
+    # -- BamUtil::getUMI over a list of names (bamutil.cpp:40-112), encoded for Batch.umi
+    def extract_umi(self, names, prefix: str, umi_words: int = 1):
+        """names: list of bytes (qname, or the MI:Z value when the record has one).  Returns (uint64 [n, umi_words], uint8 status [n])."""
+        blob = b"".join(names)
+        off = np.zeros(len(names) + 1, np.int64)
+        np.cumsum([len(x) for x in names], out=off[1:])
+        buf = np.frombuffer(blob, np.uint8) if blob else np.zeros(1, np.uint8)
+        out = np.zeros((len(names), umi_words), np.uint64)
+        status = np.zeros(max(len(names), 1), np.uint8)
+        self._check(self.lib.gcb_extract_umi(self._ctx, buf.ctypes.data, off.ctypes.data, len(names), prefix.encode(), umi_words,
+                                             out.ctypes.data, status.ctypes.data))
+        return out, status[:len(names)]
 
     def set_chunk_bytes(self, nbytes: int) -> None:
         """Payload bytes per pipeline chunk of cluster_by_umi (tuning only: results do not depend on it)."""

@@ -190,6 +190,15 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
  * synchronises the stream. */
 int gcb_batch_status(gcb_ctx *ctx, void *stream);
 
+/* BamUtil::getUMI(string qname, const string& prefix) (bamutil.cpp:40-112) for n strings at once, encoded as the
+ * `umi` field of gcb_batch wants it.  names = the strings back to back (no terminators needed), name_off[n+1] their
+ * byte offsets; the caller passes the MI:Z tag value instead of the qname when the record has one (bamutil.cpp:23-38).
+ * prefix = Options::umiPrefix ("" = no-prefix mode), at most 31 characters.  status[i] = 0, or 1 when the UMI has more
+ * than 16*umi_words characters (its code is truncated).  HOST buffers; runs on the context's stream and returns when
+ * out_umi / status are filled. */
+int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, int32_t n, const char *prefix, int32_t umi_words,
+                    uint64_t *out_umi, uint8_t *status);
+
 /* Tuning knob of gcb_consensus_batch: payload bytes per pipeline chunk (default 48 MiB; at most 16 chunks per call,
  * chunks are whole clusters).  Results do not depend on it. */
 int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes);
