@@ -30,8 +30,7 @@ constexpr int VT_THREADS = 256;
 constexpr int VT_WARPS = VT_THREADS / WARP;
 constexpr int VT_MAX_PAIRS = VT_THREADS;     // pair positions of a tile (one thread each in the prologue)
 constexpr int VT_MAX_FS = 256;               // family sides of a tile
-constexpr int VT_WARP_QUEUE = 64;            // slow columns a warp queues per bundle; more are decided inline by their owner
-constexpr int VT_SLOW_CAP = VT_WARPS * VT_WARP_QUEUE;
+constexpr int VT_SLOW_CAP = 512;             // queued slow columns; more are decided inline by their owner
 constexpr int VT_BIN_COLS = VT_THREADS / 8;  // slow columns histogrammed per pass (eight threads each)
 constexpr int VT_CHUNK = 16;                 // columns per lane
 
@@ -426,6 +425,7 @@ __global__ void __launch_bounds__(VT_THREADS, 3) vote_tiled_kernel(BatchView b, 
                                                                 int32_t slab_cap, int32_t implied) {
     GCB_DYN_SMEM(smem);
     uint64_t *bar = (uint64_t *)(smem + VT_OFF_BAR);
+    int *s_nslow = (int *)(smem + VT_OFF_NSLOW);
     int *s_nofit = (int *)(smem + VT_OFF_NOFIT);
     int *s_nfs = (int *)(smem + VT_OFF_NFS);
     int *s_next = (int *)(smem + VT_OFF_NEXT);
@@ -455,6 +455,7 @@ __global__ void __launch_bounds__(VT_THREADS, 3) vote_tiled_kernel(BatchView b, 
     if (NP == 0) return;  // clusters without pairs emit nothing
     if (tid == 0) {
         tile_barrier_init(bar);
+        *s_nslow = 0;
         *s_nofit = 0;
         *s_next = 0;
         *s_lmax = 1;
@@ -673,74 +674,74 @@ __global__ void __launch_bounds__(VT_THREADS, 3) vote_tiled_kernel(BatchView b, 
                 }
             }
         }
+        if (!mine) continue;
         // ---- what the record gets: qualities = the maxima (fast columns), bases = the template's
+        uint32_t oq[4];
         uint32_t slow0 = 0u, slow1 = 0u;
-        if (mine) {
-            uint32_t oq[4];
-            if (ft.mode == SIDE_COPY) {  // group.cpp:73-77: the record itself
+        if (ft.mode == SIDE_COPY) {  // group.cpp:73-77: the record itself
 #pragma unroll
-                for (int k = 0; k < 4; k++) oq[k] = col0 + 4 * k < qbytes ? GCB_LDS32(trec + col0 + 4 * k) : 0u;
-            } else {
+            for (int k = 0; k < 4; k++) oq[k] = col0 + 4 * k < qbytes ? GCB_LDS32(trec + col0 + 4 * k) : 0u;
+        } else {
 #pragma unroll
-                for (int k = 0; k < 4; k++) oq[k] = prmt(mo[k], me[k], 0x3715u) & cm.vb[k];  // (the hoisted loop read whole words)
-                dis0 &= cm.vn0;
-                dis1 &= cm.vn1;
-                GCB_COUNT(2, cm.nvote);
-                if (implied && len == l_out) {
-                    const uint32_t lowq0 = nibs_of_bytes(~__vcmpgeu4(oq[0], mod4), ~__vcmpgeu4(oq[1], mod4));
-                    const uint32_t lowq1 = nibs_of_bytes(~__vcmpgeu4(oq[2], mod4), ~__vcmpgeu4(oq[3], mod4));
-                    slow0 = (dis0 | lowq0) & cm.vn0;
-                    slow1 = (dis1 | lowq1) & cm.vn1;
-                } else {  // without `implied`, or with columns that are not voted, every column of the record is slow
-                    slow0 = nibs_of_bytes(cm.rb[0], cm.rb[1]);
-                    slow1 = nibs_of_bytes(cm.rb[2], cm.rb[3]);
-                }
+            for (int k = 0; k < 4; k++) oq[k] = prmt(mo[k], me[k], 0x3715u) & cm.vb[k];  // (the hoisted loop read whole words)
+            dis0 &= cm.vn0;
+            dis1 &= cm.vn1;
+            GCB_COUNT(2, cm.nvote);
+            if (implied && len == l_out) {
+                const uint32_t lowq0 = nibs_of_bytes(~__vcmpgeu4(oq[0], mod4), ~__vcmpgeu4(oq[1], mod4));
+                const uint32_t lowq1 = nibs_of_bytes(~__vcmpgeu4(oq[2], mod4), ~__vcmpgeu4(oq[3], mod4));
+                slow0 = (dis0 | lowq0) & cm.vn0;
+                slow1 = (dis1 | lowq1) & cm.vn1;
+            } else {  // without `implied`, or with columns that are not voted, every column of the record is slow
+                slow0 = nibs_of_bytes(cm.rb[0], cm.rb[1]);
+                slow1 = nibs_of_bytes(cm.rb[2], cm.rb[3]);
             }
-            uint8_t *out = t.out0 + 4 * (int64_t)ft.out4;
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (col0 + 4 * k < qbytes) *(uint32_t *)(out + col0 + 4 * k) = oq[k] & cm.rb[k];
-            if (8 * j < sbytes) *(uint32_t *)(out + qbytes + 8 * j) = bswap32(tbe0 & cm.kn0);
-            if (8 * j + 4 < sbytes) *(uint32_t *)(out + qbytes + 8 * j + 4) = bswap32(tbe1 & cm.kn1);
         }
-        // ---- the bundle's slow columns (one or two per family side of a clean library): the warp queues them and
-        // decides them four at a time, one octet of lanes per column; no CTA barrier, the other warps keep voting
-        uint32_t *wq = s_slow + warp * VT_WARP_QUEUE;
-        int qn = 0;
+        uint8_t *out = t.out0 + 4 * (int64_t)ft.out4;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (col0 + 4 * k < qbytes) *(uint32_t *)(out + col0 + 4 * k) = oq[k] & cm.rb[k];
+        if (8 * j < sbytes) *(uint32_t *)(out + qbytes + 8 * j) = bswap32(tbe0 & cm.kn0);
+        if (8 * j + 4 < sbytes) *(uint32_t *)(out + qbytes + 8 * j + 4) = bswap32(tbe1 & cm.kn1);
+        // queue the slow columns (one or two per family side of a clean library)
         for (int wsel = 0; wsel < 2; wsel++) {
             uint32_t sm = wsel ? slow1 : slow0;
-            while (__any_sync(FULL, sm != 0u)) {  // every lane that still has a slow column queues one per round
-                const bool has = sm != 0u;
-                const int k = has ? __clz((int)sm) >> 2 : 0;
-                if (has) sm &= ~(0xF0000000u >> (4 * k));
-                const unsigned vote = __ballot_sync(FULL, has);
-                if (has) {
-                    const int col = col0 + 8 * wsel + k;
-                    const int pos = qn + __popc(vote & ((1u << lane) - 1u));
-                    GCB_COUNT(3, 1);
-                    if (pos < VT_WARP_QUEUE) wq[pos] = ((uint32_t)f << 16) | (uint32_t)col;
-                    else slow_inline(t, f, col);  // queue full: this lane owns the chunk's words
-                }
-                qn += __popc(vote);
+            while (sm != 0u) {
+                const int k = __clz((int)sm) >> 2;
+                sm &= ~(0xF0000000u >> (4 * k));
+                const int col = col0 + 8 * wsel + k;
+                GCB_COUNT(3, 1);
+                const int idx = atomicAdd(s_nslow, 1);
+                if (idx < VT_SLOW_CAP) s_slow[idx] = ((uint32_t)f << 16) | (uint32_t)col;
+                else slow_inline(t, f, col);  // queue full: this lane owns the chunk's words
             }
         }
-        __syncwarp();
-        {
-            const int nq = min(qn, VT_WARP_QUEUE), oct = lane >> 3;
-            for (int base = 0; base < nq; base += 4) {
-                const bool active = base + oct < nq;
-                const uint32_t code = active ? wq[base + oct] : 0u;
-                slow_octet(t, active, (int)(code >> 16), (int)(code & 0xFFFFu), s_bins + 64 * (tid >> 3), lane & 7);
-                __syncwarp();
-            }
+    }
+    __syncthreads();
+    // ---- slow columns: one octet (eight lanes) per column, thirty-two columns per pass; an octet owns its bins
+    {
+        const int n = min(*s_nslow, VT_SLOW_CAP);
+        const int ci = tid >> 3, sub8 = tid & 7;
+        for (int base = 0; base < n; base += VT_BIN_COLS) {
+            const bool active = base + ci < n;
+            const uint32_t code = active ? s_slow[base + ci] : 0u;
+            slow_octet(t, active, (int)(code >> 16), (int)(code & 0xFFFFu), s_bins + 64 * ci, sub8);
+            __syncwarp();
         }
-        // ---- per family side: diff, mismatchInc, rollback, absolute output offset (first lane of the family side)
-        if (mine && j == 0) {
+    }
+    __syncthreads();
+    // ---- per family side: diff, mismatchInc, rollback, absolute output offset
+    if (live0 || live1) {
+        int fidx = fidx0;
+        for (int side = 0; side < 2; side++) {
+            if (fd[side].mode == SIDE_NONE) continue;
+            const int f = fidx++;
+            const FsTile ft = s_ft[f];
+            if (ft.mode == SIDE_NONE) continue;
             const int acc = s_acc[f];
             const int diff = acc & 0xFFFF, mm = (acc - diff) >> 16;
             if (mm > 5) rollback_record(t, f);
-            const int side = fs_side(ft);
-            gcb_group_result *gr = r.groups + ft.slot;
+            gcb_group_result *gr = r.groups + (P0 + tid);
             gr->diff[side] = diff;
             gr->mismatch_inc[side] = mm;
             gr->out_off[side] = out_base0 + 4 * (int64_t)ft.out4;
