@@ -29,10 +29,9 @@ namespace gcb {
 constexpr int VT_THREADS = 256;
 constexpr int VT_WARPS = VT_THREADS / WARP;
 constexpr int VT_MAX_PAIRS = VT_THREADS;     // pair positions of a tile (one thread each in the prologue)
-constexpr int VT_MAX_FS = 224;               // family sides of a tile
-constexpr int VT_SLOW_CAP = 384;             // queued slow columns; more are decided inline by their owner
+constexpr int VT_MAX_FS = 256;               // family sides of a tile
+constexpr int VT_SLOW_CAP = 512;             // queued slow columns; more are decided inline by their owner
 constexpr int VT_BIN_COLS = VT_THREADS / 8;  // slow columns histogrammed per pass (eight threads each)
-constexpr int VT_REC_COLS = 2 * VT_BIN_COLS; // slow columns whose top/second bins wait for the packed finish
 constexpr int VT_CHUNK = 16;                 // columns per lane
 
 // shared-memory map (bytes)
@@ -46,8 +45,7 @@ constexpr int VT_OFF_WSUM = 32;                                  // VT_WARPS war
 constexpr int VT_OFF_ACC = 64;                                   // int32[VT_MAX_FS]
 constexpr int VT_OFF_SLOW = VT_OFF_ACC + 4 * VT_MAX_FS;          // uint32[VT_SLOW_CAP]
 constexpr int VT_OFF_BINS = VT_OFF_SLOW + 4 * VT_SLOW_CAP;       // int32[VT_BIN_COLS][16][4]
-constexpr int VT_OFF_REC = VT_OFF_BINS + 4 * VT_BIN_COLS * 64;   // SlowRec[VT_REC_COLS]
-constexpr int VT_OFF_FT = VT_OFF_REC + 32 * VT_REC_COLS;         // FsTile[VT_MAX_FS]
+constexpr int VT_OFF_FT = VT_OFF_BINS + 4 * VT_BIN_COLS * 64;    // FsTile[VT_MAX_FS]
 constexpr int VT_OFF_VR = VT_OFF_FT + 32 * VT_MAX_FS;            // VoteRead[2*VT_MAX_PAIRS]
 constexpr int VT_OFF_SLAB = (VT_OFF_VR + 16 * 2 * VT_MAX_PAIRS + 127) & ~127;
 constexpr int VT_SLAB_SLACK = 64;  // the hoisted loop reads whole words past a record's end (masked afterwards)
@@ -223,21 +221,8 @@ GCB_DEV void slow_histogram(const TileCtx &t, const FsTile &ft, int col, int e, 
     atomicMax(bin + 3, qual);
 }
 
-// What the octet phase leaves for the packed finish of one slow column (32 bytes): the top and second bins
-// of group.cpp:395-417, the total score, and the best quality of the four bins a reference base can name.
-struct __align__(16) SlowRec {
-    int32_t top_score, top_qual;
-    int32_t sec_score, sec_qual;
-    int32_t total;
-    uint32_t acgt_maxq;          // best quality of codes 1, 2, 4, 8 in bytes 0..3 (0 when nobody showed the code)
-    uint16_t top_cnt, sec_cnt;
-    uint8_t top_base, sec_base, top_maxq, sec_maxq;
-};
-static_assert(sizeof(SlowRec) == 32, "SlowRec is 32 bytes");
-
 // group.cpp:419-525 for one slow column once its top and second bins are known.  Thread-local.
-// `acgt_maxq`: see SlowRec.
-GCB_DEV void slow_finish(const TileCtx &t, int f, int col, ColumnTop &top, int total, uint32_t acgt_maxq) {
+GCB_DEV void slow_finish(const TileCtx &t, int f, int col, ColumnTop &top, int total, const int32_t *bins) {
     const gcb_options &o = *t.o;
     const FsTile ft = t.ft[f];
     const int side = fs_side(ft);
@@ -269,7 +254,7 @@ GCB_DEV void slow_finish(const TileCtx &t, int f, int col, ColumnTop &top, int t
         int rbq = 0;
         bool any_high = false;
         if (top.need_ref && ref4 != 0) {
-            const int rmax = (int)((acgt_maxq >> (ref4 == 1 ? 0 : ref4 == 2 ? 8 : ref4 == 4 ? 16 : 24)) & 0xFFu);
+            const int rmax = bins[4 * ref4] > 0 ? bins[4 * ref4 + 3] : 0;
             if (rmax >= 128) {  // `char refBaseQual` wraps: the scan order matters (group.cpp:474-490): template first
                 int tb, tq, ts;
                 if (fetch_ent(cb, tv, col, side, o, tb, tq, ts) && tb == ref4) {
@@ -329,9 +314,7 @@ GCB_DEV void slow_decide(const TileCtx &t, int f, int col, const int32_t *bins) 
         }
     }
     ColumnTop top = column_top(*t.o, obs, nobs, total);
-    const uint32_t acgt = (uint32_t)(bins[4 * 1] > 0 ? bins[4 * 1 + 3] : 0) | ((uint32_t)(bins[4 * 2] > 0 ? bins[4 * 2 + 3] : 0) << 8) |
-                          ((uint32_t)(bins[4 * 4] > 0 ? bins[4 * 4 + 3] : 0) << 16) | ((uint32_t)(bins[4 * 8] > 0 ? bins[4 * 8 + 3] : 0) << 24);
-    slow_finish(t, f, col, top, total, acgt);
+    slow_finish(t, f, col, top, total, bins);
 }
 
 // The (score, quality sum, code) order of group.cpp:395-417 as one integer: the scans walk the sixteen bins,
@@ -345,8 +328,8 @@ GCB_DEV unsigned long long min_u64(unsigned long long a, unsigned long long b) {
 
 // One slow column by the eight lanes of an octet: group.cpp:376-393 (histogram, lanes stride the reads), then
 // the two scans of group.cpp:395-417 as a top-2 reduction of the sixteen bin keys (two bins per lane, three
-// shuffle steps); lane 0 of the octet leaves the two bins in *out for the packed finish.  Every lane of the warp must call it.
-GCB_DEV void slow_octet(const TileCtx &t, bool active, int f, int col, int32_t *bins, int sub8, SlowRec *out) {
+// shuffle steps), then lane 0 of the octet applies the rules.  Every lane of the warp must call it.
+GCB_DEV void slow_octet(const TileCtx &t, bool active, int f, int col, int32_t *bins, int sub8) {
     FsTile ft;
     ft.m = 0; ft.len = 0; ft.ent0 = 0; ft.cbase4 = 0; ft.flags = 0;
     if (active) ft = t.ft[f];
@@ -370,28 +353,16 @@ GCB_DEV void slow_octet(const TileCtx &t, bool active, int f, int col, int32_t *
         top = max_u64(top, ot);
     }
     if (!active || sub8 != 0) return;
-    const int tb = (int)(top & 0xF), sb = (int)(sec & 0xF);
-    const int4 T = b4[tb], S = b4[sb];
-    SlowRec rec;
-    rec.top_score = T.y; rec.top_qual = T.z; rec.sec_score = S.y; rec.sec_qual = S.z;
-    rec.total = total;
-    rec.acgt_maxq = (uint32_t)(b4[1].x > 0 ? b4[1].w : 0) | ((uint32_t)(b4[2].x > 0 ? b4[2].w : 0) << 8) |
-                    ((uint32_t)(b4[4].x > 0 ? b4[4].w : 0) << 16) | ((uint32_t)(b4[8].x > 0 ? b4[8].w : 0) << 24);
-    rec.top_cnt = (uint16_t)T.x; rec.sec_cnt = (uint16_t)S.x;
-    rec.top_base = (uint8_t)tb; rec.sec_base = (uint8_t)sb; rec.top_maxq = (uint8_t)T.w; rec.sec_maxq = (uint8_t)S.w;
-    *out = rec;
-}
-
-// the packed finish: one thread per slow column applies the rules to the record its octet left
-GCB_DEV void slow_finish_rec(const TileCtx &t, int f, int col, const SlowRec &rec) {
-    if (col >= (int)t.ft[f].len) {
+    if (!voted) {
         slow_unvoted(t, f, col);
         return;
     }
+    const int tb = (int)(top & 0xF), sb = (int)(sec & 0xF);
+    const int4 T = b4[tb], S = b4[sb];
     ColumnTop ct;
-    ct.top.base = rec.top_base; ct.top.cnt = rec.top_cnt; ct.top.score = rec.top_score; ct.top.qual = rec.top_qual; ct.top.maxq = rec.top_maxq;
-    ct.sec.base = rec.sec_base; ct.sec.cnt = rec.sec_cnt; ct.sec.score = rec.sec_score; ct.sec.qual = rec.sec_qual; ct.sec.maxq = rec.sec_maxq;
-    slow_finish(t, f, col, ct, rec.total, rec.acgt_maxq);
+    ct.top.base = tb; ct.top.cnt = T.x; ct.top.score = T.y; ct.top.qual = T.z; ct.top.maxq = T.w;
+    ct.sec.base = sb; ct.sec.cnt = S.x; ct.sec.score = S.y; ct.sec.qual = S.z; ct.sec.maxq = S.w;
+    slow_finish(t, f, col, ct, total, bins);
 }
 
 // a slow column decided by its owner alone (queue overflow): the histogram lives in local memory
@@ -747,26 +718,15 @@ __global__ void __launch_bounds__(VT_THREADS, 3) vote_tiled_kernel(BatchView b, 
         }
     }
     __syncthreads();
-    // ---- slow columns, sixty-four at a time: one octet (eight lanes) per column builds the histogram and reduces it
-    // to the top and second bins (thirty-two columns per pass, an octet owns its bins); then one thread per column
-    // applies the rules, so that the scalar part runs on packed warps
+    // ---- slow columns: one octet (eight lanes) per column, thirty-two columns per pass; an octet owns its bins
     {
         const int n = min(*s_nslow, VT_SLOW_CAP);
         const int ci = tid >> 3, sub8 = tid & 7;
-        SlowRec *s_rec = (SlowRec *)(smem + VT_OFF_REC);
-        for (int base = 0; base < n; base += VT_REC_COLS) {
-            for (int pass = 0; pass < VT_REC_COLS && base + pass < n; pass += VT_BIN_COLS) {
-                const bool active = base + pass + ci < n;
-                const uint32_t code = active ? s_slow[base + pass + ci] : 0u;
-                slow_octet(t, active, (int)(code >> 16), (int)(code & 0xFFFFu), s_bins + 64 * ci, sub8, s_rec + pass + ci);
-                __syncwarp();
-            }
-            __syncthreads();
-            if (tid < VT_REC_COLS && base + tid < n) {
-                const uint32_t code = s_slow[base + tid];
-                slow_finish_rec(t, (int)(code >> 16), (int)(code & 0xFFFFu), s_rec[tid]);
-            }
-            if (base + VT_REC_COLS < n) __syncthreads();
+        for (int base = 0; base < n; base += VT_BIN_COLS) {
+            const bool active = base + ci < n;
+            const uint32_t code = active ? s_slow[base + ci] : 0u;
+            slow_octet(t, active, (int)(code >> 16), (int)(code & 0xFFFFu), s_bins + 64 * ci, sub8);
+            __syncwarp();
         }
     }
     __syncthreads();
