@@ -211,9 +211,42 @@ GCB_DEV int fs_side(const FsTile &ft) { return (ft.flags & FS_SIDE1) ? 1 : 0; }
 
 // group.cpp:376-393 for one read of one slow column: its vote goes into the column's sixteen bins
 // {count, sum of scores, sum of qualities, best quality}
+// Pair::qual2score (pair.cpp:77-86) as selects
+GCB_DEV int qual2score_sel(const gcb_options &o, int q) {
+    return q >= o.high_quality ? sc8(o.score_high) : q >= o.moderate_quality ? sc8(o.score_moderate) : q >= o.low_quality ? sc8(o.score_low) : sc8(o.score_bad);
+}
+
+// fetch_ent without divergent branches (the lanes of a warp histogram different reads of different columns, so every
+// branch of fetch_ent would be walked by the whole warp): all cases are computed and selected.  Same results.
+GCB_DEV bool fetch_vote(const uint8_t *cb, const VoteRead &v, int i, int side, const gcb_options &o, int &base, int &qual, int &score) {
+    const int rp = i + v.shift;
+    if (v.own_off4 == VR_NO_VOTE || rp < 0 || rp >= v.own_l) return false;
+    const uint8_t *q = cb + 4 * (int)v.own_off4;
+    const int ql = q[rp];
+    base = base_at(q + GCB_ALIGN4(v.own_l), rp);
+    const bool info = v.ov_len != VR_NO_OVERLAP_INFO;
+    const int k = rp - v.ov_own, mp = v.ov_mate + k;
+    const bool inwin = info && k >= 0 && k < v.ov_len;
+    const bool mvalid = inwin && mp >= 0 && mp < v.mate_l;
+    const int mpi = mvalid ? mp : 0;                                  // (any in-bounds byte when there is no mate base)
+    const uint8_t *mq = cb + (mvalid ? 4 * (int)v.mate_off4 : 0);
+    const int mql = mq[mpi];
+    const int mbase = base_at(mq + (mvalid ? GCB_ALIGN4(v.mate_l) : 0), mpi);
+    const bool match = base == mbase;
+    const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
+    const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
+    const int s_plain = qual2score_sel(o, ql);
+    const int s_match = sc8(qual2score_sel(o, (ql + mql) / 2) + 4);
+    const int s_mis = mine ? sc8(qual2score_sel(o, lq >= rq ? lq - rq : rq - lq) - 3) : 0;
+    const int moderate = sc8(o.score_moderate);
+    score = !info ? moderate : !inwin ? s_plain : !mvalid ? moderate : match ? s_match : s_mis;
+    qual = (mvalid && !match) ? max(0, ql - mql) : ql;
+    return true;
+}
+
 GCB_DEV void slow_histogram(const TileCtx &t, const FsTile &ft, int col, int e, int32_t *bins) {
     int base, qual, score;
-    if (!fetch_ent(t.slab + 4 * (int)ft.cbase4, t.vr[ft.ent0 + e], col, fs_side(ft), *t.o, base, qual, score)) return;
+    if (!fetch_vote(t.slab + 4 * (int)ft.cbase4, t.vr[ft.ent0 + e], col, fs_side(ft), *t.o, base, qual, score)) return;
     int32_t *bin = bins + 4 * base;
     atomicAdd(bin, 1);
     atomicAdd(bin + 1, score);
@@ -497,8 +530,14 @@ __global__ void __launch_bounds__(VT_THREADS, 3) vote_tiled_kernel(BatchView b, 
         }
         if (lane == WARP - 1) s_wsum[warp] = incl;
         __syncthreads();
-        uint32_t pre = incl - mine;
-        for (int w = 0; w < warp; w++) pre += s_wsum[w];
+        // exclusive scan of the warp totals by every warp for itself (VT_WARPS <= 32 lanes)
+        const uint32_t wt = lane < VT_WARPS ? s_wsum[lane] : 0u;
+        uint32_t wincl = wt;
+        for (int off = 1; off < VT_WARPS; off <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, wincl, off);
+            if (lane >= off) wincl += v;
+        }
+        const uint32_t pre = incl - mine + __shfl_sync(FULL, wincl - wt, warp);
         fidx0 = (int)pre;
         if (tid == VT_THREADS - 1) {
             *s_nfs = (int)(pre + mine);
