@@ -40,6 +40,16 @@ def _cfg(contig_len=None):
     return dataclasses.replace(cfg, contig_len=contig_len) if contig_len else cfg
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one vote_tiled_kernel launch on this workload (profiles/traffic.json,
+    written from the ncu --set full capture named there); None when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)["traffic"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -291,8 +301,10 @@ def b200_arm(args):
                        "l2": "inputs larger than L2 (payload %d MB per step)" % (len(batch.payload) >> 20),
                        "stage_ms": {n: float(v) for n, v in zip(names, stage_ms)},
                        "stats": {"clusters": int(stats_vec[0]), "molecules": int(stats_vec[1]), "sscs": int(stats_vec[2]), "dcs": int(stats_vec[3])}},
-            "roofline": {"bound": "hbm", "kernel": "score_vote_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": args.traffic, "algorithmic_bytes": alg, "kernel_ms": vote_ms},
+            "roofline": {"bound": "hbm", "kernel": "vote_tiled_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": args.traffic if args.traffic is not None else (measured_traffic() if args.pairs == 1_000_000 else None),
+                         "algorithmic_bytes": alg, "kernel_ms": vote_ms,
+                         "timed": "CUDA events around the vote stage on the launching stream (vote_tiled_kernel + the generic kernel's empty launch)"},
             "e2e": {"value": args.pairs * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * e2e_s},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -316,8 +328,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=1_000_000, help="read pairs per GPU per step")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--ref-pairs-per-core", type=int, default=50_000, help="reference arm: pairs per step on each host core")
-    ap.add_argument("--cpu-pairs", type=int, default=200_000, help="cpu_baseline sample size (one core)")
-    ap.add_argument("--cpu-reps", type=int, default=8, help="cpu_baseline repetitions of the sample")
+    ap.add_argument("--cpu-pairs", type=int, default=400_000, help="cpu_baseline sample size (one core)")
+    ap.add_argument("--cpu-reps", type=int, default=10, help="cpu_baseline repetitions of the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per vote launch from an ncu capture (profiles/)")
     args = ap.parse_args()
