@@ -282,6 +282,15 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
             if (lo >= hi) leftReadMode = true;  // all equal, or no read at all
         }
 
+        // BamUtil::getRightRefPos (bamutil.cpp:379-383) of the right reads: only this general path compares them
+        if (!isLeft) {
+            for (int k = lane; k < m; k += WARP) {
+                if (!GCB_HAVE(k)) continue;
+                const gcb_read_desc rk = b.reads[GCB_SLOT(k)];
+                ws.right_ref_pos[GCB_SLOT(k)] = rk.pos < 0 ? -1 : rk.pos + cigar_ref_len(b.cigar + rk.cigar_off, rk.n_cigar);
+            }
+            __syncwarp();
+        }
         // group.cpp:196-233: containedBy[i] = 1 + #{j : read i is part of read j}
         int first_big = 0x7FFFFFFF;
         for (int k = lane; k < m; k += WARP) {
@@ -387,8 +396,6 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
     for (int i = lane; i < n; i += WARP) {
         const int64_t pair = p0 + i;
         const gcb_read_desc L = b.reads[2 * pair], R = b.reads[2 * pair + 1];
-        if (L.l_qseq >= 0) ws.right_ref_pos[2 * pair] = L.pos < 0 ? -1 : L.pos + cigar_ref_len(b.cigar + L.cigar_off, L.n_cigar);
-        if (R.l_qseq >= 0) ws.right_ref_pos[2 * pair + 1] = R.pos < 0 ? -1 : R.pos + cigar_ref_len(b.cigar + R.cigar_off, R.n_cigar);
         ws.vote_flags[2 * pair] = 0;
         ws.vote_flags[2 * pair + 1] = 0;
         PairOverlap ov = {0, 0, 0, 0};
