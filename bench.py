@@ -205,6 +205,7 @@ def b200_arm(args):
     del contigs
     opt = Options.default()
     eng = ConsensusEngine(opt, local)
+    eng.set_vote_mode(args.vote_mode)
     # the packed reference reaches every GPU by ONE NCCL broadcast from rank 0
     g_dev = torch.from_numpy(genome.packed4).to(dev) if rank == 0 else torch.empty(len(genome.packed4), dtype=torch.uint8, device=dev)
     if world > 1:
@@ -301,7 +302,7 @@ def b200_arm(args):
                        "l2": "inputs larger than L2 (payload %d MB per step)" % (len(batch.payload) >> 20),
                        "stage_ms": {n: float(v) for n, v in zip(names, stage_ms)},
                        "stats": {"clusters": int(stats_vec[0]), "molecules": int(stats_vec[1]), "sscs": int(stats_vec[2]), "dcs": int(stats_vec[3])}},
-            "roofline": {"bound": "hbm", "kernel": "vote_tiled_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "vote_pipe_kernel (+ tile_prep_kernel)" if args.vote_mode == 1 else "vote_tiled_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": args.traffic if args.traffic is not None else (measured_traffic() if args.pairs == 1_000_000 else None),
                          "algorithmic_bytes": alg, "kernel_ms": vote_ms,
                          "timed": "CUDA events around the vote stage on the launching stream (vote_tiled_kernel + the generic kernel's empty launch)"},
@@ -331,6 +332,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=400_000, help="cpu_baseline sample size (one core)")
     ap.add_argument("--cpu-reps", type=int, default=10, help="cpu_baseline repetitions of the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--vote-mode", type=int, default=0, choices=[0, 1], help="0 = one CTA per tile, 1 = persistent pipelined vote kernel")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per vote launch from an ncu capture (profiles/)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -13,10 +13,12 @@
 #include "k_score_vote.cuh"
 #include "k_umi_extract.cuh"
 #include "k_vote_tiled.cuh"
+#include "k_vote_pipe.cuh"
 
 using namespace gcb;
 
 constexpr int GCB_MAX_CHUNKS = 16;
+constexpr int GCB_VOTE_TILED = 0, GCB_VOTE_PIPELINED = 1;
 constexpr int64_t GCB_CHUNK_BYTES = 48ll << 20;  // payload per pipeline chunk of gcb_consensus_batch
 
 namespace {
@@ -40,6 +42,9 @@ struct gcb_ctx {
     // workspace (grow-only)
     DevBuf w_members, w_group_off, w_scratch, w_rrp, w_flags, w_mode, w_hasumi, w_overlap, w_slab, w_cob, w_coo, w_scan, w_err, w_tiles;
     DevBuf w_vr, w_fs, w_gtiles, w_gcount;
+    DevBuf w_thdr, w_fstiles, w_ptiles, w_pcount;  // pipelined vote: tile headers, compact family sides, tile list
+    int vote_mode = 0;                              // GCB_VOTE_TILED / GCB_VOTE_PIPELINED
+    int n_sms = 148;
     // device mirror of a host batch / result (gcb_consensus_batch)
     DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
     DevBuf d_pair_group, d_ngroups, d_groups, d_out, d_out_bytes;
@@ -91,11 +96,27 @@ void release(DevBuf &b) {
 // many CTAs as possible share an SM's 227 KB of shared memory.
 struct TilePlan {
     int32_t window, window_shift, slab_cap, smem;
+    int32_t pipelined, n_stages, stage_bytes;  // vote_pipe_kernel: ring of n_stages tiles of stage_bytes each
 };
-TilePlan plan_tiles(int32_t max_cluster_bytes) {
-    const int32_t KB = 1024, budget = 227 * KB, tables = VT_OFF_SLAB + VT_SLAB_SLACK + 1 * KB;  // + the 1 KB per-CTA reserve
+TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode) {
+    const int32_t KB = 1024, budget = 227 * KB;
     int32_t maxc = max_cluster_bytes > 0 ? ((max_cluster_bytes + 127) & ~127) : 16 * KB;
     TilePlan p;
+    memset(&p, 0, sizeof p);
+    if (vote_mode == GCB_VOTE_PIPELINED) {  // 16 KB windows: one CTA per SM keeps as many tiles in flight as fit
+        p.window_shift = 14;
+        p.window = 1 << p.window_shift;
+        p.slab_cap = p.window + maxc;
+        p.stage_bytes = (VPS_OFF_SLAB + p.slab_cap + VT_SLAB_SLACK + 127) & ~127;
+        p.n_stages = (budget - 1 * KB - VP_OFF_STAGE0) / p.stage_bytes;
+        if (p.n_stages > VP_MAX_STAGES) p.n_stages = VP_MAX_STAGES;
+        if (p.n_stages >= 3 && p.slab_cap <= VT_MAX_SLAB) {
+            p.pipelined = 1;
+            p.smem = VP_OFF_STAGE0 + p.n_stages * p.stage_bytes;
+            return p;
+        }
+    }
+    const int32_t tables = VT_OFF_SLAB + VT_SLAB_SLACK + 1 * KB;  // + the 1 KB per-CTA reserve
     if (32 * KB + maxc + tables <= budget / 3) p.window_shift = 15;       // three CTAs per SM
     else if (16 * KB + maxc + tables <= budget / 2) p.window_shift = 14;  // two
     else p.window_shift = 15;
@@ -140,6 +161,10 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_fs, 2 * n_pairs * sizeof(FsDesc));
     GCB_RES(w_gtiles, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * 4);
     GCB_RES(w_gcount, 4 * GCB_MAX_CHUNKS);
+    GCB_RES(w_thdr, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * sizeof(TileHdr));
+    GCB_RES(w_fstiles, 2 * n_pairs * sizeof(FsTile));
+    GCB_RES(w_ptiles, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * 4);
+    GCB_RES(w_pcount, 4 * GCB_MAX_CHUNKS);
 #undef GCB_RES
     ws.members = (int32_t *)ctx->w_members.p;
     ws.group_off = (int32_t *)ctx->w_group_off.p;
@@ -220,8 +245,21 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
     }
     if ((stages & GCB_STAGE_SCORE_VOTE) && n_tiles > 0) {
         GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
-        GCB_LAUNCH(vote_tiled_kernel, dim3((unsigned)n_tiles), dim3(VT_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
-                   plan.slab_cap, fast_path_implied(ctx->opt));
+        if (plan.pipelined) {
+            TileHdr *thdr = (TileHdr *)ctx->w_thdr.p + v.tile_base;
+            FsTile *fst = (FsTile *)ctx->w_fstiles.p;
+            int32_t *ptiles = (int32_t *)ctx->w_ptiles.p + v.tile_base, *pcount = (int32_t *)ctx->w_pcount.p + v.index;
+            GCB_CUDA(ctx, cudaMemsetAsync(pcount, 0, 4, stream));
+            GCB_LAUNCH(tile_prep_kernel, dim3((unsigned)n_tiles), dim3(VP_PREP_THREADS), 0, stream, b, r, ws, plan.slab_cap, thdr, fst, ptiles, pcount);
+            const unsigned pipe_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
+            GCB_LAUNCH(vote_pipe_kernel, dim3(pipe_grid), dim3(VP_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
+                       fast_path_implied(ctx->opt), plan.n_stages, plan.stage_bytes, (const TileHdr *)thdr, (const FsTile *)fst,
+                       (const int32_t *)ptiles, (const int32_t *)pcount);
+            ctx->launches++;
+        } else {
+            GCB_LAUNCH(vote_tiled_kernel, dim3((unsigned)n_tiles), dim3(VT_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
+                       plan.slab_cap, fast_path_implied(ctx->opt));
+        }
         const unsigned generic_grid = (unsigned)(n_tiles < 2 * 148 ? n_tiles : 2 * 148);
         GCB_LAUNCH(score_vote_kernel, dim3(generic_grid), dim3(VOTE_THREADS), VOTE_SMEM, stream, b, r, ws, ctx->genome, ctx->opt);
         ctx->launches += 2;
@@ -269,6 +307,7 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
     gcb_ctx *ctx = new (std::nothrow) gcb_ctx();
     if (!ctx) return GCB_ERR_ARG;
     ctx->device = device;
+    ctx->n_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     if (opt) ctx->opt = *opt;
     else gcb_default_options(&ctx->opt);
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -288,7 +327,8 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
         return GCB_ERR_CUDA;
     }
     if (cudaFuncSetAttribute(score_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        cudaFuncSetAttribute(vote_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(vote_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         gcb_destroy(ctx);
         return GCB_ERR_CUDA;
     }
@@ -302,7 +342,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
-                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
+                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_thdr, &ctx->w_fstiles, &ctx->w_ptiles, &ctx->w_pcount, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
                      &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status};
     for (DevBuf *b : all) release(*b);
@@ -364,7 +404,7 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
         return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch_device: bad sizes or alignment (payload 16 B, payload_bytes % 16, out_payload 4 B)");
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : ctx->stream;
     GCB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const TilePlan plan = plan_tiles(batch->max_cluster_bytes);
+    const TilePlan plan = plan_tiles(batch->max_cluster_bytes, ctx->vote_mode);
     const int64_t n_tiles = (batch->payload_bytes + plan.window - 1) / plan.window;
     Workspace ws;
     int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, ws);
@@ -435,7 +475,7 @@ int gcb_consensus_batch(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *hr) {
     if (K > GCB_MAX_CHUNKS) K = GCB_MAX_CHUNKS;
     if (K < 1) K = 1;
     if ((int64_t)K > (int64_t)nc) K = nc > 0 ? (int)nc : 1;
-    const TilePlan plan = plan_tiles(hb->max_cluster_bytes);
+    const TilePlan plan = plan_tiles(hb->max_cluster_bytes, ctx->vote_mode);
     ViewRange view[GCB_MAX_CHUNKS];
     {
         int32_t c_prev = 0;
@@ -545,6 +585,12 @@ int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, in
     GCB_CUDA(ctx, cudaMemcpyAsync(out_umi, ctx->u_out.p, (size_t)n * umi_words * 8, cudaMemcpyDeviceToHost, st));
     GCB_CUDA(ctx, cudaMemcpyAsync(status, ctx->u_status.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     GCB_CUDA(ctx, cudaStreamSynchronize(st));
+    return GCB_OK;
+}
+
+int gcb_set_vote_mode(gcb_ctx *ctx, int mode) {
+    if (!ctx || (mode != GCB_VOTE_TILED && mode != GCB_VOTE_PIPELINED)) return GCB_ERR_ARG;
+    ctx->vote_mode = mode;
     return GCB_OK;
 }
 

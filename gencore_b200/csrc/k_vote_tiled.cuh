@@ -255,7 +255,8 @@ GCB_DEV void slow_histogram(const TileCtx &t, const FsTile &ft, int col, int e, 
 }
 
 // group.cpp:419-525 for one slow column once its top and second bins are known.  Thread-local.
-GCB_DEV void slow_finish(const TileCtx &t, int f, int col, ColumnTop &top, int total, const int32_t *bins) {
+// `acgt_maxq`: the best quality of codes 1, 2, 4, 8 in bytes 0..3 (0 when nobody showed the code).
+GCB_DEV void slow_finish(const TileCtx &t, int f, int col, ColumnTop &top, int total, uint32_t acgt_maxq) {
     const gcb_options &o = *t.o;
     const FsTile ft = t.ft[f];
     const int side = fs_side(ft);
@@ -287,7 +288,7 @@ GCB_DEV void slow_finish(const TileCtx &t, int f, int col, ColumnTop &top, int t
         int rbq = 0;
         bool any_high = false;
         if (top.need_ref && ref4 != 0) {
-            const int rmax = bins[4 * ref4] > 0 ? bins[4 * ref4 + 3] : 0;
+            const int rmax = (int)((acgt_maxq >> (ref4 == 1 ? 0 : ref4 == 2 ? 8 : ref4 == 4 ? 16 : 24)) & 0xFFu);
             if (rmax >= 128) {  // `char refBaseQual` wraps: the scan order matters (group.cpp:474-490): template first
                 int tb, tq, ts;
                 if (fetch_ent(cb, tv, col, side, o, tb, tq, ts) && tb == ref4) {
@@ -347,7 +348,9 @@ GCB_DEV void slow_decide(const TileCtx &t, int f, int col, const int32_t *bins) 
         }
     }
     ColumnTop top = column_top(*t.o, obs, nobs, total);
-    slow_finish(t, f, col, top, total, bins);
+    const uint32_t acgt = (uint32_t)(bins[4 * 1] > 0 ? bins[4 * 1 + 3] : 0) | ((uint32_t)(bins[4 * 2] > 0 ? bins[4 * 2 + 3] : 0) << 8) |
+                          ((uint32_t)(bins[4 * 4] > 0 ? bins[4 * 4 + 3] : 0) << 16) | ((uint32_t)(bins[4 * 8] > 0 ? bins[4 * 8 + 3] : 0) << 24);
+    slow_finish(t, f, col, top, total, acgt);
 }
 
 // The (score, quality sum, code) order of group.cpp:395-417 as one integer: the scans walk the sixteen bins,
@@ -395,7 +398,9 @@ GCB_DEV void slow_octet(const TileCtx &t, bool active, int f, int col, int32_t *
     ColumnTop ct;
     ct.top.base = tb; ct.top.cnt = T.x; ct.top.score = T.y; ct.top.qual = T.z; ct.top.maxq = T.w;
     ct.sec.base = sb; ct.sec.cnt = S.x; ct.sec.score = S.y; ct.sec.qual = S.z; ct.sec.maxq = S.w;
-    slow_finish(t, f, col, ct, total, bins);
+    const uint32_t acgt = (uint32_t)(b4[1].x > 0 ? b4[1].w : 0) | ((uint32_t)(b4[2].x > 0 ? b4[2].w : 0) << 8) |
+                          ((uint32_t)(b4[4].x > 0 ? b4[4].w : 0) << 16) | ((uint32_t)(b4[8].x > 0 ? b4[8].w : 0) << 24);
+    slow_finish(t, f, col, ct, total, acgt);
 }
 
 // a slow column decided by its owner alone (queue overflow): the histogram lives in local memory

@@ -203,6 +203,11 @@ int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, in
  * chunks are whole clusters).  Results do not depend on it. */
 int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes);
 
+/* Which kernel runs GCB_STAGE_SCORE_VOTE: 0 = one CTA per tile (vote_tiled_kernel), 1 = the persistent pipelined
+ * kernel (vote_pipe_kernel, falls back to 0 for batches whose clusters are too large for its ring).  Results are
+ * identical. */
+int gcb_set_vote_mode(gcb_ctx *ctx, int mode);
+
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t gcb_launch_count(const gcb_ctx *ctx);
 

@@ -355,6 +355,7 @@ inline T atomicXor(T *p, T v) { T old = *p; *p = old ^ v; return old; }
 template <typename T>
 inline T atomicCAS(T *p, T cmp, T v) { T old = *p; if (old == cmp) *p = v; return old; }
 inline void __threadfence() {}
+inline void __threadfence_block() {}
 
 // ---- the slice of the CUDA runtime the host side uses -----------------------------------------------
 typedef int cudaError_t;

@@ -51,6 +51,20 @@ def test_cuda_matches_oracle_device_buffers(engine_cls, oracle, name):
             assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 
 
+@pytest.mark.parametrize("name,thunk", CASES, ids=[c[0] for c in CASES])
+def test_pipelined_vote_matches_oracle(engine_cls, oracle, name, thunk):
+    """The persistent pipelined vote kernel (gcb_set_vote_mode 1) on every case."""
+    batch, genome, opt = thunk()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        eng.set_vote_mode(1)
+        res = eng.cluster_by_umi(batch)
+        res2 = eng.cluster_by_umi(batch)
+    expect = oracle.consensus(batch, genome, opt)
+    assert_results_equal(batch, res, expect, name)
+    assert_results_equal(batch, res2, expect, name + " (second run)")
+
+
 @pytest.mark.parametrize("name", ["cfg3_40k", "ragged_duplex_5_big", "deep_1100", "cfg4_40k"])
 @pytest.mark.parametrize("chunk", [1 << 14, 1 << 18, 1 << 21])
 def test_pipeline_chunks_do_not_change_results(engine_cls, oracle, name, chunk):

@@ -63,3 +63,26 @@ def test_pipeline_chunks_do_not_change_results(simt_lib, oracle, name, chunk):
         eng.set_chunk_bytes(chunk)
         res = eng.cluster_by_umi(batch)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} chunk {chunk}")
+
+
+PIPE_CASES = [c for c in CASES if c[0] in ("golden_cfg1_600", "golden_cfg2_600", "golden_cfg3_600", "golden_cfg4_600", "golden_ragged_duplex",
+                                          "edge_default", "edge_strict", "ragged_none_0", "ragged_single_1", "ragged_duplex_2", "ragged_duplex_3",
+                                          "deep_1100", "low_complexity", "no_reference", "empty", "tiny_reads", "cfg2_1500", "cfg3_1500",
+                                          "cfg4_1500", "wide_umi_3")]
+
+
+@pytest.mark.parametrize("name,thunk", PIPE_CASES, ids=[c[0] for c in PIPE_CASES])
+def test_pipelined_vote_matches_oracle_under_simt_check(simt_lib, oracle, name, thunk):
+    """vote_pipe_kernel (persistent CTA, ring of staged tiles, producer thread + consumer warps) gives the same bytes."""
+    from gencore_b200.engine import ConsensusEngine
+    batch, genome, opt = thunk()
+    cnt = (ctypes.c_int64 * 6)()
+    with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
+        eng.set_reference(genome)
+        eng.set_vote_mode(1)
+        eng.lib.gcb_simt_counters(cnt, 1)
+        res = eng.cluster_by_umi(batch)
+        eng.lib.gcb_simt_counters(cnt, 1)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
+    if name.startswith(("cfg2", "cfg3", "golden_cfg")):
+        assert cnt[0] > 0, "tiles must take the pipeline"
