@@ -278,10 +278,13 @@ __global__ void __launch_bounds__(VP_THREADS, 1) vote_pipe_kernel(BatchView b, R
     // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...
     const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (my_tiles == 0) return;
+    // consumer warps are split into one group per stage: group g votes the tiles that land in stage g (k = g, g + NB, ...),
+    // so a tile is visited by exactly the warps that can find work in it and the groups run out of phase with each other
+    const int wpg = (VP_WARPS - 1) / n_stages;
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
             pipe_init(full + s, 1);
-            pipe_init(empty + s, VP_WARPS - 1);  // every consumer warp arrives once when it leaves the stage's tile
+            pipe_init(empty + s, wpg);  // every warp of the stage's group arrives once when it leaves the stage's tile
         }
         pipe_fence_init();
     }
@@ -290,12 +293,21 @@ __global__ void __launch_bounds__(VP_THREADS, 1) vote_pipe_kernel(BatchView b, R
     if (warp == 0) {
         // ---- producer: one thread, up to n_stages tiles ahead of the consumers
         if (lane != 0) return;
+        // (the directory entries and the header of tile k+1 are fetched while tile k waits for its stage)
+        int tile_n = pipe_tiles[blockIdx.x];
+        TileDir t0_n = ws.tile_dir[tile_n], t1_n = ws.tile_dir[tile_n + 1];
+        TileHdr h_n = hdr[tile_n];
         for (int k = 0; k < my_tiles; k++) {
             const int s = k % n_stages, use = k / n_stages;
-            if (use > 0) pipe_wait(empty + s, (uint32_t)((use - 1) & 1));  // every consumer has left the stage's previous tile
-            const int tile = pipe_tiles[(int64_t)blockIdx.x + (int64_t)k * gridDim.x];
-            const TileDir t0 = ws.tile_dir[tile], t1 = ws.tile_dir[tile + 1];
-            const TileHdr h = hdr[tile];
+            const TileDir t0 = t0_n, t1 = t1_n;
+            const TileHdr h = h_n;
+            if (k + 1 < my_tiles) {
+                tile_n = pipe_tiles[(int64_t)blockIdx.x + (int64_t)(k + 1) * gridDim.x];
+                t0_n = ws.tile_dir[tile_n];
+                t1_n = ws.tile_dir[tile_n + 1];
+                h_n = hdr[tile_n];
+            }
+            if (use > 0) pipe_wait(empty + s, (uint32_t)((use - 1) & 1));  // the stage's group has left its previous tile
             const int P0 = t0.p0, NP = t1.p0 - t0.p0;
             const uint32_t slab_bytes = (uint32_t)(t1.slab0 - t0.slab0), vr_bytes = 32u * (uint32_t)NP, ft_bytes = 32u * (uint32_t)h.nfs;
             uint8_t *stage = smem + VP_OFF_STAGE0 + (size_t)s * stage_bytes;
@@ -328,8 +340,10 @@ __global__ void __launch_bounds__(VP_THREADS, 1) vote_pipe_kernel(BatchView b, R
     // ---- consumers
     const uint32_t mod4 = 0x01010101u * (uint32_t)(o.moderate_quality & 0xFF);
     const uint32_t sbase = smem_base(smem);
-    for (int k = 0; k < my_tiles; k++) {
-        const int s = k % n_stages, use = k / n_stages;
+    const int group = (warp - 1) / wpg;
+    if (group >= n_stages) return;  // (warps that do not fill a group)
+    for (int k = group; k < my_tiles; k += n_stages) {
+        const int s = group, use = k / n_stages;
         pipe_wait(full + s, (uint32_t)(use & 1));
         const int stage_off = VP_OFF_STAGE0 + s * stage_bytes;
         uint8_t *stage = smem + stage_off;
