@@ -41,5 +41,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+CLI_SRC = os.path.join(CSRC, "host", "gencore_b200_cli.cpp")
+CLI_BIN = os.path.join(HERE, "bin", "gencore_b200")
+
+
+def build_cli(force: bool = False) -> str:
+    """The host pipeline (sorted BAM in, consensus BAM out) that drives the engine through its C ABI."""
+    deps = [CLI_SRC, os.path.join(ROOT, "include", "gencore_b200.h")]
+    if not force and os.path.exists(CLI_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(CLI_BIN) for d in deps):
+        return CLI_BIN
+    os.makedirs(os.path.dirname(CLI_BIN), exist_ok=True)
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", CLI_BIN, CLI_SRC, "-lz", "-ldl"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + proc.stdout + proc.stderr)
+    return CLI_BIN
+
+
 if __name__ == "__main__":
+    print(build_cli(force=True))
     print(build(force=True, verbose="--verbose" in sys.argv))

@@ -1,0 +1,84 @@
+"""Sorted BAM in, consensus BAM out: gencore_b200/bin/gencore_b200 (the host pipeline around the C ABI) against the
+UNMODIFIED reference binary (oracle/_ref/gencore) on the same synthetic BAM + FASTA — the comparison BASELINE.json's
+metric names ("output BAM bit-exact vs reference").  On the CPU box the engine behind the ABI is the SIMT-check build of
+the kernel source (test infrastructure); the `gpu` test loads the CUDA library."""
+import dataclasses
+import os
+import subprocess
+import sys
+
+import pytest
+
+import bamfile
+from gencore_b200 import build as gbuild
+from gencore_b200 import synth
+from oracle import pyoracle
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt_check"))
+
+CONFIGS = [
+    ("cfg1", 3000, []),                 # no UMI, -s 1
+    ("cfg2", 6000, []),                 # 8-nt UMI, -d 1, crosses the 10 000-read tick (Q18: -d for flushed clusters, 0 at the end)
+    ("cfg3", 7000, []),                 # duplex UMIs
+    ("cfg3", 2500, ["-s", "2", "-D", "1"]),
+    ("cfg2", 2500, ["--no_duplex", "-d", "0"]),
+    ("cfg4", 3000, ["-s", "2", "-x"]),
+]
+
+
+def _make_inputs(tmp_path, name, n_pairs):
+    cfg = synth.CONFIGS[name]
+    small = dataclasses.replace(cfg, contig_len=120_000, n_contigs=min(cfg.n_contigs, 2))
+    batch, genome, contigs = synth.make_fixed_batch(small, seed=20261017 + n_pairs, n_pairs=n_pairs, with_qnames=True)
+    fa, bam = str(tmp_path / "ref.fa"), str(tmp_path / "in.bam")
+    bamfile.genome_to_fasta(fa, contigs, genome.names)
+    n = bamfile.batch_to_bam(bam, batch, genome)
+    return fa, bam, n
+
+
+def _make_ragged_inputs(tmp_path, seed, umi):
+    """Reads of 100-250 bases with soft clips and indels, pairs without a mate (written mate-unmapped: the pass-through
+    of gencore.cpp:307-309), plus unmapped and secondary records the reference drops (Q19)."""
+    batch, genome, contigs = synth.make_ragged_batch(seed, n_clusters=500, umi=umi)
+    fa, bam = str(tmp_path / "ref.fa"), str(tmp_path / "in.bam")
+    bamfile.genome_to_fasta(fa, contigs, genome.names)
+    n = bamfile.batch_to_bam(bam, batch, genome, extras=True)
+    return fa, bam, n
+
+
+def _run_both(tmp_path, fa, bam, flags, engine_lib):
+    if not pyoracle.reference_available():
+        pytest.skip("oracle/_ref/gencore is not built")
+    ref_out, my_out = str(tmp_path / "ref.bam"), str(tmp_path / "b200.bam")
+    r = subprocess.run([pyoracle.REF_BIN, "-i", bam, "-o", ref_out, "-r", fa, "-j", str(tmp_path / "r.json"), "-h", str(tmp_path / "r.html")] + flags,
+                       capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    cli = gbuild.build_cli()
+    m = subprocess.run([cli, "-i", bam, "-o", my_out, "-r", fa, "--engine", engine_lib] + flags, capture_output=True, text=True, cwd=str(tmp_path))
+    assert m.returncode == 0, m.stderr[-2000:]
+    return bamfile.assert_same_bam(ref_out, my_out)
+
+
+@pytest.mark.parametrize("name,n_pairs,flags", CONFIGS, ids=[f"{c[0]}_{c[1]}_{'_'.join(c[2]) or 'default'}" for c in CONFIGS])
+def test_bam_pipeline_matches_reference_binary_simt(tmp_path, name, n_pairs, flags):
+    import build as simt_build
+    fa, bam, n_in = _make_inputs(tmp_path, name, n_pairs)
+    n_out = _run_both(tmp_path, fa, bam, flags, simt_build.build())
+    assert 0 < n_out < n_in
+
+
+@pytest.mark.parametrize("seed,umi,flags", [(11, "none", []), (12, "single", []), (13, "duplex", []), (14, "duplex", ["-s", "2", "-c", "8"]),
+                                            (15, "single", ["-u", "UMI", "--high_qual", "35", "--low_qual", "10"])])
+def test_bam_pipeline_ragged_matches_reference_binary_simt(tmp_path, seed, umi, flags):
+    import build as simt_build
+    fa, bam, n_in = _make_ragged_inputs(tmp_path, seed, umi)
+    n_out = _run_both(tmp_path, fa, bam, flags, simt_build.build())
+    assert 0 < n_out < n_in
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n_pairs,flags", [("cfg2", 60_000, []), ("cfg3", 40_000, []), ("cfg1", 20_000, ["-s", "2"])])
+def test_bam_pipeline_matches_reference_binary_cuda(tmp_path, name, n_pairs, flags):
+    fa, bam, n_in = _make_inputs(tmp_path, name, n_pairs)
+    n_out = _run_both(tmp_path, fa, bam, flags, gbuild.build())
+    assert 0 < n_out < n_in
