@@ -51,7 +51,7 @@ def build_cli(force: bool = False) -> str:
     if not force and os.path.exists(CLI_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(CLI_BIN) for d in deps):
         return CLI_BIN
     os.makedirs(os.path.dirname(CLI_BIN), exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", CLI_BIN, CLI_SRC, "-lz", "-ldl"]
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", CLI_BIN, CLI_SRC, "-lz", "-ldl", "-lpthread"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("g++ failed:\n" + proc.stdout + proc.stderr)

@@ -14,7 +14,12 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <future>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <set>
 #include <string>
 #include <vector>
@@ -29,20 +34,116 @@ namespace {
 }
 
 // ---------------------------------------------------------------------------------------------- BGZF
+// Both directions are block-parallel (the codec, not the GPU, bounds the whole tool): a pool of
+// worker threads inflates / deflates 64 KiB blocks, the blocks are consumed / written in file order.
 const size_t BGZF_PAYLOAD = 0xff00;
+const int CODEC_SLOTS = 128;
+
+struct CodecTask {
+    std::vector<uint8_t> in, out;
+    uint32_t isize = 0;
+    bool ready = false;  // `out` is complete
+};
+
+struct WorkerPool {
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<std::pair<CodecTask *, bool>> work;  // (task, inflate?)
+    bool stop = false;
+    explicit WorkerPool(int n) {
+        for (int i = 0; i < n; i++) threads.emplace_back([this] { loop(); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto &t : threads) t.join();
+    }
+    static void inflate_block(CodecTask *t) {
+        t->out.resize(t->isize);
+        if (!t->isize) return;
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) die("zlib");
+        zs.next_in = t->in.data();
+        zs.avail_in = (uInt)t->in.size();
+        zs.next_out = t->out.data();
+        zs.avail_out = t->isize;
+        const int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        if (rc != Z_STREAM_END) die("corrupt BGZF block");
+    }
+    static void deflate_block(CodecTask *t) {
+        const size_t n = t->in.size();
+        t->out.resize(18 + n + 1024 + 8);
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("zlib");
+        zs.next_in = t->in.data();
+        zs.avail_in = (uInt)n;
+        zs.next_out = t->out.data() + 18;
+        zs.avail_out = (uInt)(t->out.size() - 26);
+        const int rc = deflate(&zs, Z_FINISH);
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        if (rc != Z_STREAM_END) die("deflate failed");
+        const size_t total = 18 + clen + 8;
+        const uint8_t hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (uint8_t)((total - 1) & 0xff), (uint8_t)((total - 1) >> 8)};
+        memcpy(t->out.data(), hdr, 18);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), t->in.data(), (uInt)n);
+        const uint8_t tail[8] = {(uint8_t)crc, (uint8_t)(crc >> 8), (uint8_t)(crc >> 16), (uint8_t)(crc >> 24),
+                                 (uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+        memcpy(t->out.data() + 18 + clen, tail, 8);
+        t->out.resize(total);
+    }
+    void loop() {
+        for (;;) {
+            std::pair<CodecTask *, bool> job;
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cv_work.wait(l, [this] { return stop || !work.empty(); });
+                if (work.empty()) return;
+                job = work.front();
+                work.pop_front();
+            }
+            if (job.second) inflate_block(job.first);
+            else deflate_block(job.first);
+            {
+                std::lock_guard<std::mutex> l(mu);
+                job.first->ready = true;
+            }
+            cv_done.notify_all();
+        }
+    }
+    void submit(CodecTask *t, bool inflate) {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            t->ready = false;
+            work.emplace_back(t, inflate);
+        }
+        cv_work.notify_one();
+    }
+    void wait(CodecTask *t) {
+        std::unique_lock<std::mutex> l(mu);
+        cv_done.wait(l, [t] { return t->ready; });
+    }
+};
 
 struct BgzfReader {
     FILE *fp = nullptr;
+    WorkerPool *pool = nullptr;
+    std::vector<CodecTask> slots = std::vector<CodecTask>(CODEC_SLOTS);
+    size_t head = 0, tail = 0;  // blocks [head, tail) are in flight; slot = index % CODEC_SLOTS
+    bool file_eof = false;
     std::vector<uint8_t> buf;
     size_t pos = 0;
-    bool eof = false;
-    bool next_block() {
+    bool read_raw_block(CodecTask &t) {  // the compressed bytes of the next block
         uint8_t hdr[12];
         const size_t got = fread(hdr, 1, 12, fp);
-        if (got == 0) {
-            eof = true;
-            return false;
-        }
+        if (got == 0) return false;
         if (got != 12 || hdr[0] != 0x1f || hdr[1] != 0x8b || hdr[2] != 8 || !(hdr[3] & 4)) die("input is not BGZF");
         const unsigned xlen = hdr[10] | (hdr[11] << 8);
         std::vector<uint8_t> extra(xlen);
@@ -55,24 +156,31 @@ struct BgzfReader {
         }
         const long clen = (long)bsize + 1 - 12 - (long)xlen - 8;
         if (bsize < 0 || clen < 0) die("bad BGZF block header");
-        std::vector<uint8_t> comp((size_t)clen);
-        uint8_t tail[8];
-        if ((clen && fread(comp.data(), 1, (size_t)clen, fp) != (size_t)clen) || fread(tail, 1, 8, fp) != 8) die("truncated BGZF block");
-        const uint32_t isize = tail[4] | (tail[5] << 8) | (tail[6] << 16) | ((uint32_t)tail[7] << 24);
-        buf.resize(isize);
-        pos = 0;
-        if (isize) {
-            z_stream zs;
-            memset(&zs, 0, sizeof zs);
-            if (inflateInit2(&zs, -15) != Z_OK) die("zlib");
-            zs.next_in = comp.data();
-            zs.avail_in = (uInt)clen;
-            zs.next_out = buf.data();
-            zs.avail_out = isize;
-            const int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END) die("corrupt BGZF block");
+        t.in.resize((size_t)clen);
+        uint8_t tail8[8];
+        if ((clen && fread(t.in.data(), 1, (size_t)clen, fp) != (size_t)clen) || fread(tail8, 1, 8, fp) != 8) die("truncated BGZF block");
+        t.isize = tail8[4] | (tail8[5] << 8) | (tail8[6] << 16) | ((uint32_t)tail8[7] << 24);
+        return true;
+    }
+    void fill() {  // keep the pool busy
+        while (!file_eof && tail - head < (size_t)CODEC_SLOTS) {
+            CodecTask &t = slots[tail % CODEC_SLOTS];
+            if (!read_raw_block(t)) {
+                file_eof = true;
+                break;
+            }
+            pool->submit(&t, true);
+            tail++;
         }
+    }
+    bool next_block() {
+        fill();
+        if (head == tail) return false;
+        CodecTask &t = slots[head % CODEC_SLOTS];
+        pool->wait(&t);
+        buf.swap(t.out);
+        pos = 0;
+        head++;
         return true;
     }
     size_t read(void *dst, size_t n) {
@@ -80,7 +188,7 @@ struct BgzfReader {
         size_t done = 0;
         while (done < n) {
             if (pos == buf.size()) {
-                if (eof || !next_block()) break;
+                if (!next_block()) break;
                 continue;
             }
             const size_t take = std::min(buf.size() - pos, n - done);
@@ -94,32 +202,30 @@ struct BgzfReader {
 
 struct BgzfWriter {
     FILE *fp = nullptr;
+    WorkerPool *pool = nullptr;
+    std::vector<CodecTask> slots = std::vector<CodecTask>(CODEC_SLOTS);
+    size_t head = 0, tail = 0;
     std::vector<uint8_t> pending;
-    void block(const uint8_t *src, size_t n) {
-        uint8_t comp[70000];
-        z_stream zs;
-        memset(&zs, 0, sizeof zs);
-        if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("zlib");
-        zs.next_in = (Bytef *)src;
-        zs.avail_in = (uInt)n;
-        zs.next_out = comp;
-        zs.avail_out = sizeof comp;
-        const int rc = deflate(&zs, Z_FINISH);
-        const size_t clen = zs.total_out;
-        deflateEnd(&zs);
-        if (rc != Z_STREAM_END) die("deflate failed");
-        const size_t total = 18 + clen + 8;
-        const uint8_t hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, (uint8_t)((total - 1) & 0xff), (uint8_t)((total - 1) >> 8)};
-        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, (uInt)n);
-        const uint8_t tail[8] = {(uint8_t)crc, (uint8_t)(crc >> 8), (uint8_t)(crc >> 16), (uint8_t)(crc >> 24),
-                                 (uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
-        if (fwrite(hdr, 1, 18, fp) != 18 || (clen && fwrite(comp, 1, clen, fp) != clen) || fwrite(tail, 1, 8, fp) != 8) die("Writing failed, exiting ...");
+    void drain(size_t keep) {  // write finished blocks in order until at most `keep` are in flight
+        while (tail - head > keep) {
+            CodecTask &t = slots[head % CODEC_SLOTS];
+            pool->wait(&t);
+            if (fwrite(t.out.data(), 1, t.out.size(), fp) != t.out.size()) die("Writing failed, exiting ...");
+            head++;
+        }
+    }
+    void emit(const uint8_t *src, size_t n) {
+        drain(CODEC_SLOTS - 1);
+        CodecTask &t = slots[tail % CODEC_SLOTS];
+        t.in.assign(src, src + n);
+        pool->submit(&t, false);
+        tail++;
     }
     void flush(bool all) {
         size_t off = 0;
         while (pending.size() - off >= BGZF_PAYLOAD || (all && off < pending.size())) {
             const size_t n = std::min(pending.size() - off, BGZF_PAYLOAD);
-            block(pending.data() + off, n);
+            emit(pending.data() + off, n);
             off += n;
         }
         pending.erase(pending.begin(), pending.begin() + (long)off);
@@ -127,10 +233,11 @@ struct BgzfWriter {
     void write(const void *src, size_t n) {
         const uint8_t *p = (const uint8_t *)src;
         pending.insert(pending.end(), p, p + n);
-        if (pending.size() >= BGZF_PAYLOAD) flush(false);
+        if (pending.size() >= 16 * BGZF_PAYLOAD) flush(false);
     }
     void close() {
         flush(true);
+        drain(0);
         static const uint8_t eof_block[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         fwrite(eof_block, 1, 28, fp);
         fclose(fp);
@@ -441,6 +548,7 @@ struct Pipeline {
     uint64_t serial = 0;
     long tick = 0;
     std::string prefix;
+    std::future<void> engine_ready;
 
     // ---- output side (gencore.cpp:83-160)
     void write_bam(Rec *r) { write_record(out, *r); }
@@ -585,6 +693,13 @@ struct Pipeline {
 };
 
 void Pipeline::run_and_replay() {
+    if (engine_ready.valid()) {
+        engine_ready.get();
+        for (const std::string &n : hdr.names) {
+            auto it = genome.index.find(n);
+            tid_to_contig.push_back(it == genome.index.end() ? -1 : it->second);
+        }
+    }
     // 1. pack (gencore_b200.h "Encoding conventions")
     std::vector<int32_t> cpo = {0}, cref;
     std::vector<uint8_t> cflags;
@@ -776,23 +891,27 @@ void Pipeline::run_and_replay() {
 }
 
 void Pipeline::run() {
-    eng.open(cli.engine);
-    eng.check(eng.create(&cli.opt, cli.device, &eng.ctx), "gcb_create");
-    genome = load_fasta(cli.ref);
-    if (!genome.len.empty())
-        eng.check(eng.set_reference(eng.ctx, genome.packed.data(), (int64_t)genome.packed.size(), genome.off.data(), genome.len.data(), (int32_t)genome.len.size()),
-                  "gcb_set_reference");
+    // the engine (library load, CUDA context, reference upload) starts while the first reads are parsed
+    engine_ready = std::async(std::launch::async, [this] {
+        eng.open(cli.engine);
+        eng.check(eng.create(&cli.opt, cli.device, &eng.ctx), "gcb_create");
+        genome = load_fasta(cli.ref);
+        if (!genome.len.empty())
+            eng.check(eng.set_reference(eng.ctx, genome.packed.data(), (int64_t)genome.packed.size(), genome.off.data(), genome.len.data(),
+                                        (int32_t)genome.len.size()),
+                      "gcb_set_reference");
+    });
+    unsigned hw = std::thread::hardware_concurrency();
+    WorkerPool pool((int)std::max(2u, std::min(hw ? hw - 1 : 4u, 16u)));
     BgzfReader in;
+    in.pool = &pool;
+    out.pool = &pool;
     in.fp = cli.input == "-" ? stdin : fopen(cli.input.c_str(), "rb");
     if (!in.fp) die("failed to open " + cli.input);
     out.fp = cli.output == "-" ? stdout : fopen(cli.output.c_str(), "wb");
     if (!out.fp) die("failed to open output " + cli.output);
     hdr = read_header(in);
     if (hdr.names.empty()) die("this SAM file has no header");
-    for (const std::string &n : hdr.names) {
-        auto it = genome.index.find(n);
-        tid_to_contig.push_back(it == genome.index.end() ? -1 : it->second);
-    }
     write_header(out, hdr);
     prefix = cli.umi_prefix;
     bool first = true;

@@ -1,0 +1,32 @@
+"""BAM-to-BAM wall time of the host pipeline (gencore_b200/bin/gencore_b200 + libgencore_b200.so on cuda:0) next to the
+unmodified reference binary (oracle/_ref/gencore, one core) on the same synthetic cfg2-shaped BAM; checks the outputs
+match.  Not the bench.py metric (that is the hot path behind the C ABI): this is the whole tool, BGZF included."""
+import dataclasses, json, os, subprocess, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bamfile
+from gencore_b200 import build as gbuild, synth
+from oracle import pyoracle
+
+n_pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 300_000
+cfg = dataclasses.replace(synth.CONFIGS["cfg2"], contig_len=20_000_000)
+with tempfile.TemporaryDirectory() as td:
+    batch, genome, contigs = synth.make_fixed_batch(cfg, seed=20261019, n_pairs=n_pairs, with_qnames=True)
+    fa, bam = os.path.join(td, "ref.fa"), os.path.join(td, "in.bam")
+    bamfile.genome_to_fasta(fa, contigs, genome.names)
+    n_rec = bamfile.batch_to_bam(bam, batch, genome)
+    res = {}
+    for tag, cmd in (("reference", [pyoracle.REF_BIN, "-i", bam, "-o", os.path.join(td, "ref.bam"), "-r", fa, "-j", os.path.join(td, "r.json"), "-h", os.path.join(td, "r.html")]),
+                     ("b200", [gbuild.build_cli(), "-i", bam, "-o", os.path.join(td, "b200.bam"), "-r", fa])):
+        best = None
+        for rep in range(2):
+            t = time.perf_counter()
+            p = subprocess.run(cmd, capture_output=True, text=True, cwd=td)
+            dt = time.perf_counter() - t
+            assert p.returncode == 0, p.stderr[-1500:]
+            best = dt if best is None else min(best, dt)
+        res[tag] = best
+    n_out = bamfile.assert_same_bam(os.path.join(td, "ref.bam"), os.path.join(td, "b200.bam"))
+    print(json.dumps({"what": "BAM-to-BAM wall time, cfg2 shape", "pairs": n_pairs, "records_in": n_rec, "records_out": n_out, "identical_output": True,
+                      "reference_s": res["reference"], "b200_s": res["b200"], "reference_pairs_per_s": n_pairs / res["reference"],
+                      "b200_pairs_per_s": n_pairs / res["b200"], "bam_bytes": os.path.getsize(bam)}))
