@@ -14,6 +14,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <future>
@@ -27,6 +28,17 @@
 #include "gencore_b200.h"
 
 namespace {
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+const bool g_timing = getenv("GCB_TIMING") != nullptr;  // per-phase wall times on stderr
+void lap(const char *what, double &t0) {
+    if (!g_timing) return;
+    const double t = now_s();
+    fprintf(stderr, "[timing] %-28s %8.3f s\n", what, t - t0);
+    t0 = t;
+}
 
 [[noreturn]] void die(const std::string &msg) {  // util.h:250-253 error_exit
     fprintf(stderr, "ERROR: %s\n", msg.c_str());
@@ -693,8 +705,10 @@ struct Pipeline {
 };
 
 void Pipeline::run_and_replay() {
+    double t0 = now_s();
     if (engine_ready.valid()) {
         engine_ready.get();
+        lap("wait for engine start-up", t0);
         for (const std::string &n : hdr.names) {
             auto it = genome.index.find(n);
             tid_to_contig.push_back(it == genome.index.end() ? -1 : it->second);
@@ -749,6 +763,7 @@ void Pipeline::run_and_replay() {
         }
     }
     payload.resize((payload.size() + 15) & ~(size_t)15, 0);
+    lap("pack batch", t0);
     const int32_t n_pairs = (int32_t)(reads.size() / 2), n_clusters = (int32_t)cref.size();
     std::vector<int32_t> pair_group((size_t)n_pairs + 1), n_groups((size_t)n_clusters + 1);
     std::vector<gcb_group_result> groups((size_t)n_pairs + 1);
@@ -769,6 +784,7 @@ void Pipeline::run_and_replay() {
             if (umi_words == GCB_MAX_UMI_WORDS) die("UMI longer than 64 characters");
             umi_words = GCB_MAX_UMI_WORDS;
         }
+        lap("gcb_extract_umi", t0);
         umi.assign((size_t)n_pairs * umi_words, 0);
         for (int32_t p = 0; p < n_pairs; p++) {
             const uint64_t *l = &read_umi[(size_t)(2 * p) * umi_words], *r = l + umi_words;
@@ -811,6 +827,7 @@ void Pipeline::run_and_replay() {
         res.out_capacity = (int64_t)out_payload.size();
         res.out_bytes = &out_bytes;
         eng.check(eng.consensus_batch(eng.ctx, &b, &res), "gcb_consensus_batch");
+        lap("gcb_consensus_batch", t0);
     }
     // 4. replay: what the loops around clusterByUMI do with the returned pairs (gencore.cpp:355-360, 409-414)
     int32_t c = 0;
@@ -888,11 +905,13 @@ void Pipeline::run_and_replay() {
         if (slot_rec[s] && !consumed[s]) delete slot_rec[s];
     log.clear();
     pending_pairs = 0;
+    lap("replay + write", t0);
 }
 
 void Pipeline::run() {
     // the engine (library load, CUDA context, reference upload) starts while the first reads are parsed
     engine_ready = std::async(std::launch::async, [this] {
+        double t0 = now_s();
         eng.open(cli.engine);
         eng.check(eng.create(&cli.opt, cli.device, &eng.ctx), "gcb_create");
         genome = load_fasta(cli.ref);
@@ -900,6 +919,7 @@ void Pipeline::run() {
             eng.check(eng.set_reference(eng.ctx, genome.packed.data(), (int64_t)genome.packed.size(), genome.off.data(), genome.len.data(),
                                         (int32_t)genome.len.size()),
                       "gcb_set_reference");
+        lap("engine start-up (async)", t0);
     });
     unsigned hw = std::thread::hardware_concurrency();
     WorkerPool pool((int)std::max(2u, std::min(hw ? hw - 1 : 4u, 16u)));
@@ -916,6 +936,7 @@ void Pipeline::run() {
     prefix = cli.umi_prefix;
     bool first = true;
     int last_tid = -1, last_pos = -1;
+    double t_read = now_s();
     Rec *b = new Rec();
     while (read_record(in, *b)) {
         if (first) {  // gencore.cpp:207-221
@@ -944,8 +965,13 @@ void Pipeline::run() {
         b->serial = serial++;
         add_to_proper_cluster(b);
         b = new Rec();
-        if (pending_pairs >= 200000) run_and_replay();
+        if (pending_pairs >= 200000) {
+            lap("read + key", t_read);
+            run_and_replay();
+            t_read = now_s();
+        }
     }
+    lap("read + key", t_read);
     delete b;
     if (!clusters_finished) {
         clusters_finished = true;
@@ -955,7 +981,9 @@ void Pipeline::run() {
     e.kind = Event::CLEAR_OUTSET;
     log.push_back(std::move(e));
     run_and_replay();
+    double t_close = now_s();
     out.close();
+    lap("flush output", t_close);
     if (in.fp != stdin) fclose(in.fp);
     eng.destroy(eng.ctx);
 }
