@@ -178,7 +178,8 @@ def b200_arm(args):
     import torch
     import torch.distributed as dist
     from gencore_b200 import synth
-    from gencore_b200.abi import (STAGE_DUPLEX, STAGE_SCORE_VOTE, STAGE_SELECT_TEMPLATE, STAGE_UMI_GROUP, Genome, Options)
+    from gencore_b200.abi import (STAGE_DUPLEX, STAGE_SCORE_VOTE, STAGE_SELECT_TEMPLATE, STAGE_UMI_GROUP, STAGE_VOTE_ONLY,
+                                  STAGE_VOTE_PREP_ONLY, Genome, Options)
     from gencore_b200.device import DeviceBatch, DeviceResult, pinned_copy, pinned_result
     from gencore_b200.engine import ConsensusEngine
 
@@ -206,6 +207,7 @@ def b200_arm(args):
     opt = Options.default()
     eng = ConsensusEngine(opt, local)
     eng.set_vote_mode(args.vote_mode)
+    eng.set_vote_threads(args.vote_threads)
     # the packed reference reaches every GPU by ONE NCCL broadcast from rank 0
     g_dev = torch.from_numpy(genome.packed4).to(dev) if rank == 0 else torch.empty(len(genome.packed4), dtype=torch.uint8, device=dev)
     if world > 1:
@@ -219,8 +221,15 @@ def b200_arm(args):
     stream = tstream.cuda_stream
     assert stream != 0
     torch.cuda.synchronize()
-    stages = [STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_SCORE_VOTE, STAGE_DUPLEX]
-    names = ["umi_group", "select_template+scan", "score_vote", "duplex"]
+    # vote modes 1 and 2 prepare per-tile headers once per batch (tile_prep kernels): timed as its own stage
+    if args.vote_mode == 0:
+        stages = [STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_SCORE_VOTE, STAGE_DUPLEX]
+        names = ["umi_group", "select_template+scan", "score_vote", "duplex"]
+    else:
+        stages = [STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_VOTE_PREP_ONLY, STAGE_VOTE_ONLY, STAGE_DUPLEX]
+        names = ["umi_group", "select_template+scan", "tile_prep", "score_vote", "duplex"]
+    i_vote = names.index("score_vote")
+    vote_kernel = {0: "vote_tiled_kernel", 1: "vote_pipe_kernel", 2: "vote_staged_kernel"}[args.vote_mode]
 
     def step(events=None):
         for k, st in enumerate(stages):
@@ -234,6 +243,29 @@ def b200_arm(args):
         step()
     barrier()
     assert eng.batch_status() == 0, "device error flag raised during warm-up"
+    if args.sweep and rank == 0:  # tuning aid: stage times of other (vote mode, threads) settings, to stderr
+        for item in args.sweep.split(","):
+            mode_s, thr_s = item.split(":")
+            eng.set_vote_mode(int(mode_s))
+            eng.set_vote_threads(int(thr_s))
+            sw_stages = [STAGE_SCORE_VOTE] if int(mode_s) == 0 else [STAGE_VOTE_PREP_ONLY, STAGE_VOTE_ONLY]
+            for _ in range(3):
+                for st in sw_stages:
+                    eng.cluster_by_umi_device(db.struct, dr.struct, st, stream)
+            n_sw = 20
+            ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(sw_stages) + 1)] for _ in range(n_sw)]
+            for k in range(n_sw):
+                for q, st in enumerate(sw_stages):
+                    ev[k][q].record(tstream)
+                    eng.cluster_by_umi_device(db.struct, dr.struct, st, stream)
+                ev[k][len(sw_stages)].record(tstream)
+            torch.cuda.synchronize()
+            ms = [float(np.mean([ev[k][q].elapsed_time(ev[k][q + 1]) for k in range(n_sw)])) for q in range(len(sw_stages))]
+            sys.stderr.write("sweep mode=%s threads=%s stage_ms=%s\n" % (mode_s, thr_s, ["%.4f" % x for x in ms]))
+        eng.set_vote_mode(args.vote_mode)
+        eng.set_vote_threads(args.vote_threads)
+        step()
+        barrier()
     res_host = dr.to_host()
     alg = algorithmic_bytes(batch, res_host)
 
@@ -292,7 +324,7 @@ def b200_arm(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        vote_ms = float(stage_ms[2])
+        vote_ms = float(stage_ms[i_vote])
         achieved = alg["total"] / (vote_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -302,10 +334,10 @@ def b200_arm(args):
                        "l2": "inputs larger than L2 (payload %d MB per step)" % (len(batch.payload) >> 20),
                        "stage_ms": {n: float(v) for n, v in zip(names, stage_ms)},
                        "stats": {"clusters": int(stats_vec[0]), "molecules": int(stats_vec[1]), "sscs": int(stats_vec[2]), "dcs": int(stats_vec[3])}},
-            "roofline": {"bound": "hbm", "kernel": "vote_pipe_kernel (+ tile_prep_kernel)" if args.vote_mode == 1 else "vote_tiled_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": vote_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": args.traffic if args.traffic is not None else (measured_traffic() if args.pairs == 1_000_000 else None),
                          "algorithmic_bytes": alg, "kernel_ms": vote_ms,
-                         "timed": "CUDA events around the vote stage on the launching stream (vote_tiled_kernel + the generic kernel's empty launch)"},
+                         "timed": "CUDA events around the vote launches on the launching stream (%s + the generic kernel's empty launch)" % vote_kernel},
             "e2e": {"value": args.pairs * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * e2e_s},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -332,7 +364,10 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=400_000, help="cpu_baseline sample size (one core)")
     ap.add_argument("--cpu-reps", type=int, default=10, help="cpu_baseline repetitions of the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--vote-mode", type=int, default=0, choices=[0, 1], help="0 = one CTA per tile, 1 = persistent pipelined vote kernel")
+    ap.add_argument("--vote-mode", type=int, default=2, choices=[0, 1, 2],
+                    help="0 = one CTA per tile with its own prologue, 1 = persistent pipelined vote kernel, 2 = staged (default)")
+    ap.add_argument("--vote-threads", type=int, default=256, help="threads per CTA of the staged vote kernel")
+    ap.add_argument("--sweep", default="", help="tuning aid: comma-separated mode:threads settings whose vote stage times go to stderr")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per vote launch from an ncu capture (profiles/)")
     args = ap.parse_args()
     if args.impl == "reference":

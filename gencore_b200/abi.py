@@ -23,6 +23,7 @@ CLUSTER_UMI_THR_SHIFT = 4
 GROUP_DROPPED, GROUP_SSCS, GROUP_DCS, GROUP_DUPLEX_PARTNER, GROUP_DUPLEX_DIFF, GROUP_DUPLEX_SMALL = range(6)
 
 STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_SCORE_VOTE, STAGE_DUPLEX, STAGE_ALL = 1, 2, 4, 8, 15
+STAGE_VOTE_PREP_ONLY, STAGE_VOTE_ONLY = 16, 32  # measurement only: the two halves of STAGE_SCORE_VOTE
 
 
 def align4(x):

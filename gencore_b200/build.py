@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libgencore_b200.so")
 SOURCES = ["gencore_b200.cu"]
-HEADERS = ["simt.h", "device_common.cuh", "vote_column.cuh", "k_group_select.cuh", "k_score_vote.cuh", "k_duplex.cuh"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 

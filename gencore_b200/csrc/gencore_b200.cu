@@ -14,11 +14,12 @@
 #include "k_umi_extract.cuh"
 #include "k_vote_tiled.cuh"
 #include "k_vote_pipe.cuh"
+#include "k_vote_staged.cuh"
 
 using namespace gcb;
 
 constexpr int GCB_MAX_CHUNKS = 16;
-constexpr int GCB_VOTE_TILED = 0, GCB_VOTE_PIPELINED = 1;
+constexpr int GCB_VOTE_TILED = 0, GCB_VOTE_PIPELINED = 1, GCB_VOTE_STAGED = 2;
 constexpr int64_t GCB_CHUNK_BYTES = 48ll << 20;  // payload per pipeline chunk of gcb_consensus_batch
 
 namespace {
@@ -43,7 +44,9 @@ struct gcb_ctx {
     DevBuf w_members, w_group_off, w_scratch, w_rrp, w_flags, w_mode, w_hasumi, w_overlap, w_slab, w_cob, w_coo, w_scan, w_err, w_tiles;
     DevBuf w_vr, w_fs, w_gtiles, w_gcount;
     DevBuf w_thdr, w_fstiles, w_ptiles, w_pcount;  // pipelined vote: tile headers, compact family sides, tile list
-    int vote_mode = 0;                              // GCB_VOTE_TILED / GCB_VOTE_PIPELINED
+    DevBuf w_thdr2;                                 // staged vote: tile headers (compact family sides share w_fstiles)
+    int vote_mode = GCB_VOTE_STAGED;                // GCB_VOTE_TILED / GCB_VOTE_PIPELINED / GCB_VOTE_STAGED
+    int vote_threads = 256;                         // threads per CTA of vote_staged_kernel
     int n_sms = 148;
     // device mirror of a host batch / result (gcb_consensus_batch)
     DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
@@ -97,6 +100,7 @@ void release(DevBuf &b) {
 struct TilePlan {
     int32_t window, window_shift, slab_cap, smem;
     int32_t pipelined, n_stages, stage_bytes;  // vote_pipe_kernel: ring of n_stages tiles of stage_bytes each
+    int32_t staged;                            // vote_staged_kernel
 };
 TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode) {
     const int32_t KB = 1024, budget = 227 * KB;
@@ -116,7 +120,9 @@ TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode) {
             return p;
         }
     }
-    const int32_t tables = VT_OFF_SLAB + VT_SLAB_SLACK + 1 * KB;  // + the 1 KB per-CTA reserve
+    const bool staged = vote_mode == GCB_VOTE_STAGED;
+    const int32_t off_slab = staged ? VS_OFF_SLAB : VT_OFF_SLAB;
+    const int32_t tables = off_slab + VT_SLAB_SLACK + 1 * KB;  // + the 1 KB per-CTA reserve
     if (32 * KB + maxc + tables <= budget / 3) p.window_shift = 15;       // three CTAs per SM
     else if (16 * KB + maxc + tables <= budget / 2) p.window_shift = 14;  // two
     else p.window_shift = 15;
@@ -124,7 +130,8 @@ TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode) {
     p.slab_cap = p.window + maxc;
     if (p.slab_cap > VT_MAX_SLAB) p.slab_cap = VT_MAX_SLAB;
     if (p.slab_cap + tables > budget) p.slab_cap = (budget - tables) & ~127;
-    p.smem = VT_OFF_SLAB + p.slab_cap + VT_SLAB_SLACK;
+    p.smem = off_slab + p.slab_cap + VT_SLAB_SLACK;
+    p.staged = staged ? 1 : 0;
     return p;
 }
 
@@ -165,6 +172,7 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_fstiles, 2 * n_pairs * sizeof(FsTile));
     GCB_RES(w_ptiles, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * 4);
     GCB_RES(w_pcount, 4 * GCB_MAX_CHUNKS);
+    GCB_RES(w_thdr2, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * sizeof(TileHdr2));
 #undef GCB_RES
     ws.members = (int32_t *)ctx->w_members.p;
     ws.group_off = (int32_t *)ctx->w_group_off.p;
@@ -243,26 +251,50 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         GCB_LAUNCH(scan_blocks_kernel, dim3(1), dim3(WARP), 0, stream, ws, n_scan, total_out, result.out_capacity, carry_in);
         ctx->launches += 3;
     }
-    if ((stages & GCB_STAGE_SCORE_VOTE) && n_tiles > 0) {
-        GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
+    const bool run_prep = (stages & (GCB_STAGE_SCORE_VOTE | GCB_STAGE_VOTE_PREP_ONLY)) != 0;
+    const bool run_vote = (stages & (GCB_STAGE_SCORE_VOTE | GCB_STAGE_VOTE_ONLY)) != 0;
+    if ((run_prep || run_vote) && n_tiles > 0) {
         if (plan.pipelined) {
             TileHdr *thdr = (TileHdr *)ctx->w_thdr.p + v.tile_base;
             FsTile *fst = (FsTile *)ctx->w_fstiles.p;
             int32_t *ptiles = (int32_t *)ctx->w_ptiles.p + v.tile_base, *pcount = (int32_t *)ctx->w_pcount.p + v.index;
-            GCB_CUDA(ctx, cudaMemsetAsync(pcount, 0, 4, stream));
-            GCB_LAUNCH(tile_prep_kernel, dim3((unsigned)n_tiles), dim3(VP_PREP_THREADS), 0, stream, b, r, ws, plan.slab_cap, thdr, fst, ptiles, pcount);
-            const unsigned pipe_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
-            GCB_LAUNCH(vote_pipe_kernel, dim3(pipe_grid), dim3(VP_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
-                       fast_path_implied(ctx->opt), plan.n_stages, plan.stage_bytes, (const TileHdr *)thdr, (const FsTile *)fst,
-                       (const int32_t *)ptiles, (const int32_t *)pcount);
-            ctx->launches++;
-        } else {
+            if (run_prep) {
+                GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
+                GCB_CUDA(ctx, cudaMemsetAsync(pcount, 0, 4, stream));
+                GCB_LAUNCH(tile_prep_kernel, dim3((unsigned)n_tiles), dim3(VP_PREP_THREADS), 0, stream, b, r, ws, plan.slab_cap, thdr, fst, ptiles, pcount);
+                ctx->launches++;
+            }
+            if (run_vote) {
+                const unsigned pipe_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
+                GCB_LAUNCH(vote_pipe_kernel, dim3(pipe_grid), dim3(VP_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
+                           fast_path_implied(ctx->opt), plan.n_stages, plan.stage_bytes, (const TileHdr *)thdr, (const FsTile *)fst,
+                           (const int32_t *)ptiles, (const int32_t *)pcount);
+                ctx->launches++;
+            }
+        } else if (plan.staged) {
+            TileHdr2 *thdr = (TileHdr2 *)ctx->w_thdr2.p + v.tile_base;
+            FsTile *fst = (FsTile *)ctx->w_fstiles.p;
+            if (run_prep) {
+                GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
+                GCB_LAUNCH(tile_prep2_kernel, dim3((unsigned)n_tiles), dim3(VS_PREP_THREADS), 0, stream, b, r, ws, plan.slab_cap, thdr, fst);
+                ctx->launches++;
+            }
+            if (run_vote) {
+                GCB_LAUNCH(vote_staged_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
+                           ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst);
+                ctx->launches++;
+            }
+        } else if (run_vote) {
+            GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
             GCB_LAUNCH(vote_tiled_kernel, dim3((unsigned)n_tiles), dim3(VT_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
                        plan.slab_cap, fast_path_implied(ctx->opt));
+            ctx->launches++;
         }
-        const unsigned generic_grid = (unsigned)(n_tiles < 2 * 148 ? n_tiles : 2 * 148);
-        GCB_LAUNCH(score_vote_kernel, dim3(generic_grid), dim3(VOTE_THREADS), VOTE_SMEM, stream, b, r, ws, ctx->genome, ctx->opt);
-        ctx->launches += 2;
+        if (run_vote) {  // the tiles the kernels above handed over (an empty list costs one CTA wave of a few microseconds)
+            const unsigned generic_grid = (unsigned)(n_tiles < 2 * 148 ? n_tiles : 2 * 148);
+            GCB_LAUNCH(score_vote_kernel, dim3(generic_grid), dim3(VOTE_THREADS), VOTE_SMEM, stream, b, r, ws, ctx->genome, ctx->opt);
+            ctx->launches++;
+        }
     }
     if (stages & GCB_STAGE_DUPLEX) {
         GCB_LAUNCH(duplex_kernel, dim3((unsigned)((nc + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream, b, r, ws,
@@ -328,7 +360,8 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
     }
     if (cudaFuncSetAttribute(score_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(vote_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        cudaFuncSetAttribute(vote_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(vote_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         gcb_destroy(ctx);
         return GCB_ERR_CUDA;
     }
@@ -342,7 +375,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
-                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_thdr, &ctx->w_fstiles, &ctx->w_ptiles, &ctx->w_pcount, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
+                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_thdr, &ctx->w_fstiles, &ctx->w_ptiles, &ctx->w_pcount, &ctx->w_thdr2, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
                      &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status};
     for (DevBuf *b : all) release(*b);
@@ -589,8 +622,14 @@ int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, in
 }
 
 int gcb_set_vote_mode(gcb_ctx *ctx, int mode) {
-    if (!ctx || (mode != GCB_VOTE_TILED && mode != GCB_VOTE_PIPELINED)) return GCB_ERR_ARG;
+    if (!ctx || (mode != GCB_VOTE_TILED && mode != GCB_VOTE_PIPELINED && mode != GCB_VOTE_STAGED)) return GCB_ERR_ARG;
     ctx->vote_mode = mode;
+    return GCB_OK;
+}
+
+int gcb_set_vote_threads(gcb_ctx *ctx, int threads) {
+    if (!ctx || threads < WARP || threads > VS_MAX_THREADS || (threads % WARP)) return GCB_ERR_ARG;
+    ctx->vote_threads = threads;
     return GCB_OK;
 }
 

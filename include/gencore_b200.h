@@ -153,6 +153,9 @@ typedef struct gcb_result {
 #define GCB_STAGE_SCORE_VOTE 0x4u      /* pair.cpp:88-172 + group.cpp:320-579 -> out_payload, diff, mismatch_inc */
 #define GCB_STAGE_DUPLEX 0x8u          /* cluster.cpp:102-244 -> status, FR/RR, duplex merge of out_payload */
 #define GCB_STAGE_ALL 0xFu
+/* measurement only: the two halves of GCB_STAGE_SCORE_VOTE one at a time (per-tile preparation, then the vote) */
+#define GCB_STAGE_VOTE_PREP_ONLY 0x10u
+#define GCB_STAGE_VOTE_ONLY 0x20u
 
 typedef struct gcb_ctx gcb_ctx;
 
@@ -203,10 +206,14 @@ int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, in
  * chunks are whole clusters).  Results do not depend on it. */
 int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes);
 
-/* Which kernel runs GCB_STAGE_SCORE_VOTE: 0 = one CTA per tile (vote_tiled_kernel), 1 = the persistent pipelined
- * kernel (vote_pipe_kernel, falls back to 0 for batches whose clusters are too large for its ring).  Results are
- * identical. */
+/* Which kernel runs GCB_STAGE_SCORE_VOTE: 0 = one CTA per tile with its own prologue (vote_tiled_kernel), 1 = the
+ * persistent pipelined kernel (vote_pipe_kernel, falls back to 0 for batches whose clusters are too large for its
+ * ring), 2 = one CTA per tile over headers and family-side lists prepared once per batch (vote_staged_kernel, the
+ * default).  Results are identical. */
 int gcb_set_vote_mode(gcb_ctx *ctx, int mode);
+
+/* Tuning knob of vote mode 2: threads per CTA (a multiple of 32, at most 256; default 256).  Results do not depend on it. */
+int gcb_set_vote_threads(gcb_ctx *ctx, int threads);
 
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t gcb_launch_count(const gcb_ctx *ctx);

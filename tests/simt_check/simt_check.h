@@ -23,6 +23,9 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline __attribute__((always_inline))
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))

@@ -65,6 +65,28 @@ def test_pipelined_vote_matches_oracle(engine_cls, oracle, name, thunk):
     assert_results_equal(batch, res2, expect, name + " (second run)")
 
 
+@pytest.mark.parametrize("name,thunk", CASES, ids=[c[0] for c in CASES])
+def test_tiled_vote_matches_oracle(engine_cls, oracle, name, thunk):
+    """vote_tiled_kernel (gcb_set_vote_mode 0: every CTA builds its tile's family-side table itself) on every case."""
+    batch, genome, opt = thunk()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        eng.set_vote_mode(0)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
+
+
+@pytest.mark.parametrize("threads", [128, 192])
+@pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "cfg4_40k"])
+def test_staged_vote_thread_count_does_not_change_results(engine_cls, oracle, name, threads):
+    batch, genome, opt = dict(CASES)[name]()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        eng.set_vote_threads(threads)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} threads {threads}")
+
+
 @pytest.mark.parametrize("name", ["cfg3_40k", "ragged_duplex_5_big", "deep_1100", "cfg4_40k"])
 @pytest.mark.parametrize("chunk", [1 << 14, 1 << 18, 1 << 21])
 def test_pipeline_chunks_do_not_change_results(engine_cls, oracle, name, chunk):

@@ -86,3 +86,27 @@ def test_pipelined_vote_matches_oracle_under_simt_check(simt_lib, oracle, name, 
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
     if name.startswith(("cfg2", "cfg3", "golden_cfg")):
         assert cnt[0] > 0, "tiles must take the pipeline"
+
+
+@pytest.mark.parametrize("name,thunk", PIPE_CASES, ids=[c[0] for c in PIPE_CASES])
+def test_tiled_vote_matches_oracle_under_simt_check(simt_lib, oracle, name, thunk):
+    """vote_tiled_kernel (vote mode 0: every CTA computes its tile's family-side table itself) gives the same bytes."""
+    from gencore_b200.engine import ConsensusEngine
+    batch, genome, opt = thunk()
+    with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
+        eng.set_reference(genome)
+        eng.set_vote_mode(0)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
+
+
+@pytest.mark.parametrize("threads", [64, 192])
+@pytest.mark.parametrize("name", ["cfg2_1500", "ragged_duplex_2", "golden_cfg4_600"])
+def test_staged_vote_thread_count_does_not_change_results(simt_lib, oracle, name, threads):
+    from gencore_b200.engine import ConsensusEngine
+    batch, genome, opt = dict(CASES)[name]()
+    with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
+        eng.set_reference(genome)
+        eng.set_vote_threads(threads)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} threads {threads}")
