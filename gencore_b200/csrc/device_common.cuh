@@ -52,7 +52,7 @@ struct __align__(16) FsDesc {
 constexpr uint8_t FS_NOFIT = 1;         // some field does not fit its 16 bits: the tile goes to the generic kernel
 constexpr uint8_t FS_REF_OK = 2;        // group.cpp:362-367 + reference.cpp:33-71: the vote may consult the reference
 constexpr uint8_t FS_SIMPLE_CIGAR = 4;  // template CIGAR is one M/=/X op covering the read: BamUtil::getRefOffset(i) == i
-constexpr uint8_t FS_UNIFORM = 8;       // every voter has the template's geometry: same length, no shift, same overlap window
+constexpr uint8_t FS_UNIFORM = 8;       // every voter has the template's geometry: same length, no shift, same overlap window, same record-to-mate distance
 constexpr uint8_t FS_SIDE1 = 0x80;      // (set by the vote kernel) this is the right-hand side of the pairs
 constexpr uint16_t VR_NO_VOTE = 0xFFFFu;  // VoteRead.own_off4 of a read that does not vote
 

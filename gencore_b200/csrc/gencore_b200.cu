@@ -15,11 +15,12 @@
 #include "k_vote_tiled.cuh"
 #include "k_vote_pipe.cuh"
 #include "k_vote_staged.cuh"
+#include "k_vote_split.cuh"
 
 using namespace gcb;
 
 constexpr int GCB_MAX_CHUNKS = 16;
-constexpr int GCB_VOTE_TILED = 0, GCB_VOTE_PIPELINED = 1, GCB_VOTE_STAGED = 2;
+constexpr int GCB_VOTE_TILED = 0, GCB_VOTE_PIPELINED = 1, GCB_VOTE_STAGED = 2, GCB_VOTE_SPLIT = 3;
 constexpr int64_t GCB_CHUNK_BYTES = 48ll << 20;  // payload per pipeline chunk of gcb_consensus_batch
 
 namespace {
@@ -45,7 +46,10 @@ struct gcb_ctx {
     DevBuf w_vr, w_fs, w_gtiles, w_gcount;
     DevBuf w_thdr, w_fstiles, w_ptiles, w_pcount;  // pipelined vote: tile headers, compact family sides, tile list
     DevBuf w_thdr2;                                 // staged vote: tile headers (compact family sides share w_fstiles)
-    int vote_mode = GCB_VOTE_STAGED;                // GCB_VOTE_TILED / GCB_VOTE_PIPELINED / GCB_VOTE_STAGED
+    DevBuf w_sq_count, w_sq_words, w_sq_index, w_sq_acc;  // split vote: slow-column queues, per-family-side accumulators
+    int vote_mode = GCB_VOTE_SPLIT;                 // GCB_VOTE_TILED / GCB_VOTE_PIPELINED / GCB_VOTE_STAGED / GCB_VOTE_SPLIT
+    int64_t slow_queue_bytes = 0;                   // 0 = sized from the payload
+    uint32_t sq_cap_words = 0, sq_cap_recs = 0;     // per queue
     int vote_threads = 256;                         // threads per CTA of vote_staged_kernel
     int n_sms = 148;
     // device mirror of a host batch / result (gcb_consensus_batch)
@@ -100,7 +104,8 @@ void release(DevBuf &b) {
 struct TilePlan {
     int32_t window, window_shift, slab_cap, smem;
     int32_t pipelined, n_stages, stage_bytes;  // vote_pipe_kernel: ring of n_stages tiles of stage_bytes each
-    int32_t staged;                            // vote_staged_kernel
+    int32_t staged;                            // vote_staged_kernel / vote_fast_kernel (same tile geometry)
+    int32_t split;                             // vote_fast_kernel + slow_columns_kernel + vote_finalize_kernel
 };
 TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode) {
     const int32_t KB = 1024, budget = 227 * KB;
@@ -120,7 +125,7 @@ TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode) {
             return p;
         }
     }
-    const bool staged = vote_mode == GCB_VOTE_STAGED;
+    const bool staged = vote_mode == GCB_VOTE_STAGED || vote_mode == GCB_VOTE_SPLIT;
     const int32_t off_slab = staged ? VS_OFF_SLAB : VT_OFF_SLAB;
     const int32_t tables = off_slab + VT_SLAB_SLACK + 1 * KB;  // + the 1 KB per-CTA reserve
     if (32 * KB + maxc + tables <= budget / 3) p.window_shift = 15;       // three CTAs per SM
@@ -132,6 +137,7 @@ TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode) {
     if (p.slab_cap + tables > budget) p.slab_cap = (budget - tables) & ~127;
     p.smem = off_slab + p.slab_cap + VT_SLAB_SLACK;
     p.staged = staged ? 1 : 0;
+    p.split = vote_mode == GCB_VOTE_SPLIT ? 1 : 0;
     return p;
 }
 
@@ -146,7 +152,7 @@ int32_t fast_path_implied(const gcb_options &o) {
     return 1;
 }
 
-int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t n_tiles, Workspace &ws) {
+int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t n_tiles, int64_t payload_bytes, Workspace &ws) {
     int rc;
     const int64_t n_scan = (n_clusters + SCAN_BLOCK - 1) / SCAN_BLOCK;
 #define GCB_RES(buf, bytes) if ((rc = reserve(ctx, ctx->buf, (size_t)(bytes))) != GCB_OK) return rc
@@ -173,6 +179,21 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_ptiles, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * 4);
     GCB_RES(w_pcount, 4 * GCB_MAX_CHUNKS);
     GCB_RES(w_thdr2, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * sizeof(TileHdr2));
+    {   // slow-column queues: a clean library queues about 0.05 bytes per payload byte, a vote whose every column is slow
+        // (options outside fast_path_implied) about 4; what does not fit is decided inside the fast kernel
+        int64_t qbytes = ctx->slow_queue_bytes > 0 ? ctx->slow_queue_bytes : payload_bytes / 4 + (16ll << 20);
+        int64_t cap_words = qbytes / 4 / VQ_NQ;
+        if (cap_words > 0x3FFFFFF0ll) cap_words = 0x3FFFFFF0ll;
+        cap_words &= ~3ll;
+        if (cap_words < 64) cap_words = 64;
+        const int64_t cap_recs = cap_words / 8;
+        GCB_RES(w_sq_count, 8 * VQ_NQ * GCB_MAX_CHUNKS);
+        GCB_RES(w_sq_words, 4 * cap_words * VQ_NQ);
+        GCB_RES(w_sq_index, 4 * cap_recs * VQ_NQ);
+        GCB_RES(w_sq_acc, 2 * n_pairs * 4);
+        ctx->sq_cap_words = (uint32_t)cap_words;
+        ctx->sq_cap_recs = (uint32_t)cap_recs;
+    }
 #undef GCB_RES
     ws.members = (int32_t *)ctx->w_members.p;
     ws.group_off = (int32_t *)ctx->w_group_off.p;
@@ -279,7 +300,25 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                 GCB_LAUNCH(tile_prep2_kernel, dim3((unsigned)n_tiles), dim3(VS_PREP_THREADS), 0, stream, b, r, ws, plan.slab_cap, thdr, fst);
                 ctx->launches++;
             }
-            if (run_vote) {
+            if (run_vote && plan.split) {
+                // chunks of one batch run one after another on the stream and share the queues; every chunk has its own counters
+                SlowQueues sq;
+                sq.count = (unsigned long long *)ctx->w_sq_count.p + (size_t)VQ_NQ * v.index;
+                sq.words = (uint32_t *)ctx->w_sq_words.p;
+                sq.index = (uint32_t *)ctx->w_sq_index.p;
+                sq.cap_words = ctx->sq_cap_words;
+                sq.cap_recs = ctx->sq_cap_recs;
+                sq.acc = (int32_t *)ctx->w_sq_acc.p;
+                GCB_CUDA(ctx, cudaMemsetAsync(sq.count, 0, 8 * VQ_NQ, stream));
+                if (v.p1 > v.p0) GCB_CUDA(ctx, cudaMemsetAsync(sq.acc + 2 * (size_t)v.p0, 0, 8 * (size_t)(v.p1 - v.p0), stream));
+                GCB_LAUNCH(vote_fast_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
+                           ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
+                GCB_LAUNCH(slow_columns_kernel, dim3(VQ_NQ * VQ_SLOW_PARTS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ctx->genome, ctx->opt, sq,
+                           (const TileHdr2 *)thdr, (const FsTile *)fst);
+                GCB_LAUNCH(vote_finalize_kernel, dim3((unsigned)n_tiles), dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt,
+                           (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
+                ctx->launches += 3;
+            } else if (run_vote) {
                 GCB_LAUNCH(vote_staged_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
                            ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst);
                 ctx->launches++;
@@ -361,7 +400,8 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
     if (cudaFuncSetAttribute(score_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(vote_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(vote_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        cudaFuncSetAttribute(vote_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(vote_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         gcb_destroy(ctx);
         return GCB_ERR_CUDA;
     }
@@ -375,7 +415,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
-                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_thdr, &ctx->w_fstiles, &ctx->w_ptiles, &ctx->w_pcount, &ctx->w_thdr2, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
+                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_thdr, &ctx->w_fstiles, &ctx->w_ptiles, &ctx->w_pcount, &ctx->w_thdr2, &ctx->w_sq_count, &ctx->w_sq_words, &ctx->w_sq_index, &ctx->w_sq_acc, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
                      &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status};
     for (DevBuf *b : all) release(*b);
@@ -440,7 +480,7 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
     const TilePlan plan = plan_tiles(batch->max_cluster_bytes, ctx->vote_mode);
     const int64_t n_tiles = (batch->payload_bytes + plan.window - 1) / plan.window;
     Workspace ws;
-    int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, ws);
+    int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, batch->payload_bytes, ws);
     if (rc != GCB_OK) return rc;
     const ViewRange whole = {0, batch->n_clusters, 0, batch->n_pairs, 0, batch->payload_bytes, 0, 0, 0};
     if (stages & GCB_STAGE_UMI_GROUP) GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, stream));
@@ -542,7 +582,7 @@ int gcb_consensus_batch(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *hr) {
         }
     }
     Workspace ws;
-    if ((rc = reserve_workspace(ctx, hb->n_pairs, hb->n_clusters, (hb->payload_bytes + plan.window - 1) / plan.window, ws)) != GCB_OK) return rc;
+    if ((rc = reserve_workspace(ctx, hb->n_pairs, hb->n_clusters, (hb->payload_bytes + plan.window - 1) / plan.window, hb->payload_bytes, ws)) != GCB_OK) return rc;
     cudaStream_t sc = ctx->stream, sin = ctx->h2d, sout = ctx->d2h;
     GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, sc));
     for (int k = 0; k < K; k++) {
@@ -622,7 +662,7 @@ int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, in
 }
 
 int gcb_set_vote_mode(gcb_ctx *ctx, int mode) {
-    if (!ctx || (mode != GCB_VOTE_TILED && mode != GCB_VOTE_PIPELINED && mode != GCB_VOTE_STAGED)) return GCB_ERR_ARG;
+    if (!ctx || mode < GCB_VOTE_TILED || mode > GCB_VOTE_SPLIT) return GCB_ERR_ARG;
     ctx->vote_mode = mode;
     return GCB_OK;
 }
@@ -636,6 +676,12 @@ int gcb_set_vote_threads(gcb_ctx *ctx, int threads) {
 int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes) {
     if (!ctx || bytes < 16) return GCB_ERR_ARG;
     ctx->chunk_bytes = bytes;
+    return GCB_OK;
+}
+
+int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes) {
+    if (!ctx || bytes < 0) return GCB_ERR_ARG;
+    ctx->slow_queue_bytes = bytes;
     return GCB_OK;
 }
 

@@ -366,8 +366,9 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
     ch.k = best_k;
     ch.len = od.n_cigar == 0 ? warp_min(mn) : od.l_qseq;  // group.cpp:354-360: no CIGAR => only the shortest read's columns
     ch.fits = __all_sync(FULL, fits);
-    // FS_UNIFORM: every voter is as long as the template, is read at the template's columns and meets its mate
-    // through the same overlap window (true for every family of a fixed-length library)
+    // FS_UNIFORM: every voter is as long as the template, is read at the template's columns, meets its mate through
+    // the same overlap window and finds its mate's record at the same distance from its own (true for every family
+    // of a fixed-length library packed pair by pair)
     __syncwarp();
     const VoteRead tv = vr[best_k];
     bool uni = ch.len == od.l_qseq && tv.shift == 0 && tv.own_l == od.l_qseq;
@@ -375,7 +376,8 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
         const VoteRead v = vr[k];
         if (v.own_off4 == VR_NO_VOTE) continue;
         uni = uni && v.own_l == tv.own_l && v.shift == 0 && v.ov_len == tv.ov_len &&
-              (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l));
+              (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l &&
+                                 (uint16_t)(v.mate_off4 - v.own_off4) == (uint16_t)(tv.mate_off4 - tv.own_off4)));
     }
     ch.uniform = __all_sync(FULL, uni);
     return ch;

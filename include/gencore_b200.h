@@ -208,11 +208,16 @@ int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes);
 
 /* Which kernel runs GCB_STAGE_SCORE_VOTE: 0 = one CTA per tile with its own prologue (vote_tiled_kernel), 1 = the
  * persistent pipelined kernel (vote_pipe_kernel, falls back to 0 for batches whose clusters are too large for its
- * ring), 2 = one CTA per tile over headers and family-side lists prepared once per batch (vote_staged_kernel, the
- * default).  Results are identical. */
+ * ring), 2 = one CTA per tile over headers and family-side lists prepared once per batch (vote_staged_kernel),
+ * 3 = the same tiles with the slow columns queued for a second kernel (vote_fast_kernel + slow_columns_kernel +
+ * vote_finalize_kernel, the default).  Results are identical. */
 int gcb_set_vote_mode(gcb_ctx *ctx, int mode);
 
-/* Tuning knob of vote mode 2: threads per CTA (a multiple of 32, at most 256; default 256).  Results do not depend on it. */
+/* Tuning knob of vote mode 3: bytes of the slow-column queues (0 = sized from the payload).  Columns that do not fit are
+ * decided inside the fast kernel; results do not depend on it. */
+int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes);
+
+/* Tuning knob of vote modes 2 and 3: threads per CTA (a multiple of 32, at most 256; default 256).  Results do not depend on it. */
 int gcb_set_vote_threads(gcb_ctx *ctx, int threads);
 
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */

@@ -340,6 +340,7 @@ inline unsigned __vmaxu4(unsigned a, unsigned b) {
 inline unsigned __vmaxu2(unsigned a, unsigned b) {
     return std::max(a & 0xFFFFu, b & 0xFFFFu) | (std::max(a >> 16, b >> 16) << 16);
 }
+inline unsigned __vimax3_u16x2(unsigned a, unsigned b, unsigned c) { return __vmaxu2(__vmaxu2(a, b), c); }
 inline unsigned __vcmpgeu4(unsigned a, unsigned b) {
     unsigned r = 0;
     for (int i = 0; i < 4; i++)

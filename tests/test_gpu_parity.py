@@ -76,6 +76,29 @@ def test_tiled_vote_matches_oracle(engine_cls, oracle, name, thunk):
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 
 
+@pytest.mark.parametrize("name,thunk", CASES, ids=[c[0] for c in CASES])
+def test_staged_vote_matches_oracle(engine_cls, oracle, name, thunk):
+    """vote_staged_kernel (gcb_set_vote_mode 2: slow columns decided inside the tile's CTA) on every case."""
+    batch, genome, opt = thunk()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        eng.set_vote_mode(2)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
+
+
+@pytest.mark.parametrize("qbytes", [1 << 14, 1 << 20])
+@pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "cfg4_40k", "edge_strict"])
+def test_slow_queue_overflow_does_not_change_results(engine_cls, oracle, name, qbytes):
+    """Default vote mode with slow-column queues far too small: what does not fit is decided inside the fast kernel."""
+    batch, genome, opt = dict(CASES)[name]()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        eng.set_slow_queue_bytes(qbytes)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} queue {qbytes}")
+
+
 @pytest.mark.parametrize("threads", [128, 192])
 @pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "cfg4_40k"])
 def test_staged_vote_thread_count_does_not_change_results(engine_cls, oracle, name, threads):

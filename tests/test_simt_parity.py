@@ -110,3 +110,28 @@ def test_staged_vote_thread_count_does_not_change_results(simt_lib, oracle, name
         eng.set_vote_threads(threads)
         res = eng.cluster_by_umi(batch)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} threads {threads}")
+
+
+@pytest.mark.parametrize("name,thunk", PIPE_CASES, ids=[c[0] for c in PIPE_CASES])
+def test_staged_vote_matches_oracle_under_simt_check(simt_lib, oracle, name, thunk):
+    """vote_staged_kernel (vote mode 2: slow columns decided inside the tile's CTA, one thread per column) gives the same bytes."""
+    from gencore_b200.engine import ConsensusEngine
+    batch, genome, opt = thunk()
+    with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
+        eng.set_reference(genome)
+        eng.set_vote_mode(2)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
+
+
+@pytest.mark.parametrize("qbytes", [4096, 65536])
+@pytest.mark.parametrize("name", ["cfg2_1500", "ragged_duplex_2", "golden_cfg4_600", "edge_strict"])
+def test_slow_queue_overflow_does_not_change_results(simt_lib, oracle, name, qbytes):
+    """Vote mode 3 with slow-column queues far too small: what does not fit is decided inside the fast kernel."""
+    from gencore_b200.engine import ConsensusEngine
+    batch, genome, opt = dict(CASES)[name]()
+    with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
+        eng.set_reference(genome)
+        eng.set_slow_queue_bytes(qbytes)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} queue {qbytes}")
