@@ -230,7 +230,8 @@ def b200_arm(args):
         names = ["umi_group", "select_template+scan", "tile_prep", "score_vote", "duplex"]
     i_vote = names.index("score_vote")
     vote_kernel = {0: "vote_tiled_kernel", 1: "vote_pipe_kernel", 2: "vote_staged_kernel",
-                   3: "vote_fast_kernel + slow_columns_kernel + vote_finalize_kernel"}[args.vote_mode]
+                   3: "vote_fast_kernel + slow_columns_kernel + vote_finalize_kernel",
+                   4: "vote_ring_kernel + slow_columns_kernel + vote_finalize_kernel"}[args.vote_mode]
 
     def step(events=None):
         for k, st in enumerate(stages):
@@ -365,8 +366,9 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=400_000, help="cpu_baseline sample size (one core)")
     ap.add_argument("--cpu-reps", type=int, default=10, help="cpu_baseline repetitions of the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--vote-mode", type=int, default=3, choices=[0, 1, 2, 3],
-                    help="0 = one CTA per tile with its own prologue, 1 = persistent pipelined, 2 = staged, 3 = split fast/slow (default)")
+    ap.add_argument("--vote-mode", type=int, default=4, choices=[0, 1, 2, 3, 4],
+                    help="0 = one CTA per tile with its own prologue, 1 = persistent pipelined, 2 = staged, 3 = split fast/slow, "
+                         "4 = split with the fast kernel as a persistent ring (default)")
     ap.add_argument("--vote-threads", type=int, default=256, help="threads per CTA of the staged vote kernel")
     ap.add_argument("--sweep", default="", help="tuning aid: comma-separated mode:threads settings whose vote stage times go to stderr")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per vote launch from an ncu capture (profiles/)")

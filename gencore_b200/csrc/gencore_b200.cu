@@ -16,11 +16,12 @@
 #include "k_vote_pipe.cuh"
 #include "k_vote_staged.cuh"
 #include "k_vote_split.cuh"
+#include "k_vote_ring.cuh"
 
 using namespace gcb;
 
 constexpr int GCB_MAX_CHUNKS = 16;
-constexpr int GCB_VOTE_TILED = 0, GCB_VOTE_PIPELINED = 1, GCB_VOTE_STAGED = 2, GCB_VOTE_SPLIT = 3;
+constexpr int GCB_VOTE_TILED = 0, GCB_VOTE_PIPELINED = 1, GCB_VOTE_STAGED = 2, GCB_VOTE_SPLIT = 3, GCB_VOTE_RING = 4;
 constexpr int64_t GCB_CHUNK_BYTES = 48ll << 20;  // payload per pipeline chunk of gcb_consensus_batch
 
 namespace {
@@ -47,7 +48,7 @@ struct gcb_ctx {
     DevBuf w_thdr, w_fstiles, w_ptiles, w_pcount;  // pipelined vote: tile headers, compact family sides, tile list
     DevBuf w_thdr2;                                 // staged vote: tile headers (compact family sides share w_fstiles)
     DevBuf w_sq_count, w_sq_words, w_sq_index, w_sq_acc;  // split vote: slow-column queues, per-family-side accumulators
-    int vote_mode = GCB_VOTE_SPLIT;                 // GCB_VOTE_TILED / GCB_VOTE_PIPELINED / GCB_VOTE_STAGED / GCB_VOTE_SPLIT
+    int vote_mode = GCB_VOTE_RING;                  // GCB_VOTE_TILED / GCB_VOTE_PIPELINED / GCB_VOTE_STAGED / GCB_VOTE_SPLIT
     int64_t slow_queue_bytes = 0;                   // 0 = sized from the payload
     uint32_t sq_cap_words = 0, sq_cap_recs = 0;     // per queue
     int vote_threads = 256;                         // threads per CTA of vote_staged_kernel
@@ -106,6 +107,7 @@ struct TilePlan {
     int32_t pipelined, n_stages, stage_bytes;  // vote_pipe_kernel: ring of n_stages tiles of stage_bytes each
     int32_t staged;                            // vote_staged_kernel / vote_fast_kernel (same tile geometry)
     int32_t split;                             // vote_fast_kernel + slow_columns_kernel + vote_finalize_kernel
+    int32_t ring;                              // vote_ring_kernel instead of vote_fast_kernel (n_stages, stage_bytes)
 };
 TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode) {
     const int32_t KB = 1024, budget = 227 * KB;
@@ -124,6 +126,23 @@ TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode) {
             p.smem = VP_OFF_STAGE0 + p.n_stages * p.stage_bytes;
             return p;
         }
+    }
+    if (vote_mode == GCB_VOTE_RING) {  // one CTA per SM, a ring of whole tiles: 32 KB windows if three stages fit, else 16 KB
+        for (int shift = 15; shift >= 14; shift--) {
+            p.window_shift = shift;
+            p.window = 1 << shift;
+            p.slab_cap = p.window + maxc;
+            p.stage_bytes = (VRS_OFF_SLAB + p.slab_cap + VT_SLAB_SLACK + 127) & ~127;
+            p.n_stages = (budget - 1 * KB - VR_OFF_STAGE0) / p.stage_bytes;
+            if (p.n_stages > VR_MAX_STAGES) p.n_stages = VR_MAX_STAGES;
+            if ((p.n_stages >= 3 || (shift == 14 && p.n_stages >= 2)) && p.slab_cap <= VT_MAX_SLAB) {
+                p.staged = p.split = p.ring = 1;
+                p.smem = VR_OFF_STAGE0 + p.n_stages * p.stage_bytes;
+                return p;
+            }
+        }
+        memset(&p, 0, sizeof p);
+        vote_mode = GCB_VOTE_SPLIT;  // clusters too large for a ring: one tile per CTA
     }
     const bool staged = vote_mode == GCB_VOTE_STAGED || vote_mode == GCB_VOTE_SPLIT;
     const int32_t off_slab = staged ? VS_OFF_SLAB : VT_OFF_SLAB;
@@ -148,7 +167,7 @@ int32_t fast_path_implied(const gcb_options &o) {
     const int mn = sh < sm ? (sh < sl ? (sh < sb ? sh : sb) : (sl < sb ? sl : sb)) : (sm < sl ? (sm < sb ? sm : sb) : (sl < sb ? sl : sb));
     if (mn <= 0 || mn + 4 > 127) return 0;
     if (sh < o.base_score_req || sm < o.base_score_req || mn + 4 < o.base_score_req) return 0;
-    if (o.moderate_quality < 0 || o.moderate_quality > 255) return 0;
+    if (o.moderate_quality < 0 || o.moderate_quality > 128) return 0;  // (bytes_ge_flags compares bytes against thresholds <= 128)
     return 1;
 }
 
@@ -181,7 +200,8 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_thdr2, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * sizeof(TileHdr2));
     {   // slow-column queues: a clean library queues about 0.05 bytes per payload byte, a vote whose every column is slow
         // (options outside fast_path_implied) about 4; what does not fit is decided inside the fast kernel
-        int64_t qbytes = ctx->slow_queue_bytes > 0 ? ctx->slow_queue_bytes : payload_bytes / 4 + (16ll << 20);
+        int64_t qbytes = ctx->slow_queue_bytes > 0 ? ctx->slow_queue_bytes
+                         : fast_path_implied(ctx->opt) ? payload_bytes / 4 + (16ll << 20) : 5 * payload_bytes + (16ll << 20);
         int64_t cap_words = qbytes / 4 / VQ_NQ;
         if (cap_words > 0x3FFFFFF0ll) cap_words = 0x3FFFFFF0ll;
         cap_words &= ~3ll;
@@ -311,8 +331,15 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                 sq.acc = (int32_t *)ctx->w_sq_acc.p;
                 GCB_CUDA(ctx, cudaMemsetAsync(sq.count, 0, 8 * VQ_NQ, stream));
                 if (v.p1 > v.p0) GCB_CUDA(ctx, cudaMemsetAsync(sq.acc + 2 * (size_t)v.p0, 0, 8 * (size_t)(v.p1 - v.p0), stream));
-                GCB_LAUNCH(vote_fast_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
-                           ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
+                if (plan.ring) {
+                    const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
+                    GCB_LAUNCH(vote_ring_kernel, dim3(ring_grid), dim3(VR_THREADS), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
+                               fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
+                               plan.stage_bytes);
+                } else {
+                    GCB_LAUNCH(vote_fast_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
+                               ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
+                }
                 GCB_LAUNCH(slow_columns_kernel, dim3(VQ_NQ * VQ_SLOW_PARTS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ctx->genome, ctx->opt, sq,
                            (const TileHdr2 *)thdr, (const FsTile *)fst);
                 GCB_LAUNCH(vote_finalize_kernel, dim3((unsigned)n_tiles), dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt,
@@ -401,7 +428,8 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
         cudaFuncSetAttribute(vote_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(vote_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(vote_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        cudaFuncSetAttribute(vote_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(vote_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         gcb_destroy(ctx);
         return GCB_ERR_CUDA;
     }
@@ -662,7 +690,7 @@ int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, in
 }
 
 int gcb_set_vote_mode(gcb_ctx *ctx, int mode) {
-    if (!ctx || mode < GCB_VOTE_TILED || mode > GCB_VOTE_SPLIT) return GCB_ERR_ARG;
+    if (!ctx || mode < GCB_VOTE_TILED || mode > GCB_VOTE_RING) return GCB_ERR_ARG;
     ctx->vote_mode = mode;
     return GCB_OK;
 }

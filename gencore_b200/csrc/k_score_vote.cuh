@@ -233,14 +233,15 @@ GCB_DEV void store_pass(uint8_t *out, int l_out, int col0, int qual, int nib) {
 }
 
 // One (family, side): group.cpp:320-579.  Whole warp.
+// `abs_off`: out_off already holds the absolute offset (a tile that a tile-preparing vote kernel accepted and handed over later)
 GCB_DEV void vote_family_side(const BatchView &b, const ResultView &r, const Workspace &ws, const GenomeView &gv, const gcb_options &o,
-                              const uint8_t *cbase, int64_t slab0, int c, int slot, int side, int64_t out_base) {
+                              const uint8_t *cbase, int64_t slab0, int c, int slot, int side, int64_t out_base, bool abs_off) {
     const int lane = lane_id();
     const uint8_t mode = ws.side_mode[2 * (int64_t)slot + side];
     if (mode == SIDE_NONE) return;
     gcb_group_result *gr = r.groups + slot;
     const int tmpl = gr->tmpl_read[side];
-    const int64_t out_off = out_base + gr->out_off[side];
+    const int64_t out_off = abs_off ? gr->out_off[side] : out_base + gr->out_off[side];
     __syncwarp();
     if (lane == 0) gr->out_off[side] = out_off;
     const gcb_read_desc od = b.reads[tmpl];
@@ -448,7 +449,9 @@ __global__ void __launch_bounds__(VOTE_THREADS) score_vote_kernel(BatchView b, R
     uint32_t parity = 0;
     const int n_generic = *ws.generic_count;
     for (int gi = (int)blockIdx.x; gi < n_generic; gi += (int)gridDim.x) {
-    const int tile = ws.generic_tiles[gi];
+    const int tile_code = ws.generic_tiles[gi];  // ~tile: the consensus offsets of the tile's families are already absolute
+    const bool abs_off = tile_code < 0;
+    const int tile = abs_off ? ~tile_code : tile_code;
     const int c0 = ws.tile_dir[tile].c0, c1 = ws.tile_dir[tile + 1].c0;
     int cs = c0;
     while (cs < c1) {
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) score_vote_kernel(BatchView b, R
             const int64_t out_base = ws.scan_block[c / SCAN_BLOCK] + ws.cluster_out_off[c];
             const int G = r.cluster_n_groups[c], p0 = b.cluster_pair_off[c];
             for (int g = 0; g < G; g++)
-                for (int side = 0; side < 2; side++) vote_family_side(b, r, ws, gv, o, cbase, slab0, c, p0 + g, side, out_base);
+                for (int side = 0; side < 2; side++) vote_family_side(b, r, ws, gv, o, cbase, slab0, c, p0 + g, side, out_base, abs_off);
         }
         __syncthreads();
         cs = ce;

@@ -1,0 +1,405 @@
+// k_vote_ring.cuh — the fast half of the split vote (k_vote_split.cuh) as ONE persistent CTA per SM over a ring of
+// staged tiles: Pair::computeScore (pair.cpp:88-172) fused with Group::makeConsensus (group.cpp:320-579).
+//
+//   warp 0, lane 0    producer.  Walks this CTA's tiles (blockIdx.x, + gridDim.x, ...), waits for the stage's `empty`
+//                     mbarrier, writes the 64-byte stage header and issues three bulk asynchronous copies
+//                     (cp.async.bulk -> UBLKCP) onto the stage's `full` mbarrier: compact family-side list, VoteRead table,
+//                     payload slab.  Runs up to n_stages tiles ahead; the last stage it fills carries nfs < 0.
+//   warps 1..15       consumers.  Every warp visits every tile in order: waits for `full`, takes bundles of family sides
+//                     from the stage's counter until none is left, arrives on `empty`.  A tile has fewer bundles than the
+//                     CTA has warps, so the warps spread over the tiles in flight; nobody waits for a tile's last column:
+//                     the slow columns are queued for slow_columns_kernel (k_vote_split.cuh).
+//   a bundle          lanes_per_side lanes per family side, sixteen columns per lane: the branch-free uniform loop of
+//                     vote_fast_kernel (raw-order XOR residues, VIMNMX3.U16x2 over two reads, mate alignment once per
+//                     bundle).  Slow columns of the bundle are emitted COOPERATIVELY: the lanes list their columns in a
+//                     small per-warp table, one 64-bit atomic reserves all records, then eight lanes per column write the
+//                     column's entries (one lane per read).  Bundles with more than VR_ITEMS slow columns (votes whose
+//                     every column is slow) fall back to one lane per column.
+//   queue overflow    the tile is handed to the generic kernel (score_vote_kernel), which runs last and rewrites all of the
+//                     tile's records from the payload.
+#pragma once
+
+#include "k_vote_split.cuh"
+
+namespace gcb {
+
+constexpr int VR_THREADS = 512;
+constexpr int VR_WARPS = VR_THREADS / WARP;
+constexpr int VR_CONSUMERS = VR_WARPS - 1;
+constexpr int VR_MAX_STAGES = 6;
+constexpr int VR_ITEMS = 64;      // sparse slow columns of one bundle that are emitted cooperatively
+constexpr int VR_GROUP = 8;       // lanes per slow column in the cooperative emission
+
+struct __align__(16) RingStage {  // shared memory, written by the producer before the stage's `full` barrier completes
+    int64_t out_base0;
+    int32_t nfs;          // live family sides; < 0: no more tiles
+    int32_t lanes, per_bundle, n_bundles, common_l;
+    int32_t p0, tile;
+    int32_t next_bundle;  // atomic: next bundle to hand out
+    int32_t handed_over;  // atomic: the tile went to the generic kernel (queue overflow)
+    int32_t pad[5];
+};
+static_assert(sizeof(RingStage) == 64, "stage header size");
+
+// shared-memory map: [barriers][stage headers][per-warp slow-column tables][stage 0][stage 1]...
+constexpr int VR_OFF_FULL = 0;                                   // uint64[VR_MAX_STAGES]
+constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MAX_STAGES]
+constexpr int VR_OFF_HDR = 128;                                  // RingStage[VR_MAX_STAGES]
+constexpr int VR_OFF_ITEMS = VR_OFF_HDR + 64 * VR_MAX_STAGES;    // per warp: uint32 word offsets[VR_ITEMS], uint16 codes[VR_ITEMS]
+constexpr int VR_ITEM_BYTES = 6 * VR_ITEMS;
+constexpr int VR_OFF_STAGE0 = (VR_OFF_ITEMS + VR_ITEM_BYTES * VR_WARPS + 127) & ~127;
+// inside a stage
+constexpr int VRS_OFF_FT = 0;                                    // FsTile[VS_MAX_FS]
+constexpr int VRS_OFF_VR = VRS_OFF_FT + 32 * VS_MAX_FS;          // VoteRead[2*VS_MAX_PAIRS]
+constexpr int VRS_OFF_SLAB = (VRS_OFF_VR + 32 * VS_MAX_PAIRS + 127) & ~127;
+static_assert(16 * VR_MAX_STAGES <= VR_OFF_HDR && VRS_OFF_VR % 16 == 0 && VR_OFF_STAGE0 % 128 == 0, "ring layout");
+
+__global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, int32_t moderate_quality, int32_t implied,
+                                                                  const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, int32_t n_tiles,
+                                                                  int32_t n_stages, int32_t stage_bytes) {
+    GCB_DYN_SMEM(smem);
+    uint64_t *full = (uint64_t *)(smem + VR_OFF_FULL);
+    uint64_t *empty = (uint64_t *)(smem + VR_OFF_EMPTY);
+    RingStage *shdr = (RingStage *)(smem + VR_OFF_HDR);
+#define GCB_LDS32(off) (*(const uint32_t *)(smem + (off)))
+    const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; s++) {
+            pipe_init(full + s, 1);
+            pipe_init(empty + s, VR_CONSUMERS);  // every consumer warp arrives once when it leaves the stage's tile
+        }
+        pipe_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ---- producer: one thread, up to n_stages tiles ahead of the consumers
+        if (lane != 0) return;
+        int t = (int)blockIdx.x;
+        TileHdr2 h;
+        h.nfs = 0;
+        while (t < n_tiles && (h = hdr[t]).nfs <= 0) t += (int)gridDim.x;
+        int k = 0;
+        for (;; k++) {
+            const bool have = t < n_tiles;
+            const TileHdr2 cur = h;
+            const int cur_t = t;
+            if (have) {  // the next tile's header is on its way while this one waits for its stage
+                t += (int)gridDim.x;
+                while (t < n_tiles && (h = hdr[t]).nfs <= 0) t += (int)gridDim.x;
+            }
+            const int s = k % n_stages, use = k / n_stages;
+            if (use > 0) pipe_wait(empty + s, (uint32_t)((use - 1) & 1));  // every consumer has left the stage's previous tile
+            uint8_t *stage = smem + VR_OFF_STAGE0 + (size_t)s * stage_bytes;
+            RingStage sh;
+            sh.out_base0 = cur.out_base0;
+            sh.nfs = have ? cur.nfs : -1;
+            sh.lanes = cur.lanes; sh.per_bundle = cur.per_bundle; sh.n_bundles = cur.n_bundles; sh.common_l = cur.common_l;
+            sh.p0 = cur.p0; sh.tile = cur_t;
+            sh.next_bundle = 0;
+            sh.handed_over = 0;
+            sh.pad[0] = sh.pad[1] = sh.pad[2] = sh.pad[3] = sh.pad[4] = 0;
+            shdr[s] = sh;
+            if (!have) {  // the end marker: the phase completes with this arrival alone
+                pipe_expect(full + s, 0u);
+                pipe_commit(full + s);
+                break;
+            }
+            const uint32_t slab_bytes = (uint32_t)cur.slab_bytes, vr_bytes = 32u * (uint32_t)cur.np, ft_bytes = 32u * (uint32_t)cur.nfs;
+            pipe_expect(full + s, slab_bytes + vr_bytes + ft_bytes);
+            if (slab_bytes > 0) tile_copy(stage + VRS_OFF_SLAB, b.payload + cur.slab0, slab_bytes, full + s);
+            tile_copy(stage + VRS_OFF_VR, ws.vote_reads + 2 * (int64_t)cur.p0, vr_bytes, full + s);
+            tile_copy(stage + VRS_OFF_FT, fs_tiles + 2 * (int64_t)cur.p0, ft_bytes, full + s);
+            pipe_commit(full + s);
+        }
+        return;
+    }
+
+    // ---- consumers
+    const uint32_t mod4 = 0x01010101u * (uint32_t)(moderate_quality & 0xFF);
+    const uint32_t sbase = smem_base(smem);
+    uint32_t *s_itemw = (uint32_t *)(smem + VR_OFF_ITEMS + VR_ITEM_BYTES * warp);
+    uint16_t *s_item = (uint16_t *)(s_itemw + VR_ITEMS);
+    for (int k = 0;; k++) {
+        const int s = k % n_stages, use = k / n_stages;
+        pipe_wait(full + s, (uint32_t)(use & 1));
+        RingStage *sh = shdr + s;
+        const int nfs = sh->nfs;
+        if (nfs < 0) break;
+        const int nb = sh->n_bundles;
+        int bundle = 0;
+        if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
+        bundle = __shfl_sync(FULL, bundle, 0);
+        if (bundle < nb) {
+            const int stage_off = VR_OFF_STAGE0 + s * stage_bytes;
+            const FsTile *s_ft = (const FsTile *)(smem + stage_off + VRS_OFF_FT);
+            const VoteRead *s_vr = (const VoteRead *)(smem + stage_off + VRS_OFF_VR);
+            const int off_slab = stage_off + VRS_OFF_SLAB, off_vr = stage_off + VRS_OFF_VR;
+            uint8_t *out0 = r.out_payload + sh->out_base0;
+            const int p0 = sh->p0, tile = sh->tile;
+            const int qi = tile % VQ_NQ;
+            uint32_t *q_words = sq.words + (size_t)qi * sq.cap_words;
+            uint32_t *q_index = sq.index + (size_t)qi * sq.cap_recs;
+            const int L = sh->lanes, S = sh->per_bundle;  // lanes per family side (1..32), family sides per bundle (32 / L)
+            const int sub = (int)(((unsigned)lane * ((65535u / (unsigned)L) + 1u)) >> 16), j = lane - sub * L;  // lane / L, lane % L
+            const int col0 = VT_CHUNK * j;
+            const int common_l = sh->common_l;  // the masks of the tile's usual record length are computed once
+            const ChunkMasks cm_common = make_masks(common_l, common_l, col0);
+            do {
+                const int f = bundle * S + sub;
+                FsTile ft;
+                ft.ent0 = 0; ft.m = 0; ft.l_out = 0; ft.len = 0; ft.tmpl_k = 0; ft.mode = SIDE_NONE; ft.flags = 0; ft.cbase4 = 0; ft.out4 = 0;
+                if (sub < S && f < nfs) ft = s_ft[f];
+                const int l_out = ft.l_out, len = ft.len;
+                const int qbytes = GCB_ALIGN4(l_out), sbytes = GCB_ALIGN4((l_out + 1) >> 1);
+                const bool mine = ft.mode != SIDE_NONE && col0 < max(qbytes, 2 * sbytes);  // this lane owns words of the record
+                const int m = mine && ft.mode != SIDE_COPY ? (int)ft.m : 0;
+                const int mmax = __reduce_max_sync(FULL, m);
+                const int cb = off_slab + 4 * (int)ft.cbase4;  // byte offsets into the CTA's shared memory
+                const int ento = off_vr + 16 * (int)ft.ent0;
+                VoteRead tv = {0, 0, 0, 0, 0, 0, 0, 0};
+                uint32_t tbe0 = 0u, tbe1 = 0u;
+                int trec = cb;
+                if (mine) {
+                    tv = s_vr[ft.ent0 + ft.tmpl_k];
+                    trec = cb + 4 * (int)tv.own_off4;
+                    if (8 * j < sbytes) tbe0 = bswap32(GCB_LDS32(trec + qbytes + 8 * j));
+                    if (8 * j + 4 < sbytes) tbe1 = bswap32(GCB_LDS32(trec + qbytes + 8 * j + 4));
+                }
+                ChunkMasks cm = cm_common;
+                if (l_out != common_l || len != l_out) cm = make_masks(l_out, len, col0);
+                if (mine && j == 0 && ft.mode != SIDE_COPY) GCB_COUNT((ft.flags & FS_UNIFORM) ? 4 : 5, 1);
+                uint32_t mo[4] = {0u, 0u, 0u, 0u}, me[4] = {0u, 0u, 0u, 0u}, dis0 = 0u, dis1 = 0u;
+                if (ft.flags & FS_UNIFORM) {  // (see vote_fast_kernel)
+                    const int x = (int)tv.ov_own - col0;
+                    const int y = x - (int)tv.ov_mate;
+                    const int oa = max(max(0, x), y), oz = min(min(cm.nvote, x + (int)tv.ov_len), y + (int)tv.mate_l);
+                    const bool has_ov = tv.ov_len > 0 && oz > oa;
+                    const uint32_t om0 = has_ov ? nib_range(oa, oz) : 0u, om1 = has_ov ? nib_range(oa - 8, oz - 8) : 0u;
+                    const int ms = 0 - y, mw0 = ms >> 3;
+                    const unsigned msh = (unsigned)(ms & 7) * 4u;
+                    const uint32_t qbase = sbase + (uint32_t)(cb + col0), sdelta = (uint32_t)(qbytes - col0 + 8 * j);
+                    const uint32_t mdelta = has_ov ? (uint32_t)(4 * ((int)tv.mate_off4 - (int)tv.own_off4) + GCB_ALIGN4(tv.mate_l) + 4 * mw0 - col0) : 0u;
+                    const uint32_t xt = tv.own_off4;
+                    const uint32_t qt = qbase + (xt << 2);
+                    const uint32_t t0 = lds32<0>(qt + sdelta), t1 = lds32<4>(qt + sdelta);
+                    const uint32_t a0 = lds32<0>(qt + mdelta), c0 = lds32<4>(qt + mdelta), e0 = lds32<8>(qt + mdelta);
+                    uint32_t d0 = 0u, d1 = 0u, da = 0u, dc = 0u, de = 0u;
+                    uint32_t ea = sbase + (uint32_t)ento;
+                    for (int e = 0; e < mmax; e += 2, ea += 32) {
+                        uint32_t xa = lds16<0>(ea), xb = lds16<16>(ea);
+                        xa = (e < m && xa != VR_NO_VOTE) ? xa : xt;
+                        xb = (e + 1 < m && xb != VR_NO_VOTE) ? xb : xt;
+                        const uint32_t qa = qbase + (xa << 2), qb = qbase + (xb << 2);
+                        const uint32_t qa0 = lds32<0>(qa), qa1 = lds32<4>(qa), qa2 = lds32<8>(qa), qa3 = lds32<12>(qa);
+                        const uint32_t qb0 = lds32<0>(qb), qb1 = lds32<4>(qb), qb2 = lds32<8>(qb), qb3 = lds32<12>(qb);
+                        const uint32_t ra0 = lds32<0>(qa + sdelta), ra1 = lds32<4>(qa + sdelta);
+                        const uint32_t rb0 = lds32<0>(qb + sdelta), rb1 = lds32<4>(qb + sdelta);
+                        const uint32_t ma = qa + mdelta, mb = qb + mdelta;
+                        const uint32_t aa = lds32<0>(ma), ca = lds32<4>(ma), ee = lds32<8>(ma);
+                        const uint32_t ab = lds32<0>(mb), cbb = lds32<4>(mb), eb = lds32<8>(mb);
+                        mo[0] = __vimax3_u16x2(mo[0], qa0, qb0); me[0] = __vimax3_u16x2(me[0], qa0 << 8, qb0 << 8);
+                        mo[1] = __vimax3_u16x2(mo[1], qa1, qb1); me[1] = __vimax3_u16x2(me[1], qa1 << 8, qb1 << 8);
+                        mo[2] = __vimax3_u16x2(mo[2], qa2, qb2); me[2] = __vimax3_u16x2(me[2], qa2 << 8, qb2 << 8);
+                        mo[3] = __vimax3_u16x2(mo[3], qa3, qb3); me[3] = __vimax3_u16x2(me[3], qa3 << 8, qb3 << 8);
+                        d0 |= (ra0 ^ t0) | (rb0 ^ t0);
+                        d1 |= (ra1 ^ t1) | (rb1 ^ t1);
+                        da |= (aa ^ a0) | (ab ^ a0);
+                        dc |= (ca ^ c0) | (cbb ^ c0);
+                        de |= (ee ^ e0) | (eb ^ e0);
+                    }
+                    dis0 = bswap32(d0);
+                    dis1 = bswap32(d1);
+                    if (has_ov) {  // pair.cpp:133-170: a base that differs from its mate's is never a fast column
+                        const uint32_t A = bswap32(da), C = bswap32(dc), E = bswap32(de);
+                        const uint32_t ta = bswap32(a0), tc = bswap32(c0), te = bswap32(e0);
+                        const uint32_t tb0 = bswap32(t0), tb1 = bswap32(t1);
+                        dis0 |= (__funnelshift_l(C, A, msh) | (tb0 ^ __funnelshift_l(tc, ta, msh))) & om0;
+                        dis1 |= (__funnelshift_l(E, C, msh) | (tb1 ^ __funnelshift_l(te, tc, msh))) & om1;
+                    }
+                } else {
+                    for (int e = 0; e < mmax; e++) {
+                        if (e >= m) continue;
+                        const VoteRead v = s_vr[ft.ent0 + e];
+                        if (v.own_off4 == VR_NO_VOTE || v.own_l == 0) continue;
+                        const int rp0 = col0 + v.shift;
+                        const int a = max(0, 0 - rp0), z = min(cm.nvote, (int)v.own_l - rp0);
+                        if (z <= a) continue;
+                        const uint8_t *rec = smem + cb + 4 * (int)v.own_off4;
+                        const int rq = GCB_ALIGN4(v.own_l);
+                        uint32_t q[4], be0, be1;
+                        fetch16q(rec, rq, rp0, q);
+                        fetch16b(rec + rq, GCB_ALIGN4((v.own_l + 1) >> 1), rp0, be0, be1);
+                        const uint32_t vm0 = nib_range(a, z), vm1 = nib_range(a - 8, z - 8);
+                        q[0] &= bytes_lo(vm0); q[1] &= bytes_hi(vm0); q[2] &= bytes_lo(vm1); q[3] &= bytes_hi(vm1);
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            mo[kk] = __vmaxu2(mo[kk], q[kk]);
+                            me[kk] = __vmaxu2(me[kk], q[kk] << 8);
+                        }
+                        dis0 |= (be0 ^ tbe0) & vm0;
+                        dis1 |= (be1 ^ tbe1) & vm1;
+                        if (v.ov_len > 0) {  // (subtractions only: see the ptxas note in k_vote_tiled.cuh)
+                            const int x = (int)v.ov_own - rp0;
+                            const int y = x - (int)v.ov_mate;
+                            const int oa = max(max(a, x), y);
+                            const int oz = min(min(z, x + (int)v.ov_len), y + (int)v.mate_l);
+                            if (oz > oa) {
+                                const uint8_t *mrec = smem + cb + 4 * (int)v.mate_off4;
+                                uint32_t mb0, mb1;
+                                fetch16b(mrec + GCB_ALIGN4(v.mate_l), GCB_ALIGN4((v.mate_l + 1) >> 1), 0 - y, mb0, mb1);
+                                dis0 |= (be0 ^ mb0) & nib_range(oa, oz);
+                                dis1 |= (be1 ^ mb1) & nib_range(oa - 8, oz - 8);
+                            }
+                        }
+                    }
+                }
+                // ---- what the record gets: qualities = the maxima (fast columns), bases = the template's
+                uint32_t slow0 = 0u, slow1 = 0u;  // one bit per slow column (the low bit of its big-endian nibble)
+                if (mine) {
+                    uint32_t oq[4];
+                    if (ft.mode == SIDE_COPY) {  // group.cpp:73-77: the record itself
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) oq[kk] = col0 + 4 * kk < qbytes ? GCB_LDS32(trec + col0 + 4 * kk) : 0u;
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) oq[kk] = prmt(mo[kk], me[kk], 0x3715u) & cm.vb[kk];  // (the hoisted loop read whole words)
+                        GCB_COUNT(2, cm.nvote);
+                        if (implied && len == l_out) {
+                            const uint32_t lowq0 = nibs_of_flags(bytes_ge_flags(oq[0], mod4) ^ 0x80808080u, bytes_ge_flags(oq[1], mod4) ^ 0x80808080u);
+                            const uint32_t lowq1 = nibs_of_flags(bytes_ge_flags(oq[2], mod4) ^ 0x80808080u, bytes_ge_flags(oq[3], mod4) ^ 0x80808080u);
+                            slow0 = (dis0 | lowq0) & cm.vn0;
+                            slow1 = (dis1 | lowq1) & cm.vn1;
+                            slow0 |= slow0 >> 1; slow0 |= slow0 >> 2; slow0 &= 0x11111111u;  // any differing bit marks the column
+                            slow1 |= slow1 >> 1; slow1 |= slow1 >> 2; slow1 &= 0x11111111u;
+                        } else {  // without `implied`, or with columns that are not voted, every column of the record is slow
+                            slow0 = nibs_of_bytes(cm.rb[0], cm.rb[1]) & 0x11111111u;
+                            slow1 = nibs_of_bytes(cm.rb[2], cm.rb[3]) & 0x11111111u;
+                        }
+                    }
+                    uint8_t *out = out0 + 4 * (int64_t)ft.out4;
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)
+                        if (col0 + 4 * kk < qbytes) *(uint32_t *)(out + col0 + 4 * kk) = oq[kk] & cm.rb[kk];
+                    if (8 * j < sbytes) *(uint32_t *)(out + qbytes + 8 * j) = bswap32(tbe0 & cm.kn0);
+                    if (8 * j + 4 < sbytes) *(uint32_t *)(out + qbytes + 8 * j + 4) = bswap32(tbe1 & cm.kn1);
+                }
+                // ---- slow columns: one reservation per bundle (records << 32 | words), then the entries
+                const int nslow = __popc(slow0) + __popc(slow1);
+                if (__any_sync(FULL, nslow > 0)) {
+                    const uint32_t rec_words = 4u + (((uint32_t)ft.m + 3u) & ~3u);
+                    GCB_COUNT(3, nslow);
+                    const unsigned long long mine64 = ((unsigned long long)(uint32_t)nslow << 32) | ((uint32_t)nslow * rec_words);
+                    unsigned long long incl = mine64;
+                    for (int off = 1; off < WARP; off <<= 1) {
+                        const unsigned long long v = __shfl_up_sync(FULL, incl, off);
+                        if (lane >= off) incl += v;
+                    }
+                    const unsigned long long total = __shfl_sync(FULL, incl, WARP - 1);
+                    unsigned long long base64 = 0ull;
+                    if (lane == 0) base64 = atomicAdd(sq.count + qi, total);
+                    base64 = __shfl_sync(FULL, base64, 0);
+                    const uint32_t rec0 = (uint32_t)(base64 >> 32), word0 = (uint32_t)base64, T = (uint32_t)(total >> 32);
+                    const bool fits = (unsigned long long)rec0 + T <= sq.cap_recs && (unsigned long long)word0 + (uint32_t)total <= sq.cap_words;
+                    uint32_t ri = (uint32_t)((incl - mine64) >> 32), wi = word0 + (uint32_t)(incl - mine64);  // this lane's first record / word
+                    if (!fits) {
+                        // the queue is full: the generic kernel redoes the whole tile from the payload (it runs after
+                        // slow_columns_kernel and vote_finalize_kernel); the reserved index entries are marked unused
+                        for (uint32_t i = (uint32_t)lane; i < T; i += WARP)
+                            if (rec0 + i < sq.cap_recs) q_index[rec0 + i] = VQ_INVALID;
+                        if (lane == 0 && atomicExch(&sh->handed_over, 1) == 0) {
+                            ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~tile;
+                            GCB_COUNT(1, 1);
+                        }
+                    } else if (T <= (uint32_t)VR_ITEMS) {
+                        // every lane lists its columns; then eight lanes per column, one lane per read
+                        for (int wsel = 0; wsel < 2; wsel++) {
+                            uint32_t sm = wsel ? slow1 : slow0;
+                            while (sm != 0u) {
+                                const int kk = __clz((int)sm) >> 2;
+                                sm &= ~(0xF0000000u >> (4 * kk));
+                                s_item[ri] = (uint16_t)((sub << 9) | (col0 + 8 * wsel + kk));
+                                s_itemw[ri] = wi;
+                                ri++;
+                                wi += rec_words;
+                            }
+                        }
+                        __syncwarp();
+                        const int g = lane / VR_GROUP, gl = lane % VR_GROUP;
+                        for (uint32_t i = (uint32_t)g; i < T; i += WARP / VR_GROUP) {
+                            const uint32_t code = s_item[i], wofs = s_itemw[i];
+                            const int col = (int)(code & 511u), fi = bundle * S + (int)(code >> 9);
+                            const FsTile fti = s_ft[fi];
+                            const uint8_t *cbp = smem + off_slab + 4 * (int)fti.cbase4;
+                            const VoteRead *ents = s_vr + fti.ent0;
+                            uint32_t *rec = q_words + wofs;
+                            const int mi = (int)fti.m;
+                            if (gl == 0) {
+                                q_index[rec0 + i] = wofs;
+                                rec[0] = 2u * (uint32_t)p0 + (uint32_t)fi;
+                                rec[1] = (uint32_t)col | ((uint32_t)mi << 16);
+                                rec[2] = (uint32_t)fti.tmpl_k | ((col >= (int)fti.len ? SR_UNVOTED : 0u) << 16);
+                                rec[3] = (uint32_t)tile;
+                            }
+                            if ((fti.flags & FS_UNIFORM) && col < (int)fti.len) {
+                                // the column's place in pair.cpp:121-170 is the same for every read of a uniform family
+                                const VoteRead tvi = ents[fti.tmpl_k];
+                                const bool info = tvi.ov_len != VR_NO_OVERLAP_INFO;
+                                const int kq = col - (int)tvi.ov_own, mp = (int)tvi.ov_mate + kq;
+                                const bool inwin = info && kq >= 0 && kq < (int)tvi.ov_len;
+                                const bool mvalid = inwin && mp >= 0 && mp < (int)tvi.mate_l;
+                                const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
+                                const int soff = GCB_ALIGN4(fti.l_out) + (col >> 1), nsh = (col & 1) ? 0 : 4;
+                                const int mrel = mvalid ? 4 * ((int)tvi.mate_off4 - (int)tvi.own_off4) : 0, mpi = mvalid ? mp : 0;
+                                const int mqoff = mrel + mpi, msoff = mrel + (mvalid ? GCB_ALIGN4(tvi.mate_l) : 0) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
+                                for (int e = gl; e < mi; e += VR_GROUP) {
+                                    const uint32_t xo = ents[e].own_off4;
+                                    uint32_t ent = 0u;
+                                    if (xo != VR_NO_VOTE) {
+                                        const uint8_t *p = cbp + 4 * (int)xo;
+                                        const uint32_t ql = p[col], base = ((uint32_t)p[soff] >> nsh) & 0xFu;
+                                        const uint32_t mql = mvalid ? p[mqoff] : 0u, mbase = mvalid ? (((uint32_t)p[msoff] >> mnsh) & 0xFu) : 0u;
+                                        ent = ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
+                                    }
+                                    rec[4 + e] = ent;
+                                }
+                            } else {
+                                for (int e = gl; e < mi; e += VR_GROUP) rec[4 + e] = slow_entry(cbp, ents[e], col);
+                            }
+                        }
+                        __syncwarp();
+                    } else if (nslow > 0) {
+                        // a bundle full of slow columns: every lane emits its own
+                        const uint8_t *cbp = smem + cb;
+                        const VoteRead *ents = s_vr + ft.ent0;
+                        for (int wsel = 0; wsel < 2; wsel++) {
+                            uint32_t sm = wsel ? slow1 : slow0;
+                            while (sm != 0u) {
+                                const int kk = __clz((int)sm) >> 2;
+                                sm &= ~(0xF0000000u >> (4 * kk));
+                                const int col = col0 + 8 * wsel + kk;
+                                uint32_t *rec = q_words + wi;
+                                q_index[rec0 + ri] = wi;
+                                rec[0] = 2u * (uint32_t)p0 + (uint32_t)f;
+                                rec[1] = (uint32_t)col | ((uint32_t)ft.m << 16);
+                                rec[2] = (uint32_t)ft.tmpl_k | ((col >= len ? SR_UNVOTED : 0u) << 16);
+                                rec[3] = (uint32_t)tile;
+                                for (int e = 0; e < (int)ft.m; e++) rec[4 + e] = slow_entry(cbp, ents[e], col);
+                                ri++;
+                                wi += rec_words;
+                            }
+                        }
+                    }
+                }
+                if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
+                bundle = __shfl_sync(FULL, bundle, 0);
+                pipe_progress();
+            } while (bundle < nb);
+        }
+        __syncwarp();
+        if (lane == 0) pipe_arrive(empty + s);
+    }
+#undef GCB_LDS32
+}
+
+}  // namespace gcb

@@ -36,7 +36,8 @@ struct __align__(16) TileHdr2 {
     int32_t nfs;         // live family sides (FsTile entries at fs_tiles[2*p0 ..]); 0 = nothing for this kernel
     int32_t lanes;       // lanes per family side: the tile's widest record in 16-column chunks
     int32_t common_l;    // l_out of the first family side (mask set computed once per tile)
-    int32_t reserved[2];
+    int32_t per_bundle;  // family sides per warp pass = 32 / lanes
+    int32_t n_bundles;   // ceil(nfs / per_bundle)
 };
 static_assert(sizeof(TileHdr2) == 48, "tile header size");
 
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b
     const int64_t slab_bytes = t1.slab0 - t0.slab0;
     TileHdr2 h;
     h.out_base0 = 0; h.slab0 = t0.slab0; h.slab_bytes = 0; h.p0 = P0; h.np = NP; h.nfs = 0; h.lanes = 1; h.common_l = 0;
-    h.reserved[0] = h.reserved[1] = 0;
+    h.per_bundle = 32; h.n_bundles = 0;
     if (c0 >= c1 || NP == 0) {  // no cluster starts here / clusters without pairs emit nothing
         if (tid == 0) hdr[blockIdx.x] = h;
         return;
@@ -164,6 +165,8 @@ __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b
             h.nfs = (int32_t)total;
             h.lanes = s_lmax;
             h.common_l = s_common;
+            h.per_bundle = 32 / s_lmax;
+            h.n_bundles = ((int32_t)total + h.per_bundle - 1) / h.per_bundle;
             GCB_COUNT(0, 1);
         }
         hdr[blockIdx.x] = h;

@@ -358,6 +358,8 @@ template <typename T>
 inline T atomicXor(T *p, T v) { T old = *p; *p = old ^ v; return old; }
 template <typename T>
 inline T atomicCAS(T *p, T cmp, T v) { T old = *p; if (old == cmp) *p = v; return old; }
+template <typename T>
+inline T atomicExch(T *p, T v) { T old = *p; *p = v; return old; }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
 

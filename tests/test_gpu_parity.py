@@ -87,6 +87,17 @@ def test_staged_vote_matches_oracle(engine_cls, oracle, name, thunk):
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 
 
+@pytest.mark.parametrize("name,thunk", CASES, ids=[c[0] for c in CASES])
+def test_split_vote_matches_oracle(engine_cls, oracle, name, thunk):
+    """vote_fast_kernel (gcb_set_vote_mode 3: one CTA per tile, slow columns queued) on every case."""
+    batch, genome, opt = thunk()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        eng.set_vote_mode(3)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
+
+
 @pytest.mark.parametrize("qbytes", [1 << 14, 1 << 20])
 @pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "cfg4_40k", "edge_strict"])
 def test_slow_queue_overflow_does_not_change_results(engine_cls, oracle, name, qbytes):

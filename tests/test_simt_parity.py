@@ -135,3 +135,15 @@ def test_slow_queue_overflow_does_not_change_results(simt_lib, oracle, name, qby
         eng.set_slow_queue_bytes(qbytes)
         res = eng.cluster_by_umi(batch)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} queue {qbytes}")
+
+
+@pytest.mark.parametrize("name,thunk", PIPE_CASES, ids=[c[0] for c in PIPE_CASES])
+def test_split_vote_matches_oracle_under_simt_check(simt_lib, oracle, name, thunk):
+    """vote_fast_kernel (vote mode 3: one CTA per tile, slow columns queued for slow_columns_kernel) gives the same bytes."""
+    from gencore_b200.engine import ConsensusEngine
+    batch, genome, opt = thunk()
+    with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
+        eng.set_reference(genome)
+        eng.set_vote_mode(3)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
