@@ -206,7 +206,7 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
         if (cap_words > 0x3FFFFFF0ll) cap_words = 0x3FFFFFF0ll;
         cap_words &= ~3ll;
         if (cap_words < 64) cap_words = 64;
-        const int64_t cap_recs = cap_words / 8;
+        const int64_t cap_recs = cap_words / 12;  // the smallest record is 12 words
         GCB_RES(w_sq_count, 8 * VQ_NQ * GCB_MAX_CHUNKS);
         GCB_RES(w_sq_words, 4 * cap_words * VQ_NQ);
         GCB_RES(w_sq_index, 4 * cap_recs * VQ_NQ);
@@ -340,10 +340,10 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                     GCB_LAUNCH(vote_fast_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
                                ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
                 }
-                GCB_LAUNCH(slow_columns_kernel, dim3(VQ_NQ * VQ_SLOW_PARTS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ctx->genome, ctx->opt, sq,
-                           (const TileHdr2 *)thdr, (const FsTile *)fst);
-                GCB_LAUNCH(vote_finalize_kernel, dim3((unsigned)n_tiles), dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt,
-                           (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
+                GCB_LAUNCH(slow_columns_kernel, dim3(VQ_NQ * VQ_SLOW_PARTS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ctx->genome, ctx->opt, sq);
+                if (v.p1 > v.p0)
+                    GCB_LAUNCH(vote_finalize_kernel, dim3((unsigned)((2 * (int64_t)(v.p1 - v.p0) + VQ_FINAL_THREADS - 1) / VQ_FINAL_THREADS)),
+                               dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->opt, sq, v.p0, v.p1);
                 ctx->launches += 3;
             } else if (run_vote) {
                 GCB_LAUNCH(vote_staged_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,

@@ -54,6 +54,29 @@ constexpr int VRS_OFF_VR = VRS_OFF_FT + 32 * VS_MAX_FS;          // VoteRead[2*V
 constexpr int VRS_OFF_SLAB = (VRS_OFF_VR + 32 * VS_MAX_PAIRS + 127) & ~127;
 static_assert(16 * VR_MAX_STAGES <= VR_OFF_HDR && VRS_OFF_VR % 16 == 0 && VR_OFF_STAGE0 % 128 == 0, "ring layout");
 
+// a wait that sleeps between polls: a spinning warp takes issue slots from the warps that vote
+#ifndef GCB_SIMT_CHECK
+__device__ __forceinline__ void pipe_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    const uint32_t a = smem_u32(bar);
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(ns);
+    }
+}
+#else
+inline void pipe_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t) { pipe_wait(bar, parity); }
+#endif
+
 __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, int32_t moderate_quality, int32_t implied,
                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, int32_t n_tiles,
                                                                   int32_t n_stages, int32_t stage_bytes) {
@@ -89,7 +112,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 while (t < n_tiles && (h = hdr[t]).nfs <= 0) t += (int)gridDim.x;
             }
             const int s = k % n_stages, use = k / n_stages;
-            if (use > 0) pipe_wait(empty + s, (uint32_t)((use - 1) & 1));  // every consumer has left the stage's previous tile
+            if (use > 0) pipe_wait_backoff(empty + s, (uint32_t)((use - 1) & 1), 256u);  // every consumer has left the stage's previous tile
             uint8_t *stage = smem + VR_OFF_STAGE0 + (size_t)s * stage_bytes;
             RingStage sh;
             sh.out_base0 = cur.out_base0;
@@ -122,7 +145,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     uint16_t *s_item = (uint16_t *)(s_itemw + VR_ITEMS);
     for (int k = 0;; k++) {
         const int s = k % n_stages, use = k / n_stages;
-        pipe_wait(full + s, (uint32_t)(use & 1));
+        pipe_wait_backoff(full + s, (uint32_t)(use & 1), 64u);
         RingStage *sh = shdr + s;
         const int nfs = sh->nfs;
         if (nfs < 0) break;
@@ -135,8 +158,9 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             const FsTile *s_ft = (const FsTile *)(smem + stage_off + VRS_OFF_FT);
             const VoteRead *s_vr = (const VoteRead *)(smem + stage_off + VRS_OFF_VR);
             const int off_slab = stage_off + VRS_OFF_SLAB, off_vr = stage_off + VRS_OFF_VR;
-            uint8_t *out0 = r.out_payload + sh->out_base0;
-            const int p0 = sh->p0, tile = sh->tile;
+            const int64_t out_base0 = sh->out_base0;
+            uint8_t *out0 = r.out_payload + out_base0;
+            const int tile = sh->tile;
             const int qi = tile % VQ_NQ;
             uint32_t *q_words = sq.words + (size_t)qi * sq.cap_words;
             uint32_t *q_index = sq.index + (size_t)qi * sq.cap_recs;
@@ -217,9 +241,8 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                         dis0 |= (__funnelshift_l(C, A, msh) | (tb0 ^ __funnelshift_l(tc, ta, msh))) & om0;
                         dis1 |= (__funnelshift_l(E, C, msh) | (tb1 ^ __funnelshift_l(te, tc, msh))) & om1;
                     }
-                } else {
-                    for (int e = 0; e < mmax; e++) {
-                        if (e >= m) continue;
+                } else if (m > 0) {
+                    for (int e = 0; e < m; e++) {
                         const VoteRead v = s_vr[ft.ent0 + e];
                         if (v.own_off4 == VR_NO_VOTE || v.own_l == 0) continue;
                         const int rp0 = col0 + v.shift;
@@ -287,7 +310,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 // ---- slow columns: one reservation per bundle (records << 32 | words), then the entries
                 const int nslow = __popc(slow0) + __popc(slow1);
                 if (__any_sync(FULL, nslow > 0)) {
-                    const uint32_t rec_words = 4u + (((uint32_t)ft.m + 3u) & ~3u);
+                    const uint32_t rec_words = slow_rec_words(ft.m);
                     GCB_COUNT(3, nslow);
                     const unsigned long long mine64 = ((unsigned long long)(uint32_t)nslow << 32) | ((uint32_t)nslow * rec_words);
                     unsigned long long incl = mine64;
@@ -336,10 +359,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                             const int mi = (int)fti.m;
                             if (gl == 0) {
                                 q_index[rec0 + i] = wofs;
-                                rec[0] = 2u * (uint32_t)p0 + (uint32_t)fi;
-                                rec[1] = (uint32_t)col | ((uint32_t)mi << 16);
-                                rec[2] = (uint32_t)fti.tmpl_k | ((col >= (int)fti.len ? SR_UNVOTED : 0u) << 16);
-                                rec[3] = (uint32_t)tile;
+                                slow_write_header(rec, fti, col, out_base0 + 4 * (int64_t)fti.out4);
                             }
                             if ((fti.flags & FS_UNIFORM) && col < (int)fti.len) {
                                 // the column's place in pair.cpp:121-170 is the same for every read of a uniform family
@@ -361,10 +381,10 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                                         const uint32_t mql = mvalid ? p[mqoff] : 0u, mbase = mvalid ? (((uint32_t)p[msoff] >> mnsh) & 0xFu) : 0u;
                                         ent = ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
                                     }
-                                    rec[4 + e] = ent;
+                                    rec[SR_HDR_WORDS + e] = ent;
                                 }
                             } else {
-                                for (int e = gl; e < mi; e += VR_GROUP) rec[4 + e] = slow_entry(cbp, ents[e], col);
+                                for (int e = gl; e < mi; e += VR_GROUP) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
                             }
                         }
                         __syncwarp();
@@ -380,11 +400,8 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                                 const int col = col0 + 8 * wsel + kk;
                                 uint32_t *rec = q_words + wi;
                                 q_index[rec0 + ri] = wi;
-                                rec[0] = 2u * (uint32_t)p0 + (uint32_t)f;
-                                rec[1] = (uint32_t)col | ((uint32_t)ft.m << 16);
-                                rec[2] = (uint32_t)ft.tmpl_k | ((col >= len ? SR_UNVOTED : 0u) << 16);
-                                rec[3] = (uint32_t)tile;
-                                for (int e = 0; e < (int)ft.m; e++) rec[4 + e] = slow_entry(cbp, ents[e], col);
+                                slow_write_header(rec, ft, col, out_base0 + 4 * (int64_t)ft.out4);
+                                for (int e = 0; e < (int)ft.m; e++) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
                                 ri++;
                                 wi += rec_words;
                             }

@@ -33,22 +33,44 @@ namespace gcb {
 constexpr int VQ_NQ = 32;                      // slow-column queues; tile t uses queue t % VQ_NQ
 constexpr uint32_t VQ_INVALID = 0xFFFFFFFFu;   // index entry of a reservation that did not fit
 constexpr int VQ_SLOW_THREADS = 128;
-constexpr int VQ_SLOW_PARTS = 24;              // CTAs per queue in slow_columns_kernel
-constexpr int VQ_FINAL_THREADS = 64;
+constexpr int VQ_SLOW_PARTS = 96;              // CTAs per queue in slow_columns_kernel
+constexpr int VQ_FINAL_THREADS = 256;
 
 struct SlowQueues {
     unsigned long long *count;   // [VQ_NQ] records << 32 | words reserved so far (may run past the capacity)
-    uint32_t *words;             // [VQ_NQ][cap_words] records: 4 header words + n entries, padded to 4 words
+    uint32_t *words;             // [VQ_NQ][cap_words] records (see SR_HDR_WORDS)
     uint32_t *index;             // [VQ_NQ][cap_recs] word offset of every record inside its queue, VQ_INVALID = none
     uint32_t cap_words, cap_recs;
-    int32_t *acc;                // [2*n_pairs] per family side (fs_tiles index): diff + 65536 * mismatchInc
+    int32_t *acc;                // [2*n_pairs] per family side (2 * slot + side): diff + 65536 * mismatchInc
 };
 
-// record header: {fs_tiles index, col | n << 16, tmpl_k | flags << 16, tile}
-constexpr uint32_t SR_UNVOTED = 1u;   // column beyond the voted length: the record keeps the template's (rewritten) quality
+// record: SR_HDR_WORDS header words, then n entries (one per read of the family side), padded to a multiple of 4 words.
+// The header is self-contained (slow_columns_kernel needs no table lookup):
+//   [0] 2 * slot + side   [1] col | n << 16   [2] tmpl_k | flags << 16   [3] l_out
+//   [4..5] absolute offset of the consensus record in out_payload   [6..7] FsTile.ref_nib0
+constexpr int SR_HDR_WORDS = 8;
+constexpr uint32_t SR_UNVOTED = 1u;        // column beyond the voted length: the record keeps the template's (rewritten) quality
+constexpr uint32_t SR_REF_OK = 2u;         // FS_REF_OK
+constexpr uint32_t SR_SIMPLE_CIGAR = 4u;   // FS_SIMPLE_CIGAR
 // entry: quality | mate quality << 8 | base << 16 | mate base << 20 | state << 24 | SE_VOTES
 constexpr uint32_t SE_VOTES = 1u << 26;
 constexpr uint32_t SE_NO_INFO = 0u, SE_PLAIN = 1u, SE_MATE = 2u, SE_NO_MATE_BASE = 3u;
+
+GCB_DEV uint32_t slow_rec_words(int m) { return (uint32_t)SR_HDR_WORDS + (((uint32_t)m + 3u) & ~3u); }
+GCB_DEV void slow_write_header(uint32_t *rec, const FsTile &ft, int col, int64_t out_abs) {
+    const uint32_t side = (ft.flags & FS_SIDE1) ? 1u : 0u;
+    const uint32_t fl = (col >= (int)ft.len ? SR_UNVOTED : 0u) | ((ft.flags & FS_REF_OK) ? SR_REF_OK : 0u) |
+                        ((ft.flags & FS_SIMPLE_CIGAR) ? SR_SIMPLE_CIGAR : 0u);
+    uint4 a, c;
+    a.x = 2u * (uint32_t)ft.slot + side;
+    a.y = (uint32_t)col | ((uint32_t)ft.m << 16);
+    a.z = (uint32_t)ft.tmpl_k | (fl << 16);
+    a.w = (uint32_t)ft.l_out;
+    c.x = (uint32_t)(uint64_t)out_abs; c.y = (uint32_t)((uint64_t)out_abs >> 32);
+    c.z = (uint32_t)(uint64_t)ft.ref_nib0; c.w = (uint32_t)((uint64_t)ft.ref_nib0 >> 32);
+    ((uint4 *)rec)[0] = a;
+    ((uint4 *)rec)[1] = c;
+}
 
 #ifndef GCB_SIMT_CHECK
 template <int IMM>
@@ -132,6 +154,7 @@ __global__ void __launch_bounds__(VS_MAX_THREADS, 3) vote_fast_kernel(BatchView 
     if (tid == 0) {
         tile_barrier_init(bar);
         *s_next = 0;
+        *(int *)(smem + VS_OFF_NSLOW) = 0;
         const uint32_t vb = 32u * (uint32_t)h.np, fb = 32u * (uint32_t)nfs;
         tile_expect(bar, (uint32_t)h.slab_bytes + vb + fb);
         if (h.slab_bytes > 0) tile_copy(slab, b.payload + h.slab0, (uint32_t)h.slab_bytes, bar);
@@ -141,11 +164,8 @@ __global__ void __launch_bounds__(VS_MAX_THREADS, 3) vote_fast_kernel(BatchView 
     __syncthreads();
     tile_wait(bar, 0);
 
-    TileCtx t;  // (only the out-of-line paths use it: queue overflow)
-    t.b = &b; t.r = &r; t.gv = &gv; t.o = &o;
-    t.slab = slab; t.vr = s_vr; t.ft = s_ft; t.acc = sq.acc + 2 * (int64_t)h.p0;
-    t.out0 = r.out_payload + h.out_base0;
-
+    uint8_t *out0 = r.out_payload + h.out_base0;
+    int *s_handed = (int *)(smem + VS_OFF_NSLOW);  // the tile went to the generic kernel (queue overflow)
     const int qi = (int)(blockIdx.x % VQ_NQ);
     uint32_t *q_words = sq.words + (size_t)qi * sq.cap_words;
     uint32_t *q_index = sq.index + (size_t)qi * sq.cap_recs;
@@ -304,7 +324,7 @@ __global__ void __launch_bounds__(VS_MAX_THREADS, 3) vote_fast_kernel(BatchView 
                     slow1 = nibs_of_bytes(cm.rb[2], cm.rb[3]) & 0x11111111u;
                 }
             }
-            uint8_t *out = t.out0 + 4 * (int64_t)ft.out4;
+            uint8_t *out = out0 + 4 * (int64_t)ft.out4;
 #pragma unroll
             for (int k = 0; k < 4; k++)
                 if (col0 + 4 * k < qbytes) *(uint32_t *)(out + col0 + 4 * k) = oq[k] & cm.rb[k];
@@ -314,7 +334,7 @@ __global__ void __launch_bounds__(VS_MAX_THREADS, 3) vote_fast_kernel(BatchView 
         // ---- slow columns (one bit per column in slow0 / slow1): one reservation per bundle, every lane emits its own
         const int nslow = __popc(slow0) + __popc(slow1);
         if (__any_sync(FULL, nslow > 0)) {
-            const uint32_t rec_words = 4u + (((uint32_t)ft.m + 3u) & ~3u);
+            const uint32_t rec_words = slow_rec_words(ft.m);
             const uint32_t my_words = (uint32_t)nslow * rec_words;
             GCB_COUNT(3, nslow);
             // exclusive scans of the record counts and of the words over the warp (packed: records << 32 | words)
@@ -327,33 +347,31 @@ __global__ void __launch_bounds__(VS_MAX_THREADS, 3) vote_fast_kernel(BatchView 
             unsigned long long base64 = 0ull;
             if (lane == 0) base64 = atomicAdd(sq.count + qi, total);
             base64 = __shfl_sync(FULL, base64, 0);
-            const uint32_t rec0 = (uint32_t)(base64 >> 32), word0 = (uint32_t)base64;
-            const bool fits = (unsigned long long)rec0 + (uint32_t)(total >> 32) <= sq.cap_recs &&
-                              (unsigned long long)word0 + (uint32_t)total <= sq.cap_words;
+            const uint32_t rec0 = (uint32_t)(base64 >> 32), word0 = (uint32_t)base64, T = (uint32_t)(total >> 32);
+            const bool fits = (unsigned long long)rec0 + T <= sq.cap_recs && (unsigned long long)word0 + (uint32_t)total <= sq.cap_words;
             uint32_t ri = rec0 + (uint32_t)((incl - mine64) >> 32), wi = word0 + (uint32_t)(incl - mine64);
-            if (nslow > 0) {
+            if (!fits) {
+                // the queue is full: the generic kernel redoes the whole tile from the payload (it runs after
+                // slow_columns_kernel and vote_finalize_kernel); the reserved index entries are marked unused
+                for (uint32_t i = (uint32_t)lane; i < T; i += WARP)
+                    if (rec0 + i < sq.cap_recs) q_index[rec0 + i] = VQ_INVALID;
+                if (lane == 0 && atomicExch(s_handed, 1) == 0) {
+                    ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~(int32_t)blockIdx.x;
+                    GCB_COUNT(1, 1);
+                }
+            } else if (nslow > 0) {
                 const uint8_t *cbp = smem + cb;
                 const VoteRead *ents = s_vr + ft.ent0;
-                const uint32_t fsid = 2u * (uint32_t)h.p0 + (uint32_t)f;
                 for (int wsel = 0; wsel < 2; wsel++) {
                     uint32_t sm = wsel ? slow1 : slow0;
                     while (sm != 0u) {
                         const int k = __clz((int)sm) >> 2;
                         sm &= ~(0xF0000000u >> (4 * k));
                         const int col = col0 + 8 * wsel + k;
-                        if (!fits) {  // the queue is full: decide the column here (this lane owns the chunk's words)
-                            if (ri < sq.cap_recs) q_index[ri] = VQ_INVALID;
-                            ri++;
-                            slow_column_general(t, f, col);
-                            continue;
-                        }
                         uint32_t *rec = q_words + wi;
                         q_index[ri] = wi;
-                        rec[0] = fsid;
-                        rec[1] = (uint32_t)col | ((uint32_t)ft.m << 16);
-                        rec[2] = (uint32_t)ft.tmpl_k | ((col >= len ? SR_UNVOTED : 0u) << 16);
-                        rec[3] = (uint32_t)blockIdx.x;
-                        for (int e = 0; e < (int)ft.m; e++) rec[4 + e] = slow_entry(cbp, ents[e], col);
+                        slow_write_header(rec, ft, col, h.out_base0 + 4 * (int64_t)ft.out4);
+                        for (int e = 0; e < (int)ft.m; e++) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
                         ri++;
                         wi += rec_words;
                     }
@@ -396,15 +414,17 @@ __device__ __noinline__ void slow_record_wide(const gcb_options &o, const uint32
 
 // group.cpp:376-525 for one queued column
 GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeView &gv, const gcb_options &o, const SlowQueues &sq,
-                         const TileHdr2 *hdr, const FsTile *fs_tiles, const uint32_t *rec) {
-    const uint32_t fsid = rec[0], w1 = rec[1], w2 = rec[2], tile = rec[3];
+                         const uint32_t *rec) {
+    const uint4 ha = ((const uint4 *)rec)[0], hc = ((const uint4 *)rec)[1];
+    const uint32_t fsid = ha.x, w1 = ha.y, w2 = ha.z;
     const int col = (int)(w1 & 0xFFFFu), n = (int)(w1 >> 16), tmpl_k = (int)(w2 & 0xFFFFu);
-    const uint32_t *ents = rec + 4;
-    const FsTile ft = fs_tiles[fsid];
-    const int side = fs_side(ft);
-    const int qbytes = GCB_ALIGN4(ft.l_out);
-    uint8_t *out = r.out_payload + hdr[tile].out_base0 + 4 * (int64_t)ft.out4;
-    if ((w2 >> 16) & SR_UNVOTED) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
+    const uint32_t flags = w2 >> 16;
+    const uint32_t *ents = rec + SR_HDR_WORDS;
+    const int side = (int)(fsid & 1u);
+    const int qbytes = GCB_ALIGN4((int)ha.w);
+    uint8_t *out = r.out_payload + (int64_t)(((uint64_t)hc.y << 32) | hc.x);
+    const int64_t ref_nib0 = (int64_t)(((uint64_t)hc.w << 32) | hc.z);
+    if (flags & SR_UNVOTED) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
         int obase = 0, oqual = 0, sc;
         slow_decode(o, ents[tmpl_k], side, obase, oqual, sc);
         out[col] = (uint8_t)oqual;
@@ -457,13 +477,13 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
         // the record's base before the vote: the template's own (pair.cpp rewrites qualities, never bases)
         const int obase = (int)((ents[tmpl_k] >> 16) & 0xFu);
         int ref4 = 0;
-        if (ft.flags & FS_REF_OK) {  // group.cpp:430-439
+        if (flags & SR_REF_OK) {  // group.cpp:430-439
             int refpos = col;
-            if (!(ft.flags & FS_SIMPLE_CIGAR)) {
-                const gcb_read_desc od = b.reads[r.groups[ft.slot].tmpl_read[side]];
+            if (!(flags & SR_SIMPLE_CIGAR)) {
+                const gcb_read_desc od = b.reads[r.groups[fsid >> 1].tmpl_read[side]];
                 refpos = get_ref_offset(b.cigar + od.cigar_off, od.n_cigar, col);
             }
-            const int64_t nib = ft.ref_nib0 + refpos;
+            const int64_t nib = ref_nib0 + refpos;
             if (refpos >= 0 && nib >= 0 && (nib >> 1) < gv.packed_bytes) {  // the bound only guards malformed CIGARs
                 const uint8_t two = gv.packed4[nib >> 1];
                 ref4 = genome_nibble_to_bam((nib & 1) ? (two >> 4) : (two & 0xF));
@@ -497,7 +517,7 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
                 if (obase == ref4) d_mm = 1;
                 else if (co.base == ref4) d_mm = -1;
             }
-            atomicAdd(sq.acc + fsid, 1 + d_mm * 65536);
+            atomicAdd(sq.acc + fsid, 1 + d_mm * 65536);  // (fsid = 2 * slot + side)
             const int byte = col >> 1;
             const unsigned delta = ((unsigned)(obase ^ co.base) & 0xFu) << ((col & 1) ? 0 : 4);
             atomicXor((unsigned *)(out + qbytes + (byte & ~3)), delta << (8 * (byte & 3)));
@@ -507,8 +527,7 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
     out[col] = (uint8_t)new_qual;
 }
 
-__global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView b, ResultView r, GenomeView gv, gcb_options o, SlowQueues sq,
-                                                                       const TileHdr2 *hdr, const FsTile *fs_tiles) {
+__global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView b, ResultView r, GenomeView gv, gcb_options o, SlowQueues sq) {
     const int qi = (int)(blockIdx.x % VQ_NQ), part = (int)(blockIdx.x / VQ_NQ), nparts = (int)(gridDim.x / VQ_NQ);
     const uint32_t reserved = (uint32_t)(sq.count[qi] >> 32);
     const uint32_t nrec = reserved < sq.cap_recs ? reserved : sq.cap_recs;
@@ -517,36 +536,38 @@ __global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView
     for (uint32_t i = (uint32_t)part * blockDim.x + threadIdx.x; i < nrec; i += (uint32_t)nparts * blockDim.x) {
         const uint32_t off = q_index[i];
         if (off == VQ_INVALID) continue;
-        slow_record(b, r, gv, o, sq, hdr, fs_tiles, q_words + off);
+        slow_record(b, r, gv, o, sq, q_words + off);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// group.cpp:526-566 per family side once all of its columns are decided: diff, mismatchInc, rollback
-__global__ void __launch_bounds__(VQ_FINAL_THREADS) vote_finalize_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o,
-                                                                         const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq) {
-    const TileHdr2 h = hdr[blockIdx.x];
-    if (h.nfs == 0) return;
-    const FsTile *fts = fs_tiles + 2 * (int64_t)h.p0;
-    const int32_t *acc = sq.acc + 2 * (int64_t)h.p0;
-    for (int f = (int)threadIdx.x; f < h.nfs; f += (int)blockDim.x) {
-        const int a = acc[f];
-        if (a == 0) continue;  // diff and mismatchInc stay as select_template_kernel left them: 0
-        const FsTile ft = fts[f];
-        if (ft.mode == SIDE_NONE) continue;
-        const int diff = a & 0xFFFF, mm = (a - diff) >> 16;
-        if (mm > 5) {  // the template's bases and (rewritten) qualities, read from the payload itself
-            TileCtx t;
-            t.b = &b; t.r = &r; t.gv = &gv; t.o = &o;
-            t.slab = b.payload + h.slab0; t.vr = ws.vote_reads + 2 * (int64_t)h.p0; t.ft = fts; t.acc = nullptr;
-            t.out0 = r.out_payload + h.out_base0;
-            rollback_record(t, f);
+// group.cpp:526-566 per family side once all of its columns are decided: diff, mismatchInc, rollback.  One thread per
+// (slot, side); family sides that changed no base keep the zeros select_template_kernel left.
+__global__ void __launch_bounds__(VQ_FINAL_THREADS) vote_finalize_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o, SlowQueues sq,
+                                                                         int32_t p0, int32_t p1) {
+    const int64_t i = 2 * (int64_t)p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * (int64_t)p1) return;
+    const int a = sq.acc[i];
+    if (a == 0) return;
+    const int diff = a & 0xFFFF, mm = (a - diff) >> 16;
+    const int slot = (int)(i >> 1), side = (int)(i & 1);
+    gcb_group_result *gr = r.groups + slot;
+    if (mm > 5) {  // the template's bases and (rewritten) qualities, read from the payload itself
+        const FsDesc d = ws.fs_desc[i];
+        const VoteRead tv = ws.vote_reads[2 * (int64_t)d.mb + (int64_t)side * d.m + d.tmpl_k];
+        const uint8_t *cb = b.payload + ws.slab_off[d.c];
+        uint8_t *out = r.out_payload + gr->out_off[side];
+        const int l_out = d.l_out, qbytes = GCB_ALIGN4(l_out);
+        const uint8_t *tseq = cb + 4 * (int)tv.own_off4 + qbytes;
+        for (int col = 0; col < l_out; col++) {
+            int base, qual = 0, sc;
+            fetch_ent(cb, tv, col, side, o, base, qual, sc);
+            out[col] = (uint8_t)qual;
         }
-        gcb_group_result *gr = r.groups + ft.slot;
-        const int side = fs_side(ft);
-        gr->diff[side] = diff;
-        gr->mismatch_inc[side] = mm;
+        for (int k = 0; k < (l_out + 1) >> 1; k++) out[qbytes + k] = tseq[k];
     }
+    gr->diff[side] = diff;
+    gr->mismatch_inc[side] = mm;
 }
 
 }  // namespace gcb
