@@ -51,7 +51,8 @@ struct gcb_ctx {
     int vote_mode = GCB_VOTE_RING;                  // GCB_VOTE_TILED / GCB_VOTE_PIPELINED / GCB_VOTE_STAGED / GCB_VOTE_SPLIT
     int64_t slow_queue_bytes = 0;                   // 0 = sized from the payload
     uint32_t sq_cap_words = 0, sq_cap_recs = 0;     // per queue
-    int vote_threads = 256;                         // threads per CTA of vote_staged_kernel
+    int vote_threads = 256;                         // threads per CTA of vote_staged_kernel / vote_fast_kernel
+    int ring_threads = 512;                         // threads per CTA of vote_ring_kernel (512 or 768)
     int n_sms = 148;
     // device mirror of a host batch / result (gcb_consensus_batch)
     DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
@@ -333,9 +334,14 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                 if (v.p1 > v.p0) GCB_CUDA(ctx, cudaMemsetAsync(sq.acc + 2 * (size_t)v.p0, 0, 8 * (size_t)(v.p1 - v.p0), stream));
                 if (plan.ring) {
                     const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
-                    GCB_LAUNCH(vote_ring_kernel, dim3(ring_grid), dim3(VR_THREADS), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
-                               fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
-                               plan.stage_bytes);
+                    if (ctx->ring_threads == 768)
+                        GCB_LAUNCH(vote_ring_kernel<768>, dim3(ring_grid), dim3(768), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
+                                   fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
+                                   plan.stage_bytes);
+                    else
+                        GCB_LAUNCH(vote_ring_kernel<512>, dim3(ring_grid), dim3(512), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
+                                   fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
+                                   plan.stage_bytes);
                 } else {
                     GCB_LAUNCH(vote_fast_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
                                ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
@@ -429,7 +435,8 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
         cudaFuncSetAttribute(vote_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(vote_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(vote_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        cudaFuncSetAttribute(vote_ring_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(vote_ring_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         gcb_destroy(ctx);
         return GCB_ERR_CUDA;
     }
@@ -696,7 +703,12 @@ int gcb_set_vote_mode(gcb_ctx *ctx, int mode) {
 }
 
 int gcb_set_vote_threads(gcb_ctx *ctx, int threads) {
-    if (!ctx || threads < WARP || threads > VS_MAX_THREADS || (threads % WARP)) return GCB_ERR_ARG;
+    if (!ctx) return GCB_ERR_ARG;
+    if (threads == 512 || threads == 768) {  // the ring kernel's two instantiations
+        ctx->ring_threads = threads;
+        return GCB_OK;
+    }
+    if (threads < WARP || threads > VS_MAX_THREADS || (threads % WARP)) return GCB_ERR_ARG;
     ctx->vote_threads = threads;
     return GCB_OK;
 }

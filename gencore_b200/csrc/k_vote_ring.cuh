@@ -23,9 +23,8 @@
 
 namespace gcb {
 
-constexpr int VR_THREADS = 512;
-constexpr int VR_WARPS = VR_THREADS / WARP;
-constexpr int VR_CONSUMERS = VR_WARPS - 1;
+constexpr int VR_MAX_THREADS = 768;           // the kernel is instantiated for 512 and 768 threads (128 / 85 registers)
+constexpr int VR_WARPS = VR_MAX_THREADS / WARP;
 constexpr int VR_MAX_STAGES = 6;
 constexpr int VR_ITEMS = 64;      // sparse slow columns of one bundle that are emitted cooperatively
 constexpr int VR_GROUP = 8;       // lanes per slow column in the cooperative emission
@@ -54,7 +53,7 @@ constexpr int VRS_OFF_VR = VRS_OFF_FT + 32 * VS_MAX_FS;          // VoteRead[2*V
 constexpr int VRS_OFF_SLAB = (VRS_OFF_VR + 32 * VS_MAX_PAIRS + 127) & ~127;
 static_assert(16 * VR_MAX_STAGES <= VR_OFF_HDR && VRS_OFF_VR % 16 == 0 && VR_OFF_STAGE0 % 128 == 0, "ring layout");
 
-// a wait that sleeps between polls: a spinning warp takes issue slots from the warps that vote
+// a wait that lets the hardware suspend the thread between polls (a spinning warp takes issue slots from the warps that vote)
 #ifndef GCB_SIMT_CHECK
 __device__ __forceinline__ void pipe_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns) {
     const uint32_t a = smem_u32(bar);
@@ -63,21 +62,21 @@ __device__ __forceinline__ void pipe_wait_backoff(uint64_t *bar, uint32_t parity
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(a), "r"(parity)
+            : "r"(a), "r"(parity), "r"(ns)
             : "memory");
         if (done) return;
-        __nanosleep(ns);
     }
 }
 #else
 inline void pipe_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t) { pipe_wait(bar, parity); }
 #endif
 
-__global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, int32_t moderate_quality, int32_t implied,
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, int32_t moderate_quality, int32_t implied,
                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, int32_t n_tiles,
                                                                   int32_t n_stages, int32_t stage_bytes) {
     GCB_DYN_SMEM(smem);
@@ -89,7 +88,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
             pipe_init(full + s, 1);
-            pipe_init(empty + s, VR_CONSUMERS);  // every consumer warp arrives once when it leaves the stage's tile
+            pipe_init(empty + s, NT / WARP - 1);  // every consumer warp arrives once when it leaves the stage's tile
         }
         pipe_fence_init();
     }
@@ -112,7 +111,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 while (t < n_tiles && (h = hdr[t]).nfs <= 0) t += (int)gridDim.x;
             }
             const int s = k % n_stages, use = k / n_stages;
-            if (use > 0) pipe_wait_backoff(empty + s, (uint32_t)((use - 1) & 1), 256u);  // every consumer has left the stage's previous tile
+            if (use > 0) pipe_wait_backoff(empty + s, (uint32_t)((use - 1) & 1), 2000u);  // every consumer has left the stage's previous tile
             uint8_t *stage = smem + VR_OFF_STAGE0 + (size_t)s * stage_bytes;
             RingStage sh;
             sh.out_base0 = cur.out_base0;
@@ -143,18 +142,18 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     const uint32_t sbase = smem_base(smem);
     uint32_t *s_itemw = (uint32_t *)(smem + VR_OFF_ITEMS + VR_ITEM_BYTES * warp);
     uint16_t *s_item = (uint16_t *)(s_itemw + VR_ITEMS);
-    for (int k = 0;; k++) {
-        const int s = k % n_stages, use = k / n_stages;
-        pipe_wait_backoff(full + s, (uint32_t)(use & 1), 64u);
+    int s = 0, stage_off = VR_OFF_STAGE0;
+    uint32_t par = 0u;
+    for (;;) {
+        pipe_wait_backoff(full + s, par, 1000u);
         RingStage *sh = shdr + s;
         const int nfs = sh->nfs;
         if (nfs < 0) break;
         const int nb = sh->n_bundles;
-        int bundle = 0;
-        if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
+        int bundle = nb;
+        if (lane == 0 && *(volatile int32_t *)&sh->next_bundle < nb) bundle = atomicAdd(&sh->next_bundle, 1);  // (no atomic on a drained tile)
         bundle = __shfl_sync(FULL, bundle, 0);
         if (bundle < nb) {
-            const int stage_off = VR_OFF_STAGE0 + s * stage_bytes;
             const FsTile *s_ft = (const FsTile *)(smem + stage_off + VRS_OFF_FT);
             const VoteRead *s_vr = (const VoteRead *)(smem + stage_off + VRS_OFF_VR);
             const int off_slab = stage_off + VRS_OFF_SLAB, off_vr = stage_off + VRS_OFF_VR;
@@ -415,6 +414,13 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         }
         __syncwarp();
         if (lane == 0) pipe_arrive(empty + s);
+        s++;
+        stage_off += stage_bytes;
+        if (s == n_stages) {
+            s = 0;
+            stage_off = VR_OFF_STAGE0;
+            par ^= 1u;
+        }
     }
 #undef GCB_LDS32
 }

@@ -219,7 +219,8 @@ int gcb_set_vote_mode(gcb_ctx *ctx, int mode);
  * decided inside the fast kernel; results do not depend on it. */
 int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes);
 
-/* Tuning knob of vote modes 2 and 3: threads per CTA (a multiple of 32, at most 256; default 256).  Results do not depend on it. */
+/* Tuning knob: threads per CTA of vote modes 2 and 3 (a multiple of 32, at most 256; default 256), or of the ring kernel of
+ * mode 4 (512, the default, or 768).  Results do not depend on it. */
 int gcb_set_vote_threads(gcb_ctx *ctx, int threads);
 
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */

@@ -110,12 +110,13 @@ def test_slow_queue_overflow_does_not_change_results(engine_cls, oracle, name, q
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} queue {qbytes}")
 
 
-@pytest.mark.parametrize("threads", [128, 192])
+@pytest.mark.parametrize("mode,threads", [(2, 128), (3, 192), (4, 768)])
 @pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "cfg4_40k"])
-def test_staged_vote_thread_count_does_not_change_results(engine_cls, oracle, name, threads):
+def test_vote_thread_count_does_not_change_results(engine_cls, oracle, name, mode, threads):
     batch, genome, opt = dict(CASES)[name]()
     with engine_cls(opt, 0) as eng:
         eng.set_reference(genome)
+        eng.set_vote_mode(mode)
         eng.set_vote_threads(threads)
         res = eng.cluster_by_umi(batch)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} threads {threads}")

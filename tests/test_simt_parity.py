@@ -100,13 +100,14 @@ def test_tiled_vote_matches_oracle_under_simt_check(simt_lib, oracle, name, thun
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 
 
-@pytest.mark.parametrize("threads", [64, 192])
+@pytest.mark.parametrize("mode,threads", [(2, 64), (3, 192), (4, 768)])
 @pytest.mark.parametrize("name", ["cfg2_1500", "ragged_duplex_2", "golden_cfg4_600"])
-def test_staged_vote_thread_count_does_not_change_results(simt_lib, oracle, name, threads):
+def test_vote_thread_count_does_not_change_results(simt_lib, oracle, name, mode, threads):
     from gencore_b200.engine import ConsensusEngine
     batch, genome, opt = dict(CASES)[name]()
     with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
         eng.set_reference(genome)
+        eng.set_vote_mode(mode)
         eng.set_vote_threads(threads)
         res = eng.cluster_by_umi(batch)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} threads {threads}")
