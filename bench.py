@@ -247,9 +247,15 @@ def b200_arm(args):
     assert eng.batch_status() == 0, "device error flag raised during warm-up"
     if args.sweep and rank == 0:  # tuning aid: stage times of other (vote mode, threads) settings, to stderr
         for item in args.sweep.split(","):
-            mode_s, thr_s = item.split(":")
+            parts = item.split(":")  # mode:threads[:ablate[:window_shift]]
+            mode_s, thr_s = parts[0], parts[1]
             eng.set_vote_mode(int(mode_s))
             eng.set_vote_threads(int(thr_s))
+            eng.set_debug(1, int(parts[2]) if len(parts) > 2 else 0)
+            eng.set_debug(2, int(parts[3]) if len(parts) > 3 else 0)
+            if len(parts) > 3:  # the tile directory depends on the window: rebuild it
+                eng.cluster_by_umi_device(db.struct, dr.struct, STAGE_UMI_GROUP, stream)
+                eng.cluster_by_umi_device(db.struct, dr.struct, STAGE_SELECT_TEMPLATE, stream)
             sw_stages = [STAGE_SCORE_VOTE] if int(mode_s) == 0 else [STAGE_VOTE_PREP_ONLY, STAGE_VOTE_ONLY]
             for _ in range(3):
                 for st in sw_stages:
@@ -263,9 +269,14 @@ def b200_arm(args):
                 ev[k][len(sw_stages)].record(tstream)
             torch.cuda.synchronize()
             ms = [float(np.mean([ev[k][q].elapsed_time(ev[k][q + 1]) for k in range(n_sw)])) for q in range(len(sw_stages))]
-            sys.stderr.write("sweep mode=%s threads=%s stage_ms=%s\n" % (mode_s, thr_s, ["%.4f" % x for x in ms]))
+            sys.stderr.write("sweep %s stage_ms=%s\n" % (item, ["%.4f" % x for x in ms]))
         eng.set_vote_mode(args.vote_mode)
         eng.set_vote_threads(args.vote_threads)
+        eng.set_debug(1, 0)
+        eng.set_debug(2, 0)
+        if args.sweep_only:
+            eng.close()
+            return
         step()
         barrier()
     res_host = dr.to_host()
@@ -370,6 +381,7 @@ def main():
                     help="0 = one CTA per tile with its own prologue, 1 = persistent pipelined, 2 = staged, 3 = split fast/slow, "
                          "4 = split with the fast kernel as a persistent ring (default)")
     ap.add_argument("--vote-threads", type=int, default=256, help="threads per CTA of the staged vote kernel")
+    ap.add_argument("--sweep-only", action="store_true", help="stop after --sweep")
     ap.add_argument("--sweep", default="", help="tuning aid: comma-separated mode:threads settings whose vote stage times go to stderr")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per vote launch from an ncu capture (profiles/)")
     args = ap.parse_args()

@@ -4,6 +4,7 @@
 //   umi_group_kernel -> select_template_kernel -> scan_local/scan_blocks -> vote_tiled_kernel
 //   (-> score_vote_kernel for the tiles that do not fit the tiled kernel's tables) -> duplex_kernel
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -53,6 +54,8 @@ struct gcb_ctx {
     uint32_t sq_cap_words = 0, sq_cap_recs = 0;     // per queue
     int vote_threads = 256;                         // threads per CTA of vote_staged_kernel / vote_fast_kernel
     int ring_threads = 512;                         // threads per CTA of vote_ring_kernel (512 or 768)
+    int ring_window_shift = 0;                      // 0 = chosen by plan_tiles; 14 / 15 = forced (tuning)
+    int ablate = 0;                                 // profiling only (GCB_ABLATE): parts of the ring kernel switched off
     int n_sms = 148;
     // device mirror of a host batch / result (gcb_consensus_batch)
     DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
@@ -110,7 +113,7 @@ struct TilePlan {
     int32_t split;                             // vote_fast_kernel + slow_columns_kernel + vote_finalize_kernel
     int32_t ring;                              // vote_ring_kernel instead of vote_fast_kernel (n_stages, stage_bytes)
 };
-TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode) {
+TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode, int ring_window_shift = 0) {
     const int32_t KB = 1024, budget = 227 * KB;
     int32_t maxc = max_cluster_bytes > 0 ? ((max_cluster_bytes + 127) & ~127) : 16 * KB;
     TilePlan p;
@@ -130,6 +133,7 @@ TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode) {
     }
     if (vote_mode == GCB_VOTE_RING) {  // one CTA per SM, a ring of whole tiles: 32 KB windows if three stages fit, else 16 KB
         for (int shift = 15; shift >= 14; shift--) {
+            if (ring_window_shift && shift != ring_window_shift) continue;
             p.window_shift = shift;
             p.window = 1 << shift;
             p.slab_cap = p.window + maxc;
@@ -337,11 +341,11 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                     if (ctx->ring_threads == 768)
                         GCB_LAUNCH(vote_ring_kernel<768>, dim3(ring_grid), dim3(768), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
                                    fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
-                                   plan.stage_bytes);
+                                   plan.stage_bytes, ctx->ablate);
                     else
                         GCB_LAUNCH(vote_ring_kernel<512>, dim3(ring_grid), dim3(512), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
                                    fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
-                                   plan.stage_bytes);
+                                   plan.stage_bytes, ctx->ablate);
                 } else {
                     GCB_LAUNCH(vote_fast_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
                                ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
@@ -440,6 +444,8 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
         gcb_destroy(ctx);
         return GCB_ERR_CUDA;
     }
+    if (const char *e = getenv("GCB_ABLATE")) ctx->ablate = atoi(e);                      // profiling only: wrong results
+    if (const char *e = getenv("GCB_RING_WINDOW_SHIFT")) ctx->ring_window_shift = atoi(e);  // tuning only: same results
     *out = ctx;
     return GCB_OK;
 }
@@ -512,7 +518,7 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
         return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch_device: bad sizes or alignment (payload 16 B, payload_bytes % 16, out_payload 4 B)");
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : ctx->stream;
     GCB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const TilePlan plan = plan_tiles(batch->max_cluster_bytes, ctx->vote_mode);
+    const TilePlan plan = plan_tiles(batch->max_cluster_bytes, ctx->vote_mode, ctx->ring_window_shift);
     const int64_t n_tiles = (batch->payload_bytes + plan.window - 1) / plan.window;
     Workspace ws;
     int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, batch->payload_bytes, ws);
@@ -583,7 +589,7 @@ int gcb_consensus_batch(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *hr) {
     if (K > GCB_MAX_CHUNKS) K = GCB_MAX_CHUNKS;
     if (K < 1) K = 1;
     if ((int64_t)K > (int64_t)nc) K = nc > 0 ? (int)nc : 1;
-    const TilePlan plan = plan_tiles(hb->max_cluster_bytes, ctx->vote_mode);
+    const TilePlan plan = plan_tiles(hb->max_cluster_bytes, ctx->vote_mode, ctx->ring_window_shift);
     ViewRange view[GCB_MAX_CHUNKS];
     {
         int32_t c_prev = 0;
@@ -716,6 +722,14 @@ int gcb_set_vote_threads(gcb_ctx *ctx, int threads) {
 int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes) {
     if (!ctx || bytes < 16) return GCB_ERR_ARG;
     ctx->chunk_bytes = bytes;
+    return GCB_OK;
+}
+
+int gcb_set_debug(gcb_ctx *ctx, int key, int value) {
+    if (!ctx) return GCB_ERR_ARG;
+    if (key == 1) ctx->ablate = value;                 // profiling only: wrong results
+    else if (key == 2) ctx->ring_window_shift = value;  // tuning only: same results
+    else return GCB_ERR_ARG;
     return GCB_OK;
 }
 

@@ -46,7 +46,8 @@ constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MA
 constexpr int VR_OFF_HDR = 128;                                  // RingStage[VR_MAX_STAGES]
 constexpr int VR_OFF_ITEMS = VR_OFF_HDR + 64 * VR_MAX_STAGES;    // per warp: uint32 word offsets[VR_ITEMS], uint16 codes[VR_ITEMS]
 constexpr int VR_ITEM_BYTES = 6 * VR_ITEMS;
-constexpr int VR_OFF_STAGE0 = (VR_OFF_ITEMS + VR_ITEM_BYTES * VR_WARPS + 127) & ~127;
+constexpr int VR_OFF_HCACHE = (VR_OFF_ITEMS + VR_ITEM_BYTES * VR_WARPS + 15) & ~15;  // TileHdr2[32]: the producer's next tiles
+constexpr int VR_OFF_STAGE0 = (VR_OFF_HCACHE + 48 * WARP + 127) & ~127;
 // inside a stage
 constexpr int VRS_OFF_FT = 0;                                    // FsTile[VS_MAX_FS]
 constexpr int VRS_OFF_VR = VRS_OFF_FT + 32 * VS_MAX_FS;          // VoteRead[2*VS_MAX_PAIRS]
@@ -78,7 +79,9 @@ inline void pipe_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t) { pipe_w
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, int32_t moderate_quality, int32_t implied,
                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, int32_t n_tiles,
-                                                                  int32_t n_stages, int32_t stage_bytes) {
+                                                                  int32_t n_stages, int32_t stage_bytes, int32_t ablate) {
+    // `ablate` (profiling only, 0 in production; results are wrong otherwise): 1 = no slow-column emission, 2 = no read loop,
+    // 4 = no record stores, 8 = no bundle work at all
     GCB_DYN_SMEM(smem);
     uint64_t *full = (uint64_t *)(smem + VR_OFF_FULL);
     uint64_t *empty = (uint64_t *)(smem + VR_OFF_EMPTY);
@@ -95,43 +98,56 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
     __syncthreads();
 
     if (warp == 0) {
-        // ---- producer: one thread, up to n_stages tiles ahead of the consumers
-        if (lane != 0) return;
-        int t = (int)blockIdx.x;
-        TileHdr2 h;
-        h.nfs = 0;
-        while (t < n_tiles && (h = hdr[t]).nfs <= 0) t += (int)gridDim.x;
+        // ---- producer: lane 0 fills the stages, up to n_stages tiles ahead of the consumers; the whole warp fetches the
+        // headers of this CTA's next 32 tiles at once, so that no tile waits for a header on its way from global memory
+        TileHdr2 *hcache = (TileHdr2 *)(smem + VR_OFF_HCACHE);
         int k = 0;
-        for (;; k++) {
-            const bool have = t < n_tiles;
-            const TileHdr2 cur = h;
-            const int cur_t = t;
-            if (have) {  // the next tile's header is on its way while this one waits for its stage
-                t += (int)gridDim.x;
-                while (t < n_tiles && (h = hdr[t]).nfs <= 0) t += (int)gridDim.x;
+        for (int64_t base = (int64_t)blockIdx.x; base < n_tiles; base += (int64_t)WARP * gridDim.x) {
+            const int64_t mine_t = base + (int64_t)lane * gridDim.x;
+            if (mine_t < n_tiles) hcache[lane] = hdr[mine_t];
+            __syncwarp();
+            if (lane == 0) {
+                for (int i = 0; i < WARP; i++) {
+                    const int64_t t = base + (int64_t)i * gridDim.x;
+                    if (t >= n_tiles) break;
+                    const TileHdr2 cur = hcache[i];
+                    if (cur.nfs <= 0) continue;  // nothing for this kernel here (empty tile, or the generic kernel has it)
+                    const int s = k % n_stages, use = k / n_stages;
+                    if (use > 0) pipe_wait_backoff(empty + s, (uint32_t)((use - 1) & 1), 2000u);  // every consumer has left the stage's previous tile
+                    uint8_t *stage = smem + VR_OFF_STAGE0 + (size_t)s * stage_bytes;
+                    RingStage sh;
+                    sh.out_base0 = cur.out_base0;
+                    sh.nfs = cur.nfs;
+                    sh.lanes = cur.lanes; sh.per_bundle = cur.per_bundle; sh.n_bundles = cur.n_bundles; sh.common_l = cur.common_l;
+                    sh.p0 = cur.p0; sh.tile = (int32_t)t;
+                    sh.next_bundle = 0;
+                    sh.handed_over = 0;
+                    sh.pad[0] = sh.pad[1] = sh.pad[2] = sh.pad[3] = sh.pad[4] = 0;
+                    shdr[s] = sh;
+                    const uint32_t slab_bytes = (uint32_t)cur.slab_bytes, vr_bytes = 32u * (uint32_t)cur.np, ft_bytes = 32u * (uint32_t)cur.nfs;
+                    pipe_expect(full + s, slab_bytes + vr_bytes + ft_bytes);
+                    if (slab_bytes > 0) tile_copy(stage + VRS_OFF_SLAB, b.payload + cur.slab0, slab_bytes, full + s);
+                    tile_copy(stage + VRS_OFF_VR, ws.vote_reads + 2 * (int64_t)cur.p0, vr_bytes, full + s);
+                    tile_copy(stage + VRS_OFF_FT, fs_tiles + 2 * (int64_t)cur.p0, ft_bytes, full + s);
+                    pipe_commit(full + s);
+                    k++;
+                }
             }
+            __syncwarp();
+        }
+        if (lane == 0) {  // the end marker: the phase completes with this arrival alone
             const int s = k % n_stages, use = k / n_stages;
-            if (use > 0) pipe_wait_backoff(empty + s, (uint32_t)((use - 1) & 1), 2000u);  // every consumer has left the stage's previous tile
-            uint8_t *stage = smem + VR_OFF_STAGE0 + (size_t)s * stage_bytes;
+            if (use > 0) pipe_wait_backoff(empty + s, (uint32_t)((use - 1) & 1), 2000u);
             RingStage sh;
-            sh.out_base0 = cur.out_base0;
-            sh.nfs = have ? cur.nfs : -1;
-            sh.lanes = cur.lanes; sh.per_bundle = cur.per_bundle; sh.n_bundles = cur.n_bundles; sh.common_l = cur.common_l;
-            sh.p0 = cur.p0; sh.tile = cur_t;
+            sh.out_base0 = 0;
+            sh.nfs = -1;
+            sh.lanes = 1; sh.per_bundle = 32; sh.n_bundles = 0; sh.common_l = 0;
+            sh.p0 = 0; sh.tile = 0;
             sh.next_bundle = 0;
             sh.handed_over = 0;
             sh.pad[0] = sh.pad[1] = sh.pad[2] = sh.pad[3] = sh.pad[4] = 0;
             shdr[s] = sh;
-            if (!have) {  // the end marker: the phase completes with this arrival alone
-                pipe_expect(full + s, 0u);
-                pipe_commit(full + s);
-                break;
-            }
-            const uint32_t slab_bytes = (uint32_t)cur.slab_bytes, vr_bytes = 32u * (uint32_t)cur.np, ft_bytes = 32u * (uint32_t)cur.nfs;
-            pipe_expect(full + s, slab_bytes + vr_bytes + ft_bytes);
-            if (slab_bytes > 0) tile_copy(stage + VRS_OFF_SLAB, b.payload + cur.slab0, slab_bytes, full + s);
-            tile_copy(stage + VRS_OFF_VR, ws.vote_reads + 2 * (int64_t)cur.p0, vr_bytes, full + s);
-            tile_copy(stage + VRS_OFF_FT, fs_tiles + 2 * (int64_t)cur.p0, ft_bytes, full + s);
+            pipe_expect(full + s, 0u);
             pipe_commit(full + s);
         }
         return;
@@ -169,6 +185,8 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
             const int common_l = sh->common_l;  // the masks of the tile's usual record length are computed once
             const ChunkMasks cm_common = make_masks(common_l, common_l, col0);
             do {
+                if (ablate & 8) goto next_bundle;
+                {
                 const int f = bundle * S + sub;
                 FsTile ft;
                 ft.ent0 = 0; ft.m = 0; ft.l_out = 0; ft.len = 0; ft.tmpl_k = 0; ft.mode = SIDE_NONE; ft.flags = 0; ft.cbase4 = 0; ft.out4 = 0;
@@ -177,7 +195,7 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                 const int qbytes = GCB_ALIGN4(l_out), sbytes = GCB_ALIGN4((l_out + 1) >> 1);
                 const bool mine = ft.mode != SIDE_NONE && col0 < max(qbytes, 2 * sbytes);  // this lane owns words of the record
                 const int m = mine && ft.mode != SIDE_COPY ? (int)ft.m : 0;
-                const int mmax = __reduce_max_sync(FULL, m);
+                const int mmax = (ablate & 2) ? 0 : __reduce_max_sync(FULL, m);
                 const int cb = off_slab + 4 * (int)ft.cbase4;  // byte offsets into the CTA's shared memory
                 const int ento = off_vr + 16 * (int)ft.ent0;
                 VoteRead tv = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -300,14 +318,16 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                         }
                     }
                     uint8_t *out = out0 + 4 * (int64_t)ft.out4;
+                    if (!(ablate & 4)) {
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++)
                         if (col0 + 4 * kk < qbytes) *(uint32_t *)(out + col0 + 4 * kk) = oq[kk] & cm.rb[kk];
                     if (8 * j < sbytes) *(uint32_t *)(out + qbytes + 8 * j) = bswap32(tbe0 & cm.kn0);
                     if (8 * j + 4 < sbytes) *(uint32_t *)(out + qbytes + 8 * j + 4) = bswap32(tbe1 & cm.kn1);
+                    }
                 }
                 // ---- slow columns: one reservation per bundle (records << 32 | words), then the entries
-                const int nslow = __popc(slow0) + __popc(slow1);
+                const int nslow = (ablate & 1) ? 0 : __popc(slow0) + __popc(slow1);
                 if (__any_sync(FULL, nslow > 0)) {
                     const uint32_t rec_words = slow_rec_words(ft.m);
                     GCB_COUNT(3, nslow);
@@ -407,6 +427,8 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                         }
                     }
                 }
+                }
+            next_bundle:
                 if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
                 bundle = __shfl_sync(FULL, bundle, 0);
                 pipe_progress();
