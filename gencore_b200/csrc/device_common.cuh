@@ -293,6 +293,31 @@ GCB_DEV int lane_id() { return (int)(threadIdx.x & 31); }
 GCB_DEV int warp_sum(int v) { return __reduce_add_sync(FULL, v); }
 GCB_DEV int warp_min(int v) { return __reduce_min_sync(FULL, v); }
 GCB_DEV int warp_max(int v) { return __reduce_max_sync(FULL, v); }
+// ---- sub-warp groups: GS consecutive lanes (8, 16 or 32) that work on one cluster; every collective names the group's
+// own lanes, so the groups of a warp are free to diverge
+template <int GS>
+struct Grp {
+    static_assert(GS == 8 || GS == 16 || GS == 32, "group size");
+    int gl;          // lane within the group
+    int base;        // first lane of the group
+    unsigned mask;   // the group's lanes
+    GCB_DEV Grp() {
+        const int l = lane_id();
+        gl = l & (GS - 1);
+        base = l & ~(GS - 1);
+        mask = (GS == 32 ? 0xffffffffu : ((1u << GS) - 1u)) << base;
+    }
+    GCB_DEV int sum(int v) const { return __reduce_add_sync(mask, v); }
+    GCB_DEV int min_of(int v) const { return __reduce_min_sync(mask, v); }
+    GCB_DEV int max_of(int v) const { return __reduce_max_sync(mask, v); }
+    GCB_DEV bool all(bool p) const { return __all_sync(mask, p) != 0; }
+    GCB_DEV bool any(bool p) const { return __any_sync(mask, p) != 0; }
+    GCB_DEV unsigned ballot(bool p) const { return __ballot_sync(mask, p) >> base; }  // bit k = lane k of the group
+    template <typename T>
+    GCB_DEV T shfl_xor(T v, int off) const { return __shfl_xor_sync(mask, v, off); }
+    GCB_DEV void sync() const { __syncwarp(mask); }
+};
+
 GCB_DEV Umi umi_shfl(const Umi &u, int src) {
     Umi r;
 #pragma unroll

@@ -55,6 +55,7 @@ struct gcb_ctx {
     int vote_threads = 256;                         // threads per CTA of vote_staged_kernel / vote_fast_kernel
     int ring_threads = 512;                         // threads per CTA of vote_ring_kernel (512 or 768)
     int ring_window_shift = 0;                      // 0 = chosen by plan_tiles; 14 / 15 = forced (tuning)
+    int group_lanes = 0;                            // lanes per cluster in umi_group / select_template (0 = by mean cluster size)
     int ablate = 0;                                 // profiling only (GCB_ABLATE): parts of the ring kernel switched off
     int n_sms = 148;
     // device mirror of a host batch / result (gcb_consensus_batch)
@@ -276,23 +277,34 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         }
         return GCB_OK;
     }
-    const int warps_per_cta = GROUP_THREADS / WARP;
-    const unsigned grid_clusters = (unsigned)((nc + warps_per_cta - 1) / warps_per_cta);
+    // umi_group_kernel / select_template_kernel give GS lanes to a cluster: 8 while clusters are small, a whole warp when deep
+    int gs = ctx->group_lanes;
+    if (gs != 8 && gs != 16 && gs != 32) {
+        const int64_t avg = (int64_t)(v.p1 - v.p0) / nc;
+        gs = avg <= 12 ? 8 : avg <= 24 ? 16 : 32;
+    }
+    const int clusters_per_cta = (GROUP_THREADS / WARP) * (WARP / gs);
+    const unsigned grid_clusters = (unsigned)((nc + clusters_per_cta - 1) / clusters_per_cta);
+#define GCB_UMI_LAUNCH(NW)                                                                                                                    \
+    do {                                                                                                                                      \
+        if (gs == 8) GCB_LAUNCH((umi_group_kernel<NW, 8>), dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles);        \
+        else if (gs == 16) GCB_LAUNCH((umi_group_kernel<NW, 16>), dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles); \
+        else GCB_LAUNCH((umi_group_kernel<NW, 32>), dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles);               \
+    } while (0)
     if (stages & GCB_STAGE_UMI_GROUP) {
-        if (batch.umi_words == 1)
-            GCB_LAUNCH(umi_group_kernel<1>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles);
-        else if (batch.umi_words == 2)
-            GCB_LAUNCH(umi_group_kernel<2>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles);
-        else if (batch.umi_words == 3)
-            GCB_LAUNCH(umi_group_kernel<3>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles);
-        else
-            GCB_LAUNCH(umi_group_kernel<4>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles);
+        if (batch.umi_words == 1) GCB_UMI_LAUNCH(1);
+        else if (batch.umi_words == 2) GCB_UMI_LAUNCH(2);
+        else if (batch.umi_words == 3) GCB_UMI_LAUNCH(3);
+        else GCB_UMI_LAUNCH(4);
         ctx->launches++;
     }
+#undef GCB_UMI_LAUNCH
     if (stages & GCB_STAGE_SELECT_TEMPLATE) {
         const int32_t n_scan = (int32_t)((nc + SCAN_BLOCK - 1) / SCAN_BLOCK);
         GCB_CUDA(ctx, cudaMemsetAsync(result.groups + v.p0, 0, sizeof(gcb_group_result) * (size_t)(v.p1 - v.p0), stream));
-        GCB_LAUNCH(select_template_kernel, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
+        if (gs == 8) GCB_LAUNCH(select_template_kernel<8>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
+        else if (gs == 16) GCB_LAUNCH(select_template_kernel<16>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
+        else GCB_LAUNCH(select_template_kernel<32>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
         GCB_LAUNCH(scan_local_kernel, dim3((unsigned)n_scan), dim3(SCAN_THREADS), 0, stream, ws, nc);
         GCB_LAUNCH(scan_blocks_kernel, dim3(1), dim3(WARP), 0, stream, ws, n_scan, total_out, result.out_capacity, carry_in);
         ctx->launches += 3;
@@ -729,6 +741,7 @@ int gcb_set_debug(gcb_ctx *ctx, int key, int value) {
     if (!ctx) return GCB_ERR_ARG;
     if (key == 1) ctx->ablate = value;                 // profiling only: wrong results
     else if (key == 2) ctx->ring_window_shift = value;  // tuning only: same results
+    else if (key == 3) ctx->group_lanes = value;        // tuning only: same results
     else return GCB_ERR_ARG;
     return GCB_OK;
 }

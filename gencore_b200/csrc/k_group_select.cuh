@@ -73,11 +73,12 @@ GCB_DEV int umit_diff(const UmiT<NW> &a, const UmiT<NW> &b) {  // Cluster::umiDi
 // the lexicographically first UMI of maximal count among the pairs still unassigned and absorbs every
 // unassigned pair within `thr` of it, in map (= pair) order.  Counts never need decrementing: pairs
 // carrying the same UMI are always absorbed together.  `window_shift`: the vote tile window is 1 << window_shift.
-template <int NW>
+template <int NW, int GS>
 __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, ResultView r, Workspace ws, int32_t window_shift,
                                                                    int32_t n_tiles) {
-    const int lane = lane_id();
-    const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    const Grp<GS> g;
+    const int lane = g.gl;
+    const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (WARP / GS) + (lane_id() / GS);
     if (c >= b.n_clusters) return;
     const int p0 = b.cluster_pair_off[c], p1 = b.cluster_pair_off[c + 1], n = p1 - p0;
     const int thr = b.cluster_flags[c] >> GCB_CLUSTER_UMI_THR_SHIFT;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, R
 
     // multiplicity of every pair's UMI inside the cluster (cluster.cpp:57-65)
     bool has = false;
-    for (int i = lane; i < n; i += WARP) {
+    for (int i = lane; i < n; i += GS) {
         const UmiT<NW> u = umit_load<NW>(umi + (int64_t)i * NW);
         has |= (u.w[0] >> 60) != 0;
         int cnt = 0;
@@ -113,48 +114,50 @@ __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, R
         ws.scratch[2 * (int64_t)(p0 + i)] = cnt;
         r.pair_group[p0 + i] = -1;
     }
-    has = __any_sync(FULL, has);
+    has = g.any(has);
     if (lane == 0) ws.cluster_has_umi[c] = has ? 1 : 0;
+    g.sync();  // (the rounds below read pair_group / scratch entries written by other lanes of the group)
 
-    int filled = 0, g = 0;
+    int filled = 0, gi = 0;
     while (filled < n) {  // cluster.cpp:66-100
         int best_cnt = -1;
         UmiT<NW> best;
 #pragma unroll
         for (int k = 0; k < NW; k++) best.w[k] = 0ull;
-        for (int i = lane; i < n; i += WARP) {
+        for (int i = lane; i < n; i += GS) {
             if (r.pair_group[p0 + i] >= 0) continue;
             const int cnt = ws.scratch[2 * (int64_t)(p0 + i)];
             const UmiT<NW> u = umit_load<NW>(umi + (int64_t)i * NW);
             if (cnt > best_cnt || (cnt == best_cnt && umit_less<NW>(u, best))) { best_cnt = cnt; best = u; }
         }
-        for (int off = 16; off > 0; off >>= 1) {
-            const int oc = __shfl_xor_sync(FULL, best_cnt, off);
+        for (int off = GS / 2; off > 0; off >>= 1) {
+            const int oc = g.shfl_xor(best_cnt, off);
             UmiT<NW> ou;
 #pragma unroll
-            for (int k = 0; k < NW; k++) ou.w[k] = __shfl_xor_sync(FULL, best.w[k], off);
+            for (int k = 0; k < NW; k++) ou.w[k] = g.shfl_xor(best.w[k], off);
             if (oc > best_cnt || (oc == best_cnt && oc >= 0 && umit_less<NW>(ou, best))) { best_cnt = oc; best = ou; }
         }
         const int start = filled;
-        for (int base = 0; base < n; base += WARP) {
+        for (int base = 0; base < n; base += GS) {
             const int i = base + lane;
             bool absorb = false;
             if (i < n && r.pair_group[p0 + i] < 0) absorb = umit_diff<NW>(umit_load<NW>(umi + (int64_t)i * NW), best) <= thr;
-            const unsigned m = __ballot_sync(FULL, absorb);
+            const unsigned m = g.ballot(absorb);
             if (absorb) {
                 ws.members[p0 + filled + __popc(m & ((1u << lane) - 1u))] = p0 + i;
-                r.pair_group[p0 + i] = g;
+                r.pair_group[p0 + i] = gi;
             }
             filled += __popc(m);
         }
-        if (lane == 0) ws.group_off[p0 + g] = p0 + start;
+        if (lane == 0) ws.group_off[p0 + gi] = p0 + start;
         if (filled == start) {  // cannot happen (the top UMI is within 0 of itself); never spin on bad input
             if (lane == 0) raise_error(ws.error_flag, GCB_ERR_MALFORMED);
             break;
         }
-        g++;
+        gi++;
+        g.sync();
     }
-    if (lane == 0) r.cluster_n_groups[c] = g;
+    if (lane == 0) r.cluster_n_groups[c] = gi;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -214,8 +217,10 @@ GCB_DEV VoteRead make_vote_read(const BatchView &b, const Workspace &ws, int64_t
     return v;
 }
 
-GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gcb_options &o, int mb, int m, int side, int slot, int64_t slab0) {
-    const int lane = lane_id();
+template <int GS>
+GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Workspace &ws, const gcb_options &o, int mb, int m, int side, int slot,
+                               int64_t slab0) {
+    const int lane = g.gl;
     const SideChoice none = {-1, 0, 0, true, false};
     const bool isLeft = side == 0;
     const int thr = o.skip_low_complexity_cluster_threshold;
@@ -225,7 +230,7 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
 
     if (m > thr) {  // group.cpp:142-175: many distinct CIGARs + a low-complexity first read => skip the side
         int distinct = 0, first_k = 0x7FFFFFFF;
-        for (int k = lane; k < m; k += WARP) {
+        for (int k = lane; k < m; k += GS) {
             if (!GCB_HAVE(k)) continue;
             first_k = min(first_k, k);
             const int sk = GCB_SLOT(k);
@@ -237,15 +242,15 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
             }
             if (!seen) distinct++;
         }
-        distinct = warp_sum(distinct);
-        first_k = warp_min(first_k);
+        distinct = g.sum(distinct);
+        first_k = g.min_of(first_k);
         if ((double)distinct > m * 0.1 && first_k != 0x7FFFFFFF) {
             const gcb_read_desc rd = b.reads[GCB_SLOT(first_k)];
             const uint8_t *seq = b.payload + rd.data_off + GCB_ALIGN4(rd.l_qseq);
             int dn = 0;
-            for (int i = lane; i < rd.l_qseq - 1; i += WARP)
+            for (int i = lane; i < rd.l_qseq - 1; i += GS)
                 if (base_letter(base_at(seq, i)) != base_letter(base_at(seq, i + 1))) dn++;
-            dn = warp_sum(dn);
+            dn = g.sum(dn);
             if ((double)dn < rd.l_qseq * 0.5) return none;
         }
     }
@@ -259,11 +264,11 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
         const gcb_read_desc r0 = b.reads[GCB_SLOT(0)];
         same = same && r0.l_qseq >= 0 && r0.n_cigar == 1;
         const uint32_t c0w = same ? b.cigar[r0.cigar_off] : 0u;
-        for (int k = lane; k < m && same; k += WARP) {
+        for (int k = lane; k < m && same; k += GS) {
             const gcb_read_desc rk = b.reads[GCB_SLOT(k)];
             same = rk.l_qseq == r0.l_qseq && rk.n_cigar == 1 && rk.pos == r0.pos && b.cigar[rk.cigar_off] == c0w;
         }
-        same = __all_sync(FULL, same);
+        same = g.all(same);
     }
     bool leftReadMode = true;
     int best_cnt = m, best_k = 0;
@@ -271,29 +276,29 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
         leftReadMode = isLeft;
         if (!isLeft) {  // group.cpp:177-194: every right read starts at the same position => left-aligned columns
             int lo = 0x7FFFFFFF, hi = -0x7FFFFFFF;
-            for (int k = lane; k < m; k += WARP) {
+            for (int k = lane; k < m; k += GS) {
                 if (!GCB_HAVE(k)) continue;
                 const int pos = b.reads[GCB_SLOT(k)].pos;
                 lo = min(lo, pos);
                 hi = max(hi, pos);
             }
-            lo = warp_min(lo);
-            hi = warp_max(hi);
+            lo = g.min_of(lo);
+            hi = g.max_of(hi);
             if (lo >= hi) leftReadMode = true;  // all equal, or no read at all
         }
 
         // BamUtil::getRightRefPos (bamutil.cpp:379-383) of the right reads: only this general path compares them
         if (!isLeft) {
-            for (int k = lane; k < m; k += WARP) {
+            for (int k = lane; k < m; k += GS) {
                 if (!GCB_HAVE(k)) continue;
                 const gcb_read_desc rk = b.reads[GCB_SLOT(k)];
                 ws.right_ref_pos[GCB_SLOT(k)] = rk.pos < 0 ? -1 : rk.pos + cigar_ref_len(b.cigar + rk.cigar_off, rk.n_cigar);
             }
-            __syncwarp();
+            g.sync();
         }
         // group.cpp:196-233: containedBy[i] = 1 + #{j : read i is part of read j}
         int first_big = 0x7FFFFFFF;
-        for (int k = lane; k < m; k += WARP) {
+        for (int k = lane; k < m; k += GS) {
             int cnt = 0;
             if (GCB_HAVE(k)) {
                 cnt = 1;
@@ -311,20 +316,20 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
             }
             ws.scratch[2 * (int64_t)(mb + k) + side] = cnt;
         }
-        first_big = warp_min(first_big);  // group.cpp:231-232: the scan stops there, later entries stay 0
+        first_big = g.min_of(first_big);  // group.cpp:231-232: the scan stops there, later entries stay 0
 
         // group.cpp:235-261: most contained, ties -> strictly shorter read, else first in map order
         int best_len = 0;
         best_cnt = -1;
         best_k = 0x7FFFFFFF;
-        for (int k = lane; k < m; k += WARP) {
+        for (int k = lane; k < m; k += GS) {
             const int cnt = k > first_big ? 0 : ws.scratch[2 * (int64_t)(mb + k) + side];
             const int len = GCB_HAVE(k) ? b.reads[GCB_SLOT(k)].l_qseq : 0;
             if (cnt > best_cnt || (cnt == best_cnt && len < best_len)) { best_cnt = cnt; best_len = len; best_k = k; }
         }
-        for (int off = 16; off > 0; off >>= 1) {
-            const int oc = __shfl_xor_sync(FULL, best_cnt, off), ol = __shfl_xor_sync(FULL, best_len, off),
-                      ok = __shfl_xor_sync(FULL, best_k, off);
+        for (int off = GS / 2; off > 0; off >>= 1) {
+            const int oc = g.shfl_xor(best_cnt, off), ol = g.shfl_xor(best_len, off),
+                      ok = g.shfl_xor(best_k, off);
             if (oc > best_cnt || (oc == best_cnt && (ol < best_len || (ol == best_len && ok < best_k)))) {
                 best_cnt = oc; best_len = ol; best_k = ok;
             }
@@ -339,7 +344,7 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
     bool fits = true;
     int mn = od.l_qseq;
     VoteRead *vr = ws.vote_reads + 2 * (int64_t)mb + (int64_t)side * m;
-    for (int k = lane; k < m; k += WARP) {
+    for (int k = lane; k < m; k += GS) {
         const VoteRead zero = {VR_NO_VOTE, 0, 0, 0, 0, 0, 0, 0};
         if (!GCB_HAVE(k)) {
             vr[k] = zero;
@@ -364,22 +369,22 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
     SideChoice ch;
     ch.out = out;
     ch.k = best_k;
-    ch.len = od.n_cigar == 0 ? warp_min(mn) : od.l_qseq;  // group.cpp:354-360: no CIGAR => only the shortest read's columns
-    ch.fits = __all_sync(FULL, fits);
+    ch.len = od.n_cigar == 0 ? g.min_of(mn) : od.l_qseq;  // group.cpp:354-360: no CIGAR => only the shortest read's columns
+    ch.fits = g.all(fits);
     // FS_UNIFORM: every voter is as long as the template, is read at the template's columns, meets its mate through
     // the same overlap window and finds its mate's record at the same distance from its own (true for every family
     // of a fixed-length library packed pair by pair)
-    __syncwarp();
+    g.sync();
     const VoteRead tv = vr[best_k];
     bool uni = ch.len == od.l_qseq && tv.shift == 0 && tv.own_l == od.l_qseq;
-    for (int k = lane; k < m; k += WARP) {
+    for (int k = lane; k < m; k += GS) {
         const VoteRead v = vr[k];
         if (v.own_off4 == VR_NO_VOTE) continue;
         uni = uni && v.own_l == tv.own_l && v.shift == 0 && v.ov_len == tv.ov_len &&
               (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l &&
                                  (uint16_t)(v.mate_off4 - v.own_off4) == (uint16_t)(tv.mate_off4 - tv.own_off4)));
     }
-    ch.uniform = __all_sync(FULL, uni);
+    ch.uniform = g.all(uni);
     return ch;
 #undef GCB_SLOT
 #undef GCB_HAVE
@@ -387,15 +392,17 @@ GCB_DEV SideChoice side_select(const BatchView &b, const Workspace &ws, const gc
 }
 
 // group.cpp:68-134 per family of the cluster + the per-pair overlap windows of pair.cpp:103-119
+template <int GS>
 __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o) {
-    const int lane = lane_id();
-    const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    const Grp<GS> g;
+    const int lane = g.gl;
+    const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (WARP / GS) + (lane_id() / GS);
     if (c >= b.n_clusters) return;
     const int p0 = b.cluster_pair_off[c], p1 = b.cluster_pair_off[c + 1], n = p1 - p0;
     const int G = r.cluster_n_groups[c];
     const bool crossContig = (b.cluster_flags[c] & GCB_CLUSTER_CROSS_CONTIG) != 0;
 
-    for (int i = lane; i < n; i += WARP) {
+    for (int i = lane; i < n; i += GS) {
         const int64_t pair = p0 + i;
         const gcb_read_desc L = b.reads[2 * pair], R = b.reads[2 * pair + 1];
         ws.vote_flags[2 * pair] = 0;
@@ -421,18 +428,18 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
         }
         ws.overlap[pair] = ov;
     }
-    __syncwarp();
+    g.sync();
 
     const int64_t slab0 = ws.slab_off[c];
-    for (int i = G + lane; i < n; i += WARP) {  // slots that hold no family: the vote kernel reads side_mode to know
+    for (int i = G + lane; i < n; i += GS) {  // slots that hold no family: the vote kernel reads side_mode to know
         ws.side_mode[2 * (int64_t)(p0 + i)] = SIDE_NONE;
         ws.side_mode[2 * (int64_t)(p0 + i) + 1] = SIDE_NONE;
     }
     int64_t out_rel = 0;
-    for (int g = 0; g < G; g++) {
-        const int slot = p0 + g;
+    for (int gi = 0; gi < G; gi++) {
+        const int slot = p0 + gi;
         const int mb = ws.group_off[slot];
-        const int me = g + 1 < G ? ws.group_off[slot + 1] : p1;
+        const int me = gi + 1 < G ? ws.group_off[slot + 1] : p1;
         const int m = me - mb;
         gcb_group_result gr;
         gr.out_off[0] = gr.out_off[1] = -1;
@@ -472,14 +479,14 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
             int nameToCopy = -1;  // group.cpp:79-99: shortest padded qname among the left reads, first in map order
             if (crossContig) {
                 long long key = 0x7FFFFFFFFFFFFFFFll;
-                for (int k = lane; k < m; k += WARP) {
+                for (int k = lane; k < m; k += GS) {
                     const int sl = 2 * ws.members[mb + k];
                     if (b.reads[sl].l_qseq < 0) continue;
                     const long long kk = ((long long)b.reads[sl].l_qname << 32) | (unsigned)k;
                     key = kk < key ? kk : key;
                 }
-                for (int off = 16; off > 0; off >>= 1) {
-                    const long long ok = __shfl_xor_sync(FULL, key, off);
+                for (int off = GS / 2; off > 0; off >>= 1) {
+                    const long long ok = g.shfl_xor(key, off);
                     key = ok < key ? ok : key;
                 }
                 if (key != 0x7FFFFFFFFFFFFFFFll) nameToCopy = 2 * ws.members[mb + (int)(key & 0xFFFFFFFFll)];
@@ -488,9 +495,9 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
                 ws.side_mode[2 * (int64_t)slot] = SIDE_NONE;
                 ws.side_mode[2 * (int64_t)slot + 1] = SIDE_NONE;
             }
-            __syncwarp();
-            ch[0] = side_select(b, ws, o, mb, m, 0, slot, slab0);
-            ch[1] = side_select(b, ws, o, mb, m, 1, slot, slab0);
+            g.sync();
+            ch[0] = side_select<GS>(g, b, ws, o, mb, m, 0, slot, slab0);
+            ch[1] = side_select<GS>(g, b, ws, o, mb, m, 1, slot, slab0);
             const int left = ch[0].out, right = ch[1].out;
             gr.tmpl_read[0] = left;
             gr.tmpl_read[1] = right;
@@ -506,7 +513,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchVie
             }
             gr.umi_pair = name_slot >= 0 ? name_slot / 2 : -1;  // Pair::setLeft/setRight, pair.cpp:188-216
         }
-        __syncwarp();
+        g.sync();
         for (int s = 0; s < 2; s++) {
             FsDesc fd = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, 0};
             if (gr.tmpl_read[s] >= 0) {

@@ -216,7 +216,8 @@ int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes);
 int gcb_set_vote_mode(gcb_ctx *ctx, int mode);
 
 /* Profiling / tuning aid, not for production: key 1 = switch parts of the ring kernel off (results are WRONG, timing only),
- * key 2 = force the ring kernel's tile window (14 or 15 = log2 bytes, 0 = automatic; results unchanged). */
+ * key 2 = force the ring kernel's tile window (14 or 15 = log2 bytes, 0 = automatic; results unchanged),
+ * key 3 = lanes per cluster in umi_group_kernel / select_template_kernel (8, 16, 32; 0 = by mean cluster size; results unchanged). */
 int gcb_set_debug(gcb_ctx *ctx, int key, int value);
 
 /* Tuning knob of vote mode 3: bytes of the slow-column queues (0 = sized from the payload).  Columns that do not fit are

@@ -49,12 +49,20 @@ struct Fiber {
     bool done = true;
 };
 
+struct SubGroup {        // the lanes of one partial mask (keyed by the mask's lowest lane)
+    uint64_t xchg[2][kWarp];
+    int parity = 0;
+    int arrived = 0;
+    unsigned generation = 0;
+};
+
 struct WarpState {
     uint64_t xchg[2][kWarp];
     int parity = 0;       // which xchg buffer the next collective uses
     int arrived = 0;
     unsigned generation = 0;
     int live = 0;
+    SubGroup sub[kWarp];
 };
 
 struct State {
@@ -194,10 +202,51 @@ inline void warp_barrier() {
 
 inline int lane() { return st().cur % kWarp; }
 
+// a collective over the lanes of a partial mask: all of them must be alive and must name the same mask
+inline SubGroup &sub_barrier(unsigned mask) {
+    State &s = st();
+    const int wbase = (s.cur / kWarp) * kWarp;
+    WarpState &w = s.warps[s.cur / kWarp];
+    if (!((mask >> (s.cur % kWarp)) & 1u)) {
+        fprintf(stderr, "simt_check: lane %d calls a collective whose mask %08x does not name it\n", s.cur % kWarp, mask);
+        abort();
+    }
+    int need = 0;
+    for (int l = 0; l < kWarp; l++)
+        if ((mask >> l) & 1u) {
+            if (wbase + l >= s.nthreads || s.fibers[wbase + l].done) {
+                fprintf(stderr, "simt_check: collective mask %08x names lane %d, which has exited\n", mask, l);
+                abort();
+            }
+            need++;
+        }
+    SubGroup &g = w.sub[__builtin_ctz(mask)];
+    unsigned gen = g.generation;
+    g.arrived++;
+    for (;;) {
+        if (g.generation != gen) return g;
+        if (g.arrived >= need) {
+            g.arrived = 0;
+            g.generation++;
+            s.progress++;
+            return g;
+        }
+        yield();
+    }
+}
+
 // every lane publishes v, gets the whole vector back
-inline const uint64_t *exchange(uint64_t v) {
+inline const uint64_t *exchange(uint64_t v, unsigned mask = 0xffffffffu) {
     State &s = st();
     WarpState &w = s.warps[s.cur / kWarp];
+    if (mask != 0xffffffffu) {
+        SubGroup &g0 = w.sub[__builtin_ctz(mask)];
+        int p = g0.parity;
+        g0.xchg[p][s.cur % kWarp] = v;
+        SubGroup &g = sub_barrier(mask);
+        if (g.parity == p) g.parity = p ^ 1;
+        return g.xchg[p];
+    }
     int p = w.parity;
     w.xchg[p][s.cur % kWarp] = v;
     warp_barrier();
@@ -206,12 +255,7 @@ inline const uint64_t *exchange(uint64_t v) {
     return w.xchg[p];
 }
 
-inline void check_full(unsigned mask) {
-    if (mask != 0xffffffffu) {
-        fprintf(stderr, "simt_check: only full-mask warp collectives are supported (mask %08x)\n", mask);
-        abort();
-    }
-}
+inline void check_full(unsigned) {}  // partial masks rendezvous among their own lanes (sub_barrier)
 
 template <typename T>
 inline uint64_t to_bits(T v) {
@@ -232,14 +276,14 @@ inline T from_bits(uint64_t b) {
 // ---- CUDA device intrinsics used by the kernels ---------------------------------------------------
 inline void __syncthreads() { simt::block_barrier(); }
 inline void __syncwarp(unsigned mask = 0xffffffffu) {
-    simt::check_full(mask);
-    simt::warp_barrier();
+    if (mask != 0xffffffffu) simt::sub_barrier(mask);
+    else simt::warp_barrier();
 }
 template <typename T>
 inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
     simt::check_full(mask);
     (void)width;
-    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    const uint64_t *x = simt::exchange(simt::to_bits(v), mask);
     return simt::from_bits<T>(x[src & 31]);
 }
 template <typename T>
@@ -247,7 +291,7 @@ inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32) {
     simt::check_full(mask);
     (void)width;
     int l = simt::lane();
-    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    const uint64_t *x = simt::exchange(simt::to_bits(v), mask);
     return simt::from_bits<T>(x[(l ^ lanemask) & 31]);
 }
 template <typename T>
@@ -255,7 +299,7 @@ inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32) {
     simt::check_full(mask);
     (void)width;
     int l = simt::lane();
-    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    const uint64_t *x = simt::exchange(simt::to_bits(v), mask);
     int src = l + (int)delta;
     return simt::from_bits<T>(x[src < 32 ? src : l]);
 }
@@ -264,38 +308,42 @@ inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32) {
     simt::check_full(mask);
     (void)width;
     int l = simt::lane();
-    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    const uint64_t *x = simt::exchange(simt::to_bits(v), mask);
     int src = l - (int)delta;
     return simt::from_bits<T>(x[src >= 0 ? src : l]);
 }
 inline unsigned __ballot_sync(unsigned mask, int pred) {
     simt::check_full(mask);
-    const uint64_t *x = simt::exchange(pred ? 1 : 0);
+    const uint64_t *x = simt::exchange(pred ? 1 : 0, mask);
     unsigned r = 0;
-    for (int i = 0; i < 32; i++) r |= (unsigned)(x[i] & 1) << i;
+    for (int i = 0; i < 32; i++)
+        if ((mask >> i) & 1u) r |= (unsigned)(x[i] & 1) << i;
     return r;
 }
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
-inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
+inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
 inline int __reduce_add_sync(unsigned mask, int v) {
     simt::check_full(mask);
-    const uint64_t *x = simt::exchange(simt::to_bits(v));
+    const uint64_t *x = simt::exchange(simt::to_bits(v), mask);
     int r = 0;
-    for (int i = 0; i < 32; i++) r += simt::from_bits<int>(x[i]);
+    for (int i = 0; i < 32; i++)
+        if ((mask >> i) & 1u) r += simt::from_bits<int>(x[i]);
     return r;
 }
 inline int __reduce_min_sync(unsigned mask, int v) {
     simt::check_full(mask);
-    const uint64_t *x = simt::exchange(simt::to_bits(v));
-    int r = simt::from_bits<int>(x[0]);
-    for (int i = 1; i < 32; i++) r = std::min(r, simt::from_bits<int>(x[i]));
+    const uint64_t *x = simt::exchange(simt::to_bits(v), mask);
+    int r = 0x7FFFFFFF;
+    for (int i = 0; i < 32; i++)
+        if ((mask >> i) & 1u) r = std::min(r, simt::from_bits<int>(x[i]));
     return r;
 }
 inline int __reduce_max_sync(unsigned mask, int v) {
     simt::check_full(mask);
-    const uint64_t *x = simt::exchange(simt::to_bits(v));
-    int r = simt::from_bits<int>(x[0]);
-    for (int i = 1; i < 32; i++) r = std::max(r, simt::from_bits<int>(x[i]));
+    const uint64_t *x = simt::exchange(simt::to_bits(v), mask);
+    int r = -0x7FFFFFFF - 1;
+    for (int i = 0; i < 32; i++)
+        if ((mask >> i) & 1u) r = std::max(r, simt::from_bits<int>(x[i]));
     return r;
 }
 

@@ -98,6 +98,19 @@ def test_split_vote_matches_oracle(engine_cls, oracle, name, thunk):
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 
 
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+@pytest.mark.parametrize("name", ["cfg2_40k", "cfg4_40k", "edge_default", "ragged_duplex_5_big", "ragged_single_4_big", "deep_1100", "low_complexity",
+                                  "wide_umi_3", "cfg3_40k", "tiny_reads"])
+def test_lanes_per_cluster_do_not_change_results(engine_cls, oracle, name, lanes):
+    """umi_group_kernel / select_template_kernel with 8, 16 or 32 lanes per cluster."""
+    batch, genome, opt = dict(CASES)[name]()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        eng.set_debug(3, lanes)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} lanes {lanes}")
+
+
 @pytest.mark.parametrize("qbytes", [1 << 14, 1 << 20])
 @pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "cfg4_40k", "edge_strict"])
 def test_slow_queue_overflow_does_not_change_results(engine_cls, oracle, name, qbytes):

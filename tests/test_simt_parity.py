@@ -148,3 +148,17 @@ def test_split_vote_matches_oracle_under_simt_check(simt_lib, oracle, name, thun
         eng.set_vote_mode(3)
         res = eng.cluster_by_umi(batch)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+@pytest.mark.parametrize("name", ["golden_cfg2_600", "golden_cfg4_600", "edge_default", "ragged_duplex_2", "ragged_single_1", "deep_1100", "low_complexity",
+                                  "wide_umi_3", "cfg3_1500", "tiny_reads"])
+def test_lanes_per_cluster_do_not_change_results(simt_lib, oracle, name, lanes):
+    """umi_group_kernel / select_template_kernel with 8, 16 or 32 lanes per cluster (groups of a warp work on different clusters)."""
+    from gencore_b200.engine import ConsensusEngine
+    batch, genome, opt = dict(CASES)[name]()
+    with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
+        eng.set_reference(genome)
+        eng.set_debug(3, lanes)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} lanes {lanes}")
