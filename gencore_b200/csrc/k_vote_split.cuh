@@ -112,26 +112,34 @@ GCB_DEV uint32_t slow_entry(const uint8_t *cb, const VoteRead &v, int col) {
     return ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
 }
 
+// Pair::qual2score (pair.cpp:77-86) with the thresholds and the four scores in registers
+struct ScoreTab {
+    int hq, mq, lq, sh, sm, sl, sb;
+    GCB_DEV explicit ScoreTab(const gcb_options &o)
+        : hq(o.high_quality), mq(o.moderate_quality), lq(o.low_quality), sh(sc8(o.score_high)), sm(sc8(o.score_moderate)), sl(sc8(o.score_low)),
+          sb(sc8(o.score_bad)) {}
+    GCB_DEV int q2s(int q) const { return q >= hq ? sh : q >= mq ? sm : q >= lq ? sl : sb; }
+};
+
 // base, rewritten quality and score of a queue entry: the same function of the same bytes as fetch_vote
-GCB_DEV bool slow_decode(const gcb_options &o, uint32_t ent, int side, int &base, int &qual, int &score) {
+GCB_DEV bool slow_decode(const ScoreTab &t, uint32_t ent, int side, int &base, int &qual, int &score) {
     if (!(ent & SE_VOTES)) return false;
     const int ql = (int)(ent & 0xFFu), mql = (int)((ent >> 8) & 0xFFu);
     base = (int)((ent >> 16) & 0xFu);
     const int mbase = (int)((ent >> 20) & 0xFu);
     const uint32_t st = (ent >> 24) & 3u;
-    const int moderate = sc8(o.score_moderate);
     qual = ql;
     if (st == SE_MATE) {
         if (base == mbase) {  // pair.cpp:147-152
-            score = sc8(qual2score_sel(o, (ql + mql) / 2) + 4);
+            score = sc8(t.q2s((ql + mql) / 2) + 4);
         } else {  // pair.cpp:153-169
             const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
             const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
-            score = mine ? sc8(qual2score_sel(o, lq >= rq ? lq - rq : rq - lq) - 3) : 0;
+            score = mine ? sc8(t.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;
             qual = max(0, ql - mql);
         }
     } else {
-        score = st == SE_PLAIN ? qual2score_sel(o, ql) : moderate;
+        score = st == SE_PLAIN ? t.q2s(ql) : t.sm;
     }
     return true;
 }
@@ -386,11 +394,12 @@ __global__ void __launch_bounds__(VS_MAX_THREADS, 3) vote_fast_kernel(BatchView 
 // A fourth distinct code in one column: the sixteen-bin histogram in local memory (group.cpp:376-417 as written).
 __device__ __noinline__ void slow_record_wide(const gcb_options &o, const uint32_t *ents, int n, int side, ColumnTop &ct, int &total_out,
                                               uint32_t &acgt_out) {
+    const ScoreTab tab(o);
     int32_t bins[64];
     for (int k = 0; k < 64; k++) bins[k] = 0;
     for (int e = 0; e < n; e++) {
         int base, qual, score;
-        if (!slow_decode(o, ents[e], side, base, qual, score)) continue;
+        if (!slow_decode(tab, ents[e], side, base, qual, score)) continue;
         bins[4 * base]++;
         bins[4 * base + 1] += score;
         bins[4 * base + 2] += qual;
@@ -413,8 +422,8 @@ __device__ __noinline__ void slow_record_wide(const gcb_options &o, const uint32
 }
 
 // group.cpp:376-525 for one queued column
-GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeView &gv, const gcb_options &o, const SlowQueues &sq,
-                         const uint32_t *rec) {
+GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeView &gv, const gcb_options &o, const ScoreTab &tab,
+                         const SlowQueues &sq, const uint32_t *rec) {
     const uint4 ha = ((const uint4 *)rec)[0], hc = ((const uint4 *)rec)[1];
     const uint32_t fsid = ha.x, w1 = ha.y, w2 = ha.z;
     const int col = (int)(w1 & 0xFFFFu), n = (int)(w1 >> 16), tmpl_k = (int)(w2 & 0xFFFFu);
@@ -426,7 +435,7 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
     const int64_t ref_nib0 = (int64_t)(((uint64_t)hc.w << 32) | hc.z);
     if (flags & SR_UNVOTED) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
         int obase = 0, oqual = 0, sc;
-        slow_decode(o, ents[tmpl_k], side, obase, oqual, sc);
+        slow_decode(tab, ents[tmpl_k], side, obase, oqual, sc);
         out[col] = (uint8_t)oqual;
         return;
     }
@@ -434,7 +443,7 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
     bins.init();
     for (int e = 0; e < n; e++) {
         int base, qual, score;
-        if (slow_decode(o, ents[e], side, base, qual, score)) bins.add(base, qual, score);
+        if (slow_decode(tab, ents[e], side, base, qual, score)) bins.add(base, qual, score);
     }
     ColumnTop ct;
     int total = bins.total;
@@ -495,13 +504,13 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
             const int rmax = (int)((acgt >> (ref4 == 1 ? 0 : ref4 == 2 ? 8 : ref4 == 4 ? 16 : 24)) & 0xFFu);
             if (rmax >= 128) {  // `char refBaseQual` wraps: the scan order matters (group.cpp:474-490): template first
                 int tb, tq, ts;
-                if (slow_decode(o, ents[tmpl_k], side, tb, tq, ts) && tb == ref4) {
+                if (slow_decode(tab, ents[tmpl_k], side, tb, tq, ts) && tb == ref4) {
                     if (tq > rbq) rbq = sc8(tq);
                     if (tq >= o.high_quality) any_high = true;
                 }
                 for (int e = 0; e < n; e++) {
                     int base, qual, score;
-                    if (e == tmpl_k || !slow_decode(o, ents[e], side, base, qual, score) || base != ref4) continue;
+                    if (e == tmpl_k || !slow_decode(tab, ents[e], side, base, qual, score) || base != ref4) continue;
                     if (qual > rbq) rbq = sc8(qual);
                     if (qual >= o.high_quality) any_high = true;
                 }
@@ -528,15 +537,28 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
 }
 
 __global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView b, ResultView r, GenomeView gv, gcb_options o, SlowQueues sq) {
-    const int qi = (int)(blockIdx.x % VQ_NQ), part = (int)(blockIdx.x / VQ_NQ), nparts = (int)(gridDim.x / VQ_NQ);
-    const uint32_t reserved = (uint32_t)(sq.count[qi] >> 32);
-    const uint32_t nrec = reserved < sq.cap_recs ? reserved : sq.cap_recs;
-    const uint32_t *q_words = sq.words + (size_t)qi * sq.cap_words;
-    const uint32_t *q_index = sq.index + (size_t)qi * sq.cap_recs;
-    for (uint32_t i = (uint32_t)part * blockDim.x + threadIdx.x; i < nrec; i += (uint32_t)nparts * blockDim.x) {
-        const uint32_t off = q_index[i];
+    // the records of all queues as one index space, so that every warp but the last is full
+    __shared__ uint32_t s_first[VQ_NQ + 1];
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int q = 0; q < VQ_NQ; q++) {
+            s_first[q] = run;
+            const uint32_t reserved = (uint32_t)(sq.count[q] >> 32);
+            run += reserved < sq.cap_recs ? reserved : sq.cap_recs;
+        }
+        s_first[VQ_NQ] = run;
+    }
+    __syncthreads();
+    const uint32_t total = s_first[VQ_NQ];
+    const ScoreTab tab(o);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int q = 0;
+#pragma unroll
+        for (int step = VQ_NQ / 2; step > 0; step >>= 1)
+            if (s_first[q + step] <= i) q += step;
+        const uint32_t off = sq.index[(size_t)q * sq.cap_recs + (i - s_first[q])];
         if (off == VQ_INVALID) continue;
-        slow_record(b, r, gv, o, sq, q_words + off);
+        slow_record(b, r, gv, o, tab, sq, sq.words + (size_t)q * sq.cap_words + off);
     }
 }
 

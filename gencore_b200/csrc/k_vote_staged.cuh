@@ -25,8 +25,9 @@ constexpr int VS_MAX_THREADS = 256;
 constexpr int VS_MAX_PAIRS = 256;   // pair positions of a tile
 constexpr int VS_MAX_FS = 192;      // family sides of a tile
 constexpr int VS_SLOW_CAP = 384;    // queued slow columns; more are decided inline by their owner
-constexpr int VS_PREP_THREADS = 256;
-static_assert(VS_PREP_THREADS >= VS_MAX_PAIRS, "tile_prep2_kernel gives one thread to every pair position");
+constexpr int VS_PREP_THREADS = 128;
+constexpr int VS_PREP_ROUNDS = 2;
+static_assert(VS_PREP_THREADS * VS_PREP_ROUNDS >= VS_MAX_PAIRS, "tile_prep2_kernel gives one thread and round to every pair position");
 
 struct __align__(16) TileHdr2 {
     int64_t out_base0;   // first output byte of the tile
@@ -53,10 +54,12 @@ constexpr int VS_OFF_SLAB = (VS_OFF_VR + 32 * VS_MAX_PAIRS + 127) & ~127;
 static_assert(VS_OFF_FT % 16 == 0 && VS_OFF_VR % 16 == 0, "16-byte aligned tables");
 
 // ------------------------------------------------------------------------------------------------
-// One CTA per tile, one thread per pair position: what the tiled kernel's prologue computes, once per batch.
+// One CTA per tile, one thread per pair position (VS_PREP_ROUNDS rounds of VS_PREP_THREADS positions): what the tiled
+// kernel's prologue computes, once per batch.  The CTA is small so that many tiles' chains of dependent loads
+// (directory -> side modes -> family-side descriptors -> cluster offsets) are in flight on an SM at once.
 __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b, ResultView r, Workspace ws, int32_t slab_cap, TileHdr2 *hdr,
                                                                       FsTile *fs_tiles) {
-    __shared__ uint32_t s_wsum[VS_PREP_THREADS / WARP];
+    __shared__ uint32_t s_wsum[VS_PREP_ROUNDS][VS_PREP_THREADS / WARP];
     __shared__ int s_nofit, s_lmax, s_common;
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
     const TileDir t0 = ws.tile_dir[blockIdx.x], t1 = ws.tile_dir[blockIdx.x + 1];
@@ -83,43 +86,58 @@ __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b
         s_lmax = 1;
         s_common = 0;
     }
-    FsDesc fd[2];
-    fd[0].mode = fd[1].mode = SIDE_NONE;
-    fd[0].c = fd[1].c = c0;
-    if (tid < NP) {  // slots that hold no family carry SIDE_NONE in side_mode and garbage in fs_desc
-        const uint16_t modes = *(const uint16_t *)(ws.side_mode + 2 * (int64_t)(P0 + tid));
-        if ((modes & 0xFF) != SIDE_NONE) fd[0] = ws.fs_desc[2 * (int64_t)(P0 + tid)];
-        if ((modes >> 8) != SIDE_NONE) fd[1] = ws.fs_desc[2 * (int64_t)(P0 + tid) + 1];
-    }
     const int64_t out_base0 = ws.scan_block[c0 / SCAN_BLOCK] + ws.cluster_out_off[c0];
-    const bool live0 = fd[0].mode != SIDE_NONE, live1 = fd[1].mode != SIDE_NONE;
-    int64_t c_slab = 0, c_out = 0;
-    if (live0 || live1) {
-        const int c = live0 ? fd[0].c : fd[1].c;
-        c_slab = ws.slab_off[c] - t0.slab0;
-        c_out = ws.scan_block[c / SCAN_BLOCK] + ws.cluster_out_off[c] - out_base0;
+    FsDesc fd[VS_PREP_ROUNDS][2];
+    int64_t c_slab[VS_PREP_ROUNDS], c_out[VS_PREP_ROUNDS];
+    uint32_t incl[VS_PREP_ROUNDS], mine[VS_PREP_ROUNDS];
+#pragma unroll
+    for (int rd = 0; rd < VS_PREP_ROUNDS; rd++) {
+        const int pos = rd * VS_PREP_THREADS + tid;
+        fd[rd][0].mode = fd[rd][1].mode = SIDE_NONE;
+        fd[rd][0].c = fd[rd][1].c = c0;
+        if (pos < NP) {  // slots that hold no family carry SIDE_NONE in side_mode and garbage in fs_desc
+            const uint16_t modes = *(const uint16_t *)(ws.side_mode + 2 * (int64_t)(P0 + pos));
+            if ((modes & 0xFF) != SIDE_NONE) fd[rd][0] = ws.fs_desc[2 * (int64_t)(P0 + pos)];
+            if ((modes >> 8) != SIDE_NONE) fd[rd][1] = ws.fs_desc[2 * (int64_t)(P0 + pos) + 1];
+        }
+        const bool live0 = fd[rd][0].mode != SIDE_NONE, live1 = fd[rd][1].mode != SIDE_NONE;
+        c_slab[rd] = c_out[rd] = 0;
+        if (live0 || live1) {
+            const int c = live0 ? fd[rd][0].c : fd[rd][1].c;
+            c_slab[rd] = ws.slab_off[c] - t0.slab0;
+            c_out[rd] = ws.scan_block[c / SCAN_BLOCK] + ws.cluster_out_off[c] - out_base0;
+        }
+        mine[rd] = (live0 ? 1u : 0u) + (live1 ? 1u : 0u);
+        uint32_t in = mine[rd];
+        for (int off = 1; off < WARP; off <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, in, off);
+            if (lane >= off) in += v;
+        }
+        incl[rd] = in;
+        if (lane == WARP - 1) s_wsum[rd][warp] = in;
     }
-    const uint32_t mine = (live0 ? 1u : 0u) + (live1 ? 1u : 0u);
-    uint32_t incl = mine;
-    for (int off = 1; off < WARP; off <<= 1) {
-        const uint32_t v = __shfl_up_sync(FULL, incl, off);
-        if (lane >= off) incl += v;
-    }
-    if (lane == WARP - 1) s_wsum[warp] = incl;
     __syncthreads();
-    uint32_t pre = incl - mine, total = 0;
-    for (int w = 0; w < VS_PREP_THREADS / WARP; w++) {
-        if (w < warp) pre += s_wsum[w];
-        total += s_wsum[w];
+    uint32_t total = 0, pre[VS_PREP_ROUNDS];
+#pragma unroll
+    for (int rd = 0; rd < VS_PREP_ROUNDS; rd++) {
+        pre[rd] = total + incl[rd] - mine[rd];
+        for (int w = 0; w < VS_PREP_THREADS / WARP; w++) {
+            if (w < warp) pre[rd] += s_wsum[rd][w];
+            total += s_wsum[rd][w];
+        }
     }
     if (tid == 0 && total > (uint32_t)VS_MAX_FS) s_nofit = 1;
     FsTile *ft_out = fs_tiles + 2 * (int64_t)P0;
-    int64_t abs_off[2] = {-1, -1};
-    if (live0 || live1) {
-        int lneed = 1, fidx = (int)pre;
+    int64_t abs_off[VS_PREP_ROUNDS][2];
+#pragma unroll
+    for (int rd = 0; rd < VS_PREP_ROUNDS; rd++) {
+        abs_off[rd][0] = abs_off[rd][1] = -1;
+        if (mine[rd] == 0) continue;
+        const int pos = rd * VS_PREP_THREADS + tid;
+        int lneed = 1, fidx = (int)pre[rd];
         for (int side = 0; side < 2; side++) {
-            if (fd[side].mode == SIDE_NONE) continue;
-            const FsDesc d = fd[side];
+            if (fd[rd][side].mode == SIDE_NONE) continue;
+            const FsDesc d = fd[rd][side];
             FsTile ft;
             ft.ent0 = (uint16_t)(2 * (d.mb - P0) + side * (int)d.m);
             ft.m = d.m;
@@ -128,11 +146,11 @@ __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b
             ft.tmpl_k = d.tmpl_k;
             ft.mode = d.mode;
             ft.flags = (uint8_t)(d.flags | (side ? FS_SIDE1 : 0));
-            ft.cbase4 = (uint16_t)(c_slab >> 2);
-            const int64_t orel = c_out + d.out_rel;
+            ft.cbase4 = (uint16_t)(c_slab[rd] >> 2);
+            const int64_t orel = c_out[rd] + d.out_rel;
             ft.out4 = (uint16_t)(orel >> 2);
             ft.ref_nib0 = d.ref_nib0;
-            ft.slot = P0 + tid;
+            ft.slot = P0 + pos;
             ft.reserved = 0;
             const int l = d.l_out;
             const int chunks = max((GCB_ALIGN4(l) + 15) >> 4, (GCB_ALIGN4((l + 1) >> 1) + 7) >> 3);
@@ -141,7 +159,7 @@ __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b
                 raise_error(ws.error_flag, GCB_ERR_CAPACITY);
                 ft.mode = SIDE_NONE;  // keeps its place in the table but is never voted
             } else {
-                abs_off[side] = out_base0 + orel;
+                abs_off[rd][side] = out_base0 + orel;
             }
             lneed = max(lneed, min(chunks, WARP));
             if (fidx < VS_MAX_FS) ft_out[fidx] = ft;
@@ -152,8 +170,12 @@ __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b
     }
     __syncthreads();
     if (!s_nofit) {  // the absolute offsets the caller reads (the generic kernel rebases the relative ones itself)
-        if (abs_off[0] >= 0) r.groups[P0 + tid].out_off[0] = abs_off[0];
-        if (abs_off[1] >= 0) r.groups[P0 + tid].out_off[1] = abs_off[1];
+#pragma unroll
+        for (int rd = 0; rd < VS_PREP_ROUNDS; rd++) {
+            const int pos = rd * VS_PREP_THREADS + tid;
+            if (abs_off[rd][0] >= 0) r.groups[P0 + pos].out_off[0] = abs_off[rd][0];
+            if (abs_off[rd][1] >= 0) r.groups[P0 + pos].out_off[1] = abs_off[rd][1];
+        }
     }
     if (tid == 0) {
         if (s_nofit) {  // the generic kernel takes the tile
