@@ -121,6 +121,45 @@ struct ScoreTab {
     GCB_DEV int q2s(int q) const { return q >= hq ? sh : q >= mq ? sm : q >= lq ? sl : sb; }
 };
 
+// group.cpp:376-393 for up to three distinct codes, in registers and without branches (a fourth code raises `overflow`)
+struct Bins3 {
+    int b0, b1, b2;              // codes (-1 = free)
+    int c0, c1, c2;              // counts
+    int s0, s1, s2;              // score sums
+    int q0, q1, q2;              // quality sums
+    int x0, x1, x2;              // best qualities
+    int total;
+    bool overflow;
+    GCB_DEV void init() {
+        b0 = b1 = b2 = -1;
+        c0 = c1 = c2 = s0 = s1 = s2 = q0 = q1 = q2 = x0 = x1 = x2 = 0;
+        total = 0;
+        overflow = false;
+    }
+    GCB_DEV void add(int base, int qual, int score) {
+        total += score;
+        // the bin that holds the code, else the first free one
+        const bool h0 = b0 == base, h1 = b1 == base, h2 = b2 == base;
+        const bool hit = h0 || h1 || h2;
+        const bool u0 = h0 || (!hit && b0 < 0);
+        const bool u1 = h1 || (!hit && b0 >= 0 && b1 < 0);
+        const bool u2 = h2 || (!hit && b0 >= 0 && b1 >= 0 && b2 < 0);
+        overflow = overflow || !(u0 || u1 || u2);
+        if (u0) { b0 = base; c0++; s0 += score; q0 += qual; x0 = max(x0, qual); }
+        if (u1) { b1 = base; c1++; s1 += score; q1 += qual; x1 = max(x1, qual); }
+        if (u2) { b2 = base; c2++; s2 += score; q2 += qual; x2 = max(x2, qual); }
+    }
+    GCB_DEV VoteBin bin(int k) const {
+        VoteBin v;
+        v.base = k == 0 ? b0 : k == 1 ? b1 : b2;
+        v.cnt = k == 0 ? c0 : k == 1 ? c1 : c2;
+        v.score = k == 0 ? s0 : k == 1 ? s1 : s2;
+        v.qual = k == 0 ? q0 : k == 1 ? q1 : q2;
+        v.maxq = k == 0 ? x0 : k == 1 ? x1 : x2;
+        return v;
+    }
+};
+
 // base, rewritten quality and score of a queue entry: the same function of the same bytes as fetch_vote
 GCB_DEV bool slow_decode(const ScoreTab &t, uint32_t ent, int side, int &base, int &qual, int &score) {
     if (!(ent & SE_VOTES)) return false;
@@ -439,11 +478,16 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
         out[col] = (uint8_t)oqual;
         return;
     }
-    SparseBins bins;
+    Bins3 bins;
     bins.init();
-    for (int e = 0; e < n; e++) {
-        int base, qual, score;
-        if (slow_decode(tab, ents[e], side, base, qual, score)) bins.add(base, qual, score);
+    for (int e = 0; e < n; e += 4) {  // (records are padded to whole 16-byte groups of entries)
+        const uint4 v = *(const uint4 *)(ents + e);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int base, qual, score;
+            if (e + k < n && slow_decode(tab, w[k], side, base, qual, score)) bins.add(base, qual, score);
+        }
     }
     ColumnTop ct;
     int total = bins.total;
@@ -457,11 +501,12 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
         unsigned long long key[3];
 #pragma unroll
         for (int kk = 0; kk < 3; kk++) {
-            const int bb = bins.s[kk].base;
+            const VoteBin vb = bins.bin(kk);
+            const int bb = vb.base;
             const bool have = bb >= 0;
-            key[kk] = have ? bin_key(bins.s[kk].score, bins.s[kk].qual, bb) : 0ull;
+            key[kk] = have ? bin_key(vb.score, vb.qual, bb) : 0ull;
             if (have) freemask &= ~(1u << bb);
-            if (have && (bb == 1 || bb == 2 || bb == 4 || bb == 8)) acgt |= (uint32_t)bins.s[kk].maxq << (bb == 1 ? 0 : bb == 2 ? 8 : bb == 4 ? 16 : 24);
+            if (have && (bb == 1 || bb == 2 || bb == 4 || bb == 8)) acgt |= (uint32_t)vb.maxq << (bb == 1 ? 0 : bb == 2 ? 8 : bb == 4 ? 16 : 24);
         }
         const int e1 = 31 - __clz((int)freemask);
         freemask &= ~(1u << e1);
@@ -473,8 +518,8 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
         sec = max_u64(sec, min_u64(top, ke2)); top = max_u64(top, ke2);
         const int tb = (int)(top & 0xF), sb = (int)(sec & 0xF);
         const VoteBin none = {0, 0, 0, 0, 0};
-        ct.top = bins.s[0].base == tb ? bins.s[0] : bins.s[1].base == tb ? bins.s[1] : bins.s[2].base == tb ? bins.s[2] : none;
-        ct.sec = bins.s[0].base == sb ? bins.s[0] : bins.s[1].base == sb ? bins.s[1] : bins.s[2].base == sb ? bins.s[2] : none;
+        ct.top = bins.b0 == tb ? bins.bin(0) : bins.b1 == tb ? bins.bin(1) : bins.b2 == tb ? bins.bin(2) : none;
+        ct.sec = bins.b0 == sb ? bins.bin(0) : bins.b1 == sb ? bins.bin(1) : bins.b2 == sb ? bins.bin(2) : none;
         ct.top.base = tb;
         ct.sec.base = sb;
         column_rules(o, ct, total);
