@@ -44,8 +44,9 @@ static_assert(sizeof(RingStage) == 64, "stage header size");
 constexpr int VR_OFF_FULL = 0;                                   // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_HDR = 128;                                  // RingStage[VR_MAX_STAGES]
-constexpr int VR_OFF_ITEMS = VR_OFF_HDR + 64 * VR_MAX_STAGES;    // per warp: uint32 word offsets[VR_ITEMS], uint16 codes[VR_ITEMS]
-constexpr int VR_ITEM_BYTES = 6 * VR_ITEMS;
+constexpr int VR_OFF_ITEMS = VR_OFF_HDR + 64 * VR_MAX_STAGES;    // per warp: uint16 codes[VR_ITEMS] (family side in the bundle << 9 | column)
+constexpr int VR_ITEM_BYTES = 2 * VR_ITEMS;
+constexpr int VR_POOL_RECS = 64, VR_POOL_WORDS = 64 * 20;  // queue space a warp reserves at a time
 constexpr int VR_OFF_HCACHE = (VR_OFF_ITEMS + VR_ITEM_BYTES * VR_WARPS + 15) & ~15;  // TileHdr2[32]: the producer's next tiles
 constexpr int VR_OFF_STAGE0 = (VR_OFF_HCACHE + 48 * WARP + 127) & ~127;
 // inside a stage
@@ -156,8 +157,12 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
     // ---- consumers
     const uint32_t mod4 = 0x01010101u * (uint32_t)(moderate_quality & 0xFF);
     const uint32_t sbase = smem_base(smem);
-    uint32_t *s_itemw = (uint32_t *)(smem + VR_OFF_ITEMS + VR_ITEM_BYTES * warp);
-    uint16_t *s_item = (uint16_t *)(s_itemw + VR_ITEMS);
+    uint16_t *s_item = (uint16_t *)(smem + VR_OFF_ITEMS + VR_ITEM_BYTES * warp);
+    // slow-column records go to the queue of this CTA; every warp keeps a pool of reserved records / words in registers
+    const int qi = (int)(blockIdx.x % VQ_NQ);
+    uint32_t *q_words = sq.words + (size_t)qi * sq.cap_words;
+    uint32_t *q_index = sq.index + (size_t)qi * sq.cap_recs;
+    uint32_t pool_r = 0u, pool_re = 0u, pool_w = 0u, pool_we = 0u;
     int s = 0, stage_off = VR_OFF_STAGE0;
     uint32_t par = 0u;
     for (;;) {
@@ -176,9 +181,6 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
             const int64_t out_base0 = sh->out_base0;
             uint8_t *out0 = r.out_payload + out_base0;
             const int tile = sh->tile;
-            const int qi = tile % VQ_NQ;
-            uint32_t *q_words = sq.words + (size_t)qi * sq.cap_words;
-            uint32_t *q_index = sq.index + (size_t)qi * sq.cap_recs;
             const int L = sh->lanes, S = sh->per_bundle;  // lanes per family side (1..32), family sides per bundle (32 / L)
             const int sub = (int)(((unsigned)lane * ((65535u / (unsigned)L) + 1u)) >> 16), j = lane - sub * L;  // lane / L, lane % L
             const int col0 = VT_CHUNK * j;
@@ -326,50 +328,54 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                     if (8 * j + 4 < sbytes) *(uint32_t *)(out + qbytes + 8 * j + 4) = bswap32(tbe1 & cm.kn1);
                     }
                 }
-                // ---- slow columns: one reservation per bundle (records << 32 | words), then the entries
+                // ---- slow columns: records of one size per bundle, taken from the warp's own pool of reserved queue space
                 const int nslow = (ablate & 1) ? 0 : __popc(slow0) + __popc(slow1);
-                if (__any_sync(FULL, nslow > 0)) {
-                    const uint32_t rec_words = slow_rec_words(ft.m);
+                const uint32_t T = (uint32_t)__reduce_add_sync(FULL, nslow);
+                if (T > 0) {
                     GCB_COUNT(3, nslow);
-                    const unsigned long long mine64 = ((unsigned long long)(uint32_t)nslow << 32) | ((uint32_t)nslow * rec_words);
-                    unsigned long long incl = mine64;
-                    for (int off = 1; off < WARP; off <<= 1) {
-                        const unsigned long long v = __shfl_up_sync(FULL, incl, off);
-                        if (lane >= off) incl += v;
+                    const uint32_t rw = slow_rec_words(mmax), W = T * rw;
+                    if (pool_r + T > pool_re || pool_w + W > pool_we) {
+                        // a new pool (one 64-bit atomic: records << 32 | words); what is left of the old one stays unused
+                        for (uint32_t i = pool_r + (uint32_t)lane; i < pool_re; i += WARP) q_index[i] = VQ_INVALID;
+                        const uint32_t need_r = T > (uint32_t)VR_POOL_RECS ? T : (uint32_t)VR_POOL_RECS;
+                        const uint32_t need_w = W > (uint32_t)VR_POOL_WORDS ? W : (uint32_t)VR_POOL_WORDS;
+                        unsigned long long base64 = 0ull;
+                        if (lane == 0) base64 = atomicAdd(sq.count + qi, ((unsigned long long)need_r << 32) | need_w);
+                        base64 = __shfl_sync(FULL, base64, 0);
+                        const uint32_t r0 = (uint32_t)(base64 >> 32), w0 = (uint32_t)base64;
+                        if ((unsigned long long)r0 + need_r <= sq.cap_recs && (unsigned long long)w0 + need_w <= sq.cap_words) {
+                            pool_r = r0; pool_re = r0 + need_r;
+                            pool_w = w0; pool_we = w0 + need_w;
+                        } else {  // the queue is full: the reserved index entries are marked unused, the pool stays empty
+                            for (uint32_t i = r0 + (uint32_t)lane; i < r0 + need_r && i < sq.cap_recs; i += WARP) q_index[i] = VQ_INVALID;
+                            pool_r = pool_re = pool_w = pool_we = 0u;
+                        }
                     }
-                    const unsigned long long total = __shfl_sync(FULL, incl, WARP - 1);
-                    unsigned long long base64 = 0ull;
-                    if (lane == 0) base64 = atomicAdd(sq.count + qi, total);
-                    base64 = __shfl_sync(FULL, base64, 0);
-                    const uint32_t rec0 = (uint32_t)(base64 >> 32), word0 = (uint32_t)base64, T = (uint32_t)(total >> 32);
-                    const bool fits = (unsigned long long)rec0 + T <= sq.cap_recs && (unsigned long long)word0 + (uint32_t)total <= sq.cap_words;
-                    uint32_t ri = (uint32_t)((incl - mine64) >> 32), wi = word0 + (uint32_t)(incl - mine64);  // this lane's first record / word
-                    if (!fits) {
-                        // the queue is full: the generic kernel redoes the whole tile from the payload (it runs after
-                        // slow_columns_kernel and vote_finalize_kernel); the reserved index entries are marked unused
-                        for (uint32_t i = (uint32_t)lane; i < T; i += WARP)
-                            if (rec0 + i < sq.cap_recs) q_index[rec0 + i] = VQ_INVALID;
+                    if (pool_r + T > pool_re) {
+                        // no queue space: the generic kernel redoes the whole tile from the payload (it runs after
+                        // slow_columns_kernel and vote_finalize_kernel)
                         if (lane == 0 && atomicExch(&sh->handed_over, 1) == 0) {
                             ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~tile;
                             GCB_COUNT(1, 1);
                         }
                     } else if (T <= (uint32_t)VR_ITEMS) {
-                        // every lane lists its columns; then eight lanes per column, one lane per read
-                        for (int wsel = 0; wsel < 2; wsel++) {
-                            uint32_t sm = wsel ? slow1 : slow0;
-                            while (sm != 0u) {
-                                const int kk = __clz((int)sm) >> 2;
-                                sm &= ~(0xF0000000u >> (4 * kk));
-                                s_item[ri] = (uint16_t)((sub << 9) | (col0 + 8 * wsel + kk));
-                                s_itemw[ri] = wi;
-                                ri++;
-                                wi += rec_words;
+                        // every lane lists its columns (one per round); then eight lanes per column, one lane per read
+                        unsigned long long sm64 = ((unsigned long long)slow0 << 32) | slow1;
+                        uint32_t listed = 0u;
+                        while (listed < T) {
+                            const bool has = sm64 != 0ull;
+                            const unsigned bal = __ballot_sync(FULL, has);
+                            if (has) {
+                                const int kk = __clzll((long long)sm64) >> 2;
+                                sm64 &= ~(0xF000000000000000ull >> (4 * kk));
+                                s_item[listed + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((sub << 9) | (col0 + kk));
                             }
+                            listed += __popc(bal);
                         }
                         __syncwarp();
                         const int g = lane / VR_GROUP, gl = lane % VR_GROUP;
                         for (uint32_t i = (uint32_t)g; i < T; i += WARP / VR_GROUP) {
-                            const uint32_t code = s_item[i], wofs = s_itemw[i];
+                            const uint32_t code = s_item[i], wofs = pool_w + i * rw;
                             const int col = (int)(code & 511u), fi = bundle * S + (int)(code >> 9);
                             const FsTile fti = s_ft[fi];
                             const uint8_t *cbp = smem + off_slab + 4 * (int)fti.cbase4;
@@ -377,7 +383,7 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                             uint32_t *rec = q_words + wofs;
                             const int mi = (int)fti.m;
                             if (gl == 0) {
-                                q_index[rec0 + i] = wofs;
+                                q_index[pool_r + i] = wofs;
                                 slow_write_header(rec, fti, col, out_base0 + 4 * (int64_t)fti.out4);
                             }
                             if ((fti.flags & FS_UNIFORM) && col < (int)fti.len) {
@@ -407,24 +413,37 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                             }
                         }
                         __syncwarp();
-                    } else if (nslow > 0) {
+                        pool_r += T;
+                        pool_w += W;
+                    } else {
                         // a bundle full of slow columns: every lane emits its own
-                        const uint8_t *cbp = smem + cb;
-                        const VoteRead *ents = s_vr + ft.ent0;
-                        for (int wsel = 0; wsel < 2; wsel++) {
-                            uint32_t sm = wsel ? slow1 : slow0;
-                            while (sm != 0u) {
-                                const int kk = __clz((int)sm) >> 2;
-                                sm &= ~(0xF0000000u >> (4 * kk));
-                                const int col = col0 + 8 * wsel + kk;
-                                uint32_t *rec = q_words + wi;
-                                q_index[rec0 + ri] = wi;
-                                slow_write_header(rec, ft, col, out_base0 + 4 * (int64_t)ft.out4);
-                                for (int e = 0; e < (int)ft.m; e++) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
-                                ri++;
-                                wi += rec_words;
+                        uint32_t incl = (uint32_t)nslow;
+                        for (int off = 1; off < WARP; off <<= 1) {
+                            const uint32_t v = __shfl_up_sync(FULL, incl, off);
+                            if (lane >= off) incl += v;
+                        }
+                        uint32_t ri = pool_r + incl - (uint32_t)nslow;
+                        if (nslow > 0) {
+                            const uint8_t *cbp = smem + cb;
+                            const VoteRead *ents = s_vr + ft.ent0;
+                            for (int wsel = 0; wsel < 2; wsel++) {
+                                uint32_t sm = wsel ? slow1 : slow0;
+                                while (sm != 0u) {
+                                    const int kk = __clz((int)sm) >> 2;
+                                    sm &= ~(0xF0000000u >> (4 * kk));
+                                    const int col = col0 + 8 * wsel + kk;
+                                    const uint32_t wofs = pool_w + (ri - pool_r) * rw;
+                                    uint32_t *rec = q_words + wofs;
+                                    q_index[ri] = wofs;
+                                    slow_write_header(rec, ft, col, out_base0 + 4 * (int64_t)ft.out4);
+                                    for (int e = 0; e < (int)ft.m; e++) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
+                                    ri++;
+                                }
                             }
                         }
+                        __syncwarp();
+                        pool_r += T;
+                        pool_w += W;
                     }
                 }
                 }
@@ -444,6 +463,8 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
             par ^= 1u;
         }
     }
+    // what is left of the warp's pool stays unused
+    for (uint32_t i = pool_r + (uint32_t)lane; i < pool_re; i += WARP) q_index[i] = VQ_INVALID;
 #undef GCB_LDS32
 }
 

@@ -353,6 +353,7 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return (unsigned)(v >> (shift & 31));
