@@ -138,12 +138,13 @@ TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode, int ring_window_sh
             p.window_shift = shift;
             p.window = 1 << shift;
             p.slab_cap = p.window + maxc;
-            p.stage_bytes = (VRS_OFF_SLAB + p.slab_cap + VT_SLAB_SLACK + 127) & ~127;
-            p.n_stages = (budget - 1 * KB - VR_OFF_STAGE0) / p.stage_bytes;
-            if (p.n_stages > VR_MAX_STAGES) p.n_stages = VR_MAX_STAGES;
-            if ((p.n_stages >= 3 || (shift == 14 && p.n_stages >= 2)) && p.slab_cap <= VT_MAX_SLAB) {
+            // the tiles in flight share one arena; a tile takes what it needs (family-side list, VoteRead table, slab)
+            const int32_t largest = (32 * VS_MAX_FS + 32 * VS_MAX_PAIRS + p.slab_cap + VT_SLAB_SLACK + 3 * 127) & ~127;
+            p.stage_bytes = (budget - 1 * KB - VR_OFF_ARENA - VR_GUARD) & ~127;  // the arena
+            p.n_stages = VR_MAX_STAGES;
+            if ((p.stage_bytes >= 3 * largest || (shift == 14 && p.stage_bytes >= 2 * largest)) && p.slab_cap <= VT_MAX_SLAB) {
                 p.staged = p.split = p.ring = 1;
-                p.smem = VR_OFF_STAGE0 + p.n_stages * p.stage_bytes;
+                p.smem = VR_OFF_ARENA + p.stage_bytes + VR_GUARD;
                 return p;
             }
         }

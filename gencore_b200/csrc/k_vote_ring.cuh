@@ -25,7 +25,9 @@ namespace gcb {
 
 constexpr int VR_MAX_THREADS = 768;           // the kernel is instantiated for 512 and 768 threads (128 / 85 registers)
 constexpr int VR_WARPS = VR_MAX_THREADS / WARP;
-constexpr int VR_MAX_STAGES = 6;
+constexpr int VR_MAX_STAGES = 8;   // tiles in flight (barrier pairs and stage headers); their bytes come from one arena
+constexpr int VR_GUARD = 4608;     // never allocated, after the arena: the branch-free read loop may read a VoteRead table or a
+                                   // slab up to 257 entries / 64 bytes past its end (values unused)
 constexpr int VR_ITEMS = 64;      // sparse slow columns of one bundle that are emitted cooperatively
 constexpr int VR_GROUP = 8;       // lanes per slow column in the cooperative emission
 
@@ -36,7 +38,8 @@ struct __align__(16) RingStage {  // shared memory, written by the producer befo
     int32_t p0, tile;
     int32_t next_bundle;  // atomic: next bundle to hand out
     int32_t handed_over;  // atomic: the tile went to the generic kernel (queue overflow)
-    int32_t pad[5];
+    int32_t ft_off, vr_off, slab_off;  // where the tile's family-side list, VoteRead table and payload slab lie (shared-memory offsets)
+    int32_t pad[2];
 };
 static_assert(sizeof(RingStage) == 64, "stage header size");
 
@@ -48,12 +51,11 @@ constexpr int VR_OFF_ITEMS = VR_OFF_HDR + 64 * VR_MAX_STAGES;    // per warp: ui
 constexpr int VR_ITEM_BYTES = 2 * VR_ITEMS;
 constexpr int VR_POOL_RECS = 64, VR_POOL_WORDS = 64 * 20;  // queue space a warp reserves at a time
 constexpr int VR_OFF_HCACHE = (VR_OFF_ITEMS + VR_ITEM_BYTES * VR_WARPS + 15) & ~15;  // TileHdr2[32]: the producer's next tiles
-constexpr int VR_OFF_STAGE0 = (VR_OFF_HCACHE + 48 * WARP + 127) & ~127;
-// inside a stage
-constexpr int VRS_OFF_FT = 0;                                    // FsTile[VS_MAX_FS]
-constexpr int VRS_OFF_VR = VRS_OFF_FT + 32 * VS_MAX_FS;          // VoteRead[2*VS_MAX_PAIRS]
-constexpr int VRS_OFF_SLAB = (VRS_OFF_VR + 32 * VS_MAX_PAIRS + 127) & ~127;
-static_assert(16 * VR_MAX_STAGES <= VR_OFF_HDR && VRS_OFF_VR % 16 == 0 && VR_OFF_STAGE0 % 128 == 0, "ring layout");
+constexpr int VR_OFF_START = VR_OFF_HCACHE + 48 * WARP;          // uint32[VR_MAX_STAGES]: the producer's allocation starts
+constexpr int VR_OFF_ARENA = (VR_OFF_START + 4 * VR_MAX_STAGES + 127) & ~127;
+// a tile's allocation: [FsTile list][VoteRead table][slab + slack], each part rounded to 128 bytes
+static_assert(16 * VR_MAX_STAGES <= VR_OFF_HDR && VR_OFF_ARENA % 128 == 0, "ring layout");
+GCB_HD uint32_t ring_round128(uint32_t v) { return (v + 127u) & ~127u; }
 
 // a wait that lets the hardware suspend the thread between polls (a spinning warp takes issue slots from the warps that vote)
 #ifndef GCB_SIMT_CHECK
@@ -80,7 +82,7 @@ inline void pipe_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t) { pipe_w
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, int32_t moderate_quality, int32_t implied,
                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, int32_t n_tiles,
-                                                                  int32_t n_stages, int32_t stage_bytes, int32_t ablate) {
+                                                                  int32_t n_stages, int32_t arena_bytes, int32_t ablate) {
     // `ablate` (profiling only, 0 in production; results are wrong otherwise): 1 = no slow-column emission, 2 = no read loop,
     // 4 = no record stores, 8 = no bundle work at all
     GCB_DYN_SMEM(smem);
@@ -102,7 +104,28 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
         // ---- producer: lane 0 fills the stages, up to n_stages tiles ahead of the consumers; the whole warp fetches the
         // headers of this CTA's next 32 tiles at once, so that no tile waits for a header on its way from global memory
         TileHdr2 *hcache = (TileHdr2 *)(smem + VR_OFF_HCACHE);
-        int k = 0;
+        uint32_t *s_start = (uint32_t *)(smem + VR_OFF_START);
+        // tiles [oldest, k) are in flight; their allocations form the circular range [tail, head) of the arena
+        int k = 0, oldest = 0;
+        uint32_t head = 0u, tail = 0u;
+        // room for `need` bytes and a free slot, waiting for the oldest tiles to be released as long as there is none
+        auto allocate = [&](uint32_t need) -> uint32_t {
+            for (;;) {
+                if (k == oldest) head = tail = 0u;
+                if (k - oldest < n_stages) {
+                    const bool wrapped = k > oldest && head <= tail;
+                    if (!wrapped) {
+                        if (head + need <= (uint32_t)arena_bytes) return head;
+                        if (need <= tail) return 0u;  // (the end of the arena stays unused until the range wraps)
+                    } else if (head + need <= tail) {
+                        return head;
+                    }
+                }
+                pipe_wait_backoff(empty + oldest % n_stages, (uint32_t)((oldest / n_stages) & 1), 2000u);  // every consumer has left it
+                oldest++;
+                tail = oldest < k ? s_start[oldest % n_stages] : head;
+            }
+        };
         for (int64_t base = (int64_t)blockIdx.x; base < n_tiles; base += (int64_t)WARP * gridDim.x) {
             const int64_t mine_t = base + (int64_t)lane * gridDim.x;
             if (mine_t < n_tiles) hcache[lane] = hdr[mine_t];
@@ -113,9 +136,12 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                     if (t >= n_tiles) break;
                     const TileHdr2 cur = hcache[i];
                     if (cur.nfs <= 0) continue;  // nothing for this kernel here (empty tile, or the generic kernel has it)
-                    const int s = k % n_stages, use = k / n_stages;
-                    if (use > 0) pipe_wait_backoff(empty + s, (uint32_t)((use - 1) & 1), 2000u);  // every consumer has left the stage's previous tile
-                    uint8_t *stage = smem + VR_OFF_STAGE0 + (size_t)s * stage_bytes;
+                    const uint32_t slab_bytes = (uint32_t)cur.slab_bytes, vr_bytes = 32u * (uint32_t)cur.np, ft_bytes = 32u * (uint32_t)cur.nfs;
+                    const uint32_t need = ring_round128(ft_bytes) + ring_round128(vr_bytes) + ring_round128(slab_bytes + VT_SLAB_SLACK);
+                    const uint32_t at = allocate(need);
+                    const int s = k % n_stages;
+                    s_start[s] = at;
+                    head = at + need;
                     RingStage sh;
                     sh.out_base0 = cur.out_base0;
                     sh.nfs = cur.nfs;
@@ -123,13 +149,15 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                     sh.p0 = cur.p0; sh.tile = (int32_t)t;
                     sh.next_bundle = 0;
                     sh.handed_over = 0;
-                    sh.pad[0] = sh.pad[1] = sh.pad[2] = sh.pad[3] = sh.pad[4] = 0;
+                    sh.ft_off = VR_OFF_ARENA + (int32_t)at;
+                    sh.vr_off = sh.ft_off + (int32_t)ring_round128(ft_bytes);
+                    sh.slab_off = sh.vr_off + (int32_t)ring_round128(vr_bytes);
+                    sh.pad[0] = sh.pad[1] = 0;
                     shdr[s] = sh;
-                    const uint32_t slab_bytes = (uint32_t)cur.slab_bytes, vr_bytes = 32u * (uint32_t)cur.np, ft_bytes = 32u * (uint32_t)cur.nfs;
                     pipe_expect(full + s, slab_bytes + vr_bytes + ft_bytes);
-                    if (slab_bytes > 0) tile_copy(stage + VRS_OFF_SLAB, b.payload + cur.slab0, slab_bytes, full + s);
-                    tile_copy(stage + VRS_OFF_VR, ws.vote_reads + 2 * (int64_t)cur.p0, vr_bytes, full + s);
-                    tile_copy(stage + VRS_OFF_FT, fs_tiles + 2 * (int64_t)cur.p0, ft_bytes, full + s);
+                    if (slab_bytes > 0) tile_copy(smem + sh.slab_off, b.payload + cur.slab0, slab_bytes, full + s);
+                    tile_copy(smem + sh.vr_off, ws.vote_reads + 2 * (int64_t)cur.p0, vr_bytes, full + s);
+                    tile_copy(smem + sh.ft_off, fs_tiles + 2 * (int64_t)cur.p0, ft_bytes, full + s);
                     pipe_commit(full + s);
                     k++;
                 }
@@ -137,8 +165,8 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
             __syncwarp();
         }
         if (lane == 0) {  // the end marker: the phase completes with this arrival alone
-            const int s = k % n_stages, use = k / n_stages;
-            if (use > 0) pipe_wait_backoff(empty + s, (uint32_t)((use - 1) & 1), 2000u);
+            allocate(0u);
+            const int s = k % n_stages;
             RingStage sh;
             sh.out_base0 = 0;
             sh.nfs = -1;
@@ -146,7 +174,8 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
             sh.p0 = 0; sh.tile = 0;
             sh.next_bundle = 0;
             sh.handed_over = 0;
-            sh.pad[0] = sh.pad[1] = sh.pad[2] = sh.pad[3] = sh.pad[4] = 0;
+            sh.ft_off = sh.vr_off = sh.slab_off = VR_OFF_ARENA;
+            sh.pad[0] = sh.pad[1] = 0;
             shdr[s] = sh;
             pipe_expect(full + s, 0u);
             pipe_commit(full + s);
@@ -163,7 +192,7 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
     uint32_t *q_words = sq.words + (size_t)qi * sq.cap_words;
     uint32_t *q_index = sq.index + (size_t)qi * sq.cap_recs;
     uint32_t pool_r = 0u, pool_re = 0u, pool_w = 0u, pool_we = 0u;
-    int s = 0, stage_off = VR_OFF_STAGE0;
+    int s = 0;
     uint32_t par = 0u;
     for (;;) {
         pipe_wait_backoff(full + s, par, 1000u);
@@ -175,9 +204,9 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
         if (lane == 0 && *(volatile int32_t *)&sh->next_bundle < nb) bundle = atomicAdd(&sh->next_bundle, 1);  // (no atomic on a drained tile)
         bundle = __shfl_sync(FULL, bundle, 0);
         if (bundle < nb) {
-            const FsTile *s_ft = (const FsTile *)(smem + stage_off + VRS_OFF_FT);
-            const VoteRead *s_vr = (const VoteRead *)(smem + stage_off + VRS_OFF_VR);
-            const int off_slab = stage_off + VRS_OFF_SLAB, off_vr = stage_off + VRS_OFF_VR;
+            const int off_slab = sh->slab_off, off_vr = sh->vr_off;
+            const FsTile *s_ft = (const FsTile *)(smem + sh->ft_off);
+            const VoteRead *s_vr = (const VoteRead *)(smem + off_vr);
             const int64_t out_base0 = sh->out_base0;
             uint8_t *out0 = r.out_payload + out_base0;
             const int tile = sh->tile;
@@ -456,10 +485,8 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
         __syncwarp();
         if (lane == 0) pipe_arrive(empty + s);
         s++;
-        stage_off += stage_bytes;
         if (s == n_stages) {
             s = 0;
-            stage_off = VR_OFF_STAGE0;
             par ^= 1u;
         }
     }

@@ -57,7 +57,7 @@ static_assert(VS_OFF_FT % 16 == 0 && VS_OFF_VR % 16 == 0, "16-byte aligned table
 // One CTA per tile, one thread per pair position (VS_PREP_ROUNDS rounds of VS_PREP_THREADS positions): what the tiled
 // kernel's prologue computes, once per batch.  The CTA is small so that many tiles' chains of dependent loads
 // (directory -> side modes -> family-side descriptors -> cluster offsets) are in flight on an SM at once.
-__global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b, ResultView r, Workspace ws, int32_t slab_cap, TileHdr2 *hdr,
+__global__ void __launch_bounds__(VS_PREP_THREADS, 10) tile_prep2_kernel(BatchView b, ResultView r, Workspace ws, int32_t slab_cap, TileHdr2 *hdr,
                                                                       FsTile *fs_tiles) {
     __shared__ uint32_t s_wsum[VS_PREP_ROUNDS][VS_PREP_THREADS / WARP];
     __shared__ int s_nofit, s_lmax, s_common;
@@ -95,6 +95,12 @@ __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b
         const int pos = rd * VS_PREP_THREADS + tid;
         fd[rd][0].mode = fd[rd][1].mode = SIDE_NONE;
         fd[rd][0].c = fd[rd][1].c = c0;
+        if (rd > 0 && NP <= rd * VS_PREP_THREADS) {  // (the usual tile needs one round)
+            c_slab[rd] = c_out[rd] = 0;
+            mine[rd] = incl[rd] = 0u;
+            if (lane == WARP - 1) s_wsum[rd][warp] = 0u;
+            continue;
+        }
         if (pos < NP) {  // slots that hold no family carry SIDE_NONE in side_mode and garbage in fs_desc
             const uint16_t modes = *(const uint16_t *)(ws.side_mode + 2 * (int64_t)(P0 + pos));
             if ((modes & 0xFF) != SIDE_NONE) fd[rd][0] = ws.fs_desc[2 * (int64_t)(P0 + pos)];
