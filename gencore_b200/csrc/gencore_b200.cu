@@ -335,7 +335,9 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
             FsTile *fst = (FsTile *)ctx->w_fstiles.p;
             if (run_prep) {
                 GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
-                GCB_LAUNCH(tile_prep2_kernel, dim3((unsigned)n_tiles), dim3(VS_PREP_THREADS), 0, stream, b, r, ws, plan.slab_cap, thdr, fst);
+                int32_t *max_need = (int32_t *)ctx->w_pcount.p + v.index;  // (the pipelined mode's tile counter is free in this mode)
+                GCB_CUDA(ctx, cudaMemsetAsync(max_need, 0, 4, stream));
+                GCB_LAUNCH(tile_prep2_kernel, dim3((unsigned)n_tiles), dim3(VS_PREP_THREADS), 0, stream, b, r, ws, plan.slab_cap, thdr, fst, max_need);
                 ctx->launches++;
             }
             if (run_vote && plan.split) {
@@ -354,11 +356,11 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                     if (ctx->ring_threads == 768)
                         GCB_LAUNCH(vote_ring_kernel<768>, dim3(ring_grid), dim3(768), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
                                    fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
-                                   plan.stage_bytes, ctx->ablate);
+                                   plan.stage_bytes, (const int32_t *)ctx->w_pcount.p + v.index, ctx->ablate);
                     else
                         GCB_LAUNCH(vote_ring_kernel<512>, dim3(ring_grid), dim3(512), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
                                    fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
-                                   plan.stage_bytes, ctx->ablate);
+                                   plan.stage_bytes, (const int32_t *)ctx->w_pcount.p + v.index, ctx->ablate);
                 } else {
                     GCB_LAUNCH(vote_fast_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
                                ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq);

@@ -82,7 +82,8 @@ inline void pipe_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t) { pipe_w
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, int32_t moderate_quality, int32_t implied,
                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, int32_t n_tiles,
-                                                                  int32_t n_stages, int32_t arena_bytes, int32_t ablate) {
+                                                                  int32_t max_stages, int32_t arena_bytes, const int32_t *max_need,
+                                                                  int32_t ablate) {
     // `ablate` (profiling only, 0 in production; results are wrong otherwise): 1 = no slow-column emission, 2 = no read loop,
     // 4 = no record stores, 8 = no bundle work at all
     GCB_DYN_SMEM(smem);
@@ -91,6 +92,10 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
     RingStage *shdr = (RingStage *)(smem + VR_OFF_HDR);
 #define GCB_LDS32(off) (*(const uint32_t *)(smem + (off)))
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    // the arena is cut into equal stages that hold the batch's largest tile (tile_prep2_kernel measured it): as many tiles in
+    // flight as fit
+    const int32_t stage_bytes = (int32_t)ring_round128((uint32_t)max(*max_need, 128));
+    const int n_stages = min(max_stages, max(arena_bytes / stage_bytes, 1));
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
             pipe_init(full + s, 1);
@@ -104,27 +109,12 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
         // ---- producer: lane 0 fills the stages, up to n_stages tiles ahead of the consumers; the whole warp fetches the
         // headers of this CTA's next 32 tiles at once, so that no tile waits for a header on its way from global memory
         TileHdr2 *hcache = (TileHdr2 *)(smem + VR_OFF_HCACHE);
-        uint32_t *s_start = (uint32_t *)(smem + VR_OFF_START);
-        // tiles [oldest, k) are in flight; their allocations form the circular range [tail, head) of the arena
-        int k = 0, oldest = 0;
-        uint32_t head = 0u, tail = 0u;
-        // room for `need` bytes and a free slot, waiting for the oldest tiles to be released as long as there is none
-        auto allocate = [&](uint32_t need) -> uint32_t {
-            for (;;) {
-                if (k == oldest) head = tail = 0u;
-                if (k - oldest < n_stages) {
-                    const bool wrapped = k > oldest && head <= tail;
-                    if (!wrapped) {
-                        if (head + need <= (uint32_t)arena_bytes) return head;
-                        if (need <= tail) return 0u;  // (the end of the arena stays unused until the range wraps)
-                    } else if (head + need <= tail) {
-                        return head;
-                    }
-                }
-                pipe_wait_backoff(empty + oldest % n_stages, (uint32_t)((oldest / n_stages) & 1), 2000u);  // every consumer has left it
-                oldest++;
-                tail = oldest < k ? s_start[oldest % n_stages] : head;
-            }
+        int k = 0;
+        // stage k % n_stages once every consumer has left the tile it held before
+        auto allocate = [&]() -> uint32_t {
+            const int s = k % n_stages, use = k / n_stages;
+            if (use > 0) pipe_wait_backoff(empty + s, (uint32_t)((use - 1) & 1), 2000u);
+            return (uint32_t)s * (uint32_t)stage_bytes;
         };
         for (int64_t base = (int64_t)blockIdx.x; base < n_tiles; base += (int64_t)WARP * gridDim.x) {
             const int64_t mine_t = base + (int64_t)lane * gridDim.x;
@@ -137,11 +127,8 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                     const TileHdr2 cur = hcache[i];
                     if (cur.nfs <= 0) continue;  // nothing for this kernel here (empty tile, or the generic kernel has it)
                     const uint32_t slab_bytes = (uint32_t)cur.slab_bytes, vr_bytes = 32u * (uint32_t)cur.np, ft_bytes = 32u * (uint32_t)cur.nfs;
-                    const uint32_t need = ring_round128(ft_bytes) + ring_round128(vr_bytes) + ring_round128(slab_bytes + VT_SLAB_SLACK);
-                    const uint32_t at = allocate(need);
+                    const uint32_t at = allocate();
                     const int s = k % n_stages;
-                    s_start[s] = at;
-                    head = at + need;
                     RingStage sh;
                     sh.out_base0 = cur.out_base0;
                     sh.nfs = cur.nfs;
@@ -165,7 +152,7 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
             __syncwarp();
         }
         if (lane == 0) {  // the end marker: the phase completes with this arrival alone
-            allocate(0u);
+            allocate();
             const int s = k % n_stages;
             RingStage sh;
             sh.out_base0 = 0;

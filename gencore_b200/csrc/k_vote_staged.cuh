@@ -58,7 +58,7 @@ static_assert(VS_OFF_FT % 16 == 0 && VS_OFF_VR % 16 == 0, "16-byte aligned table
 // kernel's prologue computes, once per batch.  The CTA is small so that many tiles' chains of dependent loads
 // (directory -> side modes -> family-side descriptors -> cluster offsets) are in flight on an SM at once.
 __global__ void __launch_bounds__(VS_PREP_THREADS, 10) tile_prep2_kernel(BatchView b, ResultView r, Workspace ws, int32_t slab_cap, TileHdr2 *hdr,
-                                                                      FsTile *fs_tiles) {
+                                                                          FsTile *fs_tiles, int32_t *max_need) {
     __shared__ uint32_t s_wsum[VS_PREP_ROUNDS][VS_PREP_THREADS / WARP];
     __shared__ int s_nofit, s_lmax, s_common;
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -195,6 +195,9 @@ __global__ void __launch_bounds__(VS_PREP_THREADS, 10) tile_prep2_kernel(BatchVi
             h.common_l = s_common;
             h.per_bundle = 32 / s_lmax;
             h.n_bundles = ((int32_t)total + h.per_bundle - 1) / h.per_bundle;
+            // shared memory the tile takes in the ring kernel: family-side list, VoteRead table, slab + slack, each rounded to 128
+            atomicMax(max_need, (int32_t)(((32 * (int32_t)total + 127) & ~127) + ((32 * NP + 127) & ~127) +
+                                          (((int32_t)slab_bytes + VT_SLAB_SLACK + 127) & ~127)));
             GCB_COUNT(0, 1);
         }
         hdr[blockIdx.x] = h;
