@@ -24,6 +24,7 @@ GROUP_DROPPED, GROUP_SSCS, GROUP_DCS, GROUP_DUPLEX_PARTNER, GROUP_DUPLEX_DIFF, G
 
 STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_SCORE_VOTE, STAGE_DUPLEX, STAGE_ALL = 1, 2, 4, 8, 15
 STAGE_VOTE_PREP_ONLY, STAGE_VOTE_ONLY = 16, 32  # measurement only: the two halves of STAGE_SCORE_VOTE
+STAGE_VOTE_FAST_ONLY, STAGE_VOTE_REST_ONLY = 64, 128  # vote modes 3 and 4: the two halves of STAGE_VOTE_ONLY
 
 
 def align4(x):

@@ -312,7 +312,10 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
     }
     const bool run_prep = (stages & (GCB_STAGE_SCORE_VOTE | GCB_STAGE_VOTE_PREP_ONLY)) != 0;
     const bool run_vote = (stages & (GCB_STAGE_SCORE_VOTE | GCB_STAGE_VOTE_ONLY)) != 0;
-    if ((run_prep || run_vote) && n_tiles > 0) {
+    // split vote modes, measurement only: the fast kernel and (slow columns + finalize + generic) one at a time
+    const bool run_fast = run_vote || (stages & GCB_STAGE_VOTE_FAST_ONLY) != 0;
+    const bool run_rest = run_vote || (stages & GCB_STAGE_VOTE_REST_ONLY) != 0;
+    if ((run_prep || run_fast || run_rest) && n_tiles > 0) {
         if (plan.pipelined) {
             TileHdr *thdr = (TileHdr *)ctx->w_thdr.p + v.tile_base;
             FsTile *fst = (FsTile *)ctx->w_fstiles.p;
@@ -340,7 +343,7 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                 GCB_LAUNCH(tile_prep2_kernel, dim3((unsigned)n_tiles), dim3(VS_PREP_THREADS), 0, stream, b, r, ws, plan.slab_cap, thdr, fst, max_need);
                 ctx->launches++;
             }
-            if (run_vote && plan.split) {
+            if ((run_fast || run_rest) && plan.split) {
                 // chunks of one batch run one after another on the stream and share the queues; every chunk has its own counters
                 SlowQueues sq;
                 sq.count = (unsigned long long *)ctx->w_sq_count.p + (size_t)VQ_NQ * v.index;
@@ -349,27 +352,32 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                 sq.cap_words = ctx->sq_cap_words;
                 sq.cap_recs = ctx->sq_cap_recs;
                 sq.acc = (int32_t *)ctx->w_sq_acc.p;
-                GCB_CUDA(ctx, cudaMemsetAsync(sq.count, 0, 8 * VQ_NQ, stream));
-                if (v.p1 > v.p0) GCB_CUDA(ctx, cudaMemsetAsync(sq.acc + 2 * (size_t)v.p0, 0, 8 * (size_t)(v.p1 - v.p0), stream));
-                if (plan.ring) {
-                    const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
-                    if (ctx->ring_threads == 768)
-                        GCB_LAUNCH(vote_ring_kernel<768>, dim3(ring_grid), dim3(768), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
-                                   fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
-                                   plan.stage_bytes, (const int32_t *)ctx->w_pcount.p + v.index, ctx->ablate);
-                    else
-                        GCB_LAUNCH(vote_ring_kernel<512>, dim3(ring_grid), dim3(512), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
-                                   fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
-                                   plan.stage_bytes, (const int32_t *)ctx->w_pcount.p + v.index, ctx->ablate);
-                } else {
-                    GCB_LAUNCH(vote_fast_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
-                               ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
+                if (run_fast) {
+                    GCB_CUDA(ctx, cudaMemsetAsync(sq.count, 0, 8 * VQ_NQ, stream));
+                    if (v.p1 > v.p0) GCB_CUDA(ctx, cudaMemsetAsync(sq.acc + 2 * (size_t)v.p0, 0, 8 * (size_t)(v.p1 - v.p0), stream));
+                    if (plan.ring) {
+                        const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
+                        if (ctx->ring_threads == 768)
+                            GCB_LAUNCH(vote_ring_kernel<768>, dim3(ring_grid), dim3(768), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
+                                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
+                                       plan.stage_bytes, (const int32_t *)ctx->w_pcount.p + v.index, ctx->ablate);
+                        else
+                            GCB_LAUNCH(vote_ring_kernel<512>, dim3(ring_grid), dim3(512), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
+                                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
+                                       plan.stage_bytes, (const int32_t *)ctx->w_pcount.p + v.index, ctx->ablate);
+                    } else {
+                        GCB_LAUNCH(vote_fast_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
+                                   ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
+                    }
+                    ctx->launches++;
                 }
-                GCB_LAUNCH(slow_columns_kernel, dim3(VQ_NQ * VQ_SLOW_PARTS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ctx->genome, ctx->opt, sq);
-                if (v.p1 > v.p0)
-                    GCB_LAUNCH(vote_finalize_kernel, dim3((unsigned)((2 * (int64_t)(v.p1 - v.p0) + VQ_FINAL_THREADS - 1) / VQ_FINAL_THREADS)),
-                               dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->opt, sq, v.p0, v.p1);
-                ctx->launches += 3;
+                if (run_rest) {
+                    GCB_LAUNCH(slow_columns_kernel, dim3(VQ_NQ * VQ_SLOW_PARTS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ctx->genome, ctx->opt, sq);
+                    if (v.p1 > v.p0)
+                        GCB_LAUNCH(vote_finalize_kernel, dim3((unsigned)((2 * (int64_t)(v.p1 - v.p0) + VQ_FINAL_THREADS - 1) / VQ_FINAL_THREADS)),
+                                   dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->opt, sq, v.p0, v.p1);
+                    ctx->launches += 2;
+                }
             } else if (run_vote) {
                 GCB_LAUNCH(vote_staged_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
                            ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst);
@@ -381,7 +389,7 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                        plan.slab_cap, fast_path_implied(ctx->opt));
             ctx->launches++;
         }
-        if (run_vote) {  // the tiles the kernels above handed over (an empty list costs one CTA wave of a few microseconds)
+        if (run_vote || (run_rest && plan.split)) {  // the tiles the kernels above handed over (an empty list costs a few microseconds)
             const unsigned generic_grid = (unsigned)(n_tiles < 2 * 148 ? n_tiles : 2 * 148);
             GCB_LAUNCH(score_vote_kernel, dim3(generic_grid), dim3(VOTE_THREADS), VOTE_SMEM, stream, b, r, ws, ctx->genome, ctx->opt);
             ctx->launches++;

@@ -393,7 +393,7 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
 
 // group.cpp:68-134 per family of the cluster + the per-pair overlap windows of pair.cpp:103-119
 template <int GS>
-__global__ void __launch_bounds__(GROUP_THREADS) select_template_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o) {
+__global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o) {
     const Grp<GS> g;
     const int lane = g.gl;
     const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (WARP / GS) + (lane_id() / GS);

@@ -39,7 +39,8 @@ struct __align__(16) RingStage {  // shared memory, written by the producer befo
     int32_t next_bundle;  // atomic: next bundle to hand out
     int32_t handed_over;  // atomic: the tile went to the generic kernel (queue overflow)
     int32_t ft_off, vr_off, slab_off;  // where the tile's family-side list, VoteRead table and payload slab lie (shared-memory offsets)
-    int32_t pad[2];
+    int32_t first_ticket;              // bundles of this CTA's earlier tiles, modulo the number of consumer warps
+    int32_t pad[1];
 };
 static_assert(sizeof(RingStage) == 64, "stage header size");
 
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
         // ---- producer: lane 0 fills the stages, up to n_stages tiles ahead of the consumers; the whole warp fetches the
         // headers of this CTA's next 32 tiles at once, so that no tile waits for a header on its way from global memory
         TileHdr2 *hcache = (TileHdr2 *)(smem + VR_OFF_HCACHE);
-        int k = 0;
+        int k = 0, ticket = 0;
         // stage k % n_stages once every consumer has left the tile it held before
         auto allocate = [&]() -> uint32_t {
             const int s = k % n_stages, use = k / n_stages;
@@ -139,7 +140,9 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                     sh.ft_off = VR_OFF_ARENA + (int32_t)at;
                     sh.vr_off = sh.ft_off + (int32_t)ring_round128(ft_bytes);
                     sh.slab_off = sh.vr_off + (int32_t)ring_round128(vr_bytes);
-                    sh.pad[0] = sh.pad[1] = 0;
+                    sh.first_ticket = ticket;
+                    ticket = (ticket + cur.n_bundles) % (NT / WARP - 1);
+                    sh.pad[0] = 0;
                     shdr[s] = sh;
                     pipe_expect(full + s, slab_bytes + vr_bytes + ft_bytes);
                     if (slab_bytes > 0) tile_copy(smem + sh.slab_off, b.payload + cur.slab0, slab_bytes, full + s);
@@ -162,7 +165,8 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
             sh.next_bundle = 0;
             sh.handed_over = 0;
             sh.ft_off = sh.vr_off = sh.slab_off = VR_OFF_ARENA;
-            sh.pad[0] = sh.pad[1] = 0;
+            sh.first_ticket = 0;
+            sh.pad[0] = 0;
             shdr[s] = sh;
             pipe_expect(full + s, 0u);
             pipe_commit(full + s);
@@ -187,9 +191,17 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
         const int nfs = sh->nfs;
         if (nfs < 0) break;
         const int nb = sh->n_bundles;
+        // bundles are dealt round-robin over the consumer warps, across tiles: bundle i of this tile is ticket first_ticket + i
+        constexpr int NC = NT / WARP - 1;
+        const bool deal = (ablate & 16) != 0;  // (tuning aid: static round-robin instead of the stage's counter)
         int bundle = nb;
-        if (lane == 0 && *(volatile int32_t *)&sh->next_bundle < nb) bundle = atomicAdd(&sh->next_bundle, 1);  // (no atomic on a drained tile)
-        bundle = __shfl_sync(FULL, bundle, 0);
+        if (deal) {
+            bundle = (warp - 1) - sh->first_ticket;
+            if (bundle < 0) bundle += NC;
+        } else {
+            if (lane == 0 && *(volatile int32_t *)&sh->next_bundle < nb) bundle = atomicAdd(&sh->next_bundle, 1);  // (no atomic on a drained tile)
+            bundle = __shfl_sync(FULL, bundle, 0);
+        }
         if (bundle < nb) {
             const int off_slab = sh->slab_off, off_vr = sh->vr_off;
             const FsTile *s_ft = (const FsTile *)(smem + sh->ft_off);
@@ -464,8 +476,12 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                 }
                 }
             next_bundle:
-                if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
-                bundle = __shfl_sync(FULL, bundle, 0);
+                if (deal) {
+                    bundle += NC;
+                } else {
+                    if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
+                    bundle = __shfl_sync(FULL, bundle, 0);
+                }
                 pipe_progress();
             } while (bundle < nb);
         }

@@ -156,6 +156,9 @@ typedef struct gcb_result {
 /* measurement only: the two halves of GCB_STAGE_SCORE_VOTE one at a time (per-tile preparation, then the vote) */
 #define GCB_STAGE_VOTE_PREP_ONLY 0x10u
 #define GCB_STAGE_VOTE_ONLY 0x20u
+/* vote modes 3 and 4 only: the two halves of GCB_STAGE_VOTE_ONLY (fast-column kernel; slow columns + finalize + generic) */
+#define GCB_STAGE_VOTE_FAST_ONLY 0x40u
+#define GCB_STAGE_VOTE_REST_ONLY 0x80u
 
 typedef struct gcb_ctx gcb_ctx;
 
