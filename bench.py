@@ -250,13 +250,14 @@ def b200_arm(args):
     assert eng.batch_status() == 0, "device error flag raised during warm-up"
     if args.sweep and rank == 0:  # tuning aid: stage times of other (vote mode, threads) settings, to stderr
         for item in args.sweep.split(","):
-            parts = item.split(":")  # mode:threads[:ablate[:window_shift]]
+            parts = item.split(":")  # mode:threads[:ablate[:window_shift[:units per lane]]]
             mode_s, thr_s = parts[0], parts[1]
             eng.set_vote_mode(int(mode_s))
             eng.set_vote_threads(int(thr_s))
             eng.set_debug(1, int(parts[2]) if len(parts) > 2 else 0)
             eng.set_debug(2, int(parts[3]) if len(parts) > 3 else 0)
-            if len(parts) > 3:  # the tile directory depends on the window: rebuild it
+            eng.set_debug(4, int(parts[4]) if len(parts) > 4 else 1)
+            if len(parts) > 3 and int(parts[3]):  # the tile directory depends on the window: rebuild it
                 eng.cluster_by_umi_device(db.struct, dr.struct, STAGE_UMI_GROUP, stream)
                 eng.cluster_by_umi_device(db.struct, dr.struct, STAGE_SELECT_TEMPLATE, stream)
             sw_stages = [STAGE_SCORE_VOTE] if int(mode_s) == 0 else [STAGE_VOTE_PREP_ONLY, STAGE_VOTE_ONLY] if int(mode_s) < 3 else \
@@ -278,6 +279,7 @@ def b200_arm(args):
         eng.set_vote_threads(args.vote_threads)
         eng.set_debug(1, 0)
         eng.set_debug(2, 0)
+        eng.set_debug(4, 1)
         if args.sweep_only:
             eng.close()
             return

@@ -54,6 +54,7 @@ struct gcb_ctx {
     uint32_t sq_cap_words = 0, sq_cap_recs = 0;     // per queue
     int vote_threads = 256;                         // threads per CTA of vote_staged_kernel / vote_fast_kernel
     int ring_threads = 512;                         // threads per CTA of vote_ring_kernel (512 or 768)
+    int ring_units = 1;                             // units of sixteen columns per lane in vote_ring_kernel (1 or 2)
     int ring_window_shift = 0;                      // 0 = chosen by plan_tiles; 14 / 15 = forced (tuning)
     int group_lanes = 0;                            // lanes per cluster in umi_group / select_template (0 = by mean cluster size)
     int ablate = 0;                                 // profiling only (GCB_ABLATE): parts of the ring kernel switched off
@@ -357,14 +358,15 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                     if (v.p1 > v.p0) GCB_CUDA(ctx, cudaMemsetAsync(sq.acc + 2 * (size_t)v.p0, 0, 8 * (size_t)(v.p1 - v.p0), stream));
                     if (plan.ring) {
                         const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
-                        if (ctx->ring_threads == 768)
-                            GCB_LAUNCH(vote_ring_kernel<768>, dim3(ring_grid), dim3(768), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
-                                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
-                                       plan.stage_bytes, (const int32_t *)ctx->w_pcount.p + v.index, ctx->ablate);
-                        else
-                            GCB_LAUNCH(vote_ring_kernel<512>, dim3(ring_grid), dim3(512), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
-                                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages,
-                                       plan.stage_bytes, (const int32_t *)ctx->w_pcount.p + v.index, ctx->ablate);
+#define GCB_RING_LAUNCH(NT, NU)                                                                                                              \
+    GCB_LAUNCH((vote_ring_kernel<NT, NU>), dim3(ring_grid), dim3(NT), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,           \
+               fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages, plan.stage_bytes, \
+               (const int32_t *)ctx->w_pcount.p + v.index, ctx->ablate)
+                        if (ctx->ring_threads == 768 && ctx->ring_units == 2) GCB_RING_LAUNCH(768, 2);
+                        else if (ctx->ring_threads == 768) GCB_RING_LAUNCH(768, 1);
+                        else if (ctx->ring_units == 2) GCB_RING_LAUNCH(512, 2);
+                        else GCB_RING_LAUNCH(512, 1);
+#undef GCB_RING_LAUNCH
                     } else {
                         GCB_LAUNCH(vote_fast_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
                                    ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
@@ -462,8 +464,10 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
         cudaFuncSetAttribute(vote_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(vote_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(vote_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_ring_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_ring_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        cudaFuncSetAttribute(vote_ring_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(vote_ring_kernel<768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(vote_ring_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(vote_ring_kernel<768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         gcb_destroy(ctx);
         return GCB_ERR_CUDA;
     }
@@ -753,6 +757,7 @@ int gcb_set_debug(gcb_ctx *ctx, int key, int value) {
     if (key == 1) ctx->ablate = value;                 // profiling only: wrong results
     else if (key == 2) ctx->ring_window_shift = value;  // tuning only: same results
     else if (key == 3) ctx->group_lanes = value;        // tuning only: same results
+    else if (key == 4) ctx->ring_units = value == 2 ? 2 : 1;  // tuning only: same results
     else return GCB_ERR_ARG;
     return GCB_OK;
 }

@@ -80,7 +80,7 @@ __device__ __forceinline__ void pipe_wait_backoff(uint64_t *bar, uint32_t parity
 inline void pipe_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t) { pipe_wait(bar, parity); }
 #endif
 
-template <int NT>
+template <int NT, int NU>
 __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, int32_t moderate_quality, int32_t implied,
                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, int32_t n_tiles,
                                                                   int32_t max_stages, int32_t arena_bytes, const int32_t *max_need,
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
         // ---- producer: lane 0 fills the stages, up to n_stages tiles ahead of the consumers; the whole warp fetches the
         // headers of this CTA's next 32 tiles at once, so that no tile waits for a header on its way from global memory
         TileHdr2 *hcache = (TileHdr2 *)(smem + VR_OFF_HCACHE);
-        int k = 0, ticket = 0;
+        int k = 0;
         // stage k % n_stages once every consumer has left the tile it held before
         auto allocate = [&]() -> uint32_t {
             const int s = k % n_stages, use = k / n_stages;
@@ -140,8 +140,7 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                     sh.ft_off = VR_OFF_ARENA + (int32_t)at;
                     sh.vr_off = sh.ft_off + (int32_t)ring_round128(ft_bytes);
                     sh.slab_off = sh.vr_off + (int32_t)ring_round128(vr_bytes);
-                    sh.first_ticket = ticket;
-                    ticket = (ticket + cur.n_bundles) % (NT / WARP - 1);
+                    sh.first_ticket = 0;
                     sh.pad[0] = 0;
                     shdr[s] = sh;
                     pipe_expect(full + s, slab_bytes + vr_bytes + ft_bytes);
@@ -190,18 +189,13 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
         RingStage *sh = shdr + s;
         const int nfs = sh->nfs;
         if (nfs < 0) break;
-        const int nb = sh->n_bundles;
-        // bundles are dealt round-robin over the consumer warps, across tiles: bundle i of this tile is ticket first_ticket + i
-        constexpr int NC = NT / WARP - 1;
-        const bool deal = (ablate & 16) != 0;  // (tuning aid: static round-robin instead of the stage's counter)
+        // a lane owns NU units of sixteen columns; a family side takes L lanes, a bundle 32 / L family sides
+        const int L = (sh->lanes + NU - 1) / NU;
+        const int S = (int)((32u * ((65535u / (unsigned)L) + 1u)) >> 16);
+        const int nb = NU == 1 ? sh->n_bundles : (int)(((unsigned)(nfs + S - 1) * ((65535u / (unsigned)S) + 1u)) >> 16);
         int bundle = nb;
-        if (deal) {
-            bundle = (warp - 1) - sh->first_ticket;
-            if (bundle < 0) bundle += NC;
-        } else {
-            if (lane == 0 && *(volatile int32_t *)&sh->next_bundle < nb) bundle = atomicAdd(&sh->next_bundle, 1);  // (no atomic on a drained tile)
-            bundle = __shfl_sync(FULL, bundle, 0);
-        }
+        if (lane == 0 && *(volatile int32_t *)&sh->next_bundle < nb) bundle = atomicAdd(&sh->next_bundle, 1);  // (no atomic on a drained tile)
+        bundle = __shfl_sync(FULL, bundle, 0);
         if (bundle < nb) {
             const int off_slab = sh->slab_off, off_vr = sh->vr_off;
             const FsTile *s_ft = (const FsTile *)(smem + sh->ft_off);
@@ -209,11 +203,12 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
             const int64_t out_base0 = sh->out_base0;
             uint8_t *out0 = r.out_payload + out_base0;
             const int tile = sh->tile;
-            const int L = sh->lanes, S = sh->per_bundle;  // lanes per family side (1..32), family sides per bundle (32 / L)
             const int sub = (int)(((unsigned)lane * ((65535u / (unsigned)L) + 1u)) >> 16), j = lane - sub * L;  // lane / L, lane % L
-            const int col0 = VT_CHUNK * j;
+            const int col0 = VT_CHUNK * NU * j;
             const int common_l = sh->common_l;  // the masks of the tile's usual record length are computed once
-            const ChunkMasks cm_common = make_masks(common_l, common_l, col0);
+            ChunkMasks cm_common[NU];
+#pragma unroll
+            for (int u = 0; u < NU; u++) cm_common[u] = make_masks(common_l, common_l, col0 + VT_CHUNK * u);
             do {
                 if (ablate & 8) goto next_bundle;
                 {
@@ -229,135 +224,173 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                 const int cb = off_slab + 4 * (int)ft.cbase4;  // byte offsets into the CTA's shared memory
                 const int ento = off_vr + 16 * (int)ft.ent0;
                 VoteRead tv = {0, 0, 0, 0, 0, 0, 0, 0};
-                uint32_t tbe0 = 0u, tbe1 = 0u;
+                uint32_t tbe[2 * NU];
+#pragma unroll
+                for (int w = 0; w < 2 * NU; w++) tbe[w] = 0u;
                 int trec = cb;
+                const int sb0 = 8 * NU * j;  // the lane's first byte of a record's packed bases
                 if (mine) {
                     tv = s_vr[ft.ent0 + ft.tmpl_k];
                     trec = cb + 4 * (int)tv.own_off4;
-                    if (8 * j < sbytes) tbe0 = bswap32(GCB_LDS32(trec + qbytes + 8 * j));
-                    if (8 * j + 4 < sbytes) tbe1 = bswap32(GCB_LDS32(trec + qbytes + 8 * j + 4));
+#pragma unroll
+                    for (int w = 0; w < 2 * NU; w++)
+                        if (sb0 + 4 * w < sbytes) tbe[w] = bswap32(GCB_LDS32(trec + qbytes + sb0 + 4 * w));
                 }
-                ChunkMasks cm = cm_common;
-                if (l_out != common_l || len != l_out) cm = make_masks(l_out, len, col0);
+                ChunkMasks cm[NU];
+#pragma unroll
+                for (int u = 0; u < NU; u++) cm[u] = cm_common[u];
+                if (l_out != common_l || len != l_out) {
+#pragma unroll
+                    for (int u = 0; u < NU; u++) cm[u] = make_masks(l_out, len, col0 + VT_CHUNK * u);
+                }
                 if (mine && j == 0 && ft.mode != SIDE_COPY) GCB_COUNT((ft.flags & FS_UNIFORM) ? 4 : 5, 1);
-                uint32_t mo[4] = {0u, 0u, 0u, 0u}, me[4] = {0u, 0u, 0u, 0u}, dis0 = 0u, dis1 = 0u;
+                uint32_t mo[4 * NU], me[4 * NU], dis[2 * NU];
+#pragma unroll
+                for (int w = 0; w < 4 * NU; w++) mo[w] = me[w] = 0u;
+#pragma unroll
+                for (int w = 0; w < 2 * NU; w++) dis[w] = 0u;
                 if (ft.flags & FS_UNIFORM) {  // (see vote_fast_kernel)
-                    const int x = (int)tv.ov_own - col0;
-                    const int y = x - (int)tv.ov_mate;
-                    const int oa = max(max(0, x), y), oz = min(min(cm.nvote, x + (int)tv.ov_len), y + (int)tv.mate_l);
-                    const bool has_ov = tv.ov_len > 0 && oz > oa;
-                    const uint32_t om0 = has_ov ? nib_range(oa, oz) : 0u, om1 = has_ov ? nib_range(oa - 8, oz - 8) : 0u;
-                    const int ms = 0 - y, mw0 = ms >> 3;
+                    uint32_t om[2 * NU];
+                    bool has_ov = false;
+                    const int x0 = (int)tv.ov_own - col0, y0 = x0 - (int)tv.ov_mate;
+#pragma unroll
+                    for (int u = 0; u < NU; u++) {
+                        const int x = x0 - VT_CHUNK * u, y = y0 - VT_CHUNK * u;  // first column of the unit inside the window / with a mate index >= 0
+                        const int oa = max(max(0, x), y), oz = min(min(cm[u].nvote, x + (int)tv.ov_len), y + (int)tv.mate_l);
+                        const bool hu = tv.ov_len > 0 && oz > oa;
+                        om[2 * u] = hu ? nib_range(oa, oz) : 0u;
+                        om[2 * u + 1] = hu ? nib_range(oa - 8, oz - 8) : 0u;
+                        has_ov = has_ov || hu;
+                    }
+                    const int ms = 0 - y0, mw0 = ms >> 3;  // the lane's first mate column: word mw0 of the mate's bases, nibble ms & 7
                     const unsigned msh = (unsigned)(ms & 7) * 4u;
-                    const uint32_t qbase = sbase + (uint32_t)(cb + col0), sdelta = (uint32_t)(qbytes - col0 + 8 * j);
+                    const uint32_t qbase = sbase + (uint32_t)(cb + col0), sdelta = (uint32_t)(qbytes - col0 + sb0);
                     const uint32_t mdelta = has_ov ? (uint32_t)(4 * ((int)tv.mate_off4 - (int)tv.own_off4) + GCB_ALIGN4(tv.mate_l) + 4 * mw0 - col0) : 0u;
                     const uint32_t xt = tv.own_off4;
                     const uint32_t qt = qbase + (xt << 2);
-                    const uint32_t t0 = lds32<0>(qt + sdelta), t1 = lds32<4>(qt + sdelta);
-                    const uint32_t a0 = lds32<0>(qt + mdelta), c0 = lds32<4>(qt + mdelta), e0 = lds32<8>(qt + mdelta);
-                    uint32_t d0 = 0u, d1 = 0u, da = 0u, dc = 0u, de = 0u;
+                    uint32_t t[2 * NU], a0[2 * NU + 1], d[2 * NU], da[2 * NU + 1];
+#pragma unroll
+                    for (int w = 0; w < 2 * NU; w++) {
+                        t[w] = lds32r(qt + sdelta + 4 * w);
+                        d[w] = 0u;
+                    }
+#pragma unroll
+                    for (int w = 0; w < 2 * NU + 1; w++) {
+                        a0[w] = lds32r(qt + mdelta + 4 * w);
+                        da[w] = 0u;
+                    }
                     uint32_t ea = sbase + (uint32_t)ento;
                     for (int e = 0; e < mmax; e += 2, ea += 32) {
                         uint32_t xa = lds16<0>(ea), xb = lds16<16>(ea);
                         xa = (e < m && xa != VR_NO_VOTE) ? xa : xt;
                         xb = (e + 1 < m && xb != VR_NO_VOTE) ? xb : xt;
                         const uint32_t qa = qbase + (xa << 2), qb = qbase + (xb << 2);
-                        const uint32_t qa0 = lds32<0>(qa), qa1 = lds32<4>(qa), qa2 = lds32<8>(qa), qa3 = lds32<12>(qa);
-                        const uint32_t qb0 = lds32<0>(qb), qb1 = lds32<4>(qb), qb2 = lds32<8>(qb), qb3 = lds32<12>(qb);
-                        const uint32_t ra0 = lds32<0>(qa + sdelta), ra1 = lds32<4>(qa + sdelta);
-                        const uint32_t rb0 = lds32<0>(qb + sdelta), rb1 = lds32<4>(qb + sdelta);
-                        const uint32_t ma = qa + mdelta, mb = qb + mdelta;
-                        const uint32_t aa = lds32<0>(ma), ca = lds32<4>(ma), ee = lds32<8>(ma);
-                        const uint32_t ab = lds32<0>(mb), cbb = lds32<4>(mb), eb = lds32<8>(mb);
-                        mo[0] = __vimax3_u16x2(mo[0], qa0, qb0); me[0] = __vimax3_u16x2(me[0], qa0 << 8, qb0 << 8);
-                        mo[1] = __vimax3_u16x2(mo[1], qa1, qb1); me[1] = __vimax3_u16x2(me[1], qa1 << 8, qb1 << 8);
-                        mo[2] = __vimax3_u16x2(mo[2], qa2, qb2); me[2] = __vimax3_u16x2(me[2], qa2 << 8, qb2 << 8);
-                        mo[3] = __vimax3_u16x2(mo[3], qa3, qb3); me[3] = __vimax3_u16x2(me[3], qa3 << 8, qb3 << 8);
-                        d0 |= (ra0 ^ t0) | (rb0 ^ t0);
-                        d1 |= (ra1 ^ t1) | (rb1 ^ t1);
-                        da |= (aa ^ a0) | (ab ^ a0);
-                        dc |= (ca ^ c0) | (cbb ^ c0);
-                        de |= (ee ^ e0) | (eb ^ e0);
+#pragma unroll
+                        for (int w = 0; w < 4 * NU; w++) {
+                            const uint32_t va = lds32r(qa + 4 * w), vb = lds32r(qb + 4 * w);
+                            mo[w] = __vimax3_u16x2(mo[w], va, vb);
+                            me[w] = __vimax3_u16x2(me[w], va << 8, vb << 8);
+                        }
+#pragma unroll
+                        for (int w = 0; w < 2 * NU; w++) d[w] |= (lds32r(qa + sdelta + 4 * w) ^ t[w]) | (lds32r(qb + sdelta + 4 * w) ^ t[w]);
+#pragma unroll
+                        for (int w = 0; w < 2 * NU + 1; w++) da[w] |= (lds32r(qa + mdelta + 4 * w) ^ a0[w]) | (lds32r(qb + mdelta + 4 * w) ^ a0[w]);
                     }
-                    dis0 = bswap32(d0);
-                    dis1 = bswap32(d1);
+#pragma unroll
+                    for (int w = 0; w < 2 * NU; w++) dis[w] = bswap32(d[w]);
                     if (has_ov) {  // pair.cpp:133-170: a base that differs from its mate's is never a fast column
-                        const uint32_t A = bswap32(da), C = bswap32(dc), E = bswap32(de);
-                        const uint32_t ta = bswap32(a0), tc = bswap32(c0), te = bswap32(e0);
-                        const uint32_t tb0 = bswap32(t0), tb1 = bswap32(t1);
-                        dis0 |= (__funnelshift_l(C, A, msh) | (tb0 ^ __funnelshift_l(tc, ta, msh))) & om0;
-                        dis1 |= (__funnelshift_l(E, C, msh) | (tb1 ^ __funnelshift_l(te, tc, msh))) & om1;
+#pragma unroll
+                        for (int w = 0; w < 2 * NU + 1; w++) {
+                            da[w] = bswap32(da[w]);
+                            a0[w] = bswap32(a0[w]);
+                        }
+#pragma unroll
+                        for (int w = 0; w < 2 * NU; w++)
+                            dis[w] |= (__funnelshift_l(da[w + 1], da[w], msh) | (bswap32(t[w]) ^ __funnelshift_l(a0[w + 1], a0[w], msh))) & om[w];
                     }
                 } else if (m > 0) {
                     for (int e = 0; e < m; e++) {
                         const VoteRead v = s_vr[ft.ent0 + e];
                         if (v.own_off4 == VR_NO_VOTE || v.own_l == 0) continue;
-                        const int rp0 = col0 + v.shift;
-                        const int a = max(0, 0 - rp0), z = min(cm.nvote, (int)v.own_l - rp0);
-                        if (z <= a) continue;
                         const uint8_t *rec = smem + cb + 4 * (int)v.own_off4;
                         const int rq = GCB_ALIGN4(v.own_l);
-                        uint32_t q[4], be0, be1;
-                        fetch16q(rec, rq, rp0, q);
-                        fetch16b(rec + rq, GCB_ALIGN4((v.own_l + 1) >> 1), rp0, be0, be1);
-                        const uint32_t vm0 = nib_range(a, z), vm1 = nib_range(a - 8, z - 8);
-                        q[0] &= bytes_lo(vm0); q[1] &= bytes_hi(vm0); q[2] &= bytes_lo(vm1); q[3] &= bytes_hi(vm1);
 #pragma unroll
-                        for (int kk = 0; kk < 4; kk++) {
-                            mo[kk] = __vmaxu2(mo[kk], q[kk]);
-                            me[kk] = __vmaxu2(me[kk], q[kk] << 8);
-                        }
-                        dis0 |= (be0 ^ tbe0) & vm0;
-                        dis1 |= (be1 ^ tbe1) & vm1;
-                        if (v.ov_len > 0) {  // (subtractions only: see the ptxas note in k_vote_tiled.cuh)
-                            const int x = (int)v.ov_own - rp0;
-                            const int y = x - (int)v.ov_mate;
-                            const int oa = max(max(a, x), y);
-                            const int oz = min(min(z, x + (int)v.ov_len), y + (int)v.mate_l);
-                            if (oz > oa) {
-                                const uint8_t *mrec = smem + cb + 4 * (int)v.mate_off4;
-                                uint32_t mb0, mb1;
-                                fetch16b(mrec + GCB_ALIGN4(v.mate_l), GCB_ALIGN4((v.mate_l + 1) >> 1), 0 - y, mb0, mb1);
-                                dis0 |= (be0 ^ mb0) & nib_range(oa, oz);
-                                dis1 |= (be1 ^ mb1) & nib_range(oa - 8, oz - 8);
+                        for (int u = 0; u < NU; u++) {
+                            const int rp0 = col0 + VT_CHUNK * u + v.shift;
+                            const int a = max(0, 0 - rp0), z = min(cm[u].nvote, (int)v.own_l - rp0);
+                            if (z <= a) continue;
+                            uint32_t q[4], be0, be1;
+                            fetch16q(rec, rq, rp0, q);
+                            fetch16b(rec + rq, GCB_ALIGN4((v.own_l + 1) >> 1), rp0, be0, be1);
+                            const uint32_t vm0 = nib_range(a, z), vm1 = nib_range(a - 8, z - 8);
+                            q[0] &= bytes_lo(vm0); q[1] &= bytes_hi(vm0); q[2] &= bytes_lo(vm1); q[3] &= bytes_hi(vm1);
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) {
+                                mo[4 * u + kk] = __vmaxu2(mo[4 * u + kk], q[kk]);
+                                me[4 * u + kk] = __vmaxu2(me[4 * u + kk], q[kk] << 8);
+                            }
+                            dis[2 * u] |= (be0 ^ tbe[2 * u]) & vm0;
+                            dis[2 * u + 1] |= (be1 ^ tbe[2 * u + 1]) & vm1;
+                            if (v.ov_len > 0) {  // (subtractions only: see the ptxas note in k_vote_tiled.cuh)
+                                const int x = (int)v.ov_own - rp0;
+                                const int y = x - (int)v.ov_mate;
+                                const int oa = max(max(a, x), y);
+                                const int oz = min(min(z, x + (int)v.ov_len), y + (int)v.mate_l);
+                                if (oz > oa) {
+                                    const uint8_t *mrec = smem + cb + 4 * (int)v.mate_off4;
+                                    uint32_t mb0, mb1;
+                                    fetch16b(mrec + GCB_ALIGN4(v.mate_l), GCB_ALIGN4((v.mate_l + 1) >> 1), 0 - y, mb0, mb1);
+                                    dis[2 * u] |= (be0 ^ mb0) & nib_range(oa, oz);
+                                    dis[2 * u + 1] |= (be1 ^ mb1) & nib_range(oa - 8, oz - 8);
+                                }
                             }
                         }
                     }
                 }
                 // ---- what the record gets: qualities = the maxima (fast columns), bases = the template's
-                uint32_t slow0 = 0u, slow1 = 0u;  // one bit per slow column (the low bit of its big-endian nibble)
+                uint32_t slow[2 * NU];  // one bit per slow column (the low bit of its big-endian nibble)
+#pragma unroll
+                for (int w = 0; w < 2 * NU; w++) slow[w] = 0u;
                 if (mine) {
-                    uint32_t oq[4];
-                    if (ft.mode == SIDE_COPY) {  // group.cpp:73-77: the record itself
-#pragma unroll
-                        for (int kk = 0; kk < 4; kk++) oq[kk] = col0 + 4 * kk < qbytes ? GCB_LDS32(trec + col0 + 4 * kk) : 0u;
-                    } else {
-#pragma unroll
-                        for (int kk = 0; kk < 4; kk++) oq[kk] = prmt(mo[kk], me[kk], 0x3715u) & cm.vb[kk];  // (the hoisted loop read whole words)
-                        GCB_COUNT(2, cm.nvote);
-                        if (implied && len == l_out) {
-                            const uint32_t lowq0 = nibs_of_flags(bytes_ge_flags(oq[0], mod4) ^ 0x80808080u, bytes_ge_flags(oq[1], mod4) ^ 0x80808080u);
-                            const uint32_t lowq1 = nibs_of_flags(bytes_ge_flags(oq[2], mod4) ^ 0x80808080u, bytes_ge_flags(oq[3], mod4) ^ 0x80808080u);
-                            slow0 = (dis0 | lowq0) & cm.vn0;
-                            slow1 = (dis1 | lowq1) & cm.vn1;
-                            slow0 |= slow0 >> 1; slow0 |= slow0 >> 2; slow0 &= 0x11111111u;  // any differing bit marks the column
-                            slow1 |= slow1 >> 1; slow1 |= slow1 >> 2; slow1 &= 0x11111111u;
-                        } else {  // without `implied`, or with columns that are not voted, every column of the record is slow
-                            slow0 = nibs_of_bytes(cm.rb[0], cm.rb[1]) & 0x11111111u;
-                            slow1 = nibs_of_bytes(cm.rb[2], cm.rb[3]) & 0x11111111u;
-                        }
-                    }
                     uint8_t *out = out0 + 4 * (int64_t)ft.out4;
-                    if (!(ablate & 4)) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; kk++)
-                        if (col0 + 4 * kk < qbytes) *(uint32_t *)(out + col0 + 4 * kk) = oq[kk] & cm.rb[kk];
-                    if (8 * j < sbytes) *(uint32_t *)(out + qbytes + 8 * j) = bswap32(tbe0 & cm.kn0);
-                    if (8 * j + 4 < sbytes) *(uint32_t *)(out + qbytes + 8 * j + 4) = bswap32(tbe1 & cm.kn1);
+                    for (int u = 0; u < NU; u++) {
+                        const int cu = col0 + VT_CHUNK * u;
+                        uint32_t oq[4];
+                        if (ft.mode == SIDE_COPY) {  // group.cpp:73-77: the record itself
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) oq[kk] = cu + 4 * kk < qbytes ? GCB_LDS32(trec + cu + 4 * kk) : 0u;
+                        } else {
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) oq[kk] = prmt(mo[4 * u + kk], me[4 * u + kk], 0x3715u) & cm[u].vb[kk];  // (the hoisted loop read whole words)
+                            GCB_COUNT(2, cm[u].nvote);
+                            if (implied && len == l_out) {
+                                const uint32_t lowq0 = nibs_of_flags(bytes_ge_flags(oq[0], mod4) ^ 0x80808080u, bytes_ge_flags(oq[1], mod4) ^ 0x80808080u);
+                                const uint32_t lowq1 = nibs_of_flags(bytes_ge_flags(oq[2], mod4) ^ 0x80808080u, bytes_ge_flags(oq[3], mod4) ^ 0x80808080u);
+                                uint32_t s0 = (dis[2 * u] | lowq0) & cm[u].vn0, s1 = (dis[2 * u + 1] | lowq1) & cm[u].vn1;
+                                s0 |= s0 >> 1; s0 |= s0 >> 2; s0 &= 0x11111111u;  // any differing bit marks the column
+                                s1 |= s1 >> 1; s1 |= s1 >> 2; s1 &= 0x11111111u;
+                                slow[2 * u] = s0;
+                                slow[2 * u + 1] = s1;
+                            } else {  // without `implied`, or with columns that are not voted, every column of the record is slow
+                                slow[2 * u] = nibs_of_bytes(cm[u].rb[0], cm[u].rb[1]) & 0x11111111u;
+                                slow[2 * u + 1] = nibs_of_bytes(cm[u].rb[2], cm[u].rb[3]) & 0x11111111u;
+                            }
+                        }
+                        if (!(ablate & 4)) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++)
+                                if (cu + 4 * kk < qbytes) *(uint32_t *)(out + cu + 4 * kk) = oq[kk] & cm[u].rb[kk];
+                            if (sb0 + 8 * u < sbytes) *(uint32_t *)(out + qbytes + sb0 + 8 * u) = bswap32(tbe[2 * u] & cm[u].kn0);
+                            if (sb0 + 8 * u + 4 < sbytes) *(uint32_t *)(out + qbytes + sb0 + 8 * u + 4) = bswap32(tbe[2 * u + 1] & cm[u].kn1);
+                        }
                     }
                 }
                 // ---- slow columns: records of one size per bundle, taken from the warp's own pool of reserved queue space
-                const int nslow = (ablate & 1) ? 0 : __popc(slow0) + __popc(slow1);
+                int nslow = 0;
+#pragma unroll
+                for (int w = 0; w < 2 * NU; w++) nslow += __popc(slow[w]);
+                if (ablate & 1) nslow = 0;
                 const uint32_t T = (uint32_t)__reduce_add_sync(FULL, nslow);
                 if (T > 0) {
                     GCB_COUNT(3, nslow);
@@ -387,18 +420,21 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                             GCB_COUNT(1, 1);
                         }
                     } else if (T <= (uint32_t)VR_ITEMS) {
-                        // every lane lists its columns (one per round); then eight lanes per column, one lane per read
-                        unsigned long long sm64 = ((unsigned long long)slow0 << 32) | slow1;
+                        // every lane lists its columns (one per round and unit); then eight lanes per column, one lane per read
                         uint32_t listed = 0u;
-                        while (listed < T) {
-                            const bool has = sm64 != 0ull;
-                            const unsigned bal = __ballot_sync(FULL, has);
-                            if (has) {
-                                const int kk = __clzll((long long)sm64) >> 2;
-                                sm64 &= ~(0xF000000000000000ull >> (4 * kk));
-                                s_item[listed + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((sub << 9) | (col0 + kk));
+#pragma unroll
+                        for (int u = 0; u < NU; u++) {
+                            unsigned long long sm64 = ((unsigned long long)slow[2 * u] << 32) | slow[2 * u + 1];
+                            while (__any_sync(FULL, sm64 != 0ull)) {
+                                const bool has = sm64 != 0ull;
+                                const unsigned bal = __ballot_sync(FULL, has);
+                                if (has) {
+                                    const int kk = __clzll((long long)sm64) >> 2;
+                                    sm64 &= ~(0xF000000000000000ull >> (4 * kk));
+                                    s_item[listed + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((sub << 9) | (col0 + VT_CHUNK * u + kk));
+                                }
+                                listed += __popc(bal);
                             }
-                            listed += __popc(bal);
                         }
                         __syncwarp();
                         const int g = lane / VR_GROUP, gl = lane % VR_GROUP;
@@ -454,12 +490,13 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                         if (nslow > 0) {
                             const uint8_t *cbp = smem + cb;
                             const VoteRead *ents = s_vr + ft.ent0;
-                            for (int wsel = 0; wsel < 2; wsel++) {
-                                uint32_t sm = wsel ? slow1 : slow0;
+#pragma unroll
+                            for (int w = 0; w < 2 * NU; w++) {
+                                uint32_t sm = slow[w];
                                 while (sm != 0u) {
                                     const int kk = __clz((int)sm) >> 2;
                                     sm &= ~(0xF0000000u >> (4 * kk));
-                                    const int col = col0 + 8 * wsel + kk;
+                                    const int col = col0 + 8 * w + kk;
                                     const uint32_t wofs = pool_w + (ri - pool_r) * rw;
                                     uint32_t *rec = q_words + wofs;
                                     q_index[ri] = wofs;
@@ -476,12 +513,8 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                 }
                 }
             next_bundle:
-                if (deal) {
-                    bundle += NC;
-                } else {
-                    if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
-                    bundle = __shfl_sync(FULL, bundle, 0);
-                }
+                if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
+                bundle = __shfl_sync(FULL, bundle, 0);
                 pipe_progress();
             } while (bundle < nb);
         }

@@ -73,6 +73,15 @@ GCB_DEV void slow_write_header(uint32_t *rec, const FsTile &ft, int col, int64_t
 }
 
 #ifndef GCB_SIMT_CHECK
+__device__ __forceinline__ uint32_t lds32r(uint32_t addr) {  // ld.shared.u32 from a shared-window address
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+#else
+inline uint32_t lds32r(uint32_t addr) { return *(const uint32_t *)(::simt::dyn_smem() + addr); }
+#endif
+#ifndef GCB_SIMT_CHECK
 template <int IMM>
 __device__ __forceinline__ uint32_t lds16(uint32_t addr) {
     uint32_t v;

@@ -162,3 +162,21 @@ def test_lanes_per_cluster_do_not_change_results(simt_lib, oracle, name, lanes):
         eng.set_debug(3, lanes)
         res = eng.cluster_by_umi(batch)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} lanes {lanes}")
+
+
+UNIT_CASES = [c for c in CASES if c[0] in ("golden_cfg1_600", "golden_cfg2_600", "golden_cfg3_600", "golden_cfg4_600", "golden_ragged_duplex",
+                                          "edge_default", "edge_strict", "edge_loose", "ragged_none_0", "ragged_single_1", "ragged_duplex_2",
+                                          "ragged_duplex_3", "no_reference", "empty", "tiny_reads", "cfg2_1500", "cfg3_1500", "cfg4_1500",
+                                          "wide_umi_3", "ragged_single_3", "ragged_none_2")]
+
+
+@pytest.mark.parametrize("name,thunk", UNIT_CASES, ids=[c[0] for c in UNIT_CASES])
+def test_ring_with_two_units_per_lane_matches_oracle(simt_lib, oracle, name, thunk):
+    """vote_ring_kernel with thirty-two columns per lane (two units of sixteen) gives the same bytes."""
+    from gencore_b200.engine import ConsensusEngine
+    batch, genome, opt = thunk()
+    with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
+        eng.set_reference(genome)
+        eng.set_debug(4, 2)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
