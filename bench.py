@@ -34,9 +34,12 @@ WORKLOAD = "cfg2: 2x150 bp pairs, 8 bp prefix UMI, mean cluster depth 8, 1% UMI 
 SEED = 20261017 + 2
 
 
+CFG_NAME = "cfg2"
+
+
 def _cfg(contig_len=None):
     from gencore_b200 import synth
-    cfg = synth.CONFIGS["cfg2"]
+    cfg = synth.CONFIGS[CFG_NAME]
     return dataclasses.replace(cfg, contig_len=contig_len) if contig_len else cfg
 
 
@@ -400,7 +403,13 @@ def main():
     ap.add_argument("--sweep-only", action="store_true", help="stop after --sweep")
     ap.add_argument("--sweep", default="", help="tuning aid: comma-separated mode:threads settings whose vote stage times go to stderr")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per vote launch from an ncu capture (profiles/)")
+    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"],
+                    help="exploration only: another fixed-length shape of BASELINE.json (the contract's line is cfg2, the default)")
     args = ap.parse_args()
+    global CFG_NAME, WORKLOAD
+    if args.config != "cfg2":
+        CFG_NAME = args.config
+        WORKLOAD = "%s shape of BASELINE.json (exploration run, not the contract's workload)" % args.config
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -13,8 +13,7 @@
 //                     vote_fast_kernel (raw-order XOR residues, VIMNMX3.U16x2 over two reads, mate alignment once per
 //                     bundle).  Slow columns of the bundle are emitted COOPERATIVELY: the lanes list their columns in a
 //                     small per-warp table, one 64-bit atomic reserves all records, then eight lanes per column write the
-//                     column's entries (one lane per read).  Bundles with more than VR_ITEMS slow columns (votes whose
-//                     every column is slow) fall back to one lane per column.
+//                     column's entries (one lane per read), in rounds of at most VR_ITEMS columns.
 //   queue overflow    the tile is handed to the generic kernel (score_vote_kernel), which runs last and rewrites all of the
 //                     tile's records from the payload.
 #pragma once
@@ -419,94 +418,83 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                             ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~tile;
                             GCB_COUNT(1, 1);
                         }
-                    } else if (T <= (uint32_t)VR_ITEMS) {
-                        // every lane lists its columns (one per round and unit); then eight lanes per column, one lane per read
-                        uint32_t listed = 0u;
+                    } else {
+                        // rounds of at most VR_ITEMS columns: every lane lists one of its columns per ballot, then eight lanes per
+                        // column write the column's entries, one lane per read
+                        unsigned long long sm64[NU];
 #pragma unroll
-                        for (int u = 0; u < NU; u++) {
-                            unsigned long long sm64 = ((unsigned long long)slow[2 * u] << 32) | slow[2 * u + 1];
-                            while (__any_sync(FULL, sm64 != 0ull)) {
-                                const bool has = sm64 != 0ull;
+                        for (int u = 0; u < NU; u++) sm64[u] = ((unsigned long long)slow[2 * u] << 32) | slow[2 * u + 1];
+                        uint32_t emitted = 0u;
+                        while (emitted < T) {
+                            uint32_t listed = 0u;
+                            while (listed + WARP <= (uint32_t)VR_ITEMS) {
+                                bool has = false;
+                                int u_pick = 0;
+#pragma unroll
+                                for (int u = NU - 1; u >= 0; u--)
+                                    if (sm64[u] != 0ull) {
+                                        has = true;
+                                        u_pick = u;
+                                    }
                                 const unsigned bal = __ballot_sync(FULL, has);
+                                if (bal == 0u) break;
                                 if (has) {
-                                    const int kk = __clzll((long long)sm64) >> 2;
-                                    sm64 &= ~(0xF000000000000000ull >> (4 * kk));
-                                    s_item[listed + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((sub << 9) | (col0 + VT_CHUNK * u + kk));
+                                    unsigned long long v = sm64[0];
+#pragma unroll
+                                    for (int u = 1; u < NU; u++)
+                                        if (u_pick == u) v = sm64[u];
+                                    const int kk = __clzll((long long)v) >> 2;
+                                    v &= ~(0xF000000000000000ull >> (4 * kk));
+#pragma unroll
+                                    for (int u = 0; u < NU; u++)
+                                        if (u_pick == u) sm64[u] = v;
+                                    s_item[listed + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((sub << 9) | (col0 + VT_CHUNK * u_pick + kk));
                                 }
                                 listed += __popc(bal);
                             }
-                        }
-                        __syncwarp();
-                        const int g = lane / VR_GROUP, gl = lane % VR_GROUP;
-                        for (uint32_t i = (uint32_t)g; i < T; i += WARP / VR_GROUP) {
-                            const uint32_t code = s_item[i], wofs = pool_w + i * rw;
-                            const int col = (int)(code & 511u), fi = bundle * S + (int)(code >> 9);
-                            const FsTile fti = s_ft[fi];
-                            const uint8_t *cbp = smem + off_slab + 4 * (int)fti.cbase4;
-                            const VoteRead *ents = s_vr + fti.ent0;
-                            uint32_t *rec = q_words + wofs;
-                            const int mi = (int)fti.m;
-                            if (gl == 0) {
-                                q_index[pool_r + i] = wofs;
-                                slow_write_header(rec, fti, col, out_base0 + 4 * (int64_t)fti.out4);
-                            }
-                            if ((fti.flags & FS_UNIFORM) && col < (int)fti.len) {
-                                // the column's place in pair.cpp:121-170 is the same for every read of a uniform family
-                                const VoteRead tvi = ents[fti.tmpl_k];
-                                const bool info = tvi.ov_len != VR_NO_OVERLAP_INFO;
-                                const int kq = col - (int)tvi.ov_own, mp = (int)tvi.ov_mate + kq;
-                                const bool inwin = info && kq >= 0 && kq < (int)tvi.ov_len;
-                                const bool mvalid = inwin && mp >= 0 && mp < (int)tvi.mate_l;
-                                const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
-                                const int soff = GCB_ALIGN4(fti.l_out) + (col >> 1), nsh = (col & 1) ? 0 : 4;
-                                const int mrel = mvalid ? 4 * ((int)tvi.mate_off4 - (int)tvi.own_off4) : 0, mpi = mvalid ? mp : 0;
-                                const int mqoff = mrel + mpi, msoff = mrel + (mvalid ? GCB_ALIGN4(tvi.mate_l) : 0) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
-                                for (int e = gl; e < mi; e += VR_GROUP) {
-                                    const uint32_t xo = ents[e].own_off4;
-                                    uint32_t ent = 0u;
-                                    if (xo != VR_NO_VOTE) {
-                                        const uint8_t *p = cbp + 4 * (int)xo;
-                                        const uint32_t ql = p[col], base = ((uint32_t)p[soff] >> nsh) & 0xFu;
-                                        const uint32_t mql = mvalid ? p[mqoff] : 0u, mbase = mvalid ? (((uint32_t)p[msoff] >> mnsh) & 0xFu) : 0u;
-                                        ent = ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
+                            __syncwarp();
+                            const int g = lane / VR_GROUP, gl = lane % VR_GROUP;
+                            for (uint32_t i = (uint32_t)g; i < listed; i += WARP / VR_GROUP) {
+                                const uint32_t code = s_item[i], wofs = pool_w + (emitted + i) * rw;
+                                const int col = (int)(code & 511u), fi = bundle * S + (int)(code >> 9);
+                                const FsTile fti = s_ft[fi];
+                                const uint8_t *cbp = smem + off_slab + 4 * (int)fti.cbase4;
+                                const VoteRead *ents = s_vr + fti.ent0;
+                                uint32_t *rec = q_words + wofs;
+                                const int mi = (int)fti.m;
+                                if (gl == 0) {
+                                    q_index[pool_r + emitted + i] = wofs;
+                                    slow_write_header(rec, fti, col, out_base0 + 4 * (int64_t)fti.out4);
+                                }
+                                if ((fti.flags & FS_UNIFORM) && col < (int)fti.len) {
+                                    // the column's place in pair.cpp:121-170 is the same for every read of a uniform family
+                                    const VoteRead tvi = ents[fti.tmpl_k];
+                                    const bool info = tvi.ov_len != VR_NO_OVERLAP_INFO;
+                                    const int kq = col - (int)tvi.ov_own, mp = (int)tvi.ov_mate + kq;
+                                    const bool inwin = info && kq >= 0 && kq < (int)tvi.ov_len;
+                                    const bool mvalid = inwin && mp >= 0 && mp < (int)tvi.mate_l;
+                                    const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
+                                    const int soff = GCB_ALIGN4(fti.l_out) + (col >> 1), nsh = (col & 1) ? 0 : 4;
+                                    const int mrel = mvalid ? 4 * ((int)tvi.mate_off4 - (int)tvi.own_off4) : 0, mpi = mvalid ? mp : 0;
+                                    const int mqoff = mrel + mpi, msoff = mrel + (mvalid ? GCB_ALIGN4(tvi.mate_l) : 0) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
+                                    for (int e = gl; e < mi; e += VR_GROUP) {
+                                        const uint32_t xo = ents[e].own_off4;
+                                        uint32_t ent = 0u;
+                                        if (xo != VR_NO_VOTE) {
+                                            const uint8_t *p = cbp + 4 * (int)xo;
+                                            const uint32_t ql = p[col], base = ((uint32_t)p[soff] >> nsh) & 0xFu;
+                                            const uint32_t mql = mvalid ? p[mqoff] : 0u, mbase = mvalid ? (((uint32_t)p[msoff] >> mnsh) & 0xFu) : 0u;
+                                            ent = ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
+                                        }
+                                        rec[SR_HDR_WORDS + e] = ent;
                                     }
-                                    rec[SR_HDR_WORDS + e] = ent;
-                                }
-                            } else {
-                                for (int e = gl; e < mi; e += VR_GROUP) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
-                            }
-                        }
-                        __syncwarp();
-                        pool_r += T;
-                        pool_w += W;
-                    } else {
-                        // a bundle full of slow columns: every lane emits its own
-                        uint32_t incl = (uint32_t)nslow;
-                        for (int off = 1; off < WARP; off <<= 1) {
-                            const uint32_t v = __shfl_up_sync(FULL, incl, off);
-                            if (lane >= off) incl += v;
-                        }
-                        uint32_t ri = pool_r + incl - (uint32_t)nslow;
-                        if (nslow > 0) {
-                            const uint8_t *cbp = smem + cb;
-                            const VoteRead *ents = s_vr + ft.ent0;
-#pragma unroll
-                            for (int w = 0; w < 2 * NU; w++) {
-                                uint32_t sm = slow[w];
-                                while (sm != 0u) {
-                                    const int kk = __clz((int)sm) >> 2;
-                                    sm &= ~(0xF0000000u >> (4 * kk));
-                                    const int col = col0 + 8 * w + kk;
-                                    const uint32_t wofs = pool_w + (ri - pool_r) * rw;
-                                    uint32_t *rec = q_words + wofs;
-                                    q_index[ri] = wofs;
-                                    slow_write_header(rec, ft, col, out_base0 + 4 * (int64_t)ft.out4);
-                                    for (int e = 0; e < (int)ft.m; e++) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
-                                    ri++;
+                                } else {
+                                    for (int e = gl; e < mi; e += VR_GROUP) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
                                 }
                             }
+                            __syncwarp();
+                            emitted += listed;
                         }
-                        __syncwarp();
                         pool_r += T;
                         pool_w += W;
                     }
