@@ -317,6 +317,7 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
     const bool run_prep = (stages & (GCB_STAGE_SCORE_VOTE | GCB_STAGE_VOTE_PREP_ONLY)) != 0;
     const bool run_vote = (stages & (GCB_STAGE_SCORE_VOTE | GCB_STAGE_VOTE_ONLY)) != 0;
     // split vote modes, measurement only: the fast kernel and (slow columns + finalize + generic) one at a time
+    // (plans that are not split run their one vote kernel as the "fast" half and the generic kernel as the "rest")
     const bool run_fast = run_vote || (stages & GCB_STAGE_VOTE_FAST_ONLY) != 0;
     const bool run_rest = run_vote || (stages & GCB_STAGE_VOTE_REST_ONLY) != 0;
     if ((run_prep || run_fast || run_rest) && n_tiles > 0) {
@@ -330,7 +331,7 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                 GCB_LAUNCH(tile_prep_kernel, dim3((unsigned)n_tiles), dim3(VP_PREP_THREADS), 0, stream, b, r, ws, plan.slab_cap, thdr, fst, ptiles, pcount);
                 ctx->launches++;
             }
-            if (run_vote) {
+            if (run_fast) {
                 const unsigned pipe_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
                 GCB_LAUNCH(vote_pipe_kernel, dim3(pipe_grid), dim3(VP_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
                            fast_path_implied(ctx->opt), plan.n_stages, plan.stage_bytes, (const TileHdr *)thdr, (const FsTile *)fst,
@@ -383,18 +384,18 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                                    dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->opt, sq, v.p0, v.p1);
                     ctx->launches += 2;
                 }
-            } else if (run_vote) {
+            } else if (run_fast) {
                 GCB_LAUNCH(vote_staged_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
                            ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst);
                 ctx->launches++;
             }
-        } else if (run_vote) {
+        } else if (run_fast) {
             GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
             GCB_LAUNCH(vote_tiled_kernel, dim3((unsigned)n_tiles), dim3(VT_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
                        plan.slab_cap, fast_path_implied(ctx->opt));
             ctx->launches++;
         }
-        if (run_vote || (run_rest && plan.split)) {  // the tiles the kernels above handed over (an empty list costs a few microseconds)
+        if (run_rest) {  // the tiles the kernels above handed over (an empty list costs a few microseconds)
             const unsigned generic_grid = (unsigned)(n_tiles < 2 * 148 ? n_tiles : 2 * 148);
             GCB_LAUNCH(score_vote_kernel, dim3(generic_grid), dim3(VOTE_THREADS), VOTE_SMEM, stream, b, r, ws, ctx->genome, ctx->opt);
             ctx->launches++;
