@@ -1,7 +1,14 @@
 #!/bin/bash
-TAG=${1:-fin}
+# end-of-round record: full gpu test suite, the contract's two bench lines, launch list, one full capture of the ring kernel
+TAG=${1:-final}
 mkdir -p gpurun_out
-echo "== pytest gpu (all)"; timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu_$TAG.log 2>&1; tail -4 gpurun_out/pytest_gpu_$TAG.log
-echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-echo "== bam bench"; timeout 900 python scripts/bam_bench.py 300000 > gpurun_out/bam_bench_$TAG.json 2> gpurun_out/bam_bench_$TAG.err; tail -c 800 gpurun_out/bam_bench_$TAG.json; tail -3 gpurun_out/bam_bench_$TAG.err
-echo "== bench"; timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -c 2600 gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu_$TAG.log 2>&1; tail -2 gpurun_out/pytest_gpu_$TAG.log
+echo "== bench (contract line)"; timeout 600 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -c 600 gpurun_out/bench_$TAG.json; tail -2 gpurun_out/bench_$TAG.err
+echo "== bench --impl reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; tail -c 700 gpurun_out/bench_ref_$TAG.json
+echo "== ncu launch list"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list_$TAG.log 2>&1; grep -c gpu__time gpurun_out/launches_$TAG.csv
+echo "== ncu full (ring)"
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:vote_ring -s 3 -c 1 -f -o gpurun_out/prof_$TAG \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1; tail -1 gpurun_out/ncu_full_$TAG.log
