@@ -195,6 +195,8 @@ def b200_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # (NCCL prints its version banner on stdout, which carries the one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
