@@ -324,6 +324,17 @@ def b200_arm(args):
     for _ in range(2):
         eng.cluster_by_umi(pb, pr)
     barrier()
+    if args.chunk_sweep and rank == 0:  # tuning aid: end-to-end time by pipeline chunk size, to stderr
+        for mb in [int(x) for x in args.chunk_sweep.split(",")]:
+            eng.set_chunk_bytes(mb << 20)
+            eng.cluster_by_umi(pb, pr)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                eng.cluster_by_umi(pb, pr)
+            torch.cuda.synchronize()
+            sys.stderr.write("chunk sweep %d MB: %.3f ms per step\n" % (mb, (time.perf_counter() - t0) / 5 * 1e3))
+        eng.set_chunk_bytes(48 << 20)
     t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(e2e_steps):
@@ -403,6 +414,7 @@ def main():
                          "4 = split with the fast kernel as a persistent ring (default)")
     ap.add_argument("--vote-threads", type=int, default=256, help="threads per CTA of the staged vote kernel")
     ap.add_argument("--sweep-only", action="store_true", help="stop after --sweep")
+    ap.add_argument("--chunk-sweep", default="", help="tuning aid: comma-separated pipeline chunk sizes in MB whose end-to-end times go to stderr")
     ap.add_argument("--sweep", default="", help="tuning aid: comma-separated mode:threads settings whose vote stage times go to stderr")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per vote launch from an ncu capture (profiles/)")
     ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"],

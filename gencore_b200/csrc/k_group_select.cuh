@@ -192,11 +192,14 @@ GCB_DEV VoteRead make_vote_read(const BatchView &b, const Workspace &ws, int64_t
     if (ov.valid) {
         const gcb_read_desc md = b.reads[sk ^ 1];
         const int64_t moff = md.data_off - slab0;
-        int64_t own = side == 0 ? ov.left_start : ov.right_start;
-        int64_t mate = side == 0 ? ov.right_start : ov.left_start;
-        int64_t len = ov.cmp_len;
-        const int64_t a = own > 0 ? own : 0;
-        const int64_t e = own + len < rd.l_qseq ? own + len : rd.l_qseq;
+        // (32-bit sums of 32-bit CIGAR offsets and lengths: saturate instead of wrapping on absurd input)
+        const int64_t own64 = side == 0 ? ov.left_start : ov.right_start, mate64 = side == 0 ? ov.right_start : ov.left_start;
+        const int lim = 0x3FFFFFFF;
+        int own = (int)(own64 < -lim ? -lim : own64 > lim ? lim : own64);
+        int mate = (int)(mate64 < -lim ? -lim : mate64 > lim ? lim : mate64);
+        int len = ov.cmp_len < -lim ? -lim : ov.cmp_len > lim ? lim : ov.cmp_len;
+        const int a = own > 0 ? own : 0;
+        const int e = own + len < rd.l_qseq ? own + len : rd.l_qseq;
         if (len > 0 && e > a) {  // the window clipped to this read's own indices
             mate += a - own;
             own = a;
@@ -344,10 +347,12 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
     bool fits = true;
     int mn = od.l_qseq;
     VoteRead *vr = ws.vote_reads + 2 * (int64_t)mb + (int64_t)side * m;
+    VoteRead mine_v = {VR_NO_VOTE, 0, 0, 0, 0, 0, 0, 0};  // the entry this lane wrote last (its only one when m <= GS)
     for (int k = lane; k < m; k += GS) {
         const VoteRead zero = {VR_NO_VOTE, 0, 0, 0, 0, 0, 0, 0};
         if (!GCB_HAVE(k)) {
             vr[k] = zero;
+            mine_v = zero;
             continue;
         }
         const int sk = GCB_SLOT(k);
@@ -363,7 +368,8 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
         }
         ws.vote_flags[sk] = f;
         if (f & VOTE_PARTICIPATES) mn = min(mn, b.reads[sk].l_qseq);
-        vr[k] = make_vote_read(b, ws, slab0, sk, side, f, od.l_qseq, leftReadMode, fits);
+        mine_v = make_vote_read(b, ws, slab0, sk, side, f, od.l_qseq, leftReadMode, fits);
+        vr[k] = mine_v;
     }
     if (lane == 0) ws.side_mode[2 * (int64_t)slot + side] = leftReadMode ? SIDE_LEFT : SIDE_RIGHT;
     SideChoice ch;
@@ -374,15 +380,33 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
     // FS_UNIFORM: every voter is as long as the template, is read at the template's columns, meets its mate through
     // the same overlap window and finds its mate's record at the same distance from its own (true for every family
     // of a fixed-length library packed pair by pair)
-    g.sync();
-    const VoteRead tv = vr[best_k];
-    bool uni = ch.len == od.l_qseq && tv.shift == 0 && tv.own_l == od.l_qseq;
-    for (int k = lane; k < m; k += GS) {
-        const VoteRead v = vr[k];
-        if (v.own_off4 == VR_NO_VOTE) continue;
-        uni = uni && v.own_l == tv.own_l && v.shift == 0 && v.ov_len == tv.ov_len &&
-              (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l &&
-                                 (uint16_t)(v.mate_off4 - v.own_off4) == (uint16_t)(tv.mate_off4 - tv.own_off4)));
+    bool uni;
+    if (m <= GS) {  // every entry is still in the register of the lane that made it: the template's comes by shuffle
+        VoteRead tv;
+        {
+            uint32_t w[4];
+            memcpy(w, &mine_v, 16);
+#pragma unroll
+            for (int q = 0; q < 4; q++) w[q] = __shfl_sync(g.mask, w[q], g.base + best_k);
+            memcpy(&tv, w, 16);
+        }
+        const VoteRead v = mine_v;
+        uni = ch.len == od.l_qseq && tv.shift == 0 && tv.own_l == od.l_qseq;
+        if (lane < m && v.own_off4 != VR_NO_VOTE)
+            uni = uni && v.own_l == tv.own_l && v.shift == 0 && v.ov_len == tv.ov_len &&
+                  (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l &&
+                                     (uint16_t)(v.mate_off4 - v.own_off4) == (uint16_t)(tv.mate_off4 - tv.own_off4)));
+    } else {
+        g.sync();
+        const VoteRead tv = vr[best_k];
+        uni = ch.len == od.l_qseq && tv.shift == 0 && tv.own_l == od.l_qseq;
+        for (int k = lane; k < m; k += GS) {
+            const VoteRead v = vr[k];
+            if (v.own_off4 == VR_NO_VOTE) continue;
+            uni = uni && v.own_l == tv.own_l && v.shift == 0 && v.ov_len == tv.ov_len &&
+                  (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l &&
+                                     (uint16_t)(v.mate_off4 - v.own_off4) == (uint16_t)(tv.mate_off4 - tv.own_off4)));
+        }
     }
     ch.uniform = g.all(uni);
     return ch;
