@@ -324,6 +324,18 @@ def b200_arm(args):
     for _ in range(2):
         eng.cluster_by_umi(pb, pr)
     barrier()
+    if args.host_sweep and rank == 0:  # tuning aid: end-to-end time by kind of host memory for the batch, to stderr
+        for label, kw in (("torch pinned", None), ("gcb_host_alloc", dict(lib=eng.lib)), ("gcb_host_alloc write-combined", dict(lib=eng.lib, write_combined=True))):
+            pbx = pb if kw is None else pinned_copy(batch, **kw)
+            for _ in range(2):
+                eng.cluster_by_umi(pbx, pr)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                eng.cluster_by_umi(pbx, pr)
+            torch.cuda.synchronize()
+            sys.stderr.write("host sweep %s: %.3f ms per step\n" % (label, (time.perf_counter() - t0) / 5 * 1e3))
+            del pbx
     if args.chunk_sweep and rank == 0:  # tuning aid: end-to-end time by pipeline chunk size, to stderr
         for mb in [int(x) for x in args.chunk_sweep.split(",")]:
             eng.set_chunk_bytes(mb << 20)
@@ -414,6 +426,7 @@ def main():
                          "4 = split with the fast kernel as a persistent ring (default)")
     ap.add_argument("--vote-threads", type=int, default=256, help="threads per CTA of the staged vote kernel")
     ap.add_argument("--sweep-only", action="store_true", help="stop after --sweep")
+    ap.add_argument("--host-sweep", action="store_true", help="tuning aid: end-to-end times by kind of host memory, to stderr")
     ap.add_argument("--chunk-sweep", default="", help="tuning aid: comma-separated pipeline chunk sizes in MB whose end-to-end times go to stderr")
     ap.add_argument("--sweep", default="", help="tuning aid: comma-separated mode:threads settings whose vote stage times go to stderr")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per vote launch from an ncu capture (profiles/)")

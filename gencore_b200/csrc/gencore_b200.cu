@@ -756,6 +756,17 @@ int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes) {
     return GCB_OK;
 }
 
+void *gcb_host_alloc(size_t bytes, int write_combined) {
+    void *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    if (cudaHostAlloc(&p, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void gcb_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 int gcb_set_debug(gcb_ctx *ctx, int key, int value) {
     if (!ctx) return GCB_ERR_ARG;
     if (key == 1) ctx->ablate = value;                 // profiling only: wrong results

@@ -77,13 +77,37 @@ class DeviceResult:
         return res
 
 
-def pinned_copy(batch: Batch) -> Batch:
-    """The same batch with every array in page-locked host memory (what gcb_consensus_batch recommends)."""
+class _HostBlock:
+    """Page-locked host memory from gcb_host_alloc, freed with the object."""
+
+    def __init__(self, lib, nbytes: int, write_combined: bool):
+        import ctypes
+        self.lib = lib
+        self.ptr = lib.gcb_host_alloc(max(nbytes, 16), 1 if write_combined else 0)
+        if not self.ptr:
+            raise MemoryError("gcb_host_alloc failed")
+        self.array = np.ctypeslib.as_array((ctypes.c_uint8 * max(nbytes, 16)).from_address(self.ptr))
+
+    def __del__(self):
+        try:
+            self.lib.gcb_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_copy(batch: Batch, lib=None, write_combined: bool = False) -> Batch:
+    """The same batch with every array in page-locked host memory (what gcb_consensus_batch recommends).  With `lib` (the
+    loaded C library) the memory comes from gcb_host_alloc, optionally write-combined (a packed batch is only written by the host)."""
     torch = _torch()
     keep = []
 
     def pin(a: np.ndarray) -> np.ndarray:
         flat = _as_u8(a)
+        if lib is not None:
+            blk = _HostBlock(lib, flat.size, write_combined)
+            blk.array[:flat.size] = flat
+            keep.append(blk)
+            return blk.array[:flat.size].view(a.dtype).reshape(a.shape)
         t = torch.empty(max(flat.size, 16), dtype=torch.uint8).pin_memory()
         t[:flat.size].copy_(torch.from_numpy(flat))
         keep.append(t)

@@ -24,7 +24,7 @@ DEFAULT_LIB = os.path.join(HERE, "csrc", "libgencore_b200.so")
 # every symbol include/gencore_b200.h declares
 ABI_SYMBOLS = ["gcb_abi_version", "gcb_default_options", "gcb_create", "gcb_destroy", "gcb_last_error", "gcb_set_reference",
                "gcb_set_reference_device", "gcb_consensus_batch", "gcb_consensus_batch_device", "gcb_batch_status",
-               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_vote_mode", "gcb_set_vote_threads", "gcb_set_slow_queue_bytes", "gcb_set_debug"]
+               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_vote_mode", "gcb_set_vote_threads", "gcb_set_slow_queue_bytes", "gcb_set_debug", "gcb_host_alloc", "gcb_host_free"]
 
 
 class EngineError(RuntimeError):
@@ -60,6 +60,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gcb_set_chunk_bytes.restype = C.c_int
     lib.gcb_set_vote_mode.restype = C.c_int
     lib.gcb_set_vote_mode.argtypes = [C.c_void_p, C.c_int]
+    lib.gcb_host_alloc.restype = C.c_void_p
+    lib.gcb_host_alloc.argtypes = [C.c_size_t, C.c_int]
+    lib.gcb_host_free.restype = None
+    lib.gcb_host_free.argtypes = [C.c_void_p]
     lib.gcb_set_debug.restype = C.c_int
     lib.gcb_set_debug.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.gcb_set_slow_queue_bytes.restype = C.c_int

@@ -218,6 +218,13 @@ int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes);
  * identical. */
 int gcb_set_vote_mode(gcb_ctx *ctx, int mode);
 
+/* Page-locked host memory for the arrays of a gcb_batch / gcb_result handed to gcb_consensus_batch (pageable memory works,
+ * at a fraction of the link rate).  `write_combined` memory is for buffers the host only WRITES (a packed batch): the copy
+ * engine reads it without snooping the CPU caches; reading it back on the host is very slow (on the round-1 B200 box both
+ * kinds upload at the same 44 GB/s).  NULL on failure. */
+void *gcb_host_alloc(size_t bytes, int write_combined);
+void gcb_host_free(void *p);
+
 /* Profiling / tuning aid, not for production: key 1 = switch parts of the ring kernel off (results are WRONG, timing only),
  * key 2 = force the ring kernel's tile window (14 or 15 = log2 bytes, 0 = automatic; results unchanged),
  * key 3 = lanes per cluster in umi_group_kernel / select_template_kernel (8, 16, 32; 0 = by mean cluster size; results unchanged). */

@@ -436,6 +436,8 @@ inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = malloc(n); return *p ? 0 : 2; }
 inline cudaError_t cudaFreeHost(void *p) { free(p); return 0; }
+constexpr unsigned cudaHostAllocDefault = 0, cudaHostAllocWriteCombined = 4;
+inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned) { *p = malloc(n); return *p ? 0 : 2; }
 inline cudaError_t cudaGetLastError() { return 0; }
 inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDevice(int *d) { *d = 0; return 0; }
