@@ -475,8 +475,6 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
         gcb_destroy(ctx);
         return GCB_ERR_CUDA;
     }
-    if (const char *e = getenv("GCB_ABLATE")) ctx->ablate = atoi(e);                      // profiling only: wrong results
-    if (const char *e = getenv("GCB_RING_WINDOW_SHIFT")) ctx->ring_window_shift = atoi(e);  // tuning only: same results
     *out = ctx;
     return GCB_OK;
 }
@@ -769,7 +767,10 @@ void gcb_host_free(void *p) {
 
 int gcb_set_debug(gcb_ctx *ctx, int key, int value) {
     if (!ctx) return GCB_ERR_ARG;
-    if (key == 1) ctx->ablate = value;                 // profiling only: wrong results
+    if (key == 1) {  // profiling only (wrong results): refused unless the process says it is profiling
+        if (value != 0 && !getenv("GCB_PROFILING")) return GCB_ERR_ARG;
+        ctx->ablate = value;
+    }
     else if (key == 2) ctx->ring_window_shift = value;  // tuning only: same results
     else if (key == 3) ctx->group_lanes = value;        // tuning only: same results
     else if (key == 4) ctx->ring_units = value == 2 ? 2 : 1;  // tuning only: same results

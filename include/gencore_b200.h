@@ -225,7 +225,8 @@ int gcb_set_vote_mode(gcb_ctx *ctx, int mode);
 void *gcb_host_alloc(size_t bytes, int write_combined);
 void gcb_host_free(void *p);
 
-/* Profiling / tuning aid, not for production: key 1 = switch parts of the ring kernel off (results are WRONG, timing only),
+/* Profiling / tuning aid, not for production: key 1 = switch parts of the ring kernel off (results are WRONG, timing only;
+ * refused with GCB_ERR_ARG unless the environment variable GCB_PROFILING is set),
  * key 2 = force the ring kernel's tile window (14 or 15 = log2 bytes, 0 = automatic; results unchanged),
  * key 3 = lanes per cluster in umi_group_kernel / select_template_kernel (8, 16, 32; 0 = by mean cluster size; results unchanged). */
 int gcb_set_debug(gcb_ctx *ctx, int key, int value);
