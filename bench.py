@@ -237,10 +237,10 @@ def b200_arm(args):
         names = ["umi_group", "select_template+scan", "tile_prep", "score_vote", "duplex"]
     else:
         stages = [STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_VOTE_PREP_ONLY, STAGE_VOTE_FAST_ONLY, STAGE_VOTE_REST_ONLY, STAGE_DUPLEX]
-        names = ["umi_group", "select_template+scan", "tile_prep", "score_vote", "slow_columns+finalize", "duplex"]
+        names = ["umi_group", "select_template+scan", "tile_prep", "score_vote", "slow_columns+rollback", "duplex"]
     i_vote = names.index("score_vote")
     vote_kernel = {0: "vote_tiled_kernel", 1: "vote_pipe_kernel", 2: "vote_staged_kernel", 3: "vote_fast_kernel", 4: "vote_ring_kernel"}[args.vote_mode]
-    vote_parts = [k for k, n in enumerate(names) if n in ("tile_prep", "score_vote", "slow_columns+finalize")]
+    vote_parts = [k for k, n in enumerate(names) if n in ("tile_prep", "score_vote", "slow_columns+rollback")]
     def step(events=None):
         for k, st in enumerate(stages):
             if events is not None:

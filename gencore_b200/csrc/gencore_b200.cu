@@ -112,7 +112,7 @@ struct TilePlan {
     int32_t window, window_shift, slab_cap, smem;
     int32_t pipelined, n_stages, stage_bytes;  // vote_pipe_kernel: ring of n_stages tiles of stage_bytes each
     int32_t staged;                            // vote_staged_kernel / vote_fast_kernel (same tile geometry)
-    int32_t split;                             // vote_fast_kernel + slow_columns_kernel + vote_finalize_kernel
+    int32_t split;                             // vote_fast_kernel + slow_columns_kernel + vote_rollback_kernel
     int32_t ring;                              // vote_ring_kernel instead of vote_fast_kernel (n_stages, stage_bytes)
 };
 TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode, int ring_window_shift = 0) {
@@ -218,7 +218,7 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
         cap_words &= ~3ll;
         if (cap_words < 64) cap_words = 64;
         const int64_t cap_recs = cap_words / 12;  // the smallest record is 12 words
-        GCB_RES(w_sq_count, 8 * VQ_NQ * GCB_MAX_CHUNKS);
+        GCB_RES(w_sq_count, 8 * (VQ_NQ + 1) * GCB_MAX_CHUNKS);  // per chunk: VQ_NQ queue counters + the rollback list's count
         GCB_RES(w_sq_words, 4 * cap_words * VQ_NQ);
         GCB_RES(w_sq_index, 4 * cap_recs * VQ_NQ);
         GCB_RES(w_sq_acc, 2 * n_pairs * 4);
@@ -306,7 +306,6 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
 #undef GCB_UMI_LAUNCH
     if (stages & GCB_STAGE_SELECT_TEMPLATE) {
         const int32_t n_scan = (int32_t)((nc + SCAN_BLOCK - 1) / SCAN_BLOCK);
-        GCB_CUDA(ctx, cudaMemsetAsync(result.groups + v.p0, 0, sizeof(gcb_group_result) * (size_t)(v.p1 - v.p0), stream));
         if (gs == 8) GCB_LAUNCH(select_template_kernel<8>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
         else if (gs == 16) GCB_LAUNCH(select_template_kernel<16>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
         else GCB_LAUNCH(select_template_kernel<32>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
@@ -351,15 +350,16 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
             if ((run_fast || run_rest) && plan.split) {
                 // chunks of one batch run one after another on the stream and share the queues; every chunk has its own counters
                 SlowQueues sq;
-                sq.count = (unsigned long long *)ctx->w_sq_count.p + (size_t)VQ_NQ * v.index;
+                sq.count = (unsigned long long *)ctx->w_sq_count.p + (size_t)(VQ_NQ + 1) * v.index;
                 sq.words = (uint32_t *)ctx->w_sq_words.p;
                 sq.index = (uint32_t *)ctx->w_sq_index.p;
                 sq.cap_words = ctx->sq_cap_words;
                 sq.cap_recs = ctx->sq_cap_recs;
-                sq.acc = (int32_t *)ctx->w_sq_acc.p;
+                sq.rb_list = (int32_t *)ctx->w_sq_acc.p + 2 * (size_t)v.p0;
+                sq.rb_count = (int32_t *)(sq.count + VQ_NQ);
+                sq.rb_cap = 2 * (v.p1 - v.p0);
                 if (run_fast) {
-                    GCB_CUDA(ctx, cudaMemsetAsync(sq.count, 0, 8 * VQ_NQ, stream));
-                    if (v.p1 > v.p0) GCB_CUDA(ctx, cudaMemsetAsync(sq.acc + 2 * (size_t)v.p0, 0, 8 * (size_t)(v.p1 - v.p0), stream));
+                    GCB_CUDA(ctx, cudaMemsetAsync(sq.count, 0, 8 * (VQ_NQ + 1), stream));
                     if (plan.ring) {
                         const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
 #define GCB_RING_LAUNCH(NT, NU)                                                                                                              \
@@ -379,9 +379,7 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                 }
                 if (run_rest) {
                     GCB_LAUNCH(slow_columns_kernel, dim3(VQ_NQ * VQ_SLOW_PARTS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ctx->genome, ctx->opt, sq);
-                    if (v.p1 > v.p0)
-                        GCB_LAUNCH(vote_finalize_kernel, dim3((unsigned)((2 * (int64_t)(v.p1 - v.p0) + VQ_FINAL_THREADS - 1) / VQ_FINAL_THREADS)),
-                                   dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->opt, sq, v.p0, v.p1);
+                    GCB_LAUNCH(vote_rollback_kernel, dim3(VQ_FINAL_CTAS), dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->opt, sq, v.p0, v.p1);
                     ctx->launches += 2;
                 }
             } else if (run_fast) {

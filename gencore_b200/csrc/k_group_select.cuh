@@ -458,6 +458,10 @@ __global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(Batc
     for (int i = G + lane; i < n; i += GS) {  // slots that hold no family: the vote kernel reads side_mode to know
         ws.side_mode[2 * (int64_t)(p0 + i)] = SIDE_NONE;
         ws.side_mode[2 * (int64_t)(p0 + i) + 1] = SIDE_NONE;
+        int2 *row = (int2 *)(r.groups + (p0 + i));  // and their result rows read as zeros (every other row is written below)
+        static_assert(sizeof(gcb_group_result) % 8 == 0, "result rows are written as 8-byte words");
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(gcb_group_result) / 8); q++) row[q] = make_int2(0, 0);
     }
     int64_t out_rel = 0;
     for (int gi = 0; gi < G; gi++) {

@@ -243,6 +243,12 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                     for (int u = 0; u < NU; u++) cm[u] = make_masks(l_out, len, col0 + VT_CHUNK * u);
                 }
                 if (mine && j == 0 && ft.mode != SIDE_COPY) GCB_COUNT((ft.flags & FS_UNIFORM) ? 4 : 5, 1);
+                if (mine && j == 0) {  // slow_columns_kernel adds to these
+                    gcb_group_result *gr = r.groups + ft.slot;
+                    const int sd = (ft.flags & FS_SIDE1) ? 1 : 0;
+                    gr->diff[sd] = 0;
+                    gr->mismatch_inc[sd] = 0;
+                }
                 uint32_t mo[4 * NU], me[4 * NU], dis[2 * NU];
 #pragma unroll
                 for (int w = 0; w < 4 * NU; w++) mo[w] = me[w] = 0u;
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                     }
                     if (pool_r + T > pool_re) {
                         // no queue space: the generic kernel redoes the whole tile from the payload (it runs after
-                        // slow_columns_kernel and vote_finalize_kernel)
+                        // slow_columns_kernel and vote_rollback_kernel)
                         if (lane == 0 && atomicExch(&sh->handed_over, 1) == 0) {
                             ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~tile;
                             GCB_COUNT(1, 1);

@@ -15,8 +15,8 @@
 //   slow_columns_kernel   one thread per queued record, full warps: score per read (pair.cpp), three-bin register
 //                         histogram (group.cpp:376-393), top-2 selection (group.cpp:395-417), the rules and the
 //                         reference arbitration (group.cpp:419-525), patches the consensus record and adds to the
-//                         family side's diff / mismatchInc.
-//   vote_finalize_kernel  one thread per family side: diff, mismatchInc, the > 5-mismatch rollback (group.cpp:538-566).
+//                         family side's diff / mismatchInc (atomics on the result row; the fast kernel zeroed them).
+//   vote_rollback_kernel  the > 5-mismatch rollback (group.cpp:538-566) of the family sides slow_columns_kernel listed.
 //
 // The uniform-family loop of the fast kernel keeps everything in the raw byte order of the payload: disagreement with
 // the template and disagreement among the mates are OR-accumulated as XOR residues of the raw words (a mate differs
@@ -34,14 +34,17 @@ constexpr int VQ_NQ = 32;                      // slow-column queues; tile t use
 constexpr uint32_t VQ_INVALID = 0xFFFFFFFFu;   // index entry of a reservation that did not fit
 constexpr int VQ_SLOW_THREADS = 128;
 constexpr int VQ_SLOW_PARTS = 96;              // CTAs per queue in slow_columns_kernel
-constexpr int VQ_FINAL_THREADS = 256;
+constexpr int VQ_FINAL_THREADS = 128;
+constexpr int VQ_FINAL_CTAS = 64;             // vote_rollback_kernel strides over its (normally empty) list
 
 struct SlowQueues {
     unsigned long long *count;   // [VQ_NQ] records << 32 | words reserved so far (may run past the capacity)
     uint32_t *words;             // [VQ_NQ][cap_words] records (see SR_HDR_WORDS)
     uint32_t *index;             // [VQ_NQ][cap_recs] word offset of every record inside its queue, VQ_INVALID = none
     uint32_t cap_words, cap_recs;
-    int32_t *acc;                // [2*n_pairs] per family side (2 * slot + side): diff + 65536 * mismatchInc
+    int32_t *rb_list;            // [rb_cap] family sides (2 * slot + side) whose mismatchInc went from 5 to 6: rollback candidates
+    int32_t *rb_count;           // [1] entries appended to rb_list (may run past rb_cap: then every family side is checked)
+    int32_t rb_cap;
 };
 
 // record: SR_HDR_WORDS header words, then n entries (one per read of the family side), padded to a multiple of 4 words.
@@ -264,6 +267,12 @@ __global__ void __launch_bounds__(VS_MAX_THREADS, 3) vote_fast_kernel(BatchView 
         ChunkMasks cm = cm_common;
         if (l_out != common_l || len != l_out) cm = make_masks(l_out, len, col0);
         if (mine && j == 0 && ft.mode != SIDE_COPY) GCB_COUNT((ft.flags & FS_UNIFORM) ? 4 : 5, 1);
+        if (mine && j == 0) {  // slow_columns_kernel adds to these
+            gcb_group_result *gr = r.groups + ft.slot;
+            const int sd = (ft.flags & FS_SIDE1) ? 1 : 0;
+            gr->diff[sd] = 0;
+            gr->mismatch_inc[sd] = 0;
+        }
         // per-column maxima live in 16-bit lanes (VIMNMX.U16x2 / VIMNMX3.U16x2 are native, a per-byte maximum is seven
         // instructions): mo[k] tracks bytes 1 and 3 of quality word k in the high byte of each half, me[k] bytes 0 and 2
         uint32_t mo[4] = {0u, 0u, 0u, 0u}, me[4] = {0u, 0u, 0u, 0u}, dis0 = 0u, dis1 = 0u;
@@ -408,7 +417,7 @@ __global__ void __launch_bounds__(VS_MAX_THREADS, 3) vote_fast_kernel(BatchView 
             uint32_t ri = rec0 + (uint32_t)((incl - mine64) >> 32), wi = word0 + (uint32_t)(incl - mine64);
             if (!fits) {
                 // the queue is full: the generic kernel redoes the whole tile from the payload (it runs after
-                // slow_columns_kernel and vote_finalize_kernel); the reserved index entries are marked unused
+                // slow_columns_kernel and vote_rollback_kernel); the reserved index entries are marked unused
                 for (uint32_t i = (uint32_t)lane; i < T; i += WARP)
                     if (rec0 + i < sq.cap_recs) q_index[rec0 + i] = VQ_INVALID;
                 if (lane == 0 && atomicExch(s_handed, 1) == 0) {
@@ -580,7 +589,15 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
                 if (obase == ref4) d_mm = 1;
                 else if (co.base == ref4) d_mm = -1;
             }
-            atomicAdd(sq.acc + fsid, 1 + d_mm * 65536);  // (fsid = 2 * slot + side)
+            gcb_group_result *gr = r.groups + (fsid >> 1);  // (fsid = 2 * slot + side; the fast kernel zeroed both counters)
+            atomicAdd(&gr->diff[side], 1);
+            if (d_mm != 0) {
+                const int before = atomicAdd(&gr->mismatch_inc[side], d_mm);
+                if (d_mm > 0 && before == 5) {  // more than five new mismatches so far: vote_rollback_kernel looks at the final count
+                    const int k = atomicAdd(sq.rb_count, 1);
+                    if (k < sq.rb_cap) sq.rb_list[k] = (int32_t)fsid;
+                }
+            }
             const int byte = col >> 1;
             const unsigned delta = ((unsigned)(obase ^ co.base) & 0xFu) << ((col & 1) ? 0 : 4);
             atomicXor((unsigned *)(out + qbytes + (byte & ~3)), delta << (8 * (byte & 3)));
@@ -617,33 +634,36 @@ __global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView
 }
 
 // ------------------------------------------------------------------------------------------------
-// group.cpp:526-566 per family side once all of its columns are decided: diff, mismatchInc, rollback.  One thread per
-// (slot, side); family sides that changed no base keep the zeros select_template_kernel left.
-__global__ void __launch_bounds__(VQ_FINAL_THREADS) vote_finalize_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o, SlowQueues sq,
-                                                                         int32_t p0, int32_t p1) {
-    const int64_t i = 2 * (int64_t)p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * (int64_t)p1) return;
-    const int a = sq.acc[i];
-    if (a == 0) return;
-    const int diff = a & 0xFFFF, mm = (a - diff) >> 16;
+// group.cpp:538-566 once every column is decided: a family side that collected more than five new mismatches keeps the
+// template's bases and (rewritten) qualities.  The candidates were listed by slow_columns_kernel (normally none).
+GCB_DEV void rollback_family_side(const BatchView &b, const ResultView &r, const Workspace &ws, const gcb_options &o, int64_t i) {
     const int slot = (int)(i >> 1), side = (int)(i & 1);
-    gcb_group_result *gr = r.groups + slot;
-    if (mm > 5) {  // the template's bases and (rewritten) qualities, read from the payload itself
-        const FsDesc d = ws.fs_desc[i];
-        const VoteRead tv = ws.vote_reads[2 * (int64_t)d.mb + (int64_t)side * d.m + d.tmpl_k];
-        const uint8_t *cb = b.payload + ws.slab_off[d.c];
-        uint8_t *out = r.out_payload + gr->out_off[side];
-        const int l_out = d.l_out, qbytes = GCB_ALIGN4(l_out);
-        const uint8_t *tseq = cb + 4 * (int)tv.own_off4 + qbytes;
-        for (int col = 0; col < l_out; col++) {
-            int base, qual = 0, sc;
-            fetch_ent(cb, tv, col, side, o, base, qual, sc);
-            out[col] = (uint8_t)qual;
-        }
-        for (int k = 0; k < (l_out + 1) >> 1; k++) out[qbytes + k] = tseq[k];
+    const gcb_group_result *gr = r.groups + slot;
+    if (gr->mismatch_inc[side] <= 5) return;
+    const FsDesc d = ws.fs_desc[i];
+    const VoteRead tv = ws.vote_reads[2 * (int64_t)d.mb + (int64_t)side * d.m + d.tmpl_k];
+    const uint8_t *cb = b.payload + ws.slab_off[d.c];
+    uint8_t *out = r.out_payload + gr->out_off[side];
+    const int l_out = d.l_out, qbytes = GCB_ALIGN4(l_out);
+    const uint8_t *tseq = cb + 4 * (int)tv.own_off4 + qbytes;
+    for (int col = 0; col < l_out; col++) {
+        int base, qual = 0, sc;
+        fetch_ent(cb, tv, col, side, o, base, qual, sc);
+        out[col] = (uint8_t)qual;
     }
-    gr->diff[side] = diff;
-    gr->mismatch_inc[side] = mm;
+    for (int k = 0; k < (l_out + 1) >> 1; k++) out[qbytes + k] = tseq[k];
+}
+
+__global__ void __launch_bounds__(VQ_FINAL_THREADS) vote_rollback_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o, SlowQueues sq,
+                                                                         int32_t p0, int32_t p1) {
+    const int n = *sq.rb_count;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+    if (n <= sq.rb_cap) {
+        for (int64_t k = tid; k < n; k += nthreads) rollback_family_side(b, r, ws, o, sq.rb_list[k]);
+    } else {  // the list overflowed: look at every family side of the view
+        for (int64_t i = 2 * (int64_t)p0 + tid; i < 2 * (int64_t)p1; i += nthreads)
+            if (ws.side_mode[i] != SIDE_NONE && ws.side_mode[i] != SIDE_COPY) rollback_family_side(b, r, ws, o, i);
+    }
 }
 
 }  // namespace gcb

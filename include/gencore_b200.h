@@ -213,7 +213,7 @@ int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes);
  * persistent pipelined kernel (vote_pipe_kernel, falls back to 0 for batches whose clusters are too large for its
  * ring), 2 = one CTA per tile over headers and family-side lists prepared once per batch (vote_staged_kernel),
  * 3 = the same tiles with the slow columns queued for a second kernel (vote_fast_kernel + slow_columns_kernel +
- * vote_finalize_kernel), 4 = mode 3 with the fast kernel as one persistent CTA per SM over a ring of staged tiles
+ * vote_rollback_kernel), 4 = mode 3 with the fast kernel as one persistent CTA per SM over a ring of staged tiles
  * (vote_ring_kernel, the default; falls back to 3 for batches whose clusters are too large for a ring).  Results are
  * identical. */
 int gcb_set_vote_mode(gcb_ctx *ctx, int mode);

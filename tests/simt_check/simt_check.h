@@ -33,6 +33,8 @@
 struct uint3 { unsigned x, y, z; };
 struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
 struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
+struct __attribute__((aligned(8))) int2 { int x, y; };
+inline int2 make_int2(int x, int y) { int2 v = {x, y}; return v; }
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
