@@ -214,6 +214,8 @@ def b200_arm(args):
     eng = ConsensusEngine(opt, local)
     eng.set_vote_mode(args.vote_mode)
     eng.set_vote_threads(args.vote_threads)
+    if args.group_lanes:
+        eng.set_debug(3, args.group_lanes)
     # the packed reference reaches every GPU by ONE NCCL broadcast from rank 0
     g_dev = torch.from_numpy(genome.packed4).to(dev) if rank == 0 else torch.empty(len(genome.packed4), dtype=torch.uint8, device=dev)
     if world > 1:
@@ -426,6 +428,7 @@ def main():
                          "4 = split with the fast kernel as a persistent ring (default)")
     ap.add_argument("--vote-threads", type=int, default=256, help="threads per CTA of the staged vote kernel")
     ap.add_argument("--sweep-only", action="store_true", help="stop after --sweep")
+    ap.add_argument("--group-lanes", type=int, default=0, help="tuning aid: lanes per cluster in umi_group / select_template (8, 16, 32; 0 = automatic)")
     ap.add_argument("--host-sweep", action="store_true", help="tuning aid: end-to-end times by kind of host memory, to stderr")
     ap.add_argument("--chunk-sweep", default="", help="tuning aid: comma-separated pipeline chunk sizes in MB whose end-to-end times go to stderr")
     ap.add_argument("--sweep", default="", help="tuning aid: comma-separated mode:threads settings whose vote stage times go to stderr")
