@@ -41,71 +41,6 @@ GCB_DEV int duplex_merge_records(uint8_t *rec1, int len1, uint8_t *rec2, int len
     return diff;
 }
 
-// The same walk for records of at most DUPLEX_REG_BASES bases with both packed sequences in registers: the walk's only
-// state between bytes is whether it enters the next byte at its high nibble (even index) or at its low nibble (odd index,
-// after a byte whose remaining nibbles were equal), so the loop over bytes unrolls completely and no load depends on a
-// store.  Identical results to duplex_merge_records.
-constexpr int DUPLEX_REG_BASES = 160;
-GCB_DEV int duplex_merge_records_reg(uint8_t *rec1, int len1, uint8_t *rec2, int len2) {
-    constexpr int NWORDS = DUPLEX_REG_BASES / 8;
-    int diff = len1 > len2 ? len1 - len2 : len2 - len1;
-    const int len = min(len1, len2);
-    uint32_t *s1 = (uint32_t *)(rec1 + GCB_ALIGN4(len1)), *s2 = (uint32_t *)(rec2 + GCB_ALIGN4(len2));
-    const int nw = (len + 7) >> 3;
-    uint32_t w1[NWORDS], w2[NWORDS];
-#pragma unroll
-    for (int k = 0; k < NWORDS; k++) {
-        w1[k] = k < nw ? s1[k] : 0u;
-        w2[k] = k < nw ? s2[k] : 0u;
-    }
-    bool odd = false, changed = false;
-#pragma unroll
-    for (int B = 0; B < DUPLEX_REG_BASES / 2; B++) {
-        const int sh = 8 * (B & 3);
-        uint32_t a = (w1[B >> 2] >> sh) & 0xFFu, c = (w2[B >> 2] >> sh) & 0xFFu;
-        bool touched = false;
-        if (!odd && 2 * B < len && a != c) {  // index 2B: the high nibbles
-            if (base_letter((int)(a >> 4)) != base_letter((int)(c >> 4))) {
-                diff++;
-                rec1[2 * B] = 0;
-                rec2[2 * B] = 0;
-                a |= 0xF0u;
-                c |= 0xF0u;
-                touched = true;
-            }
-            odd = true;  // the walk goes on at index 2B + 1
-        }
-        if (odd) {  // index 2B + 1: the low nibbles (entered here, or coming from the high nibble above)
-            if (2 * B + 1 < len && a != c) {
-                if (base_letter((int)(a & 0xFu)) != base_letter((int)(c & 0xFu))) {
-                    diff++;
-                    rec1[2 * B + 1] = 0;
-                    rec2[2 * B + 1] = 0;
-                    a |= 0x0Fu;
-                    c |= 0x0Fu;
-                    touched = true;
-                }
-                odd = false;  // next index 2B + 2
-            }
-            // (equal bytes: the index jumps by two and stays odd)
-        }
-        if (touched) {
-            w1[B >> 2] = (w1[B >> 2] & ~(0xFFu << sh)) | (a << sh);
-            w2[B >> 2] = (w2[B >> 2] & ~(0xFFu << sh)) | (c << sh);
-            changed = true;
-        }
-    }
-    if (changed) {
-#pragma unroll
-        for (int k = 0; k < NWORDS; k++)
-            if (k < nw) {
-                s1[k] = w1[k];
-                s2[k] = w2[k];
-            }
-    }
-    return diff;
-}
-
 __global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o) {
     const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= b.n_clusters) return;
@@ -140,8 +75,7 @@ __global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, Res
                 if (t1 < 0 || t2 < 0) continue;
                 const int l1 = b.reads[t1].l_qseq, l2 = b.reads[t2].l_qseq;
                 if (r1->out_off[s] + record_bytes(l1) > r.out_capacity || r2->out_off[s] + record_bytes(l2) > r.out_capacity) continue;
-                uint8_t *q1 = r.out_payload + r1->out_off[s], *q2 = r.out_payload + r2->out_off[s];
-                diff += (l1 <= DUPLEX_REG_BASES && l2 <= DUPLEX_REG_BASES) ? duplex_merge_records_reg(q1, l1, q2, l2) : duplex_merge_records(q1, l1, q2, l2);
+                diff += duplex_merge_records(r.out_payload + r1->out_off[s], l1, r.out_payload + r2->out_off[s], l2);
             }
             r1->duplex_partner = g2;
             r1->duplex_diff = diff;
