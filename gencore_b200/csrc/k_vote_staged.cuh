@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(VS_PREP_THREADS, 10) tile_prep2_kernel(BatchVi
         if (tid == 0) hdr[blockIdx.x] = h;
         return;
     }
-    if (NP > VS_MAX_PAIRS || slab_bytes > slab_cap) {  // not a tile for the staged kernel
+    if (NP > VS_MAX_PAIRS || c1 - c0 > VS_MAX_PAIRS || slab_bytes > slab_cap) {  // not a tile for the staged kernel
         if (tid == 0) {
             hdr[blockIdx.x] = h;
             ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = (int32_t)blockIdx.x;
@@ -86,7 +86,15 @@ __global__ void __launch_bounds__(VS_PREP_THREADS, 10) tile_prep2_kernel(BatchVi
         s_lmax = 1;
         s_common = 0;
     }
-    const int64_t out_base0 = ws.scan_block[c0 / SCAN_BLOCK] + ws.cluster_out_off[c0];
+    // the tile's clusters (at most one per pair position): slab offset inside the tile and absolute output offset, fetched
+    // together with the side modes so that the family-side descriptors are the last level of dependent loads
+    __shared__ int32_t s_cslab[VS_MAX_PAIRS];
+    __shared__ int64_t s_cout[VS_MAX_PAIRS];
+    for (int k = tid; k < c1 - c0; k += VS_PREP_THREADS) {
+        const int c = c0 + k;
+        s_cslab[k] = (int32_t)(ws.slab_off[c] - t0.slab0);
+        s_cout[k] = ws.scan_block[c / SCAN_BLOCK] + ws.cluster_out_off[c];
+    }
     FsDesc fd[VS_PREP_ROUNDS][2];
     int64_t c_slab[VS_PREP_ROUNDS], c_out[VS_PREP_ROUNDS];
     uint32_t incl[VS_PREP_ROUNDS], mine[VS_PREP_ROUNDS];
@@ -108,11 +116,6 @@ __global__ void __launch_bounds__(VS_PREP_THREADS, 10) tile_prep2_kernel(BatchVi
         }
         const bool live0 = fd[rd][0].mode != SIDE_NONE, live1 = fd[rd][1].mode != SIDE_NONE;
         c_slab[rd] = c_out[rd] = 0;
-        if (live0 || live1) {
-            const int c = live0 ? fd[rd][0].c : fd[rd][1].c;
-            c_slab[rd] = ws.slab_off[c] - t0.slab0;
-            c_out[rd] = ws.scan_block[c / SCAN_BLOCK] + ws.cluster_out_off[c] - out_base0;
-        }
         mine[rd] = (live0 ? 1u : 0u) + (live1 ? 1u : 0u);
         uint32_t in = mine[rd];
         for (int off = 1; off < WARP; off <<= 1) {
@@ -123,6 +126,14 @@ __global__ void __launch_bounds__(VS_PREP_THREADS, 10) tile_prep2_kernel(BatchVi
         if (lane == WARP - 1) s_wsum[rd][warp] = in;
     }
     __syncthreads();
+    const int64_t out_base0 = s_cout[0];
+#pragma unroll
+    for (int rd = 0; rd < VS_PREP_ROUNDS; rd++)
+        if (mine[rd] != 0) {  // (a cluster of the tile starts inside it: at most as many clusters as pair positions)
+            const int k = (fd[rd][0].mode != SIDE_NONE ? fd[rd][0].c : fd[rd][1].c) - c0;
+            c_slab[rd] = s_cslab[k];
+            c_out[rd] = s_cout[k] - out_base0;
+        }
     uint32_t total = 0, pre[VS_PREP_ROUNDS];
 #pragma unroll
     for (int rd = 0; rd < VS_PREP_ROUNDS; rd++) {
