@@ -395,7 +395,7 @@ def b200_arm(args):
                          "peak_source": peak_src, "traffic": args.traffic if args.traffic is not None else (measured_traffic(vote_kernel) if args.pairs == 1_000_000 else None),
                          "algorithmic_bytes": own, "kernel_ms": vote_ms,
                          "timed": "CUDA events around the launch of %s on the launching stream" % vote_kernel,
-                         "whole_vote": {"kernels": "every launch of the vote (tile preparation, %s, slow columns, finalize, generic)" % vote_kernel,
+                         "whole_vote": {"kernels": "every launch of the vote (tile preparation, %s, slow columns, rollback, generic)" % vote_kernel,
                                         "ms": whole_ms, "algorithmic_bytes": alg["total"], "achieved": whole, "frac": whole / peak}},
             "e2e": {"value": args.pairs * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * e2e_s},
             "gpu_launches": int(launches),
