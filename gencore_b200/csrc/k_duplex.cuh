@@ -1,6 +1,6 @@
 // k_duplex.cuh — the tail of Cluster::clusterByUMI (cluster.cpp:102-188): duplex partner search,
 // Cluster::duplexMerge / duplexMergeBam (cluster.cpp:190-244) on the consensus records the vote
-// kernel wrote, and the SSCS / DCS / dropped verdict of every family.  One thread per cluster: the
+// kernel wrote, and the SSCS / DCS / dropped verdict of every family.  Two threads per cluster: the
 // partner search is a sequential stack walk in the reference and its order decides who pairs up.
 #pragma once
 
@@ -41,23 +41,30 @@ GCB_DEV int duplex_merge_records(uint8_t *rec1, int len1, uint8_t *rec2, int len
     return diff;
 }
 
+// Two threads per cluster: both walk the stack (same decisions), each merges one side of a strand pair's consensus records
+// (the walk over a record is sequential, the two sides are independent), thread 0 writes the verdicts.
 __global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o) {
-    const int c = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int c = t >> 1, side = t & 1;
     if (c >= b.n_clusters) return;
+    const unsigned pairmask = 3u << (lane_id() & ~1);  // this cluster's two lanes
     const int p0 = b.cluster_pair_off[c];
     const int G = r.cluster_n_groups[c];
     const int nw = b.umi_words;
     gcb_group_result *gr = r.groups + p0;
 
     if (!(ws.cluster_has_umi[c] && !o.disable_duplex)) {  // cluster.cpp:169-183
-        for (int g = 0; g < G; g++)
-            gr[g].status = (!o.duplex_only && gr[g].merge_reads >= o.cluster_size_req) ? GCB_GROUP_SSCS : GCB_GROUP_DROPPED;
+        if (side == 0)
+            for (int g = 0; g < G; g++)
+                gr[g].status = (!o.duplex_only && gr[g].merge_reads >= o.cluster_size_req) ? GCB_GROUP_SSCS : GCB_GROUP_DROPPED;
         return;
     }
     // cluster.cpp:119-168: pop from the back, pair with the first family (in creation order) whose UMI is the swap
     int32_t *alive = ws.scratch + 2 * (int64_t)p0;  // G <= pairs of the cluster
     int nalive = G;
-    for (int g = 0; g < G; g++) alive[g] = g;
+    if (side == 0)
+        for (int g = 0; g < G; g++) alive[g] = g;
+    __syncwarp(pairmask);
     while (nalive > 0) {
         const int g1 = alive[--nalive];
         gcb_group_result *r1 = gr + g1;
@@ -69,34 +76,40 @@ __global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, Res
             const Umi u2 = r2->umi_pair >= 0 ? umi_load(b.umi + (int64_t)r2->umi_pair * nw, nw) : umi_load(b.umi, 0);
             if (!umi_is_duplex(u1, u2)) continue;
             found = true;
-            int diff = 0;  // Cluster::duplexMerge, cluster.cpp:190-198
-            for (int s = 0; s < 2; s++) {
+            int diff = 0;  // Cluster::duplexMerge, cluster.cpp:190-198: this thread's side
+            {
+                const int s = side;
                 const int t1 = r1->tmpl_read[s], t2 = r2->tmpl_read[s];
-                if (t1 < 0 || t2 < 0) continue;
-                const int l1 = b.reads[t1].l_qseq, l2 = b.reads[t2].l_qseq;
-                if (r1->out_off[s] + record_bytes(l1) > r.out_capacity || r2->out_off[s] + record_bytes(l2) > r.out_capacity) continue;
-                diff += duplex_merge_records(r.out_payload + r1->out_off[s], l1, r.out_payload + r2->out_off[s], l2);
-            }
-            r1->duplex_partner = g2;
-            r1->duplex_diff = diff;
-            r2->duplex_partner = g1;
-            r2->duplex_diff = diff;
-            r2->status = GCB_GROUP_DUPLEX_PARTNER;
-            if (diff <= o.duplex_mismatch_threshold) {
-                if (r1->merge_reads + r2->merge_reads >= o.cluster_size_req) {
-                    r1->status = GCB_GROUP_DCS;
-                    r1->reverse_merge_reads = r2->merge_reads;  // Pair::setDuplex
-                } else {
-                    r1->status = GCB_GROUP_DUPLEX_SMALL;
+                if (t1 >= 0 && t2 >= 0) {
+                    const int l1 = b.reads[t1].l_qseq, l2 = b.reads[t2].l_qseq;
+                    if (!(r1->out_off[s] + record_bytes(l1) > r.out_capacity || r2->out_off[s] + record_bytes(l2) > r.out_capacity))
+                        diff = duplex_merge_records(r.out_payload + r1->out_off[s], l1, r.out_payload + r2->out_off[s], l2);
                 }
-            } else {
-                r1->status = GCB_GROUP_DUPLEX_DIFF;
             }
-            for (int k = i; k + 1 < nalive; k++) alive[k] = alive[k + 1];
+            diff += __shfl_xor_sync(pairmask, diff, 1);
+            if (side == 0) {
+                r1->duplex_partner = g2;
+                r1->duplex_diff = diff;
+                r2->duplex_partner = g1;
+                r2->duplex_diff = diff;
+                r2->status = GCB_GROUP_DUPLEX_PARTNER;
+                if (diff <= o.duplex_mismatch_threshold) {
+                    if (r1->merge_reads + r2->merge_reads >= o.cluster_size_req) {
+                        r1->status = GCB_GROUP_DCS;
+                        r1->reverse_merge_reads = r2->merge_reads;  // Pair::setDuplex
+                    } else {
+                        r1->status = GCB_GROUP_DUPLEX_SMALL;
+                    }
+                } else {
+                    r1->status = GCB_GROUP_DUPLEX_DIFF;
+                }
+                for (int k = i; k + 1 < nalive; k++) alive[k] = alive[k + 1];
+            }
+            __syncwarp(pairmask);
             nalive--;
             break;
         }
-        if (!found) r1->status = (!o.duplex_only && r1->merge_reads >= o.cluster_size_req) ? GCB_GROUP_SSCS : GCB_GROUP_DROPPED;
+        if (!found && side == 0) r1->status = (!o.duplex_only && r1->merge_reads >= o.cluster_size_req) ? GCB_GROUP_SSCS : GCB_GROUP_DROPPED;
     }
 }
 
