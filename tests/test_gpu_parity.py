@@ -146,6 +146,19 @@ def test_pipeline_chunks_do_not_change_results(engine_cls, oracle, name, chunk):
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} chunk {chunk}")
 
 
+@pytest.mark.parametrize("write_combined", [False, True])
+def test_batches_in_gcb_host_alloc_memory(engine_cls, oracle, write_combined):
+    """The batch arrays in page-locked memory from gcb_host_alloc (plain and write-combined) give the same results."""
+    from gencore_b200.device import pinned_copy
+    batch, genome, opt = dict(CASES)["cfg2_40k"]()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        pb = pinned_copy(batch, lib=eng.lib, write_combined=write_combined)
+        res = eng.cluster_by_umi(pb)
+        del pb
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), "cfg2_40k in gcb_host_alloc memory")
+
+
 def test_capacity_error_is_reported(engine_cls):
     from gencore_b200.abi import GCB_ERR_CAPACITY
     from gencore_b200.engine import EngineError
