@@ -209,10 +209,10 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_pcount, 4 * GCB_MAX_CHUNKS);
     GCB_RES(w_thdr2, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * sizeof(TileHdr2));
     {   // slow-column queues: a clean shallow library queues about 0.05 bytes per payload byte, a deep noisy one (1 % errors
-        // at depth 50) about 1.3, a vote whose every column is slow (options outside fast_path_implied) about 4; tiles whose
+        // at depth 30-50) 1.6-1.9, a vote whose every column is slow (options outside fast_path_implied) about 4; tiles whose
         // columns do not fit are redone by the generic kernel
         int64_t qbytes = ctx->slow_queue_bytes > 0 ? ctx->slow_queue_bytes
-                         : fast_path_implied(ctx->opt) ? 3 * payload_bytes / 2 + (16ll << 20) : 5 * payload_bytes + (16ll << 20);
+                         : fast_path_implied(ctx->opt) ? 3 * payload_bytes + (16ll << 20) : 5 * payload_bytes + (16ll << 20);
         int64_t cap_words = qbytes / 4 / VQ_NQ;
         if (cap_words > 0x3FFFFFF0ll) cap_words = 0x3FFFFFF0ll;
         cap_words &= ~3ll;
