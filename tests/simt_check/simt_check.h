@@ -51,7 +51,8 @@ struct Fiber {
     bool done = true;
 };
 
-struct SubGroup {        // the lanes of one partial mask (keyed by the mask's lowest lane)
+struct SubGroup {        // the lanes of one partial mask (keyed by the mask itself: masks that share lanes may be in use at once)
+    unsigned mask = 0;
     uint64_t xchg[2][kWarp];
     int parity = 0;
     int arrived = 0;
@@ -64,7 +65,19 @@ struct WarpState {
     int arrived = 0;
     unsigned generation = 0;
     int live = 0;
-    SubGroup sub[kWarp];
+    std::vector<SubGroup> sub;
+    SubGroup &group(unsigned mask) {
+        for (SubGroup &g : sub)
+            if (g.mask == mask) return g;
+        sub.reserve(64);  // (references handed out earlier must stay valid)
+        if (sub.size() >= 64) {
+            fprintf(stderr, "simt_check: more than 64 distinct partial masks in one warp\n");
+            abort();
+        }
+        sub.emplace_back();
+        sub.back().mask = mask;
+        return sub.back();
+    }
 };
 
 struct State {
@@ -222,7 +235,7 @@ inline SubGroup &sub_barrier(unsigned mask) {
             }
             need++;
         }
-    SubGroup &g = w.sub[__builtin_ctz(mask)];
+    SubGroup &g = w.group(mask);
     unsigned gen = g.generation;
     g.arrived++;
     for (;;) {
@@ -242,7 +255,7 @@ inline const uint64_t *exchange(uint64_t v, unsigned mask = 0xffffffffu) {
     State &s = st();
     WarpState &w = s.warps[s.cur / kWarp];
     if (mask != 0xffffffffu) {
-        SubGroup &g0 = w.sub[__builtin_ctz(mask)];
+        SubGroup &g0 = w.group(mask);
         int p = g0.parity;
         g0.xchg[p][s.cur % kWarp] = v;
         SubGroup &g = sub_barrier(mask);
