@@ -400,13 +400,8 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         }
     }
     if (stages & GCB_STAGE_DUPLEX) {
-        // duplex UMIs (two parts and an underscore) need more than one UMI word: sixteen lanes per cluster then, else two
-        if (batch.umi_words >= 2)
-            GCB_LAUNCH(duplex_kernel<16>, dim3((unsigned)((16 * (int64_t)nc + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream, b,
-                       r, ws, ctx->opt);
-        else
-            GCB_LAUNCH(duplex_kernel<2>, dim3((unsigned)((2 * (int64_t)nc + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream, b, r,
-                       ws, ctx->opt);
+        GCB_LAUNCH(duplex_kernel, dim3((unsigned)((2 * (int64_t)nc + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream, b, r, ws,
+                   ctx->opt);
         ctx->launches++;
     }
     GCB_CUDA(ctx, cudaGetLastError());
