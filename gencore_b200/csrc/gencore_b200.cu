@@ -344,7 +344,8 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
                 GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
                 int32_t *max_need = (int32_t *)ctx->w_pcount.p + v.index;  // (the pipelined mode's tile counter is free in this mode)
                 GCB_CUDA(ctx, cudaMemsetAsync(max_need, 0, 4, stream));
-                GCB_LAUNCH(tile_prep2_kernel, dim3((unsigned)n_tiles), dim3(VS_PREP_THREADS), 0, stream, b, r, ws, plan.slab_cap, thdr, fst, max_need);
+                GCB_LAUNCH(tile_prep2_kernel, dim3((unsigned)((n_tiles + VS_PREP_THREADS / WARP - 1) / (VS_PREP_THREADS / WARP))), dim3(VS_PREP_THREADS), 0,
+                           stream, b, r, ws, plan.slab_cap, thdr, fst, max_need, (int32_t)n_tiles);
                 ctx->launches++;
             }
             if ((run_fast || run_rest) && plan.split) {

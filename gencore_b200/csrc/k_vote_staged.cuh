@@ -25,9 +25,7 @@ constexpr int VS_MAX_THREADS = 256;
 constexpr int VS_MAX_PAIRS = 256;   // pair positions of a tile
 constexpr int VS_MAX_FS = 192;      // family sides of a tile
 constexpr int VS_SLOW_CAP = 384;    // queued slow columns; more are decided inline by their owner
-constexpr int VS_PREP_THREADS = 128;
-constexpr int VS_PREP_ROUNDS = 2;
-static_assert(VS_PREP_THREADS * VS_PREP_ROUNDS >= VS_MAX_PAIRS, "tile_prep2_kernel gives one thread and round to every pair position");
+constexpr int VS_PREP_THREADS = 128;  // tile_prep2_kernel: four tiles per CTA, one warp each
 
 struct __align__(16) TileHdr2 {
     int64_t out_base0;   // first output byte of the tile
@@ -54,15 +52,15 @@ constexpr int VS_OFF_SLAB = (VS_OFF_VR + 32 * VS_MAX_PAIRS + 127) & ~127;
 static_assert(VS_OFF_FT % 16 == 0 && VS_OFF_VR % 16 == 0, "16-byte aligned tables");
 
 // ------------------------------------------------------------------------------------------------
-// One CTA per tile, one thread per pair position (VS_PREP_ROUNDS rounds of VS_PREP_THREADS positions): what the tiled
-// kernel's prologue computes, once per batch.  The CTA is small so that many tiles' chains of dependent loads
-// (directory -> side modes -> family-side descriptors -> cluster offsets) are in flight on an SM at once.
-__global__ void __launch_bounds__(VS_PREP_THREADS, 10) tile_prep2_kernel(BatchView b, ResultView r, Workspace ws, int32_t slab_cap, TileHdr2 *hdr,
-                                                                          FsTile *fs_tiles, int32_t *max_need) {
-    __shared__ uint32_t s_wsum[VS_PREP_ROUNDS][VS_PREP_THREADS / WARP];
-    __shared__ int s_nofit, s_lmax, s_common;
-    const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    const TileDir t0 = ws.tile_dir[blockIdx.x], t1 = ws.tile_dir[blockIdx.x + 1];
+// One WARP per tile, 32 pair positions per pass: what the tiled kernel's prologue computes, once per batch.  The live family
+// sides are compacted with ballots (no shared memory, no CTA barrier); many tiles per SM keep their chains of dependent loads
+// (directory -> side modes -> family-side descriptors -> cluster offsets) in flight at once.
+__global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b, ResultView r, Workspace ws, int32_t slab_cap, TileHdr2 *hdr,
+                                                                      FsTile *fs_tiles, int32_t *max_need, int32_t n_tiles) {
+    const int lane = lane_id();
+    const int tile = (int)(blockIdx.x * (VS_PREP_THREADS / WARP) + (threadIdx.x >> 5));
+    if (tile >= n_tiles) return;
+    const TileDir t0 = ws.tile_dir[tile], t1 = ws.tile_dir[tile + 1];
     const int c0 = t0.c0, c1 = t1.c0;
     const int P0 = t0.p0, NP = t1.p0 - t0.p0;
     const int64_t slab_bytes = t1.slab0 - t0.slab0;
@@ -70,91 +68,46 @@ __global__ void __launch_bounds__(VS_PREP_THREADS, 10) tile_prep2_kernel(BatchVi
     h.out_base0 = 0; h.slab0 = t0.slab0; h.slab_bytes = 0; h.p0 = P0; h.np = NP; h.nfs = 0; h.lanes = 1; h.common_l = 0;
     h.per_bundle = 32; h.n_bundles = 0;
     if (c0 >= c1 || NP == 0) {  // no cluster starts here / clusters without pairs emit nothing
-        if (tid == 0) hdr[blockIdx.x] = h;
+        if (lane == 0) hdr[tile] = h;
         return;
     }
-    if (NP > VS_MAX_PAIRS || c1 - c0 > VS_MAX_PAIRS || slab_bytes > slab_cap) {  // not a tile for the staged kernel
-        if (tid == 0) {
-            hdr[blockIdx.x] = h;
-            ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = (int32_t)blockIdx.x;
+    if (NP > VS_MAX_PAIRS || slab_bytes > slab_cap) {  // not a tile for the staged kernels
+        if (lane == 0) {
+            hdr[tile] = h;
+            ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = (int32_t)tile;
             GCB_COUNT(1, 1);
         }
         return;
     }
-    if (tid == 0) {
-        s_nofit = 0;
-        s_lmax = 1;
-        s_common = 0;
-    }
-    // the tile's clusters (at most one per pair position): slab offset inside the tile and absolute output offset, fetched
-    // together with the side modes so that the family-side descriptors are the last level of dependent loads
-    __shared__ int32_t s_cslab[VS_MAX_PAIRS];
-    __shared__ int64_t s_cout[VS_MAX_PAIRS];
-    for (int k = tid; k < c1 - c0; k += VS_PREP_THREADS) {
-        const int c = c0 + k;
-        s_cslab[k] = (int32_t)(ws.slab_off[c] - t0.slab0);
-        s_cout[k] = ws.scan_block[c / SCAN_BLOCK] + ws.cluster_out_off[c];
-    }
-    FsDesc fd[VS_PREP_ROUNDS][2];
-    int64_t c_slab[VS_PREP_ROUNDS], c_out[VS_PREP_ROUNDS];
-    uint32_t incl[VS_PREP_ROUNDS], mine[VS_PREP_ROUNDS];
-#pragma unroll
-    for (int rd = 0; rd < VS_PREP_ROUNDS; rd++) {
-        const int pos = rd * VS_PREP_THREADS + tid;
-        fd[rd][0].mode = fd[rd][1].mode = SIDE_NONE;
-        fd[rd][0].c = fd[rd][1].c = c0;
-        if (rd > 0 && NP <= rd * VS_PREP_THREADS) {  // (the usual tile needs one round)
-            c_slab[rd] = c_out[rd] = 0;
-            mine[rd] = incl[rd] = 0u;
-            if (lane == WARP - 1) s_wsum[rd][warp] = 0u;
-            continue;
-        }
+    const int64_t out_base0 = ws.scan_block[c0 / SCAN_BLOCK] + ws.cluster_out_off[c0];
+    FsTile *ft_out = fs_tiles + 2 * (int64_t)P0;
+    uint32_t total = 0;
+    bool nofit = false;
+    int lmax = 1, common = 0;
+    for (int base = 0; base < NP; base += WARP) {
+        const int pos = base + lane;
+        FsDesc fd[2];
+        fd[0].mode = fd[1].mode = SIDE_NONE;
+        fd[0].c = fd[1].c = c0;
         if (pos < NP) {  // slots that hold no family carry SIDE_NONE in side_mode and garbage in fs_desc
             const uint16_t modes = *(const uint16_t *)(ws.side_mode + 2 * (int64_t)(P0 + pos));
-            if ((modes & 0xFF) != SIDE_NONE) fd[rd][0] = ws.fs_desc[2 * (int64_t)(P0 + pos)];
-            if ((modes >> 8) != SIDE_NONE) fd[rd][1] = ws.fs_desc[2 * (int64_t)(P0 + pos) + 1];
+            if ((modes & 0xFF) != SIDE_NONE) fd[0] = ws.fs_desc[2 * (int64_t)(P0 + pos)];
+            if ((modes >> 8) != SIDE_NONE) fd[1] = ws.fs_desc[2 * (int64_t)(P0 + pos) + 1];
         }
-        const bool live0 = fd[rd][0].mode != SIDE_NONE, live1 = fd[rd][1].mode != SIDE_NONE;
-        c_slab[rd] = c_out[rd] = 0;
-        mine[rd] = (live0 ? 1u : 0u) + (live1 ? 1u : 0u);
-        uint32_t in = mine[rd];
-        for (int off = 1; off < WARP; off <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, in, off);
-            if (lane >= off) in += v;
+        const bool live0 = fd[0].mode != SIDE_NONE, live1 = fd[1].mode != SIDE_NONE;
+        int64_t c_slab = 0, c_out = 0;
+        if (live0 || live1) {
+            const int c = live0 ? fd[0].c : fd[1].c;
+            c_slab = ws.slab_off[c] - t0.slab0;
+            c_out = ws.scan_block[c / SCAN_BLOCK] + ws.cluster_out_off[c] - out_base0;
         }
-        incl[rd] = in;
-        if (lane == WARP - 1) s_wsum[rd][warp] = in;
-    }
-    __syncthreads();
-    const int64_t out_base0 = s_cout[0];
-#pragma unroll
-    for (int rd = 0; rd < VS_PREP_ROUNDS; rd++)
-        if (mine[rd] != 0) {  // (a cluster of the tile starts inside it: at most as many clusters as pair positions)
-            const int k = (fd[rd][0].mode != SIDE_NONE ? fd[rd][0].c : fd[rd][1].c) - c0;
-            c_slab[rd] = s_cslab[k];
-            c_out[rd] = s_cout[k] - out_base0;
-        }
-    uint32_t total = 0, pre[VS_PREP_ROUNDS];
-#pragma unroll
-    for (int rd = 0; rd < VS_PREP_ROUNDS; rd++) {
-        pre[rd] = total + incl[rd] - mine[rd];
-        for (int w = 0; w < VS_PREP_THREADS / WARP; w++) {
-            if (w < warp) pre[rd] += s_wsum[rd][w];
-            total += s_wsum[rd][w];
-        }
-    }
-    if (tid == 0 && total > (uint32_t)VS_MAX_FS) s_nofit = 1;
-    FsTile *ft_out = fs_tiles + 2 * (int64_t)P0;
-    int64_t abs_off[VS_PREP_ROUNDS][2];
-#pragma unroll
-    for (int rd = 0; rd < VS_PREP_ROUNDS; rd++) {
-        abs_off[rd][0] = abs_off[rd][1] = -1;
-        if (mine[rd] == 0) continue;
-        const int pos = rd * VS_PREP_THREADS + tid;
-        int lneed = 1, fidx = (int)pre[rd];
+        const unsigned b0m = __ballot_sync(FULL, live0), b1m = __ballot_sync(FULL, live1), lt = (1u << lane) - 1u;
+        int fidx = (int)total + __popc(b0m & lt) + __popc(b1m & lt);
+        int lneed = 1;
+        bool bad = false;
         for (int side = 0; side < 2; side++) {
-            if (fd[rd][side].mode == SIDE_NONE) continue;
-            const FsDesc d = fd[rd][side];
+            if (fd[side].mode == SIDE_NONE) continue;
+            const FsDesc d = fd[side];
             FsTile ft;
             ft.ent0 = (uint16_t)(2 * (d.mb - P0) + side * (int)d.m);
             ft.m = d.m;
@@ -163,55 +116,52 @@ __global__ void __launch_bounds__(VS_PREP_THREADS, 10) tile_prep2_kernel(BatchVi
             ft.tmpl_k = d.tmpl_k;
             ft.mode = d.mode;
             ft.flags = (uint8_t)(d.flags | (side ? FS_SIDE1 : 0));
-            ft.cbase4 = (uint16_t)(c_slab[rd] >> 2);
-            const int64_t orel = c_out[rd] + d.out_rel;
+            ft.cbase4 = (uint16_t)(c_slab >> 2);
+            const int64_t orel = c_out + d.out_rel;
             ft.out4 = (uint16_t)(orel >> 2);
             ft.ref_nib0 = d.ref_nib0;
             ft.slot = P0 + pos;
             ft.reserved = 0;
             const int l = d.l_out;
             const int chunks = max((GCB_ALIGN4(l) + 15) >> 4, (GCB_ALIGN4((l + 1) >> 1) + 7) >> 3);
-            if ((d.flags & FS_NOFIT) || (orel >> 2) > 0xFFFF || chunks > WARP) s_nofit = 1;
+            if ((d.flags & FS_NOFIT) || (orel >> 2) > 0xFFFF || chunks > WARP) bad = true;
             if (out_base0 + orel + record_bytes(l) > r.out_capacity) {
                 raise_error(ws.error_flag, GCB_ERR_CAPACITY);
                 ft.mode = SIDE_NONE;  // keeps its place in the table but is never voted
             } else {
-                abs_off[rd][side] = out_base0 + orel;
+                // the absolute offset the caller reads (a tile that ends up with the generic kernel is listed as ~tile:
+                // "offsets already absolute")
+                r.groups[P0 + pos].out_off[side] = out_base0 + orel;
             }
             lneed = max(lneed, min(chunks, WARP));
             if (fidx < VS_MAX_FS) ft_out[fidx] = ft;
-            if (fidx == 0) s_common = l;
+            if (fidx == 0) common = l;
             fidx++;
         }
-        if (lneed > 1) atomicMax(&s_lmax, lneed);
+        total += (uint32_t)(__popc(b0m) + __popc(b1m));
+        nofit = nofit || __any_sync(FULL, bad);
+        lmax = max(lmax, __reduce_max_sync(FULL, lneed));
+        common = __reduce_max_sync(FULL, common);  // (only the lane that wrote entry 0 holds a non-zero value)
     }
-    __syncthreads();
-    if (!s_nofit) {  // the absolute offsets the caller reads (the generic kernel rebases the relative ones itself)
-#pragma unroll
-        for (int rd = 0; rd < VS_PREP_ROUNDS; rd++) {
-            const int pos = rd * VS_PREP_THREADS + tid;
-            if (abs_off[rd][0] >= 0) r.groups[P0 + pos].out_off[0] = abs_off[rd][0];
-            if (abs_off[rd][1] >= 0) r.groups[P0 + pos].out_off[1] = abs_off[rd][1];
-        }
-    }
-    if (tid == 0) {
-        if (s_nofit) {  // the generic kernel takes the tile
-            ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = (int32_t)blockIdx.x;
+    if (total > (uint32_t)VS_MAX_FS) nofit = true;
+    if (lane == 0) {
+        if (nofit) {  // the generic kernel takes the tile
+            ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~(int32_t)tile;
             GCB_COUNT(1, 1);
         } else if (total > 0) {
             h.out_base0 = out_base0;
             h.slab_bytes = (int32_t)slab_bytes;
             h.nfs = (int32_t)total;
-            h.lanes = s_lmax;
-            h.common_l = s_common;
-            h.per_bundle = 32 / s_lmax;
+            h.lanes = lmax;
+            h.common_l = common;
+            h.per_bundle = 32 / lmax;
             h.n_bundles = ((int32_t)total + h.per_bundle - 1) / h.per_bundle;
             // shared memory the tile takes in the ring kernel: family-side list, VoteRead table, slab + slack, each rounded to 128
             atomicMax(max_need, (int32_t)(((32 * (int32_t)total + 127) & ~127) + ((32 * NP + 127) & ~127) +
                                           (((int32_t)slab_bytes + VT_SLAB_SLACK + 127) & ~127)));
             GCB_COUNT(0, 1);
         }
-        hdr[blockIdx.x] = h;
+        hdr[tile] = h;
     }
 }
 
