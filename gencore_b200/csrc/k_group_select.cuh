@@ -171,12 +171,12 @@ struct SideChoice {
     bool uniform;  // every voter shares the template's geometry (FS_UNIFORM)
 };
 
-// The VoteRead of a read (see device_common.cuh) from its descriptor `rd`, its mate's `md` and the pair's overlap window;
-// `fits` is cleared when a field overflows.
-GCB_DEV VoteRead make_vote_read_from(const gcb_read_desc &rd, const gcb_read_desc &md, const PairOverlap &ov, int64_t slab0, int side, uint8_t f,
-                                     int l_out, bool left_mode, bool &fits) {
+// The VoteRead of read slot sk (see device_common.cuh); `fits` is cleared when a field overflows.
+GCB_DEV VoteRead make_vote_read(const BatchView &b, const Workspace &ws, int64_t slab0, int sk, int side, uint8_t f, int l_out, bool left_mode,
+                                bool &fits) {
     VoteRead v = {VR_NO_VOTE, 0, 0, 0, 0, 0, 0, 0};
     if (!(f & VOTE_PARTICIPATES)) return v;
+    const gcb_read_desc rd = b.reads[sk];
     const int64_t off = rd.data_off - slab0;
     const int d = (f & VOTE_LENDIFF0) ? 0 : rd.l_qseq - l_out;  // group.cpp:339-349
     const int shift = left_mode ? 0 : d;
@@ -188,7 +188,9 @@ GCB_DEV VoteRead make_vote_read_from(const gcb_read_desc &rd, const gcb_read_des
     v.own_l = (int16_t)rd.l_qseq;
     v.shift = (int16_t)shift;
     v.ov_len = VR_NO_OVERLAP_INFO;
+    const PairOverlap ov = ws.overlap[sk >> 1];
     if (ov.valid) {
+        const gcb_read_desc md = b.reads[sk ^ 1];
         const int64_t moff = md.data_off - slab0;
         // (32-bit sums of 32-bit CIGAR offsets and lengths: saturate instead of wrapping on absurd input)
         const int64_t own64 = side == 0 ? ov.left_start : ov.right_start, mate64 = side == 0 ? ov.right_start : ov.left_start;
@@ -216,97 +218,6 @@ GCB_DEV VoteRead make_vote_read_from(const gcb_read_desc &rd, const gcb_read_des
         v.ov_len = (int16_t)len;
     }
     return v;
-}
-
-// The VoteRead of read slot sk; loads what make_vote_read_from needs.
-GCB_DEV VoteRead make_vote_read(const BatchView &b, const Workspace &ws, int64_t slab0, int sk, int side, uint8_t f, int l_out, bool left_mode,
-                                bool &fits) {
-    if (!(f & VOTE_PARTICIPATES)) {
-        const VoteRead v = {VR_NO_VOTE, 0, 0, 0, 0, 0, 0, 0};
-        return v;
-    }
-    const gcb_read_desc rd = b.reads[sk];
-    const PairOverlap ov = ws.overlap[sk >> 1];
-    gcb_read_desc md = rd;
-    if (ov.valid) md = b.reads[sk ^ 1];
-    return make_vote_read_from(rd, md, ov, slab0, side, f, l_out, left_mode, fits);
-}
-
-// FS_UNIFORM between a voter's entry and the template's (see side_select)
-GCB_DEV bool vote_read_like_template(const VoteRead &v, const VoteRead &tv) {
-    return v.own_l == tv.own_l && v.shift == 0 && v.ov_len == tv.ov_len &&
-           (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l &&
-                              (uint16_t)(v.mate_off4 - v.own_off4) == (uint16_t)(tv.mate_off4 - tv.own_off4)));
-}
-
-// The usual family, BOTH sides in one pass: every pair has both reads, and on each side one identical CIGAR op, one length,
-// one position (side_select's shortcut).  Then on each side the template is the first read in map order, every read
-// votes, columns are left-aligned.  Each pair's two descriptors are loaded once and serve both sides, so the chain of
-// dependent loads is walked once instead of twice.  Returns false (nothing written) when the family is not of that kind.
-template <int GS>
-GCB_DEV bool sides_select_same(const Grp<GS> &g, const BatchView &b, const Workspace &ws, const gcb_options &o, int mb, int m, int slot, int64_t slab0,
-                               SideChoice ch[2]) {
-    if (m > o.skip_low_complexity_cluster_threshold || m > GS) return false;  // (larger families: one side at a time)
-    const int lane = g.gl;
-    gcb_read_desc d[2];
-    uint32_t cw[2] = {0u, 0u};
-    int pair = 0;
-    bool ok = true;
-    if (lane < m) {
-        pair = ws.members[mb + lane];
-        d[0] = b.reads[2 * (int64_t)pair];
-        d[1] = b.reads[2 * (int64_t)pair + 1];
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            ok = ok && d[s].l_qseq >= 0 && d[s].n_cigar == 1;
-            if (ok) cw[s] = b.cigar[d[s].cigar_off];
-        }
-    } else {
-        d[0].l_qseq = d[1].l_qseq = -1;
-        d[0].pos = d[1].pos = 0;
-        d[0].n_cigar = d[1].n_cigar = 0;
-        d[0].data_off = d[1].data_off = 0;
-        d[0].cigar_off = d[1].cigar_off = 0;
-        d[0].l_qname = d[1].l_qname = 0;
-        d[0].isize = d[1].isize = 0;
-    }
-    // everybody like the first pair
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-        const int l0 = __shfl_sync(g.mask, d[s].l_qseq, g.base), p0 = __shfl_sync(g.mask, d[s].pos, g.base);
-        const uint32_t c0 = __shfl_sync(g.mask, cw[s], g.base);
-        if (lane < m) ok = ok && d[s].l_qseq == l0 && d[s].pos == p0 && cw[s] == c0;
-    }
-    if (!g.all(ok)) return false;
-    const PairOverlap ov = lane < m ? ws.overlap[pair] : PairOverlap{0, 0, 0, 0};
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-        bool fits = true;
-        const int l_out = __shfl_sync(g.mask, d[s].l_qseq, g.base);
-        VoteRead v = {VR_NO_VOTE, 0, 0, 0, 0, 0, 0, 0};
-        if (lane < m) {
-            v = make_vote_read_from(d[s], d[1 - s], ov, slab0, s, VOTE_PARTICIPATES, l_out, true, fits);
-            ws.vote_flags[2 * (int64_t)pair + s] = VOTE_PARTICIPATES;
-            ws.vote_reads[2 * (int64_t)mb + (int64_t)s * m + lane] = v;
-        }
-        if (lane == 0) ws.side_mode[2 * (int64_t)slot + s] = SIDE_LEFT;
-        VoteRead tv;
-        {
-            uint32_t w[4];
-            memcpy(w, &v, 16);
-#pragma unroll
-            for (int q = 0; q < 4; q++) w[q] = __shfl_sync(g.mask, w[q], g.base);
-            memcpy(&tv, w, 16);
-        }
-        bool uni = tv.shift == 0 && tv.own_l == l_out;
-        if (lane < m && v.own_off4 != VR_NO_VOTE) uni = uni && vote_read_like_template(v, tv);
-        ch[s].out = 2 * __shfl_sync(g.mask, pair, g.base) + s;
-        ch[s].k = 0;
-        ch[s].len = l_out;  // (one CIGAR op: group.cpp:354-360 keeps the template's length)
-        ch[s].fits = g.all(fits);
-        ch[s].uniform = g.all(uni);
-    }
-    return true;
 }
 
 template <int GS>
@@ -482,7 +393,9 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
         const VoteRead v = mine_v;
         uni = ch.len == od.l_qseq && tv.shift == 0 && tv.own_l == od.l_qseq;
         if (lane < m && v.own_off4 != VR_NO_VOTE)
-            uni = uni && vote_read_like_template(v, tv);
+            uni = uni && v.own_l == tv.own_l && v.shift == 0 && v.ov_len == tv.ov_len &&
+                  (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l &&
+                                     (uint16_t)(v.mate_off4 - v.own_off4) == (uint16_t)(tv.mate_off4 - tv.own_off4)));
     } else {
         g.sync();
         const VoteRead tv = vr[best_k];
@@ -490,7 +403,9 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
         for (int k = lane; k < m; k += GS) {
             const VoteRead v = vr[k];
             if (v.own_off4 == VR_NO_VOTE) continue;
-            uni = uni && vote_read_like_template(v, tv);
+            uni = uni && v.own_l == tv.own_l && v.shift == 0 && v.ov_len == tv.ov_len &&
+                  (v.ov_len <= 0 || (v.ov_own == tv.ov_own && v.ov_mate == tv.ov_mate && v.mate_l == tv.mate_l &&
+                                     (uint16_t)(v.mate_off4 - v.own_off4) == (uint16_t)(tv.mate_off4 - tv.own_off4)));
         }
     }
     ch.uniform = g.all(uni);
@@ -609,10 +524,8 @@ __global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(Batc
                 ws.side_mode[2 * (int64_t)slot + 1] = SIDE_NONE;
             }
             g.sync();
-            if (!sides_select_same<GS>(g, b, ws, o, mb, m, slot, slab0, ch)) {
-                ch[0] = side_select<GS>(g, b, ws, o, mb, m, 0, slot, slab0);
-                ch[1] = side_select<GS>(g, b, ws, o, mb, m, 1, slot, slab0);
-            }
+            ch[0] = side_select<GS>(g, b, ws, o, mb, m, 0, slot, slab0);
+            ch[1] = side_select<GS>(g, b, ws, o, mb, m, 1, slot, slab0);
             const int left = ch[0].out, right = ch[1].out;
             gr.tmpl_read[0] = left;
             gr.tmpl_read[1] = right;
