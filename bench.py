@@ -182,8 +182,8 @@ def b200_arm(args):
     import torch
     import torch.distributed as dist
     from gencore_b200 import synth
-    from gencore_b200.abi import (STAGE_DUPLEX, STAGE_SCORE_VOTE, STAGE_SELECT_TEMPLATE, STAGE_UMI_GROUP, STAGE_VOTE_FAST_ONLY, STAGE_VOTE_ONLY,
-                                  STAGE_VOTE_PREP_ONLY, STAGE_VOTE_REST_ONLY, Genome, Options)
+    from gencore_b200.abi import (STAGE_DUPLEX, STAGE_SELECT_TEMPLATE, STAGE_UMI_GROUP, STAGE_VOTE_FAST_ONLY, STAGE_VOTE_PREP_ONLY,
+                                  STAGE_VOTE_REST_ONLY, Options)
     from gencore_b200.device import DeviceBatch, DeviceResult, pinned_copy, pinned_result
     from gencore_b200.engine import ConsensusEngine
 
@@ -208,12 +208,12 @@ def b200_arm(args):
     # every rank builds the same genome (same seed) and its own coordinate window of read pairs
     grng = np.random.Generator(np.random.PCG64(SEED))
     contigs, genome = synth.random_genome(grng, [cfg.contig_len] * cfg.n_contigs)
-    batch, _, _ = synth.make_fixed_batch(cfg, seed=SEED + 104729 * rank, n_pairs=args.pairs, with_qnames=False, genome_cache=(contigs, genome))
+    batch, _, _ = synth.make_batch(cfg, seed=SEED + 104729 * rank, n_pairs=args.pairs, with_qnames=False, genome_cache=(contigs, genome))
     del contigs
     opt = Options.default()
     eng = ConsensusEngine(opt, local)
-    eng.set_vote_mode(args.vote_mode)
-    eng.set_vote_threads(args.vote_threads)
+    if args.window_shift:
+        eng.set_debug(2, args.window_shift)
     if args.group_lanes:
         eng.set_debug(3, args.group_lanes)
     # the packed reference reaches every GPU by ONE NCCL broadcast from rank 0
@@ -229,20 +229,12 @@ def b200_arm(args):
     stream = tstream.cuda_stream
     assert stream != 0
     torch.cuda.synchronize()
-    # vote modes 1-4 prepare per-tile headers once per batch (tile_prep kernels), modes 3 and 4 decide the slow columns in a
-    # second kernel: each part is timed as its own stage
-    if args.vote_mode == 0:
-        stages = [STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_SCORE_VOTE, STAGE_DUPLEX]
-        names = ["umi_group", "select_template+scan", "score_vote", "duplex"]
-    elif args.vote_mode in (1, 2):
-        stages = [STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_VOTE_PREP_ONLY, STAGE_VOTE_ONLY, STAGE_DUPLEX]
-        names = ["umi_group", "select_template+scan", "tile_prep", "score_vote", "duplex"]
-    else:
-        stages = [STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_VOTE_PREP_ONLY, STAGE_VOTE_FAST_ONLY, STAGE_VOTE_REST_ONLY, STAGE_DUPLEX]
-        names = ["umi_group", "select_template+scan", "tile_prep", "score_vote", "slow_columns+rollback", "duplex"]
+    # the vote is timed in its three parts: per-tile preparation, the ring kernel, rollback + the generic kernel's tiles
+    stages = [STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_VOTE_PREP_ONLY, STAGE_VOTE_FAST_ONLY, STAGE_VOTE_REST_ONLY, STAGE_DUPLEX]
+    names = ["umi_group", "select_template+scan", "tile_prep", "score_vote", "rollback+generic", "duplex"]
     i_vote = names.index("score_vote")
-    vote_kernel = {0: "vote_tiled_kernel", 1: "vote_pipe_kernel", 2: "vote_staged_kernel", 3: "vote_fast_kernel", 4: "vote_ring_kernel"}[args.vote_mode]
-    vote_parts = [k for k, n in enumerate(names) if n in ("tile_prep", "score_vote", "slow_columns+rollback")]
+    vote_kernel = "vote_ring_kernel"
+    vote_parts = [k for k, n in enumerate(names) if n in ("tile_prep", "score_vote", "rollback+generic")]
     def step(events=None):
         for k, st in enumerate(stages):
             if events is not None:
@@ -255,43 +247,6 @@ def b200_arm(args):
         step()
     barrier()
     assert eng.batch_status() == 0, "device error flag raised during warm-up"
-    if args.sweep and rank == 0:  # tuning aid: stage times of other (vote mode, threads) settings, to stderr
-        for item in args.sweep.split(","):
-            parts = item.split(":")  # mode:threads[:ablate[:window_shift[:units per lane]]]
-            mode_s, thr_s = parts[0], parts[1]
-            eng.set_vote_mode(int(mode_s))
-            eng.set_vote_threads(int(thr_s))
-            eng.set_debug(1, int(parts[2]) if len(parts) > 2 else 0)
-            eng.set_debug(2, int(parts[3]) if len(parts) > 3 else 0)
-            eng.set_debug(4, int(parts[4]) if len(parts) > 4 else 1)
-            if len(parts) > 3 and int(parts[3]):  # the tile directory depends on the window: rebuild it
-                eng.cluster_by_umi_device(db.struct, dr.struct, STAGE_UMI_GROUP, stream)
-                eng.cluster_by_umi_device(db.struct, dr.struct, STAGE_SELECT_TEMPLATE, stream)
-            sw_stages = [STAGE_SCORE_VOTE] if int(mode_s) == 0 else [STAGE_VOTE_PREP_ONLY, STAGE_VOTE_ONLY] if int(mode_s) < 3 else \
-                [STAGE_VOTE_PREP_ONLY, STAGE_VOTE_FAST_ONLY, STAGE_VOTE_REST_ONLY]
-            for _ in range(3):
-                for st in sw_stages:
-                    eng.cluster_by_umi_device(db.struct, dr.struct, st, stream)
-            n_sw = 20
-            ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(sw_stages) + 1)] for _ in range(n_sw)]
-            for k in range(n_sw):
-                for q, st in enumerate(sw_stages):
-                    ev[k][q].record(tstream)
-                    eng.cluster_by_umi_device(db.struct, dr.struct, st, stream)
-                ev[k][len(sw_stages)].record(tstream)
-            torch.cuda.synchronize()
-            ms = [float(np.mean([ev[k][q].elapsed_time(ev[k][q + 1]) for k in range(n_sw)])) for q in range(len(sw_stages))]
-            sys.stderr.write("sweep %s stage_ms=%s\n" % (item, ["%.4f" % x for x in ms]))
-        eng.set_vote_mode(args.vote_mode)
-        eng.set_vote_threads(args.vote_threads)
-        eng.set_debug(1, 0)
-        eng.set_debug(2, 0)
-        eng.set_debug(4, 1)
-        if args.sweep_only:
-            eng.close()
-            return
-        step()
-        barrier()
     res_host = dr.to_host()
     alg = algorithmic_bytes(batch, res_host)
 
@@ -375,12 +330,9 @@ def b200_arm(args):
         peak, peak_src = peaks()
         vote_ms = float(stage_ms[i_vote])
         whole_ms = float(sum(stage_ms[k] for k in vote_parts))
-        # the dominant kernel reads every read's bases and qualities and writes every consensus record; in vote modes 3 and 4
-        # the reference bases are read by slow_columns_kernel (reported with the whole vote)
+        # the dominant kernel reads every read's bases and qualities, the reference bases of its slow columns, and writes every
+        # consensus record: the whole of SURVEY 8(d)'s algorithmic bytes
         own = dict(alg)
-        if args.vote_mode >= 3:
-            own["reference_in"] = 0
-            own["total"] = own["reads_in"] + own["consensus_out"]
         achieved = own["total"] / (vote_ms * 1e-3) / 1e9
         whole = alg["total"] / (whole_ms * 1e-3) / 1e9
         line = {
@@ -423,17 +375,12 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=400_000, help="cpu_baseline sample size (one core)")
     ap.add_argument("--cpu-reps", type=int, default=10, help="cpu_baseline repetitions of the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--vote-mode", type=int, default=4, choices=[0, 1, 2, 3, 4],
-                    help="0 = one CTA per tile with its own prologue, 1 = persistent pipelined, 2 = staged, 3 = split fast/slow, "
-                         "4 = split with the fast kernel as a persistent ring (default)")
-    ap.add_argument("--vote-threads", type=int, default=256, help="threads per CTA of the staged vote kernel")
-    ap.add_argument("--sweep-only", action="store_true", help="stop after --sweep")
+    ap.add_argument("--window-shift", type=int, default=0, help="tuning aid: log2 of the vote's tile window (14 or 15; 0 = automatic)")
     ap.add_argument("--group-lanes", type=int, default=0, help="tuning aid: lanes per cluster in umi_group / select_template (8, 16, 32; 0 = automatic)")
     ap.add_argument("--host-sweep", action="store_true", help="tuning aid: end-to-end times by kind of host memory, to stderr")
     ap.add_argument("--chunk-sweep", default="", help="tuning aid: comma-separated pipeline chunk sizes in MB whose end-to-end times go to stderr")
-    ap.add_argument("--sweep", default="", help="tuning aid: comma-separated mode:threads settings whose vote stage times go to stderr")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per vote launch from an ncu capture (profiles/)")
-    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4"],
+    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="exploration only: another fixed-length shape of BASELINE.json (the contract's line is cfg2, the default)")
     args = ap.parse_args()
     global CFG_NAME, WORKLOAD

@@ -12,7 +12,7 @@ from typing import List, Optional
 
 import numpy as np
 
-GCB_ABI_VERSION = 1
+GCB_ABI_VERSION = 2
 GCB_MAX_UMI_WORDS = 4
 
 GCB_OK, GCB_ERR_ARG, GCB_ERR_CUDA, GCB_ERR_NO_DEVICE, GCB_ERR_CAPACITY, GCB_ERR_MALFORMED = 0, -1, -2, -3, -4, -5
@@ -24,7 +24,7 @@ GROUP_DROPPED, GROUP_SSCS, GROUP_DCS, GROUP_DUPLEX_PARTNER, GROUP_DUPLEX_DIFF, G
 
 STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_SCORE_VOTE, STAGE_DUPLEX, STAGE_ALL = 1, 2, 4, 8, 15
 STAGE_VOTE_PREP_ONLY, STAGE_VOTE_ONLY = 16, 32  # measurement only: the two halves of STAGE_SCORE_VOTE
-STAGE_VOTE_FAST_ONLY, STAGE_VOTE_REST_ONLY = 64, 128  # vote modes 3 and 4: the two halves of STAGE_VOTE_ONLY
+STAGE_VOTE_FAST_ONLY, STAGE_VOTE_REST_ONLY = 64, 128  # the two halves of STAGE_VOTE_ONLY: ring kernel; rollback + generic
 
 
 def align4(x):

@@ -1,8 +1,8 @@
 // gencore_b200.cu — the C ABI of libgencore_b200.so (include/gencore_b200.h) and the launch sequence
 // of one batch.  Host code only sizes buffers, moves bytes and launches; all arithmetic of the
 // reference's hot path lives in the kernels:
-//   umi_group_kernel -> select_template_kernel -> scan_local/scan_blocks -> vote_tiled_kernel
-//   (-> score_vote_kernel for the tiles that do not fit the tiled kernel's tables) -> duplex_kernel
+//   umi_group_kernel -> select_template_kernel -> scan_local/scan_blocks -> tile_prep2_kernel -> vote_ring_kernel
+//   -> vote_rollback_kernel -> score_vote_kernel (the tiles that do not fit a ring stage) -> duplex_kernel
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -13,16 +13,11 @@
 #include "k_group_select.cuh"
 #include "k_score_vote.cuh"
 #include "k_umi_extract.cuh"
-#include "k_vote_tiled.cuh"
-#include "k_vote_pipe.cuh"
-#include "k_vote_staged.cuh"
-#include "k_vote_split.cuh"
 #include "k_vote_ring.cuh"
 
 using namespace gcb;
 
 constexpr int GCB_MAX_CHUNKS = 16;
-constexpr int GCB_VOTE_TILED = 0, GCB_VOTE_PIPELINED = 1, GCB_VOTE_STAGED = 2, GCB_VOTE_SPLIT = 3, GCB_VOTE_RING = 4;
 constexpr int64_t GCB_CHUNK_BYTES = 48ll << 20;  // payload per pipeline chunk of gcb_consensus_batch
 
 namespace {
@@ -46,18 +41,11 @@ struct gcb_ctx {
     // workspace (grow-only)
     DevBuf w_members, w_group_off, w_scratch, w_rrp, w_flags, w_mode, w_hasumi, w_overlap, w_slab, w_cob, w_coo, w_scan, w_err, w_tiles;
     DevBuf w_vr, w_fs, w_gtiles, w_gcount;
-    DevBuf w_thdr, w_fstiles, w_ptiles, w_pcount;  // pipelined vote: tile headers, compact family sides, tile list
-    DevBuf w_thdr2;                                 // staged vote: tile headers (compact family sides share w_fstiles)
-    DevBuf w_sq_count, w_sq_words, w_sq_index, w_sq_acc;  // split vote: slow-column queues, per-family-side accumulators
-    int vote_mode = GCB_VOTE_RING;                  // GCB_VOTE_TILED / GCB_VOTE_PIPELINED / GCB_VOTE_STAGED / GCB_VOTE_SPLIT
-    int64_t slow_queue_bytes = 0;                   // 0 = sized from the payload
-    uint32_t sq_cap_words = 0, sq_cap_recs = 0;     // per queue
-    int vote_threads = 256;                         // threads per CTA of vote_staged_kernel / vote_fast_kernel
-    int ring_threads = 512;                         // threads per CTA of vote_ring_kernel (512 or 768)
-    int ring_units = 1;                             // units of sixteen columns per lane in vote_ring_kernel (1 or 2)
-    int ring_window_shift = 0;                      // 0 = chosen by plan_tiles; 14 / 15 = forced (tuning)
-    int group_lanes = 0;                            // lanes per cluster in umi_group / select_template (0 = by mean cluster size)
-    int ablate = 0;                                 // profiling only (GCB_ABLATE): parts of the ring kernel switched off
+    DevBuf w_fstiles, w_thdr2, w_need;   // the tiles' compact family-side lists, their headers, the largest tile's shared-memory need (per chunk)
+    DevBuf w_rb_list, w_rb_count;        // rollback candidates (per chunk: one counter)
+    int ring_window_shift = 0;           // 0 = chosen by plan_tiles; 14 / 15 = forced (tuning)
+    int group_lanes = 0;                 // lanes per cluster in umi_group / select_template (0 = by mean cluster size)
+    int force_generic = 0;               // tests: every tile goes to the generic kernel
     int n_sms = 148;
     // device mirror of a host batch / result (gcb_consensus_batch)
     DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
@@ -105,68 +93,41 @@ void release(DevBuf &b) {
     b.cap = 0;
 }
 
-// Tile geometry of the tiled vote kernel for one batch: the payload window whose clusters form a tile and
-// the staging buffer that holds the largest such tile (window + the largest cluster), chosen so that as
-// many CTAs as possible share an SM's 227 KB of shared memory.
+// Tile geometry of the vote for one batch: the payload window whose clusters form a tile, and the shared-memory arena of
+// the ring kernel, which must hold the largest such tile (window + the largest cluster) at least once.
 struct TilePlan {
-    int32_t window, window_shift, slab_cap, smem;
-    int32_t pipelined, n_stages, stage_bytes;  // vote_pipe_kernel: ring of n_stages tiles of stage_bytes each
-    int32_t staged;                            // vote_staged_kernel / vote_fast_kernel (same tile geometry)
-    int32_t split;                             // vote_fast_kernel + slow_columns_kernel + vote_rollback_kernel
-    int32_t ring;                              // vote_ring_kernel instead of vote_fast_kernel (n_stages, stage_bytes)
+    int32_t window, window_shift, slab_cap;
+    int32_t ring;         // vote_ring_kernel takes the tiles (0: clusters too large for the arena, the generic kernel takes all)
+    int32_t arena, smem;  // bytes
 };
-TilePlan plan_tiles(int32_t max_cluster_bytes, int vote_mode, int ring_window_shift = 0) {
+TilePlan plan_tiles(int32_t max_cluster_bytes, int ring_window_shift = 0) {
     const int32_t KB = 1024, budget = 227 * KB;
-    int32_t maxc = max_cluster_bytes > 0 ? ((max_cluster_bytes + 127) & ~127) : 16 * KB;
+    const int32_t maxc = max_cluster_bytes > 0 ? ((max_cluster_bytes + 127) & ~127) : 16 * KB;
     TilePlan p;
     memset(&p, 0, sizeof p);
-    if (vote_mode == GCB_VOTE_PIPELINED) {  // 16 KB windows: one CTA per SM keeps as many tiles in flight as fit
-        p.window_shift = 14;
-        p.window = 1 << p.window_shift;
+    p.arena = (budget - 1 * KB - VR_OFF_ARENA - VR_GUARD) & ~127;
+    p.smem = VR_OFF_ARENA + p.arena + VR_GUARD;
+    // 32 KB windows while three of the largest tiles fit the arena (the tiles of a batch of small clusters are about a window each,
+    // so the ring is deeper than that), else 16 KB windows as long as one tile fits
+    for (int shift = 15; shift >= 14; shift--) {
+        if (ring_window_shift && shift != ring_window_shift) continue;
+        p.window_shift = shift;
+        p.window = 1 << shift;
         p.slab_cap = p.window + maxc;
-        p.stage_bytes = (VPS_OFF_SLAB + p.slab_cap + VT_SLAB_SLACK + 127) & ~127;
-        p.n_stages = (budget - 1 * KB - VP_OFF_STAGE0) / p.stage_bytes;
-        if (p.n_stages > VP_MAX_STAGES) p.n_stages = VP_MAX_STAGES;
-        if (p.n_stages >= 3 && p.slab_cap <= VT_MAX_SLAB) {
-            p.pipelined = 1;
-            p.smem = VP_OFF_STAGE0 + p.n_stages * p.stage_bytes;
+        if (p.slab_cap > VT_MAX_SLAB) p.slab_cap = VT_MAX_SLAB;
+        // a tile of the largest slab with the tables of a family of pairs that fills it (a pair of two one-base reads is 16 bytes)
+        const int32_t tables = 3 * 128 + 8 * KB;
+        const int32_t largest = p.window + maxc + VT_SLAB_SLACK + tables;
+        if (p.window + maxc <= VT_MAX_SLAB && (p.arena >= 3 * largest || (shift == 14 && p.arena >= largest))) {
+            p.ring = 1;
             return p;
         }
     }
-    if (vote_mode == GCB_VOTE_RING) {  // one CTA per SM, a ring of whole tiles: 32 KB windows if three stages fit, else 16 KB
-        for (int shift = 15; shift >= 14; shift--) {
-            if (ring_window_shift && shift != ring_window_shift) continue;
-            p.window_shift = shift;
-            p.window = 1 << shift;
-            p.slab_cap = p.window + maxc;
-            // the tiles in flight share one arena; a tile takes what it needs (family-side list, VoteRead table, slab)
-            const int32_t largest = (32 * VS_MAX_FS + 32 * VS_MAX_PAIRS + p.slab_cap + VT_SLAB_SLACK + 3 * 127) & ~127;
-            p.stage_bytes = (budget - 1 * KB - VR_OFF_ARENA - VR_GUARD) & ~127;  // the arena
-            p.n_stages = VR_MAX_STAGES;
-            if ((p.stage_bytes >= 3 * largest || (shift == 14 && p.stage_bytes >= 2 * largest)) && p.slab_cap <= VT_MAX_SLAB) {
-                p.staged = p.split = p.ring = 1;
-                p.smem = VR_OFF_ARENA + p.stage_bytes + VR_GUARD;
-                return p;
-            }
-        }
-        // clusters too large for a ring (a depth-100 cluster of 2x150 pairs is 100 KB): one tile per CTA with the slow columns
-        // decided in place (vote_tiled_kernel measured 7.4 ms against 20 ms for the split kernels on the depth-100, 1 %-error shape)
-        memset(&p, 0, sizeof p);
-        vote_mode = GCB_VOTE_TILED;
-    }
-    const bool staged = vote_mode == GCB_VOTE_STAGED || vote_mode == GCB_VOTE_SPLIT;
-    const int32_t off_slab = staged ? VS_OFF_SLAB : VT_OFF_SLAB;
-    const int32_t tables = off_slab + VT_SLAB_SLACK + 1 * KB;  // + the 1 KB per-CTA reserve
-    if (32 * KB + maxc + tables <= budget / 3) p.window_shift = 15;       // three CTAs per SM
-    else if (16 * KB + maxc + tables <= budget / 2) p.window_shift = 14;  // two
-    else p.window_shift = 15;
+    // clusters too large for a stage: every tile goes to the generic kernel (no size limits)
+    p.window_shift = ring_window_shift ? ring_window_shift : 15;
     p.window = 1 << p.window_shift;
-    p.slab_cap = p.window + maxc;
-    if (p.slab_cap > VT_MAX_SLAB) p.slab_cap = VT_MAX_SLAB;
-    if (p.slab_cap + tables > budget) p.slab_cap = (budget - tables) & ~127;
-    p.smem = off_slab + p.slab_cap + VT_SLAB_SLACK;
-    p.staged = staged ? 1 : 0;
-    p.split = vote_mode == GCB_VOTE_SPLIT ? 1 : 0;
+    p.slab_cap = 0;
+    p.ring = 0;
     return p;
 }
 
@@ -181,7 +142,7 @@ int32_t fast_path_implied(const gcb_options &o) {
     return 1;
 }
 
-int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t n_tiles, int64_t payload_bytes, Workspace &ws) {
+int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t n_tiles, Workspace &ws) {
     int rc;
     const int64_t n_scan = (n_clusters + SCAN_BLOCK - 1) / SCAN_BLOCK;
 #define GCB_RES(buf, bytes) if ((rc = reserve(ctx, ctx->buf, (size_t)(bytes))) != GCB_OK) return rc
@@ -203,28 +164,11 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_fs, 2 * n_pairs * sizeof(FsDesc));
     GCB_RES(w_gtiles, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * 4);
     GCB_RES(w_gcount, 4 * GCB_MAX_CHUNKS);
-    GCB_RES(w_thdr, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * sizeof(TileHdr));
     GCB_RES(w_fstiles, 2 * n_pairs * sizeof(FsTile));
-    GCB_RES(w_ptiles, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * 4);
-    GCB_RES(w_pcount, 4 * GCB_MAX_CHUNKS);
     GCB_RES(w_thdr2, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * sizeof(TileHdr2));
-    {   // slow-column queues: a clean shallow library queues about 0.05 bytes per payload byte, a deep noisy one (1 % errors
-        // at depth 30-50) 1.6-1.9, a vote whose every column is slow (options outside fast_path_implied) about 4; tiles whose
-        // columns do not fit are redone by the generic kernel
-        int64_t qbytes = ctx->slow_queue_bytes > 0 ? ctx->slow_queue_bytes
-                         : fast_path_implied(ctx->opt) ? 3 * payload_bytes + (16ll << 20) : 5 * payload_bytes + (16ll << 20);
-        int64_t cap_words = qbytes / 4 / VQ_NQ;
-        if (cap_words > 0x3FFFFFF0ll) cap_words = 0x3FFFFFF0ll;
-        cap_words &= ~3ll;
-        if (cap_words < 64) cap_words = 64;
-        const int64_t cap_recs = cap_words / 12;  // the smallest record is 12 words
-        GCB_RES(w_sq_count, 8 * (VQ_NQ + 1) * GCB_MAX_CHUNKS);  // per chunk: VQ_NQ queue counters + the rollback list's count
-        GCB_RES(w_sq_words, 4 * cap_words * VQ_NQ);
-        GCB_RES(w_sq_index, 4 * cap_recs * VQ_NQ);
-        GCB_RES(w_sq_acc, 2 * n_pairs * 4);
-        ctx->sq_cap_words = (uint32_t)cap_words;
-        ctx->sq_cap_recs = (uint32_t)cap_recs;
-    }
+    GCB_RES(w_need, 4 * GCB_MAX_CHUNKS);
+    GCB_RES(w_rb_list, 2 * n_pairs * 4);
+    GCB_RES(w_rb_count, 4 * GCB_MAX_CHUNKS);
 #undef GCB_RES
     ws.members = (int32_t *)ctx->w_members.p;
     ws.group_off = (int32_t *)ctx->w_group_off.p;
@@ -313,88 +257,41 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         GCB_LAUNCH(scan_blocks_kernel, dim3(1), dim3(WARP), 0, stream, ws, n_scan, total_out, result.out_capacity, carry_in);
         ctx->launches += 3;
     }
+    // measurement: the vote's three parts can be run one at a time (tile preparation; the ring kernel; rollback + generic)
     const bool run_prep = (stages & (GCB_STAGE_SCORE_VOTE | GCB_STAGE_VOTE_PREP_ONLY)) != 0;
     const bool run_vote = (stages & (GCB_STAGE_SCORE_VOTE | GCB_STAGE_VOTE_ONLY)) != 0;
-    // split vote modes, measurement only: the fast kernel and (slow columns + finalize + generic) one at a time
-    // (plans that are not split run their one vote kernel as the "fast" half and the generic kernel as the "rest")
     const bool run_fast = run_vote || (stages & GCB_STAGE_VOTE_FAST_ONLY) != 0;
     const bool run_rest = run_vote || (stages & GCB_STAGE_VOTE_REST_ONLY) != 0;
     if ((run_prep || run_fast || run_rest) && n_tiles > 0) {
-        if (plan.pipelined) {
-            TileHdr *thdr = (TileHdr *)ctx->w_thdr.p + v.tile_base;
-            FsTile *fst = (FsTile *)ctx->w_fstiles.p;
-            int32_t *ptiles = (int32_t *)ctx->w_ptiles.p + v.tile_base, *pcount = (int32_t *)ctx->w_pcount.p + v.index;
-            if (run_prep) {
-                GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
-                GCB_CUDA(ctx, cudaMemsetAsync(pcount, 0, 4, stream));
-                GCB_LAUNCH(tile_prep_kernel, dim3((unsigned)n_tiles), dim3(VP_PREP_THREADS), 0, stream, b, r, ws, plan.slab_cap, thdr, fst, ptiles, pcount);
-                ctx->launches++;
-            }
-            if (run_fast) {
-                const unsigned pipe_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
-                GCB_LAUNCH(vote_pipe_kernel, dim3(pipe_grid), dim3(VP_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
-                           fast_path_implied(ctx->opt), plan.n_stages, plan.stage_bytes, (const TileHdr *)thdr, (const FsTile *)fst,
-                           (const int32_t *)ptiles, (const int32_t *)pcount);
-                ctx->launches++;
-            }
-        } else if (plan.staged) {
-            TileHdr2 *thdr = (TileHdr2 *)ctx->w_thdr2.p + v.tile_base;
-            FsTile *fst = (FsTile *)ctx->w_fstiles.p;
-            if (run_prep) {
-                GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
-                int32_t *max_need = (int32_t *)ctx->w_pcount.p + v.index;  // (the pipelined mode's tile counter is free in this mode)
-                GCB_CUDA(ctx, cudaMemsetAsync(max_need, 0, 4, stream));
-                GCB_LAUNCH(tile_prep2_kernel, dim3((unsigned)((n_tiles + VS_PREP_THREADS / WARP - 1) / (VS_PREP_THREADS / WARP))), dim3(VS_PREP_THREADS), 0,
-                           stream, b, r, ws, plan.slab_cap, thdr, fst, max_need, (int32_t)n_tiles);
-                ctx->launches++;
-            }
-            if ((run_fast || run_rest) && plan.split) {
-                // chunks of one batch run one after another on the stream and share the queues; every chunk has its own counters
-                SlowQueues sq;
-                sq.count = (unsigned long long *)ctx->w_sq_count.p + (size_t)(VQ_NQ + 1) * v.index;
-                sq.words = (uint32_t *)ctx->w_sq_words.p;
-                sq.index = (uint32_t *)ctx->w_sq_index.p;
-                sq.cap_words = ctx->sq_cap_words;
-                sq.cap_recs = ctx->sq_cap_recs;
-                sq.rb_list = (int32_t *)ctx->w_sq_acc.p + 2 * (size_t)v.p0;
-                sq.rb_count = (int32_t *)(sq.count + VQ_NQ);
-                sq.rb_cap = 2 * (v.p1 - v.p0);
-                if (run_fast) {
-                    GCB_CUDA(ctx, cudaMemsetAsync(sq.count, 0, 8 * (VQ_NQ + 1), stream));
-                    if (plan.ring) {
-                        const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
-#define GCB_RING_LAUNCH(NT, NU)                                                                                                              \
-    GCB_LAUNCH((vote_ring_kernel<NT, NU>), dim3(ring_grid), dim3(NT), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,           \
-               fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.n_stages, plan.stage_bytes, \
-               (const int32_t *)ctx->w_pcount.p + v.index, ctx->ablate)
-                        if (ctx->ring_threads == 768 && ctx->ring_units == 2) GCB_RING_LAUNCH(768, 2);
-                        else if (ctx->ring_threads == 768) GCB_RING_LAUNCH(768, 1);
-                        else if (ctx->ring_units == 2) GCB_RING_LAUNCH(512, 2);
-                        else GCB_RING_LAUNCH(512, 1);
-#undef GCB_RING_LAUNCH
-                    } else {
-                        GCB_LAUNCH(vote_fast_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
-                                   ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq);
-                    }
-                    ctx->launches++;
-                }
-                if (run_rest) {
-                    GCB_LAUNCH(slow_columns_kernel, dim3(VQ_NQ * VQ_SLOW_PARTS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ctx->genome, ctx->opt, sq);
-                    GCB_LAUNCH(vote_rollback_kernel, dim3(VQ_FINAL_CTAS), dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->opt, sq, v.p0, v.p1);
-                    ctx->launches += 2;
-                }
-            } else if (run_fast) {
-                GCB_LAUNCH(vote_staged_kernel, dim3((unsigned)n_tiles), dim3((unsigned)ctx->vote_threads), plan.smem, stream, b, r, ws, ctx->genome,
-                           ctx->opt, fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst);
-                ctx->launches++;
-            }
-        } else if (run_fast) {
+        TileHdr2 *thdr = (TileHdr2 *)ctx->w_thdr2.p + v.tile_base;
+        FsTile *fst = (FsTile *)ctx->w_fstiles.p;
+        int32_t *max_need = (int32_t *)ctx->w_need.p + v.index;
+        // chunks of one batch run one after another on the stream; every chunk has its own rollback counter and list range
+        RollbackList rb;
+        rb.list = (int32_t *)ctx->w_rb_list.p + 2 * (size_t)v.p0;
+        rb.count = (int32_t *)ctx->w_rb_count.p + v.index;
+        rb.cap = 2 * (v.p1 - v.p0);
+        if (run_prep) {
             GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
-            GCB_LAUNCH(vote_tiled_kernel, dim3((unsigned)n_tiles), dim3(VT_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
-                       plan.slab_cap, fast_path_implied(ctx->opt));
+            GCB_CUDA(ctx, cudaMemsetAsync(max_need, 0, 4, stream));
+            GCB_LAUNCH(tile_prep2_kernel, dim3((unsigned)((n_tiles + VS_PREP_THREADS / WARP - 1) / (VS_PREP_THREADS / WARP))), dim3(VS_PREP_THREADS), 0,
+                       stream, b, r, ws, plan.slab_cap, plan.arena, thdr, fst, max_need, (int32_t)n_tiles, (int32_t)(ctx->force_generic || !plan.ring));
             ctx->launches++;
         }
-        if (run_rest) {  // the tiles the kernels above handed over (an empty list costs a few microseconds)
+        if (run_fast && plan.ring && !ctx->force_generic) {
+            GCB_CUDA(ctx, cudaMemsetAsync(rb.count, 0, 4, stream));
+            const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
+            GCB_LAUNCH(vote_ring_kernel, dim3(ring_grid), dim3(VR_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
+                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, rb, (int32_t)n_tiles, plan.arena,
+                       (const int32_t *)max_need);
+            ctx->launches++;
+        }
+        if (run_rest) {
+            if (plan.ring && !ctx->force_generic) {
+                GCB_LAUNCH(vote_rollback_kernel, dim3(VQ_FINAL_CTAS), dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->opt, rb, v.p0, v.p1);
+                ctx->launches++;
+            }
+            // the tiles tile_prep2_kernel handed over (an empty list costs a few microseconds)
             const unsigned generic_grid = (unsigned)(n_tiles < 2 * 148 ? n_tiles : 2 * 148);
             GCB_LAUNCH(score_vote_kernel, dim3(generic_grid), dim3(VOTE_THREADS), VOTE_SMEM, stream, b, r, ws, ctx->genome, ctx->opt);
             ctx->launches++;
@@ -463,14 +360,7 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
         return GCB_ERR_CUDA;
     }
     if (cudaFuncSetAttribute(score_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_ring_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_ring_kernel<768, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_ring_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(vote_ring_kernel<768, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        cudaFuncSetAttribute(vote_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
         gcb_destroy(ctx);
         return GCB_ERR_CUDA;
     }
@@ -484,7 +374,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
-                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_thdr, &ctx->w_fstiles, &ctx->w_ptiles, &ctx->w_pcount, &ctx->w_thdr2, &ctx->w_sq_count, &ctx->w_sq_words, &ctx->w_sq_index, &ctx->w_sq_acc, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
+                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_need, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
                      &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status};
     for (DevBuf *b : all) release(*b);
@@ -546,10 +436,10 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
         return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch_device: bad sizes or alignment (payload 16 B, payload_bytes % 16, out_payload 4 B)");
     cudaStream_t stream = stream_ ? (cudaStream_t)stream_ : ctx->stream;
     GCB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const TilePlan plan = plan_tiles(batch->max_cluster_bytes, ctx->vote_mode, ctx->ring_window_shift);
+    const TilePlan plan = plan_tiles(batch->max_cluster_bytes, ctx->ring_window_shift);
     const int64_t n_tiles = (batch->payload_bytes + plan.window - 1) / plan.window;
     Workspace ws;
-    int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, batch->payload_bytes, ws);
+    int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, ws);
     if (rc != GCB_OK) return rc;
     const ViewRange whole = {0, batch->n_clusters, 0, batch->n_pairs, 0, batch->payload_bytes, 0, 0, 0};
     if (stages & GCB_STAGE_UMI_GROUP) GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, stream));
@@ -617,7 +507,7 @@ int gcb_consensus_batch(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *hr) {
     if (K > GCB_MAX_CHUNKS) K = GCB_MAX_CHUNKS;
     if (K < 1) K = 1;
     if ((int64_t)K > (int64_t)nc) K = nc > 0 ? (int)nc : 1;
-    const TilePlan plan = plan_tiles(hb->max_cluster_bytes, ctx->vote_mode, ctx->ring_window_shift);
+    const TilePlan plan = plan_tiles(hb->max_cluster_bytes, ctx->ring_window_shift);
     ViewRange view[GCB_MAX_CHUNKS];
     {
         int32_t c_prev = 0;
@@ -651,7 +541,7 @@ int gcb_consensus_batch(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *hr) {
         }
     }
     Workspace ws;
-    if ((rc = reserve_workspace(ctx, hb->n_pairs, hb->n_clusters, (hb->payload_bytes + plan.window - 1) / plan.window, hb->payload_bytes, ws)) != GCB_OK) return rc;
+    if ((rc = reserve_workspace(ctx, hb->n_pairs, hb->n_clusters, (hb->payload_bytes + plan.window - 1) / plan.window, ws)) != GCB_OK) return rc;
     cudaStream_t sc = ctx->stream, sin = ctx->h2d, sout = ctx->d2h;
     GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, sc));
     for (int k = 0; k < K; k++) {
@@ -730,23 +620,6 @@ int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, in
     return GCB_OK;
 }
 
-int gcb_set_vote_mode(gcb_ctx *ctx, int mode) {
-    if (!ctx || mode < GCB_VOTE_TILED || mode > GCB_VOTE_RING) return GCB_ERR_ARG;
-    ctx->vote_mode = mode;
-    return GCB_OK;
-}
-
-int gcb_set_vote_threads(gcb_ctx *ctx, int threads) {
-    if (!ctx) return GCB_ERR_ARG;
-    if (threads == 512 || threads == 768) {  // the ring kernel's two instantiations
-        ctx->ring_threads = threads;
-        return GCB_OK;
-    }
-    if (threads < WARP || threads > VS_MAX_THREADS || (threads % WARP)) return GCB_ERR_ARG;
-    ctx->vote_threads = threads;
-    return GCB_OK;
-}
-
 int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes) {
     if (!ctx || bytes < 16) return GCB_ERR_ARG;
     ctx->chunk_bytes = bytes;
@@ -766,20 +639,10 @@ void gcb_host_free(void *p) {
 
 int gcb_set_debug(gcb_ctx *ctx, int key, int value) {
     if (!ctx) return GCB_ERR_ARG;
-    if (key == 1) {  // profiling only (wrong results): refused unless the process says it is profiling
-        if (value != 0 && !getenv("GCB_PROFILING")) return GCB_ERR_ARG;
-        ctx->ablate = value;
-    }
-    else if (key == 2) ctx->ring_window_shift = value;  // tuning only: same results
-    else if (key == 3) ctx->group_lanes = value;        // tuning only: same results
-    else if (key == 4) ctx->ring_units = value == 2 ? 2 : 1;  // tuning only: same results
+    if (key == 2) ctx->ring_window_shift = (value == 14 || value == 15) ? value : 0;  // tuning only: same results
+    else if (key == 3) ctx->group_lanes = value;                                      // tuning only: same results
+    else if (key == 5) ctx->force_generic = value != 0;                               // tests: the generic kernel votes every tile
     else return GCB_ERR_ARG;
-    return GCB_OK;
-}
-
-int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes) {
-    if (!ctx || bytes < 0) return GCB_ERR_ARG;
-    ctx->slow_queue_bytes = bytes;
     return GCB_OK;
 }
 
@@ -788,7 +651,7 @@ int64_t gcb_launch_count(const gcb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 #ifdef GCB_SIMT_CHECK
 // tests only (CPU SIMT-check build): which vote path the tiles and columns took
 void gcb_simt_counters(int64_t *out, int reset) {
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < 8; k++) {
         out[k] = g_simt_counters[k];
         if (reset) g_simt_counters[k] = 0;
     }

@@ -1,120 +1,372 @@
-// k_vote_ring.cuh — the fast half of the split vote (k_vote_split.cuh) as ONE persistent CTA per SM over a ring of
-// staged tiles: Pair::computeScore (pair.cpp:88-172) fused with Group::makeConsensus (group.cpp:320-579).
+// k_vote_ring.cuh — the vote: Pair::computeScore (pair.cpp:88-172) fused with Group::makeConsensus (group.cpp:320-579),
+// ONE persistent CTA per SM over a ring of staged tiles (vote_tile.cuh).
 //
-//   warp 0, lane 0    producer.  Walks this CTA's tiles (blockIdx.x, + gridDim.x, ...), waits for the stage's `empty`
-//                     mbarrier, writes the 64-byte stage header and issues three bulk asynchronous copies
-//                     (cp.async.bulk -> UBLKCP) onto the stage's `full` mbarrier: compact family-side list, VoteRead table,
-//                     payload slab.  Runs up to n_stages tiles ahead; the last stage it fills carries nfs < 0.
-//   warps 1..15       consumers.  Every warp visits every tile in order: waits for `full`, takes bundles of family sides
-//                     from the stage's counter until none is left, arrives on `empty`.  A tile has fewer bundles than the
-//                     CTA has warps, so the warps spread over the tiles in flight; nobody waits for a tile's last column:
-//                     the slow columns are queued for slow_columns_kernel (k_vote_split.cuh).
-//   a bundle          lanes_per_side lanes per family side, sixteen columns per lane: the branch-free uniform loop of
-//                     vote_fast_kernel (raw-order XOR residues, VIMNMX3.U16x2 over two reads, mate alignment once per
-//                     bundle).  Slow columns of the bundle are emitted COOPERATIVELY: the lanes list their columns in a
-//                     small per-warp table, one 64-bit atomic reserves all records, then eight lanes per column write the
-//                     column's entries (one lane per read), in rounds of at most VR_ITEMS columns.
-//   queue overflow    the tile is handed to the generic kernel (score_vote_kernel), which runs last and rewrites all of the
-//                     tile's records from the payload.
+//   warp 0            producer.  The whole warp fetches the headers of this CTA's next 32 tiles (blockIdx.x, + gridDim.x, ...)
+//                     at once; lane 0 then waits for a stage's `empty` mbarrier, writes the stage header and issues three
+//                     bulk asynchronous copies (cp.async.bulk -> UBLKCP) onto the stage's `full` mbarrier: compact
+//                     family-side list, VoteRead table, payload slab.  Stages are equal slices of one arena sized by the
+//                     batch's largest tile, so small tiles give a deep ring and a 100 KB cluster still gets a stage.
+//   warps 1..15       voters.  Every warp visits every tile in order: waits for `full`, takes bundles of family sides from
+//                     the stage's counter until none is left, arrives on `empty`.  A tile has fewer bundles than the CTA has
+//                     warps, so the warps spread over the tiles in flight; nobody waits at a CTA barrier.
+//   a bundle          32 / L family sides, L lanes each, sixteen columns per lane.  FAST columns (every voter shows the
+//                     template's base, no read disagrees with its mate inside the pair overlap, best quality >=
+//                     moderateQuality: exactly group.cpp:421-427 under `implied`) are finished in the word: per-column maxima
+//                     in 16-bit lanes (VIMNMX3.U16x2 over two reads per iteration), disagreement as OR-accumulated XOR
+//                     residues of the raw words; uniform families (every fixed-length library) run a branch-free loop.
+//   slow columns      a lane that found slow columns appends ONE list entry (family side, lane, 16-bit column mask) to the
+//                     stage's list.  The warp that finishes the tile's last bundle closes the tile: it turns the list into
+//                     prefix sums of column counts and publishes it; the columns are then decided one THREAD per column,
+//                     32 at a time, straight from the staged slab (three-bin register histogram, group.cpp:376-525) by the
+//                     closing warp and by every warp that would otherwise wait for a tile — batches are grabbed with a
+//                     compare-and-swap on (tile epoch, next column), so a warp may help a tile it has already left.  The
+//                     stage is released when every voter has left it AND its last slow column is decided (`empty` counts
+//                     one arrival more than there are voter warps).
+// Nothing is queued in global memory and no second kernel reads the reads again: a tile's bytes cross HBM once.
 #pragma once
 
-#include "k_vote_split.cuh"
+#include "vote_tile.cuh"
 
 namespace gcb {
 
-constexpr int VR_MAX_THREADS = 768;           // the kernel is instantiated for 512 and 768 threads (128 / 85 registers)
-constexpr int VR_WARPS = VR_MAX_THREADS / WARP;
-constexpr int VR_MAX_STAGES = 8;   // tiles in flight (barrier pairs and stage headers); their bytes come from one arena
+constexpr int VR_THREADS = 512;
+constexpr int VR_WARPS = VR_THREADS / WARP;
+constexpr int VR_MAX_STAGES = 12;  // tiles in flight (barrier pairs and stage headers); their bytes come from one arena
 constexpr int VR_GUARD = 4608;     // never allocated, after the arena: the branch-free read loop may read a VoteRead table or a
                                    // slab up to 257 entries / 64 bytes past its end (values unused)
-constexpr int VR_ITEMS = 64;      // sparse slow columns of one bundle that are emitted cooperatively
-constexpr int VR_GROUP = 8;       // lanes per slow column in the cooperative emission
+constexpr uint32_t VR_COL_BITS = 20, VR_COL_MASK = (1u << VR_COL_BITS) - 1u;  // drain word: tile epoch << 20 | next column
 
-struct __align__(16) RingStage {  // shared memory, written by the producer before the stage's `full` barrier completes
+struct __align__(16) RingStage {  // shared memory; the first part is written by the producer before `full` completes
     int64_t out_base0;
     int32_t nfs;          // live family sides; < 0: no more tiles
-    int32_t lanes, per_bundle, n_bundles, common_l;
+    int32_t lanes, n_bundles, common_l;
     int32_t p0, tile;
-    int32_t next_bundle;  // atomic: next bundle to hand out
-    int32_t handed_over;  // atomic: the tile went to the generic kernel (queue overflow)
     int32_t ft_off, vr_off, slab_off;  // where the tile's family-side list, VoteRead table and payload slab lie (shared-memory offsets)
-    int32_t first_ticket;              // bundles of this CTA's earlier tiles, modulo the number of consumer warps
-    int32_t pad[1];
+    int32_t sl_off;                    // slow-column list: uint32 entries[sl_cap], then uint32 prefix[sl_cap]
+    int32_t sl_cap;
+    uint32_t epoch;                    // this CTA's tile counter, 12 bits
+    // the voters' part
+    int32_t next_bundle;   // atomic: next bundle to hand out
+    int32_t done;          // atomic: bundles finished
+    int32_t n_entries;     // atomic: slow-column list entries
+    int32_t drain_total;   // slow columns of the tile (valid once drain_word names column 0)
+    uint32_t drain_word;   // epoch << 20 | next slow column to decide; next = all ones until the tile is closed
+    int32_t cols_done;     // atomic: slow columns decided
+    int32_t pad[2];
 };
-static_assert(sizeof(RingStage) == 64, "stage header size");
+static_assert(sizeof(RingStage) == 96, "stage header size");
 
-// shared-memory map: [barriers][stage headers][per-warp slow-column tables][stage 0][stage 1]...
+// shared-memory map: [barriers][help bits][stage headers][producer's header cache][arena]
 constexpr int VR_OFF_FULL = 0;                                   // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MAX_STAGES]
-constexpr int VR_OFF_HDR = 128;                                  // RingStage[VR_MAX_STAGES]
-constexpr int VR_OFF_ITEMS = VR_OFF_HDR + 64 * VR_MAX_STAGES;    // per warp: uint16 codes[VR_ITEMS] (family side in the bundle << 9 | column)
-constexpr int VR_ITEM_BYTES = 2 * VR_ITEMS;
-constexpr int VR_POOL_RECS = 64, VR_POOL_WORDS = 64 * 20;  // queue space a warp reserves at a time
-constexpr int VR_OFF_HCACHE = (VR_OFF_ITEMS + VR_ITEM_BYTES * VR_WARPS + 15) & ~15;  // TileHdr2[32]: the producer's next tiles
-constexpr int VR_OFF_START = VR_OFF_HCACHE + 48 * WARP;          // uint32[VR_MAX_STAGES]: the producer's allocation starts
-constexpr int VR_OFF_ARENA = (VR_OFF_START + 4 * VR_MAX_STAGES + 127) & ~127;
-// a tile's allocation: [FsTile list][VoteRead table][slab + slack], each part rounded to 128 bytes
-static_assert(16 * VR_MAX_STAGES <= VR_OFF_HDR && VR_OFF_ARENA % 128 == 0, "ring layout");
+constexpr int VR_OFF_HELP = 16 * VR_MAX_STAGES;                  // uint32: stages whose slow columns wait for a warp
+constexpr int VR_OFF_HDR = 16 * VR_MAX_STAGES + 16;              // RingStage[VR_MAX_STAGES]
+constexpr int VR_OFF_HCACHE = VR_OFF_HDR + 96 * VR_MAX_STAGES;   // TileHdr2[32]: the producer's next tiles
+constexpr int VR_OFF_ARENA = (VR_OFF_HCACHE + 48 * WARP + 127) & ~127;
+// a tile's allocation: [FsTile list][VoteRead table][slab + slack][slow-column list + prefix], each part rounded to 128 bytes
+static_assert(VR_OFF_HDR % 16 == 0 && VR_OFF_HCACHE % 16 == 0 && VR_OFF_ARENA % 128 == 0, "ring layout");
 GCB_HD uint32_t ring_round128(uint32_t v) { return (v + 127u) & ~127u; }
 
-// a wait that lets the hardware suspend the thread between polls (a spinning warp takes issue slots from the warps that vote)
-#ifndef GCB_SIMT_CHECK
-__device__ __forceinline__ void pipe_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns) {
-    const uint32_t a = smem_u32(bar);
+struct RingCtx {  // what deciding a slow column needs besides the stage
+    const BatchView *b;
+    const ResultView *r;
+    const GenomeView *gv;
+    const gcb_options *o;
+    RollbackList rb;
+    uint8_t *smem;
+};
+
+// group.cpp:376-525 for one slow column of family side f of the staged tile, by one thread.  For a uniform family side
+// (every voter has the template's length, no column shift, the same overlap window) what pair.cpp:121-170 needs to know
+// about the column — inside the overlap or not, the mate index — is computed once; each read then is its quality byte,
+// its base nibble and, inside the overlap, its mate's, added to a three-bin register histogram.  The two scans of
+// group.cpp:395-417 are a top-2 selection over the three bins and the two largest codes nobody showed (bin_key order).
+__device__ __noinline__ void ring_slow_column(const RingCtx &x, const RingStage *sh, int f, int col) {
+    const gcb_options &o = *x.o;
+    const ScoreTab tab(o);
+    const FsTile ft = ((const FsTile *)(x.smem + sh->ft_off))[f];
+    const uint8_t *cb = x.smem + sh->slab_off + 4 * (int)ft.cbase4;
+    const VoteRead *ents = (const VoteRead *)(x.smem + sh->vr_off) + ft.ent0;
+    const VoteRead tv = ents[ft.tmpl_k];
+    const int side = fs_side(ft);
+    const int qbytes = GCB_ALIGN4(ft.l_out);
+    uint8_t *out = x.r->out_payload + sh->out_base0 + 4 * (int64_t)ft.out4;
+    GCB_COUNT(3, 1);
+    if (col >= (int)ft.len) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
+        int obase = 0, oqual = 0, sc;
+        fetch_ent(cb, tv, col, side, o, obase, oqual, sc);
+        out[col] = (uint8_t)oqual;
+        return;
+    }
+    Bins3 bins;
+    bins.init();
+    const int m = (int)ft.m;
+    if (ft.flags & FS_UNIFORM) {
+        const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
+        const int k = col - (int)tv.ov_own, mp = (int)tv.ov_mate + k;
+        const bool inwin = info && k >= 0 && k < (int)tv.ov_len;
+        const bool mvalid = inwin && mp >= 0 && mp < (int)tv.mate_l;
+        const bool plain = info && !inwin;  // pair.cpp:121-131: outside the overlap the score follows the quality
+        const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
+        const int mpi = mvalid ? mp : 0;
+        const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
+        for (int e = 0; e < m; e++) {
+            const uint32_t w = *(const uint32_t *)(ents + e);  // own_off4 | mate_off4 << 16
+            if ((w & 0xFFFFu) == VR_NO_VOTE) continue;
+            const uint8_t *rec = cb + 4 * (int)(w & 0xFFFFu);
+            int ql = rec[col];
+            const int base = (rec[soff] >> nsh) & 0xF;
+            int score;
+            if (mvalid) {
+                const uint8_t *mrec = cb + 4 * (int)(w >> 16);
+                const int mql = mrec[mpi];
+                const int mbase = (mrec[msoff] >> mnsh) & 0xF;
+                const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
+                const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
+                const int s_match = sc8(tab.q2s((ql + mql) / 2) + 4);                        // pair.cpp:147-152
+                const int s_mis = mine ? sc8(tab.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;  // pair.cpp:153-169
+                score = base == mbase ? s_match : s_mis;
+                ql = base == mbase ? ql : max(0, ql - mql);
+            } else {
+                score = plain ? tab.q2s(ql) : tab.sm;
+            }
+            bins.add(base, ql, score);
+        }
+    } else {
+        for (int e = 0; e < m; e++) {
+            int base, qual, score;
+            if (fetch_vote(cb, ents[e], col, side, tab, base, qual, score)) bins.add(base, qual, score);
+        }
+    }
+    ColumnTop ct;
+    int total = bins.total;
+    uint32_t acgt = 0;  // the best quality of codes 1, 2, 4, 8 in bytes 0..3 (0 when nobody showed the code)
+    if (bins.overflow) {  // a fourth distinct code: the sixteen-bin histogram in local memory (group.cpp:376-417 as written)
+        int32_t h[64];
+        for (int q = 0; q < 64; q++) h[q] = 0;
+        for (int e = 0; e < m; e++) {
+            int base, qual, score;
+            if (!fetch_ent(cb, ents[e], col, side, o, base, qual, score)) continue;
+            h[4 * base]++;
+            h[4 * base + 1] += score;
+            h[4 * base + 2] += qual;
+            h[4 * base + 3] = max(h[4 * base + 3], qual);
+        }
+        VoteBin obs[16];
+        int nobs = 0;
+        total = 0;
+        for (int q = 0; q < 16; q++)
+            if (h[4 * q] > 0) {
+                obs[nobs].base = q; obs[nobs].cnt = h[4 * q]; obs[nobs].score = h[4 * q + 1]; obs[nobs].qual = h[4 * q + 2]; obs[nobs].maxq = h[4 * q + 3];
+                total += obs[nobs].score;
+                nobs++;
+            }
+        ct = column_top(o, obs, nobs, total);
+        acgt = (uint32_t)(h[4 * 1] > 0 ? h[4 * 1 + 3] : 0) | ((uint32_t)(h[4 * 2] > 0 ? h[4 * 2 + 3] : 0) << 8) |
+               ((uint32_t)(h[4 * 4] > 0 ? h[4 * 4 + 3] : 0) << 16) | ((uint32_t)(h[4 * 8] > 0 ? h[4 * 8 + 3] : 0) << 24);
+    } else {
+        // top and second: every bin competes with its (score, quality sum, code) key; the codes nobody showed compete
+        // with (0, 0, code), of which only the two largest can place
+        unsigned freemask = 0xFFFFu;
+        unsigned long long key[3];
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++) {
+            const VoteBin vb = bins.bin(kk);
+            const int bb = vb.base;
+            const bool have = bb >= 0;
+            key[kk] = have ? bin_key(vb.score, vb.qual, bb) : 0ull;
+            if (have) freemask &= ~(1u << bb);
+            if (have && (bb == 1 || bb == 2 || bb == 4 || bb == 8)) acgt |= (uint32_t)vb.maxq << (bb == 1 ? 0 : bb == 2 ? 8 : bb == 4 ? 16 : 24);
+        }
+        const int e1 = 31 - __clz((int)freemask);
+        freemask &= ~(1u << e1);
+        const int e2 = 31 - __clz((int)freemask);
+        const unsigned long long ke1 = bin_key(0, 0, e1), ke2 = bin_key(0, 0, e2);
+        unsigned long long top = max_u64(key[0], key[1]), sec = min_u64(key[0], key[1]);
+        sec = max_u64(sec, min_u64(top, key[2])); top = max_u64(top, key[2]);
+        sec = max_u64(sec, min_u64(top, ke1)); top = max_u64(top, ke1);
+        sec = max_u64(sec, min_u64(top, ke2)); top = max_u64(top, ke2);
+        const int tb = (int)(top & 0xF), sb = (int)(sec & 0xF);
+        const VoteBin none = {0, 0, 0, 0, 0};
+        ct.top = bins.b0 == tb ? bins.bin(0) : bins.b1 == tb ? bins.bin(1) : bins.b2 == tb ? bins.bin(2) : none;
+        ct.sec = bins.b0 == sb ? bins.bin(0) : bins.b1 == sb ? bins.bin(1) : bins.b2 == sb ? bins.bin(2) : none;
+        ct.top.base = tb;
+        ct.sec.base = sb;
+        column_rules(o, ct, total);
+    }
+    int new_qual;
+    if (ct.fast) {
+        new_qual = ct.top.maxq;  // group.cpp:422-426: the base is NOT written
+    } else {
+        // the record's base before the vote: the template's own (pair.cpp rewrites qualities, never bases)
+        const int obase = base_at(cb + 4 * (int)tv.own_off4 + qbytes, col);
+        int ref4 = 0;
+        if (ft.flags & FS_REF_OK) {  // group.cpp:430-439
+            int refpos = col;
+            if (!(ft.flags & FS_SIMPLE_CIGAR)) {
+                const gcb_read_desc od = x.b->reads[x.r->groups[ft.slot].tmpl_read[side]];
+                refpos = get_ref_offset(x.b->cigar + od.cigar_off, od.n_cigar, col);
+            }
+            const int64_t nib = ft.ref_nib0 + refpos;
+            if (refpos >= 0 && nib >= 0 && (nib >> 1) < x.gv->packed_bytes) {  // the bound only guards malformed CIGARs
+                const uint8_t two = x.gv->packed4[nib >> 1];
+                ref4 = genome_nibble_to_bam((nib & 1) ? (two >> 4) : (two & 0xF));
+            }
+        }
+        int rbq = 0;
+        bool any_high = false;
+        if (ct.need_ref && ref4 != 0) {
+            const int rmax = (int)((acgt >> (ref4 == 1 ? 0 : ref4 == 2 ? 8 : ref4 == 4 ? 16 : 24)) & 0xFFu);
+            if (rmax >= 128) {  // `char refBaseQual` wraps: the scan order matters (group.cpp:474-490): template first
+                int tb, tq, ts;
+                if (fetch_ent(cb, tv, col, side, o, tb, tq, ts) && tb == ref4) {
+                    if (tq > rbq) rbq = sc8(tq);
+                    if (tq >= o.high_quality) any_high = true;
+                }
+                for (int e = 0; e < m; e++) {
+                    int base, qual, score;
+                    if (e == ft.tmpl_k || !fetch_ent(cb, ents[e], col, side, o, base, qual, score) || base != ref4) continue;
+                    if (qual > rbq) rbq = sc8(qual);
+                    if (qual >= o.high_quality) any_high = true;
+                }
+            } else {
+                rbq = rmax;
+                any_high = rmax >= o.high_quality;
+            }
+        }
+        const ColumnOut co = column_arbitrate(o, ct, ref4, rbq, any_high);
+        if (obase != co.base) {  // group.cpp:509-524
+            int d_mm = 0;
+            if (ref4 != 0) {
+                if (obase == ref4) d_mm = 1;
+                else if (co.base == ref4) d_mm = -1;
+            }
+            gcb_group_result *gr = x.r->groups + ft.slot;  // (the bundle's lane 0 zeroed both counters before the tile was closed)
+            atomicAdd(&gr->diff[side], 1);
+            if (d_mm != 0) {
+                const int before = atomicAdd(&gr->mismatch_inc[side], d_mm);
+                if (d_mm > 0 && before == 5) {  // more than five new mismatches so far: vote_rollback_kernel looks at the final count
+                    const int kk = atomicAdd(x.rb.count, 1);
+                    if (kk < x.rb.cap) x.rb.list[kk] = 2 * ft.slot + side;
+                }
+            }
+            const int byte = col >> 1;
+            const unsigned delta = ((unsigned)(obase ^ co.base) & 0xFu) << ((col & 1) ? 0 : 4);
+            atomicXor((unsigned *)(out + qbytes + (byte & ~3)), delta << (8 * (byte & 3)));
+        }
+        new_qual = co.qual;
+    }
+    out[col] = (uint8_t)new_qual;
+}
+
+// Up to 32 slow columns of stage `s` at a time, one thread per column, until none is left to grab.  Whoever decides the
+// tile's last column makes the drain's arrival on the stage's `empty` barrier.
+GCB_DEV void ring_drain(const RingCtx &x, RingStage *shdr, uint64_t *empty, int s, int lane, bool helping) {
+    RingStage *sh = shdr + s;
+    uint32_t *help = (uint32_t *)(x.smem + VR_OFF_HELP);
     for (;;) {
-        uint32_t done;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(a), "r"(parity), "r"(ns)
-            : "memory");
-        if (done) return;
+        int got = -1, total = 0;
+        if (lane == 0) {
+            const uint32_t w = *(volatile uint32_t *)&sh->drain_word;
+            total = *(volatile int32_t *)&sh->drain_total;
+            const uint32_t c = w & VR_COL_MASK;
+            if ((int64_t)c < (int64_t)total) {
+                got = atomicCAS(&sh->drain_word, w, w + 32u) == w ? (int)c : -2;
+                if (got >= 0 && got + 32 >= total) atomicAnd(help, ~(1u << s));  // the tile's last batch is taken
+            }
+        }
+        got = __shfl_sync(FULL, got, 0);
+        if (got == -2) continue;  // another warp was faster: look again
+        if (got < 0) return;
+        total = __shfl_sync(FULL, total, 0);
+        __threadfence_block();
+        const int idx = got + lane;
+        if (idx < total) {
+            const uint32_t *sl = (const uint32_t *)(x.smem + sh->sl_off);
+            const uint32_t *pf = sl + sh->sl_cap;
+            int lo = 0, hi = *(volatile int32_t *)&sh->n_entries - 1;
+            while (lo < hi) {  // the first entry whose inclusive column count exceeds idx
+                const int mid = (lo + hi) >> 1;
+                if ((int)pf[mid] > idx) hi = mid;
+                else lo = mid + 1;
+            }
+            const uint32_t code = sl[lo];
+            uint32_t mask = code & 0xFFFFu;
+            int rank = idx - ((int)pf[lo] - __popc(mask));
+            while (rank-- > 0) mask &= mask - 1u;
+            const int bit = __ffs((int)mask) - 1;  // bit 8 * w + i of the mask = column 8 * w + 7 - i of the lane's sixteen
+            const int col = VT_CHUNK * (int)((code >> 16) & 31u) + (bit & 8) + 7 - (bit & 7);
+            ring_slow_column(x, sh, (int)(code >> 21), col);
+            if (helping) GCB_COUNT(6, 1);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const int n = min(32, total - got);
+            __threadfence_block();
+            if (atomicAdd(&sh->cols_done, n) + n == total) pipe_arrive(empty + s);
+        }
+        pipe_progress();
     }
 }
-#else
-inline void pipe_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t) { pipe_wait(bar, parity); }
-#endif
 
-template <int NT, int NU>
-__global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, int32_t moderate_quality, int32_t implied,
-                                                                  const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, int32_t n_tiles,
-                                                                  int32_t max_stages, int32_t arena_bytes, const int32_t *max_need,
-                                                                  int32_t ablate) {
-    // `ablate` (profiling only, 0 in production; results are wrong otherwise): 1 = no slow-column emission, 2 = no read loop,
-    // 4 = no record stores, 8 = no bundle work at all
+__global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o, int32_t implied,
+                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, RollbackList rb, int32_t n_tiles,
+                                                                   int32_t arena_bytes, const int32_t *max_need) {
     GCB_DYN_SMEM(smem);
     uint64_t *full = (uint64_t *)(smem + VR_OFF_FULL);
     uint64_t *empty = (uint64_t *)(smem + VR_OFF_EMPTY);
     RingStage *shdr = (RingStage *)(smem + VR_OFF_HDR);
+    uint32_t *help = (uint32_t *)(smem + VR_OFF_HELP);
 #define GCB_LDS32(off) (*(const uint32_t *)(smem + (off)))
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
     // the arena is cut into equal stages that hold the batch's largest tile (tile_prep2_kernel measured it): as many tiles in
     // flight as fit
     const int32_t stage_bytes = (int32_t)ring_round128((uint32_t)max(*max_need, 128));
-    const int n_stages = min(max_stages, max(arena_bytes / stage_bytes, 1));
+    const int n_stages = min(VR_MAX_STAGES, max(arena_bytes / stage_bytes, 1));
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
             pipe_init(full + s, 1);
-            pipe_init(empty + s, NT / WARP - 1);  // every consumer warp arrives once when it leaves the stage's tile
+            pipe_init(empty + s, VR_WARPS);  // every voter warp arrives once when it leaves the stage's tile, the drain once
         }
+        *help = 0u;
         pipe_fence_init();
     }
     __syncthreads();
 
     if (warp == 0) {
-        // ---- producer: lane 0 fills the stages, up to n_stages tiles ahead of the consumers; the whole warp fetches the
+        // ---- producer: lane 0 fills the stages, up to n_stages tiles ahead of the voters; the whole warp fetches the
         // headers of this CTA's next 32 tiles at once, so that no tile waits for a header on its way from global memory
         TileHdr2 *hcache = (TileHdr2 *)(smem + VR_OFF_HCACHE);
         int k = 0;
-        // stage k % n_stages once every consumer has left the tile it held before
+        // stage k % n_stages once every voter has left the tile it held before and that tile's slow columns are decided
         auto allocate = [&]() -> uint32_t {
             const int s = k % n_stages, use = k / n_stages;
-            if (use > 0) pipe_wait_backoff(empty + s, (uint32_t)((use - 1) & 1), 2000u);
+            GCB_TRACE(200 + s);
+            if (use > 0) GCB_COUNT(7, 1);
+            if (use > 0)
+                while (!pipe_try_wait(empty + s, (uint32_t)((use - 1) & 1), 1000u)) pipe_relax(200u);
+            GCB_TRACE(300 + s);
             return (uint32_t)s * (uint32_t)stage_bytes;
+        };
+        auto fill = [&](RingStage &sh, const TileHdr2 &cur, int32_t tile, uint32_t at) {
+            const uint32_t vr_bytes = 32u * (uint32_t)cur.np, ft_bytes = 32u * (uint32_t)max(cur.nfs, 0);
+            sh.out_base0 = cur.out_base0;
+            sh.nfs = cur.nfs;
+            sh.lanes = cur.lanes; sh.n_bundles = cur.n_bundles; sh.common_l = cur.common_l;
+            sh.p0 = cur.p0; sh.tile = tile;
+            sh.ft_off = VR_OFF_ARENA + (int32_t)at;
+            sh.vr_off = sh.ft_off + (int32_t)ring_round128(ft_bytes);
+            sh.slab_off = sh.vr_off + (int32_t)ring_round128(vr_bytes);
+            sh.sl_off = sh.slab_off + (int32_t)ring_round128((uint32_t)cur.slab_bytes + VT_SLAB_SLACK);
+            sh.sl_cap = max(cur.nfs, 0) * cur.lanes;
+            sh.epoch = (uint32_t)k & 0xFFFu;
+            sh.next_bundle = 0;
+            sh.done = 0;
+            sh.n_entries = 0;
+            sh.drain_total = 0;
+            sh.drain_word = (sh.epoch << VR_COL_BITS) | VR_COL_MASK;
+            sh.cols_done = 0;
+            sh.pad[0] = sh.pad[1] = 0;
         };
         for (int64_t base = (int64_t)blockIdx.x; base < n_tiles; base += (int64_t)WARP * gridDim.x) {
             const int64_t mine_t = base + (int64_t)lane * gridDim.x;
@@ -130,17 +382,7 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
                     const uint32_t at = allocate();
                     const int s = k % n_stages;
                     RingStage sh;
-                    sh.out_base0 = cur.out_base0;
-                    sh.nfs = cur.nfs;
-                    sh.lanes = cur.lanes; sh.per_bundle = cur.per_bundle; sh.n_bundles = cur.n_bundles; sh.common_l = cur.common_l;
-                    sh.p0 = cur.p0; sh.tile = (int32_t)t;
-                    sh.next_bundle = 0;
-                    sh.handed_over = 0;
-                    sh.ft_off = VR_OFF_ARENA + (int32_t)at;
-                    sh.vr_off = sh.ft_off + (int32_t)ring_round128(ft_bytes);
-                    sh.slab_off = sh.vr_off + (int32_t)ring_round128(vr_bytes);
-                    sh.first_ticket = 0;
-                    sh.pad[0] = 0;
+                    fill(sh, cur, (int32_t)t, at);
                     shdr[s] = sh;
                     pipe_expect(full + s, slab_bytes + vr_bytes + ft_bytes);
                     if (slab_bytes > 0) tile_copy(smem + sh.slab_off, b.payload + cur.slab0, slab_bytes, full + s);
@@ -153,18 +395,13 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
             __syncwarp();
         }
         if (lane == 0) {  // the end marker: the phase completes with this arrival alone
-            allocate();
+            const uint32_t at = allocate();
             const int s = k % n_stages;
+            TileHdr2 cur;
+            cur.out_base0 = 0; cur.slab0 = 0; cur.slab_bytes = 0; cur.p0 = 0; cur.np = 0; cur.nfs = -1; cur.lanes = 1; cur.common_l = 0;
+            cur.per_bundle = 32; cur.n_bundles = 0;
             RingStage sh;
-            sh.out_base0 = 0;
-            sh.nfs = -1;
-            sh.lanes = 1; sh.per_bundle = 32; sh.n_bundles = 0; sh.common_l = 0;
-            sh.p0 = 0; sh.tile = 0;
-            sh.next_bundle = 0;
-            sh.handed_over = 0;
-            sh.ft_off = sh.vr_off = sh.slab_off = VR_OFF_ARENA;
-            sh.first_ticket = 0;
-            sh.pad[0] = 0;
+            fill(sh, cur, 0, at);
             shdr[s] = sh;
             pipe_expect(full + s, 0u);
             pipe_commit(full + s);
@@ -172,345 +409,261 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
         return;
     }
 
-    // ---- consumers
-    const uint32_t mod4 = 0x01010101u * (uint32_t)(moderate_quality & 0xFF);
+    // ---- voters
+    RingCtx x;
+    x.b = &b; x.r = &r; x.gv = &gv; x.o = &o; x.rb = rb; x.smem = smem;
+    const uint32_t mod4 = 0x01010101u * (uint32_t)(o.moderate_quality & 0xFF);
     const uint32_t sbase = smem_base(smem);
-    uint16_t *s_item = (uint16_t *)(smem + VR_OFF_ITEMS + VR_ITEM_BYTES * warp);
-    // slow-column records go to the queue of this CTA; every warp keeps a pool of reserved records / words in registers
-    const int qi = (int)(blockIdx.x % VQ_NQ);
-    uint32_t *q_words = sq.words + (size_t)qi * sq.cap_words;
-    uint32_t *q_index = sq.index + (size_t)qi * sq.cap_recs;
-    uint32_t pool_r = 0u, pool_re = 0u, pool_w = 0u, pool_we = 0u;
+    // lane geometry and masks are kept across tiles while the tile shape (lanes per family side, usual record length) stays
+    int cur_L = 0, cur_l = -1, S = 32, sub = 0, j = 0, col0 = 0;
+    ChunkMasks cm_common = make_masks(0, 0, 0);
     int s = 0;
     uint32_t par = 0u;
     for (;;) {
-        pipe_wait_backoff(full + s, par, 1000u);
+        // the next tile; while it is on its way the warp decides slow columns of the tiles that wait for hands
+        for (;;) {
+            GCB_TRACE(100 + s);
+            if (__all_sync(FULL, pipe_try_wait(full + s, par, 200u))) break;
+            uint32_t hb = 0u;
+            if (lane == 0) hb = *(volatile uint32_t *)help;
+            hb = __shfl_sync(FULL, hb, 0);
+            if (hb != 0u) ring_drain(x, shdr, empty, __ffs((int)hb) - 1, lane, true);
+            else pipe_relax(100u);
+        }
         RingStage *sh = shdr + s;
         const int nfs = sh->nfs;
         if (nfs < 0) break;
-        // a lane owns NU units of sixteen columns; a family side takes L lanes, a bundle 32 / L family sides
-        const int L = (sh->lanes + NU - 1) / NU;
-        const int S = (int)((32u * ((65535u / (unsigned)L) + 1u)) >> 16);
-        const int nb = NU == 1 ? sh->n_bundles : (int)(((unsigned)(nfs + S - 1) * ((65535u / (unsigned)S) + 1u)) >> 16);
+        GCB_TRACE(400 + s);
+        const int nb = sh->n_bundles;
         int bundle = nb;
         if (lane == 0 && *(volatile int32_t *)&sh->next_bundle < nb) bundle = atomicAdd(&sh->next_bundle, 1);  // (no atomic on a drained tile)
         bundle = __shfl_sync(FULL, bundle, 0);
+        bool closer = false;
         if (bundle < nb) {
+            if (sh->lanes != cur_L) {  // a lane owns sixteen columns; a family side takes L lanes, a bundle 32 / L family sides
+                cur_L = sh->lanes;
+                S = (int)((32u * ((65535u / (unsigned)cur_L) + 1u)) >> 16);
+                sub = (int)(((unsigned)lane * ((65535u / (unsigned)cur_L) + 1u)) >> 16);  // lane / L
+                j = lane - sub * cur_L;                                                      // lane % L
+                col0 = VT_CHUNK * j;
+                cur_l = -1;
+            }
+            if (sh->common_l != cur_l) {  // the masks of the tile's usual record length
+                cur_l = sh->common_l;
+                cm_common = make_masks(cur_l, cur_l, col0);
+            }
             const int off_slab = sh->slab_off, off_vr = sh->vr_off;
             const FsTile *s_ft = (const FsTile *)(smem + sh->ft_off);
             const VoteRead *s_vr = (const VoteRead *)(smem + off_vr);
-            const int64_t out_base0 = sh->out_base0;
-            uint8_t *out0 = r.out_payload + out_base0;
-            const int tile = sh->tile;
-            const int sub = (int)(((unsigned)lane * ((65535u / (unsigned)L) + 1u)) >> 16), j = lane - sub * L;  // lane / L, lane % L
-            const int col0 = VT_CHUNK * NU * j;
-            const int common_l = sh->common_l;  // the masks of the tile's usual record length are computed once
-            ChunkMasks cm_common[NU];
-#pragma unroll
-            for (int u = 0; u < NU; u++) cm_common[u] = make_masks(common_l, common_l, col0 + VT_CHUNK * u);
+            uint8_t *out0 = r.out_payload + sh->out_base0;
+            uint32_t *s_list = (uint32_t *)(smem + sh->sl_off);
+            const int sb0 = 8 * j;  // the lane's first byte of a record's packed bases
             do {
-                if (ablate & 8) goto next_bundle;
-                {
                 const int f = bundle * S + sub;
-                FsTile ft;
-                ft.ent0 = 0; ft.m = 0; ft.l_out = 0; ft.len = 0; ft.tmpl_k = 0; ft.mode = SIDE_NONE; ft.flags = 0; ft.cbase4 = 0; ft.out4 = 0;
-                if (sub < S && f < nfs) ft = s_ft[f];
+                const bool have = sub < S && f < nfs;
+                FsTile ft = s_ft[have ? f : 0];
+                if (!have) ft.mode = SIDE_NONE;
                 const int l_out = ft.l_out, len = ft.len;
                 const int qbytes = GCB_ALIGN4(l_out), sbytes = GCB_ALIGN4((l_out + 1) >> 1);
                 const bool mine = ft.mode != SIDE_NONE && col0 < max(qbytes, 2 * sbytes);  // this lane owns words of the record
                 const int m = mine && ft.mode != SIDE_COPY ? (int)ft.m : 0;
-                const int mmax = (ablate & 2) ? 0 : __reduce_max_sync(FULL, m);
+                const int mmax = __reduce_max_sync(FULL, m);
                 const int cb = off_slab + 4 * (int)ft.cbase4;  // byte offsets into the CTA's shared memory
                 const int ento = off_vr + 16 * (int)ft.ent0;
                 VoteRead tv = {0, 0, 0, 0, 0, 0, 0, 0};
-                uint32_t tbe[2 * NU];
-#pragma unroll
-                for (int w = 0; w < 2 * NU; w++) tbe[w] = 0u;
+                uint32_t tbe0 = 0u, tbe1 = 0u;
                 int trec = cb;
-                const int sb0 = 8 * NU * j;  // the lane's first byte of a record's packed bases
                 if (mine) {
                     tv = s_vr[ft.ent0 + ft.tmpl_k];
                     trec = cb + 4 * (int)tv.own_off4;
-#pragma unroll
-                    for (int w = 0; w < 2 * NU; w++)
-                        if (sb0 + 4 * w < sbytes) tbe[w] = bswap32(GCB_LDS32(trec + qbytes + sb0 + 4 * w));
+                    if (sb0 < sbytes) tbe0 = bswap32(GCB_LDS32(trec + qbytes + sb0));
+                    if (sb0 + 4 < sbytes) tbe1 = bswap32(GCB_LDS32(trec + qbytes + sb0 + 4));
                 }
-                ChunkMasks cm[NU];
-#pragma unroll
-                for (int u = 0; u < NU; u++) cm[u] = cm_common[u];
-                if (l_out != common_l || len != l_out) {
-#pragma unroll
-                    for (int u = 0; u < NU; u++) cm[u] = make_masks(l_out, len, col0 + VT_CHUNK * u);
-                }
+                ChunkMasks cm = cm_common;
+                if (l_out != cur_l || len != l_out) cm = make_masks(l_out, len, col0);
                 if (mine && j == 0 && ft.mode != SIDE_COPY) GCB_COUNT((ft.flags & FS_UNIFORM) ? 4 : 5, 1);
-                if (mine && j == 0) {  // slow_columns_kernel adds to these
+                if (mine && j == 0) {  // the slow columns add to these
                     gcb_group_result *gr = r.groups + ft.slot;
                     const int sd = (ft.flags & FS_SIDE1) ? 1 : 0;
                     gr->diff[sd] = 0;
                     gr->mismatch_inc[sd] = 0;
                 }
-                uint32_t mo[4 * NU], me[4 * NU], dis[2 * NU];
-#pragma unroll
-                for (int w = 0; w < 4 * NU; w++) mo[w] = me[w] = 0u;
-#pragma unroll
-                for (int w = 0; w < 2 * NU; w++) dis[w] = 0u;
-                if (ft.flags & FS_UNIFORM) {  // (see vote_fast_kernel)
-                    uint32_t om[2 * NU];
-                    bool has_ov = false;
-                    const int x0 = (int)tv.ov_own - col0, y0 = x0 - (int)tv.ov_mate;
-#pragma unroll
-                    for (int u = 0; u < NU; u++) {
-                        const int x = x0 - VT_CHUNK * u, y = y0 - VT_CHUNK * u;  // first column of the unit inside the window / with a mate index >= 0
-                        const int oa = max(max(0, x), y), oz = min(min(cm[u].nvote, x + (int)tv.ov_len), y + (int)tv.mate_l);
-                        const bool hu = tv.ov_len > 0 && oz > oa;
-                        om[2 * u] = hu ? nib_range(oa, oz) : 0u;
-                        om[2 * u + 1] = hu ? nib_range(oa - 8, oz - 8) : 0u;
-                        has_ov = has_ov || hu;
-                    }
-                    const int ms = 0 - y0, mw0 = ms >> 3;  // the lane's first mate column: word mw0 of the mate's bases, nibble ms & 7
+                // per-column maxima live in 16-bit lanes (VIMNMX3.U16x2 is native, a per-byte maximum is seven instructions):
+                // mo[k] tracks bytes 1 and 3 of quality word k in the high byte of each half, me[k] bytes 0 and 2 (word << 8)
+                uint32_t mo[4] = {0u, 0u, 0u, 0u}, me[4] = {0u, 0u, 0u, 0u}, dis0 = 0u, dis1 = 0u;
+                if (ft.flags & FS_UNIFORM) {
+                    // hoisted geometry: every voter is read at the template's columns and meets its mate at the same offset,
+                    // and every mate's record lies at the same distance from its read's record
+                    const int xw = (int)tv.ov_own - col0;   // first column of the lane inside the overlap window
+                    const int yw = xw - (int)tv.ov_mate;    // first column of the lane whose mate index is >= 0
+                    const int oa = max(max(0, xw), yw), oz = min(min(cm.nvote, xw + (int)tv.ov_len), yw + (int)tv.mate_l);
+                    const bool has_ov = tv.ov_len > 0 && oz > oa;
+                    const uint32_t om0 = has_ov ? nib_range(oa, oz) : 0u, om1 = has_ov ? nib_range(oa - 8, oz - 8) : 0u;
+                    const int ms = 0 - yw, mw0 = ms >> 3;  // the lane's first mate column: word mw0 of the mate's bases, nibble ms & 7
                     const unsigned msh = (unsigned)(ms & 7) * 4u;
                     const uint32_t qbase = sbase + (uint32_t)(cb + col0), sdelta = (uint32_t)(qbytes - col0 + sb0);
+                    // mate words relative to the read's own quality chunk.  Words that hold no overlapped column read whatever
+                    // lies there (the CTA's shared memory: the lane's window starts at most two words before the mate's bases
+                    // and ends inside the slab's slack) and are masked by om0 / om1; lanes without overlap re-read their own chunk.
                     const uint32_t mdelta = has_ov ? (uint32_t)(4 * ((int)tv.mate_off4 - (int)tv.own_off4) + GCB_ALIGN4(tv.mate_l) + 4 * mw0 - col0) : 0u;
                     const uint32_t xt = tv.own_off4;
                     const uint32_t qt = qbase + (xt << 2);
-                    uint32_t t[2 * NU], a0[2 * NU + 1], d[2 * NU], da[2 * NU + 1];
-#pragma unroll
-                    for (int w = 0; w < 2 * NU; w++) {
-                        t[w] = lds32r(qt + sdelta + 4 * w);
-                        d[w] = 0u;
-                    }
-#pragma unroll
-                    for (int w = 0; w < 2 * NU + 1; w++) {
-                        a0[w] = lds32r(qt + mdelta + 4 * w);
-                        da[w] = 0u;
-                    }
+                    const uint32_t t0 = lds32<0>(qt + sdelta), t1 = lds32<4>(qt + sdelta);                              // the template's bases, raw
+                    const uint32_t a0 = lds32<0>(qt + mdelta), c0 = lds32<4>(qt + mdelta), e0 = lds32<8>(qt + mdelta);  // its mate's
+                    uint32_t d0 = 0u, d1 = 0u, da = 0u, dc = 0u, de = 0u;
                     uint32_t ea = sbase + (uint32_t)ento;
                     for (int e = 0; e < mmax; e += 2, ea += 32) {
                         uint32_t xa = lds16<0>(ea), xb = lds16<16>(ea);
-                        xa = (e < m && xa != VR_NO_VOTE) ? xa : xt;
-                        xb = (e + 1 < m && xb != VR_NO_VOTE) ? xb : xt;
+                        xa = (e < m && xa != VR_NO_VOTE) ? xa : xt;  // reads that do not vote are replaced by the template's own
+                        xb = (e + 1 < m && xb != VR_NO_VOTE) ? xb : xt;  // record (maximum and OR are idempotent)
                         const uint32_t qa = qbase + (xa << 2), qb = qbase + (xb << 2);
-#pragma unroll
-                        for (int w = 0; w < 4 * NU; w++) {
-                            const uint32_t va = lds32r(qa + 4 * w), vb = lds32r(qb + 4 * w);
-                            mo[w] = __vimax3_u16x2(mo[w], va, vb);
-                            me[w] = __vimax3_u16x2(me[w], va << 8, vb << 8);
-                        }
-#pragma unroll
-                        for (int w = 0; w < 2 * NU; w++) d[w] |= (lds32r(qa + sdelta + 4 * w) ^ t[w]) | (lds32r(qb + sdelta + 4 * w) ^ t[w]);
-#pragma unroll
-                        for (int w = 0; w < 2 * NU + 1; w++) da[w] |= (lds32r(qa + mdelta + 4 * w) ^ a0[w]) | (lds32r(qb + mdelta + 4 * w) ^ a0[w]);
+                        const uint32_t qa0 = lds32<0>(qa), qa1 = lds32<4>(qa), qa2 = lds32<8>(qa), qa3 = lds32<12>(qa);
+                        const uint32_t qb0 = lds32<0>(qb), qb1 = lds32<4>(qb), qb2 = lds32<8>(qb), qb3 = lds32<12>(qb);
+                        const uint32_t ra0 = lds32<0>(qa + sdelta), ra1 = lds32<4>(qa + sdelta);
+                        const uint32_t rb0 = lds32<0>(qb + sdelta), rb1 = lds32<4>(qb + sdelta);
+                        const uint32_t ma = qa + mdelta, mb = qb + mdelta;
+                        const uint32_t aa = lds32<0>(ma), ca = lds32<4>(ma), ee = lds32<8>(ma);
+                        const uint32_t ab = lds32<0>(mb), cbb = lds32<4>(mb), eb = lds32<8>(mb);
+                        mo[0] = __vimax3_u16x2(mo[0], qa0, qb0); me[0] = __vimax3_u16x2(me[0], qa0 << 8, qb0 << 8);
+                        mo[1] = __vimax3_u16x2(mo[1], qa1, qb1); me[1] = __vimax3_u16x2(me[1], qa1 << 8, qb1 << 8);
+                        mo[2] = __vimax3_u16x2(mo[2], qa2, qb2); me[2] = __vimax3_u16x2(me[2], qa2 << 8, qb2 << 8);
+                        mo[3] = __vimax3_u16x2(mo[3], qa3, qb3); me[3] = __vimax3_u16x2(me[3], qa3 << 8, qb3 << 8);
+                        d0 |= (ra0 ^ t0) | (rb0 ^ t0);
+                        d1 |= (ra1 ^ t1) | (rb1 ^ t1);
+                        da |= (aa ^ a0) | (ab ^ a0);
+                        dc |= (ca ^ c0) | (cbb ^ c0);
+                        de |= (ee ^ e0) | (eb ^ e0);
                     }
-#pragma unroll
-                    for (int w = 0; w < 2 * NU; w++) dis[w] = bswap32(d[w]);
+                    dis0 = bswap32(d0);
+                    dis1 = bswap32(d1);
                     if (has_ov) {  // pair.cpp:133-170: a base that differs from its mate's is never a fast column
-#pragma unroll
-                        for (int w = 0; w < 2 * NU + 1; w++) {
-                            da[w] = bswap32(da[w]);
-                            a0[w] = bswap32(a0[w]);
-                        }
-#pragma unroll
-                        for (int w = 0; w < 2 * NU; w++)
-                            dis[w] |= (__funnelshift_l(da[w + 1], da[w], msh) | (bswap32(t[w]) ^ __funnelshift_l(a0[w + 1], a0[w], msh))) & om[w];
+                        const uint32_t A = bswap32(da), C = bswap32(dc), E = bswap32(de);
+                        const uint32_t ta = bswap32(a0), tc = bswap32(c0), te = bswap32(e0);
+                        dis0 |= (__funnelshift_l(C, A, msh) | (bswap32(t0) ^ __funnelshift_l(tc, ta, msh))) & om0;
+                        dis1 |= (__funnelshift_l(E, C, msh) | (bswap32(t1) ^ __funnelshift_l(te, tc, msh))) & om1;
                     }
                 } else if (m > 0) {
                     for (int e = 0; e < m; e++) {
                         const VoteRead v = s_vr[ft.ent0 + e];
                         if (v.own_off4 == VR_NO_VOTE || v.own_l == 0) continue;
+                        const int rp0 = col0 + v.shift;
+                        const int a = max(0, 0 - rp0), z = min(cm.nvote, (int)v.own_l - rp0);
+                        if (z <= a) continue;
                         const uint8_t *rec = smem + cb + 4 * (int)v.own_off4;
                         const int rq = GCB_ALIGN4(v.own_l);
+                        uint32_t q[4], be0, be1;
+                        fetch16q(rec, rq, rp0, q);
+                        fetch16b(rec + rq, GCB_ALIGN4((v.own_l + 1) >> 1), rp0, be0, be1);
+                        const uint32_t vm0 = nib_range(a, z), vm1 = nib_range(a - 8, z - 8);
+                        q[0] &= bytes_lo(vm0); q[1] &= bytes_hi(vm0); q[2] &= bytes_lo(vm1); q[3] &= bytes_hi(vm1);
 #pragma unroll
-                        for (int u = 0; u < NU; u++) {
-                            const int rp0 = col0 + VT_CHUNK * u + v.shift;
-                            const int a = max(0, 0 - rp0), z = min(cm[u].nvote, (int)v.own_l - rp0);
-                            if (z <= a) continue;
-                            uint32_t q[4], be0, be1;
-                            fetch16q(rec, rq, rp0, q);
-                            fetch16b(rec + rq, GCB_ALIGN4((v.own_l + 1) >> 1), rp0, be0, be1);
-                            const uint32_t vm0 = nib_range(a, z), vm1 = nib_range(a - 8, z - 8);
-                            q[0] &= bytes_lo(vm0); q[1] &= bytes_hi(vm0); q[2] &= bytes_lo(vm1); q[3] &= bytes_hi(vm1);
-#pragma unroll
-                            for (int kk = 0; kk < 4; kk++) {
-                                mo[4 * u + kk] = __vmaxu2(mo[4 * u + kk], q[kk]);
-                                me[4 * u + kk] = __vmaxu2(me[4 * u + kk], q[kk] << 8);
-                            }
-                            dis[2 * u] |= (be0 ^ tbe[2 * u]) & vm0;
-                            dis[2 * u + 1] |= (be1 ^ tbe[2 * u + 1]) & vm1;
-                            if (v.ov_len > 0) {  // (subtractions only: see the ptxas note in k_vote_tiled.cuh)
-                                const int x = (int)v.ov_own - rp0;
-                                const int y = x - (int)v.ov_mate;
-                                const int oa = max(max(a, x), y);
-                                const int oz = min(min(z, x + (int)v.ov_len), y + (int)v.mate_l);
-                                if (oz > oa) {
-                                    const uint8_t *mrec = smem + cb + 4 * (int)v.mate_off4;
-                                    uint32_t mb0, mb1;
-                                    fetch16b(mrec + GCB_ALIGN4(v.mate_l), GCB_ALIGN4((v.mate_l + 1) >> 1), 0 - y, mb0, mb1);
-                                    dis[2 * u] |= (be0 ^ mb0) & nib_range(oa, oz);
-                                    dis[2 * u + 1] |= (be1 ^ mb1) & nib_range(oa - 8, oz - 8);
-                                }
+                        for (int kk = 0; kk < 4; kk++) {
+                            mo[kk] = __vmaxu2(mo[kk], q[kk]);
+                            me[kk] = __vmaxu2(me[kk], q[kk] << 8);
+                        }
+                        dis0 |= (be0 ^ tbe0) & vm0;
+                        dis1 |= (be1 ^ tbe1) & vm1;
+                        if (v.ov_len > 0) {
+                            // chunk column k pairs own index rp0+k with mate index k - y.  (Written with subtractions only:
+                            // ptxas 12.9 dropped the negation when it folded max(a, max(x, -t)) into one VIMNMX3 on sm_100a —
+                            // the PTX was right, the SASS and the B200 were not; profiles/r01_notes.md has the listing.)
+                            const int xv = (int)v.ov_own - rp0;  // first chunk column inside the overlap window
+                            const int yv = xv - (int)v.ov_mate;  // first chunk column whose mate index is >= 0
+                            const int oa = max(max(a, xv), yv);
+                            const int oz = min(min(z, xv + (int)v.ov_len), yv + (int)v.mate_l);
+                            if (oz > oa) {
+                                const uint8_t *mrec = smem + cb + 4 * (int)v.mate_off4;
+                                uint32_t mb0, mb1;
+                                fetch16b(mrec + GCB_ALIGN4(v.mate_l), GCB_ALIGN4((v.mate_l + 1) >> 1), 0 - yv, mb0, mb1);
+                                dis0 |= (be0 ^ mb0) & nib_range(oa, oz);
+                                dis1 |= (be1 ^ mb1) & nib_range(oa - 8, oz - 8);
                             }
                         }
                     }
                 }
                 // ---- what the record gets: qualities = the maxima (fast columns), bases = the template's
-                uint32_t slow[2 * NU];  // one bit per slow column (the low bit of its big-endian nibble)
-#pragma unroll
-                for (int w = 0; w < 2 * NU; w++) slow[w] = 0u;
+                uint32_t slow0 = 0u, slow1 = 0u;  // one bit per slow column (the low bit of its big-endian nibble)
                 if (mine) {
                     uint8_t *out = out0 + 4 * (int64_t)ft.out4;
+                    uint32_t oq[4];
+                    if (ft.mode == SIDE_COPY) {  // group.cpp:73-77: the record itself
 #pragma unroll
-                    for (int u = 0; u < NU; u++) {
-                        const int cu = col0 + VT_CHUNK * u;
-                        uint32_t oq[4];
-                        if (ft.mode == SIDE_COPY) {  // group.cpp:73-77: the record itself
-#pragma unroll
-                            for (int kk = 0; kk < 4; kk++) oq[kk] = cu + 4 * kk < qbytes ? GCB_LDS32(trec + cu + 4 * kk) : 0u;
-                        } else {
-#pragma unroll
-                            for (int kk = 0; kk < 4; kk++) oq[kk] = prmt(mo[4 * u + kk], me[4 * u + kk], 0x3715u) & cm[u].vb[kk];  // (the hoisted loop read whole words)
-                            GCB_COUNT(2, cm[u].nvote);
-                            if (implied && len == l_out) {
-                                const uint32_t lowq0 = nibs_of_flags(bytes_ge_flags(oq[0], mod4) ^ 0x80808080u, bytes_ge_flags(oq[1], mod4) ^ 0x80808080u);
-                                const uint32_t lowq1 = nibs_of_flags(bytes_ge_flags(oq[2], mod4) ^ 0x80808080u, bytes_ge_flags(oq[3], mod4) ^ 0x80808080u);
-                                uint32_t s0 = (dis[2 * u] | lowq0) & cm[u].vn0, s1 = (dis[2 * u + 1] | lowq1) & cm[u].vn1;
-                                s0 |= s0 >> 1; s0 |= s0 >> 2; s0 &= 0x11111111u;  // any differing bit marks the column
-                                s1 |= s1 >> 1; s1 |= s1 >> 2; s1 &= 0x11111111u;
-                                slow[2 * u] = s0;
-                                slow[2 * u + 1] = s1;
-                            } else {  // without `implied`, or with columns that are not voted, every column of the record is slow
-                                slow[2 * u] = nibs_of_bytes(cm[u].rb[0], cm[u].rb[1]) & 0x11111111u;
-                                slow[2 * u + 1] = nibs_of_bytes(cm[u].rb[2], cm[u].rb[3]) & 0x11111111u;
-                            }
-                        }
-                        if (!(ablate & 4)) {
-#pragma unroll
-                            for (int kk = 0; kk < 4; kk++)
-                                if (cu + 4 * kk < qbytes) *(uint32_t *)(out + cu + 4 * kk) = oq[kk] & cm[u].rb[kk];
-                            if (sb0 + 8 * u < sbytes) *(uint32_t *)(out + qbytes + sb0 + 8 * u) = bswap32(tbe[2 * u] & cm[u].kn0);
-                            if (sb0 + 8 * u + 4 < sbytes) *(uint32_t *)(out + qbytes + sb0 + 8 * u + 4) = bswap32(tbe[2 * u + 1] & cm[u].kn1);
-                        }
-                    }
-                }
-                // ---- slow columns: records of one size per bundle, taken from the warp's own pool of reserved queue space
-                int nslow = 0;
-#pragma unroll
-                for (int w = 0; w < 2 * NU; w++) nslow += __popc(slow[w]);
-                if (ablate & 1) nslow = 0;
-                const uint32_t T = (uint32_t)__reduce_add_sync(FULL, nslow);
-                if (T > 0) {
-                    GCB_COUNT(3, nslow);
-                    const uint32_t rw = slow_rec_words(mmax), W = T * rw;
-                    if (pool_r + T > pool_re || pool_w + W > pool_we) {
-                        // a new pool (one 64-bit atomic: records << 32 | words); what is left of the old one stays unused
-                        for (uint32_t i = pool_r + (uint32_t)lane; i < pool_re; i += WARP) q_index[i] = VQ_INVALID;
-                        const uint32_t need_r = T > (uint32_t)VR_POOL_RECS ? T : (uint32_t)VR_POOL_RECS;
-                        const uint32_t need_w = W > (uint32_t)VR_POOL_WORDS ? W : (uint32_t)VR_POOL_WORDS;
-                        unsigned long long base64 = 0ull;
-                        if (lane == 0) base64 = atomicAdd(sq.count + qi, ((unsigned long long)need_r << 32) | need_w);
-                        base64 = __shfl_sync(FULL, base64, 0);
-                        const uint32_t r0 = (uint32_t)(base64 >> 32), w0 = (uint32_t)base64;
-                        if ((unsigned long long)r0 + need_r <= sq.cap_recs && (unsigned long long)w0 + need_w <= sq.cap_words) {
-                            pool_r = r0; pool_re = r0 + need_r;
-                            pool_w = w0; pool_we = w0 + need_w;
-                        } else {  // the queue is full: the reserved index entries are marked unused, the pool stays empty
-                            for (uint32_t i = r0 + (uint32_t)lane; i < r0 + need_r && i < sq.cap_recs; i += WARP) q_index[i] = VQ_INVALID;
-                            pool_r = pool_re = pool_w = pool_we = 0u;
-                        }
-                    }
-                    if (pool_r + T > pool_re) {
-                        // no queue space: the generic kernel redoes the whole tile from the payload (it runs after
-                        // slow_columns_kernel and vote_rollback_kernel)
-                        if (lane == 0 && atomicExch(&sh->handed_over, 1) == 0) {
-                            ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~tile;
-                            GCB_COUNT(1, 1);
-                        }
+                        for (int kk = 0; kk < 4; kk++) oq[kk] = col0 + 4 * kk < qbytes ? GCB_LDS32(trec + col0 + 4 * kk) : 0u;
                     } else {
-                        // rounds of at most VR_ITEMS columns: every lane lists one of its columns per ballot, then eight lanes per
-                        // column write the column's entries, one lane per read
-                        unsigned long long sm64[NU];
 #pragma unroll
-                        for (int u = 0; u < NU; u++) sm64[u] = ((unsigned long long)slow[2 * u] << 32) | slow[2 * u + 1];
-                        uint32_t emitted = 0u;
-                        while (emitted < T) {
-                            uint32_t listed = 0u;
-                            while (listed + WARP <= (uint32_t)VR_ITEMS) {
-                                bool has = false;
-                                int u_pick = 0;
-#pragma unroll
-                                for (int u = NU - 1; u >= 0; u--)
-                                    if (sm64[u] != 0ull) {
-                                        has = true;
-                                        u_pick = u;
-                                    }
-                                const unsigned bal = __ballot_sync(FULL, has);
-                                if (bal == 0u) break;
-                                if (has) {
-                                    unsigned long long v = sm64[0];
-#pragma unroll
-                                    for (int u = 1; u < NU; u++)
-                                        if (u_pick == u) v = sm64[u];
-                                    const int kk = __clzll((long long)v) >> 2;
-                                    v &= ~(0xF000000000000000ull >> (4 * kk));
-#pragma unroll
-                                    for (int u = 0; u < NU; u++)
-                                        if (u_pick == u) sm64[u] = v;
-                                    s_item[listed + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((sub << 9) | (col0 + VT_CHUNK * u_pick + kk));
-                                }
-                                listed += __popc(bal);
-                            }
-                            __syncwarp();
-                            const int g = lane / VR_GROUP, gl = lane % VR_GROUP;
-                            for (uint32_t i = (uint32_t)g; i < listed; i += WARP / VR_GROUP) {
-                                const uint32_t code = s_item[i], wofs = pool_w + (emitted + i) * rw;
-                                const int col = (int)(code & 511u), fi = bundle * S + (int)(code >> 9);
-                                const FsTile fti = s_ft[fi];
-                                const uint8_t *cbp = smem + off_slab + 4 * (int)fti.cbase4;
-                                const VoteRead *ents = s_vr + fti.ent0;
-                                uint32_t *rec = q_words + wofs;
-                                const int mi = (int)fti.m;
-                                if (gl == 0) {
-                                    q_index[pool_r + emitted + i] = wofs;
-                                    slow_write_header(rec, fti, col, out_base0 + 4 * (int64_t)fti.out4);
-                                }
-                                if ((fti.flags & FS_UNIFORM) && col < (int)fti.len) {
-                                    // the column's place in pair.cpp:121-170 is the same for every read of a uniform family
-                                    const VoteRead tvi = ents[fti.tmpl_k];
-                                    const bool info = tvi.ov_len != VR_NO_OVERLAP_INFO;
-                                    const int kq = col - (int)tvi.ov_own, mp = (int)tvi.ov_mate + kq;
-                                    const bool inwin = info && kq >= 0 && kq < (int)tvi.ov_len;
-                                    const bool mvalid = inwin && mp >= 0 && mp < (int)tvi.mate_l;
-                                    const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
-                                    const int soff = GCB_ALIGN4(fti.l_out) + (col >> 1), nsh = (col & 1) ? 0 : 4;
-                                    const int mrel = mvalid ? 4 * ((int)tvi.mate_off4 - (int)tvi.own_off4) : 0, mpi = mvalid ? mp : 0;
-                                    const int mqoff = mrel + mpi, msoff = mrel + (mvalid ? GCB_ALIGN4(tvi.mate_l) : 0) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
-                                    for (int e = gl; e < mi; e += VR_GROUP) {
-                                        const uint32_t xo = ents[e].own_off4;
-                                        uint32_t ent = 0u;
-                                        if (xo != VR_NO_VOTE) {
-                                            const uint8_t *p = cbp + 4 * (int)xo;
-                                            const uint32_t ql = p[col], base = ((uint32_t)p[soff] >> nsh) & 0xFu;
-                                            const uint32_t mql = mvalid ? p[mqoff] : 0u, mbase = mvalid ? (((uint32_t)p[msoff] >> mnsh) & 0xFu) : 0u;
-                                            ent = ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
-                                        }
-                                        rec[SR_HDR_WORDS + e] = ent;
-                                    }
-                                } else {
-                                    for (int e = gl; e < mi; e += VR_GROUP) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
-                                }
-                            }
-                            __syncwarp();
-                            emitted += listed;
+                        for (int kk = 0; kk < 4; kk++) oq[kk] = prmt(mo[kk], me[kk], 0x3715u) & cm.vb[kk];  // (the hoisted loop read whole words)
+                        GCB_COUNT(2, cm.nvote);
+                        if (implied && len == l_out) {
+                            const uint32_t lowq0 = nibs_of_flags(bytes_ge_flags(oq[0], mod4) ^ 0x80808080u, bytes_ge_flags(oq[1], mod4) ^ 0x80808080u);
+                            const uint32_t lowq1 = nibs_of_flags(bytes_ge_flags(oq[2], mod4) ^ 0x80808080u, bytes_ge_flags(oq[3], mod4) ^ 0x80808080u);
+                            slow0 = (dis0 | lowq0) & cm.vn0;
+                            slow1 = (dis1 | lowq1) & cm.vn1;
+                            slow0 |= slow0 >> 1; slow0 |= slow0 >> 2;  // any differing bit marks the column
+                            slow1 |= slow1 >> 1; slow1 |= slow1 >> 2;
+                        } else {  // without `implied`, or with columns that are not voted, every column of the record is slow
+                            slow0 = nibs_of_bytes(cm.rb[0], cm.rb[1]);
+                            slow1 = nibs_of_bytes(cm.rb[2], cm.rb[3]);
                         }
-                        pool_r += T;
-                        pool_w += W;
                     }
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)
+                        if (col0 + 4 * kk < qbytes) *(uint32_t *)(out + col0 + 4 * kk) = oq[kk] & cm.rb[kk];
+                    if (sb0 < sbytes) *(uint32_t *)(out + qbytes + sb0) = bswap32(tbe0 & cm.kn0);
+                    if (sb0 + 4 < sbytes) *(uint32_t *)(out + qbytes + sb0 + 4) = bswap32(tbe1 & cm.kn1);
                 }
+                // ---- slow columns: one list entry per lane (family side << 21 | lane of the family side << 16 | column mask)
+                const uint32_t mask16 = nib_flags_to_byte(slow0) | (nib_flags_to_byte(slow1) << 8);
+                const unsigned bal = __ballot_sync(FULL, mask16 != 0u);
+                if (bal != 0u) {
+                    int at = 0;
+                    if (lane == 0) at = atomicAdd(&sh->n_entries, __popc(bal));
+                    at = __shfl_sync(FULL, at, 0);
+                    if (mask16 != 0u) s_list[at + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)f << 21) | ((uint32_t)j << 16) | mask16;
                 }
-            next_bundle:
-                if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
+                // ---- the bundle is finished; the warp that finishes the tile's last one closes the tile
+                __syncwarp();
+                int fin = 0;
+                if (lane == 0) {
+                    __threadfence_block();
+                    fin = atomicAdd(&sh->done, 1) + 1;
+                    bundle = fin < nb ? atomicAdd(&sh->next_bundle, 1) : nb;
+                }
+                fin = __shfl_sync(FULL, fin, 0);
                 bundle = __shfl_sync(FULL, bundle, 0);
+                closer = fin == nb;
                 pipe_progress();
             } while (bundle < nb);
+        }
+        if (closer) {
+            // every bundle of the tile is done: prefix sums of the entries' column counts, then the tile's slow columns are
+            // open to every warp of the CTA
+            __threadfence_block();
+            const int n = *(volatile int32_t *)&sh->n_entries;
+            uint32_t *s_list = (uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap;
+            int run = 0;
+            for (int base = 0; base < n; base += WARP) {
+                const int i = base + lane;
+                int incl = i < n ? __popc(s_list[i] & 0xFFFFu) : 0;
+                for (int off = 1; off < WARP; off <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, off);
+                    if (lane >= off) incl += v;
+                }
+                if (i < n) s_pf[i] = (uint32_t)(run + incl);
+                run += __shfl_sync(FULL, incl, WARP - 1);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (run == 0) {
+                    pipe_arrive(empty + s);  // nothing to decide: the drain's arrival
+                } else {
+                    sh->drain_total = run;
+                    __threadfence_block();
+                    *(volatile uint32_t *)&sh->drain_word = sh->epoch << VR_COL_BITS;
+                    if (run > WARP) atomicOr(help, 1u << s);
+                }
+            }
+            __syncwarp();
+            if (run > 0) ring_drain(x, shdr, empty, s, lane, false);
         }
         __syncwarp();
         if (lane == 0) pipe_arrive(empty + s);
@@ -520,8 +673,6 @@ __global__ void __launch_bounds__(NT, 1) vote_ring_kernel(BatchView b, ResultVie
             par ^= 1u;
         }
     }
-    // what is left of the warp's pool stays unused
-    for (uint32_t i = pool_r + (uint32_t)lane; i < pool_re; i += WARP) q_index[i] = VQ_INVALID;
 #undef GCB_LDS32
 }
 

@@ -24,7 +24,7 @@ DEFAULT_LIB = os.path.join(HERE, "csrc", "libgencore_b200.so")
 # every symbol include/gencore_b200.h declares
 ABI_SYMBOLS = ["gcb_abi_version", "gcb_default_options", "gcb_create", "gcb_destroy", "gcb_last_error", "gcb_set_reference",
                "gcb_set_reference_device", "gcb_consensus_batch", "gcb_consensus_batch_device", "gcb_batch_status",
-               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_vote_mode", "gcb_set_vote_threads", "gcb_set_slow_queue_bytes", "gcb_set_debug", "gcb_host_alloc", "gcb_host_free"]
+               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_debug", "gcb_host_alloc", "gcb_host_free"]
 
 
 class EngineError(RuntimeError):
@@ -58,18 +58,12 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gcb_extract_umi.restype = C.c_int
     lib.gcb_extract_umi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.gcb_set_chunk_bytes.restype = C.c_int
-    lib.gcb_set_vote_mode.restype = C.c_int
-    lib.gcb_set_vote_mode.argtypes = [C.c_void_p, C.c_int]
     lib.gcb_host_alloc.restype = C.c_void_p
     lib.gcb_host_alloc.argtypes = [C.c_size_t, C.c_int]
     lib.gcb_host_free.restype = None
     lib.gcb_host_free.argtypes = [C.c_void_p]
     lib.gcb_set_debug.restype = C.c_int
     lib.gcb_set_debug.argtypes = [C.c_void_p, C.c_int, C.c_int]
-    lib.gcb_set_slow_queue_bytes.restype = C.c_int
-    lib.gcb_set_slow_queue_bytes.argtypes = [C.c_void_p, C.c_int64]
-    lib.gcb_set_vote_threads.restype = C.c_int
-    lib.gcb_set_vote_threads.argtypes = [C.c_void_p, C.c_int]
     lib.gcb_set_chunk_bytes.argtypes = [C.c_void_p, C.c_int64]
     lib.gcb_launch_count.restype = C.c_int64
     lib.gcb_launch_count.argtypes = [C.c_void_p]
@@ -157,21 +151,9 @@ class ConsensusEngine:
         """Payload bytes per pipeline chunk of cluster_by_umi (tuning only: results do not depend on it)."""
         self._check(self.lib.gcb_set_chunk_bytes(self._ctx, nbytes))
 
-    def set_vote_mode(self, mode: int) -> None:
-        """0 = one CTA per tile with its own prologue, 1 = persistent pipelined, 2 = staged, 3 = split fast/slow (default); same results."""
-        self._check(self.lib.gcb_set_vote_mode(self._ctx, mode))
-
     def set_debug(self, key: int, value: int) -> None:
-        """Profiling / tuning aid (see gcb_set_debug)."""
+        """Tuning / test aid (see gcb_set_debug): 2 = tile window shift, 3 = lanes per cluster, 5 = generic kernel only."""
         self._check(self.lib.gcb_set_debug(self._ctx, key, value))
-
-    def set_slow_queue_bytes(self, nbytes: int) -> None:
-        """Bytes of the slow-column queues of vote mode 3 (tuning / tests: columns that do not fit are decided in the fast kernel)."""
-        self._check(self.lib.gcb_set_slow_queue_bytes(self._ctx, nbytes))
-
-    def set_vote_threads(self, threads: int) -> None:
-        """Threads per CTA of the staged vote kernel (tuning only)."""
-        self._check(self.lib.gcb_set_vote_threads(self._ctx, threads))
 
     def batch_status(self, stream: int = 0) -> int:
         return self.lib.gcb_batch_status(self._ctx, C.c_void_p(stream))

@@ -42,6 +42,11 @@ def shard_batch(batch: Batch, world: int, rank: int) -> Tuple[Batch, Tuple[int, 
     return sub, (c0, c1)
 
 
+def split_batch(batch: Batch, parts: int) -> List[Batch]:
+    """The batch cut into `parts` coordinate windows (every one a valid gcb_batch), in order."""
+    return [shard_batch(batch, parts, r)[0] for r in range(parts)]
+
+
 STATS_FIELDS = ("pre_cluster", "pre_multi_cluster", "pre_molecule", "pre_molecule_se", "pre_molecule_pe", "pre_uncounted",
                 "post_cluster", "post_multi_cluster", "post_sscs", "post_dcs")
 

@@ -1,10 +1,12 @@
 """Synthetic workloads in the packed batch format (SURVEY §8(d) generator, BASELINE.json configs).
 
-Two producers:
+Three producers:
   * `BatchBuilder`   — read-by-read construction (tests, edge cases, ragged/clip/indel stress);
   * `make_fixed_batch` — vectorised numpy generator for the fixed-length 2x150 configs
-    (cfg1..cfg4 shapes) that scales to millions of pairs in seconds (bench.py).
-Both emit pairs of a cluster in the iteration order of the reference's map<qname+NUL padding>.
+    (cfg1..cfg4 shapes) that scales to millions of pairs in seconds (bench.py);
+  * `make_ragged_fixed` — vectorised generator of the cfg5 shape (mixed lengths, soft clips, indels);
+  `make_batch` picks between the last two by the config.
+All emit pairs of a cluster in the iteration order of the reference's map<qname+NUL padding>.
 No consensus arithmetic lives here.
 """
 from __future__ import annotations
@@ -298,7 +300,7 @@ def make_ragged_batch(seed: int, n_clusters: int = 200, depth: float = 6.0, read
 
 @dataclass
 class FixedConfig:
-    """The fixed-length shapes of BASELINE.json configs 0-3 (cfg1..cfg4 in SURVEY §8(d))."""
+    """The shapes of BASELINE.json configs 0-4 (cfg1..cfg5 in SURVEY §8(d)); cfg5 is the ragged one (`make_batch`)."""
     name: str
     n_pairs: int
     read_len: int = 150
@@ -313,6 +315,11 @@ class FixedConfig:
     insert_sigma: float = 40.0
     umi_thr: int = 1
     supporting_reads: int = 1
+    # cfg5 (ragged-column stress): reads of read_len_min..read_len bases, a soft clip of 1-30 bases at one end of
+    # clip_frac of the reads, one 1-10 base insertion or deletion in indel_frac of them
+    read_len_min: int = 0         # 0 = fixed length
+    clip_frac: float = 0.0
+    indel_frac: float = 0.0
 
 
 CONFIGS: Dict[str, FixedConfig] = {
@@ -322,6 +329,9 @@ CONFIGS: Dict[str, FixedConfig] = {
     "cfg3": FixedConfig("cfg3", 10_000_000, depth=20.0, umi="duplex", err=0.001, n_contigs=16, contig_len=10_000_000),
     "cfg4": FixedConfig("cfg4", 50_000_000, depth=100.0, umi="duplex", err=0.01, n_contigs=16, contig_len=10_000_000,
                         insert_mu=167.0, insert_sigma=20.0, supporting_reads=2),
+    "cfg5": FixedConfig("cfg5", 5_000_000, read_len=250, read_len_min=100, depth=6.0, umi="single", err=0.001, umi_err=0.01,
+                        shared_frac=0.10, n_contigs=4, contig_len=25_000_000, insert_mu=330.0, insert_sigma=60.0,
+                        clip_frac=0.20, indel_frac=0.05),
 }
 
 _QUAL_LUT = np.empty(256, np.uint8)  # {37:.90, 25:.06, 11:.03, 2:.01} on a 1/256 grid
@@ -487,3 +497,188 @@ def make_fixed_batch(cfg: FixedConfig, seed: int, n_pairs: Optional[int] = None,
               np.minimum(nm, 255).astype(np.uint8), "UMI" if cfg.umi != "none" else "")
     b.validate()
     return b, genome, contigs
+
+
+# ----------------------------------------------------------------------------- vectorised ragged generator (cfg5)
+
+
+def make_ragged_fixed(cfg: FixedConfig, seed: int, n_pairs: Optional[int] = None, with_qnames: bool = True,
+                      genome_cache: Optional[Tuple[List[np.ndarray], Genome]] = None, own_len_frac: float = 0.3):
+    """cfg5: read length uniform read_len_min..read_len per molecule and side, `own_len_frac` of the reads trimmed
+    further at their 3' end (left reads keep their start, right reads their end: the right-aligned column mode of group.cpp:339-349),
+    clip_frac of the reads with a 1-30 base soft clip at one end, indel_frac with one 1-10 base insertion or deletion.
+    Returns (Batch, Genome, contigs); deterministic in (cfg, seed, n_pairs)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    Lmin, Lmax = cfg.read_len_min, cfg.read_len
+    n_target = cfg.n_pairs if n_pairs is None else n_pairs
+    if genome_cache is None:
+        contigs, genome = random_genome(rng, [cfg.contig_len] * cfg.n_contigs)
+    else:
+        contigs, genome = genome_cache
+    # ---- molecules (as make_fixed_batch)
+    n_mol = int(n_target / cfg.depth * 1.25) + 64
+    fam = 1 + rng.poisson(max(cfg.depth - 1.0, 0.0), n_mol).astype(np.int64)
+    while fam.sum() < n_target:
+        fam = np.concatenate([fam, 1 + rng.poisson(max(cfg.depth - 1.0, 0.0), n_mol).astype(np.int64)])
+    csum = np.cumsum(fam)
+    n_mol = int(np.searchsorted(csum, n_target, side="left")) + 1
+    fam = fam[:n_mol]
+    fam[-1] -= int(csum[n_mol - 1] - n_target)
+    if fam[-1] <= 0:
+        fam, n_mol = fam[:-1], n_mol - 1
+    N = int(fam.sum())
+    mol_len = rng.integers(Lmin, Lmax + 1, (n_mol, 2))
+    insert = np.rint(rng.normal(cfg.insert_mu, cfg.insert_sigma, n_mol)).astype(np.int64)
+    insert = np.clip(np.maximum(insert, mol_len.max(axis=1) + 12), Lmin, 2 * Lmax + 100)
+    contig = rng.integers(0, cfg.n_contigs, n_mol)
+    start = rng.integers(40, cfg.contig_len - insert.max() - 80, n_mol)
+    shared = np.flatnonzero(rng.random(n_mol) < cfg.shared_frac)
+    shared = shared[shared > 0]
+    for a in (insert, contig, start):
+        a[shared] = a[shared - 1]
+    order = np.lexsort((np.arange(n_mol), insert, start, contig))
+    fam, insert, contig, start, mol_len = fam[order], insert[order], contig[order], start[order], mol_len[order]
+    mol_len = np.minimum(mol_len, (insert - 12)[:, None])  # (a molecule that took another's coordinates keeps its reads inside them)
+    new_cluster = np.ones(n_mol, bool)
+    new_cluster[1:] = (contig[1:] != contig[:-1]) | (start[1:] != start[:-1]) | (insert[1:] != insert[:-1])
+    cluster_of_mol = np.cumsum(new_cluster) - 1
+    n_clusters = int(cluster_of_mol[-1]) + 1
+    mol_of_pair = np.repeat(np.arange(n_mol), fam)
+    pair_first = np.concatenate([[0], np.cumsum(fam)[:-1]])
+    dup = np.arange(N) - pair_first[mol_of_pair]
+    cluster_of_pair = cluster_of_mol[mol_of_pair]
+    cluster_pair_off = np.zeros(n_clusters + 1, np.int32)
+    np.add.at(cluster_pair_off, cluster_of_pair + 1, 1)
+    cluster_pair_off = np.cumsum(cluster_pair_off).astype(np.int32)
+    cluster_ref = contig[np.flatnonzero(new_cluster)].astype(np.int32)
+    cluster_flags = np.full(n_clusters, cfg.umi_thr << CLUSTER_UMI_THR_SHIFT, np.uint8)
+    # ---- UMIs (8 characters, one word)
+    k = 8
+    fields = (rng.integers(0, 4, (n_mol, k), dtype=np.uint8) + 1)[mol_of_pair]
+    nerr = rng.binomial(N * k, cfg.umi_err)
+    if nerr:
+        fields[rng.integers(0, N, nerr), rng.integers(0, k, nerr)] = rng.integers(1, 5, nerr, dtype=np.uint8)
+    umi = np.zeros((N, 1), np.uint64)
+    for j in range(k):
+        umi[:, 0] |= fields[:, j].astype(np.uint64) << np.uint64(60 - 4 * j)
+    umi_chars = np.frombuffer(b"?ACGT_", np.uint8)[fields]
+    # ---- per-read shape: slot 2p = left, 2p+1 = right
+    R = 2 * N
+    side = np.tile(np.asarray([0, 1]), N)
+    l = mol_len[np.repeat(mol_of_pair, 2), side].astype(np.int64)
+    own = rng.random(R) < own_len_frac
+    l[own] = rng.integers(Lmin, l[own] + 1)
+    clip = rng.random(R) < cfg.clip_frac
+    clip_n = np.where(clip, rng.integers(1, 31, R), 0)
+    clip_left = rng.random(R) < 0.5
+    clipL, clipR = np.where(clip_left, clip_n, 0), np.where(clip_left, 0, clip_n)
+    core = l - clipL - clipR
+    ind = (rng.random(R) < cfg.indel_frac) & (core > 40)
+    ind_k = np.where(ind, rng.integers(1, 11, R), 0)
+    ind_ins = ind & (rng.random(R) < 0.5)
+    ind_del = ind & ~ind_ins
+    ind_a = np.where(ind, rng.integers(10, np.maximum(core - 20, 11)), 0)
+    refspan = core - np.where(ind_ins, ind_k, 0) + np.where(ind_del, ind_k, 0)
+    mstart = np.repeat(start[mol_of_pair], 2)
+    mins = np.repeat(insert[mol_of_pair], 2)
+    pos = np.where(side == 0, mstart, mstart + mins - refspan)
+    goff = np.concatenate([[0], np.cumsum([len(c) for c in contigs])[:-1]]).astype(np.int64)
+    gall = np.concatenate(contigs) if len(contigs) > 1 else contigs[0]
+    gpos = goff[np.repeat(contig[mol_of_pair], 2)] + pos
+    # ---- CIGARs: [clipL S] a M [k I|D] rest M [clipR S]
+    ops = np.zeros((R, 5), np.uint32)
+    valid = np.zeros((R, 5), bool)
+    ops[:, 0], valid[:, 0] = (clipL << 4) | 4, clipL > 0
+    first_m = np.where(ind, ind_a, core)
+    ops[:, 1], valid[:, 1] = (first_m << 4) | 0, True
+    ops[:, 2], valid[:, 2] = (ind_k << 4) | np.where(ind_ins, 1, 2), ind
+    ops[:, 3], valid[:, 3] = ((core - ind_a - np.where(ind_ins, ind_k, 0)) << 4) | 0, ind
+    ops[:, 4], valid[:, 4] = (clipR << 4) | 4, clipR > 0
+    n_cigar = valid.sum(axis=1)
+    cigar = ops[valid].astype(np.uint32)
+    cigar_off = np.concatenate([[0], np.cumsum(n_cigar)[:-1]])
+    # ---- payload layout
+    rec = ((l + 3) & ~3) + (((l + 1) // 2 + 3) & ~3)
+    reads_per_cluster = 2 * np.diff(cluster_pair_off).astype(np.int64)
+    cl_of_read = np.repeat(np.arange(n_clusters), reads_per_cluster)
+    rec_csum = np.cumsum(rec)
+    cl_first = np.concatenate([[0], np.cumsum(reads_per_cluster)[:-1]])
+    cl_bytes = np.add.reduceat(rec, cl_first)
+    cl_start = np.concatenate([[0], np.cumsum((cl_bytes + 15) & ~15)[:-1]])
+    within = rec_csum - rec - (rec_csum - rec)[cl_first][cl_of_read]
+    data_off = cl_start[cl_of_read] + within
+    total = int(((cl_bytes + 15) & ~15).sum())
+    payload = np.zeros(total, np.uint8)
+    nm = np.zeros(R, np.int64)
+    W = Lmax + (Lmax & 1)
+    ar = np.arange(W, dtype=np.int64)
+    CH = 200_000
+    for r0 in range(0, R, CH):
+        r1 = min(R, r0 + CH)
+        n = r1 - r0
+        ll, cL, cR, a_, k_, ins_, del_ = l[r0:r1, None], clipL[r0:r1, None], clipR[r0:r1, None], ind_a[r0:r1, None], ind_k[r0:r1, None], \
+            ind_ins[r0:r1, None], ind_del[r0:r1, None]
+        q = ar[None, :]
+        c = q - cL
+        inq = q < ll
+        rnd = (c < 0) | (q >= ll - cR) | (ins_ & (c >= a_) & (c < a_ + k_))
+        shift = np.where(ins_ & (c >= a_ + k_), -k_, 0) + np.where(del_ & (c >= a_), k_, 0)
+        gi = np.clip(gpos[r0:r1, None] + c + shift, 0, len(gall) - 1)
+        seq = gall[gi]
+        rb = BASES[rng.integers(0, 4, (n, W), dtype=np.uint8)]
+        seq = np.where(rnd, rb, seq)
+        qual = _QUAL_LUT[rng.integers(0, 256, (n, W), dtype=np.uint8)]
+        err = (rng.random((n, W)) < cfg.err) & inq & ~rnd
+        ne = int(err.sum())
+        if ne:
+            seq[err] = BASES[(np.searchsorted(BASES, seq[err]) + rng.integers(1, 4, ne)) % 4]
+            qual[err] = _ERRQ_LUT[rng.integers(0, 256, ne, dtype=np.uint8)]
+        nm[r0:r1] = err.sum(axis=1) + k_[:, 0]
+        codes = np.where(inq, BAM_CODE[seq], 0).astype(np.uint8)
+        packed = (codes[:, 0::2] << 4) | codes[:, 1::2]
+        qual = np.where(inq, qual, 0).astype(np.uint8)
+        # scatter: quality bytes, then packed bases at align4(l)
+        do = data_off[r0:r1, None]
+        qm = inq
+        payload[(do + q)[qm]] = qual[qm]
+        hb = ar[None, :W // 2]
+        sm = hb < (ll + 1) // 2
+        payload[(do + ((ll + 3) & ~3) + hb)[sm]] = packed[sm]
+    reads = np.zeros(R, READ_DESC)
+    reads["data_off"] = data_off
+    reads["l_qseq"] = l
+    reads["pos"] = pos
+    isz = mins.copy()
+    isz[1::2] *= -1
+    reads["isize"] = isz
+    reads["cigar_off"] = cigar_off
+    reads["n_cigar"] = n_cigar
+    qn = None
+    width = 4 + 9 + 1 + 5 + 5 + k
+    if with_qnames:
+        mat = np.empty((N, width), np.uint8)
+        mat[:, 0:4] = np.frombuffer(b"SIM:", np.uint8)
+        m = mol_of_pair.copy()
+        for j in range(9):
+            mat[:, 12 - j] = 48 + (m % 10)
+            m //= 10
+        mat[:, 13] = ord(":")
+        d = dup.copy()
+        for j in range(5):
+            mat[:, 18 - j] = 48 + (d % 10)
+            d //= 10
+        mat[:, 19:24] = np.frombuffer(b":UMI_", np.uint8)
+        mat[:, 24:] = umi_chars
+        qn = np.ascontiguousarray(mat).view(f"S{width}").ravel()
+    reads["l_qname"] = padded_l_qname(width)
+    b = Batch(cluster_pair_off, cluster_ref, cluster_flags, umi, reads, cigar, payload, qn, np.minimum(nm, 255).astype(np.uint8), "UMI")
+    b.validate()
+    return b, genome, contigs
+
+
+def make_batch(cfg: FixedConfig, seed: int, n_pairs: Optional[int] = None, with_qnames: bool = True,
+               genome_cache: Optional[Tuple[List[np.ndarray], Genome]] = None):
+    """The batch of a BASELINE.json config: fixed-length shapes from make_fixed_batch, cfg5 from make_ragged_fixed."""
+    if cfg.read_len_min > 0:
+        return make_ragged_fixed(cfg, seed, n_pairs, with_qnames, genome_cache)
+    return make_fixed_batch(cfg, seed, n_pairs, with_qnames, genome_cache)

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define GCB_ABI_VERSION 1
+#define GCB_ABI_VERSION 2
 #define GCB_ALIGN4(x) (((x) + 3) & ~3)
 #define GCB_MAX_UMI_WORDS 4 /* UMIs up to 64 characters */
 
@@ -147,16 +147,16 @@ typedef struct gcb_result {
     int64_t *out_bytes;        /* [1] bytes used */
 } gcb_result;
 
-/* stage mask for gcb_consensus_batch_device: the four kernels of the path */
+/* stage mask for gcb_consensus_batch_device: the four stages of the path */
 #define GCB_STAGE_UMI_GROUP 0x1u       /* cluster.cpp:55-100  -> pair_group, cluster_n_groups */
 #define GCB_STAGE_SELECT_TEMPLATE 0x2u /* group.cpp:136-313   -> tmpl_read, out_off, qname_donor, umi_pair */
 #define GCB_STAGE_SCORE_VOTE 0x4u      /* pair.cpp:88-172 + group.cpp:320-579 -> out_payload, diff, mismatch_inc */
 #define GCB_STAGE_DUPLEX 0x8u          /* cluster.cpp:102-244 -> status, FR/RR, duplex merge of out_payload */
 #define GCB_STAGE_ALL 0xFu
-/* measurement only: the two halves of GCB_STAGE_SCORE_VOTE one at a time (per-tile preparation, then the vote) */
+/* measurement only: the parts of GCB_STAGE_SCORE_VOTE one at a time — per-tile preparation (tile_prep2_kernel), then the
+ * vote, or the vote's two halves: the ring kernel (vote_ring_kernel), then rollback + the generic kernel's tiles */
 #define GCB_STAGE_VOTE_PREP_ONLY 0x10u
 #define GCB_STAGE_VOTE_ONLY 0x20u
-/* vote modes 3 and 4 only: the two halves of GCB_STAGE_VOTE_ONLY (fast-column kernel; slow columns + finalize + generic) */
 #define GCB_STAGE_VOTE_FAST_ONLY 0x40u
 #define GCB_STAGE_VOTE_REST_ONLY 0x80u
 
@@ -209,15 +209,6 @@ int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, in
  * chunks are whole clusters).  Results do not depend on it. */
 int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes);
 
-/* Which kernel runs GCB_STAGE_SCORE_VOTE: 0 = one CTA per tile with its own prologue (vote_tiled_kernel), 1 = the
- * persistent pipelined kernel (vote_pipe_kernel, falls back to 0 for batches whose clusters are too large for its
- * ring), 2 = one CTA per tile over headers and family-side lists prepared once per batch (vote_staged_kernel),
- * 3 = the same tiles with the slow columns queued for a second kernel (vote_fast_kernel + slow_columns_kernel +
- * vote_rollback_kernel), 4 = mode 3 with the fast kernel as one persistent CTA per SM over a ring of staged tiles
- * (vote_ring_kernel, the default; falls back to 3 for batches whose clusters are too large for a ring).  Results are
- * identical. */
-int gcb_set_vote_mode(gcb_ctx *ctx, int mode);
-
 /* Page-locked host memory for the arrays of a gcb_batch / gcb_result handed to gcb_consensus_batch (pageable memory works,
  * at a fraction of the link rate).  `write_combined` memory is for buffers the host only WRITES (a packed batch): the copy
  * engine reads it without snooping the CPU caches; reading it back on the host is very slow (on the round-1 B200 box both
@@ -225,19 +216,10 @@ int gcb_set_vote_mode(gcb_ctx *ctx, int mode);
 void *gcb_host_alloc(size_t bytes, int write_combined);
 void gcb_host_free(void *p);
 
-/* Profiling / tuning aid, not for production: key 1 = switch parts of the ring kernel off (results are WRONG, timing only;
- * refused with GCB_ERR_ARG unless the environment variable GCB_PROFILING is set),
- * key 2 = force the ring kernel's tile window (14 or 15 = log2 bytes, 0 = automatic; results unchanged),
- * key 3 = lanes per cluster in umi_group_kernel / select_template_kernel (8, 16, 32; 0 = by mean cluster size; results unchanged). */
+/* Tuning / test aid; results never depend on it.  key 2 = force the vote's tile window (14 or 15 = log2 bytes, 0 = automatic),
+ * key 3 = lanes per cluster in umi_group_kernel / select_template_kernel (8, 16, 32; 0 = by mean cluster size),
+ * key 5 = non-zero: every tile is voted by the generic kernel (score_vote_kernel) instead of the ring kernel. */
 int gcb_set_debug(gcb_ctx *ctx, int key, int value);
-
-/* Tuning knob of vote mode 3: bytes of the slow-column queues (0 = sized from the payload).  Columns that do not fit are
- * decided inside the fast kernel; results do not depend on it. */
-int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes);
-
-/* Tuning knob: threads per CTA of vote modes 2 and 3 (a multiple of 32, at most 256; default 256), or of the ring kernel of
- * mode 4 (512, the default, or 768).  Results do not depend on it. */
-int gcb_set_vote_threads(gcb_ctx *ctx, int threads);
 
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t gcb_launch_count(const gcb_ctx *ctx);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Exploration: stage times of the hot path on a fixed-length duplex shape of a given depth and error rate (not a bench line).
-    python scripts/shape_perf.py <depth> <err> [pairs]"""
-import dataclasses, os, sys, time
+"""Exploration (not a bench line): stage times of the hot path on other shapes, one process, one GPU.
+    python scripts/shape_perf.py <spec> [<spec> ...]     spec = cfgN[:pairs[:window_shift]] | deep:<depth>:<err>[:pairs[:window_shift]]"""
+import dataclasses, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,16 +11,25 @@ from gencore_b200.abi import (STAGE_ALL, STAGE_DUPLEX, STAGE_SELECT_TEMPLATE, ST
 from gencore_b200.device import DeviceBatch, DeviceResult
 from gencore_b200.engine import ConsensusEngine
 
-depth, err = float(sys.argv[1]), float(sys.argv[2])
-pairs = int(sys.argv[3]) if len(sys.argv) > 3 else 500_000
-cfg = dataclasses.replace(synth.CONFIGS["cfg4"], depth=depth, err=err, n_contigs=2, contig_len=10_000_000)
-batch, genome, _ = synth.make_fixed_batch(cfg, seed=77, n_pairs=pairs, with_qnames=False)
-print("depth %g err %g: %d clusters, %d pairs, %.0f MB payload" % (depth, err, batch.n_clusters, batch.n_pairs, len(batch.payload) / 1e6))
 dev = torch.device("cuda:0")
-for mode in (4, 0):
-    with ConsensusEngine(Options.default(), 0) as eng:
+for spec in sys.argv[1:]:
+    f = spec.split(":")
+    if f[0] == "deep":
+        depth, err = float(f[1]), float(f[2])
+        pairs = int(f[3]) if len(f) > 3 else 500_000
+        shift = int(f[4]) if len(f) > 4 else 0
+        cfg = dataclasses.replace(synth.CONFIGS["cfg4"], depth=depth, err=err, n_contigs=2, contig_len=10_000_000)
+    else:
+        pairs = int(f[1]) if len(f) > 1 else 1_000_000
+        shift = int(f[2]) if len(f) > 2 else 0
+        cfg = synth.CONFIGS[f[0]]
+        cfg = dataclasses.replace(cfg, n_contigs=min(cfg.n_contigs, 2), contig_len=min(cfg.contig_len, 20_000_000))
+    batch, genome, _ = synth.make_batch(cfg, seed=77, n_pairs=pairs, with_qnames=False)
+    opt = Options.default(cluster_size_req=cfg.supporting_reads)
+    with ConsensusEngine(opt, 0) as eng:
         eng.set_reference(genome)
-        eng.set_vote_mode(mode)
+        if shift:
+            eng.set_debug(2, shift)
         db = DeviceBatch.from_host(batch, dev)
         dr = DeviceResult.allocate(batch.n_pairs, batch.n_clusters, len(batch.payload), dev)
         ts = torch.cuda.Stream(device=dev)
@@ -28,7 +37,8 @@ for mode in (4, 0):
         for _ in range(3):
             eng.cluster_by_umi_device(db.struct, dr.struct, STAGE_ALL, ts.cuda_stream)
         torch.cuda.synchronize()
-        n = 5
+        assert eng.batch_status() == 0
+        n = 10
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(n)]
         for k in range(n):
             for q, st in enumerate(stages):
@@ -37,5 +47,8 @@ for mode in (4, 0):
             ev[k][len(stages)].record(ts)
         torch.cuda.synchronize()
         ms = [float(np.mean([ev[k][q].elapsed_time(ev[k][q + 1]) for k in range(n)])) for q in range(len(stages))]
-        print("mode %d stage ms (umi, select, prep, vote, rest, duplex): %s  total %.3f  -> %.3g pairs/s" %
-              (mode, ["%.3f" % x for x in ms], sum(ms), batch.n_pairs / (sum(ms) * 1e-3)))
+        print("%s: %d clusters, %d pairs, %.0f MB payload, max cluster %d KB; stage ms (umi, select, prep, ring, rest, duplex): %s  total %.3f -> %.3g pairs/s, "
+              "vote %.2f TB/s of payload" % (spec, batch.n_clusters, batch.n_pairs, len(batch.payload) / 1e6, batch.max_cluster_bytes() >> 10,
+                                             ["%.3f" % x for x in ms], sum(ms), batch.n_pairs / (sum(ms) * 1e-3), len(batch.payload) / (sum(ms[2:5]) * 1e-3) / 1e12),
+              flush=True)
+    del db, dr

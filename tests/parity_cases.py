@@ -32,11 +32,16 @@ def ragged_case(seed, umi, n_clusters=60):
     return batch, genome, list(cases.OPTION_SETS.values())[seed % len(cases.OPTION_SETS)]
 
 
-def fixed_case(name, n_pairs, contig_len=200_000):
+def fixed_case(name, n_pairs, contig_len=200_000, **over):
     cfg = synth.CONFIGS[name]
-    small = dataclasses.replace(cfg, contig_len=contig_len, n_contigs=min(cfg.n_contigs, 2))
-    batch, genome, _ = synth.make_fixed_batch(small, seed=20261017, n_pairs=n_pairs, with_qnames=False)
+    small = dataclasses.replace(cfg, contig_len=contig_len, n_contigs=min(cfg.n_contigs, 2), **over)
+    batch, genome, _ = synth.make_batch(small, seed=20261017, n_pairs=n_pairs, with_qnames=False)
     return batch, genome, Options.default(cluster_size_req=cfg.supporting_reads)
+
+
+def noisy_deep_case(n_pairs, depth, err, contig_len=200_000):
+    """Deep duplex families with many slow columns: the tile's slow-column list is long and other warps help to decide it."""
+    return fixed_case("cfg3", n_pairs, contig_len, depth=float(depth), err=err)
 
 
 def deep_case():
@@ -97,12 +102,17 @@ def small_cases():
     out += [("deep_1100", deep_case), ("low_complexity", low_complexity_case), ("no_reference", no_reference_case),
             ("empty", empty_case), ("tiny_reads", tiny_reads_case),
             ("wide_umi_3", lambda: wide_umi_case(3)), ("wide_umi_4", lambda: wide_umi_case(4))]
-    out += [(f"{n}_1500", (lambda n=n: fixed_case(n, 1500))) for n in ("cfg1", "cfg2", "cfg3", "cfg4")]
+    out += [(f"{n}_1500", (lambda n=n: fixed_case(n, 1500))) for n in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5")]
+    out += [("cfg2_6000", lambda: fixed_case("cfg2", 6000)),           # many tiles per CTA: the ring's stages are used again and again
+            ("deep30_noisy", lambda: noisy_deep_case(1500, 30, 0.01)),
+            ("deep300_noisy", lambda: noisy_deep_case(1500, 300, 0.003))]  # clusters of ~130 KB: one tile fills the ring kernel's arena
     return out
 
 
 def gpu_cases():
     out = small_cases()
     out += [(f"ragged_{umi}_{seed}_big", (lambda s=seed, u=umi: ragged_case(s, u, 400))) for seed in range(4, 8) for umi in ("none", "single", "duplex")]
-    out += [(f"{n}_40k", (lambda n=n: fixed_case(n, 40_000, 2_000_000))) for n in ("cfg1", "cfg2", "cfg3", "cfg4")]
+    out += [(f"{n}_40k", (lambda n=n: fixed_case(n, 40_000, 2_000_000))) for n in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5")]
+    out += [("deep50_noisy_40k", lambda: noisy_deep_case(40_000, 50, 0.01, 2_000_000)),
+            ("deep400_40k", lambda: noisy_deep_case(40_000, 400, 0.002, 2_000_000))]
     return out

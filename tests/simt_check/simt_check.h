@@ -90,9 +90,11 @@ struct State {
     int bar_arrived = 0;
     unsigned bar_generation = 0;
     uint64_t progress = 0;
+    uint64_t soft_progress = 0;  // polls of a spin wait (simt::relax): a fiber moved, but nothing was completed
     std::vector<uint8_t> smem;
     const std::function<void()> *body = nullptr;
     uint64_t launches = 0;
+    int tags[2048] = {0};  // debugging aid: where every fiber last said it was (GCB_TRACE)
 };
 
 inline State &st() {
@@ -108,10 +110,17 @@ inline dim3 blockDim, gridDim;
 namespace simt {
 
 inline uint8_t *dyn_smem() { return st().smem.data(); }
+inline void trace(int tag) { st().tags[st().cur] = tag; }
+inline void relax();
 
 inline void yield() {
     State &s = st();
     swapcontext(&s.fibers[s.cur].ctx, &s.sched);
+}
+
+inline void relax() {  // one poll of a spin wait
+    st().soft_progress++;
+    yield();
 }
 
 inline void trampoline() {
@@ -144,8 +153,9 @@ inline void run_block(int nthreads, const std::function<void()> &body) {
         f.done = false;
         s.warps[t / kWarp].live++;
     }
+    int idle_sweeps = 0;
     while (s.live > 0) {
-        uint64_t before = s.progress;
+        uint64_t before = s.progress, soft_before = s.soft_progress;
         for (int t = 0; t < nthreads; t++) {
             if (s.fibers[t].done) continue;
             s.cur = t;
@@ -153,8 +163,15 @@ inline void run_block(int nthreads, const std::function<void()> &body) {
             threadIdx.y = threadIdx.z = 0;
             swapcontext(&s.sched, &s.fibers[t].ctx);
         }
-        if (s.live > 0 && s.progress == before) {
+        // a sweep in which nothing completed is a deadlock unless fibers are polling (a poll loop interleaved with warp
+        // collectives can go a few sweeps without completing one); polling alone for thousands of sweeps is one too
+        idle_sweeps = s.progress == before ? idle_sweeps + 1 : 0;
+        if (s.live > 0 && s.progress == before && (s.soft_progress == soft_before || idle_sweeps > 100000)) {
             fprintf(stderr, "simt_check: deadlock in block %u (%d threads alive, none can advance)\n", blockIdx.x, s.live);
+            for (int q = 0; q < 64; q++) fprintf(stderr, "%s%016llx", q % 4 ? " " : "\n  smem ", (unsigned long long)((uint64_t *)s.smem.data())[q]);
+            fprintf(stderr, "\n");
+            for (int t = 0; t < nthreads; t += 1)
+                if (!s.fibers[t].done && (t % kWarp == 0 || s.tags[t] != s.tags[t - 1])) fprintf(stderr, "  thread %d tag %d\n", t, s.tags[t]);
             abort();
         }
     }
@@ -421,6 +438,10 @@ template <typename T>
 inline T atomicMax(T *p, T v) { T old = *p; if (v > old) *p = v; return old; }
 template <typename T>
 inline T atomicXor(T *p, T v) { T old = *p; *p = old ^ v; return old; }
+template <typename T>
+inline T atomicAnd(T *p, T v) { T old = *p; *p = old & v; return old; }
+template <typename T>
+inline T atomicOr(T *p, T v) { T old = *p; *p = old | v; return old; }
 template <typename T>
 inline T atomicCAS(T *p, T cmp, T v) { T old = *p; if (old == cmp) *p = v; return old; }
 template <typename T>

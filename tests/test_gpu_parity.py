@@ -1,6 +1,9 @@
 """Parity tests proper: the CUDA library (gencore_b200/csrc/libgencore_b200.so) through its C ABI on a
-B200 against the oracle, bit-exact, on the shared case list; then size-independent properties at
-BASELINE.json's bench size."""
+B200 against the oracle, bit-exact, on the shared case list; then the BASELINE.json shapes at bench size
+(one million pairs each) compared record for record with the oracle, plus size-independent properties."""
+import dataclasses
+import os
+
 import numpy as np
 import pytest
 
@@ -28,11 +31,14 @@ def test_cuda_matches_oracle_host_buffers(engine_cls, oracle, name, thunk):
     with engine_cls(opt, 0) as eng:
         eng.set_reference(genome)
         res = eng.cluster_by_umi(batch)
+        res2 = eng.cluster_by_umi(batch)  # the second run must give the same answer (no state leaks between batches)
         assert eng.launches > 0 or batch.n_clusters == 0
-    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
+    expect = oracle.consensus(batch, genome, opt)
+    assert_results_equal(batch, res, expect, name)
+    assert_results_equal(batch, res2, expect, name + " (second run)")
 
 
-@pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "deep_1100"])
+@pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "deep_1100", "cfg5_40k", "deep400_40k"])
 def test_cuda_matches_oracle_device_buffers(engine_cls, oracle, name):
     import torch
     from gencore_b200.device import DeviceBatch, DeviceResult
@@ -43,7 +49,7 @@ def test_cuda_matches_oracle_device_buffers(engine_cls, oracle, name):
         db = DeviceBatch.from_host(batch, dev)
         dr = DeviceResult.allocate(batch.n_pairs, batch.n_clusters, len(batch.payload), dev)
         torch.cuda.synchronize()
-        for _ in range(2):  # the second run must give the same answer (no state leaks between batches)
+        for _ in range(2):
             eng.cluster_by_umi_device(db.struct, dr.struct, STAGE_ALL, torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
             assert eng.batch_status() == 0
@@ -52,55 +58,30 @@ def test_cuda_matches_oracle_device_buffers(engine_cls, oracle, name):
 
 
 @pytest.mark.parametrize("name,thunk", CASES, ids=[c[0] for c in CASES])
-def test_pipelined_vote_matches_oracle(engine_cls, oracle, name, thunk):
-    """The persistent pipelined vote kernel (gcb_set_vote_mode 1) on every case."""
+def test_generic_vote_matches_oracle(engine_cls, oracle, name, thunk):
+    """score_vote_kernel (no size limits; takes the tiles the ring kernel cannot stage) on every tile of every case."""
     batch, genome, opt = thunk()
     with engine_cls(opt, 0) as eng:
         eng.set_reference(genome)
-        eng.set_vote_mode(1)
-        res = eng.cluster_by_umi(batch)
-        res2 = eng.cluster_by_umi(batch)
-    expect = oracle.consensus(batch, genome, opt)
-    assert_results_equal(batch, res, expect, name)
-    assert_results_equal(batch, res2, expect, name + " (second run)")
-
-
-@pytest.mark.parametrize("name,thunk", CASES, ids=[c[0] for c in CASES])
-def test_tiled_vote_matches_oracle(engine_cls, oracle, name, thunk):
-    """vote_tiled_kernel (gcb_set_vote_mode 0: every CTA builds its tile's family-side table itself) on every case."""
-    batch, genome, opt = thunk()
-    with engine_cls(opt, 0) as eng:
-        eng.set_reference(genome)
-        eng.set_vote_mode(0)
+        eng.set_debug(5, 1)
         res = eng.cluster_by_umi(batch)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 
 
 @pytest.mark.parametrize("name,thunk", CASES, ids=[c[0] for c in CASES])
-def test_staged_vote_matches_oracle(engine_cls, oracle, name, thunk):
-    """vote_staged_kernel (gcb_set_vote_mode 2: slow columns decided inside the tile's CTA) on every case."""
+def test_small_tile_window_matches_oracle(engine_cls, oracle, name, thunk):
+    """The vote over 16 KB payload windows (twice the tiles, a deeper ring) on every case."""
     batch, genome, opt = thunk()
     with engine_cls(opt, 0) as eng:
         eng.set_reference(genome)
-        eng.set_vote_mode(2)
-        res = eng.cluster_by_umi(batch)
-    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
-
-
-@pytest.mark.parametrize("name,thunk", CASES, ids=[c[0] for c in CASES])
-def test_split_vote_matches_oracle(engine_cls, oracle, name, thunk):
-    """vote_fast_kernel (gcb_set_vote_mode 3: one CTA per tile, slow columns queued) on every case."""
-    batch, genome, opt = thunk()
-    with engine_cls(opt, 0) as eng:
-        eng.set_reference(genome)
-        eng.set_vote_mode(3)
+        eng.set_debug(2, 14)
         res = eng.cluster_by_umi(batch)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 
 
 @pytest.mark.parametrize("lanes", [8, 16, 32])
 @pytest.mark.parametrize("name", ["cfg2_40k", "cfg4_40k", "edge_default", "ragged_duplex_5_big", "ragged_single_4_big", "deep_1100", "low_complexity",
-                                  "wide_umi_3", "cfg3_40k", "tiny_reads"])
+                                  "wide_umi_3", "cfg3_40k", "tiny_reads", "cfg5_40k"])
 def test_lanes_per_cluster_do_not_change_results(engine_cls, oracle, name, lanes):
     """umi_group_kernel / select_template_kernel with 8, 16 or 32 lanes per cluster."""
     batch, genome, opt = dict(CASES)[name]()
@@ -111,31 +92,7 @@ def test_lanes_per_cluster_do_not_change_results(engine_cls, oracle, name, lanes
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} lanes {lanes}")
 
 
-@pytest.mark.parametrize("qbytes", [1 << 14, 1 << 20])
-@pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "cfg4_40k", "edge_strict"])
-def test_slow_queue_overflow_does_not_change_results(engine_cls, oracle, name, qbytes):
-    """Default vote mode with slow-column queues far too small: what does not fit is decided inside the fast kernel."""
-    batch, genome, opt = dict(CASES)[name]()
-    with engine_cls(opt, 0) as eng:
-        eng.set_reference(genome)
-        eng.set_slow_queue_bytes(qbytes)
-        res = eng.cluster_by_umi(batch)
-    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} queue {qbytes}")
-
-
-@pytest.mark.parametrize("mode,threads", [(2, 128), (3, 192), (4, 768)])
-@pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "cfg4_40k"])
-def test_vote_thread_count_does_not_change_results(engine_cls, oracle, name, mode, threads):
-    batch, genome, opt = dict(CASES)[name]()
-    with engine_cls(opt, 0) as eng:
-        eng.set_reference(genome)
-        eng.set_vote_mode(mode)
-        eng.set_vote_threads(threads)
-        res = eng.cluster_by_umi(batch)
-    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} threads {threads}")
-
-
-@pytest.mark.parametrize("name", ["cfg3_40k", "ragged_duplex_5_big", "deep_1100", "cfg4_40k"])
+@pytest.mark.parametrize("name", ["cfg3_40k", "ragged_duplex_5_big", "deep_1100", "cfg4_40k", "cfg5_40k", "deep50_noisy_40k"])
 @pytest.mark.parametrize("chunk", [1 << 14, 1 << 18, 1 << 21])
 def test_pipeline_chunks_do_not_change_results(engine_cls, oracle, name, chunk):
     batch, genome, opt = dict(CASES)[name]()
@@ -171,40 +128,72 @@ def test_capacity_error_is_reported(engine_cls):
         assert ei.value.code == GCB_ERR_CAPACITY
 
 
-def test_full_size_properties(engine_cls, oracle):
-    """cfg2 at the bench size (1M pairs): properties that need no oracle run, plus an oracle check on a slice."""
+def _oracle_parallel(batch, genome, opt, n_parts):
+    """The oracle over the whole batch, clusters split over host processes (results are per cluster, so the parts concatenate)."""
+    import multiprocessing as mp
+    from gencore_b200.shard import split_batch
+    parts = split_batch(batch, n_parts)
+    with mp.get_context("fork").Pool(min(n_parts, os.cpu_count() or 1)) as pool:
+        return parts, pool.starmap(_oracle_part, [(p, genome, opt) for p in parts])
+
+
+def _oracle_part(part, genome, opt):
+    from oracle.pyoracle import Oracle
+    return Oracle().consensus(part, genome, opt)
+
+
+FULL = [("cfg1", 10_000), ("cfg2", 1_000_000), ("cfg3", 1_000_000), ("cfg4", 1_000_000), ("cfg5", 1_000_000)]
+
+
+@pytest.mark.parametrize("name,n_pairs", FULL, ids=[f"{n}_{p}" for n, p in FULL])
+def test_full_size_matches_oracle(engine_cls, name, n_pairs):
+    """Every BASELINE.json shape at bench size (cfg1 at its own 10 k pairs, the others at the 1 M pairs per GPU that bench.py
+    times): the WHOLE result against the oracle, record for record, plus properties that need no oracle."""
     from gencore_b200 import synth
-    batch, genome, _ = synth.make_fixed_batch(synth.CONFIGS["cfg2"], seed=20261019, n_pairs=1_000_000, with_qnames=False)
-    opt = Options.default()
+    cfg = synth.CONFIGS[name]
+    cfg = dataclasses.replace(cfg, n_contigs=min(cfg.n_contigs, 2), contig_len=min(cfg.contig_len, 20_000_000))
+    batch, genome, _ = synth.make_batch(cfg, seed=20261019, n_pairs=n_pairs, with_qnames=False)
+    opt = Options.default(cluster_size_req=cfg.supporting_reads)
     with engine_cls(opt, 0) as eng:
         eng.set_reference(genome)
         res = eng.cluster_by_umi(batch)
         res2 = eng.cluster_by_umi(batch)
-    # determinism
-    assert np.array_equal(res.groups, res2.groups) and np.array_equal(res.out_payload[:res.out_bytes[0]], res2.out_payload[:res2.out_bytes[0]])
+    n = int(res.out_bytes[0])
+    assert np.array_equal(res.groups, res2.groups) and np.array_equal(res.out_payload[:n], res2.out_payload[:n]), "not deterministic"
     slots = group_slots(batch, res)
     g = res.groups[slots]
-    # every pair is in exactly one family and family sizes add up
     assert (res.pair_group >= 0).all()
-    assert int(g["merge_reads"].sum()) == batch.n_pairs
-    # no UMI pair is a duplex here, every family survives with -s 1
-    assert ((g["status"] == GROUP_SSCS) | (g["status"] == GROUP_DCS)).all()
-    # consensus records tile the output exactly, in order
+    assert int(g["merge_reads"].sum()) == batch.n_pairs, "every pair is in exactly one family"
+    # consensus records tile the output exactly, in slot order
     l = batch.reads["l_qseq"][np.maximum(g["tmpl_read"], 0)].astype(np.int64)
     sz = np.where(g["tmpl_read"] >= 0, ((l + 3) & ~3) + (((l + 1) // 2 + 3) & ~3), 0)
     offs = g["out_off"].reshape(-1)[(g["tmpl_read"] >= 0).reshape(-1)]
     assert np.array_equal(offs, np.concatenate([[0], np.cumsum(sz.reshape(-1)[sz.reshape(-1) > 0])[:-1]]))
-    assert int(res.out_bytes[0]) == int(sz.sum())
-    # consensus of a family whose reads all agree is the template itself (idempotence): vote again over the output
-    # -> checked through the oracle on the first 2000 clusters
-    c1 = 2000
-    p1 = int(batch.cluster_pair_off[c1])
-    from gencore_b200.abi import Batch
-    sub = Batch(batch.cluster_pair_off[:c1 + 1].copy(), batch.cluster_ref[:c1].copy(), batch.cluster_flags[:c1].copy(), batch.umi[:p1].copy(),
-                batch.reads[:2 * p1].copy(), batch.cigar, batch.payload[:int(batch.reads["data_off"][2 * p1])].copy(), None, None, batch.umi_prefix)
-    ref = oracle.consensus(sub, genome, opt)
-    nslots = group_slots(sub, ref)
-    assert np.array_equal(res.cluster_n_groups[:c1], ref.cluster_n_groups)
-    for name in ref.groups.dtype.names:
-        assert np.array_equal(res.groups[nslots][name], ref.groups[nslots][name]), name
-    assert np.array_equal(res.out_payload[:ref.out_bytes[0]], ref.out_payload[:ref.out_bytes[0]])
+    assert n == int(sz.sum())
+    if name == "cfg2":  # no UMI pair is a duplex there, every family survives -s 1
+        assert ((g["status"] == GROUP_SSCS) | (g["status"] == GROUP_DCS)).all()
+    # the whole batch against the oracle (host cores in parallel: clusters are independent)
+    parts, refs = _oracle_parallel(batch, genome, opt, 16)
+    c0 = p0 = 0
+    out0 = 0
+    for part, ref in zip(parts, refs):
+        c1, p1 = c0 + part.n_clusters, p0 + part.n_pairs
+        assert np.array_equal(res.cluster_n_groups[c0:c1], ref.cluster_n_groups), f"{name}: cluster_n_groups of clusters {c0}..{c1}"
+        assert np.array_equal(res.pair_group[p0:p1], ref.pair_group)
+        ps = group_slots(part, ref)
+        mine, theirs = res.groups[ps + p0], ref.groups[ps]
+        for field in theirs.dtype.names:
+            a, b = mine[field], theirs[field]
+            if field in ("tmpl_read", "qname_donor"):
+                b = np.where(b >= 0, b + 2 * p0, b)
+            elif field == "umi_pair":
+                b = np.where(b >= 0, b + p0, b)
+            elif field == "out_off":
+                b = np.where(theirs["tmpl_read"] >= 0, b + out0, b)
+                a = np.where(theirs["tmpl_read"] >= 0, a, b)
+            assert np.array_equal(a, b), f"{name}: groups[{field}] of pairs {p0}..{p1}"
+        nb = int(ref.out_bytes[0])
+        assert np.array_equal(res.out_payload[out0:out0 + nb], ref.out_payload[:nb]), f"{name}: consensus records of clusters {c0}..{c1}"
+        out0 += nb
+        c0, p0 = c1, p1
+    assert out0 == n and p0 == batch.n_pairs
