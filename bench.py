@@ -5,10 +5,12 @@ depth 8"), one process per GPU.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl b200|reference]
 
-A step is one pass of the whole path over one batch (P read pairs per GPU, weak scaling: every rank owns
-its own coordinate window).  `value` is measured with the batch resident in HBM (CUDA events, max over
-ranks); `e2e` goes through gcb_consensus_batch with pinned HOST buffers, copies inside the timed region;
-`roofline` is the score+vote kernel's algorithmic bytes over its own CUDA-event time.
+A pass is the whole path over one batch (P read pairs per GPU, weak scaling: every rank owns its own
+coordinate window); a timed step is `--inner` passes over the resident batch.  `value` is measured with the
+batch resident in HBM (CUDA events, max over ranks); `e2e` goes through gcb_consensus_batch with pinned HOST
+buffers, copies inside the timed region; `roofline` is the vote kernel's algorithmic bytes over its own
+CUDA-event time.  `configs` carries the other BASELINE.json shapes (N = 1), `strong` one input sharded by
+contig over the N GPUs; a window of every timed batch is compared with the oracle after the timed region.
 `--impl reference` times the reference's own Cluster::clusterByUMI (oracle/_ref, the unmodified reference
 sources) on the host cores over a bounded sample of the same workload.
 """
@@ -178,13 +180,158 @@ def algorithmic_bytes(batch, res):
     return {"reads_in": reads_in, "consensus_out": out, "reference_in": ref, "total": reads_in + out + ref}
 
 
+STAGE_NAMES = ["umi_group", "select_template+scan", "tile_prep", "score_vote", "rollback+generic", "duplex"]
+VOTE_KERNEL = "vote_ring_kernel"
+
+
+class ShapeRun:
+    """One batch of one shape resident on one GPU: device-timed passes (CUDA events on the launching stream, per stage),
+    end-to-end passes through gcb_consensus_batch with pinned host buffers, and an oracle check of a window of the batch."""
+
+    def __init__(self, eng, torch, dev, batch, genome):
+        from gencore_b200.abi import (STAGE_DUPLEX, STAGE_SELECT_TEMPLATE, STAGE_UMI_GROUP, STAGE_VOTE_FAST_ONLY, STAGE_VOTE_PREP_ONLY,
+                                      STAGE_VOTE_REST_ONLY)
+        from gencore_b200.device import DeviceBatch, DeviceResult
+        self.eng, self.torch, self.dev, self.batch, self.genome = eng, torch, dev, batch, genome
+        self.db = DeviceBatch.from_host(batch, dev)
+        self.cap = len(batch.payload) // 4 + 4096 if batch.n_pairs >= 100_000 else len(batch.payload)
+        self.dr = DeviceResult.allocate(batch.n_pairs, batch.n_clusters, self.cap, dev)
+        # the kernels are launched on this (non-default) stream and the CUDA events are recorded on it
+        self.tstream = torch.cuda.Stream(device=dev)
+        assert self.tstream.cuda_stream != 0
+        # the vote is timed in its three parts: per-tile preparation, the ring kernel, rollback + the generic kernel's tiles
+        self.stages = [STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_VOTE_PREP_ONLY, STAGE_VOTE_FAST_ONLY, STAGE_VOTE_REST_ONLY, STAGE_DUPLEX]
+        torch.cuda.synchronize()
+
+    def one_pass(self, events=None):
+        for k, st in enumerate(self.stages):
+            if events is not None:
+                events[k].record(self.tstream)
+            self.eng.cluster_by_umi_device(self.db.struct, self.dr.struct, st, self.tstream.cuda_stream)
+        if events is not None:
+            events[len(self.stages)].record(self.tstream)
+
+    def warm(self, n):
+        for _ in range(max(n, 3)):
+            self.one_pass()
+        self.torch.cuda.synchronize()
+        assert self.eng.batch_status() == 0, "device error flag raised during warm-up"
+        self.res_host = self.dr.to_host()
+        self.alg = algorithmic_bytes(self.batch, self.res_host)
+
+    def timed(self, steps, inner, barrier):
+        """steps x inner passes between two events; returns (total ms, per-pass stage ms)."""
+        torch = self.torch
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(self.stages) + 1)] for _ in range(steps * inner)]
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(self.tstream)
+        for k in range(steps * inner):
+            self.one_pass(evs[k])
+        t1.record(self.tstream)
+        barrier()
+        stage_ms = np.zeros(len(self.stages))
+        for e in evs:
+            for q in range(len(self.stages)):
+                stage_ms[q] += e[q].elapsed_time(e[q + 1])
+        return t0.elapsed_time(t1), stage_ms / (steps * inner)
+
+    def e2e(self, steps, barrier):
+        """seconds per call of gcb_consensus_batch: pinned host buffers in, results back on the host."""
+        from gencore_b200.device import pinned_copy, pinned_result
+        self.pb = pinned_copy(self.batch)
+        self.pr = pinned_result(self.batch, self.cap)
+        for _ in range(2):
+            self.eng.cluster_by_umi(self.pb, self.pr)
+        barrier()
+        t = time.perf_counter()
+        for _ in range(steps):
+            self.eng.cluster_by_umi(self.pb, self.pr)
+        barrier()
+        sec = (time.perf_counter() - t) / steps
+        assert np.array_equal(self.pr.groups, self.res_host.groups), "host-buffer path and device-buffer path disagree"
+        b = self.batch
+        self.h2d = sum(int(np.ascontiguousarray(getattr(b, n)).nbytes) for n in ("cluster_pair_off", "cluster_ref", "cluster_flags", "umi", "reads", "cigar", "payload"))
+        self.d2h = int(self.pr.pair_group.nbytes + self.pr.cluster_n_groups.nbytes + self.pr.groups.nbytes + 8 + 4 + int(self.pr.out_bytes[0]))
+        return sec
+
+    def check_window(self, opt, n_clusters=3000):
+        """After the timed region: a window of the timed batch against the oracle, bit for bit (the checker, never the thing measured)."""
+        from gencore_b200.shard import slice_batch
+        from gencore_b200.verify import assert_window_equal
+        from oracle.pyoracle import Oracle
+        b = self.batch
+        c0 = max(0, b.n_clusters // 2 - n_clusters // 2)
+        c1 = min(b.n_clusters, c0 + n_clusters)
+        part = slice_batch(b, c0, c1)
+        ref = Oracle().consensus(part, self.genome, opt)
+        assert_window_equal(self.res_host, part, ref, c0, int(b.cluster_pair_off[c0]), "bench window")
+        return {"clusters": [int(c0), int(c1)], "pairs": int(part.n_pairs), "equal_to_oracle": True}
+
+    def roofline(self, stage_ms, peak):
+        vote_ms = float(stage_ms[3])
+        whole_ms = float(stage_ms[2] + stage_ms[3] + stage_ms[4])
+        return vote_ms, whole_ms, self.alg["total"] / (vote_ms * 1e-3) / 1e9 / peak, self.alg["total"] / (whole_ms * 1e-3) / 1e9 / peak
+
+    def free(self):
+        self.db = self.dr = self.pb = self.pr = None
+
+
+def strong_scaling_leg(args, eng, torch, dist, dev, rank, world, barrier):
+    """ONE input sharded by contig.  The cfg3 shape (duplex UMIs, depth 20) on 16 contigs, contig c generated from its
+    own seed; rank r owns contigs [16r/N, 16(r+1)/N) and sends each through gcb_consensus_batch (host buffers).  Total work is fixed,
+    so value(N) / value(1) is the strong-scaling curve; the digest over every contig's result must be the same for every N."""
+    import hashlib
+    from gencore_b200 import synth
+    from gencore_b200.abi import Options
+    from gencore_b200.device import pinned_copy, pinned_result
+    NC = 16
+    cfg = dataclasses.replace(synth.CONFIGS["cfg3"], n_contigs=1, contig_len=10_000_000)
+    per = args.strong_pairs // NC
+    mine = [c for c in range(NC) if c * world // NC == rank]
+    opt = Options.default()
+    digests, items = {}, []
+    for c in mine:
+        batch, genome, _ = synth.make_batch(cfg, seed=SEED + 31 * (c + 1), n_pairs=per, with_qnames=False)
+        items.append((c, pinned_copy(batch), pinned_result(batch, len(batch.payload) // 4 + 4096), genome))
+    # every contig's reference slice is set right before its batch (a sharded run keeps only its own contigs' reference on the device)
+    def run_all():
+        for c, pb, pr, genome in items:
+            eng.set_reference(genome)
+            eng.cluster_by_umi(pb, pr)
+    run_all()
+    barrier()
+    t = time.perf_counter()
+    for _ in range(args.strong_steps):
+        run_all()
+    barrier()
+    sec = (time.perf_counter() - t) / args.strong_steps
+    for c, pb, pr, genome in items:
+        n = int(pr.out_bytes[0])
+        h = hashlib.sha256()
+        h.update(pr.cluster_n_groups.tobytes()); h.update(pr.pair_group.tobytes()); h.update(pr.groups.tobytes()); h.update(pr.out_payload[:n].tobytes())
+        digests[c] = h.hexdigest()
+    if world > 1:
+        tt = torch.tensor([sec], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec = float(tt.item())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, digests)
+        digests = {k: v for d in gathered for k, v in d.items()}
+    h = hashlib.sha256()
+    for c in range(NC):
+        h.update(digests[c].encode())
+    return {"workload": "cfg3 shape (2x150, duplex UMI, depth 20), %d pairs on %d contigs, sharded by contig; every contig through "
+                        "gcb_consensus_batch with host buffers" % (per * NC, NC),
+            "scaling": "strong", "pairs": per * NC, "contigs_per_rank": len(mine), "ms": 1000 * sec, "value": per * NC / sec, "unit": UNIT,
+            "result_sha256": h.hexdigest(), "steps": args.strong_steps}
+
+
 def b200_arm(args):
     import torch
     import torch.distributed as dist
     from gencore_b200 import synth
-    from gencore_b200.abi import (STAGE_DUPLEX, STAGE_SELECT_TEMPLATE, STAGE_UMI_GROUP, STAGE_VOTE_FAST_ONLY, STAGE_VOTE_PREP_ONLY,
-                                  STAGE_VOTE_REST_ONLY, Options)
-    from gencore_b200.device import DeviceBatch, DeviceResult, pinned_copy, pinned_result
+    from gencore_b200.abi import Options
     from gencore_b200.engine import ConsensusEngine
 
     rank = int(os.environ.get("RANK", "0"))
@@ -210,7 +357,7 @@ def b200_arm(args):
     contigs, genome = synth.random_genome(grng, [cfg.contig_len] * cfg.n_contigs)
     batch, _, _ = synth.make_batch(cfg, seed=SEED + 104729 * rank, n_pairs=args.pairs, with_qnames=False, genome_cache=(contigs, genome))
     del contigs
-    opt = Options.default()
+    opt = Options.default(cluster_size_req=cfg.supporting_reads)
     eng = ConsensusEngine(opt, local)
     if args.window_shift:
         eng.set_debug(2, args.window_shift)
@@ -222,137 +369,120 @@ def b200_arm(args):
         dist.broadcast(g_dev, src=0)
     eng.set_reference_device(g_dev.data_ptr(), g_dev.numel(), genome.contig_off, genome.contig_len, keepalive=g_dev)
 
-    db = DeviceBatch.from_host(batch, dev)
-    dr = DeviceResult.allocate(batch.n_pairs, batch.n_clusters, len(batch.payload) // 4 + 4096, dev)
-    # the kernels are launched on this (non-default) stream and the CUDA events are recorded on it
-    tstream = torch.cuda.Stream(device=dev)
-    stream = tstream.cuda_stream
-    assert stream != 0
-    torch.cuda.synchronize()
-    # the vote is timed in its three parts: per-tile preparation, the ring kernel, rollback + the generic kernel's tiles
-    stages = [STAGE_UMI_GROUP, STAGE_SELECT_TEMPLATE, STAGE_VOTE_PREP_ONLY, STAGE_VOTE_FAST_ONLY, STAGE_VOTE_REST_ONLY, STAGE_DUPLEX]
-    names = ["umi_group", "select_template+scan", "tile_prep", "score_vote", "rollback+generic", "duplex"]
-    i_vote = names.index("score_vote")
-    vote_kernel = "vote_ring_kernel"
-    vote_parts = [k for k, n in enumerate(names) if n in ("tile_prep", "score_vote", "rollback+generic")]
-    def step(events=None):
-        for k, st in enumerate(stages):
-            if events is not None:
-                events[k].record(tstream)
-            eng.cluster_by_umi_device(db.struct, dr.struct, st, stream)
-        if events is not None:
-            events[len(stages)].record(tstream)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    assert eng.batch_status() == 0, "device error flag raised during warm-up"
-    res_host = dr.to_host()
-    alg = algorithmic_bytes(batch, res_host)
-
+    run = ShapeRun(eng, torch, dev, batch, genome)
+    run.warm(args.warmup)
     sampler = ClockSampler(local) if rank == 0 else None
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(args.steps)]
     launches0 = eng.launches
-    barrier()
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record(tstream)
-    for k in range(args.steps):
-        step(evs[k])
-    t_end.record(tstream)
-    barrier()
+    total_ms, stage_ms = run.timed(args.steps, args.inner, barrier)
     launches = eng.launches - launches0
-    total_ms = t_start.elapsed_time(t_end)
-    stage_ms = np.zeros(len(stages))
-    for k in range(args.steps):
-        for s in range(len(stages)):
-            stage_ms[s] += evs[k][s].elapsed_time(evs[k][s + 1])
-    stage_ms /= args.steps
+    clocks = sampler.stop() if sampler else None
     if world > 1:
         tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
     ms_per_step = total_ms / args.steps
-    value = args.pairs * world / (ms_per_step / 1000.0)
+    pairs_per_step = args.pairs * args.inner
+    value = pairs_per_step * world / (ms_per_step / 1000.0)
 
-    # ---- end to end: host buffers through the C ABI, H2D/D2H inside the timed region
-    pb = pinned_copy(batch)
-    pr = pinned_result(batch, len(batch.payload) // 4 + 4096)
-    for _ in range(2):
-        eng.cluster_by_umi(pb, pr)
-    barrier()
+    # ---- end to end: host buffers through the C ABI, H2D/D2H inside the timed region (one batch per step)
+    sampler = ClockSampler(local) if rank == 0 else None
+    e2e_s = run.e2e(max(3, args.steps), barrier)
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    clocks_e2e = sampler.stop() if sampler else None
     if args.host_sweep and rank == 0:  # tuning aid: end-to-end time by kind of host memory for the batch, to stderr
+        from gencore_b200.device import pinned_copy
         for label, kw in (("torch pinned", None), ("gcb_host_alloc", dict(lib=eng.lib)), ("gcb_host_alloc write-combined", dict(lib=eng.lib, write_combined=True))):
-            pbx = pb if kw is None else pinned_copy(batch, **kw)
+            pbx = run.pb if kw is None else pinned_copy(batch, **kw)
             for _ in range(2):
-                eng.cluster_by_umi(pbx, pr)
+                eng.cluster_by_umi(pbx, run.pr)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(5):
-                eng.cluster_by_umi(pbx, pr)
+                eng.cluster_by_umi(pbx, run.pr)
             torch.cuda.synchronize()
             sys.stderr.write("host sweep %s: %.3f ms per step\n" % (label, (time.perf_counter() - t0) / 5 * 1e3))
             del pbx
     if args.chunk_sweep and rank == 0:  # tuning aid: end-to-end time by pipeline chunk size, to stderr
         for mb in [int(x) for x in args.chunk_sweep.split(",")]:
             eng.set_chunk_bytes(mb << 20)
-            eng.cluster_by_umi(pb, pr)
+            eng.cluster_by_umi(run.pb, run.pr)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(5):
-                eng.cluster_by_umi(pb, pr)
+                eng.cluster_by_umi(run.pb, run.pr)
             torch.cuda.synchronize()
             sys.stderr.write("chunk sweep %d MB: %.3f ms per step\n" % (mb, (time.perf_counter() - t0) / 5 * 1e3))
         eng.set_chunk_bytes(48 << 20)
-    t0 = time.perf_counter()
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(e2e_steps):
-        eng.cluster_by_umi(pb, pr)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    clocks = sampler.stop() if sampler else None
-    h2d = sum(int(np.ascontiguousarray(getattr(batch, n)).nbytes) for n in ("cluster_pair_off", "cluster_ref", "cluster_flags", "umi", "reads", "cigar", "payload"))
-    d2h = int(pr.pair_group.nbytes + pr.cluster_n_groups.nbytes + pr.groups.nbytes + 8 + 4 + int(pr.out_bytes[0]))
-    assert np.array_equal(pr.groups, res_host.groups), "host-buffer path and device-buffer path disagree"
+    parity = run.check_window(opt) if rank == 0 else None
 
     # final gather of per-rank Stats: all counters are additive
     from gencore_b200.hoststats import stats_from_result
-    st = stats_from_result(batch, res_host)
+    st = stats_from_result(batch, run.res_host)
     stats_vec = torch.tensor([st.pre_cluster, st.pre_molecule, st.post_sscs, st.post_dcs], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(stats_vec)
+    peak, peak_src = peaks()
+    vote_ms, whole_ms, frac, whole_frac = run.roofline(stage_ms, peak)
+    alg, h2d, d2h, n_clusters, payload_mb = run.alg, run.h2d, run.d2h, batch.n_clusters, len(batch.payload) >> 20
+    run.free()
+    del run, batch
+
+    # ---- the other shapes of BASELINE.json, one GPU each: cfg1 at its own size, cfg3-cfg5 as one GPU's share (N = 1 runs only)
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = {}
+        for name in ("cfg1", "cfg3", "cfg4", "cfg5"):
+            c = synth.CONFIGS[name]
+            n_pairs = min(c.n_pairs, args.pairs)
+            c = dataclasses.replace(c, n_contigs=min(c.n_contigs, 2), contig_len=min(c.contig_len, 20_000_000))
+            b2, g2, _ = synth.make_batch(c, seed=SEED + 17, n_pairs=n_pairs, with_qnames=False)
+            o2 = Options.default(cluster_size_req=c.supporting_reads)
+            with ConsensusEngine(o2, local) as e2:
+                e2.set_reference(g2)
+                r2 = ShapeRun(e2, torch, dev, b2, g2)
+                r2.warm(3)
+                inner2 = 4 if n_pairs >= 100_000 else 64
+                tot, sms = r2.timed(5, inner2, barrier)
+                sec = r2.e2e(5, barrier)
+                vms, wms, fr, wfr = r2.roofline(sms, peak)
+                configs[name] = {"pairs": n_pairs, "clusters": b2.n_clusters, "max_cluster_kb": b2.max_cluster_bytes() >> 10, "options": "-s %d" % c.supporting_reads,
+                                 "value": n_pairs * 5 * inner2 / (tot * 1e-3), "e2e": n_pairs / sec, "unit": UNIT,
+                                 "stage_ms": {n: float(v) for n, v in zip(STAGE_NAMES, sms)},
+                                 "roofline_frac": fr, "whole_vote_frac": wfr, "algorithmic_bytes": r2.alg["total"],
+                                 "parity": r2.check_window(o2)}
+                r2.free()
+            del b2, g2, r2
+    strong = strong_scaling_leg(args, eng, torch, dist, dev, rank, world, barrier) if not args.no_strong else None
 
     if rank == 0:
-        peak, peak_src = peaks()
-        vote_ms = float(stage_ms[i_vote])
-        whole_ms = float(sum(stage_ms[k] for k in vote_parts))
-        # the dominant kernel reads every read's bases and qualities, the reference bases of its slow columns, and writes every
-        # consensus record: the whole of SURVEY 8(d)'s algorithmic bytes
-        own = dict(alg)
-        achieved = own["total"] / (vote_ms * 1e-3) / 1e9
-        whole = alg["total"] / (whole_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": args.pairs, "clusters_per_gpu": batch.n_clusters,
-                       "l2": "inputs larger than L2 (payload %d MB per step)" % (len(batch.payload) >> 20),
-                       "stage_ms": {n: float(v) for n, v in zip(names, stage_ms)},
-                       "stats": {"clusters": int(stats_vec[0]), "molecules": int(stats_vec[1]), "sscs": int(stats_vec[2]), "dcs": int(stats_vec[3])}},
-            "roofline": {"bound": "hbm", "kernel": vote_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": args.traffic if args.traffic is not None else (measured_traffic(vote_kernel) if args.pairs == 1_000_000 else None),
-                         "algorithmic_bytes": own, "kernel_ms": vote_ms,
-                         "timed": "CUDA events around the launch of %s on the launching stream" % vote_kernel,
-                         "whole_vote": {"kernels": "every launch of the vote (tile preparation, %s, slow columns, rollback, generic)" % vote_kernel,
-                                        "ms": whole_ms, "algorithmic_bytes": alg["total"], "achieved": whole, "frac": whole / peak}},
-            "e2e": {"value": args.pairs * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * e2e_s},
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": args.pairs, "passes_per_step": args.inner, "pairs_per_step_per_gpu": pairs_per_step,
+                       "clusters_per_gpu": n_clusters,
+                       "l2": "inputs larger than L2 (payload %d MB per pass)" % payload_mb,
+                       "stage_ms_per_pass": {n: float(v) for n, v in zip(STAGE_NAMES, stage_ms)},
+                       "stats": {"clusters": int(stats_vec[0]), "molecules": int(stats_vec[1]), "sscs": int(stats_vec[2]), "dcs": int(stats_vec[3])},
+                       "parity": parity},
+            "roofline": {"bound": "hbm", "kernel": VOTE_KERNEL, "achieved": frac * peak, "peak": peak, "unit": "GB/s", "frac": frac,
+                         "peak_source": peak_src, "traffic": args.traffic if args.traffic is not None else (measured_traffic(VOTE_KERNEL) if args.pairs == 1_000_000 else None),
+                         "algorithmic_bytes": alg, "kernel_ms": vote_ms,
+                         "timed": "CUDA events around every launch of %s on the launching stream, mean over the timed region" % VOTE_KERNEL,
+                         "whole_vote": {"kernels": "every launch of the vote (tile_prep2_kernel, %s, vote_rollback_kernel, score_vote_kernel)" % VOTE_KERNEL,
+                                        "ms": whole_ms, "algorithmic_bytes": alg["total"], "achieved": whole_frac * peak, "frac": whole_frac}},
+            "e2e": {"value": args.pairs * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * e2e_s,
+                    "pairs_per_step_per_gpu": args.pairs, "steps": max(3, args.steps)},
             "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": clocks, "clocks_e2e": clocks_e2e,
         }
+        if configs is not None:
+            line["configs"] = configs
+        if strong is not None:
+            line["strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
             kind, pairs, per_rep = run_reference_sample(args.cpu_pairs, 1, args.cpu_reps)
             line["cpu_baseline"] = {"value": pairs / float(np.mean(per_rep)), "unit": UNIT, "cores": 1, "kind": kind,
@@ -369,7 +499,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=1_000_000, help="read pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="read pairs per GPU per pass")
+    ap.add_argument("--inner", type=int, default=32, help="passes over the resident batch per timed step (a pass takes ~0.4 ms: 32 of them make the "
+                                                          "device-timed region of 20 steps a quarter of a second, long enough for the clock sampler)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (cfg1, cfg3, cfg4, cfg5 on one GPU)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (`strong`)")
+    ap.add_argument("--strong-pairs", type=int, default=4_000_000, help="strong-scaling leg: pairs of the one sharded input")
+    ap.add_argument("--strong-steps", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--ref-pairs-per-core", type=int, default=50_000, help="reference arm: pairs per step on each host core")
     ap.add_argument("--cpu-pairs", type=int, default=400_000, help="cpu_baseline sample size (one core)")

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -334,6 +335,7 @@ bool read_record(BgzfReader &in, Rec &r) {
     r.mpos = (int32_t)le32(&d[24]);
     r.isize = (int32_t)le32(&d[28]);
     size_t off = 32;
+    if (r.l_seq < 0) die("corrupt BAM record");  // (a negative length would wrap the size check below)
     if (off + l_name + 4 * n_cig + (size_t)(r.l_seq + 1) / 2 + (size_t)r.l_seq > block) die("corrupt BAM record");
     r.qname.assign((const char *)&d[off], l_name ? strnlen((const char *)&d[off], l_name) : 0);
     off += l_name;
@@ -749,8 +751,12 @@ void Pipeline::run_and_replay() {
                         payload.resize((payload.size() + 3) & ~(size_t)3, 0);
                         // the UMI comes from the MI:Z tag when there is one, else from the name (bamutil.cpp:23-38)
                         const uint8_t *mi = aux_find(r->aux, "MI");
-                        if (mi && (*mi == 'Z' || *mi == 'H')) names.append((const char *)mi + 1);
-                        else names.append(r->qname);
+                        if (mi && (*mi == 'Z' || *mi == 'H')) {  // (the value ends at its NUL or at the end of the aux block)
+                            const char *v = (const char *)mi + 1;
+                            names.append(v, strnlen(v, (size_t)(r->aux.data() + r->aux.size() - (const uint8_t *)v)));
+                        } else {
+                            names.append(r->qname);
+                        }
                     }
                     name_off.push_back((int64_t)names.size());
                     reads.push_back(d);
@@ -962,6 +968,7 @@ void Pipeline::run() {
             continue;
         }
         if (b->flag & (0x100 | 0x800)) continue;  // secondary / supplementary (bamutil.cpp:368-373)
+        if ((size_t)b->tid >= hdr.lens.size() || b->mtid >= (int32_t)hdr.lens.size()) die("corrupt BAM record");  // (contig ids index the header)
         b->serial = serial++;
         add_to_proper_cluster(b);
         b = new Rec();
@@ -999,10 +1006,14 @@ int main(int argc, char **argv) {
     c.opt.high_quality = 30; c.opt.moderate_quality = 20; c.opt.low_quality = 15;
     c.opt.score_high = 8; c.opt.score_moderate = 6; c.opt.score_low = 4; c.opt.score_bad = 2;
     c.opt.skip_low_complexity_cluster_threshold = 1000; c.opt.score_percent_req = 0.8;
-    {
-        std::string self = argv[0];
+    {   // the engine library lies next to the binary's directory: $GENCORE_B200_ENGINE, else relative to /proc/self/exe (argv[0] is
+        // only a name when the binary was found through PATH)
+        const char *env = getenv("GENCORE_B200_ENGINE");
+        char exe[4096];
+        const ssize_t n = readlink("/proc/self/exe", exe, sizeof exe - 1);
+        std::string self = n > 0 ? std::string(exe, (size_t)n) : std::string(argv[0]);
         const size_t slash = self.rfind('/');
-        c.engine = (slash == std::string::npos ? std::string(".") : self.substr(0, slash)) + "/../csrc/libgencore_b200.so";
+        c.engine = env ? std::string(env) : (slash == std::string::npos ? std::string(".") : self.substr(0, slash)) + "/../csrc/libgencore_b200.so";
     }
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];

@@ -16,16 +16,17 @@
 //                     residues of the raw words; uniform families (every fixed-length library) run a branch-free loop.
 //   slow columns      a lane that found slow columns appends ONE list entry (family side, lane, 16-bit column mask) to the
 //                     stage's list.  The warp that finishes the tile's last bundle closes the tile: it turns the list into
-//                     prefix sums of column counts and publishes it; the columns are then decided one THREAD per column,
-//                     32 at a time, straight from the staged slab (three-bin register histogram, group.cpp:376-525) by the
-//                     closing warp and by every warp that would otherwise wait for a tile — batches are grabbed with a
-//                     compare-and-swap on (tile epoch, next column), so a warp may help a tile it has already left.  The
-//                     stage is released when every voter has left it AND its last slow column is decided (`empty` counts
-//                     one arrival more than there are voter warps).
-// Nothing is queued in global memory and no second kernel reads the reads again: a tile's bytes cross HBM once.
+//                     prefix sums (columns, queue words), reserves the tile's records in a global queue with one 64-bit
+//                     atomic and EXTRACTS what the columns need of the tile, one thread per column, 32 columns at a time:
+//                     per read its quality, base, mate quality, mate base and overlap state (k_slow_columns.cuh).  The
+//                     stage is released as soon as that is written; slow_columns_kernel decides the columns afterwards at
+//                     full occupancy.  (Deciding them here, from the staged slab, was measured: the chain of dependent
+//                     loads of a column held every stage for microseconds and the voters starved — profiles/r03_notes.md.)
+//   queue overflow    the tile is handed to the generic kernel (score_vote_kernel), which runs last and rewrites all of the
+//                     tile's records from the payload.
 #pragma once
 
-#include "vote_tile.cuh"
+#include "k_slow_columns.cuh"
 
 namespace gcb {
 
@@ -34,7 +35,6 @@ constexpr int VR_WARPS = VR_THREADS / WARP;
 constexpr int VR_MAX_STAGES = 12;  // tiles in flight (barrier pairs and stage headers); their bytes come from one arena
 constexpr int VR_GUARD = 4608;     // never allocated, after the arena: the branch-free read loop may read a VoteRead table or a
                                    // slab up to 257 entries / 64 bytes past its end (values unused)
-constexpr uint32_t VR_COL_BITS = 20, VR_COL_MASK = (1u << VR_COL_BITS) - 1u;  // drain word: tile epoch << 20 | next column
 
 struct __align__(16) RingStage {  // shared memory; the first part is written by the producer before `full` completes
     int64_t out_base0;
@@ -42,281 +42,34 @@ struct __align__(16) RingStage {  // shared memory; the first part is written by
     int32_t lanes, n_bundles, common_l;
     int32_t p0, tile;
     int32_t ft_off, vr_off, slab_off;  // where the tile's family-side list, VoteRead table and payload slab lie (shared-memory offsets)
-    int32_t sl_off;                    // slow-column list: uint32 entries[sl_cap], then uint32 prefix[sl_cap]
+    int32_t sl_off;                    // slow-column list: uint32 entries[sl_cap], then their inclusive column counts, then their queue words
     int32_t sl_cap;
-    uint32_t epoch;                    // this CTA's tile counter, 12 bits
+    int32_t pad0;
     // the voters' part
     int32_t next_bundle;   // atomic: next bundle to hand out
     int32_t done;          // atomic: bundles finished
     int32_t n_entries;     // atomic: slow-column list entries
-    int32_t drain_total;   // slow columns of the tile (valid once drain_word names column 0)
-    uint32_t drain_word;   // epoch << 20 | next slow column to decide; next = all ones until the tile is closed
-    int32_t cols_done;     // atomic: slow columns decided
-    int32_t pad[2];
+    int32_t pad1;
 };
-static_assert(sizeof(RingStage) == 96, "stage header size");
+static_assert(sizeof(RingStage) == 80, "stage header size");
 
-// shared-memory map: [barriers][help bits][stage headers][producer's header cache][arena]
+// shared-memory map: [barriers][stage headers][producer's header cache][arena]
 constexpr int VR_OFF_FULL = 0;                                   // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MAX_STAGES]
-constexpr int VR_OFF_HELP = 16 * VR_MAX_STAGES;                  // uint32: stages whose slow columns wait for a warp
-constexpr int VR_OFF_HDR = 16 * VR_MAX_STAGES + 16;              // RingStage[VR_MAX_STAGES]
-constexpr int VR_OFF_HCACHE = VR_OFF_HDR + 96 * VR_MAX_STAGES;   // TileHdr2[32]: the producer's next tiles
+constexpr int VR_OFF_HDR = 16 * VR_MAX_STAGES;                   // RingStage[VR_MAX_STAGES]
+constexpr int VR_OFF_HCACHE = VR_OFF_HDR + 80 * VR_MAX_STAGES;   // TileHdr2[32]: the producer's next tiles
 constexpr int VR_OFF_ARENA = (VR_OFF_HCACHE + 48 * WARP + 127) & ~127;
-// a tile's allocation: [FsTile list][VoteRead table][slab + slack][slow-column list + prefix], each part rounded to 128 bytes
+// a tile's allocation: [FsTile list][VoteRead table][slab + slack][slow-column list + two prefix arrays], each part rounded to 128 bytes
 static_assert(VR_OFF_HDR % 16 == 0 && VR_OFF_HCACHE % 16 == 0 && VR_OFF_ARENA % 128 == 0, "ring layout");
 GCB_HD uint32_t ring_round128(uint32_t v) { return (v + 127u) & ~127u; }
 
-struct RingCtx {  // what deciding a slow column needs besides the stage
-    const BatchView *b;
-    const ResultView *r;
-    const GenomeView *gv;
-    const gcb_options *o;
-    RollbackList rb;
-    uint8_t *smem;
-};
-
-// group.cpp:376-525 for one slow column of family side f of the staged tile, by one thread.  For a uniform family side
-// (every voter has the template's length, no column shift, the same overlap window) what pair.cpp:121-170 needs to know
-// about the column — inside the overlap or not, the mate index — is computed once; each read then is its quality byte,
-// its base nibble and, inside the overlap, its mate's, added to a three-bin register histogram.  The two scans of
-// group.cpp:395-417 are a top-2 selection over the three bins and the two largest codes nobody showed (bin_key order).
-__device__ __noinline__ void ring_slow_column(const RingCtx &x, const RingStage *sh, int f, int col) {
-    const gcb_options &o = *x.o;
-    const ScoreTab tab(o);
-    const FsTile ft = ((const FsTile *)(x.smem + sh->ft_off))[f];
-    const uint8_t *cb = x.smem + sh->slab_off + 4 * (int)ft.cbase4;
-    const VoteRead *ents = (const VoteRead *)(x.smem + sh->vr_off) + ft.ent0;
-    const VoteRead tv = ents[ft.tmpl_k];
-    const int side = fs_side(ft);
-    const int qbytes = GCB_ALIGN4(ft.l_out);
-    uint8_t *out = x.r->out_payload + sh->out_base0 + 4 * (int64_t)ft.out4;
-    GCB_COUNT(3, 1);
-    if (col >= (int)ft.len) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
-        int obase = 0, oqual = 0, sc;
-        fetch_ent(cb, tv, col, side, o, obase, oqual, sc);
-        out[col] = (uint8_t)oqual;
-        return;
-    }
-    Bins3 bins;
-    bins.init();
-    const int m = (int)ft.m;
-    if (ft.flags & FS_UNIFORM) {
-        const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
-        const int k = col - (int)tv.ov_own, mp = (int)tv.ov_mate + k;
-        const bool inwin = info && k >= 0 && k < (int)tv.ov_len;
-        const bool mvalid = inwin && mp >= 0 && mp < (int)tv.mate_l;
-        const bool plain = info && !inwin;  // pair.cpp:121-131: outside the overlap the score follows the quality
-        const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
-        const int mpi = mvalid ? mp : 0;
-        const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
-        for (int e = 0; e < m; e++) {
-            const uint32_t w = *(const uint32_t *)(ents + e);  // own_off4 | mate_off4 << 16
-            if ((w & 0xFFFFu) == VR_NO_VOTE) continue;
-            const uint8_t *rec = cb + 4 * (int)(w & 0xFFFFu);
-            int ql = rec[col];
-            const int base = (rec[soff] >> nsh) & 0xF;
-            int score;
-            if (mvalid) {
-                const uint8_t *mrec = cb + 4 * (int)(w >> 16);
-                const int mql = mrec[mpi];
-                const int mbase = (mrec[msoff] >> mnsh) & 0xF;
-                const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
-                const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
-                const int s_match = sc8(tab.q2s((ql + mql) / 2) + 4);                        // pair.cpp:147-152
-                const int s_mis = mine ? sc8(tab.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;  // pair.cpp:153-169
-                score = base == mbase ? s_match : s_mis;
-                ql = base == mbase ? ql : max(0, ql - mql);
-            } else {
-                score = plain ? tab.q2s(ql) : tab.sm;
-            }
-            bins.add(base, ql, score);
-        }
-    } else {
-        for (int e = 0; e < m; e++) {
-            int base, qual, score;
-            if (fetch_vote(cb, ents[e], col, side, tab, base, qual, score)) bins.add(base, qual, score);
-        }
-    }
-    ColumnTop ct;
-    int total = bins.total;
-    uint32_t acgt = 0;  // the best quality of codes 1, 2, 4, 8 in bytes 0..3 (0 when nobody showed the code)
-    if (bins.overflow) {  // a fourth distinct code: the sixteen-bin histogram in local memory (group.cpp:376-417 as written)
-        int32_t h[64];
-        for (int q = 0; q < 64; q++) h[q] = 0;
-        for (int e = 0; e < m; e++) {
-            int base, qual, score;
-            if (!fetch_ent(cb, ents[e], col, side, o, base, qual, score)) continue;
-            h[4 * base]++;
-            h[4 * base + 1] += score;
-            h[4 * base + 2] += qual;
-            h[4 * base + 3] = max(h[4 * base + 3], qual);
-        }
-        VoteBin obs[16];
-        int nobs = 0;
-        total = 0;
-        for (int q = 0; q < 16; q++)
-            if (h[4 * q] > 0) {
-                obs[nobs].base = q; obs[nobs].cnt = h[4 * q]; obs[nobs].score = h[4 * q + 1]; obs[nobs].qual = h[4 * q + 2]; obs[nobs].maxq = h[4 * q + 3];
-                total += obs[nobs].score;
-                nobs++;
-            }
-        ct = column_top(o, obs, nobs, total);
-        acgt = (uint32_t)(h[4 * 1] > 0 ? h[4 * 1 + 3] : 0) | ((uint32_t)(h[4 * 2] > 0 ? h[4 * 2 + 3] : 0) << 8) |
-               ((uint32_t)(h[4 * 4] > 0 ? h[4 * 4 + 3] : 0) << 16) | ((uint32_t)(h[4 * 8] > 0 ? h[4 * 8 + 3] : 0) << 24);
-    } else {
-        // top and second: every bin competes with its (score, quality sum, code) key; the codes nobody showed compete
-        // with (0, 0, code), of which only the two largest can place
-        unsigned freemask = 0xFFFFu;
-        unsigned long long key[3];
-#pragma unroll
-        for (int kk = 0; kk < 3; kk++) {
-            const VoteBin vb = bins.bin(kk);
-            const int bb = vb.base;
-            const bool have = bb >= 0;
-            key[kk] = have ? bin_key(vb.score, vb.qual, bb) : 0ull;
-            if (have) freemask &= ~(1u << bb);
-            if (have && (bb == 1 || bb == 2 || bb == 4 || bb == 8)) acgt |= (uint32_t)vb.maxq << (bb == 1 ? 0 : bb == 2 ? 8 : bb == 4 ? 16 : 24);
-        }
-        const int e1 = 31 - __clz((int)freemask);
-        freemask &= ~(1u << e1);
-        const int e2 = 31 - __clz((int)freemask);
-        const unsigned long long ke1 = bin_key(0, 0, e1), ke2 = bin_key(0, 0, e2);
-        unsigned long long top = max_u64(key[0], key[1]), sec = min_u64(key[0], key[1]);
-        sec = max_u64(sec, min_u64(top, key[2])); top = max_u64(top, key[2]);
-        sec = max_u64(sec, min_u64(top, ke1)); top = max_u64(top, ke1);
-        sec = max_u64(sec, min_u64(top, ke2)); top = max_u64(top, ke2);
-        const int tb = (int)(top & 0xF), sb = (int)(sec & 0xF);
-        const VoteBin none = {0, 0, 0, 0, 0};
-        ct.top = bins.b0 == tb ? bins.bin(0) : bins.b1 == tb ? bins.bin(1) : bins.b2 == tb ? bins.bin(2) : none;
-        ct.sec = bins.b0 == sb ? bins.bin(0) : bins.b1 == sb ? bins.bin(1) : bins.b2 == sb ? bins.bin(2) : none;
-        ct.top.base = tb;
-        ct.sec.base = sb;
-        column_rules(o, ct, total);
-    }
-    int new_qual;
-    if (ct.fast) {
-        new_qual = ct.top.maxq;  // group.cpp:422-426: the base is NOT written
-    } else {
-        // the record's base before the vote: the template's own (pair.cpp rewrites qualities, never bases)
-        const int obase = base_at(cb + 4 * (int)tv.own_off4 + qbytes, col);
-        int ref4 = 0;
-        if (ft.flags & FS_REF_OK) {  // group.cpp:430-439
-            int refpos = col;
-            if (!(ft.flags & FS_SIMPLE_CIGAR)) {
-                const gcb_read_desc od = x.b->reads[x.r->groups[ft.slot].tmpl_read[side]];
-                refpos = get_ref_offset(x.b->cigar + od.cigar_off, od.n_cigar, col);
-            }
-            const int64_t nib = ft.ref_nib0 + refpos;
-            if (refpos >= 0 && nib >= 0 && (nib >> 1) < x.gv->packed_bytes) {  // the bound only guards malformed CIGARs
-                const uint8_t two = x.gv->packed4[nib >> 1];
-                ref4 = genome_nibble_to_bam((nib & 1) ? (two >> 4) : (two & 0xF));
-            }
-        }
-        int rbq = 0;
-        bool any_high = false;
-        if (ct.need_ref && ref4 != 0) {
-            const int rmax = (int)((acgt >> (ref4 == 1 ? 0 : ref4 == 2 ? 8 : ref4 == 4 ? 16 : 24)) & 0xFFu);
-            if (rmax >= 128) {  // `char refBaseQual` wraps: the scan order matters (group.cpp:474-490): template first
-                int tb, tq, ts;
-                if (fetch_ent(cb, tv, col, side, o, tb, tq, ts) && tb == ref4) {
-                    if (tq > rbq) rbq = sc8(tq);
-                    if (tq >= o.high_quality) any_high = true;
-                }
-                for (int e = 0; e < m; e++) {
-                    int base, qual, score;
-                    if (e == ft.tmpl_k || !fetch_ent(cb, ents[e], col, side, o, base, qual, score) || base != ref4) continue;
-                    if (qual > rbq) rbq = sc8(qual);
-                    if (qual >= o.high_quality) any_high = true;
-                }
-            } else {
-                rbq = rmax;
-                any_high = rmax >= o.high_quality;
-            }
-        }
-        const ColumnOut co = column_arbitrate(o, ct, ref4, rbq, any_high);
-        if (obase != co.base) {  // group.cpp:509-524
-            int d_mm = 0;
-            if (ref4 != 0) {
-                if (obase == ref4) d_mm = 1;
-                else if (co.base == ref4) d_mm = -1;
-            }
-            gcb_group_result *gr = x.r->groups + ft.slot;  // (the bundle's lane 0 zeroed both counters before the tile was closed)
-            atomicAdd(&gr->diff[side], 1);
-            if (d_mm != 0) {
-                const int before = atomicAdd(&gr->mismatch_inc[side], d_mm);
-                if (d_mm > 0 && before == 5) {  // more than five new mismatches so far: vote_rollback_kernel looks at the final count
-                    const int kk = atomicAdd(x.rb.count, 1);
-                    if (kk < x.rb.cap) x.rb.list[kk] = 2 * ft.slot + side;
-                }
-            }
-            const int byte = col >> 1;
-            const unsigned delta = ((unsigned)(obase ^ co.base) & 0xFu) << ((col & 1) ? 0 : 4);
-            atomicXor((unsigned *)(out + qbytes + (byte & ~3)), delta << (8 * (byte & 3)));
-        }
-        new_qual = co.qual;
-    }
-    out[col] = (uint8_t)new_qual;
-}
-
-// Up to 32 slow columns of stage `s` at a time, one thread per column, until none is left to grab.  Whoever decides the
-// tile's last column makes the drain's arrival on the stage's `empty` barrier.
-GCB_DEV void ring_drain(const RingCtx &x, RingStage *shdr, uint64_t *empty, int s, int lane, bool helping) {
-    RingStage *sh = shdr + s;
-    uint32_t *help = (uint32_t *)(x.smem + VR_OFF_HELP);
-    for (;;) {
-        int got = -1, total = 0;
-        if (lane == 0) {
-            const uint32_t w = *(volatile uint32_t *)&sh->drain_word;
-            total = *(volatile int32_t *)&sh->drain_total;
-            const uint32_t c = w & VR_COL_MASK;
-            if ((int64_t)c < (int64_t)total) {
-                got = atomicCAS(&sh->drain_word, w, w + 32u) == w ? (int)c : -2;
-                if (got >= 0 && got + 32 >= total) atomicAnd(help, ~(1u << s));  // the tile's last batch is taken
-            }
-        }
-        got = __shfl_sync(FULL, got, 0);
-        if (got == -2) continue;  // another warp was faster: look again
-        if (got < 0) return;
-        total = __shfl_sync(FULL, total, 0);
-        __threadfence_block();
-        const int idx = got + lane;
-        if (idx < total) {
-            const uint32_t *sl = (const uint32_t *)(x.smem + sh->sl_off);
-            const uint32_t *pf = sl + sh->sl_cap;
-            int lo = 0, hi = *(volatile int32_t *)&sh->n_entries - 1;
-            while (lo < hi) {  // the first entry whose inclusive column count exceeds idx
-                const int mid = (lo + hi) >> 1;
-                if ((int)pf[mid] > idx) hi = mid;
-                else lo = mid + 1;
-            }
-            const uint32_t code = sl[lo];
-            uint32_t mask = code & 0xFFFFu;
-            int rank = idx - ((int)pf[lo] - __popc(mask));
-            while (rank-- > 0) mask &= mask - 1u;
-            const int bit = __ffs((int)mask) - 1;  // bit 8 * w + i of the mask = column 8 * w + 7 - i of the lane's sixteen
-            const int col = VT_CHUNK * (int)((code >> 16) & 31u) + (bit & 8) + 7 - (bit & 7);
-            ring_slow_column(x, sh, (int)(code >> 21), col);
-            if (helping) GCB_COUNT(6, 1);
-        }
-        __syncwarp();
-        if (lane == 0) {
-            const int n = min(32, total - got);
-            __threadfence_block();
-            if (atomicAdd(&sh->cols_done, n) + n == total) pipe_arrive(empty + s);
-        }
-        pipe_progress();
-    }
-}
-
-__global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o, int32_t implied,
-                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, RollbackList rb, int32_t n_tiles,
+__global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, int32_t moderate_quality, int32_t implied,
+                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, int32_t n_tiles,
                                                                    int32_t arena_bytes, const int32_t *max_need) {
     GCB_DYN_SMEM(smem);
     uint64_t *full = (uint64_t *)(smem + VR_OFF_FULL);
     uint64_t *empty = (uint64_t *)(smem + VR_OFF_EMPTY);
     RingStage *shdr = (RingStage *)(smem + VR_OFF_HDR);
-    uint32_t *help = (uint32_t *)(smem + VR_OFF_HELP);
 #define GCB_LDS32(off) (*(const uint32_t *)(smem + (off)))
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
     // the arena is cut into equal stages that hold the batch's largest tile (tile_prep2_kernel measured it): as many tiles in
@@ -326,9 +79,8 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
             pipe_init(full + s, 1);
-            pipe_init(empty + s, VR_WARPS);  // every voter warp arrives once when it leaves the stage's tile, the drain once
+            pipe_init(empty + s, VR_WARPS - 1);  // every voter warp arrives once when it leaves the stage's tile
         }
-        *help = 0u;
         pipe_fence_init();
     }
     __syncthreads();
@@ -338,7 +90,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         // headers of this CTA's next 32 tiles at once, so that no tile waits for a header on its way from global memory
         TileHdr2 *hcache = (TileHdr2 *)(smem + VR_OFF_HCACHE);
         int k = 0;
-        // stage k % n_stages once every voter has left the tile it held before and that tile's slow columns are decided
+        // stage k % n_stages once every voter has left the tile it held before
         auto allocate = [&]() -> uint32_t {
             const int s = k % n_stages, use = k / n_stages;
             GCB_TRACE(200 + s);
@@ -359,14 +111,11 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             sh.slab_off = sh.vr_off + (int32_t)ring_round128(vr_bytes);
             sh.sl_off = sh.slab_off + (int32_t)ring_round128((uint32_t)cur.slab_bytes + VT_SLAB_SLACK);
             sh.sl_cap = max(cur.nfs, 0) * cur.lanes;
-            sh.epoch = (uint32_t)k & 0xFFFu;
+            sh.pad0 = 0;
             sh.next_bundle = 0;
             sh.done = 0;
             sh.n_entries = 0;
-            sh.drain_total = 0;
-            sh.drain_word = (sh.epoch << VR_COL_BITS) | VR_COL_MASK;
-            sh.cols_done = 0;
-            sh.pad[0] = sh.pad[1] = 0;
+            sh.pad1 = 0;
         };
         for (int64_t base = (int64_t)blockIdx.x; base < n_tiles; base += (int64_t)WARP * gridDim.x) {
             const int64_t mine_t = base + (int64_t)lane * gridDim.x;
@@ -410,9 +159,11 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     }
 
     // ---- voters
-    RingCtx x;
-    x.b = &b; x.r = &r; x.gv = &gv; x.o = &o; x.rb = rb; x.smem = smem;
-    const uint32_t mod4 = 0x01010101u * (uint32_t)(o.moderate_quality & 0xFF);
+    const uint32_t mod4 = 0x01010101u * (uint32_t)(moderate_quality & 0xFF);
+    // slow-column records go to the queue of this CTA
+    const int qi = (int)(blockIdx.x % VQ_NQ);
+    uint32_t *q_words = sq.words + (size_t)qi * sq.cap_words;
+    uint32_t *q_index = sq.index + (size_t)qi * sq.cap_recs;
     const uint32_t sbase = smem_base(smem);
     // lane geometry and masks are kept across tiles while the tile shape (lanes per family side, usual record length) stays
     int cur_L = 0, cur_l = -1, S = 32, sub = 0, j = 0, col0 = 0;
@@ -420,16 +171,8 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     int s = 0;
     uint32_t par = 0u;
     for (;;) {
-        // the next tile; while it is on its way the warp decides slow columns of the tiles that wait for hands
-        for (;;) {
-            GCB_TRACE(100 + s);
-            if (__all_sync(FULL, pipe_try_wait(full + s, par, 200u))) break;
-            uint32_t hb = 0u;
-            if (lane == 0) hb = *(volatile uint32_t *)help;
-            hb = __shfl_sync(FULL, hb, 0);
-            if (hb != 0u) ring_drain(x, shdr, empty, __ffs((int)hb) - 1, lane, true);
-            else pipe_relax(100u);
-        }
+        GCB_TRACE(100 + s);
+        pipe_wait(full + s, par, 1000u);
         RingStage *sh = shdr + s;
         const int nfs = sh->nfs;
         if (nfs < 0) break;
@@ -635,35 +378,109 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             } while (bundle < nb);
         }
         if (closer) {
-            // every bundle of the tile is done: prefix sums of the entries' column counts, then the tile's slow columns are
-            // open to every warp of the CTA
+            // every bundle of the tile is done: prefix sums of the entries' column counts and queue words, one reservation,
+            // then one thread per slow column writes the column's record
             __threadfence_block();
             const int n = *(volatile int32_t *)&sh->n_entries;
-            uint32_t *s_list = (uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap;
-            int run = 0;
+            uint32_t *s_list = (uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap, *s_pw = s_pf + sh->sl_cap;
+            const FsTile *s_ft = (const FsTile *)(smem + sh->ft_off);
+            const VoteRead *s_vr = (const VoteRead *)(smem + sh->vr_off);
+            int run = 0, runw = 0;
             for (int base = 0; base < n; base += WARP) {
                 const int i = base + lane;
-                int incl = i < n ? __popc(s_list[i] & 0xFFFFu) : 0;
+                int incl = 0, inclw = 0;
+                if (i < n) {
+                    const uint32_t code = s_list[i];
+                    incl = __popc(code & 0xFFFFu);
+                    inclw = incl * (int)slow_rec_words(s_ft[code >> 21].m);
+                }
                 for (int off = 1; off < WARP; off <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, off);
-                    if (lane >= off) incl += v;
+                    const int v = __shfl_up_sync(FULL, incl, off), vw = __shfl_up_sync(FULL, inclw, off);
+                    if (lane >= off) {
+                        incl += v;
+                        inclw += vw;
+                    }
                 }
-                if (i < n) s_pf[i] = (uint32_t)(run + incl);
+                if (i < n) {
+                    s_pf[i] = (uint32_t)(run + incl);
+                    s_pw[i] = (uint32_t)(runw + inclw);
+                }
                 run += __shfl_sync(FULL, incl, WARP - 1);
+                runw += __shfl_sync(FULL, inclw, WARP - 1);
             }
             __syncwarp();
-            if (lane == 0) {
-                if (run == 0) {
-                    pipe_arrive(empty + s);  // nothing to decide: the drain's arrival
+            if (run > 0) {
+                unsigned long long base64 = 0ull;
+                if (lane == 0) base64 = atomicAdd(sq.count + qi, ((unsigned long long)(uint32_t)run << 32) | (uint32_t)runw);
+                base64 = __shfl_sync(FULL, base64, 0);
+                const uint32_t r0 = (uint32_t)(base64 >> 32), w0 = (uint32_t)base64;
+                if ((unsigned long long)r0 + (uint32_t)run > sq.cap_recs || (unsigned long long)w0 + (uint32_t)runw > sq.cap_words) {
+                    // no queue space: the reserved index entries are marked unused and the generic kernel redoes the whole tile
+                    // from the payload (it runs after slow_columns_kernel and vote_rollback_kernel)
+#ifdef GCB_SIMT_CHECK
+                    if (lane == 0 && getenv("GCB_DBG")) fprintf(stderr, "overflow: r0 %u run %d cap %u w0 %u runw %d capw %u n %d\n", r0, run, sq.cap_recs, w0, runw, sq.cap_words, n);
+#endif
+                    for (uint32_t i = r0 + (uint32_t)lane; i < r0 + (uint32_t)run && i < sq.cap_recs; i += WARP) q_index[i] = VQ_INVALID;
+                    if (lane == 0) {
+                        ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~sh->tile;
+                        GCB_COUNT(1, 1);
+                    }
                 } else {
-                    sh->drain_total = run;
-                    __threadfence_block();
-                    *(volatile uint32_t *)&sh->drain_word = sh->epoch << VR_COL_BITS;
-                    if (run > WARP) atomicOr(help, 1u << s);
+                    const uint8_t *slab = smem + sh->slab_off;
+                    const int64_t out_base0 = sh->out_base0;
+                    for (int c0 = 0; c0 < run; c0 += WARP) {
+                        const int idx = c0 + lane;
+                        if (idx < run) {
+                            int lo = 0, hi = n - 1;
+                            while (lo < hi) {  // the first entry whose inclusive column count exceeds idx
+                                const int mid = (lo + hi) >> 1;
+                                if ((int)s_pf[mid] > idx) hi = mid;
+                                else lo = mid + 1;
+                            }
+                            const uint32_t code = s_list[lo];
+                            uint32_t mask = code & 0xFFFFu;
+                            const int ncol = __popc(mask), rank = idx - ((int)s_pf[lo] - ncol);
+                            for (int q = 0; q < rank; q++) mask &= mask - 1u;
+                            const int bit = __ffs((int)mask) - 1;  // bit 8 * w + i of the mask = column 8 * w + 7 - i of the lane's sixteen
+                            const int col = VT_CHUNK * (int)((code >> 16) & 31u) + (bit & 8) + 7 - (bit & 7);
+                            const FsTile fti = s_ft[code >> 21];
+                            const int mi = (int)fti.m;
+                            const uint32_t rw = slow_rec_words(mi);
+                            const uint32_t wofs = w0 + (s_pw[lo] - (uint32_t)ncol * rw) + (uint32_t)rank * rw;
+                            uint32_t *rec = q_words + wofs;
+                            q_index[r0 + (uint32_t)idx] = wofs;
+                            slow_write_header(rec, fti, col, out_base0 + 4 * (int64_t)fti.out4);
+                            const uint8_t *cbp = slab + 4 * (int)fti.cbase4;
+                            const VoteRead *ents = s_vr + fti.ent0;
+                            if ((fti.flags & FS_UNIFORM) && col < (int)fti.len) {
+                                // the column's place in pair.cpp:121-170 is the same for every read of a uniform family
+                                const VoteRead tvi = ents[fti.tmpl_k];
+                                const bool info = tvi.ov_len != VR_NO_OVERLAP_INFO;
+                                const int kq = col - (int)tvi.ov_own, mp = (int)tvi.ov_mate + kq;
+                                const bool inwin = info && kq >= 0 && kq < (int)tvi.ov_len;
+                                const bool mvalid = inwin && mp >= 0 && mp < (int)tvi.mate_l;
+                                const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
+                                const int soff = GCB_ALIGN4(fti.l_out) + (col >> 1), nsh = (col & 1) ? 0 : 4;
+                                const int mrel = mvalid ? 4 * ((int)tvi.mate_off4 - (int)tvi.own_off4) : 0, mpi = mvalid ? mp : 0;
+                                const int mqoff = mrel + mpi, msoff = mrel + (mvalid ? GCB_ALIGN4(tvi.mate_l) : 0) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
+                                for (int e = 0; e < mi; e++) {
+                                    const uint32_t xo = ents[e].own_off4;
+                                    uint32_t ent = 0u;
+                                    if (xo != VR_NO_VOTE) {
+                                        const uint8_t *p = cbp + 4 * (int)xo;
+                                        const uint32_t ql = p[col], base = ((uint32_t)p[soff] >> nsh) & 0xFu;
+                                        const uint32_t mql = mvalid ? p[mqoff] : 0u, mbase = mvalid ? (((uint32_t)p[msoff] >> mnsh) & 0xFu) : 0u;
+                                        ent = ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
+                                    }
+                                    rec[SR_HDR_WORDS + e] = ent;
+                                }
+                            } else {
+                                for (int e = 0; e < mi; e++) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
+                            }
+                        }
+                    }
                 }
             }
-            __syncwarp();
-            if (run > 0) ring_drain(x, shdr, empty, s, lane, false);
         }
         __syncwarp();
         if (lane == 0) pipe_arrive(empty + s);

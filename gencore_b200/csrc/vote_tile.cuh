@@ -330,9 +330,10 @@ struct Bins3 {
         const bool u1 = h1 || (!hit && b0 >= 0 && b1 < 0);
         const bool u2 = h2 || (!hit && b0 >= 0 && b1 >= 0 && b2 < 0);
         overflow = overflow || !(u0 || u1 || u2);
-        if (u0) { b0 = base; c0++; s0 += score; q0 += qual; x0 = max(x0, qual); }
-        if (u1) { b1 = base; c1++; s1 += score; q1 += qual; x1 = max(x1, qual); }
-        if (u2) { b2 = base; c2++; s2 += score; q2 += qual; x2 = max(x2, qual); }
+        // (selects, not branches: the threads of a warp histogram different columns)
+        b0 = u0 ? base : b0; c0 += u0 ? 1 : 0; s0 += u0 ? score : 0; q0 += u0 ? qual : 0; x0 = max(x0, u0 ? qual : 0);
+        b1 = u1 ? base : b1; c1 += u1 ? 1 : 0; s1 += u1 ? score : 0; q1 += u1 ? qual : 0; x1 = max(x1, u1 ? qual : 0);
+        b2 = u2 ? base : b2; c2 += u2 ? 1 : 0; s2 += u2 ? score : 0; q2 += u2 ? qual : 0; x2 = max(x2, u2 ? qual : 0);
     }
     GCB_DEV VoteBin bin(int k) const {
         VoteBin v;
@@ -374,8 +375,8 @@ GCB_DEV ChunkMasks make_masks(int l_out, int len, int col0) {
 // (directory -> side modes -> family-side descriptors -> cluster offsets) in flight at once.  `max_need`: the largest
 // shared-memory allocation a tile of this view takes in the vote kernel.
 GCB_HD int32_t tile_smem_need(int32_t nfs, int32_t np, int32_t slab_bytes, int32_t lanes) {
-    // family-side list, VoteRead table, slab + slack, slow-column list + its prefix sums (one entry per family side and lane)
-    return ((32 * nfs + 127) & ~127) + ((32 * np + 127) & ~127) + ((slab_bytes + VT_SLAB_SLACK + 127) & ~127) + ((8 * nfs * lanes + 127) & ~127);
+    // family-side list, VoteRead table, slab + slack, slow-column list + its two prefix sums (one entry per family side and lane)
+    return ((32 * nfs + 127) & ~127) + ((32 * np + 127) & ~127) + ((slab_bytes + VT_SLAB_SLACK + 127) & ~127) + ((12 * nfs * lanes + 127) & ~127);
 }
 
 __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b, ResultView r, Workspace ws, int32_t slab_cap, int32_t arena,

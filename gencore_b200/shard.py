@@ -28,6 +28,11 @@ def shard_batch(batch: Batch, world: int, rank: int) -> Tuple[Batch, Tuple[int, 
     """The sub-batch of rank `rank` (offsets rebased so that it is a valid gcb_batch on its own)."""
     b = window_bounds(batch, world)
     c0, c1 = int(b[rank]), int(b[rank + 1])
+    return slice_batch(batch, c0, c1), (c0, c1)
+
+
+def slice_batch(batch: Batch, c0: int, c1: int) -> Batch:
+    """Clusters [c0, c1) as a gcb_batch of their own."""
     p0, p1 = int(batch.cluster_pair_off[c0]), int(batch.cluster_pair_off[c1])
     slab = batch.cluster_slab_bounds()
     s0, s1 = int(slab[c0]), int(slab[c1])
@@ -39,7 +44,7 @@ def shard_batch(batch: Batch, world: int, rank: int) -> Tuple[Batch, Tuple[int, 
         batch.umi[p0:p1].copy(), reads, batch.cigar, np.ascontiguousarray(batch.payload[s0:s1]),
         batch.qnames[p0:p1] if batch.qnames is not None else None, batch.nm[2 * p0:2 * p1] if batch.nm is not None else None,
         batch.umi_prefix)
-    return sub, (c0, c1)
+    return sub
 
 
 def split_batch(batch: Batch, parts: int) -> List[Batch]:

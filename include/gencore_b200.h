@@ -154,7 +154,7 @@ typedef struct gcb_result {
 #define GCB_STAGE_DUPLEX 0x8u          /* cluster.cpp:102-244 -> status, FR/RR, duplex merge of out_payload */
 #define GCB_STAGE_ALL 0xFu
 /* measurement only: the parts of GCB_STAGE_SCORE_VOTE one at a time — per-tile preparation (tile_prep2_kernel), then the
- * vote, or the vote's two halves: the ring kernel (vote_ring_kernel), then rollback + the generic kernel's tiles */
+ * vote, or the vote's two halves: the ring kernel (vote_ring_kernel), then slow columns + rollback + the generic kernel's tiles */
 #define GCB_STAGE_VOTE_PREP_ONLY 0x10u
 #define GCB_STAGE_VOTE_ONLY 0x20u
 #define GCB_STAGE_VOTE_FAST_ONLY 0x40u
@@ -220,6 +220,10 @@ void gcb_host_free(void *p);
  * key 3 = lanes per cluster in umi_group_kernel / select_template_kernel (8, 16, 32; 0 = by mean cluster size),
  * key 5 = non-zero: every tile is voted by the generic kernel (score_vote_kernel) instead of the ring kernel. */
 int gcb_set_debug(gcb_ctx *ctx, int key, int value);
+
+/* Tuning knob: bytes of the slow-column queues between vote_ring_kernel and slow_columns_kernel (0 = sized from the payload).
+ * Tiles whose slow columns do not fit are voted by the generic kernel; results do not depend on it. */
+int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes);
 
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t gcb_launch_count(const gcb_ctx *ctx);
