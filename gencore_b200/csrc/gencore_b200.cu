@@ -110,24 +110,25 @@ TilePlan plan_tiles(int32_t max_cluster_bytes, int ring_window_shift = 0) {
     memset(&p, 0, sizeof p);
     p.arena = (budget - 1 * KB - VR_OFF_ARENA - VR_GUARD) & ~127;
     p.smem = VR_OFF_ARENA + p.arena + VR_GUARD;
-    // 32 KB windows while three of the largest tiles fit the arena (the tiles of a batch of small clusters are about a window each,
-    // so the ring is deeper than that), else 16 KB windows as long as one tile fits
-    for (int shift = 15; shift >= 14; shift--) {
-        if (ring_window_shift && shift != ring_window_shift) continue;
+    // 16 KB windows: a tile is about a window plus half a cluster, so a batch of small clusters keeps ten or more tiles in flight
+    // in the ring kernel's arena and its voter warps work in three groups; a batch whose largest cluster nearly fills the arena
+    // still gets one tile in flight.  (32 KB windows measured slower on every shape: fewer, larger tiles in flight.)
+    {
+        const int shift = ring_window_shift ? ring_window_shift : 14;
         p.window_shift = shift;
         p.window = 1 << shift;
         p.slab_cap = p.window + maxc;
         if (p.slab_cap > VT_MAX_SLAB) p.slab_cap = VT_MAX_SLAB;
-        // a tile of the largest slab with the tables of a family of pairs that fills it (a pair of two one-base reads is 16 bytes)
-        const int32_t tables = 3 * 128 + 8 * KB;
+        // a tile of the largest slab with the tables of a family of pairs that fills it
+        const int32_t tables = 4 * 128 + 12 * KB;
         const int32_t largest = p.window + maxc + VT_SLAB_SLACK + tables;
-        if (p.window + maxc <= VT_MAX_SLAB && (p.arena >= 3 * largest || (shift == 14 && p.arena >= largest))) {
+        if (p.window + maxc <= VT_MAX_SLAB && p.arena >= largest) {
             p.ring = 1;
             return p;
         }
     }
     // clusters too large for a stage: every tile goes to the generic kernel (no size limits)
-    p.window_shift = ring_window_shift ? ring_window_shift : 15;
+    p.window_shift = ring_window_shift ? ring_window_shift : 14;
     p.window = 1 << p.window_shift;
     p.slab_cap = 0;
     p.ring = 0;
@@ -308,8 +309,8 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
             GCB_CUDA(ctx, cudaMemsetAsync(rb.count, 0, 4, stream));
             GCB_CUDA(ctx, cudaMemsetAsync(sq.count, 0, 8 * VQ_NQ, stream));
             const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
-            GCB_LAUNCH(vote_ring_kernel, dim3(ring_grid), dim3(VR_THREADS), plan.smem, stream, b, r, ws, (int32_t)ctx->opt.moderate_quality,
-                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.arena,
+            GCB_LAUNCH(vote_ring_kernel, dim3(ring_grid), dim3(VR_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
+                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, rb, (int32_t)n_tiles, plan.arena,
                        (const int32_t *)max_need);
             ctx->launches++;
         }

@@ -2,13 +2,15 @@
 // ONE persistent CTA per SM over a ring of staged tiles (vote_tile.cuh).
 //
 //   warp 0            producer.  The whole warp fetches the headers of this CTA's next 32 tiles (blockIdx.x, + gridDim.x, ...)
-//                     at once; lane 0 then waits for a stage's `empty` mbarrier, writes the stage header and issues three
-//                     bulk asynchronous copies (cp.async.bulk -> UBLKCP) onto the stage's `full` mbarrier: compact
-//                     family-side list, VoteRead table, payload slab.  Stages are equal slices of one arena sized by the
-//                     batch's largest tile, so small tiles give a deep ring and a 100 KB cluster still gets a stage.
-//   warps 1..15       voters.  Every warp visits every tile in order: waits for `full`, takes bundles of family sides from
-//                     the stage's counter until none is left, arrives on `empty`.  A tile has fewer bundles than the CTA has
-//                     warps, so the warps spread over the tiles in flight; nobody waits at a CTA barrier.
+//                     at once; lane 0 then allocates what the tile needs from a ring-buffer arena (a tile takes what it
+//                     needs, space is freed in tile order as the oldest tile's `empty` mbarrier completes), writes the slot's
+//                     header and issues three bulk asynchronous copies (cp.async.bulk -> UBLKCP) onto the slot's `full`
+//                     mbarrier: compact family-side list, VoteRead table, payload slab.  Up to VR_MAX_STAGES tiles in flight.
+//   warps 1..15       voters, in G groups (three while six or more of the batch's largest tile fit the arena, else one).  The
+//                     CTA's k-th tile belongs to group k % G; every warp of the group visits the group's tiles in order:
+//                     waits for `full`, takes bundles of family sides from the tile's counter until none is left, arrives
+//                     on `empty`.  A tile of a 16 KB window has about three bundles for the five warps of its group; the
+//                     groups decouple the tiles in flight from each other and a warp only walks a third of the tiles.
 //   a bundle          32 / L family sides, L lanes each, sixteen columns per lane.  FAST columns (every voter shows the
 //                     template's base, no read disagrees with its mate inside the pair overlap, best quality >=
 //                     moderateQuality: exactly group.cpp:421-427 under `implied`) are finished in the word: per-column maxima
@@ -32,7 +34,8 @@ namespace gcb {
 
 constexpr int VR_THREADS = 512;
 constexpr int VR_WARPS = VR_THREADS / WARP;
-constexpr int VR_MAX_STAGES = 12;  // tiles in flight (barrier pairs and stage headers); their bytes come from one arena
+constexpr int VR_MAX_STAGES = 16;  // tiles in flight (barrier pairs and stage headers); their bytes come from one ring-buffer arena
+constexpr int VR_GROUPS = 3;       // groups of voter warps when the tiles are small
 constexpr int VR_GUARD = 4608;     // never allocated, after the arena: the branch-free read loop may read a VoteRead table or a
                                    // slab up to 257 entries / 64 bytes past its end (values unused)
 
@@ -44,42 +47,240 @@ struct __align__(16) RingStage {  // shared memory; the first part is written by
     int32_t ft_off, vr_off, slab_off;  // where the tile's family-side list, VoteRead table and payload slab lie (shared-memory offsets)
     int32_t sl_off;                    // slow-column list: uint32 entries[sl_cap], then their inclusive column counts, then their queue words
     int32_t sl_cap;
-    int32_t pad0;
+    int32_t deep;          // the tile's slow columns are decided here, by all the voter warps together (see the header)
     // the voters' part
     int32_t next_bundle;   // atomic: next bundle to hand out
     int32_t done;          // atomic: bundles finished
     int32_t n_entries;     // atomic: slow-column list entries
-    int32_t pad1;
+    int32_t closed;        // deep tiles: the list is complete and its prefix sums are written
+    int32_t drain_total;   // deep tiles: slow columns of the tile
+    int32_t next_col;      // deep tiles, atomic: next slow column to decide
+    int32_t pad[2];
 };
-static_assert(sizeof(RingStage) == 80, "stage header size");
+static_assert(sizeof(RingStage) == 96, "stage header size");
 
 // shared-memory map: [barriers][stage headers][producer's header cache][arena]
 constexpr int VR_OFF_FULL = 0;                                   // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_HDR = 16 * VR_MAX_STAGES;                   // RingStage[VR_MAX_STAGES]
-constexpr int VR_OFF_HCACHE = VR_OFF_HDR + 80 * VR_MAX_STAGES;   // TileHdr2[32]: the producer's next tiles
+constexpr int VR_OFF_HCACHE = VR_OFF_HDR + 96 * VR_MAX_STAGES;   // TileHdr2[32]: the producer's next tiles
 constexpr int VR_OFF_ARENA = (VR_OFF_HCACHE + 48 * WARP + 127) & ~127;
 // a tile's allocation: [FsTile list][VoteRead table][slab + slack][slow-column list + two prefix arrays], each part rounded to 128 bytes
 static_assert(VR_OFF_HDR % 16 == 0 && VR_OFF_HCACHE % 16 == 0 && VR_OFF_ARENA % 128 == 0, "ring layout");
 GCB_HD uint32_t ring_round128(uint32_t v) { return (v + 127u) & ~127u; }
 
-__global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, int32_t moderate_quality, int32_t implied,
-                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, int32_t n_tiles,
-                                                                   int32_t arena_bytes, const int32_t *max_need) {
+struct RingCtx {  // what deciding a slow column inside the CTA needs besides the stage
+    const BatchView *b;
+    const ResultView *r;
+    const GenomeView *gv;
+    const gcb_options *o;
+    RollbackList rb;
+};
+
+// group.cpp:376-525 for one slow column of family side f of the staged tile, by one thread.  For a uniform family side
+// (every voter has the template's length, no column shift, the same overlap window) what pair.cpp:121-170 needs to know
+// about the column — inside the overlap or not, the mate index — is computed once; each read then is its quality byte,
+// its base nibble and, inside the overlap, its mate's, added to a three-bin register histogram.  The two scans of
+// group.cpp:395-417 are a top-2 selection over the three bins and the two largest codes nobody showed (bin_key order).
+// (Deep tiles only: see the kernel's header.  The pointers are derived from the shared-memory symbol inside the function, so
+// that the loads are LDS and not generic loads.)
+__device__ __noinline__ void ring_slow_column(const RingCtx &x, int ft_off, int vr_off, int slab_off, int64_t out_base0, int f, int col) {
+    GCB_DYN_SMEM(smem);
+    const gcb_options &o = *x.o;
+    const ScoreTab tab(o);
+    const FsTile ft = ((const FsTile *)(smem + ft_off))[f];
+    const uint8_t *cb = smem + slab_off + 4 * (int)ft.cbase4;
+    const VoteRead *ents = (const VoteRead *)(smem + vr_off) + ft.ent0;
+    const VoteRead tv = ents[ft.tmpl_k];
+    const int side = fs_side(ft);
+    const int qbytes = GCB_ALIGN4(ft.l_out);
+    uint8_t *out = x.r->out_payload + out_base0 + 4 * (int64_t)ft.out4;
+    GCB_COUNT(3, 1);
+    if (col >= (int)ft.len) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
+        int obase = 0, oqual = 0, sc;
+        fetch_ent(cb, tv, col, side, o, obase, oqual, sc);
+        out[col] = (uint8_t)oqual;
+        return;
+    }
+    Bins3 bins;
+    bins.init();
+    const int m = (int)ft.m;
+    if (ft.flags & FS_UNIFORM) {
+        const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
+        const int k = col - (int)tv.ov_own, mp = (int)tv.ov_mate + k;
+        const bool inwin = info && k >= 0 && k < (int)tv.ov_len;
+        const bool mvalid = inwin && mp >= 0 && mp < (int)tv.mate_l;
+        const bool plain = info && !inwin;  // pair.cpp:121-131: outside the overlap the score follows the quality
+        const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
+        const int mpi = mvalid ? mp : 0;
+        const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
+        for (int e = 0; e < m; e++) {
+            const uint32_t w = *(const uint32_t *)(ents + e);  // own_off4 | mate_off4 << 16
+            if ((w & 0xFFFFu) == VR_NO_VOTE) continue;
+            const uint8_t *rec = cb + 4 * (int)(w & 0xFFFFu);
+            int ql = rec[col];
+            const int base = (rec[soff] >> nsh) & 0xF;
+            int score;
+            if (mvalid) {
+                const uint8_t *mrec = cb + 4 * (int)(w >> 16);
+                const int mql = mrec[mpi];
+                const int mbase = (mrec[msoff] >> mnsh) & 0xF;
+                const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
+                const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
+                const int s_match = sc8(tab.q2s((ql + mql) / 2) + 4);                        // pair.cpp:147-152
+                const int s_mis = mine ? sc8(tab.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;  // pair.cpp:153-169
+                score = base == mbase ? s_match : s_mis;
+                ql = base == mbase ? ql : max(0, ql - mql);
+            } else {
+                score = plain ? tab.q2s(ql) : tab.sm;
+            }
+            bins.add(base, ql, score);
+        }
+    } else {
+        for (int e = 0; e < m; e++) {
+            int base, qual, score;
+            if (fetch_vote(cb, ents[e], col, side, tab, base, qual, score)) bins.add(base, qual, score);
+        }
+    }
+    ColumnTop ct;
+    int total = bins.total;
+    uint32_t acgt = 0;  // the best quality of codes 1, 2, 4, 8 in bytes 0..3 (0 when nobody showed the code)
+    if (bins.overflow) {  // a fourth distinct code: the sixteen-bin histogram in local memory (group.cpp:376-417 as written)
+        int32_t h[64];
+        for (int q = 0; q < 64; q++) h[q] = 0;
+        for (int e = 0; e < m; e++) {
+            int base, qual, score;
+            if (!fetch_ent(cb, ents[e], col, side, o, base, qual, score)) continue;
+            h[4 * base]++;
+            h[4 * base + 1] += score;
+            h[4 * base + 2] += qual;
+            h[4 * base + 3] = max(h[4 * base + 3], qual);
+        }
+        VoteBin obs[16];
+        int nobs = 0;
+        total = 0;
+        for (int q = 0; q < 16; q++)
+            if (h[4 * q] > 0) {
+                obs[nobs].base = q; obs[nobs].cnt = h[4 * q]; obs[nobs].score = h[4 * q + 1]; obs[nobs].qual = h[4 * q + 2]; obs[nobs].maxq = h[4 * q + 3];
+                total += obs[nobs].score;
+                nobs++;
+            }
+        ct = column_top(o, obs, nobs, total);
+        acgt = (uint32_t)(h[4 * 1] > 0 ? h[4 * 1 + 3] : 0) | ((uint32_t)(h[4 * 2] > 0 ? h[4 * 2 + 3] : 0) << 8) |
+               ((uint32_t)(h[4 * 4] > 0 ? h[4 * 4 + 3] : 0) << 16) | ((uint32_t)(h[4 * 8] > 0 ? h[4 * 8 + 3] : 0) << 24);
+    } else {
+        // top and second: every bin competes with its (score, quality sum, code) key; the codes nobody showed compete
+        // with (0, 0, code), of which only the two largest can place
+        unsigned freemask = 0xFFFFu;
+        unsigned long long key[3];
+#pragma unroll
+        for (int kk = 0; kk < 3; kk++) {
+            const VoteBin vb = bins.bin(kk);
+            const int bb = vb.base;
+            const bool have = bb >= 0;
+            key[kk] = have ? bin_key(vb.score, vb.qual, bb) : 0ull;
+            if (have) freemask &= ~(1u << bb);
+            if (have && (bb == 1 || bb == 2 || bb == 4 || bb == 8)) acgt |= (uint32_t)vb.maxq << (bb == 1 ? 0 : bb == 2 ? 8 : bb == 4 ? 16 : 24);
+        }
+        const int e1 = 31 - __clz((int)freemask);
+        freemask &= ~(1u << e1);
+        const int e2 = 31 - __clz((int)freemask);
+        const unsigned long long ke1 = bin_key(0, 0, e1), ke2 = bin_key(0, 0, e2);
+        unsigned long long top = max_u64(key[0], key[1]), sec = min_u64(key[0], key[1]);
+        sec = max_u64(sec, min_u64(top, key[2])); top = max_u64(top, key[2]);
+        sec = max_u64(sec, min_u64(top, ke1)); top = max_u64(top, ke1);
+        sec = max_u64(sec, min_u64(top, ke2)); top = max_u64(top, ke2);
+        const int tb = (int)(top & 0xF), sb = (int)(sec & 0xF);
+        const VoteBin none = {0, 0, 0, 0, 0};
+        ct.top = bins.b0 == tb ? bins.bin(0) : bins.b1 == tb ? bins.bin(1) : bins.b2 == tb ? bins.bin(2) : none;
+        ct.sec = bins.b0 == sb ? bins.bin(0) : bins.b1 == sb ? bins.bin(1) : bins.b2 == sb ? bins.bin(2) : none;
+        ct.top.base = tb;
+        ct.sec.base = sb;
+        column_rules(o, ct, total);
+    }
+    int new_qual;
+    if (ct.fast) {
+        new_qual = ct.top.maxq;  // group.cpp:422-426: the base is NOT written
+    } else {
+        // the record's base before the vote: the template's own (pair.cpp rewrites qualities, never bases)
+        const int obase = base_at(cb + 4 * (int)tv.own_off4 + qbytes, col);
+        int ref4 = 0;
+        if (ft.flags & FS_REF_OK) {  // group.cpp:430-439
+            int refpos = col;
+            if (!(ft.flags & FS_SIMPLE_CIGAR)) {
+                const gcb_read_desc od = x.b->reads[x.r->groups[ft.slot].tmpl_read[side]];
+                refpos = get_ref_offset(x.b->cigar + od.cigar_off, od.n_cigar, col);
+            }
+            const int64_t nib = ft.ref_nib0 + refpos;
+            if (refpos >= 0 && nib >= 0 && (nib >> 1) < x.gv->packed_bytes) {  // the bound only guards malformed CIGARs
+                const uint8_t two = x.gv->packed4[nib >> 1];
+                ref4 = genome_nibble_to_bam((nib & 1) ? (two >> 4) : (two & 0xF));
+            }
+        }
+        int rbq = 0;
+        bool any_high = false;
+        if (ct.need_ref && ref4 != 0) {
+            const int rmax = (int)((acgt >> (ref4 == 1 ? 0 : ref4 == 2 ? 8 : ref4 == 4 ? 16 : 24)) & 0xFFu);
+            if (rmax >= 128) {  // `char refBaseQual` wraps: the scan order matters (group.cpp:474-490): template first
+                int tb, tq, ts;
+                if (fetch_ent(cb, tv, col, side, o, tb, tq, ts) && tb == ref4) {
+                    if (tq > rbq) rbq = sc8(tq);
+                    if (tq >= o.high_quality) any_high = true;
+                }
+                for (int e = 0; e < m; e++) {
+                    int base, qual, score;
+                    if (e == ft.tmpl_k || !fetch_ent(cb, ents[e], col, side, o, base, qual, score) || base != ref4) continue;
+                    if (qual > rbq) rbq = sc8(qual);
+                    if (qual >= o.high_quality) any_high = true;
+                }
+            } else {
+                rbq = rmax;
+                any_high = rmax >= o.high_quality;
+            }
+        }
+        const ColumnOut co = column_arbitrate(o, ct, ref4, rbq, any_high);
+        if (obase != co.base) {  // group.cpp:509-524
+            int d_mm = 0;
+            if (ref4 != 0) {
+                if (obase == ref4) d_mm = 1;
+                else if (co.base == ref4) d_mm = -1;
+            }
+            gcb_group_result *gr = x.r->groups + ft.slot;  // (the bundle's lane 0 zeroed both counters before the tile was closed)
+            atomicAdd(&gr->diff[side], 1);
+            if (d_mm != 0) {
+                const int before = atomicAdd(&gr->mismatch_inc[side], d_mm);
+                if (d_mm > 0 && before == 5) {  // more than five new mismatches so far: vote_rollback_kernel looks at the final count
+                    const int kk = atomicAdd(x.rb.count, 1);
+                    if (kk < x.rb.cap) x.rb.list[kk] = 2 * ft.slot + side;
+                }
+            }
+            const int byte = col >> 1;
+            const unsigned delta = ((unsigned)(obase ^ co.base) & 0xFu) << ((col & 1) ? 0 : 4);
+            atomicXor((unsigned *)(out + qbytes + (byte & ~3)), delta << (8 * (byte & 3)));
+        }
+        new_qual = co.qual;
+    }
+    out[col] = (uint8_t)new_qual;
+}
+
+__global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o, int32_t implied,
+                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, RollbackList rb,
+                                                                   int32_t n_tiles, int32_t arena_bytes, const int32_t *max_need) {
     GCB_DYN_SMEM(smem);
     uint64_t *full = (uint64_t *)(smem + VR_OFF_FULL);
     uint64_t *empty = (uint64_t *)(smem + VR_OFF_EMPTY);
     RingStage *shdr = (RingStage *)(smem + VR_OFF_HDR);
 #define GCB_LDS32(off) (*(const uint32_t *)(smem + (off)))
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    // the arena is cut into equal stages that hold the batch's largest tile (tile_prep2_kernel measured it): as many tiles in
-    // flight as fit
-    const int32_t stage_bytes = (int32_t)ring_round128((uint32_t)max(*max_need, 128));
-    const int n_stages = min(VR_MAX_STAGES, max(arena_bytes / stage_bytes, 1));
+    // the batch's largest tile (tile_prep2_kernel measured it) decides how the voters are organised: small tiles -> many in
+    // flight -> three groups of five warps; tiles that fill the arena -> all fifteen warps on every tile
+    const int32_t largest = (int32_t)ring_round128((uint32_t)max(*max_need, 128));
+    const int n_groups = arena_bytes >= 6 * largest ? VR_GROUPS : 1, wpg = (VR_WARPS - 1) / n_groups;
+    const int n_stages = VR_MAX_STAGES;
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
             pipe_init(full + s, 1);
-            pipe_init(empty + s, VR_WARPS - 1);  // every voter warp arrives once when it leaves the stage's tile
+            pipe_init(empty + s, wpg);  // every voter warp of the tile's group arrives once when it leaves the tile
         }
         pipe_fence_init();
     }
@@ -90,15 +291,41 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         // headers of this CTA's next 32 tiles at once, so that no tile waits for a header on its way from global memory
         TileHdr2 *hcache = (TileHdr2 *)(smem + VR_OFF_HCACHE);
         int k = 0;
-        // stage k % n_stages once every voter has left the tile it held before
-        auto allocate = [&]() -> uint32_t {
-            const int s = k % n_stages, use = k / n_stages;
+        // ring-buffer arena: the tiles in flight are k_tail .. k-1, their allocations lie between off_of[k_tail] and head (wrapping);
+        // slot k % n_stages (barriers, header) once the tile that used it before is released
+        int k_tail = 0;
+        uint32_t head = 0u, off_of[VR_MAX_STAGES];
+        auto release_oldest = [&]() {
+            const int s = k_tail % n_stages, use = k_tail / n_stages;
             GCB_TRACE(200 + s);
-            if (use > 0) GCB_COUNT(7, 1);
-            if (use > 0)
-                while (!pipe_try_wait(empty + s, (uint32_t)((use - 1) & 1), 1000u)) pipe_relax(200u);
+            while (!pipe_try_wait(empty + s, (uint32_t)(use & 1), 1000u)) pipe_relax(200u);
             GCB_TRACE(300 + s);
-            return (uint32_t)s * (uint32_t)stage_bytes;
+            k_tail++;
+        };
+        auto allocate = [&](uint32_t need) -> uint32_t {
+            uint32_t at;
+            for (;;) {
+                if (k - k_tail == n_stages) {
+                    release_oldest();
+                    continue;
+                }
+                if (k == k_tail) {  // nothing in flight
+                    at = 0u;
+                    break;
+                }
+                const uint32_t tail = off_of[k_tail % n_stages];
+                if (head > tail) {  // free: [head, arena) and [0, tail)
+                    if (head + need <= (uint32_t)arena_bytes) { at = head; break; }
+                    if (need <= tail) { at = 0u; GCB_COUNT(7, 1); break; }
+                } else if (head + need <= tail) {  // free: [head, tail) (head == tail: full)
+                    at = head;
+                    break;
+                }
+                release_oldest();
+            }
+            off_of[k % n_stages] = at;
+            head = at + need;
+            return at;
         };
         auto fill = [&](RingStage &sh, const TileHdr2 &cur, int32_t tile, uint32_t at) {
             const uint32_t vr_bytes = 32u * (uint32_t)cur.np, ft_bytes = 32u * (uint32_t)max(cur.nfs, 0);
@@ -111,11 +338,15 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             sh.slab_off = sh.vr_off + (int32_t)ring_round128(vr_bytes);
             sh.sl_off = sh.slab_off + (int32_t)ring_round128((uint32_t)cur.slab_bytes + VT_SLAB_SLACK);
             sh.sl_cap = max(cur.nfs, 0) * cur.lanes;
-            sh.pad0 = 0;
+            // a tile of deep families (24 pairs or more per family side on average): few bundles, long lists of slow columns
+            sh.deep = cur.nfs > 0 && 2 * cur.np >= 24 * cur.nfs;
             sh.next_bundle = 0;
             sh.done = 0;
             sh.n_entries = 0;
-            sh.pad1 = 0;
+            sh.closed = 0;
+            sh.drain_total = 0;
+            sh.next_col = 0;
+            sh.pad[0] = sh.pad[1] = 0;
         };
         for (int64_t base = (int64_t)blockIdx.x; base < n_tiles; base += (int64_t)WARP * gridDim.x) {
             const int64_t mine_t = base + (int64_t)lane * gridDim.x;
@@ -128,7 +359,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     const TileHdr2 cur = hcache[i];
                     if (cur.nfs <= 0) continue;  // nothing for this kernel here (empty tile, or the generic kernel has it)
                     const uint32_t slab_bytes = (uint32_t)cur.slab_bytes, vr_bytes = 32u * (uint32_t)cur.np, ft_bytes = 32u * (uint32_t)cur.nfs;
-                    const uint32_t at = allocate();
+                    const uint32_t at = allocate((uint32_t)tile_smem_need(cur.nfs, cur.np, cur.slab_bytes, cur.lanes));
                     const int s = k % n_stages;
                     RingStage sh;
                     fill(sh, cur, (int32_t)t, at);
@@ -143,23 +374,28 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             }
             __syncwarp();
         }
-        if (lane == 0) {  // the end marker: the phase completes with this arrival alone
-            const uint32_t at = allocate();
-            const int s = k % n_stages;
-            TileHdr2 cur;
-            cur.out_base0 = 0; cur.slab0 = 0; cur.slab_bytes = 0; cur.p0 = 0; cur.np = 0; cur.nfs = -1; cur.lanes = 1; cur.common_l = 0;
-            cur.per_bundle = 32; cur.n_bundles = 0;
-            RingStage sh;
-            fill(sh, cur, 0, at);
-            shdr[s] = sh;
-            pipe_expect(full + s, 0u);
-            pipe_commit(full + s);
+        if (lane == 0) {  // one end marker per group: the phase completes with this arrival alone
+            for (int g = 0; g < n_groups; g++) {
+                const uint32_t at = allocate(128u);
+                const int s = k % n_stages;
+                TileHdr2 cur;
+                cur.out_base0 = 0; cur.slab0 = 0; cur.slab_bytes = 0; cur.p0 = 0; cur.np = 0; cur.nfs = -1; cur.lanes = 1; cur.common_l = 0;
+                cur.per_bundle = 32; cur.n_bundles = 0;
+                RingStage sh;
+                fill(sh, cur, 0, at);
+                shdr[s] = sh;
+                pipe_expect(full + s, 0u);
+                pipe_commit(full + s);
+                k++;
+            }
         }
         return;
     }
 
     // ---- voters
-    const uint32_t mod4 = 0x01010101u * (uint32_t)(moderate_quality & 0xFF);
+    RingCtx x;
+    x.b = &b; x.r = &r; x.gv = &gv; x.o = &o; x.rb = rb;
+    const uint32_t mod4 = 0x01010101u * (uint32_t)(o.moderate_quality & 0xFF);
     // slow-column records go to the queue of this CTA
     const int qi = (int)(blockIdx.x % VQ_NQ);
     uint32_t *q_words = sq.words + (size_t)qi * sq.cap_words;
@@ -168,9 +404,11 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     // lane geometry and masks are kept across tiles while the tile shape (lanes per family side, usual record length) stays
     int cur_L = 0, cur_l = -1, S = 32, sub = 0, j = 0, col0 = 0;
     ChunkMasks cm_common = make_masks(0, 0, 0);
-    int s = 0;
-    uint32_t par = 0u;
-    for (;;) {
+    // this warp's group and the group's tiles: k = group, group + G, ...; tile k lives in slot k % n_stages
+    const int group = (warp - 1) % n_groups;
+    for (int k = group;; k += n_groups) {
+        const int s = k % n_stages;
+        const uint32_t par = (uint32_t)((k / n_stages) & 1);
         GCB_TRACE(100 + s);
         pipe_wait(full + s, par, 1000u);
         RingStage *sh = shdr + s;
@@ -409,7 +647,13 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 runw += __shfl_sync(FULL, inclw, WARP - 1);
             }
             __syncwarp();
-            if (run > 0) {
+            if (sh->deep) {  // the columns are decided here: open the list to every warp (below)
+                if (lane == 0) {
+                    sh->drain_total = run;
+                    __threadfence_block();
+                    *(volatile int32_t *)&sh->closed = 1;
+                }
+            } else if (run > 0) {
                 unsigned long long base64 = 0ull;
                 if (lane == 0) base64 = atomicAdd(sq.count + qi, ((unsigned long long)(uint32_t)run << 32) | (uint32_t)runw);
                 base64 = __shfl_sync(FULL, base64, 0);
@@ -482,13 +726,42 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 }
             }
         }
+        if (sh->deep) {
+            // every voter warp waits for the tile to be closed and then decides slow columns, 32 at a time, one thread per
+            // column, straight from the staged slab: a deep tile has hundreds of them and nothing else for the warps to do
+            while (*(volatile int32_t *)&sh->closed == 0) pipe_relax(100u);
+            __threadfence_block();
+            const int total = *(volatile int32_t *)&sh->drain_total, n = *(volatile int32_t *)&sh->n_entries;
+            const uint32_t *s_list = (const uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap;
+            const int ft_off = sh->ft_off, vr_off = sh->vr_off, slab_off = sh->slab_off;
+            const int64_t out_base0 = sh->out_base0;
+            for (;;) {
+                int c0 = 0;
+                if (lane == 0) c0 = atomicAdd(&sh->next_col, WARP);
+                c0 = __shfl_sync(FULL, c0, 0);
+                if (c0 >= total) break;
+                const int idx = c0 + lane;
+                if (idx < total) {
+                    int lo = 0, hi = n - 1;
+                    while (lo < hi) {  // the first entry whose inclusive column count exceeds idx
+                        const int mid = (lo + hi) >> 1;
+                        if ((int)s_pf[mid] > idx) hi = mid;
+                        else lo = mid + 1;
+                    }
+                    const uint32_t code = s_list[lo];
+                    uint32_t mask = code & 0xFFFFu;
+                    const int rank = idx - ((int)s_pf[lo] - __popc(mask));
+                    for (int q = 0; q < rank; q++) mask &= mask - 1u;
+                    const int bit = __ffs((int)mask) - 1;
+                    const int col = VT_CHUNK * (int)((code >> 16) & 31u) + (bit & 8) + 7 - (bit & 7);
+                    ring_slow_column(x, ft_off, vr_off, slab_off, out_base0, (int)(code >> 21), col);
+                }
+                __syncwarp();
+                pipe_progress();
+            }
+        }
         __syncwarp();
         if (lane == 0) pipe_arrive(empty + s);
-        s++;
-        if (s == n_stages) {
-            s = 0;
-            par ^= 1u;
-        }
     }
 #undef GCB_LDS32
 }

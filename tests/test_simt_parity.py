@@ -87,10 +87,10 @@ def test_generic_vote_matches_oracle_under_simt_check(simt_lib, oracle, name, th
 
 
 @pytest.mark.parametrize("name,thunk", LIGHT_CASES, ids=[c[0] for c in LIGHT_CASES])
-def test_small_tile_window_matches_oracle_under_simt_check(simt_lib, oracle, name, thunk):
-    """The vote over 16 KB payload windows instead of 32 KB ones: twice the tiles, same bytes."""
+def test_large_tile_window_matches_oracle_under_simt_check(simt_lib, oracle, name, thunk):
+    """The vote over 32 KB payload windows instead of 16 KB ones (half the tiles, one group of fifteen voter warps): same bytes."""
     batch, genome, opt = thunk()
-    res, _ = run(simt_lib, batch, genome, opt, lambda eng: eng.set_debug(2, 14))
+    res, _ = run(simt_lib, batch, genome, opt, lambda eng: eng.set_debug(2, 15))
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 
 
