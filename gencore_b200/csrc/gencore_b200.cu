@@ -2,7 +2,7 @@
 // of one batch.  Host code only sizes buffers, moves bytes and launches; all arithmetic of the
 // reference's hot path lives in the kernels:
 //   umi_group_kernel -> select_template_kernel -> scan_local/scan_blocks -> tile_prep2_kernel -> vote_ring_kernel
-//   -> slow_columns_kernel -> vote_rollback_kernel -> score_vote_kernel (the tiles that do not fit a ring stage) -> duplex_kernel
+//   -> slow_columns_kernel -> vote_rollback_kernel -> score_vote_kernel (the tiles that do not fit the ring's arena) -> duplex_kernel
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -43,9 +43,8 @@ struct gcb_ctx {
     DevBuf w_vr, w_fs, w_gtiles, w_gcount;
     DevBuf w_fstiles, w_thdr2, w_need;   // the tiles' compact family-side lists, their headers, the largest tile's shared-memory need (per chunk)
     DevBuf w_rb_list, w_rb_count;        // rollback candidates (per chunk: one counter)
-    DevBuf w_sq_count, w_sq_words, w_sq_index;  // slow-column queues (per chunk: VQ_NQ counters)
-    int64_t slow_queue_bytes = 0;        // 0 = sized from the payload
-    uint32_t sq_cap_words = 0, sq_cap_recs = 0;  // per queue
+    DevBuf w_sl_entries, w_sl_count;     // the ring kernel's list of lanes with slow columns (per chunk: one counter)
+    uint32_t sl_cap = 0;
     int ring_window_shift = 0;           // 0 = chosen by plan_tiles; 14 / 15 = forced (tuning)
     int group_lanes = 0;                 // lanes per cluster in umi_group / select_template (0 = by mean cluster size)
     int force_generic = 0;               // tests: every tile goes to the generic kernel
@@ -173,21 +172,12 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_need, 4 * GCB_MAX_CHUNKS);
     GCB_RES(w_rb_list, 2 * n_pairs * 4);
     GCB_RES(w_rb_count, 4 * GCB_MAX_CHUNKS);
-    {   // slow-column queues: a clean shallow library queues about 0.05 bytes per payload byte, a deep noisy one (1 % errors
-        // at depth 30-100) 1.6-1.9, a vote whose every column is slow (options outside fast_path_implied) about 4; tiles whose
-        // columns do not fit are redone by the generic kernel
-        int64_t qbytes = ctx->slow_queue_bytes > 0 ? ctx->slow_queue_bytes
-                         : fast_path_implied(ctx->opt) ? 3 * payload_bytes + (16ll << 20) : 5 * payload_bytes + (16ll << 20);
-        int64_t cap_words = qbytes / 4 / VQ_NQ;
-        if (cap_words > 0x3FFFFFF0ll) cap_words = 0x3FFFFFF0ll;
-        cap_words &= ~3ll;
-        if (cap_words < 64) cap_words = 64;
-        const int64_t cap_recs = cap_words / 12;  // the smallest record is 12 words
-        GCB_RES(w_sq_count, 8 * VQ_NQ * GCB_MAX_CHUNKS);
-        GCB_RES(w_sq_words, 4 * cap_words * VQ_NQ);
-        GCB_RES(w_sq_index, 4 * cap_recs * VQ_NQ);
-        ctx->sq_cap_words = (uint32_t)cap_words;
-        ctx->sq_cap_recs = (uint32_t)cap_recs;
+    {   // one list entry per sixteen columns of a family side at most (its template's chunk is at least 24 payload bytes), plus the
+        // blocks the ring kernel's warps reserve and may leave partly unused
+        const int64_t cap = payload_bytes / 24 + (int64_t)ctx->n_sms * VR_WARPS * VQ_POOL + 1024;
+        GCB_RES(w_sl_entries, 8 * cap);
+        GCB_RES(w_sl_count, 4 * GCB_MAX_CHUNKS);
+        ctx->sl_cap = (uint32_t)(cap > 0x7FFFFFF0ll ? 0x7FFFFFF0ll : cap);
     }
 #undef GCB_RES
     ws.members = (int32_t *)ctx->w_members.p;
@@ -254,6 +244,14 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
     }
     const int clusters_per_cta = (GROUP_THREADS / WARP) * (WARP / gs);
     const unsigned grid_clusters = (unsigned)((nc + clusters_per_cta - 1) / clusters_per_cta);
+    // select_template_kernel keeps a cluster of at most GS pairs in registers: sixteen lanes unless the clusters are tiny or huge
+    int gs_sel = ctx->group_lanes;
+    if (gs_sel != 8 && gs_sel != 16 && gs_sel != 32) {
+        const int64_t avg = (int64_t)(v.p1 - v.p0) / nc;
+        gs_sel = avg <= 4 ? 8 : avg <= 12 ? 16 : 32;
+    }
+    const int sel_per_cta = (GROUP_THREADS / WARP) * (WARP / gs_sel);
+    const unsigned grid_sel = (unsigned)((nc + sel_per_cta - 1) / sel_per_cta);
 #define GCB_UMI_LAUNCH(NW)                                                                                                                    \
     do {                                                                                                                                      \
         if (gs == 8) GCB_LAUNCH((umi_group_kernel<NW, 8>), dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, plan.window_shift, (int32_t)n_tiles);        \
@@ -270,9 +268,9 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
 #undef GCB_UMI_LAUNCH
     if (stages & GCB_STAGE_SELECT_TEMPLATE) {
         const int32_t n_scan = (int32_t)((nc + SCAN_BLOCK - 1) / SCAN_BLOCK);
-        if (gs == 8) GCB_LAUNCH(select_template_kernel<8>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
-        else if (gs == 16) GCB_LAUNCH(select_template_kernel<16>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
-        else GCB_LAUNCH(select_template_kernel<32>, dim3(grid_clusters), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
+        if (gs_sel == 8) GCB_LAUNCH(select_template_kernel<8>, dim3(grid_sel), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
+        else if (gs_sel == 16) GCB_LAUNCH(select_template_kernel<16>, dim3(grid_sel), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
+        else GCB_LAUNCH(select_template_kernel<32>, dim3(grid_sel), dim3(GROUP_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt);
         GCB_LAUNCH(scan_local_kernel, dim3((unsigned)n_scan), dim3(SCAN_THREADS), 0, stream, ws, nc);
         GCB_LAUNCH(scan_blocks_kernel, dim3(1), dim3(WARP), 0, stream, ws, n_scan, total_out, result.out_capacity, carry_in);
         ctx->launches += 3;
@@ -291,13 +289,11 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         rb.list = (int32_t *)ctx->w_rb_list.p + 2 * (size_t)v.p0;
         rb.count = (int32_t *)ctx->w_rb_count.p + v.index;
         rb.cap = 2 * (v.p1 - v.p0);
-        // ... and its own queue counters (the queues themselves are shared: the chunks' votes never overlap)
-        SlowQueues sq;
-        sq.count = (unsigned long long *)ctx->w_sq_count.p + (size_t)VQ_NQ * v.index;
-        sq.words = (uint32_t *)ctx->w_sq_words.p;
-        sq.index = (uint32_t *)ctx->w_sq_index.p;
-        sq.cap_words = ctx->sq_cap_words;
-        sq.cap_recs = ctx->sq_cap_recs;
+        // ... and its own slow-column list counter (the list itself is shared: the chunks' votes never overlap)
+        SlowList sl;
+        sl.entries = (uint2 *)ctx->w_sl_entries.p;
+        sl.count = (unsigned int *)ctx->w_sl_count.p + v.index;
+        sl.cap = ctx->sl_cap;
         if (run_prep) {
             GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
             GCB_CUDA(ctx, cudaMemsetAsync(max_need, 0, 4, stream));
@@ -307,16 +303,16 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         }
         if (run_fast && plan.ring && !ctx->force_generic) {
             GCB_CUDA(ctx, cudaMemsetAsync(rb.count, 0, 4, stream));
-            GCB_CUDA(ctx, cudaMemsetAsync(sq.count, 0, 8 * VQ_NQ, stream));
+            GCB_CUDA(ctx, cudaMemsetAsync(sl.count, 0, 4, stream));
             const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
             GCB_LAUNCH(vote_ring_kernel, dim3(ring_grid), dim3(VR_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
-                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, rb, (int32_t)n_tiles, plan.arena,
+                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sl, rb, (int32_t)n_tiles, plan.arena,
                        (const int32_t *)max_need);
             ctx->launches++;
         }
         if (run_rest) {
             if (plan.ring && !ctx->force_generic) {
-                GCB_LAUNCH(slow_columns_kernel, dim3(VQ_SLOW_CTAS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ctx->genome, ctx->opt, sq, rb);
+                GCB_LAUNCH(slow_columns_kernel, dim3(VQ_SLOW_CTAS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt, sl, rb);
                 ctx->launches++;
                 GCB_LAUNCH(vote_rollback_kernel, dim3(VQ_FINAL_CTAS), dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->opt, rb, v.p0, v.p1);
                 ctx->launches++;
@@ -406,7 +402,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
     DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
-                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_need, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->w_sq_count, &ctx->w_sq_words, &ctx->w_sq_index, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
+                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_need, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->w_sl_entries, &ctx->w_sl_count, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
                      &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status};
     for (DevBuf *b : all) release(*b);
@@ -689,12 +685,6 @@ int gcb_set_debug(gcb_ctx *ctx, int key, int value) {
     else if (key == 3) ctx->group_lanes = value;                                      // tuning only: same results
     else if (key == 5) ctx->force_generic = value != 0;                               // tests: the generic kernel votes every tile
     else return GCB_ERR_ARG;
-    return GCB_OK;
-}
-
-int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes) {
-    if (!ctx || bytes < 0) return GCB_ERR_ARG;
-    ctx->slow_queue_bytes = bytes;
     return GCB_OK;
 }
 

@@ -9,6 +9,17 @@
 
 namespace gcb {
 
+// coverage counters of the CPU SIMT-check build (tests only): ring tiles, generic tiles, voted columns, slow columns,
+// uniform family sides, non-uniform family sides, clusters selected in registers, arena wrap-arounds
+#ifdef GCB_SIMT_CHECK
+inline int64_t g_simt_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define GCB_COUNT(k, n) (g_simt_counters[k] += (n))
+#define GCB_TRACE(tag) ::simt::trace(tag)
+#else
+#define GCB_COUNT(k, n) ((void)0)
+#define GCB_TRACE(tag) ((void)0)
+#endif
+
 struct BatchView {  // gcb_batch with device pointers
     int32_t n_clusters, n_pairs, umi_words;
     const int32_t *cluster_pair_off;
@@ -415,6 +426,206 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
 #undef GCB_CIG
 }
 
+// ------------------------------------------------------------------------------------------------
+// The usual cluster in registers: at most GS pairs, every pair with both reads, every read one CIGAR op, and inside every
+// family the reads of a side identical in length, position and CIGAR.  Then (group.cpp:136-313) every read is part of every
+// other, the containment counts tie, the lengths tie, so a family's template is its first read in map order, every read
+// votes, and the columns are left-aligned on both sides — what side_select computes for such a family through its `same`
+// shortcut.  Here lane i of the group holds pair i's two descriptors for the whole cluster: the family of a pair comes
+// from pair_group (members are in pair order), the template's geometry by shuffle, and nothing is read twice — the general
+// path below walks a chain of dependent loads (members -> descriptor -> CIGAR) per family and side.
+// Returns false (nothing written) when the cluster is not of that kind.
+template <int GS>
+GCB_DEV bool select_cluster_fast(const Grp<GS> &g, const BatchView &b, const ResultView &r, const Workspace &ws, const GenomeView &gv, int c, int p0,
+                                 int n, int G) {
+    const int lane = g.gl;
+    const bool act = lane < n;
+    const int64_t pair = p0 + (act ? lane : 0);
+    const uint4 *dp = (const uint4 *)(b.reads + 2 * pair);
+    const uint4 l0 = dp[0], l1 = dp[1], r0 = dp[2], r1 = dp[3];  // gcb_read_desc: {data_off lo, hi, l_qseq, pos} {isize, cigar_off, n_cigar | l_qname << 16, -}
+    const int gid = act ? r.pair_group[pair] : -1;
+    const int64_t slab0 = ws.slab_off[c];
+    const int L_l = (int)l0.z, L_pos = (int)l0.w, L_isize = (int)l1.x, L_ncig = (int)(l1.z & 0xFFFFu), L_lqn = (int)(l1.z >> 16);
+    const int R_l = (int)r0.z, R_pos = (int)r0.w, R_isize = (int)r1.x, R_ncig = (int)(r1.z & 0xFFFFu), R_lqn = (int)(r1.z >> 16);
+    const int64_t L_off = ((int64_t)l0.y << 32 | l0.x) - slab0, R_off = ((int64_t)r0.y << 32 | r0.x) - slab0;
+    bool ok = !act || (L_l >= 0 && R_l >= 0 && L_ncig == 1 && R_ncig == 1);
+    // every field of a VoteRead must fit its 16 bits (make_vote_read)
+    ok = ok && (!act || (L_off >= 0 && R_off >= 0 && (L_off >> 2) < VR_NO_VOTE && (R_off >> 2) < VR_NO_VOTE && L_l <= 0x7FFF && R_l <= 0x7FFF));
+    if (!g.all(ok)) return false;
+    const uint32_t L_cig = act ? b.cigar[(int)l1.y] : 0u, R_cig = act ? b.cigar[(int)r1.y] : 0u;
+    // pair.cpp:103-119: the overlap window of the pair (both reads have one op: an M block or nothing)
+    PairOverlap ov = {0, 0, 0, 0};
+    {
+        const int ll = cig_op(L_cig) == OP_MATCH ? cig_len(L_cig) : 0, rl = cig_op(R_cig) == OP_MATCH ? cig_len(R_cig) : 0;
+        if (ll > 0 && rl > 0) {
+            const int posDis = R_pos - L_pos;
+            ov.valid = 1;
+            if (posDis >= 0) {
+                ov.left_start = posDis;
+                ov.right_start = 0;
+                ov.cmp_len = min(ll - posDis, rl);
+            } else {
+                ov.left_start = 0;
+                ov.right_start = 0 - posDis;
+                ov.cmp_len = min(ll, rl + posDis);
+            }
+        }
+    }
+    // the two VoteReads of the pair (make_vote_read with every read voting, no column shift)
+    VoteRead v[2];
+    bool fits = true;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        VoteRead w = {VR_NO_VOTE, 0, 0, 0, 0, 0, 0, 0};
+        const int own_l = side == 0 ? L_l : R_l, mate_l = side == 0 ? R_l : L_l;
+        w.own_off4 = (uint16_t)((side == 0 ? L_off : R_off) >> 2);
+        w.own_l = (int16_t)own_l;
+        w.shift = 0;
+        w.ov_len = VR_NO_OVERLAP_INFO;
+        if (ov.valid) {
+            int own = side == 0 ? ov.left_start : ov.right_start, mate = side == 0 ? ov.right_start : ov.left_start, len = ov.cmp_len;
+            const int lim = 0x3FFFFFFF;
+            own = own < -lim ? -lim : own > lim ? lim : own;
+            mate = mate < -lim ? -lim : mate > lim ? lim : mate;
+            len = len < -lim ? -lim : len > lim ? lim : len;
+            const int a = own > 0 ? own : 0;
+            const int e = own + len < own_l ? own + len : own_l;
+            if (len > 0 && e > a) {  // the window clipped to this read's own indices
+                mate += a - own;
+                own = a;
+                len = e - a;
+            } else {
+                own = mate = len = 0;
+            }
+            if (mate < -0x8000 || mate > 0x7FFF) fits = false;
+            w.mate_off4 = (uint16_t)((side == 0 ? R_off : L_off) >> 2);
+            w.mate_l = (int16_t)mate_l;
+            w.ov_own = (int16_t)own;
+            w.ov_mate = (int16_t)mate;
+            w.ov_len = (int16_t)len;
+        }
+        v[side] = w;
+    }
+    if (!g.all(!act || fits)) return false;
+    // every family: its members are the lanes whose pair_group names it, in lane (= map) order
+    bool same = true;
+    for (int gi = 0; gi < G; gi++) {
+        const unsigned fm = g.ballot(gid == gi);
+        if (fm == 0u) return false;  // (cannot happen: every family has a pair)
+        const int first = __ffs((int)fm) - 1 + g.base;
+        const bool mem = gid == gi;
+        // (every lane of the group takes part in every shuffle)
+        const int fl = __shfl_sync(g.mask, L_l, first), fp = __shfl_sync(g.mask, L_pos, first), gl_ = __shfl_sync(g.mask, R_l, first),
+                  gp = __shfl_sync(g.mask, R_pos, first);
+        const uint32_t fc = __shfl_sync(g.mask, L_cig, first), gc = __shfl_sync(g.mask, R_cig, first);
+        same = same && (!mem || (L_l == fl && L_pos == fp && L_cig == fc && R_l == gl_ && R_pos == gp && R_cig == gc));
+    }
+    if (!g.all(same)) return false;
+
+    // ---- the cluster is of the usual kind: write what select_template_kernel's general path would
+    if (act) {
+        ws.overlap[pair] = ov;
+        *(uint16_t *)(ws.vote_flags + 2 * pair) = (uint16_t)(VOTE_PARTICIPATES | (VOTE_PARTICIPATES << 8));
+    }
+    if (lane >= G && act) {  // slots that hold no family
+        *(uint16_t *)(ws.side_mode + 2 * pair) = (uint16_t)(SIDE_NONE | (SIDE_NONE << 8));
+        int2 *row = (int2 *)(r.groups + pair);
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(gcb_group_result) / 8); q++) row[q] = make_int2(0, 0);
+    }
+    const int contig = b.cluster_ref[c];
+    int64_t out_rel = 0;
+    int mb = p0;  // families lie in `members` in creation order
+    for (int gi = 0; gi < G; gi++) {
+        const unsigned fm = g.ballot(gid == gi);
+        const int m = __popc(fm), first = __ffs((int)fm) - 1 + g.base;
+        const bool mem = gid == gi;
+        const int rank = __popc(fm & ((1u << lane) - 1u));
+        // the template's entries (the family's first pair), for the uniformity test of group.cpp's FS_UNIFORM shortcut
+        uint32_t w0[4], w1[4], t0[4], t1[4];
+        memcpy(w0, &v[0], 16);
+        memcpy(w1, &v[1], 16);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            t0[q] = __shfl_sync(g.mask, w0[q], first);
+            t1[q] = __shfl_sync(g.mask, w1[q], first);
+        }
+        VoteRead tv[2];
+        memcpy(&tv[0], t0, 16);
+        memcpy(&tv[1], t1, 16);
+        bool uni[2];
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const VoteRead &x = v[side], &t = tv[side];
+            // (same length, no shift: given) same overlap window and the same distance from a read's record to its mate's
+            const bool u = !mem || (x.ov_len == t.ov_len && (x.ov_len <= 0 || (x.ov_own == t.ov_own && x.ov_mate == t.ov_mate && x.mate_l == t.mate_l &&
+                                                                                (uint16_t)(x.mate_off4 - x.own_off4) == (uint16_t)(t.mate_off4 - t.own_off4))));
+            uni[side] = g.all(u);
+        }
+        if (mem) {
+            ws.vote_reads[2 * (int64_t)mb + rank] = v[0];
+            ws.vote_reads[2 * (int64_t)mb + m + rank] = v[1];
+        }
+        if (lane + g.base == first) {
+            const int slot = p0 + gi;
+            const int left = 2 * (int)pair, right = left + 1;
+            gcb_group_result gr;
+            gr.tmpl_read[0] = left;
+            gr.tmpl_read[1] = right;
+            gr.qname_donor[0] = gr.qname_donor[1] = -1;
+            int name_slot;
+            if (L_lqn <= R_lqn) { gr.qname_donor[1] = left; name_slot = left; }  // group.cpp:114-123
+            else { gr.qname_donor[0] = right; name_slot = right; }
+            gr.diff[0] = gr.diff[1] = 0;
+            gr.mismatch_inc[0] = gr.mismatch_inc[1] = 0;
+            gr.merge_reads = m;
+            gr.reverse_merge_reads = 0;
+            gr.status = 0;
+            gr.duplex_partner = -1;
+            gr.duplex_diff = 0;
+            gr.umi_pair = name_slot / 2;
+            int64_t orel = out_rel;
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                const int l_out = side == 0 ? L_l : R_l, pos = side == 0 ? L_pos : R_pos, isize = side == 0 ? L_isize : R_isize;
+                const uint32_t cg = side == 0 ? L_cig : R_cig;
+                FsDesc fd = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, 0};
+                fd.c = c;
+                if (isize != 0 && gv.packed4 && contig >= 0 && contig < gv.n_contigs) {  // group.cpp:362-367 + reference.cpp:33-71
+                    const int64_t span = (int64_t)get_ref_offset(&cg, 1, l_out - 1) + 1;
+                    if ((int64_t)pos + span < gv.contig_len[contig]) {
+                        fd.flags |= FS_REF_OK;
+                        fd.ref_nib0 = 2 * gv.contig_off[contig] + pos;
+                    }
+                }
+                const int op = cig_op(cg);
+                if (query_consum(op) && ref_consum(op) && cig_len(cg) >= l_out) fd.flags |= FS_SIMPLE_CIGAR;
+                if (uni[side]) fd.flags |= FS_UNIFORM;
+                gr.out_off[side] = orel;  // cluster-relative; the vote rebases it after the scan
+                fd.mb = mb;
+                fd.m = (uint16_t)m;
+                fd.l_out = (uint16_t)l_out;
+                fd.len = (uint16_t)l_out;
+                fd.tmpl_k = 0;
+                fd.mode = SIDE_LEFT;
+                fd.out_rel = (uint32_t)orel;
+                if (orel > 0xFFFFFFFFll) fd.flags |= FS_NOFIT;
+                orel += record_bytes(l_out);
+                ws.fs_desc[2 * (int64_t)slot + side] = fd;
+            }
+            *(uint16_t *)(ws.side_mode + 2 * (int64_t)slot) = (uint16_t)(SIDE_LEFT | (SIDE_LEFT << 8));
+            r.groups[slot] = gr;
+        }
+        out_rel += record_bytes(__shfl_sync(g.mask, L_l, first)) + record_bytes(__shfl_sync(g.mask, R_l, first));
+        mb += m;
+    }
+    if (lane == 0) {
+        ws.cluster_out_bytes[c] = out_rel;
+        GCB_COUNT(6, 1);
+    }
+    return true;
+}
+
 // group.cpp:68-134 per family of the cluster + the per-pair overlap windows of pair.cpp:103-119
 template <int GS>
 __global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o) {
@@ -425,6 +636,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(Batc
     const int p0 = b.cluster_pair_off[c], p1 = b.cluster_pair_off[c + 1], n = p1 - p0;
     const int G = r.cluster_n_groups[c];
     const bool crossContig = (b.cluster_flags[c] & GCB_CLUSTER_CROSS_CONTIG) != 0;
+    if (n > 0 && n <= GS && !crossContig && select_cluster_fast<GS>(g, b, r, ws, gv, c, p0, n, G)) return;
 
     for (int i = lane; i < n; i += GS) {
         const int64_t pair = p0 + i;

@@ -1,167 +1,120 @@
-// k_slow_columns.cuh — the slow columns of the vote, decided at full occupancy: group.cpp:376-525 for every column the
-// ring kernel (k_vote_ring.cuh) could not finish in the word.
+// k_slow_columns.cuh — the slow columns of the vote: group.cpp:376-525 for every column the ring kernel (k_vote_ring.cuh)
+// could not finish in the word, one THREAD per column.
 //
-// The ring kernel keeps a tile's payload in shared memory only as long as its warps vote; what a slow column needs of the
-// tile — per read of the family side its quality, its base nibble, its mate's quality and base nibble and where
-// pair.cpp:121-170 puts the column (no overlap information / outside the overlap / mate base present / mate index out of
-// range): 4 bytes per read behind a 32-byte self-contained header — is extracted by the warp that closes the tile, one
-// thread per column, into a global queue (one 64-bit atomic per tile reserves the tile's records and words in one
-// counter).  slow_columns_kernel then takes one record per thread: score per read (pair.cpp), three-bin
-// register histogram (group.cpp:376-393), top-2 selection (group.cpp:395-417), the rules and the reference arbitration
-// (group.cpp:419-525); it patches the consensus record and adds to the family side's diff / mismatchInc (atomics on the
-// result row; the ring kernel zeroed them).  The deciding is a chain of dependent small loads: it wants many resident
-// warps, which the one-CTA-per-SM ring cannot give it.
+// decide_column() is the decision itself, over pointers to the family side's VoteRead entries and to its cluster's slab:
+// score per read (pair.cpp:121-170), three-bin register histogram (group.cpp:376-393), top-2 selection (group.cpp:395-417),
+// the rules and the reference arbitration (group.cpp:419-525); it patches the consensus record and adds to the family
+// side's diff / mismatchInc (atomics on the result row; the ring kernel zeroed them).  Two callers:
+//   * the ring kernel itself for tiles of deep families (hundreds of slow columns per tile, decided by all the voter warps
+//     from the staged slab in shared memory);
+//   * slow_columns_kernel for everything else.  The ring kernel only LISTS those columns — 8 bytes per lane that found any:
+//     family side, lane, 16-bit column mask — and never waits for them; this kernel, launched right behind it at full
+//     occupancy, reads the few bytes a column needs (per read a quality, a base nibble and the mate's) from the payload in
+//     global memory.  The deciding is a chain of dependent small loads that wants many resident warps, which the
+//     one-CTA-per-SM ring cannot give it; extracting the bytes inside the ring instead (measured both per bundle and per
+//     tile: profiles/r03_notes.md) either costs a third of the ring's instructions or holds every stage while one warp
+//     walks the tile's list.
 #pragma once
 
 #include "vote_tile.cuh"
 
 namespace gcb {
 
-constexpr int VQ_NQ = 1;                       // slow-column queues; the tiles of CTA b use queue b % VQ_NQ (one reservation per tile: one
-                                               // counter takes them all, and the whole capacity is there for whoever needs it)
-constexpr uint32_t VQ_INVALID = 0xFFFFFFFFu;   // index entry of a reservation that did not fit
 constexpr int VQ_SLOW_THREADS = 128;
-constexpr int VQ_SLOW_CTAS = 148 * 8;          // slow_columns_kernel strides over the records
+constexpr int VQ_SLOW_CTAS = 148 * 8;          // slow_columns_kernel strides over the list
+constexpr uint32_t VQ_POOL = 128;              // list entries a voter warp reserves at a time (one global atomic)
 
-struct SlowQueues {
-    unsigned long long *count;   // [VQ_NQ] records << 32 | words reserved so far (may run past the capacity)
-    uint32_t *words;             // [VQ_NQ][cap_words] records (see SR_HDR_WORDS)
-    uint32_t *index;             // [VQ_NQ][cap_recs] word offset of every record inside its queue, VQ_INVALID = none
-    uint32_t cap_words, cap_recs;
+struct SlowList {   // the ring kernel's list of lanes with slow columns
+    uint2 *entries;          // .x = 2 * slot + side, .y = lane of the family side << 16 | column mask (bit 8 * w + i = column 8 * w + 7 - i); .y == 0: unused
+    unsigned int *count;     // [1] entries reserved so far
+    uint32_t cap;            // >= one entry per sixteen columns of every family side: the list cannot overflow
 };
 
-// record: SR_HDR_WORDS header words, then n entries (one per read of the family side), padded to a multiple of 4 words.
-// The header is self-contained (slow_columns_kernel needs no table lookup):
-//   [0] 2 * slot + side   [1] col | n << 16   [2] tmpl_k | flags << 16   [3] l_out
-//   [4..5] absolute offset of the consensus record in out_payload   [6..7] FsTile.ref_nib0
-constexpr int SR_HDR_WORDS = 8;
-constexpr uint32_t SR_UNVOTED = 1u;        // column beyond the voted length: the record keeps the template's (rewritten) quality
-constexpr uint32_t SR_REF_OK = 2u;         // FS_REF_OK
-constexpr uint32_t SR_SIMPLE_CIGAR = 4u;   // FS_SIMPLE_CIGAR
-// entry: quality | mate quality << 8 | base << 16 | mate base << 20 | state << 24 | SE_VOTES
-constexpr uint32_t SE_VOTES = 1u << 26;
-constexpr uint32_t SE_NO_INFO = 0u, SE_PLAIN = 1u, SE_MATE = 2u, SE_NO_MATE_BASE = 3u;
+// what a column's decision needs to know of its family side
+struct SlowSide {
+    int m, l_out, len, tmpl_k, side, flags, slot;
+    int64_t ref_nib0;
+};
 
-GCB_DEV uint32_t slow_rec_words(int m) { return (uint32_t)SR_HDR_WORDS + (((uint32_t)m + 3u) & ~3u); }
-GCB_DEV void slow_write_header(uint32_t *rec, const FsTile &ft, int col, int64_t out_abs) {
-    const uint32_t side = (ft.flags & FS_SIDE1) ? 1u : 0u;
-    const uint32_t fl = (col >= (int)ft.len ? SR_UNVOTED : 0u) | ((ft.flags & FS_REF_OK) ? SR_REF_OK : 0u) |
-                        ((ft.flags & FS_SIMPLE_CIGAR) ? SR_SIMPLE_CIGAR : 0u);
-    uint4 a, c;
-    a.x = 2u * (uint32_t)ft.slot + side;
-    a.y = (uint32_t)col | ((uint32_t)ft.m << 16);
-    a.z = (uint32_t)ft.tmpl_k | (fl << 16);
-    a.w = (uint32_t)ft.l_out;
-    c.x = (uint32_t)(uint64_t)out_abs; c.y = (uint32_t)((uint64_t)out_abs >> 32);
-    c.z = (uint32_t)(uint64_t)ft.ref_nib0; c.w = (uint32_t)((uint64_t)ft.ref_nib0 >> 32);
-    ((uint4 *)rec)[0] = a;
-    ((uint4 *)rec)[1] = c;
-}
-
-// what pair.cpp:88-172 needs of read `v` at template column `col`, as a queue entry (0 = the read has no base there)
-GCB_DEV uint32_t slow_entry(const uint8_t *cb, const VoteRead &v, int col) {
-    const int rp = col + v.shift;
-    if (v.own_off4 == VR_NO_VOTE || rp < 0 || rp >= v.own_l) return 0u;
-    const uint8_t *q = cb + 4 * (int)v.own_off4;
-    const uint32_t ql = q[rp];
-    const uint32_t base = (uint32_t)base_at(q + GCB_ALIGN4(v.own_l), rp);
-    const bool info = v.ov_len != VR_NO_OVERLAP_INFO;
-    const int k = rp - v.ov_own, mp = v.ov_mate + k;
-    const bool inwin = info && k >= 0 && k < v.ov_len;
-    const bool mvalid = inwin && mp >= 0 && mp < v.mate_l;
-    uint32_t mql = 0u, mbase = 0u;
-    if (mvalid) {
-        const uint8_t *mq = cb + 4 * (int)v.mate_off4;
-        mql = mq[mp];
-        mbase = (uint32_t)base_at(mq + GCB_ALIGN4(v.mate_l), mp);
-    }
-    const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
-    return ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
-}
-
-// base, rewritten quality and score of a queue entry: the same function of the same bytes as fetch_vote
-GCB_DEV bool slow_decode(const ScoreTab &t, uint32_t ent, int side, int &base, int &qual, int &score) {
-    if (!(ent & SE_VOTES)) return false;
-    const int ql = (int)(ent & 0xFFu), mql = (int)((ent >> 8) & 0xFFu);
-    base = (int)((ent >> 16) & 0xFu);
-    const int mbase = (int)((ent >> 20) & 0xFu);
-    const uint32_t st = (ent >> 24) & 3u;
-    const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
-    const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
-    const int s_match = sc8(t.q2s((ql + mql) / 2) + 4);                        // pair.cpp:147-152
-    const int s_mis = mine ? sc8(t.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;  // pair.cpp:153-169
-    const bool mism = st == SE_MATE && base != mbase;
-    score = st == SE_MATE ? (mism ? s_mis : s_match) : st == SE_PLAIN ? t.q2s(ql) : t.sm;
-    qual = mism ? max(0, ql - mql) : ql;
-    return true;
-}
-
-// ------------------------------------------------------------------------------------------------
-// A fourth distinct code in one column: the sixteen-bin histogram in local memory (group.cpp:376-417 as written).
-__device__ __noinline__ void slow_record_wide(const gcb_options &o, const uint32_t *ents, int n, int side, ColumnTop &ct, int &total_out,
-                                              uint32_t &acgt_out) {
+GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const GenomeView &gv, const gcb_options &o, const RollbackList &rb,
+                           const SlowSide &fs, const uint8_t *cb, const VoteRead *ents, uint8_t *out, int col) {
     const ScoreTab tab(o);
-    int32_t bins[64];
-    for (int k = 0; k < 64; k++) bins[k] = 0;
-    for (int e = 0; e < n; e++) {
-        int base, qual, score;
-        if (!slow_decode(tab, ents[e], side, base, qual, score)) continue;
-        bins[4 * base]++;
-        bins[4 * base + 1] += score;
-        bins[4 * base + 2] += qual;
-        bins[4 * base + 3] = max(bins[4 * base + 3], qual);
-    }
-    VoteBin obs[16];
-    int nobs = 0, total = 0;
-    for (int k = 0; k < 16; k++) {
-        const int cnt = bins[4 * k];
-        if (cnt > 0) {
-            obs[nobs].base = k; obs[nobs].cnt = cnt; obs[nobs].score = bins[4 * k + 1]; obs[nobs].qual = bins[4 * k + 2]; obs[nobs].maxq = bins[4 * k + 3];
-            total += obs[nobs].score;
-            nobs++;
-        }
-    }
-    ct = column_top(o, obs, nobs, total);
-    total_out = total;
-    acgt_out = (uint32_t)(bins[4 * 1] > 0 ? bins[4 * 1 + 3] : 0) | ((uint32_t)(bins[4 * 2] > 0 ? bins[4 * 2 + 3] : 0) << 8) |
-               ((uint32_t)(bins[4 * 4] > 0 ? bins[4 * 4 + 3] : 0) << 16) | ((uint32_t)(bins[4 * 8] > 0 ? bins[4 * 8 + 3] : 0) << 24);
-}
-
-// group.cpp:376-525 for one queued column
-GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeView &gv, const gcb_options &o, const ScoreTab &tab,
-                         const RollbackList &rb, const uint32_t *rec) {
-    const uint4 ha = ((const uint4 *)rec)[0], hc = ((const uint4 *)rec)[1];
-    const uint32_t fsid = ha.x, w1 = ha.y, w2 = ha.z;
-    const int col = (int)(w1 & 0xFFFFu), n = (int)(w1 >> 16), tmpl_k = (int)(w2 & 0xFFFFu);
-    const uint32_t flags = w2 >> 16;
-    const uint32_t *ents = rec + SR_HDR_WORDS;
-    const int side = (int)(fsid & 1u);
-    const int qbytes = GCB_ALIGN4((int)ha.w);
-    uint8_t *out = r.out_payload + (int64_t)(((uint64_t)hc.y << 32) | hc.x);
-    const int64_t ref_nib0 = (int64_t)(((uint64_t)hc.w << 32) | hc.z);
+    const VoteRead tv = ents[fs.tmpl_k];
+    const int side = fs.side;
+    const int qbytes = GCB_ALIGN4(fs.l_out);
     GCB_COUNT(3, 1);
-    if (flags & SR_UNVOTED) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
+    if (col >= fs.len) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
         int obase = 0, oqual = 0, sc;
-        slow_decode(tab, ents[tmpl_k], side, obase, oqual, sc);
+        fetch_ent(cb, tv, col, side, o, obase, oqual, sc);
         out[col] = (uint8_t)oqual;
         return;
     }
     Bins3 bins;
     bins.init();
-    for (int e = 0; e < n; e += 4) {  // (records are padded to whole 16-byte groups of entries)
-        const uint4 v = *(const uint4 *)(ents + e);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
+    const int m = fs.m;
+    if (fs.flags & FS_UNIFORM) {
+        const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
+        const int k = col - (int)tv.ov_own, mp = (int)tv.ov_mate + k;
+        const bool inwin = info && k >= 0 && k < (int)tv.ov_len;
+        const bool mvalid = inwin && mp >= 0 && mp < (int)tv.mate_l;
+        const bool plain = info && !inwin;  // pair.cpp:121-131: outside the overlap the score follows the quality
+        const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
+        const int mpi = mvalid ? mp : 0;
+        const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
+        for (int e = 0; e < m; e++) {
+            const uint32_t w = *(const uint32_t *)(ents + e);  // own_off4 | mate_off4 << 16
+            if ((w & 0xFFFFu) == VR_NO_VOTE) continue;
+            const uint8_t *rec = cb + 4 * (int)(w & 0xFFFFu);
+            int ql = rec[col];
+            const int base = (rec[soff] >> nsh) & 0xF;
+            int score;
+            if (mvalid) {
+                const uint8_t *mrec = cb + 4 * (int)(w >> 16);
+                const int mql = mrec[mpi];
+                const int mbase = (mrec[msoff] >> mnsh) & 0xF;
+                const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
+                const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
+                const int s_match = sc8(tab.q2s((ql + mql) / 2) + 4);                        // pair.cpp:147-152
+                const int s_mis = mine ? sc8(tab.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;  // pair.cpp:153-169
+                score = base == mbase ? s_match : s_mis;
+                ql = base == mbase ? ql : max(0, ql - mql);
+            } else {
+                score = plain ? tab.q2s(ql) : tab.sm;
+            }
+            bins.add(base, ql, score);
+        }
+    } else {
+        for (int e = 0; e < m; e++) {
             int base, qual, score;
-            if (e + k < n && slow_decode(tab, w[k], side, base, qual, score)) bins.add(base, qual, score);
+            if (fetch_vote(cb, ents[e], col, side, tab, base, qual, score)) bins.add(base, qual, score);
         }
     }
     ColumnTop ct;
     int total = bins.total;
-    uint32_t acgt = 0;
-    if (bins.overflow) {
-        slow_record_wide(o, ents, n, side, ct, total, acgt);
+    uint32_t acgt = 0;  // the best quality of codes 1, 2, 4, 8 in bytes 0..3 (0 when nobody showed the code)
+    if (bins.overflow) {  // a fourth distinct code: the sixteen-bin histogram in local memory (group.cpp:376-417 as written)
+        int32_t h[64];
+        for (int q = 0; q < 64; q++) h[q] = 0;
+        for (int e = 0; e < m; e++) {
+            int base, qual, score;
+            if (!fetch_ent(cb, ents[e], col, side, o, base, qual, score)) continue;
+            h[4 * base]++;
+            h[4 * base + 1] += score;
+            h[4 * base + 2] += qual;
+            h[4 * base + 3] = max(h[4 * base + 3], qual);
+        }
+        VoteBin obs[16];
+        int nobs = 0;
+        total = 0;
+        for (int q = 0; q < 16; q++)
+            if (h[4 * q] > 0) {
+                obs[nobs].base = q; obs[nobs].cnt = h[4 * q]; obs[nobs].score = h[4 * q + 1]; obs[nobs].qual = h[4 * q + 2]; obs[nobs].maxq = h[4 * q + 3];
+                total += obs[nobs].score;
+                nobs++;
+            }
+        ct = column_top(o, obs, nobs, total);
+        acgt = (uint32_t)(h[4 * 1] > 0 ? h[4 * 1 + 3] : 0) | ((uint32_t)(h[4 * 2] > 0 ? h[4 * 2 + 3] : 0) << 8) |
+               ((uint32_t)(h[4 * 4] > 0 ? h[4 * 4 + 3] : 0) << 16) | ((uint32_t)(h[4 * 8] > 0 ? h[4 * 8 + 3] : 0) << 24);
     } else {
         // top and second: every bin competes with its (score, quality sum, code) key; the codes nobody showed compete
         // with (0, 0, code), of which only the two largest can place
@@ -197,15 +150,15 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
         new_qual = ct.top.maxq;  // group.cpp:422-426: the base is NOT written
     } else {
         // the record's base before the vote: the template's own (pair.cpp rewrites qualities, never bases)
-        const int obase = (int)((ents[tmpl_k] >> 16) & 0xFu);
+        const int obase = base_at(cb + 4 * (int)tv.own_off4 + qbytes, col);
         int ref4 = 0;
-        if (flags & SR_REF_OK) {  // group.cpp:430-439
+        if (fs.flags & FS_REF_OK) {  // group.cpp:430-439
             int refpos = col;
-            if (!(flags & SR_SIMPLE_CIGAR)) {
-                const gcb_read_desc od = b.reads[r.groups[fsid >> 1].tmpl_read[side]];
+            if (!(fs.flags & FS_SIMPLE_CIGAR)) {
+                const gcb_read_desc od = b.reads[r.groups[fs.slot].tmpl_read[side]];
                 refpos = get_ref_offset(b.cigar + od.cigar_off, od.n_cigar, col);
             }
-            const int64_t nib = ref_nib0 + refpos;
+            const int64_t nib = fs.ref_nib0 + refpos;
             if (refpos >= 0 && nib >= 0 && (nib >> 1) < gv.packed_bytes) {  // the bound only guards malformed CIGARs
                 const uint8_t two = gv.packed4[nib >> 1];
                 ref4 = genome_nibble_to_bam((nib & 1) ? (two >> 4) : (two & 0xF));
@@ -217,13 +170,13 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
             const int rmax = (int)((acgt >> (ref4 == 1 ? 0 : ref4 == 2 ? 8 : ref4 == 4 ? 16 : 24)) & 0xFFu);
             if (rmax >= 128) {  // `char refBaseQual` wraps: the scan order matters (group.cpp:474-490): template first
                 int tb, tq, ts;
-                if (slow_decode(tab, ents[tmpl_k], side, tb, tq, ts) && tb == ref4) {
+                if (fetch_ent(cb, tv, col, side, o, tb, tq, ts) && tb == ref4) {
                     if (tq > rbq) rbq = sc8(tq);
                     if (tq >= o.high_quality) any_high = true;
                 }
-                for (int e = 0; e < n; e++) {
+                for (int e = 0; e < m; e++) {
                     int base, qual, score;
-                    if (e == tmpl_k || !slow_decode(tab, ents[e], side, base, qual, score) || base != ref4) continue;
+                    if (e == fs.tmpl_k || !fetch_ent(cb, ents[e], col, side, o, base, qual, score) || base != ref4) continue;
                     if (qual > rbq) rbq = sc8(qual);
                     if (qual >= o.high_quality) any_high = true;
                 }
@@ -239,13 +192,13 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
                 if (obase == ref4) d_mm = 1;
                 else if (co.base == ref4) d_mm = -1;
             }
-            gcb_group_result *gr = r.groups + (fsid >> 1);  // (fsid = 2 * slot + side; the ring kernel zeroed both counters)
+            gcb_group_result *gr = r.groups + fs.slot;  // (the bundle's lane 0 zeroed both counters before the tile was closed)
             atomicAdd(&gr->diff[side], 1);
             if (d_mm != 0) {
                 const int before = atomicAdd(&gr->mismatch_inc[side], d_mm);
                 if (d_mm > 0 && before == 5) {  // more than five new mismatches so far: vote_rollback_kernel looks at the final count
-                    const int k = atomicAdd(rb.count, 1);
-                    if (k < rb.cap) rb.list[k] = (int32_t)fsid;
+                    const int kk = atomicAdd(rb.count, 1);
+                    if (kk < rb.cap) rb.list[kk] = 2 * fs.slot + side;
                 }
             }
             const int byte = col >> 1;
@@ -257,28 +210,29 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
     out[col] = (uint8_t)new_qual;
 }
 
-__global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView b, ResultView r, GenomeView gv, gcb_options o, SlowQueues sq,
-                                                                       RollbackList rb) {
-    // the records of all queues as one index space, so that every warp but the last is full
-    __shared__ uint32_t s_first[VQ_NQ + 1];
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int q = 0; q < VQ_NQ; q++) {
-            s_first[q] = run;
-            const uint32_t reserved = (uint32_t)(sq.count[q] >> 32);
-            run += reserved < sq.cap_recs ? reserved : sq.cap_recs;
-        }
-        s_first[VQ_NQ] = run;
-    }
-    __syncthreads();
-    const uint32_t total = s_first[VQ_NQ];
-    const ScoreTab tab(o);
+// a column of a family side, everything read from global memory
+GCB_DEV void decide_column_global(const BatchView &b, const ResultView &r, const Workspace &ws, const GenomeView &gv, const gcb_options &o,
+                                  const RollbackList &rb, uint32_t fsid, int col) {
+    const FsDesc d = ws.fs_desc[fsid];
+    SlowSide fs;
+    fs.m = d.m; fs.l_out = d.l_out; fs.len = d.len; fs.tmpl_k = d.tmpl_k; fs.side = (int)(fsid & 1u); fs.flags = d.flags; fs.slot = (int)(fsid >> 1);
+    fs.ref_nib0 = d.ref_nib0;
+    const VoteRead *ents = ws.vote_reads + 2 * (int64_t)d.mb + (int64_t)fs.side * d.m;
+    decide_column(b, r, gv, o, rb, fs, b.payload + ws.slab_off[d.c], ents, r.out_payload + r.groups[fs.slot].out_off[fs.side], col);
+}
+
+__global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o,
+                                                                       SlowList sl, RollbackList rb) {
+    const uint32_t total = min(*sl.count, sl.cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int q = 0;
-        while (q + 1 < VQ_NQ && s_first[q + 1] <= i) q++;
-        const uint32_t off = sq.index[(size_t)q * sq.cap_recs + (i - s_first[q])];
-        if (off == VQ_INVALID) continue;
-        slow_record(b, r, gv, o, tab, rb, sq.words + (size_t)q * sq.cap_words + off);
+        const uint2 e = sl.entries[i];
+        uint32_t mask = e.y & 0xFFFFu;
+        const int col0 = VT_CHUNK * (int)(e.y >> 16);
+        while (mask != 0u) {
+            const int bit = __ffs((int)mask) - 1;
+            mask &= mask - 1u;
+            decide_column_global(b, r, ws, gv, o, rb, e.x, col0 + (bit & 8) + 7 - (bit & 7));
+        }
     }
 }
 

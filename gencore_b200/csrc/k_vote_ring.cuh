@@ -16,16 +16,15 @@
 //                     moderateQuality: exactly group.cpp:421-427 under `implied`) are finished in the word: per-column maxima
 //                     in 16-bit lanes (VIMNMX3.U16x2 over two reads per iteration), disagreement as OR-accumulated XOR
 //                     residues of the raw words; uniform families (every fixed-length library) run a branch-free loop.
-//   slow columns      a lane that found slow columns appends ONE list entry (family side, lane, 16-bit column mask) to the
-//                     stage's list.  The warp that finishes the tile's last bundle closes the tile: it turns the list into
-//                     prefix sums (columns, queue words), reserves the tile's records in a global queue with one 64-bit
-//                     atomic and EXTRACTS what the columns need of the tile, one thread per column, 32 columns at a time:
-//                     per read its quality, base, mate quality, mate base and overlap state (k_slow_columns.cuh).  The
-//                     stage is released as soon as that is written; slow_columns_kernel decides the columns afterwards at
-//                     full occupancy.  (Deciding them here, from the staged slab, was measured: the chain of dependent
-//                     loads of a column held every stage for microseconds and the voters starved — profiles/r03_notes.md.)
-//   queue overflow    the tile is handed to the generic kernel (score_vote_kernel), which runs last and rewrites all of the
-//                     tile's records from the payload.
+//   slow columns      a lane that found slow columns appends ONE 8-byte entry (family side, lane, 16-bit column mask) to a
+//                     global list, from a block of entries its warp reserved with one atomic; slow_columns_kernel
+//                     (k_slow_columns.cuh) decides the listed columns right behind this kernel, reading the few bytes a
+//                     column needs from the payload in global memory.  The ring never waits for a slow column.
+//   deep tiles        (24 pairs or more per family side on average: few bundles, hundreds of slow columns per tile) keep
+//                     their list in the stage; the warp that finishes the tile's last bundle closes it (prefix sums of the
+//                     entries' column counts), and ALL voter warps of the tile then decide the columns, 32 at a time, one
+//                     thread per column, straight from the staged slab — a deep tile has nothing else for them to do, and
+//                     its reads never cross HBM a second time.
 #pragma once
 
 #include "k_slow_columns.cuh"
@@ -77,194 +76,20 @@ struct RingCtx {  // what deciding a slow column inside the CTA needs besides th
     RollbackList rb;
 };
 
-// group.cpp:376-525 for one slow column of family side f of the staged tile, by one thread.  For a uniform family side
-// (every voter has the template's length, no column shift, the same overlap window) what pair.cpp:121-170 needs to know
-// about the column — inside the overlap or not, the mate index — is computed once; each read then is its quality byte,
-// its base nibble and, inside the overlap, its mate's, added to a three-bin register histogram.  The two scans of
-// group.cpp:395-417 are a top-2 selection over the three bins and the two largest codes nobody showed (bin_key order).
-// (Deep tiles only: see the kernel's header.  The pointers are derived from the shared-memory symbol inside the function, so
-// that the loads are LDS and not generic loads.)
+// One slow column of family side f of a staged (deep) tile, decided from shared memory.  (The pointers are derived from the
+// shared-memory symbol inside the function, so that the loads are LDS and not generic loads.)
 __device__ __noinline__ void ring_slow_column(const RingCtx &x, int ft_off, int vr_off, int slab_off, int64_t out_base0, int f, int col) {
     GCB_DYN_SMEM(smem);
-    const gcb_options &o = *x.o;
-    const ScoreTab tab(o);
     const FsTile ft = ((const FsTile *)(smem + ft_off))[f];
-    const uint8_t *cb = smem + slab_off + 4 * (int)ft.cbase4;
-    const VoteRead *ents = (const VoteRead *)(smem + vr_off) + ft.ent0;
-    const VoteRead tv = ents[ft.tmpl_k];
-    const int side = fs_side(ft);
-    const int qbytes = GCB_ALIGN4(ft.l_out);
-    uint8_t *out = x.r->out_payload + out_base0 + 4 * (int64_t)ft.out4;
-    GCB_COUNT(3, 1);
-    if (col >= (int)ft.len) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
-        int obase = 0, oqual = 0, sc;
-        fetch_ent(cb, tv, col, side, o, obase, oqual, sc);
-        out[col] = (uint8_t)oqual;
-        return;
-    }
-    Bins3 bins;
-    bins.init();
-    const int m = (int)ft.m;
-    if (ft.flags & FS_UNIFORM) {
-        const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
-        const int k = col - (int)tv.ov_own, mp = (int)tv.ov_mate + k;
-        const bool inwin = info && k >= 0 && k < (int)tv.ov_len;
-        const bool mvalid = inwin && mp >= 0 && mp < (int)tv.mate_l;
-        const bool plain = info && !inwin;  // pair.cpp:121-131: outside the overlap the score follows the quality
-        const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
-        const int mpi = mvalid ? mp : 0;
-        const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
-        for (int e = 0; e < m; e++) {
-            const uint32_t w = *(const uint32_t *)(ents + e);  // own_off4 | mate_off4 << 16
-            if ((w & 0xFFFFu) == VR_NO_VOTE) continue;
-            const uint8_t *rec = cb + 4 * (int)(w & 0xFFFFu);
-            int ql = rec[col];
-            const int base = (rec[soff] >> nsh) & 0xF;
-            int score;
-            if (mvalid) {
-                const uint8_t *mrec = cb + 4 * (int)(w >> 16);
-                const int mql = mrec[mpi];
-                const int mbase = (mrec[msoff] >> mnsh) & 0xF;
-                const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
-                const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
-                const int s_match = sc8(tab.q2s((ql + mql) / 2) + 4);                        // pair.cpp:147-152
-                const int s_mis = mine ? sc8(tab.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;  // pair.cpp:153-169
-                score = base == mbase ? s_match : s_mis;
-                ql = base == mbase ? ql : max(0, ql - mql);
-            } else {
-                score = plain ? tab.q2s(ql) : tab.sm;
-            }
-            bins.add(base, ql, score);
-        }
-    } else {
-        for (int e = 0; e < m; e++) {
-            int base, qual, score;
-            if (fetch_vote(cb, ents[e], col, side, tab, base, qual, score)) bins.add(base, qual, score);
-        }
-    }
-    ColumnTop ct;
-    int total = bins.total;
-    uint32_t acgt = 0;  // the best quality of codes 1, 2, 4, 8 in bytes 0..3 (0 when nobody showed the code)
-    if (bins.overflow) {  // a fourth distinct code: the sixteen-bin histogram in local memory (group.cpp:376-417 as written)
-        int32_t h[64];
-        for (int q = 0; q < 64; q++) h[q] = 0;
-        for (int e = 0; e < m; e++) {
-            int base, qual, score;
-            if (!fetch_ent(cb, ents[e], col, side, o, base, qual, score)) continue;
-            h[4 * base]++;
-            h[4 * base + 1] += score;
-            h[4 * base + 2] += qual;
-            h[4 * base + 3] = max(h[4 * base + 3], qual);
-        }
-        VoteBin obs[16];
-        int nobs = 0;
-        total = 0;
-        for (int q = 0; q < 16; q++)
-            if (h[4 * q] > 0) {
-                obs[nobs].base = q; obs[nobs].cnt = h[4 * q]; obs[nobs].score = h[4 * q + 1]; obs[nobs].qual = h[4 * q + 2]; obs[nobs].maxq = h[4 * q + 3];
-                total += obs[nobs].score;
-                nobs++;
-            }
-        ct = column_top(o, obs, nobs, total);
-        acgt = (uint32_t)(h[4 * 1] > 0 ? h[4 * 1 + 3] : 0) | ((uint32_t)(h[4 * 2] > 0 ? h[4 * 2 + 3] : 0) << 8) |
-               ((uint32_t)(h[4 * 4] > 0 ? h[4 * 4 + 3] : 0) << 16) | ((uint32_t)(h[4 * 8] > 0 ? h[4 * 8 + 3] : 0) << 24);
-    } else {
-        // top and second: every bin competes with its (score, quality sum, code) key; the codes nobody showed compete
-        // with (0, 0, code), of which only the two largest can place
-        unsigned freemask = 0xFFFFu;
-        unsigned long long key[3];
-#pragma unroll
-        for (int kk = 0; kk < 3; kk++) {
-            const VoteBin vb = bins.bin(kk);
-            const int bb = vb.base;
-            const bool have = bb >= 0;
-            key[kk] = have ? bin_key(vb.score, vb.qual, bb) : 0ull;
-            if (have) freemask &= ~(1u << bb);
-            if (have && (bb == 1 || bb == 2 || bb == 4 || bb == 8)) acgt |= (uint32_t)vb.maxq << (bb == 1 ? 0 : bb == 2 ? 8 : bb == 4 ? 16 : 24);
-        }
-        const int e1 = 31 - __clz((int)freemask);
-        freemask &= ~(1u << e1);
-        const int e2 = 31 - __clz((int)freemask);
-        const unsigned long long ke1 = bin_key(0, 0, e1), ke2 = bin_key(0, 0, e2);
-        unsigned long long top = max_u64(key[0], key[1]), sec = min_u64(key[0], key[1]);
-        sec = max_u64(sec, min_u64(top, key[2])); top = max_u64(top, key[2]);
-        sec = max_u64(sec, min_u64(top, ke1)); top = max_u64(top, ke1);
-        sec = max_u64(sec, min_u64(top, ke2)); top = max_u64(top, ke2);
-        const int tb = (int)(top & 0xF), sb = (int)(sec & 0xF);
-        const VoteBin none = {0, 0, 0, 0, 0};
-        ct.top = bins.b0 == tb ? bins.bin(0) : bins.b1 == tb ? bins.bin(1) : bins.b2 == tb ? bins.bin(2) : none;
-        ct.sec = bins.b0 == sb ? bins.bin(0) : bins.b1 == sb ? bins.bin(1) : bins.b2 == sb ? bins.bin(2) : none;
-        ct.top.base = tb;
-        ct.sec.base = sb;
-        column_rules(o, ct, total);
-    }
-    int new_qual;
-    if (ct.fast) {
-        new_qual = ct.top.maxq;  // group.cpp:422-426: the base is NOT written
-    } else {
-        // the record's base before the vote: the template's own (pair.cpp rewrites qualities, never bases)
-        const int obase = base_at(cb + 4 * (int)tv.own_off4 + qbytes, col);
-        int ref4 = 0;
-        if (ft.flags & FS_REF_OK) {  // group.cpp:430-439
-            int refpos = col;
-            if (!(ft.flags & FS_SIMPLE_CIGAR)) {
-                const gcb_read_desc od = x.b->reads[x.r->groups[ft.slot].tmpl_read[side]];
-                refpos = get_ref_offset(x.b->cigar + od.cigar_off, od.n_cigar, col);
-            }
-            const int64_t nib = ft.ref_nib0 + refpos;
-            if (refpos >= 0 && nib >= 0 && (nib >> 1) < x.gv->packed_bytes) {  // the bound only guards malformed CIGARs
-                const uint8_t two = x.gv->packed4[nib >> 1];
-                ref4 = genome_nibble_to_bam((nib & 1) ? (two >> 4) : (two & 0xF));
-            }
-        }
-        int rbq = 0;
-        bool any_high = false;
-        if (ct.need_ref && ref4 != 0) {
-            const int rmax = (int)((acgt >> (ref4 == 1 ? 0 : ref4 == 2 ? 8 : ref4 == 4 ? 16 : 24)) & 0xFFu);
-            if (rmax >= 128) {  // `char refBaseQual` wraps: the scan order matters (group.cpp:474-490): template first
-                int tb, tq, ts;
-                if (fetch_ent(cb, tv, col, side, o, tb, tq, ts) && tb == ref4) {
-                    if (tq > rbq) rbq = sc8(tq);
-                    if (tq >= o.high_quality) any_high = true;
-                }
-                for (int e = 0; e < m; e++) {
-                    int base, qual, score;
-                    if (e == ft.tmpl_k || !fetch_ent(cb, ents[e], col, side, o, base, qual, score) || base != ref4) continue;
-                    if (qual > rbq) rbq = sc8(qual);
-                    if (qual >= o.high_quality) any_high = true;
-                }
-            } else {
-                rbq = rmax;
-                any_high = rmax >= o.high_quality;
-            }
-        }
-        const ColumnOut co = column_arbitrate(o, ct, ref4, rbq, any_high);
-        if (obase != co.base) {  // group.cpp:509-524
-            int d_mm = 0;
-            if (ref4 != 0) {
-                if (obase == ref4) d_mm = 1;
-                else if (co.base == ref4) d_mm = -1;
-            }
-            gcb_group_result *gr = x.r->groups + ft.slot;  // (the bundle's lane 0 zeroed both counters before the tile was closed)
-            atomicAdd(&gr->diff[side], 1);
-            if (d_mm != 0) {
-                const int before = atomicAdd(&gr->mismatch_inc[side], d_mm);
-                if (d_mm > 0 && before == 5) {  // more than five new mismatches so far: vote_rollback_kernel looks at the final count
-                    const int kk = atomicAdd(x.rb.count, 1);
-                    if (kk < x.rb.cap) x.rb.list[kk] = 2 * ft.slot + side;
-                }
-            }
-            const int byte = col >> 1;
-            const unsigned delta = ((unsigned)(obase ^ co.base) & 0xFu) << ((col & 1) ? 0 : 4);
-            atomicXor((unsigned *)(out + qbytes + (byte & ~3)), delta << (8 * (byte & 3)));
-        }
-        new_qual = co.qual;
-    }
-    out[col] = (uint8_t)new_qual;
+    SlowSide fs;
+    fs.m = ft.m; fs.l_out = ft.l_out; fs.len = ft.len; fs.tmpl_k = ft.tmpl_k; fs.side = fs_side(ft); fs.flags = ft.flags; fs.slot = ft.slot;
+    fs.ref_nib0 = ft.ref_nib0;
+    decide_column(*x.b, *x.r, *x.gv, *x.o, x.rb, fs, smem + slab_off + 4 * (int)ft.cbase4, (const VoteRead *)(smem + vr_off) + ft.ent0,
+                  x.r->out_payload + out_base0 + 4 * (int64_t)ft.out4, col);
 }
 
 __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o, int32_t implied,
-                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueues sq, RollbackList rb,
+                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowList sl, RollbackList rb,
                                                                    int32_t n_tiles, int32_t arena_bytes, const int32_t *max_need) {
     GCB_DYN_SMEM(smem);
     uint64_t *full = (uint64_t *)(smem + VR_OFF_FULL);
@@ -338,8 +163,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             sh.slab_off = sh.vr_off + (int32_t)ring_round128(vr_bytes);
             sh.sl_off = sh.slab_off + (int32_t)ring_round128((uint32_t)cur.slab_bytes + VT_SLAB_SLACK);
             sh.sl_cap = max(cur.nfs, 0) * cur.lanes;
-            // a tile of deep families (24 pairs or more per family side on average): few bundles, long lists of slow columns
-            sh.deep = cur.nfs > 0 && 2 * cur.np >= 24 * cur.nfs;
+            sh.deep = tile_is_deep(cur.nfs, cur.np) ? 1 : 0;  // few bundles, long lists of slow columns
             sh.next_bundle = 0;
             sh.done = 0;
             sh.n_entries = 0;
@@ -396,10 +220,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     RingCtx x;
     x.b = &b; x.r = &r; x.gv = &gv; x.o = &o; x.rb = rb;
     const uint32_t mod4 = 0x01010101u * (uint32_t)(o.moderate_quality & 0xFF);
-    // slow-column records go to the queue of this CTA
-    const int qi = (int)(blockIdx.x % VQ_NQ);
-    uint32_t *q_words = sq.words + (size_t)qi * sq.cap_words;
-    uint32_t *q_index = sq.index + (size_t)qi * sq.cap_recs;
+    uint32_t pool_i = 0u, pool_e = 0u;  // this warp's block of reserved entries of the global slow-column list
     const uint32_t sbase = smem_base(smem);
     // lane geometry and masks are kept across tiles while the tile shape (lanes per family side, usual record length) stays
     int cur_L = 0, cur_l = -1, S = 32, sub = 0, j = 0, col0 = 0;
@@ -416,6 +237,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         if (nfs < 0) break;
         GCB_TRACE(400 + s);
         const int nb = sh->n_bundles;
+        const bool deep = sh->deep != 0;
         int bundle = nb;
         if (lane == 0 && *(volatile int32_t *)&sh->next_bundle < nb) bundle = atomicAdd(&sh->next_bundle, 1);  // (no atomic on a drained tile)
         bundle = __shfl_sync(FULL, bundle, 0);
@@ -592,141 +414,72 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     if (sb0 < sbytes) *(uint32_t *)(out + qbytes + sb0) = bswap32(tbe0 & cm.kn0);
                     if (sb0 + 4 < sbytes) *(uint32_t *)(out + qbytes + sb0 + 4) = bswap32(tbe1 & cm.kn1);
                 }
-                // ---- slow columns: one list entry per lane (family side << 21 | lane of the family side << 16 | column mask)
+                // ---- slow columns: one list entry per lane that found any
                 const uint32_t mask16 = nib_flags_to_byte(slow0) | (nib_flags_to_byte(slow1) << 8);
                 const unsigned bal = __ballot_sync(FULL, mask16 != 0u);
-                if (bal != 0u) {
-                    int at = 0;
-                    if (lane == 0) at = atomicAdd(&sh->n_entries, __popc(bal));
-                    at = __shfl_sync(FULL, at, 0);
-                    if (mask16 != 0u) s_list[at + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)f << 21) | ((uint32_t)j << 16) | mask16;
+                if (deep) {
+                    // the stage's own list (family side << 21 | lane of the family side << 16 | column mask) ...
+                    if (bal != 0u) {
+                        int at = 0;
+                        if (lane == 0) at = atomicAdd(&sh->n_entries, __popc(bal));
+                        at = __shfl_sync(FULL, at, 0);
+                        if (mask16 != 0u) s_list[at + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)f << 21) | ((uint32_t)j << 16) | mask16;
+                    }
+                    // ... and the warp that finishes the tile's last bundle closes the tile
+                    __syncwarp();
+                    int fin = 0;
+                    if (lane == 0) {
+                        __threadfence_block();
+                        fin = atomicAdd(&sh->done, 1) + 1;
+                    }
+                    fin = __shfl_sync(FULL, fin, 0);
+                    closer = fin == nb;
+                } else if (bal != 0u) {
+                    const uint32_t ne = (uint32_t)__popc(bal);
+                    if (pool_i + ne > pool_e) {  // a new block (what is left of the old one is marked unused)
+                        for (uint32_t i = pool_i + (uint32_t)lane; i < pool_e; i += WARP) sl.entries[i] = make_uint2(0u, 0u);
+                        unsigned int base = 0u;
+                        if (lane == 0) base = atomicAdd(sl.count, VQ_POOL);
+                        base = __shfl_sync(FULL, base, 0);
+                        if (base + VQ_POOL > sl.cap) {  // (cannot happen: the list holds an entry for every lane of every family side)
+                            if (lane == 0) raise_error(ws.error_flag, GCB_ERR_MALFORMED);
+                            base = 0u;
+                        }
+                        pool_i = base;
+                        pool_e = base + VQ_POOL;
+                    }
+                    if (mask16 != 0u) sl.entries[pool_i + __popc(bal & ((1u << lane) - 1u))] = make_uint2(2u * (uint32_t)ft.slot + ((ft.flags & FS_SIDE1) ? 1u : 0u), ((uint32_t)j << 16) | mask16);
+                    pool_i += ne;
                 }
-                // ---- the bundle is finished; the warp that finishes the tile's last one closes the tile
-                __syncwarp();
-                int fin = 0;
-                if (lane == 0) {
-                    __threadfence_block();
-                    fin = atomicAdd(&sh->done, 1) + 1;
-                    bundle = fin < nb ? atomicAdd(&sh->next_bundle, 1) : nb;
-                }
-                fin = __shfl_sync(FULL, fin, 0);
+                if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
                 bundle = __shfl_sync(FULL, bundle, 0);
-                closer = fin == nb;
                 pipe_progress();
             } while (bundle < nb);
         }
         if (closer) {
-            // every bundle of the tile is done: prefix sums of the entries' column counts and queue words, one reservation,
-            // then one thread per slow column writes the column's record
+            // every bundle of the (deep) tile is done: prefix sums of the entries' column counts, then the list is open to every warp
             __threadfence_block();
             const int n = *(volatile int32_t *)&sh->n_entries;
-            uint32_t *s_list = (uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap, *s_pw = s_pf + sh->sl_cap;
-            const FsTile *s_ft = (const FsTile *)(smem + sh->ft_off);
-            const VoteRead *s_vr = (const VoteRead *)(smem + sh->vr_off);
-            int run = 0, runw = 0;
+            uint32_t *s_list = (uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap;
+            int run = 0;
             for (int base = 0; base < n; base += WARP) {
                 const int i = base + lane;
-                int incl = 0, inclw = 0;
-                if (i < n) {
-                    const uint32_t code = s_list[i];
-                    incl = __popc(code & 0xFFFFu);
-                    inclw = incl * (int)slow_rec_words(s_ft[code >> 21].m);
-                }
+                int incl = i < n ? __popc(s_list[i] & 0xFFFFu) : 0;
                 for (int off = 1; off < WARP; off <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, off), vw = __shfl_up_sync(FULL, inclw, off);
-                    if (lane >= off) {
-                        incl += v;
-                        inclw += vw;
-                    }
+                    const int v = __shfl_up_sync(FULL, incl, off);
+                    if (lane >= off) incl += v;
                 }
-                if (i < n) {
-                    s_pf[i] = (uint32_t)(run + incl);
-                    s_pw[i] = (uint32_t)(runw + inclw);
-                }
+                if (i < n) s_pf[i] = (uint32_t)(run + incl);
                 run += __shfl_sync(FULL, incl, WARP - 1);
-                runw += __shfl_sync(FULL, inclw, WARP - 1);
             }
             __syncwarp();
-            if (sh->deep) {  // the columns are decided here: open the list to every warp (below)
-                if (lane == 0) {
-                    sh->drain_total = run;
-                    __threadfence_block();
-                    *(volatile int32_t *)&sh->closed = 1;
-                }
-            } else if (run > 0) {
-                unsigned long long base64 = 0ull;
-                if (lane == 0) base64 = atomicAdd(sq.count + qi, ((unsigned long long)(uint32_t)run << 32) | (uint32_t)runw);
-                base64 = __shfl_sync(FULL, base64, 0);
-                const uint32_t r0 = (uint32_t)(base64 >> 32), w0 = (uint32_t)base64;
-                if ((unsigned long long)r0 + (uint32_t)run > sq.cap_recs || (unsigned long long)w0 + (uint32_t)runw > sq.cap_words) {
-                    // no queue space: the reserved index entries are marked unused and the generic kernel redoes the whole tile
-                    // from the payload (it runs after slow_columns_kernel and vote_rollback_kernel)
-#ifdef GCB_SIMT_CHECK
-                    if (lane == 0 && getenv("GCB_DBG")) fprintf(stderr, "overflow: r0 %u run %d cap %u w0 %u runw %d capw %u n %d\n", r0, run, sq.cap_recs, w0, runw, sq.cap_words, n);
-#endif
-                    for (uint32_t i = r0 + (uint32_t)lane; i < r0 + (uint32_t)run && i < sq.cap_recs; i += WARP) q_index[i] = VQ_INVALID;
-                    if (lane == 0) {
-                        ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~sh->tile;
-                        GCB_COUNT(1, 1);
-                    }
-                } else {
-                    const uint8_t *slab = smem + sh->slab_off;
-                    const int64_t out_base0 = sh->out_base0;
-                    for (int c0 = 0; c0 < run; c0 += WARP) {
-                        const int idx = c0 + lane;
-                        if (idx < run) {
-                            int lo = 0, hi = n - 1;
-                            while (lo < hi) {  // the first entry whose inclusive column count exceeds idx
-                                const int mid = (lo + hi) >> 1;
-                                if ((int)s_pf[mid] > idx) hi = mid;
-                                else lo = mid + 1;
-                            }
-                            const uint32_t code = s_list[lo];
-                            uint32_t mask = code & 0xFFFFu;
-                            const int ncol = __popc(mask), rank = idx - ((int)s_pf[lo] - ncol);
-                            for (int q = 0; q < rank; q++) mask &= mask - 1u;
-                            const int bit = __ffs((int)mask) - 1;  // bit 8 * w + i of the mask = column 8 * w + 7 - i of the lane's sixteen
-                            const int col = VT_CHUNK * (int)((code >> 16) & 31u) + (bit & 8) + 7 - (bit & 7);
-                            const FsTile fti = s_ft[code >> 21];
-                            const int mi = (int)fti.m;
-                            const uint32_t rw = slow_rec_words(mi);
-                            const uint32_t wofs = w0 + (s_pw[lo] - (uint32_t)ncol * rw) + (uint32_t)rank * rw;
-                            uint32_t *rec = q_words + wofs;
-                            q_index[r0 + (uint32_t)idx] = wofs;
-                            slow_write_header(rec, fti, col, out_base0 + 4 * (int64_t)fti.out4);
-                            const uint8_t *cbp = slab + 4 * (int)fti.cbase4;
-                            const VoteRead *ents = s_vr + fti.ent0;
-                            if ((fti.flags & FS_UNIFORM) && col < (int)fti.len) {
-                                // the column's place in pair.cpp:121-170 is the same for every read of a uniform family
-                                const VoteRead tvi = ents[fti.tmpl_k];
-                                const bool info = tvi.ov_len != VR_NO_OVERLAP_INFO;
-                                const int kq = col - (int)tvi.ov_own, mp = (int)tvi.ov_mate + kq;
-                                const bool inwin = info && kq >= 0 && kq < (int)tvi.ov_len;
-                                const bool mvalid = inwin && mp >= 0 && mp < (int)tvi.mate_l;
-                                const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
-                                const int soff = GCB_ALIGN4(fti.l_out) + (col >> 1), nsh = (col & 1) ? 0 : 4;
-                                const int mrel = mvalid ? 4 * ((int)tvi.mate_off4 - (int)tvi.own_off4) : 0, mpi = mvalid ? mp : 0;
-                                const int mqoff = mrel + mpi, msoff = mrel + (mvalid ? GCB_ALIGN4(tvi.mate_l) : 0) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
-                                for (int e = 0; e < mi; e++) {
-                                    const uint32_t xo = ents[e].own_off4;
-                                    uint32_t ent = 0u;
-                                    if (xo != VR_NO_VOTE) {
-                                        const uint8_t *p = cbp + 4 * (int)xo;
-                                        const uint32_t ql = p[col], base = ((uint32_t)p[soff] >> nsh) & 0xFu;
-                                        const uint32_t mql = mvalid ? p[mqoff] : 0u, mbase = mvalid ? (((uint32_t)p[msoff] >> mnsh) & 0xFu) : 0u;
-                                        ent = ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
-                                    }
-                                    rec[SR_HDR_WORDS + e] = ent;
-                                }
-                            } else {
-                                for (int e = 0; e < mi; e++) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
-                            }
-                        }
-                    }
-                }
+            if (lane == 0) {
+                sh->drain_total = run;
+                __threadfence_block();
+                *(volatile int32_t *)&sh->closed = 1;
             }
         }
-        if (sh->deep) {
+        if (deep) {
             // every voter warp waits for the tile to be closed and then decides slow columns, 32 at a time, one thread per
             // column, straight from the staged slab: a deep tile has hundreds of them and nothing else for the warps to do
             while (*(volatile int32_t *)&sh->closed == 0) pipe_relax(100u);
@@ -763,6 +516,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         __syncwarp();
         if (lane == 0) pipe_arrive(empty + s);
     }
+    for (uint32_t i = pool_i + (uint32_t)lane; i < pool_e; i += WARP) sl.entries[i] = make_uint2(0u, 0u);  // what is left of the warp's block
 #undef GCB_LDS32
 }
 

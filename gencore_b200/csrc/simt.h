@@ -10,8 +10,11 @@
 
 #ifdef GCB_SIMT_CHECK
 #include "simt_check.h"
-#define GCB_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    ::simt::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+#define GCB_LAUNCH(kernel, grid, block, smem, stream, ...)                                   \
+    do {                                                                                    \
+        if (getenv("GCB_SIMT_TRACE")) fprintf(stderr, "simt launch %s\n", #kernel);         \
+        ::simt::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); });            \
+    } while (0)
 #define GCB_DYN_SMEM(name) uint8_t *name = ::simt::dyn_smem()
 #else
 #include <cuda_runtime.h>

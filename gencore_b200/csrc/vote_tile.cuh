@@ -57,17 +57,6 @@ struct RollbackList {
     int32_t cap;
 };
 
-// coverage counters of the CPU SIMT-check build (tests only): ring tiles, generic tiles, voted columns, slow columns,
-// uniform family sides, non-uniform family sides, slow columns decided by a warp that was waiting for a tile, stage re-uses
-#ifdef GCB_SIMT_CHECK
-inline int64_t g_simt_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define GCB_COUNT(k, n) (g_simt_counters[k] += (n))
-#define GCB_TRACE(tag) ::simt::trace(tag)
-#else
-#define GCB_COUNT(k, n) ((void)0)
-#define GCB_TRACE(tag) ((void)0)
-#endif
-
 // ---- mbarrier / bulk-copy wrappers.  Under SIMT-check (one OS thread, fibers) a barrier is a count of completed
 // phases and a wait yields to the other fibers until the phase it names is over; copies are synchronous.
 #ifndef GCB_SIMT_CHECK
@@ -374,9 +363,12 @@ GCB_DEV ChunkMasks make_masks(int l_out, int len, int col0) {
 // compacted with ballots (no shared memory, no CTA barrier); many tiles per SM keep their chains of dependent loads
 // (directory -> side modes -> family-side descriptors -> cluster offsets) in flight at once.  `max_need`: the largest
 // shared-memory allocation a tile of this view takes in the vote kernel.
+GCB_HD bool tile_is_deep(int32_t nfs, int32_t np) { return nfs > 0 && 2 * np >= 24 * nfs; }  // 24 pairs or more per family side on average
 GCB_HD int32_t tile_smem_need(int32_t nfs, int32_t np, int32_t slab_bytes, int32_t lanes) {
-    // family-side list, VoteRead table, slab + slack, slow-column list + its two prefix sums (one entry per family side and lane)
-    return ((32 * nfs + 127) & ~127) + ((32 * np + 127) & ~127) + ((slab_bytes + VT_SLAB_SLACK + 127) & ~127) + ((12 * nfs * lanes + 127) & ~127);
+    // family-side list, VoteRead table, slab + slack; a deep tile also its slow-column list and the list's prefix sums (one entry
+    // per family side and lane)
+    return ((32 * nfs + 127) & ~127) + ((32 * np + 127) & ~127) + ((slab_bytes + VT_SLAB_SLACK + 127) & ~127) +
+           (tile_is_deep(nfs, np) ? ((8 * nfs * lanes + 127) & ~127) : 0);
 }
 
 __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b, ResultView r, Workspace ws, int32_t slab_cap, int32_t arena,

@@ -11,7 +11,7 @@ if [ "${2:-tests}" = "tests" ]; then
 fi
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 tail -c 3000 gpurun_out/bench_$tag.json
-timeout 900 python scripts/shape_perf.py cfg1 cfg3 cfg4 cfg5 cfg2:1000000:15 deep:30:0.01 deep:30:0.003 deep:50:0.003 > gpurun_out/shapes_$tag.log 2>&1
+timeout 900 python scripts/shape_perf.py cfg1 cfg3 cfg4 cfg5 cfg2:1000000:15 cfg2:1000000:14 deep:30:0.01 deep:30:0.003 deep:50:0.003 > gpurun_out/shapes_$tag.log 2>&1
 cat gpurun_out/shapes_$tag.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 40 --csv --log-file gpurun_out/launches_$tag.csv \
   python bench.py --steps 2 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/launches_$tag.log 2>&1

@@ -34,6 +34,8 @@ struct uint3 { unsigned x, y, z; };
 struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
 struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
 struct __attribute__((aligned(8))) int2 { int x, y; };
+struct __attribute__((aligned(8))) uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 v = {x, y}; return v; }
 inline int2 make_int2(int x, int y) { int2 v = {x, y}; return v; }
 struct dim3 {
     unsigned x, y, z;
