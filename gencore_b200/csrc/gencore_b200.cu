@@ -2,7 +2,7 @@
 // of one batch.  Host code only sizes buffers, moves bytes and launches; all arithmetic of the
 // reference's hot path lives in the kernels:
 //   umi_group_kernel -> select_template_kernel -> scan_local/scan_blocks -> tile_prep2_kernel -> vote_ring_kernel
-//   -> slow_columns_kernel -> vote_rollback_kernel -> score_vote_kernel (the tiles that do not fit the ring's arena) -> duplex_kernel
+//   -> vote_rollback_kernel -> score_vote_kernel (the tiles that do not fit the ring's arena) -> duplex_kernel
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -43,8 +43,6 @@ struct gcb_ctx {
     DevBuf w_vr, w_fs, w_gtiles, w_gcount;
     DevBuf w_fstiles, w_thdr2, w_need;   // the tiles' compact family-side lists, their headers, the largest tile's shared-memory need (per chunk)
     DevBuf w_rb_list, w_rb_count;        // rollback candidates (per chunk: one counter)
-    DevBuf w_sl_entries, w_sl_count;     // the ring kernel's list of lanes with slow columns (per chunk: one counter)
-    uint32_t sl_cap = 0;
     int ring_window_shift = 0;           // 0 = chosen by plan_tiles; 14 / 15 = forced (tuning)
     int group_lanes = 0;                 // lanes per cluster in umi_group / select_template (0 = by mean cluster size)
     int force_generic = 0;               // tests: every tile goes to the generic kernel
@@ -109,11 +107,12 @@ TilePlan plan_tiles(int32_t max_cluster_bytes, int ring_window_shift = 0) {
     memset(&p, 0, sizeof p);
     p.arena = (budget - 1 * KB - VR_OFF_ARENA - VR_GUARD) & ~127;
     p.smem = VR_OFF_ARENA + p.arena + VR_GUARD;
-    // 16 KB windows: a tile is about a window plus half a cluster, so a batch of small clusters keeps ten or more tiles in flight
-    // in the ring kernel's arena and its voter warps work in three groups; a batch whose largest cluster nearly fills the arena
-    // still gets one tile in flight.  (32 KB windows measured slower on every shape: fewer, larger tiles in flight.)
+    // 32 KB windows: a tile is about a window plus half a cluster; five or six of them are in flight in the ring kernel's arena and
+    // all fifteen voter warps walk every tile.  A batch whose largest cluster nearly fills the arena still gets one tile in flight.
+    // (16 KB windows, with the voters in three groups, measured slower on the BASELINE shapes: twice the tiles for the one
+    // producer lane and for every warp's walk; gcb_set_debug key 2 selects them.)
     {
-        const int shift = ring_window_shift ? ring_window_shift : 14;
+        const int shift = ring_window_shift ? ring_window_shift : 15;
         p.window_shift = shift;
         p.window = 1 << shift;
         p.slab_cap = p.window + maxc;
@@ -127,7 +126,7 @@ TilePlan plan_tiles(int32_t max_cluster_bytes, int ring_window_shift = 0) {
         }
     }
     // clusters too large for a stage: every tile goes to the generic kernel (no size limits)
-    p.window_shift = ring_window_shift ? ring_window_shift : 14;
+    p.window_shift = ring_window_shift ? ring_window_shift : 15;
     p.window = 1 << p.window_shift;
     p.slab_cap = 0;
     p.ring = 0;
@@ -145,7 +144,7 @@ int32_t fast_path_implied(const gcb_options &o) {
     return 1;
 }
 
-int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t n_tiles, int64_t payload_bytes, Workspace &ws) {
+int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t n_tiles, Workspace &ws) {
     int rc;
     const int64_t n_scan = (n_clusters + SCAN_BLOCK - 1) / SCAN_BLOCK;
 #define GCB_RES(buf, bytes) if ((rc = reserve(ctx, ctx->buf, (size_t)(bytes))) != GCB_OK) return rc
@@ -172,13 +171,6 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_need, 4 * GCB_MAX_CHUNKS);
     GCB_RES(w_rb_list, 2 * n_pairs * 4);
     GCB_RES(w_rb_count, 4 * GCB_MAX_CHUNKS);
-    {   // one list entry per sixteen columns of a family side at most (its template's chunk is at least 24 payload bytes), plus the
-        // blocks the ring kernel's warps reserve and may leave partly unused
-        const int64_t cap = payload_bytes / 24 + (int64_t)ctx->n_sms * VR_WARPS * VQ_POOL + 1024;
-        GCB_RES(w_sl_entries, 8 * cap);
-        GCB_RES(w_sl_count, 4 * GCB_MAX_CHUNKS);
-        ctx->sl_cap = (uint32_t)(cap > 0x7FFFFFF0ll ? 0x7FFFFFF0ll : cap);
-    }
 #undef GCB_RES
     ws.members = (int32_t *)ctx->w_members.p;
     ws.group_off = (int32_t *)ctx->w_group_off.p;
@@ -218,7 +210,7 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
     const int32_t nc = v.c1 - v.c0;
     const int64_t n_tiles = (v.s1 - v.s0 + plan.window - 1) / plan.window;
     BatchView b = {nc, v.p1, batch.umi_words, batch.cluster_pair_off + v.c0, batch.cluster_ref + v.c0, batch.cluster_flags + v.c0,
-                   batch.umi, batch.reads, batch.cigar, batch.payload, v.s1, v.s0};
+                   batch.umi, batch.reads, batch.cigar, batch.payload, v.s1, v.s0, batch.n_cigar_ops};
     ResultView r = {result.pair_group, result.cluster_n_groups + v.c0, result.groups, result.out_payload, result.out_capacity, total_out};
     Workspace ws = ws0;
     ws.cluster_has_umi += v.c0;
@@ -289,11 +281,6 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         rb.list = (int32_t *)ctx->w_rb_list.p + 2 * (size_t)v.p0;
         rb.count = (int32_t *)ctx->w_rb_count.p + v.index;
         rb.cap = 2 * (v.p1 - v.p0);
-        // ... and its own slow-column list counter (the list itself is shared: the chunks' votes never overlap)
-        SlowList sl;
-        sl.entries = (uint2 *)ctx->w_sl_entries.p;
-        sl.count = (unsigned int *)ctx->w_sl_count.p + v.index;
-        sl.cap = ctx->sl_cap;
         if (run_prep) {
             GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
             GCB_CUDA(ctx, cudaMemsetAsync(max_need, 0, 4, stream));
@@ -303,17 +290,14 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         }
         if (run_fast && plan.ring && !ctx->force_generic) {
             GCB_CUDA(ctx, cudaMemsetAsync(rb.count, 0, 4, stream));
-            GCB_CUDA(ctx, cudaMemsetAsync(sl.count, 0, 4, stream));
             const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
             GCB_LAUNCH(vote_ring_kernel, dim3(ring_grid), dim3(VR_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
-                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sl, rb, (int32_t)n_tiles, plan.arena,
+                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, rb, (int32_t)n_tiles, plan.arena,
                        (const int32_t *)max_need);
             ctx->launches++;
         }
         if (run_rest) {
             if (plan.ring && !ctx->force_generic) {
-                GCB_LAUNCH(slow_columns_kernel, dim3(VQ_SLOW_CTAS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt, sl, rb);
-                ctx->launches++;
                 GCB_LAUNCH(vote_rollback_kernel, dim3(VQ_FINAL_CTAS), dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->opt, rb, v.p0, v.p1);
                 ctx->launches++;
             }
@@ -402,7 +386,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
     DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
-                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_need, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->w_sl_entries, &ctx->w_sl_count, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
+                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_need, &ctx->w_rb_list, &ctx->w_rb_count,  &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
                      &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status};
     for (DevBuf *b : all) release(*b);
@@ -467,7 +451,7 @@ int gcb_consensus_batch_device(gcb_ctx *ctx, const gcb_batch *batch, gcb_result 
     const TilePlan plan = plan_tiles(batch->max_cluster_bytes, ctx->ring_window_shift);
     const int64_t n_tiles = (batch->payload_bytes + plan.window - 1) / plan.window;
     Workspace ws;
-    int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, batch->payload_bytes, ws);
+    int rc = reserve_workspace(ctx, batch->n_pairs, batch->n_clusters, n_tiles, ws);
     if (rc != GCB_OK) return rc;
     const ViewRange whole = {0, batch->n_clusters, 0, batch->n_pairs, 0, batch->payload_bytes, 0, 0, 0};
     if (stages & GCB_STAGE_UMI_GROUP) GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, stream));
@@ -508,6 +492,19 @@ static int consensus_batch_host(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *h
     GCB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t nc = (size_t)hb->n_clusters, np = (size_t)hb->n_pairs;
     int rc;
+    // the host itself walks cluster_pair_off (chunk boundaries, copy sizes): it must be monotone inside [0, n_pairs] before
+    // anything is sized from it; everything else about the batch is validated on the device (GCB_ERR_MALFORMED)
+    if (nc > 0) {
+        if (!hb->cluster_pair_off || !hb->reads || !hb->payload) return fail(ctx, GCB_ERR_ARG, "gcb_consensus_batch: null array");
+        int32_t prev = hb->cluster_pair_off[0];
+        bool ok = prev >= 0;
+        for (size_t c = 1; c <= nc && ok; c++) {
+            const int32_t cur = hb->cluster_pair_off[c];
+            ok = cur >= prev;
+            prev = cur;
+        }
+        if (!ok || prev > hb->n_pairs) return fail(ctx, GCB_ERR_MALFORMED, "gcb_consensus_batch: cluster_pair_off is not monotone inside [0, n_pairs]");
+    }
 #define GCB_RESERVE(buf, bytes) if ((rc = reserve(ctx, ctx->buf, (bytes))) != GCB_OK) return rc
     GCB_RESERVE(d_pair_off, (nc + 1) * 4);
     GCB_RESERVE(d_cref, nc * 4);
@@ -583,7 +580,7 @@ static int consensus_batch_host(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *h
         }
     }
     Workspace ws;
-    if ((rc = reserve_workspace(ctx, hb->n_pairs, hb->n_clusters, (hb->payload_bytes + plan.window - 1) / plan.window, hb->payload_bytes, ws)) != GCB_OK) return rc;
+    if ((rc = reserve_workspace(ctx, hb->n_pairs, hb->n_clusters, (hb->payload_bytes + plan.window - 1) / plan.window, ws)) != GCB_OK) return rc;
     cudaStream_t sc = ctx->stream, sin = ctx->h2d, sout = ctx->d2h;
     GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, sc));
     for (int k = 0; k < K; k++) {

@@ -41,12 +41,49 @@ GCB_DEV int duplex_merge_records(uint8_t *rec1, int len1, uint8_t *rec2, int len
     return diff;
 }
 
+// The same walk over copies of the two sequences in shared memory (the walk is a chain of dependent byte reads: from global
+// memory every step costs an L2 round trip, from shared memory a few cycles).  s1 / s2: this thread's two staging rows of
+// DUPLEX_STAGE_WORDS words.  The modifications go to global memory AND to the copies (the walk re-reads what it wrote).
+constexpr int DUPLEX_STAGE_WORDS = 39;  // 156 bytes = 312 bases; odd, so that the threads' rows fall into different banks
+GCB_DEV int duplex_merge_staged(uint8_t *rec1, int len1, uint8_t *rec2, int len2, uint32_t *s1, uint32_t *s2) {
+    int diff = len1 > len2 ? len1 - len2 : len2 - len1;
+    const int len = min(len1, len2);
+    uint8_t *qual1 = rec1, *qual2 = rec2;
+    uint8_t *seq1 = rec1 + GCB_ALIGN4(len1), *seq2 = rec2 + GCB_ALIGN4(len2);
+    const int nw = (((len + 1) >> 1) + 3) >> 2;  // (records are 4-byte aligned and padded to whole words)
+    for (int k = 0; k < nw; k++) {
+        s1[k] = ((const uint32_t *)seq1)[k];
+        s2[k] = ((const uint32_t *)seq2)[k];
+    }
+    uint8_t *b1 = (uint8_t *)s1, *b2 = (uint8_t *)s2;
+    for (int i = 0; i < len; i++) {
+        const uint8_t a = b1[i >> 1], c = b2[i >> 1];
+        if (a == c) {
+            i++;
+            continue;
+        }
+        const int x1 = (i & 1) ? (a & 0xF) : (a >> 4), x2 = (i & 1) ? (c & 0xF) : (c >> 4);
+        if (base_letter(x1) != base_letter(x2)) {
+            diff++;
+            qual1[i] = 0;
+            qual2[i] = 0;
+            const uint8_t m = (i & 1) ? 0x0F : 0xF0;
+            b1[i >> 1] = (uint8_t)(a | m);
+            b2[i >> 1] = (uint8_t)(c | m);
+            seq1[i >> 1] = (uint8_t)(a | m);
+            seq2[i >> 1] = (uint8_t)(c | m);
+        }
+    }
+    return diff;
+}
+
 // Two threads per cluster: both walk the stack (same decisions), each merges one side of a strand pair's consensus records
 // (the walk over a record is sequential, the two sides are independent), thread 0 writes the verdicts.
 __global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o) {
+    __shared__ uint32_t s_stage[DUPLEX_THREADS][2][DUPLEX_STAGE_WORDS];
     const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int c = t >> 1, side = t & 1;
-    if (c >= b.n_clusters) return;
+    if (c >= b.n_clusters || batch_is_malformed(ws.error_flag)) return;
     const unsigned pairmask = 3u << (lane_id() & ~1);  // this cluster's two lanes
     const int p0 = b.cluster_pair_off[c];
     const int G = r.cluster_n_groups[c];
@@ -82,8 +119,13 @@ __global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, Res
                 const int t1 = r1->tmpl_read[s], t2 = r2->tmpl_read[s];
                 if (t1 >= 0 && t2 >= 0) {
                     const int l1 = b.reads[t1].l_qseq, l2 = b.reads[t2].l_qseq;
-                    if (!(r1->out_off[s] + record_bytes(l1) > r.out_capacity || r2->out_off[s] + record_bytes(l2) > r.out_capacity))
-                        diff = duplex_merge_records(r.out_payload + r1->out_off[s], l1, r.out_payload + r2->out_off[s], l2);
+                    if (!(r1->out_off[s] + record_bytes(l1) > r.out_capacity || r2->out_off[s] + record_bytes(l2) > r.out_capacity)) {
+                        if (min(l1, l2) <= 8 * DUPLEX_STAGE_WORDS)
+                            diff = duplex_merge_staged(r.out_payload + r1->out_off[s], l1, r.out_payload + r2->out_off[s], l2, s_stage[threadIdx.x][0],
+                                                       s_stage[threadIdx.x][1]);
+                        else
+                            diff = duplex_merge_records(r.out_payload + r1->out_off[s], l1, r.out_payload + r2->out_off[s], l2);
+                    }
                 }
             }
             diff += __shfl_xor_sync(pairmask, diff, 1);

@@ -31,7 +31,19 @@ struct BatchView {  // gcb_batch with device pointers
     const uint8_t *payload;
     int64_t payload_bytes;   // end of this view's payload (absolute offset)
     int64_t payload_origin;  // start of this view's payload: vote tiles are windows counted from here
+    int64_t n_cigar_ops;     // entries of `cigar`
 };
+
+// The documented preconditions of a gcb_batch are checked on the device, where the descriptors are read anyway: a batch that
+// breaks one raises GCB_ERR_MALFORMED, the offending cluster emits nothing, and every later kernel of the batch returns at once
+// (a misplaced slab would otherwise reach the bulk copies of the vote as an unaligned address: a sticky fault, not an error code).
+GCB_DEV bool batch_is_malformed(const int32_t *error_flag) { return *(volatile const int32_t *)error_flag == GCB_ERR_MALFORMED; }
+// a read's record must lie inside its cluster's slab [lo, hi) at a 4-byte boundary, its CIGAR inside the pool
+GCB_DEV bool read_desc_ok(const BatchView &b, const gcb_read_desc &d, int64_t lo, int64_t hi) {
+    if (d.l_qseq < 0) return true;  // an empty slot
+    return (d.data_off & 3) == 0 && d.data_off >= lo && d.data_off + record_bytes(d.l_qseq) <= hi && d.cigar_off >= 0 &&
+           (int64_t)d.cigar_off + d.n_cigar <= b.n_cigar_ops;
+}
 
 struct ResultView {  // gcb_result with device pointers
     int32_t *pair_group;
@@ -94,6 +106,25 @@ __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, R
     const int p0 = b.cluster_pair_off[c], p1 = b.cluster_pair_off[c + 1], n = p1 - p0;
     const int thr = b.cluster_flags[c] >> GCB_CLUSTER_UMI_THR_SHIFT;
     const uint64_t *umi = b.umi + (int64_t)p0 * NW;
+    {   // preconditions: monotone pair offsets inside the batch; the cluster's slab 16-byte aligned, after the previous cluster's,
+        // inside this view's payload
+        bool bad = p0 < 0 || p1 < p0 || p1 > b.n_pairs;
+        if (!bad) {
+            const int64_t s = p0 < b.n_pairs ? b.reads[2 * (int64_t)p0].data_off : b.payload_bytes;
+            bad = (s & 15) != 0 || s < b.payload_origin || s > b.payload_bytes;
+            if (!bad && c > 0) {
+                const int pp = b.cluster_pair_off[c - 1];
+                bad = pp < 0 || pp > p0 || (pp < b.n_pairs && b.reads[2 * (int64_t)pp].data_off > s);
+            }
+        }
+        if (bad) {  // (uniform over the cluster's lanes)
+            if (lane == 0) {
+                raise_error(ws.error_flag, GCB_ERR_MALFORMED);
+                r.cluster_n_groups[c] = 0;
+            }
+            return;
+        }
+    }
 
     if (lane == 0) {
         // slab bounds of this cluster and the vote kernel's tile directory: tile t owns the clusters
@@ -632,10 +663,25 @@ __global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(Batc
     const Grp<GS> g;
     const int lane = g.gl;
     const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (WARP / GS) + (lane_id() / GS);
-    if (c >= b.n_clusters) return;
+    if (c >= b.n_clusters || batch_is_malformed(ws.error_flag)) return;
     const int p0 = b.cluster_pair_off[c], p1 = b.cluster_pair_off[c + 1], n = p1 - p0;
     const int G = r.cluster_n_groups[c];
     const bool crossContig = (b.cluster_flags[c] & GCB_CLUSTER_CROSS_CONTIG) != 0;
+    {   // preconditions of the cluster's reads (see read_desc_ok)
+        const int64_t lo = ws.slab_off[c], hi = ws.slab_off[c + 1];
+        bool bad = false;
+        for (int i = lane; i < n; i += GS) {
+            const int64_t pair = p0 + i;
+            bad = bad || !read_desc_ok(b, b.reads[2 * pair], lo, hi) || !read_desc_ok(b, b.reads[2 * pair + 1], lo, hi) || b.reads[2 * pair].l_qseq < 0;
+        }
+        if (g.any(bad)) {
+            if (lane == 0) {
+                raise_error(ws.error_flag, GCB_ERR_MALFORMED);
+                ws.cluster_out_bytes[c] = 0;
+            }
+            return;
+        }
+    }
     if (n > 0 && n <= GS && !crossContig && select_cluster_fast<GS>(g, b, r, ws, gv, c, p0, n, G)) return;
 
     for (int i = lane; i < n; i += GS) {

@@ -4,31 +4,14 @@
 // decide_column() is the decision itself, over pointers to the family side's VoteRead entries and to its cluster's slab:
 // score per read (pair.cpp:121-170), three-bin register histogram (group.cpp:376-393), top-2 selection (group.cpp:395-417),
 // the rules and the reference arbitration (group.cpp:419-525); it patches the consensus record and adds to the family
-// side's diff / mismatchInc (atomics on the result row; the ring kernel zeroed them).  Two callers:
-//   * the ring kernel itself for tiles of deep families (hundreds of slow columns per tile, decided by all the voter warps
-//     from the staged slab in shared memory);
-//   * slow_columns_kernel for everything else.  The ring kernel only LISTS those columns — 8 bytes per lane that found any:
-//     family side, lane, 16-bit column mask — and never waits for them; this kernel, launched right behind it at full
-//     occupancy, reads the few bytes a column needs (per read a quality, a base nibble and the mate's) from the payload in
-//     global memory.  The deciding is a chain of dependent small loads that wants many resident warps, which the
-//     one-CTA-per-SM ring cannot give it; extracting the bytes inside the ring instead (measured both per bundle and per
-//     tile: profiles/r03_notes.md) either costs a third of the ring's instructions or holds every stage while one warp
-//     walks the tile's list.
+// side's diff / mismatchInc (atomics on the result row, which select_template_kernel wrote with zeros).  Both callers live in
+// the ring kernel: its decider warps (everything from global memory, decide_column_global) and, for tiles of deep
+// families, all its voter warps (from the staged slab in shared memory).
 #pragma once
 
 #include "vote_tile.cuh"
 
 namespace gcb {
-
-constexpr int VQ_SLOW_THREADS = 128;
-constexpr int VQ_SLOW_CTAS = 148 * 8;          // slow_columns_kernel strides over the list
-constexpr uint32_t VQ_POOL = 128;              // list entries a voter warp reserves at a time (one global atomic)
-
-struct SlowList {   // the ring kernel's list of lanes with slow columns
-    uint2 *entries;          // .x = 2 * slot + side, .y = lane of the family side << 16 | column mask (bit 8 * w + i = column 8 * w + 7 - i); .y == 0: unused
-    unsigned int *count;     // [1] entries reserved so far
-    uint32_t cap;            // >= one entry per sixteen columns of every family side: the list cannot overflow
-};
 
 // what a column's decision needs to know of its family side
 struct SlowSide {
@@ -219,21 +202,6 @@ GCB_DEV void decide_column_global(const BatchView &b, const ResultView &r, const
     fs.ref_nib0 = d.ref_nib0;
     const VoteRead *ents = ws.vote_reads + 2 * (int64_t)d.mb + (int64_t)fs.side * d.m;
     decide_column(b, r, gv, o, rb, fs, b.payload + ws.slab_off[d.c], ents, r.out_payload + r.groups[fs.slot].out_off[fs.side], col);
-}
-
-__global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o,
-                                                                       SlowList sl, RollbackList rb) {
-    const uint32_t total = min(*sl.count, sl.cap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const uint2 e = sl.entries[i];
-        uint32_t mask = e.y & 0xFFFFu;
-        const int col0 = VT_CHUNK * (int)(e.y >> 16);
-        while (mask != 0u) {
-            const int bit = __ffs((int)mask) - 1;
-            mask &= mask - 1u;
-            decide_column_global(b, r, ws, gv, o, rb, e.x, col0 + (bit & 8) + 7 - (bit & 7));
-        }
-    }
 }
 
 }  // namespace gcb

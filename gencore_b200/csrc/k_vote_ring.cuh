@@ -16,10 +16,15 @@
 //                     moderateQuality: exactly group.cpp:421-427 under `implied`) are finished in the word: per-column maxima
 //                     in 16-bit lanes (VIMNMX3.U16x2 over two reads per iteration), disagreement as OR-accumulated XOR
 //                     residues of the raw words; uniform families (every fixed-length library) run a branch-free loop.
-//   slow columns      a lane that found slow columns appends ONE 8-byte entry (family side, lane, 16-bit column mask) to a
-//                     global list, from a block of entries its warp reserved with one atomic; slow_columns_kernel
-//                     (k_slow_columns.cuh) decides the listed columns right behind this kernel, reading the few bytes a
-//                     column needs from the payload in global memory.  The ring never waits for a slow column.
+//   slow columns      a lane that found slow columns publishes ONE 8-byte entry (family side, lane, 16-bit column mask) in a
+//                     ring buffer in shared memory and goes on; the stage is released as if the columns did not exist.
+//   warps 16..19      deciders.  They pool the entries of all the tiles into rounds of exactly 32 columns, one thread per
+//                     column, and decide them (k_slow_columns.cuh: group.cpp:376-525) reading the few bytes a column needs —
+//                     per read a quality, a base nibble and the mate's — from the payload in GLOBAL memory: the tile crossed
+//                     this SM microseconds ago, so these are L2 hits, and no stage waits for a chain of dependent loads.
+//                     (Measured alternatives, profiles/r03_notes.md: deciding from the staged slab, or extracting records
+//                     from it per tile, holds every stage and starves the voters; extracting per bundle costs a third of the
+//                     kernel's instructions; a second kernel behind this one finds the payload gone from L2.)
 //   deep tiles        (24 pairs or more per family side on average: few bundles, hundreds of slow columns per tile) keep
 //                     their list in the stage; the warp that finishes the tile's last bundle closes it (prefix sums of the
 //                     entries' column counts), and ALL voter warps of the tile then decide the columns, 32 at a time, one
@@ -31,8 +36,10 @@
 
 namespace gcb {
 
-constexpr int VR_THREADS = 512;
+constexpr int VR_THREADS = 640;    // warp 0 produces, fifteen warps vote, four decide slow columns (96 registers per thread)
 constexpr int VR_WARPS = VR_THREADS / WARP;
+constexpr int VR_VOTERS = 15, VR_DECIDERS = VR_WARPS - 1 - VR_VOTERS;
+constexpr int VR_CQ = 1024;        // entries of the CTA's slow-column ring buffer between voters and deciders
 constexpr int VR_MAX_STAGES = 16;  // tiles in flight (barrier pairs and stage headers); their bytes come from one ring-buffer arena
 constexpr int VR_GROUPS = 3;       // groups of voter warps when the tiles are small
 constexpr int VR_GUARD = 4608;     // never allocated, after the arena: the branch-free read loop may read a VoteRead table or a
@@ -63,18 +70,34 @@ constexpr int VR_OFF_FULL = 0;                                   // uint64[VR_MA
 constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_HDR = 16 * VR_MAX_STAGES;                   // RingStage[VR_MAX_STAGES]
 constexpr int VR_OFF_HCACHE = VR_OFF_HDR + 96 * VR_MAX_STAGES;   // TileHdr2[32]: the producer's next tiles
-constexpr int VR_OFF_ARENA = (VR_OFF_HCACHE + 48 * WARP + 127) & ~127;
+constexpr int VR_OFF_CQCTL = VR_OFF_HCACHE + 48 * WARP;          // CqCtl
+constexpr int VR_OFF_CQ = VR_OFF_CQCTL + 16;                     // uint2[VR_CQ]
+constexpr int VR_OFF_ARENA = (VR_OFF_CQ + 8 * VR_CQ + 127) & ~127;
 // a tile's allocation: [FsTile list][VoteRead table][slab + slack][slow-column list + two prefix arrays], each part rounded to 128 bytes
 static_assert(VR_OFF_HDR % 16 == 0 && VR_OFF_HCACHE % 16 == 0 && VR_OFF_ARENA % 128 == 0, "ring layout");
 GCB_HD uint32_t ring_round128(uint32_t v) { return (v + 127u) & ~127u; }
+
+struct CqCtl {  // the slow-column ring buffer's counters (entry i lives in slot i % VR_CQ; counters only grow)
+    uint32_t wr;           // atomic: entries reserved by voters
+    uint32_t rd;           // atomic: entries grabbed by deciders
+    uint32_t consumed;     // entries copied out of the buffer, committed in order: slot i may be rewritten once i - consumed < VR_CQ
+    uint32_t voters_done;  // atomic: voter warps that have left the kernel
+};
 
 struct RingCtx {  // what deciding a slow column inside the CTA needs besides the stage
     const BatchView *b;
     const ResultView *r;
     const GenomeView *gv;
     const gcb_options *o;
+    const Workspace *ws;
     RollbackList rb;
 };
+
+// One listed slow column, everything read from global memory: the tile it came from crossed this SM microseconds ago, so
+// the payload bytes, the VoteRead entries and the family-side descriptor are L2 hits.
+__device__ __noinline__ void ring_slow_column_global(const RingCtx &x, uint32_t fsid, int col) {
+    decide_column_global(*x.b, *x.r, *x.ws, *x.gv, *x.o, x.rb, fsid, col);
+}
 
 // One slow column of family side f of a staged (deep) tile, decided from shared memory.  (The pointers are derived from the
 // shared-memory symbol inside the function, so that the loads are LDS and not generic loads.)
@@ -89,9 +112,10 @@ __device__ __noinline__ void ring_slow_column(const RingCtx &x, int ft_off, int 
 }
 
 __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o, int32_t implied,
-                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowList sl, RollbackList rb,
+                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, RollbackList rb,
                                                                    int32_t n_tiles, int32_t arena_bytes, const int32_t *max_need) {
     GCB_DYN_SMEM(smem);
+    if (batch_is_malformed(ws.error_flag)) return;  // (every thread of the grid sees the same flag: the kernels that raise it have finished)
     uint64_t *full = (uint64_t *)(smem + VR_OFF_FULL);
     uint64_t *empty = (uint64_t *)(smem + VR_OFF_EMPTY);
     RingStage *shdr = (RingStage *)(smem + VR_OFF_HDR);
@@ -100,15 +124,19 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     // the batch's largest tile (tile_prep2_kernel measured it) decides how the voters are organised: small tiles -> many in
     // flight -> three groups of five warps; tiles that fill the arena -> all fifteen warps on every tile
     const int32_t largest = (int32_t)ring_round128((uint32_t)max(*max_need, 128));
-    const int n_groups = arena_bytes >= 6 * largest ? VR_GROUPS : 1, wpg = (VR_WARPS - 1) / n_groups;
+    const int n_groups = arena_bytes >= 6 * largest ? VR_GROUPS : 1, wpg = VR_VOTERS / n_groups;
     const int n_stages = VR_MAX_STAGES;
+    CqCtl *cq = (CqCtl *)(smem + VR_OFF_CQCTL);
+    uint2 *cq_ent = (uint2 *)(smem + VR_OFF_CQ);
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
             pipe_init(full + s, 1);
             pipe_init(empty + s, wpg);  // every voter warp of the tile's group arrives once when it leaves the tile
         }
+        cq->wr = cq->rd = cq->consumed = cq->voters_done = 0u;
         pipe_fence_init();
     }
+    for (int i = tid; i < VR_CQ; i += VR_THREADS) cq_ent[i] = make_uint2(0u, 0u);  // (bit 31 of .y says which lap of the buffer wrote the slot)
     __syncthreads();
 
     if (warp == 0) {
@@ -216,11 +244,89 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         return;
     }
 
-    // ---- voters
     RingCtx x;
-    x.b = &b; x.r = &r; x.gv = &gv; x.o = &o; x.rb = rb;
+    x.b = &b; x.r = &r; x.gv = &gv; x.o = &o; x.ws = &ws; x.rb = rb;
+    if (warp > VR_VOTERS) {
+        // ---- deciders: pool the voters' entries into rounds of 32 slow columns, one thread per column.  Every lane holds at
+        // most one pending entry (family side, lane, mask of columns still to decide); empty lanes refill from the buffer.
+        uint32_t my_fs = 0u, my_y = 0u;
+        bool open = true;  // the buffer may still deliver entries
+        for (;;) {
+            const bool want = (my_y & 0xFFFFu) == 0u;
+            const unsigned wbal = __ballot_sync(FULL, want);
+            if (open && wbal != 0u) {
+                const uint32_t ne = (uint32_t)__popc(wbal);
+                uint32_t g0 = 0u;
+                if (lane == 0) g0 = atomicAdd(&cq->rd, ne);
+                g0 = __shfl_sync(FULL, g0, 0);
+                bool none = false;
+                if (want) {
+                    const uint32_t i = g0 + (uint32_t)__popc(wbal & ((1u << lane) - 1u));
+                    const uint32_t expect = ((i / VR_CQ) & 1u) ^ 1u;
+                    for (;;) {
+                        const unsigned long long e = *(volatile unsigned long long *)&cq_ent[i % VR_CQ];  // (.x low, .y high)
+                        const uint32_t ey = (uint32_t)(e >> 32);
+                        if ((ey >> 31) == expect && (ey & 0xFFFFu) != 0u) {
+                            my_fs = (uint32_t)e;
+                            my_y = ey & 0x7FFFFFFFu;
+                            break;
+                        }
+                        // no voter is left and the entry was never reserved: there is nothing more to come
+                        if (*(volatile uint32_t *)&cq->voters_done == (uint32_t)VR_VOTERS && i >= *(volatile uint32_t *)&cq->wr) {
+                            none = true;
+                            break;
+                        }
+                        pipe_relax(100u);
+                    }
+                }
+                __syncwarp();
+                __threadfence_block();  // (the entries' records were stored before the entries were published)
+                if (lane == 0) {  // the slots are free again: committed in grab order
+                    while (*(volatile uint32_t *)&cq->consumed != g0) pipe_relax(20u);
+                    __threadfence_block();
+                    *(volatile uint32_t *)&cq->consumed = g0 + ne;
+                }
+                if (__any_sync(FULL, none)) open = false;
+                pipe_progress();
+            }
+            const int cnt = __popc(my_y & 0xFFFFu);
+            int incl = cnt;
+            for (int off = 1; off < WARP; off <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, off);
+                if (lane >= off) incl += v;
+            }
+            const int T = __shfl_sync(FULL, incl, WARP - 1);
+            if (T == 0) {
+                if (!open) break;
+                continue;
+            }
+            // column c of the round belongs to the first lane whose inclusive count exceeds c
+            int lo = 0, hi = WARP - 1;
+#pragma unroll
+            for (int step = 0; step < 5; step++) {
+                const int mid = (lo + hi) >> 1;
+                const int v = __shfl_sync(FULL, incl, mid);
+                if (v > lane) hi = mid;
+                else lo = mid + 1;
+            }
+            const uint32_t o_fs = __shfl_sync(FULL, my_fs, lo), o_y = __shfl_sync(FULL, my_y, lo);
+            const int o_excl = __shfl_sync(FULL, incl - cnt, lo);
+            if (lane < T) {
+                uint32_t mask = o_y & 0xFFFFu;
+                for (int q = lane - o_excl; q > 0; q--) mask &= mask - 1u;
+                const int bit = __ffs((int)mask) - 1;  // bit 8 * w + i of the mask = column 8 * w + 7 - i of the lane's sixteen
+                ring_slow_column_global(x, o_fs, VT_CHUNK * (int)((o_y >> 16) & 31u) + (bit & 8) + 7 - (bit & 7));
+            }
+            // the owners drop the columns this round took
+            int take = min(max(WARP - (incl - cnt), 0), cnt);
+            for (; take > 0; take--) my_y &= my_y - 1u | 0xFFFF0000u;
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ---- voters
     const uint32_t mod4 = 0x01010101u * (uint32_t)(o.moderate_quality & 0xFF);
-    uint32_t pool_i = 0u, pool_e = 0u;  // this warp's block of reserved entries of the global slow-column list
     const uint32_t sbase = smem_base(smem);
     // lane geometry and masks are kept across tiles while the tile shape (lanes per family side, usual record length) stays
     int cur_L = 0, cur_l = -1, S = 32, sub = 0, j = 0, col0 = 0;
@@ -285,12 +391,6 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 ChunkMasks cm = cm_common;
                 if (l_out != cur_l || len != l_out) cm = make_masks(l_out, len, col0);
                 if (mine && j == 0 && ft.mode != SIDE_COPY) GCB_COUNT((ft.flags & FS_UNIFORM) ? 4 : 5, 1);
-                if (mine && j == 0) {  // the slow columns add to these
-                    gcb_group_result *gr = r.groups + ft.slot;
-                    const int sd = (ft.flags & FS_SIDE1) ? 1 : 0;
-                    gr->diff[sd] = 0;
-                    gr->mismatch_inc[sd] = 0;
-                }
                 // per-column maxima live in 16-bit lanes (VIMNMX3.U16x2 is native, a per-byte maximum is seven instructions):
                 // mo[k] tracks bytes 1 and 3 of quality word k in the high byte of each half, me[k] bytes 0 and 2 (word << 8)
                 uint32_t mo[4] = {0u, 0u, 0u, 0u}, me[4] = {0u, 0u, 0u, 0u}, dis0 = 0u, dis1 = 0u;
@@ -435,21 +535,21 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     fin = __shfl_sync(FULL, fin, 0);
                     closer = fin == nb;
                 } else if (bal != 0u) {
+                    // ... or the CTA's ring buffer: the deciders take the entries from there (this warp never waits for them)
                     const uint32_t ne = (uint32_t)__popc(bal);
-                    if (pool_i + ne > pool_e) {  // a new block (what is left of the old one is marked unused)
-                        for (uint32_t i = pool_i + (uint32_t)lane; i < pool_e; i += WARP) sl.entries[i] = make_uint2(0u, 0u);
-                        unsigned int base = 0u;
-                        if (lane == 0) base = atomicAdd(sl.count, VQ_POOL);
-                        base = __shfl_sync(FULL, base, 0);
-                        if (base + VQ_POOL > sl.cap) {  // (cannot happen: the list holds an entry for every lane of every family side)
-                            if (lane == 0) raise_error(ws.error_flag, GCB_ERR_MALFORMED);
-                            base = 0u;
-                        }
-                        pool_i = base;
-                        pool_e = base + VQ_POOL;
+                    uint32_t idx = 0u;
+                    if (lane == 0) {
+                        idx = atomicAdd(&cq->wr, ne);
+                        while ((int32_t)(idx + ne - *(volatile uint32_t *)&cq->consumed) > VR_CQ) pipe_relax(50u);  // (room for the entries)
                     }
-                    if (mask16 != 0u) sl.entries[pool_i + __popc(bal & ((1u << lane) - 1u))] = make_uint2(2u * (uint32_t)ft.slot + ((ft.flags & FS_SIDE1) ? 1u : 0u), ((uint32_t)j << 16) | mask16);
-                    pool_i += ne;
+                    idx = __shfl_sync(FULL, idx, 0);
+                    __threadfence_block();  // the record's words (stored above) before the entry that lets a decider patch them
+                    if (mask16 != 0u) {
+                        const uint32_t e = idx + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                        const uint32_t ex = 2u * (uint32_t)ft.slot + ((ft.flags & FS_SIDE1) ? 1u : 0u);
+                        const uint32_t ey = ((((e / VR_CQ) & 1u) ^ 1u) << 31) | ((uint32_t)j << 16) | mask16;
+                        *(volatile unsigned long long *)&cq_ent[e % VR_CQ] = ((unsigned long long)ey << 32) | ex;  // one 8-byte store
+                    }
                 }
                 if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
                 bundle = __shfl_sync(FULL, bundle, 0);
@@ -516,7 +616,11 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         __syncwarp();
         if (lane == 0) pipe_arrive(empty + s);
     }
-    for (uint32_t i = pool_i + (uint32_t)lane; i < pool_e; i += WARP) sl.entries[i] = make_uint2(0u, 0u);  // what is left of the warp's block
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        atomicAdd(&cq->voters_done, 1u);
+    }
 #undef GCB_LDS32
 }
 

@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b
                                                                       int32_t force_generic) {
     const int lane = lane_id();
     const int tile = (int)(blockIdx.x * (VS_PREP_THREADS / WARP) + (threadIdx.x >> 5));
-    if (tile >= n_tiles) return;
+    if (tile >= n_tiles || batch_is_malformed(ws.error_flag)) return;
     const TileDir t0 = ws.tile_dir[tile], t1 = ws.tile_dir[tile + 1];
     const int c0 = t0.c0, c1 = t1.c0;
     const int P0 = t0.p0, NP = t1.p0 - t0.p0;
@@ -508,6 +508,7 @@ GCB_DEV void rollback_family_side(const BatchView &b, const ResultView &r, const
 
 __global__ void __launch_bounds__(VQ_FINAL_THREADS) vote_rollback_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o, RollbackList rb,
                                                                          int32_t p0, int32_t p1) {
+    if (batch_is_malformed(ws.error_flag)) return;
     const int n = *rb.count;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
     if (n <= rb.cap) {

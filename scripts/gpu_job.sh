@@ -11,12 +11,10 @@ if [ "${2:-tests}" = "tests" ]; then
 fi
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 tail -c 3000 gpurun_out/bench_$tag.json
-timeout 900 python scripts/shape_perf.py cfg1 cfg3 cfg4 cfg5 cfg2:1000000:15 cfg2:1000000:14 deep:30:0.01 deep:30:0.003 deep:50:0.003 > gpurun_out/shapes_$tag.log 2>&1
+timeout 900 python scripts/shape_perf.py cfg1 cfg3 cfg4 cfg5 cfg2:1000000:14 deep:30:0.01 deep:30:0.003 deep:50:0.003 > gpurun_out/shapes_$tag.log 2>&1
 cat gpurun_out/shapes_$tag.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 40 --csv --log-file gpurun_out/launches_$tag.csv \
   python bench.py --steps 2 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/launches_$tag.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:vote_ring -s 3 -c 1 -o gpurun_out/prof_ring_$tag \
   python bench.py --steps 1 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/ncu_ring_$tag.log 2>&1
 ls -la gpurun_out | tail -8
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:slow_columns -s 3 -c 1 -o gpurun_out/prof_slow_$tag \
-  python bench.py --steps 1 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/ncu_slow_$tag.log 2>&1

@@ -69,12 +69,12 @@ def test_generic_vote_matches_oracle(engine_cls, oracle, name, thunk):
 
 
 @pytest.mark.parametrize("name,thunk", CASES, ids=[c[0] for c in CASES])
-def test_large_tile_window_matches_oracle(engine_cls, oracle, name, thunk):
-    """The vote over 32 KB payload windows (half the tiles, one group of fifteen voter warps) on every case."""
+def test_small_tile_window_matches_oracle(engine_cls, oracle, name, thunk):
+    """The vote over 16 KB payload windows (twice the tiles, the voter warps in three groups) on every case."""
     batch, genome, opt = thunk()
     with engine_cls(opt, 0) as eng:
         eng.set_reference(genome)
-        eng.set_debug(2, 15)
+        eng.set_debug(2, 14)
         res = eng.cluster_by_umi(batch)
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 

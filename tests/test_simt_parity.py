@@ -89,10 +89,10 @@ def test_generic_vote_matches_oracle_under_simt_check(simt_lib, oracle, name, th
 
 
 @pytest.mark.parametrize("name,thunk", LIGHT_CASES, ids=[c[0] for c in LIGHT_CASES])
-def test_large_tile_window_matches_oracle_under_simt_check(simt_lib, oracle, name, thunk):
-    """The vote over 32 KB payload windows instead of 16 KB ones (half the tiles, one group of fifteen voter warps): same bytes."""
+def test_small_tile_window_matches_oracle_under_simt_check(simt_lib, oracle, name, thunk):
+    """The vote over 16 KB payload windows instead of 32 KB ones (twice the tiles, the voter warps in three groups): same bytes."""
     batch, genome, opt = thunk()
-    res, _ = run(simt_lib, batch, genome, opt, lambda eng: eng.set_debug(2, 15))
+    res, _ = run(simt_lib, batch, genome, opt, lambda eng: eng.set_debug(2, 14))
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 
 
@@ -104,3 +104,36 @@ def test_lanes_per_cluster_do_not_change_results(simt_lib, oracle, name, lanes):
     batch, genome, opt = dict(CASES)[name]()
     res, _ = run(simt_lib, batch, genome, opt, lambda eng: eng.set_debug(3, lanes))
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} lanes {lanes}")
+
+
+@pytest.mark.parametrize("what", ["slab_misaligned", "pair_off_not_monotone", "data_off_unaligned", "cigar_out_of_range", "record_outside_slab"])
+def test_malformed_batches_are_refused(simt_lib, what):
+    """A batch that breaks a documented precondition comes back as GCB_ERR_MALFORMED (no fault, no hang)."""
+    import numpy as np
+    from gencore_b200.abi import GCB_ERR_MALFORMED
+    from gencore_b200.engine import ConsensusEngine, EngineError
+    batch, genome, opt = dict(CASES)["cfg2_1500"]()
+    reads = batch.reads.copy()
+    pair_off = batch.cluster_pair_off.copy()
+    c = batch.n_clusters // 2
+    p = int(pair_off[c])
+    if what == "slab_misaligned":
+        reads["data_off"][2 * p:] += 4
+    elif what == "pair_off_not_monotone":
+        pair_off[c] = pair_off[c + 1] + 3
+    elif what == "data_off_unaligned":
+        reads["data_off"][2 * p + 1] += 1
+    elif what == "cigar_out_of_range":
+        reads["cigar_off"][2 * p + 1] = len(batch.cigar) + 5
+    else:
+        reads["data_off"][2 * p + 3] = len(batch.payload) - 16
+    import dataclasses
+    bad = dataclasses.replace(batch, reads=reads, cluster_pair_off=pair_off)
+    with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
+        eng.set_reference(genome)
+        with pytest.raises(EngineError) as ei:
+            eng.cluster_by_umi(bad)
+        assert ei.value.code == GCB_ERR_MALFORMED
+        # the context stays usable
+        res = eng.cluster_by_umi(batch)
+    assert int(res.out_bytes[0]) > 0
