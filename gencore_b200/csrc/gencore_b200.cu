@@ -12,6 +12,7 @@
 #include "k_duplex.cuh"
 #include "k_group_select.cuh"
 #include "k_score_vote.cuh"
+#include "k_fasta_pack.cuh"
 #include "k_umi_extract.cuh"
 #include "k_vote_ring.cuh"
 
@@ -51,6 +52,7 @@ struct gcb_ctx {
     DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
     DevBuf d_pair_group, d_ngroups, d_groups, d_out, d_out_bytes;
     DevBuf u_names, u_off, u_out, u_status;  // gcb_extract_umi
+    DevBuf f_text, f_anchor, f_cnt, f_hpos, f_hbase, f_flag, f_coff, f_out;  // gcb_pack_fasta
     // gcb_consensus_batch pipelines chunks of clusters: copies in, kernels and copies out run on three streams
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaEvent_t ev_in[GCB_MAX_CHUNKS] = {nullptr}, ev_done[GCB_MAX_CHUNKS] = {nullptr}, ev_out[GCB_MAX_CHUNKS] = {nullptr};
@@ -388,7 +390,8 @@ void gcb_destroy(gcb_ctx *ctx) {
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
                      &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_need, &ctx->w_rb_list, &ctx->w_rb_count,  &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
-                     &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status};
+                     &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status, &ctx->f_text, &ctx->f_anchor, &ctx->f_cnt, &ctx->f_hpos, &ctx->f_hbase,
+                     &ctx->f_flag, &ctx->f_coff, &ctx->f_out};
     for (DevBuf *b : all) release(*b);
     for (int k = 0; k < GCB_MAX_CHUNKS; k++) {
         if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
@@ -656,6 +659,82 @@ int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, in
     GCB_CUDA(ctx, cudaMemcpyAsync(out_umi, ctx->u_out.p, (size_t)n * umi_words * 8, cudaMemcpyDeviceToHost, st));
     GCB_CUDA(ctx, cudaMemcpyAsync(status, ctx->u_status.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     GCB_CUDA(ctx, cudaStreamSynchronize(st));
+    return GCB_OK;
+}
+
+int gcb_pack_fasta(gcb_ctx *ctx, const char *text, int64_t n, int32_t max_contigs, uint8_t *packed4_out, int64_t packed_cap, int64_t *contig_off,
+                   int64_t *contig_len, int64_t *name_off, int32_t *name_len, int32_t *n_contigs, int64_t *packed_bytes) {
+    if (!ctx || n < 0 || (n > 0 && !text) || max_contigs < 0 || !n_contigs || !packed_bytes || packed_cap < 0 ||
+        (max_contigs > 0 && (!contig_off || !contig_len || !name_off || !name_len)))
+        return fail(ctx, GCB_ERR_ARG, "gcb_pack_fasta: bad argument");
+    *n_contigs = 0;
+    *packed_bytes = 0;
+    // fastareader.cpp:33-40: the reader starts behind the first '>' of the file, wherever it is
+    const char *first = n > 0 ? (const char *)memchr(text, '>', (size_t)n) : nullptr;
+    if (!first) return GCB_OK;
+    const int64_t skip = first - text, m = n - skip;
+    const int64_t n_blocks = (m + FA_BLOCK - 1) / FA_BLOCK;
+    GCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = reserve(ctx, ctx->f_text, (size_t)m)) != GCB_OK || (rc = reserve(ctx, ctx->f_anchor, (size_t)(n_blocks + 1) * 8)) != GCB_OK ||
+        (rc = reserve(ctx, ctx->f_cnt, (size_t)(n_blocks + 1) * 16)) != GCB_OK || (rc = reserve(ctx, ctx->f_hpos, (size_t)max_contigs * 8)) != GCB_OK ||
+        (rc = reserve(ctx, ctx->f_hbase, (size_t)max_contigs * 8)) != GCB_OK || (rc = reserve(ctx, ctx->f_flag, 4)) != GCB_OK ||
+        (rc = reserve(ctx, ctx->f_coff, (size_t)max_contigs * 8)) != GCB_OK)
+        return rc;
+    cudaStream_t st = ctx->stream;
+    GCB_CUDA(ctx, cudaMemcpyAsync(ctx->f_text.p, first, (size_t)m, cudaMemcpyHostToDevice, st));
+    GCB_CUDA(ctx, cudaMemsetAsync(ctx->f_flag.p, 0, 4, st));
+    const FaView v = {(const uint8_t *)ctx->f_text.p, m};
+    int64_t *anchor = (int64_t *)ctx->f_anchor.p, *cnt = (int64_t *)ctx->f_cnt.p, *hpos = (int64_t *)ctx->f_hpos.p, *hbase = (int64_t *)ctx->f_hbase.p;
+    GCB_LAUNCH(fa_anchor_kernel, dim3((unsigned)n_blocks), dim3(FA_THREADS), 0, st, v, anchor);
+    GCB_LAUNCH(fa_scan_kernel<FaMax>, dim3(1), dim3(FA_THREADS), 0, st, anchor, n_blocks, 1);
+    GCB_LAUNCH(fa_count_kernel, dim3((unsigned)n_blocks), dim3(FA_THREADS), 0, st, v, (const int64_t *)anchor, cnt);
+    GCB_LAUNCH(fa_scan_kernel<FaSum>, dim3(1), dim3(FA_THREADS), 0, st, cnt, n_blocks, 2);
+    GCB_LAUNCH(fa_header_kernel, dim3((unsigned)n_blocks), dim3(FA_THREADS), 0, st, v, (const int64_t *)anchor, (const int64_t *)cnt, hpos, hbase,
+               max_contigs, (int32_t *)ctx->f_flag.p);
+    ctx->launches += 5;
+    GCB_CUDA(ctx, cudaGetLastError());
+    int64_t totals[2] = {0, 0};
+    int32_t flag = 0;
+    GCB_CUDA(ctx, cudaMemcpyAsync(totals, cnt + 2 * n_blocks, 16, cudaMemcpyDeviceToHost, st));
+    GCB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->f_flag.p, 4, cudaMemcpyDeviceToHost, st));
+    GCB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (flag & 2) return fail(ctx, GCB_ERR_MALFORMED, "gcb_pack_fasta: a header line the reference does not read as one ('>' before a line end or another '>')");
+    if ((flag & 1) || totals[1] > max_contigs) return fail(ctx, GCB_ERR_CAPACITY, "gcb_pack_fasta: more contigs than max_contigs");
+    const int32_t nc = (int32_t)totals[1];
+    if (nc > 0) {
+        GCB_CUDA(ctx, cudaMemcpyAsync(name_off, hpos, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+        GCB_CUDA(ctx, cudaMemcpyAsync(contig_len, hbase, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+        GCB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    int64_t bytes = 0;
+    for (int32_t i = 0; i < nc; i++) {
+        const int64_t end = i + 1 < nc ? contig_len[i + 1] : totals[0];
+        contig_len[i] = end - contig_len[i];  // bases between this header and the next
+        contig_off[i] = bytes;
+        bytes += ((contig_len[i] + 1) / 2 + 15) & ~(int64_t)15;
+        // the contig's id: the header up to the first space (fastareader.cpp:98-102); offsets are into the caller's text
+        const int64_t h = skip + name_off[i] + 1;
+        int64_t e = h;
+        while (e < n && text[e] != '\n' && text[e] != ' ') e++;
+        name_off[i] = h;
+        name_len[i] = (int32_t)(e - h);
+    }
+    if (bytes == 0) bytes = 16;
+    if (bytes > packed_cap || !packed4_out) return fail(ctx, GCB_ERR_CAPACITY, "gcb_pack_fasta: packed4_out too small");
+    if ((rc = reserve(ctx, ctx->f_out, (size_t)bytes)) != GCB_OK) return rc;
+    GCB_CUDA(ctx, cudaMemsetAsync(ctx->f_out.p, 0, (size_t)bytes, st));
+    if (nc > 0) {
+        GCB_CUDA(ctx, cudaMemcpyAsync(ctx->f_coff.p, contig_off, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+        GCB_LAUNCH(fa_pack_kernel, dim3((unsigned)n_blocks), dim3(FA_THREADS), 0, st, v, (const int64_t *)anchor, (const int64_t *)cnt, (const int64_t *)hbase,
+                   (const int64_t *)ctx->f_coff.p, nc, (uint32_t *)ctx->f_out.p);
+        ctx->launches++;
+        GCB_CUDA(ctx, cudaGetLastError());
+    }
+    GCB_CUDA(ctx, cudaMemcpyAsync(packed4_out, ctx->f_out.p, (size_t)bytes, cudaMemcpyDeviceToHost, st));
+    GCB_CUDA(ctx, cudaStreamSynchronize(st));
+    *n_contigs = nc;
+    *packed_bytes = bytes;
     return GCB_OK;
 }
 

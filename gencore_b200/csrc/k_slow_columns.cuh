@@ -35,6 +35,9 @@ GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const Genome
     Bins3 bins;
     bins.init();
     const int m = fs.m;
+    // (the reference base of a simple-CIGAR template is fetched now, so that its load overlaps the reads')
+    const bool ref_early = (fs.flags & FS_REF_OK) && (fs.flags & FS_SIMPLE_CIGAR) && fs.ref_nib0 + col >= 0 && ((fs.ref_nib0 + col) >> 1) < gv.packed_bytes;
+    const uint8_t ref_two = ref_early ? gv.packed4[(fs.ref_nib0 + col) >> 1] : (uint8_t)0;
     if (fs.flags & FS_UNIFORM) {
         const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
         const int k = col - (int)tv.ov_own, mp = (int)tv.ov_mate + k;
@@ -44,27 +47,44 @@ GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const Genome
         const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
         const int mpi = mvalid ? mp : 0;
         const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
-        for (int e = 0; e < m; e++) {
-            const uint32_t w = *(const uint32_t *)(ents + e);  // own_off4 | mate_off4 << 16
-            if ((w & 0xFFFFu) == VR_NO_VOTE) continue;
-            const uint8_t *rec = cb + 4 * (int)(w & 0xFFFFu);
-            int ql = rec[col];
-            const int base = (rec[soff] >> nsh) & 0xF;
-            int score;
-            if (mvalid) {
-                const uint8_t *mrec = cb + 4 * (int)(w >> 16);
-                const int mql = mrec[mpi];
-                const int mbase = (mrec[msoff] >> mnsh) & 0xF;
-                const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
-                const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
-                const int s_match = sc8(tab.q2s((ql + mql) / 2) + 4);                        // pair.cpp:147-152
-                const int s_mis = mine ? sc8(tab.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;  // pair.cpp:153-169
-                score = base == mbase ? s_match : s_mis;
-                ql = base == mbase ? ql : max(0, ql - mql);
-            } else {
-                score = plain ? tab.q2s(ql) : tab.sm;
+        // eight reads at a time, in two waves of independent loads (where their records lie, then their bytes): a column decided
+        // from global memory waits for two round trips per eight reads instead of two per read
+        for (int e0 = 0; e0 < m; e0 += 8) {
+            uint32_t w[8], x[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) w[u] = e0 + u < m ? *(const uint32_t *)(ents + e0 + u) : (uint32_t)VR_NO_VOTE;  // own_off4 | mate_off4 << 16
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                x[u] = 0u;
+                if ((w[u] & 0xFFFFu) != VR_NO_VOTE) {
+                    const uint8_t *rec = cb + 4 * (int)(w[u] & 0xFFFFu);
+                    x[u] = (uint32_t)rec[col] | ((uint32_t)rec[soff] << 8);
+                    if (mvalid) {
+                        const uint8_t *mrec = cb + 4 * (int)(w[u] >> 16);
+                        x[u] |= ((uint32_t)mrec[mpi] << 16) | ((uint32_t)mrec[msoff] << 24);
+                    }
+                }
             }
-            bins.add(base, ql, score);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if ((w[u] & 0xFFFFu) == VR_NO_VOTE) continue;
+                int ql = (int)(x[u] & 0xFFu);
+                const int base = (int)((x[u] >> (8 + nsh)) & 0xFu);
+                int score;
+                if (mvalid) {
+                    const int mql = (int)((x[u] >> 16) & 0xFFu);
+                    const int mbase = (int)((x[u] >> (24 + mnsh)) & 0xFu);
+                    const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
+                    const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
+                    const int s_match = sc8(tab.q2s((ql + mql) / 2) + 4);                        // pair.cpp:147-152
+                    const int s_mis = mine ? sc8(tab.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;  // pair.cpp:153-169
+                    score = base == mbase ? s_match : s_mis;
+                    ql = base == mbase ? ql : max(0, ql - mql);
+                } else {
+                    score = plain ? tab.q2s(ql) : tab.sm;
+                }
+                bins.add(base, ql, score);
+            }
         }
     } else {
         for (int e = 0; e < m; e++) {
@@ -143,7 +163,7 @@ GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const Genome
             }
             const int64_t nib = fs.ref_nib0 + refpos;
             if (refpos >= 0 && nib >= 0 && (nib >> 1) < gv.packed_bytes) {  // the bound only guards malformed CIGARs
-                const uint8_t two = gv.packed4[nib >> 1];
+                const uint8_t two = ref_early ? ref_two : gv.packed4[nib >> 1];
                 ref4 = genome_nibble_to_bam((nib & 1) ? (two >> 4) : (two & 0xF));
             }
         }

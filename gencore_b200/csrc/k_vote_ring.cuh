@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         // ---- producer: lane 0 fills the stages, up to n_stages tiles ahead of the voters; the whole warp fetches the
         // headers of this CTA's next 32 tiles at once, so that no tile waits for a header on its way from global memory
         TileHdr2 *hcache = (TileHdr2 *)(smem + VR_OFF_HCACHE);
+        const uint64_t l2_keep = tile_l2_policy_keep();
         int k = 0;
         // ring-buffer arena: the tiles in flight are k_tail .. k-1, their allocations lie between off_of[k_tail] and head (wrapping);
         // slot k % n_stages (barriers, header) once the tile that used it before is released
@@ -217,8 +218,9 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     fill(sh, cur, (int32_t)t, at);
                     shdr[s] = sh;
                     pipe_expect(full + s, slab_bytes + vr_bytes + ft_bytes);
-                    if (slab_bytes > 0) tile_copy(smem + sh.slab_off, b.payload + cur.slab0, slab_bytes, full + s);
-                    tile_copy(smem + sh.vr_off, ws.vote_reads + 2 * (int64_t)cur.p0, vr_bytes, full + s);
+                    // (the deciders read a few bytes of the slab and of the VoteRead table again, from L2: keep the lines there)
+                    if (slab_bytes > 0) tile_copy_hint(smem + sh.slab_off, b.payload + cur.slab0, slab_bytes, full + s, l2_keep);
+                    tile_copy_hint(smem + sh.vr_off, ws.vote_reads + 2 * (int64_t)cur.p0, vr_bytes, full + s, l2_keep);
                     tile_copy(smem + sh.ft_off, fs_tiles + 2 * (int64_t)cur.p0, ft_bytes, full + s);
                     pipe_commit(full + s);
                     k++;

@@ -24,7 +24,7 @@ DEFAULT_LIB = os.path.join(HERE, "csrc", "libgencore_b200.so")
 # every symbol include/gencore_b200.h declares
 ABI_SYMBOLS = ["gcb_abi_version", "gcb_default_options", "gcb_create", "gcb_destroy", "gcb_last_error", "gcb_set_reference",
                "gcb_set_reference_device", "gcb_consensus_batch", "gcb_consensus_batch_device", "gcb_batch_status",
-               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_debug", "gcb_host_alloc", "gcb_host_free"]
+               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_debug", "gcb_pack_fasta", "gcb_host_alloc", "gcb_host_free"]
 
 
 class EngineError(RuntimeError):
@@ -57,6 +57,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gcb_batch_status.argtypes = [C.c_void_p, C.c_void_p]
     lib.gcb_extract_umi.restype = C.c_int
     lib.gcb_extract_umi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.gcb_pack_fasta.restype = C.c_int
+    lib.gcb_pack_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
     lib.gcb_set_chunk_bytes.restype = C.c_int
     lib.gcb_host_alloc.restype = C.c_void_p
     lib.gcb_host_alloc.argtypes = [C.c_size_t, C.c_int]
@@ -146,6 +149,20 @@ class ConsensusEngine:
         self._check(self.lib.gcb_extract_umi(self._ctx, buf.ctypes.data, off.ctypes.data, len(names), prefix.encode(), umi_words,
                                              out.ctypes.data, status.ctypes.data))
         return out, status[:len(names)]
+
+    # -- FastaReader::readAll + to4bits (fastareader.cpp:58-152): FASTA text -> Genome
+    def pack_fasta(self, text: bytes, max_contigs: int = 4096) -> Genome:
+        buf = np.frombuffer(text, np.uint8) if len(text) else np.zeros(1, np.uint8)
+        cap = len(text) // 2 + 16 * max_contigs + 16
+        out = np.zeros(cap, np.uint8)
+        off, ln, noff = (np.zeros(max(max_contigs, 1), np.int64) for _ in range(3))
+        nlen = np.zeros(max(max_contigs, 1), np.int32)
+        nc, nb = C.c_int32(0), C.c_int64(0)
+        self._check(self.lib.gcb_pack_fasta(self._ctx, buf.ctypes.data, len(text), max_contigs, out.ctypes.data, cap, off.ctypes.data, ln.ctypes.data,
+                                            noff.ctypes.data, nlen.ctypes.data, C.byref(nc), C.byref(nb)))
+        n = nc.value
+        names = [text[int(noff[i]):int(noff[i]) + int(nlen[i])].decode("latin-1") for i in range(n)]
+        return Genome(np.ascontiguousarray(out[:max(nb.value, 16)]), off[:n].copy(), ln[:n].copy(), names)
 
     def set_chunk_bytes(self, nbytes: int) -> None:
         """Payload bytes per pipeline chunk of cluster_by_umi (tuning only: results do not depend on it)."""

@@ -205,6 +205,17 @@ int gcb_batch_status(gcb_ctx *ctx, void *stream);
 int gcb_extract_umi(gcb_ctx *ctx, const char *names, const int64_t *name_off, int32_t n, const char *prefix, int32_t umi_words,
                     uint64_t *out_umi, uint8_t *status);
 
+/* FastaReader::readAll + to4bits (fastareader.cpp:58-152) on the device: the text of a FASTA file in, the genome in the layout
+ * gcb_set_reference wants out.  text / outputs are HOST buffers.  Contig i (file order) has contig_len[i] bases at byte
+ * contig_off[i] (16-byte aligned) of packed4_out; its id — the header up to the first space, fastareader.cpp:98-102 — is
+ * text[name_off[i] .. name_off[i] + name_len[i]).  (The reference keeps its contigs in a map by id: of two contigs with the same
+ * id the LATER one wins.)  Everything the reference's reader does with odd input is reproduced — text before the first '>',
+ * lower case, CR, digits, '-' and '*', blank lines that swallow the next line — except the two header shapes it
+ * does not read as headers ('>' directly before a line end or another '>'): GCB_ERR_MALFORMED.  GCB_ERR_CAPACITY when there
+ * are more than max_contigs contigs or packed_cap (n / 2 + 16 * max_contigs + 16 is always enough) is too small. */
+int gcb_pack_fasta(gcb_ctx *ctx, const char *text, int64_t n, int32_t max_contigs, uint8_t *packed4_out, int64_t packed_cap,
+                   int64_t *contig_off, int64_t *contig_len, int64_t *name_off, int32_t *name_len, int32_t *n_contigs, int64_t *packed_bytes);
+
 /* Tuning knob of gcb_consensus_batch: payload bytes per pipeline chunk (default 48 MiB; at most 16 chunks per call,
  * chunks are whole clusters).  Results do not depend on it. */
 int gcb_set_chunk_bytes(gcb_ctx *ctx, int64_t bytes);

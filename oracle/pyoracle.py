@@ -208,3 +208,25 @@ class Reference:
         n = self.lib.gcr_get_umi(qname.encode(), prefix.encode(), buf, 512)
         assert n >= 0
         return buf.value.decode()
+
+
+def reference_fasta_load(text: bytes, max_contigs: int = 64):
+    """The reference's own FastaReader over `text`: (ids, sizes, offsets, packed bytes) in file order."""
+    lib = C.CDLL(REF_SO)
+    lib.gcr_fasta_load.restype = C.c_int
+    lib.gcr_fasta_load.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    ids = np.zeros(256 * max_contigs, np.uint8)
+    sizes, offs = np.zeros(max_contigs, np.int64), np.zeros(max_contigs, np.int64)
+    cap = len(text) // 2 + 16 * max_contigs + 16
+    packed = np.zeros(cap, np.uint8)
+    with tempfile.NamedTemporaryFile(suffix=".fa", delete=False) as f:
+        f.write(text)
+        path = f.name
+    try:
+        n = lib.gcr_fasta_load(path.encode(), max_contigs, ids.ctypes.data, sizes.ctypes.data, offs.ctypes.data, packed.ctypes.data, cap)
+    finally:
+        os.unlink(path)
+    if n < 0:
+        raise RuntimeError("gcr_fasta_load failed")
+    names = [bytes(ids[256 * i:256 * (i + 1)]).split(b"\0")[0] for i in range(n)]
+    return names, sizes[:n].copy(), offs[:n].copy(), packed

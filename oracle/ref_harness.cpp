@@ -239,4 +239,34 @@ int gcr_get_umi(const char *qname, const char *prefix, char *out, int cap) {
 }
 int gcr_self_test(void) { return (BamUtil::test() && Cluster::test()) ? 1 : 0; }
 
+// The reference's own FastaReader (fastareader.cpp) over a file, contig by contig in FILE order (readNext is driven as
+// readAll drives it, fastareader.cpp:159-170, without the map that would hide a repeated id): id (NUL-terminated, up to 255
+// bytes each), size in bases, and the 4-bit data back to back at 16-byte aligned offsets.  Returns the number of contigs, or
+// -1 when something does not fit.
+int gcr_fasta_load(const char *path, int max_contigs, char *ids, int64_t *sizes, int64_t *offs, uint8_t *packed, int64_t packed_cap) {
+    Options opt;
+    int n = 0;
+    int64_t at = 0;
+    try {
+        FastaReader reader(&opt, path);
+        while (reader.hasNext()) {
+            reader.readNext();
+            if (n >= max_contigs) return -1;
+            const std::string id = reader.currentID();
+            const int64_t bytes = (reader.mCurrentSize + 1) / 2;
+            if (id.size() > 255 || at + bytes > packed_cap) return -1;
+            memcpy(ids + 256 * n, id.c_str(), id.size() + 1);
+            sizes[n] = reader.mCurrentSize;
+            offs[n] = at;
+            if (bytes) memcpy(packed + at, reader.mCurrentSequence, (size_t)bytes);
+            delete[] reader.mCurrentSequence;
+            at += (bytes + 15) & ~(int64_t)15;
+            n++;
+        }
+    } catch (...) {
+        return -1;
+    }
+    return n;
+}
+
 }  // extern "C"
