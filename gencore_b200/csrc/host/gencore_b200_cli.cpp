@@ -430,6 +430,7 @@ struct Engine {
     decltype(&gcb_set_reference) set_reference;
     decltype(&gcb_consensus_batch) consensus_batch;
     decltype(&gcb_extract_umi) extract_umi;
+    decltype(&gcb_pack_fasta) pack_fasta;
     decltype(&gcb_default_options) default_options;
     template <typename F>
     void sym(F &f, const char *name) {
@@ -445,6 +446,7 @@ struct Engine {
         sym(set_reference, "gcb_set_reference");
         sym(consensus_batch, "gcb_consensus_batch");
         sym(extract_umi, "gcb_extract_umi");
+        sym(pack_fasta, "gcb_pack_fasta");
         sym(default_options, "gcb_default_options");
     }
     void check(int rc, const char *what) {
@@ -459,7 +461,9 @@ struct Genome {
     std::map<std::string, int> index;
 };
 
-Genome load_fasta(const std::string &path) {
+// The file is read here; reading it the way FastaReader does (readNext + to4bits) and packing it is the engine's work
+// (gcb_pack_fasta: the genome is packed on the GPU).  Of two contigs with one id the later wins, as in the reference's map.
+Genome load_fasta(const std::string &path, Engine &eng) {
     FILE *fp = fopen(path.c_str(), "rb");
     if (!fp) die("Failed to open file: " + path);
     std::string all;
@@ -468,43 +472,22 @@ Genome load_fasta(const std::string &path) {
     while ((n = fread(chunk, 1, sizeof chunk, fp)) > 0) all.append(chunk, n);
     fclose(fp);
     Genome g;
-    size_t i = 0;
-    // FastaReader::readNext: the first character of every line is taken as it is (upper-cased), the rest of the line
-    // keeps letters, '-' and '*' (util.h:194-210 str_keep_valid_sequence)
-    while (i < all.size() && all[i] != '>') i++;  // (readAll's first readNext consumes up to the first '>')
-    while (i < all.size()) {
-        i++;  // '>'
-        size_t eol = all.find('\n', i);
-        if (eol == std::string::npos) eol = all.size();
-        std::string header = all.substr(i, eol - i);
-        i = eol < all.size() ? eol + 1 : eol;
-        std::string seq;
-        while (i < all.size() && all[i] != '>') {
-            char c = all[i++];
-            if (c >= 'a' && c <= 'z') c = (char)(c - ('a' - 'A'));
-            seq.push_back(c);
-            eol = all.find('\n', i);
-            if (eol == std::string::npos) eol = all.size();
-            for (size_t k = i; k < eol; k++) {
-                char d = all[k];
-                if (d >= 'a' && d <= 'z') d = (char)(d - ('a' - 'A'));
-                if ((d >= 'A' && d <= 'Z') || d == '-' || d == '*') seq.push_back(d);
-            }
-            i = eol < all.size() ? eol + 1 : eol;
-        }
-        const std::string id = header.substr(0, header.find(' '));
-        g.index[id] = (int)g.len.size();
-        g.off.push_back((int64_t)g.packed.size());
-        g.len.push_back((int64_t)seq.size());
-        const size_t bytes = (seq.size() + 1) / 2;
-        const size_t base = g.packed.size();
-        g.packed.resize(base + ((bytes + 15) & ~(size_t)15), 0);
-        for (size_t k = 0; k < seq.size(); k++) {  // to4bits: even index in the low nibble
-            const char c = seq[k];
-            const uint8_t bits = c == 'A' ? 1 : c == 'T' ? 2 : c == 'C' ? 3 : c == 'G' ? 4 : 0;
-            g.packed[base + k / 2] |= (k % 2 == 0) ? bits : (uint8_t)(bits << 4);
-        }
-    }
+    int32_t max_contigs = 1;
+    for (char c : all) max_contigs += c == '>';
+    g.packed.assign(all.size() / 2 + 16 * (size_t)max_contigs + 16, 0);
+    g.off.assign((size_t)max_contigs, 0);
+    g.len.assign((size_t)max_contigs, 0);
+    std::vector<int64_t> name_off((size_t)max_contigs);
+    std::vector<int32_t> name_len((size_t)max_contigs);
+    int32_t nc = 0;
+    int64_t bytes = 0;
+    eng.check(eng.pack_fasta(eng.ctx, all.data(), (int64_t)all.size(), max_contigs, g.packed.data(), (int64_t)g.packed.size(), g.off.data(), g.len.data(),
+                             name_off.data(), name_len.data(), &nc, &bytes),
+              "gcb_pack_fasta");
+    g.packed.resize((size_t)bytes);
+    g.off.resize((size_t)nc);
+    g.len.resize((size_t)nc);
+    for (int32_t i = 0; i < nc; i++) g.index[all.substr((size_t)name_off[(size_t)i], (size_t)name_len[(size_t)i])] = i;
     return g;
 }
 
@@ -920,7 +903,7 @@ void Pipeline::run() {
         double t0 = now_s();
         eng.open(cli.engine);
         eng.check(eng.create(&cli.opt, cli.device, &eng.ctx), "gcb_create");
-        genome = load_fasta(cli.ref);
+        genome = load_fasta(cli.ref, eng);
         if (!genome.len.empty())
             eng.check(eng.set_reference(eng.ctx, genome.packed.data(), (int64_t)genome.packed.size(), genome.off.data(), genome.len.data(),
                                         (int32_t)genome.len.size()),

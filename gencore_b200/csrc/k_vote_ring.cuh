@@ -16,15 +16,12 @@
 //                     moderateQuality: exactly group.cpp:421-427 under `implied`) are finished in the word: per-column maxima
 //                     in 16-bit lanes (VIMNMX3.U16x2 over two reads per iteration), disagreement as OR-accumulated XOR
 //                     residues of the raw words; uniform families (every fixed-length library) run a branch-free loop.
-//   slow columns      a lane that found slow columns publishes ONE 8-byte entry (family side, lane, 16-bit column mask) in a
-//                     ring buffer in shared memory and goes on; the stage is released as if the columns did not exist.
-//   warps 16..19      deciders.  They pool the entries of all the tiles into rounds of exactly 32 columns, one thread per
-//                     column, and decide them (k_slow_columns.cuh: group.cpp:376-525) reading the few bytes a column needs —
-//                     per read a quality, a base nibble and the mate's — from the payload in GLOBAL memory: the tile crossed
-//                     this SM microseconds ago, so these are L2 hits, and no stage waits for a chain of dependent loads.
-//                     (Measured alternatives, profiles/r03_notes.md: deciding from the staged slab, or extracting records
-//                     from it per tile, holds every stage and starves the voters; extracting per bundle costs a third of the
-//                     kernel's instructions; a second kernel behind this one finds the payload gone from L2.)
+//   slow columns      the lane that found a slow column writes the column's record into a global queue right away: a 32-byte
+//                     self-contained header, then per read of the family side its quality, base, mate quality, mate base and
+//                     overlap state (4 bytes).  Queue space comes from a per-warp pool reserved with one 64-bit atomic
+//                     (records and words in one counter) per ~10 bundles; slow_columns_kernel (k_slow_columns.cuh) decides
+//                     the queued columns at full occupancy.  A full queue hands the tile to the generic kernel.  The ring
+//                     never waits for a slow column.  (Measured alternatives, profiles/r03_notes.md.)
 //   deep tiles        (24 pairs or more per family side on average: few bundles, hundreds of slow columns per tile) keep
 //                     their list in the stage; the warp that finishes the tile's last bundle closes it (prefix sums of the
 //                     entries' column counts), and ALL voter warps of the tile then decide the columns, 32 at a time, one
@@ -36,10 +33,9 @@
 
 namespace gcb {
 
-constexpr int VR_THREADS = 640;    // warp 0 produces, fifteen warps vote, four decide slow columns (96 registers per thread)
+constexpr int VR_THREADS = 512;    // warp 0 produces, fifteen warps vote (128 registers per thread)
 constexpr int VR_WARPS = VR_THREADS / WARP;
-constexpr int VR_VOTERS = 15, VR_DECIDERS = VR_WARPS - 1 - VR_VOTERS;
-constexpr int VR_CQ = 1024;        // entries of the CTA's slow-column ring buffer between voters and deciders
+constexpr int VR_VOTERS = VR_WARPS - 1;
 constexpr int VR_MAX_STAGES = 16;  // tiles in flight (barrier pairs and stage headers); their bytes come from one ring-buffer arena
 constexpr int VR_GROUPS = 3;       // groups of voter warps when the tiles are small
 constexpr int VR_GUARD = 4608;     // never allocated, after the arena: the branch-free read loop may read a VoteRead table or a
@@ -70,34 +66,18 @@ constexpr int VR_OFF_FULL = 0;                                   // uint64[VR_MA
 constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_HDR = 16 * VR_MAX_STAGES;                   // RingStage[VR_MAX_STAGES]
 constexpr int VR_OFF_HCACHE = VR_OFF_HDR + 96 * VR_MAX_STAGES;   // TileHdr2[32]: the producer's next tiles
-constexpr int VR_OFF_CQCTL = VR_OFF_HCACHE + 48 * WARP;          // CqCtl
-constexpr int VR_OFF_CQ = VR_OFF_CQCTL + 16;                     // uint2[VR_CQ]
-constexpr int VR_OFF_ARENA = (VR_OFF_CQ + 8 * VR_CQ + 127) & ~127;
+constexpr int VR_OFF_ARENA = (VR_OFF_HCACHE + 48 * WARP + 127) & ~127;
 // a tile's allocation: [FsTile list][VoteRead table][slab + slack][slow-column list + two prefix arrays], each part rounded to 128 bytes
 static_assert(VR_OFF_HDR % 16 == 0 && VR_OFF_HCACHE % 16 == 0 && VR_OFF_ARENA % 128 == 0, "ring layout");
 GCB_HD uint32_t ring_round128(uint32_t v) { return (v + 127u) & ~127u; }
-
-struct CqCtl {  // the slow-column ring buffer's counters (entry i lives in slot i % VR_CQ; counters only grow)
-    uint32_t wr;           // atomic: entries reserved by voters
-    uint32_t rd;           // atomic: entries grabbed by deciders
-    uint32_t consumed;     // entries copied out of the buffer, committed in order: slot i may be rewritten once i - consumed < VR_CQ
-    uint32_t voters_done;  // atomic: voter warps that have left the kernel
-};
 
 struct RingCtx {  // what deciding a slow column inside the CTA needs besides the stage
     const BatchView *b;
     const ResultView *r;
     const GenomeView *gv;
     const gcb_options *o;
-    const Workspace *ws;
     RollbackList rb;
 };
-
-// One listed slow column, everything read from global memory: the tile it came from crossed this SM microseconds ago, so
-// the payload bytes, the VoteRead entries and the family-side descriptor are L2 hits.
-__device__ __noinline__ void ring_slow_column_global(const RingCtx &x, uint32_t fsid, int col) {
-    decide_column_global(*x.b, *x.r, *x.ws, *x.gv, *x.o, x.rb, fsid, col);
-}
 
 // One slow column of family side f of a staged (deep) tile, decided from shared memory.  (The pointers are derived from the
 // shared-memory symbol inside the function, so that the loads are LDS and not generic loads.)
@@ -112,7 +92,7 @@ __device__ __noinline__ void ring_slow_column(const RingCtx &x, int ft_off, int 
 }
 
 __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o, int32_t implied,
-                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, RollbackList rb,
+                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueue sq, RollbackList rb,
                                                                    int32_t n_tiles, int32_t arena_bytes, const int32_t *max_need) {
     GCB_DYN_SMEM(smem);
     if (batch_is_malformed(ws.error_flag)) return;  // (every thread of the grid sees the same flag: the kernels that raise it have finished)
@@ -126,24 +106,19 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     const int32_t largest = (int32_t)ring_round128((uint32_t)max(*max_need, 128));
     const int n_groups = arena_bytes >= 6 * largest ? VR_GROUPS : 1, wpg = VR_VOTERS / n_groups;
     const int n_stages = VR_MAX_STAGES;
-    CqCtl *cq = (CqCtl *)(smem + VR_OFF_CQCTL);
-    uint2 *cq_ent = (uint2 *)(smem + VR_OFF_CQ);
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
             pipe_init(full + s, 1);
             pipe_init(empty + s, wpg);  // every voter warp of the tile's group arrives once when it leaves the tile
         }
-        cq->wr = cq->rd = cq->consumed = cq->voters_done = 0u;
         pipe_fence_init();
     }
-    for (int i = tid; i < VR_CQ; i += VR_THREADS) cq_ent[i] = make_uint2(0u, 0u);  // (bit 31 of .y says which lap of the buffer wrote the slot)
     __syncthreads();
 
     if (warp == 0) {
         // ---- producer: lane 0 fills the stages, up to n_stages tiles ahead of the voters; the whole warp fetches the
         // headers of this CTA's next 32 tiles at once, so that no tile waits for a header on its way from global memory
         TileHdr2 *hcache = (TileHdr2 *)(smem + VR_OFF_HCACHE);
-        const uint64_t l2_keep = tile_l2_policy_keep();
         int k = 0;
         // ring-buffer arena: the tiles in flight are k_tail .. k-1, their allocations lie between off_of[k_tail] and head (wrapping);
         // slot k % n_stages (barriers, header) once the tile that used it before is released
@@ -218,9 +193,8 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     fill(sh, cur, (int32_t)t, at);
                     shdr[s] = sh;
                     pipe_expect(full + s, slab_bytes + vr_bytes + ft_bytes);
-                    // (the deciders read a few bytes of the slab and of the VoteRead table again, from L2: keep the lines there)
-                    if (slab_bytes > 0) tile_copy_hint(smem + sh.slab_off, b.payload + cur.slab0, slab_bytes, full + s, l2_keep);
-                    tile_copy_hint(smem + sh.vr_off, ws.vote_reads + 2 * (int64_t)cur.p0, vr_bytes, full + s, l2_keep);
+                    if (slab_bytes > 0) tile_copy(smem + sh.slab_off, b.payload + cur.slab0, slab_bytes, full + s);
+                    tile_copy(smem + sh.vr_off, ws.vote_reads + 2 * (int64_t)cur.p0, vr_bytes, full + s);
                     tile_copy(smem + sh.ft_off, fs_tiles + 2 * (int64_t)cur.p0, ft_bytes, full + s);
                     pipe_commit(full + s);
                     k++;
@@ -247,88 +221,10 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     }
 
     RingCtx x;
-    x.b = &b; x.r = &r; x.gv = &gv; x.o = &o; x.ws = &ws; x.rb = rb;
-    if (warp > VR_VOTERS) {
-        // ---- deciders: pool the voters' entries into rounds of 32 slow columns, one thread per column.  Every lane holds at
-        // most one pending entry (family side, lane, mask of columns still to decide); empty lanes refill from the buffer.
-        uint32_t my_fs = 0u, my_y = 0u;
-        bool open = true;  // the buffer may still deliver entries
-        for (;;) {
-            const bool want = (my_y & 0xFFFFu) == 0u;
-            const unsigned wbal = __ballot_sync(FULL, want);
-            if (open && wbal != 0u) {
-                const uint32_t ne = (uint32_t)__popc(wbal);
-                uint32_t g0 = 0u;
-                if (lane == 0) g0 = atomicAdd(&cq->rd, ne);
-                g0 = __shfl_sync(FULL, g0, 0);
-                bool none = false;
-                if (want) {
-                    const uint32_t i = g0 + (uint32_t)__popc(wbal & ((1u << lane) - 1u));
-                    const uint32_t expect = ((i / VR_CQ) & 1u) ^ 1u;
-                    for (;;) {
-                        const unsigned long long e = *(volatile unsigned long long *)&cq_ent[i % VR_CQ];  // (.x low, .y high)
-                        const uint32_t ey = (uint32_t)(e >> 32);
-                        if ((ey >> 31) == expect && (ey & 0xFFFFu) != 0u) {
-                            my_fs = (uint32_t)e;
-                            my_y = ey & 0x7FFFFFFFu;
-                            break;
-                        }
-                        // no voter is left and the entry was never reserved: there is nothing more to come
-                        if (*(volatile uint32_t *)&cq->voters_done == (uint32_t)VR_VOTERS && i >= *(volatile uint32_t *)&cq->wr) {
-                            none = true;
-                            break;
-                        }
-                        pipe_relax(100u);
-                    }
-                }
-                __syncwarp();
-                __threadfence_block();  // (the entries' records were stored before the entries were published)
-                if (lane == 0) {  // the slots are free again: committed in grab order
-                    while (*(volatile uint32_t *)&cq->consumed != g0) pipe_relax(20u);
-                    __threadfence_block();
-                    *(volatile uint32_t *)&cq->consumed = g0 + ne;
-                }
-                if (__any_sync(FULL, none)) open = false;
-                pipe_progress();
-            }
-            const int cnt = __popc(my_y & 0xFFFFu);
-            int incl = cnt;
-            for (int off = 1; off < WARP; off <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, off);
-                if (lane >= off) incl += v;
-            }
-            const int T = __shfl_sync(FULL, incl, WARP - 1);
-            if (T == 0) {
-                if (!open) break;
-                continue;
-            }
-            // column c of the round belongs to the first lane whose inclusive count exceeds c
-            int lo = 0, hi = WARP - 1;
-#pragma unroll
-            for (int step = 0; step < 5; step++) {
-                const int mid = (lo + hi) >> 1;
-                const int v = __shfl_sync(FULL, incl, mid);
-                if (v > lane) hi = mid;
-                else lo = mid + 1;
-            }
-            const uint32_t o_fs = __shfl_sync(FULL, my_fs, lo), o_y = __shfl_sync(FULL, my_y, lo);
-            const int o_excl = __shfl_sync(FULL, incl - cnt, lo);
-            if (lane < T) {
-                uint32_t mask = o_y & 0xFFFFu;
-                for (int q = lane - o_excl; q > 0; q--) mask &= mask - 1u;
-                const int bit = __ffs((int)mask) - 1;  // bit 8 * w + i of the mask = column 8 * w + 7 - i of the lane's sixteen
-                ring_slow_column_global(x, o_fs, VT_CHUNK * (int)((o_y >> 16) & 31u) + (bit & 8) + 7 - (bit & 7));
-            }
-            // the owners drop the columns this round took
-            int take = min(max(WARP - (incl - cnt), 0), cnt);
-            for (; take > 0; take--) my_y &= my_y - 1u | 0xFFFF0000u;
-            __syncwarp();
-        }
-        return;
-    }
-
+    x.b = &b; x.r = &r; x.gv = &gv; x.o = &o; x.rb = rb;
     // ---- voters
     const uint32_t mod4 = 0x01010101u * (uint32_t)(o.moderate_quality & 0xFF);
+    uint32_t pool_r = 0u, pool_re = 0u, pool_w = 0u, pool_we = 0u;  // this warp's reserved records / words of the slow-column queue
     const uint32_t sbase = smem_base(smem);
     // lane geometry and masks are kept across tiles while the tile shape (lanes per family side, usual record length) stays
     int cur_L = 0, cur_l = -1, S = 32, sub = 0, j = 0, col0 = 0;
@@ -537,20 +433,79 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     fin = __shfl_sync(FULL, fin, 0);
                     closer = fin == nb;
                 } else if (bal != 0u) {
-                    // ... or the CTA's ring buffer: the deciders take the entries from there (this warp never waits for them)
-                    const uint32_t ne = (uint32_t)__popc(bal);
-                    uint32_t idx = 0u;
-                    if (lane == 0) {
-                        idx = atomicAdd(&cq->wr, ne);
-                        while ((int32_t)(idx + ne - *(volatile uint32_t *)&cq->consumed) > VR_CQ) pipe_relax(50u);  // (room for the entries)
+                    // ... or a record per slow column in the global queue, written by the lane that found the column: records of
+                    // one size per bundle, from the warp's own pool of reserved queue space
+                    const int cnt = __popc(mask16);
+                    int incl = cnt;
+                    for (int off = 1; off < WARP; off <<= 1) {
+                        const int v = __shfl_up_sync(FULL, incl, off);
+                        if (lane >= off) incl += v;
                     }
-                    idx = __shfl_sync(FULL, idx, 0);
-                    __threadfence_block();  // the record's words (stored above) before the entry that lets a decider patch them
-                    if (mask16 != 0u) {
-                        const uint32_t e = idx + (uint32_t)__popc(bal & ((1u << lane) - 1u));
-                        const uint32_t ex = 2u * (uint32_t)ft.slot + ((ft.flags & FS_SIDE1) ? 1u : 0u);
-                        const uint32_t ey = ((((e / VR_CQ) & 1u) ^ 1u) << 31) | ((uint32_t)j << 16) | mask16;
-                        *(volatile unsigned long long *)&cq_ent[e % VR_CQ] = ((unsigned long long)ey << 32) | ex;  // one 8-byte store
+                    const uint32_t T = (uint32_t)__shfl_sync(FULL, incl, WARP - 1), rw = slow_rec_words(mmax), W = T * rw;
+                    if (pool_r + T > pool_re || pool_w + W > pool_we) {
+                        // a new pool (one 64-bit atomic: records << 32 | words); what is left of the old one stays unused
+                        for (uint32_t i = pool_r + (uint32_t)lane; i < pool_re; i += WARP) sq.index[i] = VQ_INVALID;
+                        const uint32_t need_r = T > VQ_POOL_RECS ? T : VQ_POOL_RECS, need_w = W > VQ_POOL_WORDS ? W : VQ_POOL_WORDS;
+                        unsigned long long base64 = 0ull;
+                        if (lane == 0) base64 = atomicAdd(sq.count, ((unsigned long long)need_r << 32) | need_w);
+                        base64 = __shfl_sync(FULL, base64, 0);
+                        const uint32_t r0 = (uint32_t)(base64 >> 32), w0 = (uint32_t)base64;
+                        if ((unsigned long long)r0 + need_r <= sq.cap_recs && (unsigned long long)w0 + need_w <= sq.cap_words) {
+                            pool_r = r0; pool_re = r0 + need_r;
+                            pool_w = w0; pool_we = w0 + need_w;
+                        } else {  // the queue is full: the reserved index entries are marked unused, the pool stays empty
+                            for (uint32_t i = r0 + (uint32_t)lane; i < r0 + need_r && i < sq.cap_recs; i += WARP) sq.index[i] = VQ_INVALID;
+                            pool_r = pool_re = pool_w = pool_we = 0u;
+                        }
+                    }
+                    if (pool_r + T > pool_re) {
+                        // no queue space: the generic kernel redoes the whole tile from the payload (it runs after
+                        // slow_columns_kernel and vote_rollback_kernel)
+                        if (lane == 0 && atomicExch(&sh->closed, 1) == 0) {
+                            ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~sh->tile;
+                            GCB_COUNT(1, 1);
+                        }
+                    } else {
+                        uint32_t ri = pool_r + (uint32_t)(incl - cnt), mk = mask16;
+                        const uint8_t *cbp = smem + cb;
+                        const VoteRead *ents = s_vr + ft.ent0;
+                        const int64_t out_abs = sh->out_base0 + 4 * (int64_t)ft.out4;
+                        while (mk != 0u) {
+                            const int bit = __ffs((int)mk) - 1;  // bit 8 * w + i of the mask = column 8 * w + 7 - i of the lane's sixteen
+                            mk &= mk - 1u;
+                            const int col = col0 + (bit & 8) + 7 - (bit & 7);
+                            const uint32_t wofs = pool_w + (ri - pool_r) * rw;
+                            uint32_t *rec = sq.words + wofs;
+                            sq.index[ri] = wofs;
+                            slow_write_header(rec, ft, col, out_abs);
+                            if ((ft.flags & FS_UNIFORM) && col < len) {
+                                // the column's place in pair.cpp:121-170 is the same for every read of a uniform family
+                                const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
+                                const int kq = col - (int)tv.ov_own, mp = (int)tv.ov_mate + kq;
+                                const bool inwin = info && kq >= 0 && kq < (int)tv.ov_len;
+                                const bool mvalid = inwin && mp >= 0 && mp < (int)tv.mate_l;
+                                const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
+                                const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
+                                const int mrel = mvalid ? 4 * ((int)tv.mate_off4 - (int)tv.own_off4) : 0, mpi = mvalid ? mp : 0;
+                                const int mqoff = mrel + mpi, msoff = mrel + (mvalid ? GCB_ALIGN4(tv.mate_l) : 0) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
+                                for (int e = 0; e < (int)ft.m; e++) {
+                                    const uint32_t xo = ents[e].own_off4;
+                                    uint32_t ent = 0u;
+                                    if (xo != VR_NO_VOTE) {
+                                        const uint8_t *p = cbp + 4 * (int)xo;
+                                        const uint32_t ql = p[col], base = ((uint32_t)p[soff] >> nsh) & 0xFu;
+                                        const uint32_t mql = mvalid ? p[mqoff] : 0u, mbase = mvalid ? (((uint32_t)p[msoff] >> mnsh) & 0xFu) : 0u;
+                                        ent = ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
+                                    }
+                                    rec[SR_HDR_WORDS + e] = ent;
+                                }
+                            } else {
+                                for (int e = 0; e < (int)ft.m; e++) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
+                            }
+                            ri++;
+                        }
+                        pool_r += T;
+                        pool_w += W;
                     }
                 }
                 if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
@@ -618,11 +573,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         __syncwarp();
         if (lane == 0) pipe_arrive(empty + s);
     }
-    __syncwarp();
-    if (lane == 0) {
-        __threadfence_block();
-        atomicAdd(&cq->voters_done, 1u);
-    }
+    for (uint32_t i = pool_r + (uint32_t)lane; i < pool_re; i += WARP) sq.index[i] = VQ_INVALID;  // what is left of the warp's pool
 #undef GCB_LDS32
 }
 

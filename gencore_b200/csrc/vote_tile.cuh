@@ -68,17 +68,6 @@ __device__ __forceinline__ void tile_copy(void *dst, const void *src, uint32_t b
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// the same copy with an L2 eviction priority (createpolicy): `keep` = evict_last — the bytes are read again from L2 soon
-__device__ __forceinline__ uint64_t tile_l2_policy_keep() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void tile_copy_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-                 : "memory");
-}
 __device__ __forceinline__ void pipe_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -106,8 +95,6 @@ __device__ __forceinline__ void pipe_relax(uint32_t ns) { __nanosleep(ns); }  //
 #else
 inline void tile_expect(uint64_t *, uint32_t) {}
 inline void tile_copy(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
-inline uint64_t tile_l2_policy_keep() { return 0; }
-inline void tile_copy_hint(void *dst, const void *src, uint32_t bytes, uint64_t *, uint64_t) { memcpy(dst, src, bytes); }
 // bits 0..15 completed phases, 16..31 arrivals of the current phase, 32..47 arrivals a phase needs
 inline void pipe_init(uint64_t *bar, int count) { *bar = (uint64_t)count << 32; }
 inline void pipe_fence_init() {}

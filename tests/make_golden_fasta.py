@@ -1,4 +1,4 @@
-"""Writes tests/golden/fasta.npz: what the UNMODIFIED reference's FastaReader (oracle/_ref, built from /root/reference)
+"""Writes tests/golden_fasta/fasta.npz: what the UNMODIFIED reference's FastaReader (oracle/_ref, built from /root/reference)
 makes of every text of tests/fasta_cases.py.  Run in the build container:  python tests/make_golden_fasta.py"""
 import os
 import sys
@@ -19,5 +19,5 @@ for name, text in fasta_cases().items():
     out[name + "/sizes"] = sizes
     out[name + "/offs"] = offs
     out[name + "/packed"] = packed[:int(offs[-1] + (sizes[-1] + 1) // 2) if len(sizes) else 0]
-np.savez_compressed(os.path.join(HERE, "golden", "fasta.npz"), **out)
+np.savez_compressed(os.path.join(HERE, "golden_fasta", "fasta.npz"), **out)
 print("wrote", len(fasta_cases()), "cases")

@@ -1,5 +1,5 @@
 """gcb_pack_fasta (k_fasta_pack.cuh) against the reference's own FastaReader: golden vectors generated from the unmodified
-reference (tests/golden/fasta.npz, tests/make_golden_fasta.py), a literal restatement of readNext (fasta_cases.restate_fasta),
+reference (tests/golden_fasta/fasta.npz, tests/make_golden_fasta.py), a literal restatement of readNext (fasta_cases.restate_fasta),
 the kernels under the SIMT interpreter on the CPU box and the CUDA library on the B200."""
 import os
 import sys
@@ -12,7 +12,7 @@ from fasta_cases import MALFORMED, fasta_cases, restate_fasta
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "simt_check"))
 CASES = fasta_cases()
-GOLDEN = np.load(os.path.join(HERE, "golden", "fasta.npz"), allow_pickle=False)
+GOLDEN = np.load(os.path.join(HERE, "golden_fasta", "fasta.npz"), allow_pickle=False)
 
 
 def golden(name):
@@ -32,7 +32,7 @@ def assert_genome(genome, ids, sizes, packed, what):
 
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_golden_text_is_current(name):
-    assert bytes(GOLDEN[name + "/text"]) == CASES[name], "tests/golden/fasta.npz is stale: run tests/make_golden_fasta.py"
+    assert bytes(GOLDEN[name + "/text"]) == CASES[name], "tests/golden_fasta/fasta.npz is stale: run tests/make_golden_fasta.py"
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
