@@ -6,96 +6,12 @@
 //                     side's diff / mismatchInc (atomics on the result row, which select_template_kernel wrote with zeros).
 //   decide_column()   histogram straight from the family side's VoteRead entries and its cluster's slab (score per read:
 //                     pair.cpp:121-170; three-bin register histogram: group.cpp:376-393).  The ring kernel's voter warps
-//                     call it for tiles of deep families, from the staged slab in shared memory.
-//   slow_columns_kernel   everything else.  The ring kernel keeps a tile in shared memory only as long as its warps vote;
-//                     what a slow column needs of the tile — per read its quality, its base nibble, its mate's quality and
-//                     base nibble and where pair.cpp:121-170 puts the column: 4 bytes per read behind a 32-byte
-//                     self-contained header — is written by the lane that found the column into a global queue (one
-//                     64-bit atomic per ~10 bundles reserves a warp's records and words in one counter), and this kernel
-//                     takes one record per thread at full occupancy: the deciding is a chain of dependent small loads that
-//                     wants many resident warps, which the one-CTA-per-SM ring cannot give it.  (Measured alternatives,
-//                     profiles/r03_notes.md: deciding inside the ring — from the staged slab, or from the L2 by dedicated
-//                     warps —, extracting per tile instead of per bundle, re-reading the payload from a second kernel.)
+//                     call it, 32 columns of a closed tile at a time, from the slab staged in shared memory.
 #pragma once
 
 #include "vote_tile.cuh"
 
 namespace gcb {
-
-constexpr uint32_t VQ_INVALID = 0xFFFFFFFFu;   // index entry of a reservation that was not used
-constexpr int VQ_SLOW_THREADS = 128;
-constexpr int VQ_SLOW_CTAS = 148 * 8;          // slow_columns_kernel strides over the records
-constexpr uint32_t VQ_POOL_RECS = 64, VQ_POOL_WORDS = 64 * 20;  // queue space a voter warp reserves at a time
-
-struct SlowQueue {
-    unsigned long long *count;   // [1] records << 32 | words reserved so far (may run past the capacity)
-    uint32_t *words;             // [cap_words] records (see SR_HDR_WORDS)
-    uint32_t *index;             // [cap_recs] word offset of every record, VQ_INVALID = none
-    uint32_t cap_words, cap_recs;
-};
-
-// record: SR_HDR_WORDS header words, then n entries (one per read of the family side), padded to a multiple of 4 words.
-// The header is self-contained (slow_columns_kernel needs no table lookup):
-//   [0] 2 * slot + side   [1] col | n << 16   [2] tmpl_k | flags << 16   [3] l_out
-//   [4..5] absolute offset of the consensus record in out_payload   [6..7] ref_nib0
-constexpr int SR_HDR_WORDS = 8;
-constexpr uint32_t SR_UNVOTED = 0x100u;    // (next to the FS_* flags) column beyond the voted length: the record keeps the template's (rewritten) quality
-// entry: quality | mate quality << 8 | base << 16 | mate base << 20 | state << 24 | SE_VOTES
-constexpr uint32_t SE_VOTES = 1u << 26;
-constexpr uint32_t SE_NO_INFO = 0u, SE_PLAIN = 1u, SE_MATE = 2u, SE_NO_MATE_BASE = 3u;
-
-GCB_DEV uint32_t slow_rec_words(int m) { return (uint32_t)SR_HDR_WORDS + (((uint32_t)m + 3u) & ~3u); }
-GCB_DEV void slow_write_header(uint32_t *rec, const FsTile &ft, int col, int64_t out_abs) {
-    const uint32_t side = (ft.flags & FS_SIDE1) ? 1u : 0u;
-    const uint32_t fl = (uint32_t)ft.flags | (col >= (int)ft.len ? SR_UNVOTED : 0u);
-    uint4 a, c;
-    a.x = 2u * (uint32_t)ft.slot + side;
-    a.y = (uint32_t)col | ((uint32_t)ft.m << 16);
-    a.z = (uint32_t)ft.tmpl_k | (fl << 16);
-    a.w = (uint32_t)ft.l_out;
-    c.x = (uint32_t)(uint64_t)out_abs; c.y = (uint32_t)((uint64_t)out_abs >> 32);
-    c.z = (uint32_t)(uint64_t)ft.ref_nib0; c.w = (uint32_t)((uint64_t)ft.ref_nib0 >> 32);
-    ((uint4 *)rec)[0] = a;
-    ((uint4 *)rec)[1] = c;
-}
-
-// what pair.cpp:88-172 needs of read `v` at template column `col`, as a queue entry (0 = the read has no base there)
-GCB_DEV uint32_t slow_entry(const uint8_t *cb, const VoteRead &v, int col) {
-    const int rp = col + v.shift;
-    if (v.own_off4 == VR_NO_VOTE || rp < 0 || rp >= v.own_l) return 0u;
-    const uint8_t *q = cb + 4 * (int)v.own_off4;
-    const uint32_t ql = q[rp];
-    const uint32_t base = (uint32_t)base_at(q + GCB_ALIGN4(v.own_l), rp);
-    const bool info = v.ov_len != VR_NO_OVERLAP_INFO;
-    const int k = rp - v.ov_own, mp = v.ov_mate + k;
-    const bool inwin = info && k >= 0 && k < v.ov_len;
-    const bool mvalid = inwin && mp >= 0 && mp < v.mate_l;
-    uint32_t mql = 0u, mbase = 0u;
-    if (mvalid) {
-        const uint8_t *mq = cb + 4 * (int)v.mate_off4;
-        mql = mq[mp];
-        mbase = (uint32_t)base_at(mq + GCB_ALIGN4(v.mate_l), mp);
-    }
-    const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
-    return ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
-}
-
-// base, rewritten quality and score of a queue entry: the same function of the same bytes as fetch_vote
-GCB_DEV bool slow_decode(const ScoreTab &t, uint32_t ent, int side, int &base, int &qual, int &score) {
-    if (!(ent & SE_VOTES)) return false;
-    const int ql = (int)(ent & 0xFFu), mql = (int)((ent >> 8) & 0xFFu);
-    base = (int)((ent >> 16) & 0xFu);
-    const int mbase = (int)((ent >> 20) & 0xFu);
-    const uint32_t st = (ent >> 24) & 3u;
-    const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
-    const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
-    const int s_match = sc8(t.q2s((ql + mql) / 2) + 4);                        // pair.cpp:147-152
-    const int s_mis = mine ? sc8(t.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;  // pair.cpp:153-169
-    const bool mism = st == SE_MATE && base != mbase;
-    score = st == SE_MATE ? (mism ? s_mis : s_match) : st == SE_PLAIN ? t.q2s(ql) : t.sm;
-    qual = mism ? max(0, ql - mql) : ql;
-    return true;
-}
 
 // what a column's decision needs to know of its family side
 struct SlowSide {
@@ -303,59 +219,6 @@ GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const Genome
             if (fetch_ent(cb, ents[e], col, side, o, base, qual, score)) f(base, qual, score, e == fs.tmpl_k);
         }
     });
-}
-
-// One queued column (group.cpp:376-525 from its record)
-GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeView &gv, const gcb_options &o, const ScoreTab &tab,
-                         const RollbackList &rb, const uint32_t *rec) {
-    const uint4 ha = ((const uint4 *)rec)[0], hc = ((const uint4 *)rec)[1];
-    const uint32_t fsid = ha.x, w1 = ha.y, w2 = ha.z;
-    const int col = (int)(w1 & 0xFFFFu), n = (int)(w1 >> 16);
-    const uint32_t flags = w2 >> 16;
-    const uint32_t *ents = rec + SR_HDR_WORDS;
-    SlowSide fs;
-    fs.m = n; fs.l_out = (int)ha.w; fs.len = (int)ha.w; fs.tmpl_k = (int)(w2 & 0xFFFFu); fs.side = (int)(fsid & 1u); fs.flags = (int)(flags & 0xFFu);
-    fs.slot = (int)(fsid >> 1);
-    fs.ref_nib0 = (int64_t)(((uint64_t)hc.w << 32) | hc.z);
-    const int side = fs.side;
-    uint8_t *out = r.out_payload + (int64_t)(((uint64_t)hc.y << 32) | hc.x);
-    GCB_COUNT(3, 1);
-    if (flags & SR_UNVOTED) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
-        int obase = 0, oqual = 0, sc;
-        slow_decode(tab, ents[fs.tmpl_k], side, obase, oqual, sc);
-        out[col] = (uint8_t)oqual;
-        return;
-    }
-    Bins3 bins;
-    bins.init();
-    for (int e = 0; e < n; e += 4) {  // (records are padded to whole 16-byte groups of entries)
-        const uint4 v = *(const uint4 *)(ents + e);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int base, qual, score;
-            if (e + k < n && slow_decode(tab, w[k], side, base, qual, score)) bins.add(base, qual, score);
-        }
-    }
-    // the record's base before the vote: the template's own (pair.cpp rewrites qualities, never bases)
-    finish_column(b, r, gv, o, rb, fs, out, col, bins, (int)((ents[fs.tmpl_k] >> 16) & 0xFu), [&](auto &&f) {
-        for (int e = 0; e < n; e++) {
-            int base, qual, score;
-            if (slow_decode(tab, ents[e], side, base, qual, score)) f(base, qual, score, e == fs.tmpl_k);
-        }
-    });
-}
-
-__global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o,
-                                                                       SlowQueue sq, RollbackList rb) {
-    if (batch_is_malformed(ws.error_flag)) return;
-    const uint32_t reserved = (uint32_t)(*sq.count >> 32), total = reserved < sq.cap_recs ? reserved : sq.cap_recs;
-    const ScoreTab tab(o);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const uint32_t off = sq.index[i];
-        if (off == VQ_INVALID) continue;
-        slow_record(b, r, gv, o, tab, rb, sq.words + off);
-    }
 }
 
 }  // namespace gcb

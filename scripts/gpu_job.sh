@@ -17,6 +17,3 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 4
   python bench.py --steps 2 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/launches_$tag.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:vote_ring -s 3 -c 1 -o gpurun_out/prof_ring_$tag \
   python bench.py --steps 1 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/ncu_ring_$tag.log 2>&1
-ls -la gpurun_out | tail -8
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:slow_columns -s 3 -c 1 -o gpurun_out/prof_slow_$tag \
-  python bench.py --steps 1 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/ncu_slow_$tag.log 2>&1
