@@ -335,6 +335,25 @@ struct Bins3 {
     }
 };
 
+// the same for up to two distinct codes (a third raises `overflow`): what most slow columns need
+struct Bins2 {
+    int bA, bB, cA, cB, sA, sB, qA, qB, xA, xB, total;
+    bool overflow;
+    GCB_DEV void init() {
+        bA = bB = -1;
+        cA = cB = sA = sB = qA = qB = xA = xB = total = 0;
+        overflow = false;
+    }
+    GCB_DEV void add(int base, int qual, int score) {
+        total += score;
+        const bool uA = bA < 0 || bA == base;
+        const bool uB = !uA && (bB < 0 || bB == base);
+        overflow = overflow || !(uA || uB);
+        bA = uA ? base : bA; cA += uA ? 1 : 0; sA += uA ? score : 0; qA += uA ? qual : 0; xA = max(xA, uA ? qual : 0);
+        bB = uB ? base : bB; cB += uB ? 1 : 0; sB += uB ? score : 0; qB += uB ? qual : 0; xB = max(xB, uB ? qual : 0);
+    }
+};
+
 // what a lane needs to know about its sixteen columns of a record of l_out bases of which `len` are voted
 struct ChunkMasks {
     uint32_t vn0, vn1;   // voted columns, nibble masks of columns 0-7 and 8-15
