@@ -2,7 +2,7 @@
 // of one batch.  Host code only sizes buffers, moves bytes and launches; all arithmetic of the
 // reference's hot path lives in the kernels:
 //   umi_group_kernel -> select_template_kernel -> scan_local/scan_blocks -> tile_prep2_kernel -> vote_ring_kernel
-//   -> vote_rollback_kernel -> score_vote_kernel (the tiles that do not fit the ring's arena) -> duplex_kernel
+//   -> slow_columns_kernel -> vote_rollback_kernel -> score_vote_kernel (the tiles that do not fit the ring's arena) -> duplex_kernel
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -44,6 +44,9 @@ struct gcb_ctx {
     DevBuf w_vr, w_fs, w_gtiles, w_gcount;
     DevBuf w_fstiles, w_thdr2;           // the tiles' compact family-side lists and their headers
     DevBuf w_rb_list, w_rb_count;        // rollback candidates (per chunk: one counter)
+    DevBuf w_sq_count, w_sq_words, w_sq_index;  // slow-column queue (per chunk: one counter)
+    int64_t slow_queue_bytes = 0;        // 0 = sized from the payload
+    uint32_t sq_cap_words = 0, sq_cap_recs = 0;
     int ring_window_shift = 0;           // 0 = chosen by plan_tiles; 14 / 15 = forced (tuning)
     int group_lanes = 0;                 // lanes per cluster in umi_group / select_template (0 = by mean cluster size)
     int force_generic = 0;               // tests: every tile goes to the generic kernel
@@ -172,6 +175,22 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_thdr2, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * sizeof(TileHdr2));
     GCB_RES(w_rb_list, 2 * n_pairs * 4);
     GCB_RES(w_rb_count, 4 * GCB_MAX_CHUNKS);
+    {   // slow-column queue: a clean shallow library queues about 0.08 bytes per payload byte, a noisy one of depth 30 (1 % errors:
+        // a third of its columns are slow) about 1.5, a vote whose every column is slow (options outside fast_path_implied) about
+        // 4; tiles whose columns do not fit are redone by the generic kernel
+        int64_t qbytes = ctx->slow_queue_bytes > 0 ? ctx->slow_queue_bytes
+                         : fast_path_implied(ctx->opt) ? 2 * payload_bytes + (16ll << 20) : 5 * payload_bytes + (16ll << 20);
+        int64_t cap_words = qbytes / 4;
+        if (cap_words > 0xFFFFFFF0ll) cap_words = 0xFFFFFFF0ll;
+        cap_words &= ~3ll;
+        if (cap_words < 64) cap_words = 64;
+        const int64_t cap_recs = cap_words / 12;  // the smallest record is 12 words
+        GCB_RES(w_sq_count, 8 * GCB_MAX_CHUNKS);
+        GCB_RES(w_sq_words, 4 * cap_words);
+        GCB_RES(w_sq_index, 4 * cap_recs);
+        ctx->sq_cap_words = (uint32_t)cap_words;
+        ctx->sq_cap_recs = (uint32_t)cap_recs;
+    }
 #undef GCB_RES
     ws.members = (int32_t *)ctx->w_members.p;
     ws.group_off = (int32_t *)ctx->w_group_off.p;
@@ -281,6 +300,13 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         rb.list = (int32_t *)ctx->w_rb_list.p + 2 * (size_t)v.p0;
         rb.count = (int32_t *)ctx->w_rb_count.p + v.index;
         rb.cap = 2 * (v.p1 - v.p0);
+        // ... and its own queue counter (the queue itself is shared: the chunks' votes never overlap)
+        SlowQueue sq;
+        sq.count = (unsigned long long *)ctx->w_sq_count.p + v.index;
+        sq.words = (uint32_t *)ctx->w_sq_words.p;
+        sq.index = (uint32_t *)ctx->w_sq_index.p;
+        sq.cap_words = ctx->sq_cap_words;
+        sq.cap_recs = ctx->sq_cap_recs;
         if (run_prep) {
             GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
             GCB_LAUNCH(tile_prep2_kernel, dim3((unsigned)((n_tiles + VS_PREP_THREADS / WARP - 1) / (VS_PREP_THREADS / WARP))), dim3(VS_PREP_THREADS), 0,
@@ -289,13 +315,16 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         }
         if (run_fast && plan.ring && !ctx->force_generic) {
             GCB_CUDA(ctx, cudaMemsetAsync(rb.count, 0, 4, stream));
+            GCB_CUDA(ctx, cudaMemsetAsync(sq.count, 0, 8, stream));
             const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
             GCB_LAUNCH(vote_ring_kernel, dim3(ring_grid), dim3(VR_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
-                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, rb, (int32_t)n_tiles, plan.arena);
+                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.arena);
             ctx->launches++;
         }
         if (run_rest) {
             if (plan.ring && !ctx->force_generic) {
+                GCB_LAUNCH(slow_columns_kernel, dim3(VQ_SLOW_CTAS), dim3(VQ_SLOW_THREADS), 0, stream, b, r, ws, ctx->genome, ctx->opt, sq, rb);
+                ctx->launches++;
                 GCB_LAUNCH(vote_rollback_kernel, dim3(VQ_FINAL_CTAS), dim3(VQ_FINAL_THREADS), 0, stream, b, r, ws, ctx->opt, rb, v.p0, v.p1);
                 ctx->launches++;
             }
@@ -384,7 +413,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
     DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
-                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
+                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->w_sq_count, &ctx->w_sq_words, &ctx->w_sq_index, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
                      &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status, &ctx->f_text, &ctx->f_anchor, &ctx->f_cnt, &ctx->f_hpos, &ctx->f_hbase,
                      &ctx->f_flag, &ctx->f_coff, &ctx->f_out};
@@ -757,6 +786,12 @@ int gcb_set_debug(gcb_ctx *ctx, int key, int value) {
     else if (key == 3) ctx->group_lanes = value;                                      // tuning only: same results
     else if (key == 5) ctx->force_generic = value != 0;                               // tests: the generic kernel votes every tile
     else return GCB_ERR_ARG;
+    return GCB_OK;
+}
+
+int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes) {
+    if (!ctx || bytes < 0) return GCB_ERR_ARG;
+    ctx->slow_queue_bytes = bytes;
     return GCB_OK;
 }
 

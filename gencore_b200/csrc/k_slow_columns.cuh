@@ -4,14 +4,132 @@
 //   finish_column()   the decision once the column's histogram is known: top-2 selection (group.cpp:395-417), the rules
 //                     and the reference arbitration (group.cpp:419-525); patches the consensus record and adds to the family
 //                     side's diff / mismatchInc (atomics on the result row, which select_template_kernel wrote with zeros).
-//   decide_column()   histogram straight from the family side's VoteRead entries and its cluster's slab (score per read:
-//                     pair.cpp:121-170; three-bin register histogram: group.cpp:376-393).  The ring kernel's voter warps
-//                     call it, 32 columns of a closed tile at a time, from the slab staged in shared memory.
+//   slow_columns_kernel   The ring kernel keeps a tile in shared memory only as long as it must; what a slow column needs of
+//                     the tile — per read its quality, its base nibble, its mate's quality and base nibble and where
+//                     pair.cpp:121-170 puts the column: 4 bytes per read behind a 32-byte self-contained header — is
+//                     extracted into a global queue by the ring kernel's warps, 32 columns of a closed tile at a time, one
+//                     thread per column (slow_extract_column), and this kernel takes one record per thread at full
+//                     occupancy: deciding is a chain of dependent small loads and a page of code that wants many resident
+//                     warps and its own instruction cache, which the one-CTA-per-SM ring cannot give it.  (Measured
+//                     alternatives, profiles/r03_notes.md: deciding inside the ring from the staged slab — by the warp that
+//                     found the column, by all warps of a closed tile, by whoever is free —, per-lane and per-bundle
+//                     extraction, re-reading the payload from the second kernel.)
 #pragma once
 
 #include "vote_tile.cuh"
 
 namespace gcb {
+
+constexpr uint32_t VQ_INVALID = 0xFFFFFFFFu;   // index entry of a reservation that was not used
+constexpr int VQ_SLOW_THREADS = 128;
+constexpr int VQ_SLOW_CTAS = 148 * 8;          // slow_columns_kernel strides over the records
+
+struct SlowQueue {
+    unsigned long long *count;   // [1] records << 32 | words reserved so far (may run past the capacity)
+    uint32_t *words;             // [cap_words] records (see SR_HDR_WORDS)
+    uint32_t *index;             // [cap_recs] word offset of every record, VQ_INVALID = none
+    uint32_t cap_words, cap_recs;
+};
+
+// record: SR_HDR_WORDS header words, then n entries (one per read of the family side), padded to a multiple of 4 words.
+// The header is self-contained (slow_columns_kernel needs no table lookup):
+//   [0] 2 * slot + side   [1] col | n << 16   [2] tmpl_k | flags << 16   [3] l_out
+//   [4..5] absolute offset of the consensus record in out_payload   [6..7] ref_nib0
+constexpr int SR_HDR_WORDS = 8;
+constexpr uint32_t SR_UNVOTED = 0x100u;    // (next to the FS_* flags) column beyond the voted length: the record keeps the template's (rewritten) quality
+// entry: quality | mate quality << 8 | base << 16 | mate base << 20 | state << 24 | SE_VOTES
+constexpr uint32_t SE_VOTES = 1u << 26;
+constexpr uint32_t SE_NO_INFO = 0u, SE_PLAIN = 1u, SE_MATE = 2u, SE_NO_MATE_BASE = 3u;
+
+GCB_DEV uint32_t slow_rec_words(int m) { return (uint32_t)SR_HDR_WORDS + (((uint32_t)m + 3u) & ~3u); }
+GCB_DEV void slow_write_header(uint32_t *rec, const FsTile &ft, int col, int64_t out_abs) {
+    const uint32_t side = (ft.flags & FS_SIDE1) ? 1u : 0u;
+    const uint32_t fl = (uint32_t)ft.flags | (col >= (int)ft.len ? SR_UNVOTED : 0u);
+    uint4 a, c;
+    a.x = 2u * (uint32_t)ft.slot + side;
+    a.y = (uint32_t)col | ((uint32_t)ft.m << 16);
+    a.z = (uint32_t)ft.tmpl_k | (fl << 16);
+    a.w = (uint32_t)ft.l_out;
+    c.x = (uint32_t)(uint64_t)out_abs; c.y = (uint32_t)((uint64_t)out_abs >> 32);
+    c.z = (uint32_t)(uint64_t)ft.ref_nib0; c.w = (uint32_t)((uint64_t)ft.ref_nib0 >> 32);
+    ((uint4 *)rec)[0] = a;
+    ((uint4 *)rec)[1] = c;
+}
+
+// what pair.cpp:88-172 needs of read `v` at template column `col`, as a queue entry (0 = the read has no base there)
+GCB_DEV uint32_t slow_entry(const uint8_t *cb, const VoteRead &v, int col) {
+    const int rp = col + v.shift;
+    if (v.own_off4 == VR_NO_VOTE || rp < 0 || rp >= v.own_l) return 0u;
+    const uint8_t *q = cb + 4 * (int)v.own_off4;
+    const uint32_t ql = q[rp];
+    const uint32_t base = (uint32_t)base_at(q + GCB_ALIGN4(v.own_l), rp);
+    const bool info = v.ov_len != VR_NO_OVERLAP_INFO;
+    const int k = rp - v.ov_own, mp = v.ov_mate + k;
+    const bool inwin = info && k >= 0 && k < v.ov_len;
+    const bool mvalid = inwin && mp >= 0 && mp < v.mate_l;
+    uint32_t mql = 0u, mbase = 0u;
+    if (mvalid) {
+        const uint8_t *mq = cb + 4 * (int)v.mate_off4;
+        mql = mq[mp];
+        mbase = (uint32_t)base_at(mq + GCB_ALIGN4(v.mate_l), mp);
+    }
+    const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
+    return ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
+}
+
+// One slow column of family side `ft` of a staged tile as a queue record: the header, then one entry per read of the family
+// side.  `cb`: the cluster's slab, `ents`: the family side's VoteRead entries (both in shared memory).
+GCB_DEV void slow_extract_column(uint32_t *rec, const FsTile &ft, const uint8_t *cb, const VoteRead *ents, int64_t out_abs, int col) {
+    slow_write_header(rec, ft, col, out_abs);
+    const int m = ft.m;
+    if ((ft.flags & FS_UNIFORM) && col < (int)ft.len) {
+        // the column's place in pair.cpp:121-170 is the same for every read of a uniform family
+        const VoteRead tv = ents[ft.tmpl_k];
+        const int qbytes = GCB_ALIGN4((int)ft.l_out);
+        const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
+        const int kq = col - (int)tv.ov_own, mp = (int)tv.ov_mate + kq;
+        const bool inwin = info && kq >= 0 && kq < (int)tv.ov_len;
+        const bool mvalid = inwin && mp >= 0 && mp < (int)tv.mate_l;
+        const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
+        const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
+        const int mpi = mvalid ? mp : 0;
+        const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
+        const uint32_t tag = (st << 24) | SE_VOTES;
+        for (int e = 0; e < m; e++) {
+            const uint32_t w = *(const uint32_t *)(ents + e);  // own_off4 | mate_off4 << 16
+            uint32_t ent = 0u;
+            if ((w & 0xFFFFu) != VR_NO_VOTE) {
+                const uint8_t *p = cb + 4 * (int)(w & 0xFFFFu);
+                ent = (uint32_t)p[col] | ((((uint32_t)p[soff] >> nsh) & 0xFu) << 16) | tag;
+                if (mvalid) {
+                    const uint8_t *q = cb + 4 * (int)(w >> 16);
+                    ent |= ((uint32_t)q[mpi] << 8) | ((((uint32_t)q[msoff] >> mnsh) & 0xFu) << 20);
+                }
+            }
+            rec[SR_HDR_WORDS + e] = ent;
+        }
+    } else {
+        for (int e = 0; e < m; e++) rec[SR_HDR_WORDS + e] = slow_entry(cb, ents[e], col);
+    }
+}
+
+// base, rewritten quality and score of a queue entry: the same function of the same bytes as fetch_vote
+GCB_DEV bool slow_decode(const ScoreTab &t, uint32_t ent, int side, int &base, int &qual, int &score) {
+    if (!(ent & SE_VOTES)) return false;
+    const int ql = (int)(ent & 0xFFu), mql = (int)((ent >> 8) & 0xFFu);
+    base = (int)((ent >> 16) & 0xFu);
+    const int mbase = (int)((ent >> 20) & 0xFu);
+    const uint32_t st = (ent >> 24) & 3u;
+    // pair.cpp:121-170 with one qual2score: of the read's quality outside the overlap, of the mean quality when the mates agree
+    // (+4), of the difference when they do not (-3 for the better read — the left one on a tie —, nothing for the other, whose
+    // quality is rewritten)
+    const bool mate = st == SE_MATE, match = base == mbase, ge = ql >= mql;
+    const bool mine = side == 0 ? ge : (mql < ql);
+    const int sc = t.q2s(!mate ? ql : match ? (ql + mql) >> 1 : ge ? ql - mql : mql - ql);
+    score = mate ? (match ? sc8(sc + 4) : mine ? sc8(sc - 3) : 0) : st == SE_PLAIN ? sc : t.sm;
+    qual = (mate && !match) ? max(0, ql - mql) : ql;
+    return true;
+}
 
 // what a column's decision needs to know of its family side
 struct SlowSide {
@@ -142,96 +260,70 @@ GCB_DEV void finish_column(const BatchView &b, const ResultView &r, const Genome
     out[col] = (uint8_t)new_qual;
 }
 
-// One column of a family side from its VoteRead entries `ents` and its cluster's slab `cb` (shared or global memory).
-GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const GenomeView &gv, const gcb_options &o, const RollbackList &rb,
-                           const SlowSide &fs, const uint8_t *cb, const VoteRead *ents, uint8_t *out, int col) {
-    const ScoreTab tab(o);
-    const VoteRead tv = ents[fs.tmpl_k];
+// One queued column (group.cpp:376-525 from its record)
+GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeView &gv, const gcb_options &o, const ScoreTab &tab,
+                         const RollbackList &rb, const uint32_t *rec) {
+    const uint4 ha = ((const uint4 *)rec)[0], hc = ((const uint4 *)rec)[1];
+    const uint32_t fsid = ha.x, w1 = ha.y, w2 = ha.z;
+    const int col = (int)(w1 & 0xFFFFu), n = (int)(w1 >> 16);
+    const uint32_t flags = w2 >> 16;
+    const uint32_t *ents = rec + SR_HDR_WORDS;
+    SlowSide fs;
+    fs.m = n; fs.l_out = (int)ha.w; fs.len = (int)ha.w; fs.tmpl_k = (int)(w2 & 0xFFFFu); fs.side = (int)(fsid & 1u); fs.flags = (int)(flags & 0xFFu);
+    fs.slot = (int)(fsid >> 1);
+    fs.ref_nib0 = (int64_t)(((uint64_t)hc.w << 32) | hc.z);
     const int side = fs.side;
-    const int qbytes = GCB_ALIGN4(fs.l_out);
+    uint8_t *out = r.out_payload + (int64_t)(((uint64_t)hc.y << 32) | hc.x);
     GCB_COUNT(3, 1);
-    if (col >= fs.len) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
+    if (flags & SR_UNVOTED) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
         int obase = 0, oqual = 0, sc;
-        fetch_ent(cb, tv, col, side, o, obase, oqual, sc);
+        slow_decode(tab, ents[fs.tmpl_k], side, obase, oqual, sc);
         out[col] = (uint8_t)oqual;
         return;
     }
+    // most slow columns show two codes: a two-bin histogram first, the three-bin one when a third code turns up
     Bins3 bins;
     bins.init();
-    const int m = fs.m;
-    if (fs.flags & FS_UNIFORM) {
-        const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
-        const int k = col - (int)tv.ov_own, mp = (int)tv.ov_mate + k;
-        const bool inwin = info && k >= 0 && k < (int)tv.ov_len;
-        const bool mvalid = inwin && mp >= 0 && mp < (int)tv.mate_l;
-        const bool plain = info && !inwin;  // pair.cpp:121-131: outside the overlap the score follows the quality
-        const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
-        const int mpi = mvalid ? mp : 0;
-        const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
-        // eight reads at a time, in two waves of independent loads (where their records lie, then their bytes)
-        auto walk = [&](auto &acc) {
-            for (int e0 = 0; e0 < m; e0 += 8) {
-                uint32_t w[8], x[8];
+    auto walk = [&](auto &acc) {
+        for (int e = 0; e < n; e += 4) {  // (records are padded to whole 16-byte groups of entries)
+            const uint4 v = *(const uint4 *)(ents + e);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int u = 0; u < 8; u++) w[u] = e0 + u < m ? *(const uint32_t *)(ents + e0 + u) : (uint32_t)VR_NO_VOTE;  // own_off4 | mate_off4 << 16
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    x[u] = 0u;
-                    if ((w[u] & 0xFFFFu) != VR_NO_VOTE) {
-                        const uint8_t *rec = cb + 4 * (int)(w[u] & 0xFFFFu);
-                        x[u] = (uint32_t)rec[col] | ((uint32_t)rec[soff] << 8);
-                        if (mvalid) {
-                            const uint8_t *mrec = cb + 4 * (int)(w[u] >> 16);
-                            x[u] |= ((uint32_t)mrec[mpi] << 16) | ((uint32_t)mrec[msoff] << 24);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    if ((w[u] & 0xFFFFu) == VR_NO_VOTE) continue;
-                    int ql = (int)(x[u] & 0xFFu);
-                    const int base = (int)((x[u] >> (8 + nsh)) & 0xFu);
-                    int score;
-                    if (mvalid) {
-                        // pair.cpp:147-169 with one qual2score: of the mean quality when the mates agree (+4), of the difference
-                        // when they do not (-3 for the better read, nothing for the other, whose quality is rewritten)
-                        const int mql = (int)((x[u] >> 16) & 0xFFu);
-                        const int mbase = (int)((x[u] >> (24 + mnsh)) & 0xFu);
-                        const bool match = base == mbase, ge = ql >= mql;
-                        const bool mine = side == 0 ? ge : (mql < ql);  // left read wins ties
-                        const int sc = tab.q2s(match ? (ql + mql) >> 1 : ge ? ql - mql : mql - ql);
-                        score = match ? sc8(sc + 4) : mine ? sc8(sc - 3) : 0;
-                        ql = match ? ql : max(0, ql - mql);
-                    } else {
-                        score = plain ? tab.q2s(ql) : tab.sm;
-                    }
-                    acc.add(base, ql, score);
-                }
+            for (int k = 0; k < 4; k++) {
+                int base, qual, score;
+                if (e + k < n && slow_decode(tab, w[k], side, base, qual, score)) acc.add(base, qual, score);
             }
-        };
-        // most slow columns show two codes: a two-bin histogram first, the three-bin one when a third code turns up
-        Bins2 two;
-        two.init();
-        walk(two);
-        if (!two.overflow) {
-            bins.b0 = two.bA; bins.c0 = two.cA; bins.s0 = two.sA; bins.q0 = two.qA; bins.x0 = two.xA;
-            bins.b1 = two.bB; bins.c1 = two.cB; bins.s1 = two.sB; bins.q1 = two.qB; bins.x1 = two.xB;
-            bins.total = two.total;
-        } else {
-            walk(bins);
         }
+    };
+    Bins2 two;
+    two.init();
+    walk(two);
+    if (!two.overflow) {
+        bins.b0 = two.bA; bins.c0 = two.cA; bins.s0 = two.sA; bins.q0 = two.qA; bins.x0 = two.xA;
+        bins.b1 = two.bB; bins.c1 = two.cB; bins.s1 = two.sB; bins.q1 = two.qB; bins.x1 = two.xB;
+        bins.total = two.total;
     } else {
-        for (int e = 0; e < m; e++) {
-            int base, qual, score;
-            if (fetch_vote(cb, ents[e], col, side, tab, base, qual, score)) bins.add(base, qual, score);
-        }
+        walk(bins);
     }
-    finish_column(b, r, gv, o, rb, fs, out, col, bins, base_at(cb + 4 * (int)tv.own_off4 + qbytes, col), [&](auto &&f) {
-        for (int e = 0; e < m; e++) {
+    // the record's base before the vote: the template's own (pair.cpp rewrites qualities, never bases)
+    finish_column(b, r, gv, o, rb, fs, out, col, bins, (int)((ents[fs.tmpl_k] >> 16) & 0xFu), [&](auto &&f) {
+        for (int e = 0; e < n; e++) {
             int base, qual, score;
-            if (fetch_ent(cb, ents[e], col, side, o, base, qual, score)) f(base, qual, score, e == fs.tmpl_k);
+            if (slow_decode(tab, ents[e], side, base, qual, score)) f(base, qual, score, e == fs.tmpl_k);
         }
     });
+}
+
+__global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o,
+                                                                       SlowQueue sq, RollbackList rb) {
+    if (batch_is_malformed(ws.error_flag)) return;
+    const uint32_t reserved = (uint32_t)(*sq.count >> 32), total = reserved < sq.cap_recs ? reserved : sq.cap_recs;
+    const ScoreTab tab(o);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t off = sq.index[i];
+        if (off == VQ_INVALID) continue;
+        slow_record(b, r, gv, o, tab, rb, sq.words + off);
+    }
 }
 
 }  // namespace gcb

@@ -16,13 +16,16 @@
 //   slow columns      a lane that finds slow columns among its sixteen appends one entry (family side, lane, column mask) to the
 //                     tile's list in shared memory.  The warp that finishes the tile's last bundle CLOSES the tile (prefix sums
 //                     of the entries' column counts) and the tile's slow columns become work for the whole CTA: any voter
-//                     warp — between two tiles, or while it waits for a tile that has not arrived — claims 32 columns at a
-//                     time (compare-and-swap on the tile's claim word, which carries the tile's generation, so a warp that
-//                     looks at a recycled stage never claims from the wrong tile) and decides them one thread per column,
-//                     straight from the staged slab (decide_column, k_slow_columns.cuh).  The tile is released by the last
-//                     of: every voter warp leaving it, and its last slow column being decided.  No queue in global memory, no
-//                     second kernel, the reads cross HBM once; nobody waits for a slow column unless the arena is full of
-//                     tiles that wait for theirs.  (Measured alternatives, profiles/r03_notes.md.)
+//                     warp claims 32 columns at a time (compare-and-swap on the tile's claim word) and extracts them, one
+//                     thread per column, into the global queue slow_columns_kernel decides from (k_slow_columns.cuh): a
+//                     32-byte self-contained header, then per read of the family side its quality, base, mate quality, mate
+//                     base and overlap state (4 bytes); queue space is one 64-bit atomic per 32 columns.  A full queue hands
+//                     the tile to the generic kernel.
+//   no walks          No warp walks the tiles.  Work is a claim: 32 slow columns of a closed tile — first, because the oldest
+//                     tile's columns hold the arena — or a bundle of the head tile (the first one that still has any).  The
+//                     claim words carry the tile's number, so a stale look at a recycled stage claims nothing.  A tile is
+//                     released by whoever finishes it: the warp that closes it when it has no slow column, else the warp
+//                     that extracts its last one.  (Measured alternatives, profiles/r03_notes.md.)
 #pragma once
 
 #include "k_slow_columns.cuh"
@@ -46,7 +49,7 @@ struct __align__(16) RingStage {  // shared memory; the first part is written by
     int32_t ft_off, vr_off, slab_off;  // where the tile's family-side list, VoteRead table and payload slab lie (shared-memory offsets)
     int32_t sl_off;                    // slow-column list: uint32 entries[sl_cap], then their inclusive column counts
     int32_t sl_cap;
-    int32_t pad0;
+    int32_t overflow;      // atomic: the queue had no room for some column of the tile (the generic kernel redoes the tile)
     // the voters' part
     uint32_t bclaim;       // atomic (compare-and-swap): (tile number & 0xFFF) << 20 | bundles handed out so far
     int32_t done;          // atomic: bundles finished
@@ -71,28 +74,8 @@ constexpr int VR_OFF_ARENA = (VR_OFF_CTRL + 16 + 127) & ~127;
 static_assert(VR_OFF_HDR % 16 == 0 && VR_OFF_HCACHE % 16 == 0 && VR_OFF_ARENA % 128 == 0, "ring layout");
 GCB_HD uint32_t ring_round128(uint32_t v) { return (v + 127u) & ~127u; }
 
-struct RingCtx {  // what deciding a slow column needs besides the stage
-    const BatchView *b;
-    const ResultView *r;
-    const GenomeView *gv;
-    const gcb_options *o;
-    RollbackList rb;
-};
-
-// One slow column of family side f of a staged tile, decided from shared memory.  (The pointers are derived from the
-// shared-memory symbol inside the function, so that the loads are LDS and not generic loads.)
-__device__ __noinline__ void ring_slow_column(const RingCtx &x, int ft_off, int vr_off, int slab_off, int64_t out_base0, int f, int col) {
-    GCB_DYN_SMEM(smem);
-    const FsTile ft = ((const FsTile *)(smem + ft_off))[f];
-    SlowSide fs;
-    fs.m = ft.m; fs.l_out = ft.l_out; fs.len = ft.len; fs.tmpl_k = ft.tmpl_k; fs.side = fs_side(ft); fs.flags = ft.flags; fs.slot = ft.slot;
-    fs.ref_nib0 = ft.ref_nib0;
-    decide_column(*x.b, *x.r, *x.gv, *x.o, x.rb, fs, smem + slab_off + 4 * (int)ft.cbase4, (const VoteRead *)(smem + vr_off) + ft.ent0,
-                  x.r->out_payload + out_base0 + 4 * (int64_t)ft.out4, col);
-}
-
 __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o, int32_t implied,
-                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, RollbackList rb,
+                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueue sq,
                                                                    int32_t n_tiles, int32_t arena_bytes) {
     GCB_DYN_SMEM(smem);
     if (batch_is_malformed(ws.error_flag)) return;  // (every thread of the grid sees the same flag: the kernels that raise it have finished)
@@ -166,7 +149,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             sh.slab_off = sh.vr_off + (int32_t)ring_round128(vr_bytes);
             sh.sl_off = sh.slab_off + (int32_t)ring_round128((uint32_t)cur.slab_bytes + VT_SLAB_SLACK);
             sh.sl_cap = max(cur.nfs, 0) * cur.lanes;
-            sh.pad0 = 0;
+            sh.overflow = 0;
             sh.bclaim = ((uint32_t)k & 0xFFFu) << VR_CLAIM_GEN_SHIFT;
             sh.done = 0;
             sh.n_entries = 0;
@@ -218,8 +201,6 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         return;
     }
 
-    RingCtx x;
-    x.b = &b; x.r = &r; x.gv = &gv; x.o = &o; x.rb = rb;
     // ---- voters
     const uint32_t mod4 = 0x01010101u * (uint32_t)(o.moderate_quality & 0xFF);
     const uint32_t sbase = smem_base(smem);
@@ -237,9 +218,11 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             for (int t = dk; t <= head;) {
                 RingStage *h = shdr + (t % n_stages);
                 const uint32_t v = *(volatile uint32_t *)&h->claim;
+                // (the head tile's header may be half written: the producer fills it in before the tile's `full` phase)
+                if (t == head && !pipe_try_wait(full + (t % n_stages), (uint32_t)((t / n_stages) & 1), 0u)) break;
                 if ((v >> VR_CLAIM_GEN_SHIFT) != ((uint32_t)t & 0xFFFu)) {
-                    if (t == head) break;  // (not here yet)
-                    if (t == dk) dk++;     // the stage holds a later tile: tile t is decided and released
+                    if (t == head) break;  // (read before the header was there)
+                    if (t == dk) dk++;     // the stage holds a later tile: tile t is extracted and released
                     t++;
                     continue;
                 }
@@ -267,6 +250,9 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         __syncwarp();
         RingStage *h = shdr + got_s;
         const int idx = c0 + lane;
+        FsTile ft;
+        ft.m = 0;
+        int col = 0;
         if (idx < total) {
             const uint32_t *s_list = (const uint32_t *)(smem + h->sl_off), *s_pf = s_list + h->sl_cap;
             int lo = 0, hi = h->n_entries - 1;
@@ -280,8 +266,31 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             const int rank = idx - ((int)s_pf[lo] - __popc(mask));
             for (int q = 0; q < rank; q++) mask &= mask - 1u;
             const int bit = __ffs((int)mask) - 1;  // bit 8 * w + i of the mask = column 8 * w + 7 - i of the lane's sixteen
-            const int col = VT_CHUNK * (int)((code >> 16) & 31u) + (bit & 8) + 7 - (bit & 7);
-            ring_slow_column(x, h->ft_off, h->vr_off, h->slab_off, h->out_base0, (int)(code >> 21), col);
+            col = VT_CHUNK * (int)((code >> 16) & 31u) + (bit & 8) + 7 - (bit & 7);
+            ft = ((const FsTile *)(smem + h->ft_off))[code >> 21];
+        }
+        // queue space for the warp's columns: records of one size (the largest family side among them), one atomic
+        const uint32_t n_cols = (uint32_t)min(WARP, total - c0), stride = slow_rec_words(__reduce_max_sync(FULL, (int)ft.m)), W = n_cols * stride;
+        unsigned long long base64 = ~0ull;
+        if (lane == 0 && (uint32_t)*(volatile unsigned long long *)sq.count < sq.cap_words)  // (a full queue is not counted further)
+            base64 = atomicAdd(sq.count, ((unsigned long long)n_cols << 32) | W);
+        base64 = __shfl_sync(FULL, base64, 0);
+        const uint32_t r0 = (uint32_t)(base64 >> 32), w0 = (uint32_t)base64;
+        if (base64 != ~0ull && (unsigned long long)r0 + n_cols <= sq.cap_recs && (unsigned long long)w0 + W <= sq.cap_words) {
+            if (idx < total) {
+                const uint32_t wofs = w0 + (uint32_t)lane * stride;
+                sq.index[r0 + (uint32_t)lane] = wofs;
+                slow_extract_column(sq.words + wofs, ft, smem + h->slab_off + 4 * (int)ft.cbase4, (const VoteRead *)(smem + h->vr_off) + ft.ent0,
+                                    h->out_base0 + 4 * (int64_t)ft.out4, col);
+            }
+        } else {
+            // no room: what was reserved stays unused, and the generic kernel redoes the whole tile from the payload (it runs
+            // after slow_columns_kernel and vote_rollback_kernel)
+            if (base64 != ~0ull && idx < total && (unsigned long long)r0 + (uint32_t)lane < sq.cap_recs) sq.index[r0 + (uint32_t)lane] = VQ_INVALID;
+            if (lane == 0 && atomicExch(&h->overflow, 1) == 0) {
+                ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~h->tile;
+                GCB_COUNT(1, 1);
+            }
         }
         __syncwarp();
         if (lane == 0) {

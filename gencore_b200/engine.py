@@ -24,7 +24,7 @@ DEFAULT_LIB = os.path.join(HERE, "csrc", "libgencore_b200.so")
 # every symbol include/gencore_b200.h declares
 ABI_SYMBOLS = ["gcb_abi_version", "gcb_default_options", "gcb_create", "gcb_destroy", "gcb_last_error", "gcb_set_reference",
                "gcb_set_reference_device", "gcb_consensus_batch", "gcb_consensus_batch_device", "gcb_batch_status",
-               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_debug", "gcb_pack_fasta", "gcb_host_alloc", "gcb_host_free"]
+               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_debug", "gcb_set_slow_queue_bytes", "gcb_pack_fasta", "gcb_host_alloc", "gcb_host_free"]
 
 
 class EngineError(RuntimeError):
@@ -57,6 +57,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gcb_batch_status.argtypes = [C.c_void_p, C.c_void_p]
     lib.gcb_extract_umi.restype = C.c_int
     lib.gcb_extract_umi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.gcb_set_slow_queue_bytes.restype = C.c_int
+    lib.gcb_set_slow_queue_bytes.argtypes = [C.c_void_p, C.c_int64]
     lib.gcb_pack_fasta.restype = C.c_int
     lib.gcb_pack_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
@@ -171,6 +173,10 @@ class ConsensusEngine:
     def set_debug(self, key: int, value: int) -> None:
         """Tuning / test aid (see gcb_set_debug): 2 = tile window shift, 3 = lanes per cluster, 5 = generic kernel only."""
         self._check(self.lib.gcb_set_debug(self._ctx, key, value))
+
+    def set_slow_queue_bytes(self, nbytes: int) -> None:
+        """Bytes of the slow-column queue (tuning / tests: tiles whose columns do not fit are voted by the generic kernel)."""
+        self._check(self.lib.gcb_set_slow_queue_bytes(self._ctx, nbytes))
 
     def batch_status(self, stream: int = 0) -> int:
         return self.lib.gcb_batch_status(self._ctx, C.c_void_p(stream))

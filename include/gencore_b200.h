@@ -232,6 +232,10 @@ void gcb_host_free(void *p);
  * key 5 = non-zero: every tile is voted by the generic kernel (score_vote_kernel) instead of the ring kernel. */
 int gcb_set_debug(gcb_ctx *ctx, int key, int value);
 
+/* Tuning knob: bytes of the slow-column queue between vote_ring_kernel and slow_columns_kernel (0 = sized from the payload).
+ * Tiles whose slow columns do not fit are voted by the generic kernel; results do not depend on it. */
+int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes);
+
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t gcb_launch_count(const gcb_ctx *ctx);
 

@@ -92,6 +92,18 @@ def test_lanes_per_cluster_do_not_change_results(engine_cls, oracle, name, lanes
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} lanes {lanes}")
 
 
+@pytest.mark.parametrize("qbytes", [1 << 14, 1 << 20])
+@pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "cfg4_40k", "edge_strict", "deep50_noisy_40k"])
+def test_slow_queue_overflow_does_not_change_results(engine_cls, oracle, name, qbytes):
+    """A slow-column queue far too small: the tiles whose columns do not fit are redone by the generic kernel."""
+    batch, genome, opt = dict(CASES)[name]()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        eng.set_slow_queue_bytes(qbytes)
+        res = eng.cluster_by_umi(batch)
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} queue {qbytes}")
+
+
 @pytest.mark.parametrize("name", ["cfg3_40k", "ragged_duplex_5_big", "deep_1100", "cfg4_40k", "cfg5_40k", "deep50_noisy_40k"])
 @pytest.mark.parametrize("chunk", [1 << 14, 1 << 18, 1 << 21])
 def test_pipeline_chunks_do_not_change_results(engine_cls, oracle, name, chunk):

@@ -96,6 +96,17 @@ def test_small_tile_window_matches_oracle_under_simt_check(simt_lib, oracle, nam
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), name)
 
 
+@pytest.mark.parametrize("qbytes", [4096, 65536])
+@pytest.mark.parametrize("name", ["cfg2_1500", "ragged_duplex_2", "golden_cfg4_600", "edge_strict", "deep30_noisy"])
+def test_slow_queue_overflow_does_not_change_results(simt_lib, oracle, name, qbytes):
+    """A slow-column queue far too small: the tiles whose columns do not fit are redone by the generic kernel."""
+    batch, genome, opt = dict(CASES)[name]()
+    res, cnt = run(simt_lib, batch, genome, opt, lambda eng: eng.set_slow_queue_bytes(qbytes))
+    assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} queue {qbytes}")
+    if qbytes == 4096:
+        assert cnt[1] > 0, "some tile must have been handed to the generic kernel"
+
+
 @pytest.mark.parametrize("name,lanes", [(n, l) for n in ["golden_cfg2_600", "golden_cfg4_600", "edge_default", "ragged_duplex_2", "ragged_single_1",
                                                          "low_complexity", "wide_umi_3", "cfg3_1500", "tiny_reads", "cfg5_1500"] for l in [8, 16, 32]] +
                          [("deep_1100", 8)])
