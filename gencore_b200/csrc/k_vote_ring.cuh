@@ -21,11 +21,9 @@
 //                     32-byte self-contained header, then per read of the family side its quality, base, mate quality, mate
 //                     base and overlap state (4 bytes); queue space is one 64-bit atomic per 32 columns.  A full queue hands
 //                     the tile to the generic kernel.
-//   no walks          No warp walks the tiles.  Work is a claim: 32 slow columns of a closed tile — first, because the oldest
-//                     tile's columns hold the arena — or a bundle of the head tile (the first one that still has any).  The
-//                     claim words carry the tile's number, so a stale look at a recycled stage claims nothing.  A tile is
-//                     released by whoever finishes it: the warp that closes it when it has no slow column, else the warp
-//                     that extracts its last one.  (Measured alternatives, profiles/r03_notes.md.)
+//   release           A tile is released when every voter warp has left it and its last slow column is extracted.  A warp
+//                     extracts between two tiles and while it waits for a tile that has not arrived.  (Measured
+//                     alternatives, profiles/r03_notes.md.)
 #pragma once
 
 #include "k_slow_columns.cuh"
@@ -51,7 +49,7 @@ struct __align__(16) RingStage {  // shared memory; the first part is written by
     int32_t sl_cap;
     int32_t overflow;      // atomic: the queue had no room for some column of the tile (the generic kernel redoes the tile)
     // the voters' part
-    uint32_t bclaim;       // atomic (compare-and-swap): (tile number & 0xFFF) << 20 | bundles handed out so far
+    int32_t next_bundle;   // atomic: next bundle to hand out
     int32_t done;          // atomic: bundles finished
     int32_t n_entries;     // atomic: slow-column list entries
     int32_t closed;        // the list is complete and its prefix sums are written
@@ -67,8 +65,7 @@ constexpr int VR_OFF_FULL = 0;                                   // uint64[VR_MA
 constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_HDR = 16 * VR_MAX_STAGES;                   // RingStage[VR_MAX_STAGES]
 constexpr int VR_OFF_HCACHE = VR_OFF_HDR + 96 * VR_MAX_STAGES;   // TileHdr2[32]: the producer's next tiles
-constexpr int VR_OFF_CTRL = VR_OFF_HCACHE + 48 * WARP;          // int32[4]: [0] tiles that are closed and have slow columns nobody has claimed yet,
-                                                                 // [1] the first tile that may still have bundles to hand out
+constexpr int VR_OFF_CTRL = VR_OFF_HCACHE + 48 * WARP;          // int32[4]: [0] tiles that are closed and have slow columns nobody has claimed yet
 constexpr int VR_OFF_ARENA = (VR_OFF_CTRL + 16 + 127) & ~127;
 // a tile's allocation: [FsTile list][VoteRead table][slab + slack][slow-column list + two prefix arrays], each part rounded to 128 bytes
 static_assert(VR_OFF_HDR % 16 == 0 && VR_OFF_HCACHE % 16 == 0 && VR_OFF_ARENA % 128 == 0, "ring layout");
@@ -84,15 +81,15 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     RingStage *shdr = (RingStage *)(smem + VR_OFF_HDR);
 #define GCB_LDS32(off) (*(const uint32_t *)(smem + (off)))
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    int32_t *drain_pending = (int32_t *)(smem + VR_OFF_CTRL), *head_tile = drain_pending + 1;
+    int32_t *drain_pending = (int32_t *)(smem + VR_OFF_CTRL);
     constexpr int n_stages = VR_MAX_STAGES;
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
             pipe_init(full + s, 1);
-            pipe_init(empty + s, 1);  // whoever decides the tile's last slow column (the closing warp itself when there is none)
+            pipe_init(empty + s, VR_VOTERS + 1);  // every voter warp arrives once when it leaves the tile, and once more whoever extracts
+                                                  // the tile's last slow column (the closing warp itself when there is none)
         }
         drain_pending[0] = 0;
-        head_tile[0] = 0;
         pipe_fence_init();
     }
     __syncthreads();
@@ -150,7 +147,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             sh.sl_off = sh.slab_off + (int32_t)ring_round128((uint32_t)cur.slab_bytes + VT_SLAB_SLACK);
             sh.sl_cap = max(cur.nfs, 0) * cur.lanes;
             sh.overflow = 0;
-            sh.bclaim = ((uint32_t)k & 0xFFFu) << VR_CLAIM_GEN_SHIFT;
+            sh.next_bundle = 0;
             sh.done = 0;
             sh.n_entries = 0;
             sh.closed = 0;
@@ -207,22 +204,18 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     // lane geometry and masks are kept across tiles while the tile shape (lanes per family side, usual record length) stays
     int cur_L = 0, cur_l = -1, S = 32, sub = 0, j = 0, col0 = 0;
     ChunkMasks cm_common = make_masks(0, 0, 0);
-    // ---- slow columns of closed tiles: work for any voter warp.  Lane 0 looks at the tiles dk .. head_tile (oldest first; dk
-    // moves past the tiles that are released or fully handed out), claims up to 32 columns of the first one that has any, and
-    // the warp decides them, one thread per column.  Returns false when nothing could be claimed.
+    // ---- slow columns of closed tiles: work for any voter warp.  Lane 0 looks at the tiles dk .. k_hi-1 (the ones this warp has
+    // seen arrive, oldest first; dk moves past the tiles that are released or fully handed out), claims up to 32 columns of
+    // the first one that has any, and the warp extracts them, one thread per column.  Returns false when nothing could be claimed.
     int dk = 0;  // (lane 0's)
-    auto help_drain = [&]() -> bool {
+    auto help_drain = [&](int k_hi) -> bool {
         int got_s = -1, c0 = 0, total = 0;
         if (lane == 0) {
-            const int head = *(volatile int32_t *)head_tile;  // every tile before it has arrived (its bundles are handed out)
-            for (int t = dk; t <= head;) {
+            for (int t = dk; t < k_hi;) {
                 RingStage *h = shdr + (t % n_stages);
                 const uint32_t v = *(volatile uint32_t *)&h->claim;
-                // (the head tile's header may be half written: the producer fills it in before the tile's `full` phase)
-                if (t == head && !pipe_try_wait(full + (t % n_stages), (uint32_t)((t / n_stages) & 1), 0u)) break;
-                if ((v >> VR_CLAIM_GEN_SHIFT) != ((uint32_t)t & 0xFFFu)) {
-                    if (t == head) break;  // (read before the header was there)
-                    if (t == dk) dk++;     // the stage holds a later tile: tile t is extracted and released
+                if ((v >> VR_CLAIM_GEN_SHIFT) != ((uint32_t)t & 0xFFFu)) {  // the stage holds a later tile: tile t is extracted and released
+                    if (t == dk) dk++;
                     t++;
                     continue;
                 }
@@ -306,51 +299,30 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         if (lane == 0) p = *(volatile int32_t *)drain_pending;
         return __shfl_sync(FULL, p, 0) > 0;
     };
-    // ---- the voters' loop: no warp walks the tiles.  Work is (1) 32 slow columns of a closed tile — first, because the oldest
-    // tile's columns hold the arena — or (2) a bundle of the first tile that still has any (head_tile; tile k lives in slot
-    // k % n_stages, its claim words carry k's low bits, so a stale look at a recycled stage claims nothing).
-    bool ended = false;
-    for (;;) {
-        if (drain_is_pending() && help_drain()) continue;
-        int k = 0, bundle = 0, what = 0;  // 1: a bundle, 2: the end marker is at the head
-        if (lane == 0) {
-            for (;;) {
-                k = *(volatile int32_t *)head_tile;
-                const int s = k % n_stages;
-                if (!pipe_try_wait(full + s, (uint32_t)((k / n_stages) & 1), 0u)) break;  // not here yet
-                RingStage *h = shdr + s;
-                const uint32_t v = *(volatile uint32_t *)&h->bclaim;
-                if ((v >> VR_CLAIM_GEN_SHIFT) != ((uint32_t)k & 0xFFFu)) continue;  // the stage was recycled: head_tile has moved
-                if (*(volatile int32_t *)&h->nfs < 0) {
-                    what = 2;
-                    break;
-                }
-                const int idx = (int)(v & VR_CLAIM_COL_MASK);
-                if (idx >= *(volatile int32_t *)&h->n_bundles) {  // all handed out: the next tile is the head
-                    atomicMax(head_tile, k + 1);
-                    continue;
-                }
-                if (atomicCAS(&h->bclaim, v, v + 1u) != v) continue;
-                bundle = idx;
-                what = 1;
-                break;
-            }
-        }
-        what = __shfl_sync(FULL, what, 0);
-        if (what != 1) {
-            if (what == 2) ended = true;
-            if (ended && !help_drain()) break;  // (a warp that closes a tile after this point decides its columns itself)
-            pipe_relax(100u);
-            continue;
-        }
-        k = __shfl_sync(FULL, k, 0);
-        bundle = __shfl_sync(FULL, bundle, 0);
-        __syncwarp();  // (lane 0 observed the tile's `full` phase)
+    // tile k lives in slot k % n_stages
+    int k = 0;
+    for (;; k++) {
         const int s = k % n_stages;
+        const uint32_t par = (uint32_t)((k / n_stages) & 1);
+        GCB_TRACE(100 + s);
+        // wait for the tile; slow columns of earlier tiles are extracted meanwhile
+        for (;;) {  // (lane 0 polls for the warp: the branch below holds collectives)
+            int here = 0;
+            if (lane == 0) here = pipe_try_wait(full + s, par, 500u) ? 1 : 0;
+            if (__shfl_sync(FULL, here, 0)) break;
+            if (!(drain_is_pending() && help_drain(k))) pipe_relax(20u);
+        }
+        pipe_wait(full + s, par, 200u);  // every lane observes the completed phase itself (returns at once)
         RingStage *sh = shdr + s;
-        const int nfs = sh->nfs, nb = sh->n_bundles;
+        const int nfs = sh->nfs;
+        if (nfs < 0) break;
         GCB_TRACE(400 + s);
-        {
+        const int nb = sh->n_bundles;
+        int bundle = nb;
+        if (lane == 0 && *(volatile int32_t *)&sh->next_bundle < nb) bundle = atomicAdd(&sh->next_bundle, 1);  // (no atomic on a drained tile)
+        bundle = __shfl_sync(FULL, bundle, 0);
+        bool closer = false;
+        if (bundle < nb) {
             if (sh->lanes != cur_L) {  // a lane owns sixteen columns; a family side takes L lanes, a bundle 32 / L family sides
                 cur_L = sh->lanes;
                 S = (int)((32u * ((65535u / (unsigned)cur_L) + 1u)) >> 16);
@@ -369,7 +341,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             uint8_t *out0 = r.out_payload + sh->out_base0;
             uint32_t *s_list = (uint32_t *)(smem + sh->sl_off);
             const int sb0 = 8 * j;  // the lane's first byte of a record's packed bases
-            {
+            do {
                 const int f = bundle * S + sub;
                 const bool have = sub < S && f < nfs;
                 FsTile ft = s_ft[have ? f : 0];
@@ -526,18 +498,21 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     at = __shfl_sync(FULL, at, 0);
                     if (mask16 != 0u) s_list[at + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)f << 21) | ((uint32_t)j << 16) | mask16;
                 }
-            }
+                // the warp that finishes the tile's last bundle closes the tile; every warp takes its next bundle
+                __syncwarp();
+                int fin = 0;
+                if (lane == 0) {
+                    __threadfence_block();  // the entries above, and the record's words in global memory, before the count
+                    fin = atomicAdd(&sh->done, 1) + 1;
+                    bundle = atomicAdd(&sh->next_bundle, 1);
+                }
+                fin = __shfl_sync(FULL, fin, 0);
+                bundle = __shfl_sync(FULL, bundle, 0);
+                closer = closer || fin == nb;
+                pipe_progress();
+            } while (bundle < nb);
         }
-        // the warp that finishes the tile's last bundle closes the tile
-        __syncwarp();
-        int fin = 0;
-        if (lane == 0) {
-            __threadfence_block();  // the entries above, and the record's words in global memory, before the count
-            fin = atomicAdd(&sh->done, 1) + 1;
-        }
-        fin = __shfl_sync(FULL, fin, 0);
-        pipe_progress();
-        if (fin == nb) {
+        if (closer) {
             // every bundle of the tile is done: prefix sums of the entries' column counts, then the list is open to every warp
             __threadfence_block();
             int n = 0;
@@ -558,7 +533,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             __syncwarp();
             if (lane == 0) {
                 if (run == 0) {
-                    pipe_arrive(empty + s);  // no slow column: the tile is released
+                    pipe_arrive(empty + s);  // no slow column: the extra arrival is the closing warp's
                 } else {
                     sh->drain_total = run;
                     __threadfence_block();
@@ -567,7 +542,12 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 }
             }
         }
+        __syncwarp();
+        if (lane == 0) pipe_arrive(empty + s);
+        if (drain_is_pending()) help_drain(k + 1);  // one chunk between two tiles keeps the stream of tiles going
     }
+    // no more tiles: what is left to decide (a warp that closes a tile after this point comes by here itself)
+    while (help_drain(k)) {}
 #undef GCB_LDS32
 }
 
