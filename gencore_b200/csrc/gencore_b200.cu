@@ -42,7 +42,7 @@ struct gcb_ctx {
     // workspace (grow-only)
     DevBuf w_members, w_group_off, w_scratch, w_rrp, w_flags, w_mode, w_hasumi, w_overlap, w_slab, w_cob, w_coo, w_scan, w_err, w_tiles;
     DevBuf w_vr, w_fs, w_gtiles, w_gcount;
-    DevBuf w_fstiles, w_thdr2;           // the tiles' compact family-side lists and their headers
+    DevBuf w_fstiles, w_thdr2, w_need;   // the tiles' compact family-side lists, their headers, the largest tile's shared-memory need (per chunk)
     DevBuf w_rb_list, w_rb_count;        // rollback candidates (per chunk: one counter)
     DevBuf w_sq_count, w_sq_words, w_sq_index;  // slow-column queue (per chunk: one counter)
     int64_t slow_queue_bytes = 0;        // 0 = sized from the payload
@@ -173,11 +173,13 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_gcount, 4 * GCB_MAX_CHUNKS);
     GCB_RES(w_fstiles, 2 * n_pairs * sizeof(FsTile));
     GCB_RES(w_thdr2, (n_tiles + 2 * GCB_MAX_CHUNKS + 1) * sizeof(TileHdr2));
+    GCB_RES(w_need, 4 * GCB_MAX_CHUNKS);
     GCB_RES(w_rb_list, 2 * n_pairs * 4);
     GCB_RES(w_rb_count, 4 * GCB_MAX_CHUNKS);
     {   // slow-column queue: a clean shallow library queues about 0.08 bytes per payload byte, a noisy one of depth 30 (1 % errors:
         // a third of its columns are slow) about 1.5, a vote whose every column is slow (options outside fast_path_implied) about
-        // 4; tiles whose columns do not fit are redone by the generic kernel
+        // 4; deep families never use it (their tiles are decided in place); tiles whose columns do not fit are redone by the
+        // generic kernel
         int64_t qbytes = ctx->slow_queue_bytes > 0 ? ctx->slow_queue_bytes
                          : fast_path_implied(ctx->opt) ? 2 * payload_bytes + (16ll << 20) : 5 * payload_bytes + (16ll << 20);
         int64_t cap_words = qbytes / 4;
@@ -295,6 +297,7 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
     if ((run_prep || run_fast || run_rest) && n_tiles > 0) {
         TileHdr2 *thdr = (TileHdr2 *)ctx->w_thdr2.p + v.tile_base;
         FsTile *fst = (FsTile *)ctx->w_fstiles.p;
+        int32_t *max_need = (int32_t *)ctx->w_need.p + v.index;
         // chunks of one batch run one after another on the stream; every chunk has its own rollback counter and list range
         RollbackList rb;
         rb.list = (int32_t *)ctx->w_rb_list.p + 2 * (size_t)v.p0;
@@ -309,8 +312,9 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         sq.cap_recs = ctx->sq_cap_recs;
         if (run_prep) {
             GCB_CUDA(ctx, cudaMemsetAsync(ws.generic_count, 0, 4, stream));
+            GCB_CUDA(ctx, cudaMemsetAsync(max_need, 0, 4, stream));
             GCB_LAUNCH(tile_prep2_kernel, dim3((unsigned)((n_tiles + VS_PREP_THREADS / WARP - 1) / (VS_PREP_THREADS / WARP))), dim3(VS_PREP_THREADS), 0,
-                       stream, b, r, ws, plan.slab_cap, plan.arena, thdr, fst, (int32_t)n_tiles, (int32_t)(ctx->force_generic || !plan.ring));
+                       stream, b, r, ws, plan.slab_cap, plan.arena, thdr, fst, max_need, (int32_t)n_tiles, (int32_t)(ctx->force_generic || !plan.ring));
             ctx->launches++;
         }
         if (run_fast && plan.ring && !ctx->force_generic) {
@@ -318,7 +322,8 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
             GCB_CUDA(ctx, cudaMemsetAsync(sq.count, 0, 8, stream));
             const unsigned ring_grid = (unsigned)(n_tiles < ctx->n_sms ? n_tiles : ctx->n_sms);
             GCB_LAUNCH(vote_ring_kernel, dim3(ring_grid), dim3(VR_THREADS), plan.smem, stream, b, r, ws, ctx->genome, ctx->opt,
-                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, (int32_t)n_tiles, plan.arena);
+                       fast_path_implied(ctx->opt), (const TileHdr2 *)thdr, (const FsTile *)fst, sq, rb, (int32_t)n_tiles, plan.arena,
+                       (const int32_t *)max_need);
             ctx->launches++;
         }
         if (run_rest) {
@@ -413,7 +418,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
     DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
-                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->w_sq_count, &ctx->w_sq_words, &ctx->w_sq_index, &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
+                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_need, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->w_sq_count, &ctx->w_sq_words, &ctx->w_sq_index,  &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
                      &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status, &ctx->f_text, &ctx->f_anchor, &ctx->f_cnt, &ctx->f_hpos, &ctx->f_hbase,
                      &ctx->f_flag, &ctx->f_coff, &ctx->f_out};

@@ -4,16 +4,18 @@
 //   finish_column()   the decision once the column's histogram is known: top-2 selection (group.cpp:395-417), the rules
 //                     and the reference arbitration (group.cpp:419-525); patches the consensus record and adds to the family
 //                     side's diff / mismatchInc (atomics on the result row, which select_template_kernel wrote with zeros).
-//   slow_columns_kernel   The ring kernel keeps a tile in shared memory only as long as it must; what a slow column needs of
-//                     the tile — per read its quality, its base nibble, its mate's quality and base nibble and where
-//                     pair.cpp:121-170 puts the column: 4 bytes per read behind a 32-byte self-contained header — is
-//                     extracted into a global queue by the ring kernel's warps, 32 columns of a closed tile at a time, one
-//                     thread per column (slow_extract_column), and this kernel takes one record per thread at full
-//                     occupancy: deciding is a chain of dependent small loads and a page of code that wants many resident
-//                     warps and its own instruction cache, which the one-CTA-per-SM ring cannot give it.  (Measured
-//                     alternatives, profiles/r03_notes.md: deciding inside the ring from the staged slab — by the warp that
-//                     found the column, by all warps of a closed tile, by whoever is free —, per-lane and per-bundle
-//                     extraction, re-reading the payload from the second kernel.)
+//   decide_column()   histogram straight from the family side's VoteRead entries and its cluster's slab (score per read:
+//                     pair.cpp:121-170; three-bin register histogram: group.cpp:376-393).  The ring kernel's voter warps
+//                     call it for tiles of deep families, from the staged slab in shared memory.
+//   slow_columns_kernel   everything else.  The ring kernel keeps a tile in shared memory only as long as its warps vote;
+//                     what a slow column needs of the tile — per read its quality, its base nibble, its mate's quality and
+//                     base nibble and where pair.cpp:121-170 puts the column: 4 bytes per read behind a 32-byte
+//                     self-contained header — is written by the lane that found the column into a global queue (one
+//                     64-bit atomic per ~10 bundles reserves a warp's records and words in one counter), and this kernel
+//                     takes one record per thread at full occupancy: the deciding is a chain of dependent small loads that
+//                     wants many resident warps, which the one-CTA-per-SM ring cannot give it.  (Measured alternatives,
+//                     profiles/r03_notes.md: deciding inside the ring — from the staged slab, or from the L2 by dedicated
+//                     warps —, extracting per tile instead of per bundle, re-reading the payload from a second kernel.)
 #pragma once
 
 #include "vote_tile.cuh"
@@ -23,6 +25,7 @@ namespace gcb {
 constexpr uint32_t VQ_INVALID = 0xFFFFFFFFu;   // index entry of a reservation that was not used
 constexpr int VQ_SLOW_THREADS = 128;
 constexpr int VQ_SLOW_CTAS = 148 * 8;          // slow_columns_kernel strides over the records
+constexpr uint32_t VQ_POOL_RECS = 64, VQ_POOL_WORDS = 64 * 20;  // queue space a voter warp reserves at a time
 
 struct SlowQueue {
     unsigned long long *count;   // [1] records << 32 | words reserved so far (may run past the capacity)
@@ -75,42 +78,6 @@ GCB_DEV uint32_t slow_entry(const uint8_t *cb, const VoteRead &v, int col) {
     }
     const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
     return ql | (mql << 8) | (base << 16) | (mbase << 20) | (st << 24) | SE_VOTES;
-}
-
-// One slow column of family side `ft` of a staged tile as a queue record: the header, then one entry per read of the family
-// side.  `cb`: the cluster's slab, `ents`: the family side's VoteRead entries (both in shared memory).
-GCB_DEV void slow_extract_column(uint32_t *rec, const FsTile &ft, const uint8_t *cb, const VoteRead *ents, int64_t out_abs, int col) {
-    slow_write_header(rec, ft, col, out_abs);
-    const int m = ft.m;
-    if ((ft.flags & FS_UNIFORM) && col < (int)ft.len) {
-        // the column's place in pair.cpp:121-170 is the same for every read of a uniform family
-        const VoteRead tv = ents[ft.tmpl_k];
-        const int qbytes = GCB_ALIGN4((int)ft.l_out);
-        const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
-        const int kq = col - (int)tv.ov_own, mp = (int)tv.ov_mate + kq;
-        const bool inwin = info && kq >= 0 && kq < (int)tv.ov_len;
-        const bool mvalid = inwin && mp >= 0 && mp < (int)tv.mate_l;
-        const uint32_t st = !info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE;
-        const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
-        const int mpi = mvalid ? mp : 0;
-        const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
-        const uint32_t tag = (st << 24) | SE_VOTES;
-        for (int e = 0; e < m; e++) {
-            const uint32_t w = *(const uint32_t *)(ents + e);  // own_off4 | mate_off4 << 16
-            uint32_t ent = 0u;
-            if ((w & 0xFFFFu) != VR_NO_VOTE) {
-                const uint8_t *p = cb + 4 * (int)(w & 0xFFFFu);
-                ent = (uint32_t)p[col] | ((((uint32_t)p[soff] >> nsh) & 0xFu) << 16) | tag;
-                if (mvalid) {
-                    const uint8_t *q = cb + 4 * (int)(w >> 16);
-                    ent |= ((uint32_t)q[mpi] << 8) | ((((uint32_t)q[msoff] >> mnsh) & 0xFu) << 20);
-                }
-            }
-            rec[SR_HDR_WORDS + e] = ent;
-        }
-    } else {
-        for (int e = 0; e < m; e++) rec[SR_HDR_WORDS + e] = slow_entry(cb, ents[e], col);
-    }
 }
 
 // base, rewritten quality and score of a queue entry: the same function of the same bytes as fetch_vote
@@ -258,6 +225,85 @@ GCB_DEV void finish_column(const BatchView &b, const ResultView &r, const Genome
         new_qual = co.qual;
     }
     out[col] = (uint8_t)new_qual;
+}
+
+// One column of a family side from its VoteRead entries `ents` and its cluster's slab `cb` (shared or global memory).
+GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const GenomeView &gv, const gcb_options &o, const RollbackList &rb,
+                           const SlowSide &fs, const uint8_t *cb, const VoteRead *ents, uint8_t *out, int col) {
+    const ScoreTab tab(o);
+    const VoteRead tv = ents[fs.tmpl_k];
+    const int side = fs.side;
+    const int qbytes = GCB_ALIGN4(fs.l_out);
+    GCB_COUNT(3, 1);
+    if (col >= fs.len) {  // beyond the voted columns the record keeps what it held (rewritten qualities)
+        int obase = 0, oqual = 0, sc;
+        fetch_ent(cb, tv, col, side, o, obase, oqual, sc);
+        out[col] = (uint8_t)oqual;
+        return;
+    }
+    Bins3 bins;
+    bins.init();
+    const int m = fs.m;
+    if (fs.flags & FS_UNIFORM) {
+        const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
+        const int k = col - (int)tv.ov_own, mp = (int)tv.ov_mate + k;
+        const bool inwin = info && k >= 0 && k < (int)tv.ov_len;
+        const bool mvalid = inwin && mp >= 0 && mp < (int)tv.mate_l;
+        const bool plain = info && !inwin;  // pair.cpp:121-131: outside the overlap the score follows the quality
+        const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
+        const int mpi = mvalid ? mp : 0;
+        const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
+        // eight reads at a time, in two waves of independent loads (where their records lie, then their bytes): a column decided
+        // from global memory waits for two round trips per eight reads instead of two per read
+        for (int e0 = 0; e0 < m; e0 += 8) {
+            uint32_t w[8], x[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) w[u] = e0 + u < m ? *(const uint32_t *)(ents + e0 + u) : (uint32_t)VR_NO_VOTE;  // own_off4 | mate_off4 << 16
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                x[u] = 0u;
+                if ((w[u] & 0xFFFFu) != VR_NO_VOTE) {
+                    const uint8_t *rec = cb + 4 * (int)(w[u] & 0xFFFFu);
+                    x[u] = (uint32_t)rec[col] | ((uint32_t)rec[soff] << 8);
+                    if (mvalid) {
+                        const uint8_t *mrec = cb + 4 * (int)(w[u] >> 16);
+                        x[u] |= ((uint32_t)mrec[mpi] << 16) | ((uint32_t)mrec[msoff] << 24);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if ((w[u] & 0xFFFFu) == VR_NO_VOTE) continue;
+                int ql = (int)(x[u] & 0xFFu);
+                const int base = (int)((x[u] >> (8 + nsh)) & 0xFu);
+                int score;
+                if (mvalid) {
+                    const int mql = (int)((x[u] >> 16) & 0xFFu);
+                    const int mbase = (int)((x[u] >> (24 + mnsh)) & 0xFu);
+                    const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
+                    const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
+                    const int s_match = sc8(tab.q2s((ql + mql) / 2) + 4);                        // pair.cpp:147-152
+                    const int s_mis = mine ? sc8(tab.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;  // pair.cpp:153-169
+                    score = base == mbase ? s_match : s_mis;
+                    ql = base == mbase ? ql : max(0, ql - mql);
+                } else {
+                    score = plain ? tab.q2s(ql) : tab.sm;
+                }
+                bins.add(base, ql, score);
+            }
+        }
+    } else {
+        for (int e = 0; e < m; e++) {
+            int base, qual, score;
+            if (fetch_vote(cb, ents[e], col, side, tab, base, qual, score)) bins.add(base, qual, score);
+        }
+    }
+    finish_column(b, r, gv, o, rb, fs, out, col, bins, base_at(cb + 4 * (int)tv.own_off4 + qbytes, col), [&](auto &&f) {
+        for (int e = 0; e < m; e++) {
+            int base, qual, score;
+            if (fetch_ent(cb, ents[e], col, side, o, base, qual, score)) f(base, qual, score, e == fs.tmpl_k);
+        }
+    });
 }
 
 // One queued column (group.cpp:376-525 from its record)

@@ -6,24 +6,27 @@
 //                     needs, space is freed in tile order as the oldest tile's `empty` mbarrier completes), writes the slot's
 //                     header and issues three bulk asynchronous copies (cp.async.bulk -> UBLKCP) onto the slot's `full`
 //                     mbarrier: compact family-side list, VoteRead table, payload slab.  Up to VR_MAX_STAGES tiles in flight.
-//   warps 1..15       voters.  Every warp visits the CTA's tiles in order: waits for `full`, takes bundles of family sides from
-//                     the tile's counter until none is left, arrives on `empty`.
+//   warps 1..15       voters, in G groups (three while six or more of the batch's largest tile fit the arena, else one).  The
+//                     CTA's k-th tile belongs to group k % G; every warp of the group visits the group's tiles in order:
+//                     waits for `full`, takes bundles of family sides from the tile's counter until none is left, arrives
+//                     on `empty`.  A tile of a 16 KB window has about three bundles for the five warps of its group; the
+//                     groups decouple the tiles in flight from each other and a warp only walks a third of the tiles.
 //   a bundle          32 / L family sides, L lanes each, sixteen columns per lane.  FAST columns (every voter shows the
 //                     template's base, no read disagrees with its mate inside the pair overlap, best quality >=
 //                     moderateQuality: exactly group.cpp:421-427 under `implied`) are finished in the word: per-column maxima
 //                     in 16-bit lanes (VIMNMX3.U16x2 over two reads per iteration), disagreement as OR-accumulated XOR
 //                     residues of the raw words; uniform families (every fixed-length library) run a branch-free loop.
-//   slow columns      a lane that finds slow columns among its sixteen appends one entry (family side, lane, column mask) to the
-//                     tile's list in shared memory.  The warp that finishes the tile's last bundle CLOSES the tile (prefix sums
-//                     of the entries' column counts) and the tile's slow columns become work for the whole CTA: any voter
-//                     warp claims 32 columns at a time (compare-and-swap on the tile's claim word) and extracts them, one
-//                     thread per column, into the global queue slow_columns_kernel decides from (k_slow_columns.cuh): a
-//                     32-byte self-contained header, then per read of the family side its quality, base, mate quality, mate
-//                     base and overlap state (4 bytes); queue space is one 64-bit atomic per 32 columns.  A full queue hands
-//                     the tile to the generic kernel.
-//   release           A tile is released when every voter warp has left it and its last slow column is extracted.  A warp
-//                     extracts between two tiles and while it waits for a tile that has not arrived.  (Measured
-//                     alternatives, profiles/r03_notes.md.)
+//   slow columns      the bundle's slow columns are written into a global queue right away, eight lanes per column (one lane per
+//                     read): a 32-byte self-contained header, then per read of the family side its quality, base, mate
+//                     quality, mate base and overlap state (4 bytes).  Queue space comes from a per-warp pool reserved with one 64-bit atomic
+//                     (records and words in one counter) per ~10 bundles; slow_columns_kernel (k_slow_columns.cuh) decides
+//                     the queued columns at full occupancy.  A full queue hands the tile to the generic kernel.  The ring
+//                     never waits for a slow column.  (Measured alternatives, profiles/r03_notes.md.)
+//   deep tiles        (24 pairs or more per family side on average: few bundles, hundreds of slow columns per tile) keep
+//                     their list in the stage; the warp that finishes the tile's last bundle closes it (prefix sums of the
+//                     entries' column counts), and ALL voter warps of the tile then decide the columns, 32 at a time, one
+//                     thread per column, straight from the staged slab — a deep tile has nothing else for them to do, and
+//                     its reads never cross HBM a second time.
 #pragma once
 
 #include "k_slow_columns.cuh"
@@ -34,8 +37,7 @@ constexpr int VR_THREADS = 512;    // warp 0 produces, fifteen warps vote (128 r
 constexpr int VR_WARPS = VR_THREADS / WARP;
 constexpr int VR_VOTERS = VR_WARPS - 1;
 constexpr int VR_MAX_STAGES = 16;  // tiles in flight (barrier pairs and stage headers); their bytes come from one ring-buffer arena
-constexpr uint32_t VR_CLAIM_GEN_SHIFT = 20;  // RingStage::claim = tile generation << 20 | next slow column to hand out
-constexpr uint32_t VR_CLAIM_COL_MASK = (1u << VR_CLAIM_GEN_SHIFT) - 1u;
+constexpr int VR_GROUPS = 3;       // groups of voter warps when the tiles are small
 constexpr int VR_GUARD = 4608;     // never allocated, after the arena: the branch-free read loop may read a VoteRead table or a
                                    // slab up to 257 entries / 64 bytes past its end (values unused)
 
@@ -45,35 +47,56 @@ struct __align__(16) RingStage {  // shared memory; the first part is written by
     int32_t lanes, n_bundles, common_l;
     int32_t p0, tile;
     int32_t ft_off, vr_off, slab_off;  // where the tile's family-side list, VoteRead table and payload slab lie (shared-memory offsets)
-    int32_t sl_off;                    // slow-column list: uint32 entries[sl_cap], then their inclusive column counts
+    int32_t sl_off;                    // slow-column list: uint32 entries[sl_cap], then their inclusive column counts, then their queue words
     int32_t sl_cap;
-    int32_t overflow;      // atomic: the queue had no room for some column of the tile (the generic kernel redoes the tile)
+    int32_t deep;          // the tile's slow columns are decided here, by all the voter warps together (see the header)
     // the voters' part
     int32_t next_bundle;   // atomic: next bundle to hand out
     int32_t done;          // atomic: bundles finished
     int32_t n_entries;     // atomic: slow-column list entries
-    int32_t closed;        // the list is complete and its prefix sums are written
-    int32_t drain_total;   // slow columns of the tile (valid once closed)
-    uint32_t claim;        // atomic (compare-and-swap): (tile number & 0xFFF) << 20 | slow columns handed out so far
-    int32_t cols_done;     // atomic: slow columns decided
-    int32_t pad1;
+    int32_t closed;        // deep tiles: the list is complete and its prefix sums are written
+    int32_t drain_total;   // deep tiles: slow columns of the tile
+    int32_t next_col;      // deep tiles, atomic: next slow column to decide
+    int32_t pad[2];
 };
 static_assert(sizeof(RingStage) == 96, "stage header size");
 
-// shared-memory map: [barriers][stage headers][producer's header cache][CTA control words][arena]
+// shared-memory map: [barriers][stage headers][producer's header cache][arena]
 constexpr int VR_OFF_FULL = 0;                                   // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_HDR = 16 * VR_MAX_STAGES;                   // RingStage[VR_MAX_STAGES]
 constexpr int VR_OFF_HCACHE = VR_OFF_HDR + 96 * VR_MAX_STAGES;   // TileHdr2[32]: the producer's next tiles
-constexpr int VR_OFF_CTRL = VR_OFF_HCACHE + 48 * WARP;          // int32[4]: [0] tiles that are closed and have slow columns nobody has claimed yet
-constexpr int VR_OFF_ARENA = (VR_OFF_CTRL + 16 + 127) & ~127;
+constexpr int VR_ITEMS = 64;       // slow columns of one bundle that are emitted per round
+constexpr int VR_GROUP = 8;        // lanes per slow column in the emission
+constexpr int VR_OFF_ITEMS = VR_OFF_HCACHE + 48 * WARP;          // per warp: uint16 codes[VR_ITEMS] (family side in the bundle << 9 | column)
+constexpr int VR_OFF_ARENA = (VR_OFF_ITEMS + 2 * VR_ITEMS * VR_WARPS + 127) & ~127;
 // a tile's allocation: [FsTile list][VoteRead table][slab + slack][slow-column list + two prefix arrays], each part rounded to 128 bytes
 static_assert(VR_OFF_HDR % 16 == 0 && VR_OFF_HCACHE % 16 == 0 && VR_OFF_ARENA % 128 == 0, "ring layout");
 GCB_HD uint32_t ring_round128(uint32_t v) { return (v + 127u) & ~127u; }
 
+struct RingCtx {  // what deciding a slow column inside the CTA needs besides the stage
+    const BatchView *b;
+    const ResultView *r;
+    const GenomeView *gv;
+    const gcb_options *o;
+    RollbackList rb;
+};
+
+// One slow column of family side f of a staged (deep) tile, decided from shared memory.  (The pointers are derived from the
+// shared-memory symbol inside the function, so that the loads are LDS and not generic loads.)
+__device__ __noinline__ void ring_slow_column(const RingCtx &x, int ft_off, int vr_off, int slab_off, int64_t out_base0, int f, int col) {
+    GCB_DYN_SMEM(smem);
+    const FsTile ft = ((const FsTile *)(smem + ft_off))[f];
+    SlowSide fs;
+    fs.m = ft.m; fs.l_out = ft.l_out; fs.len = ft.len; fs.tmpl_k = ft.tmpl_k; fs.side = fs_side(ft); fs.flags = ft.flags; fs.slot = ft.slot;
+    fs.ref_nib0 = ft.ref_nib0;
+    decide_column(*x.b, *x.r, *x.gv, *x.o, x.rb, fs, smem + slab_off + 4 * (int)ft.cbase4, (const VoteRead *)(smem + vr_off) + ft.ent0,
+                  x.r->out_payload + out_base0 + 4 * (int64_t)ft.out4, col);
+}
+
 __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o, int32_t implied,
-                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueue sq,
-                                                                   int32_t n_tiles, int32_t arena_bytes) {
+                                                                   const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueue sq, RollbackList rb,
+                                                                   int32_t n_tiles, int32_t arena_bytes, const int32_t *max_need) {
     GCB_DYN_SMEM(smem);
     if (batch_is_malformed(ws.error_flag)) return;  // (every thread of the grid sees the same flag: the kernels that raise it have finished)
     uint64_t *full = (uint64_t *)(smem + VR_OFF_FULL);
@@ -81,15 +104,16 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     RingStage *shdr = (RingStage *)(smem + VR_OFF_HDR);
 #define GCB_LDS32(off) (*(const uint32_t *)(smem + (off)))
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    int32_t *drain_pending = (int32_t *)(smem + VR_OFF_CTRL);
-    constexpr int n_stages = VR_MAX_STAGES;
+    // the batch's largest tile (tile_prep2_kernel measured it) decides how the voters are organised: small tiles -> many in
+    // flight -> three groups of five warps; tiles that fill the arena -> all fifteen warps on every tile
+    const int32_t largest = (int32_t)ring_round128((uint32_t)max(*max_need, 128));
+    const int n_groups = arena_bytes >= 6 * largest ? VR_GROUPS : 1, wpg = VR_VOTERS / n_groups;
+    const int n_stages = VR_MAX_STAGES;
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
             pipe_init(full + s, 1);
-            pipe_init(empty + s, VR_VOTERS + 1);  // every voter warp arrives once when it leaves the tile, and once more whoever extracts
-                                                  // the tile's last slow column (the closing warp itself when there is none)
+            pipe_init(empty + s, wpg);  // every voter warp of the tile's group arrives once when it leaves the tile
         }
-        drain_pending[0] = 0;
         pipe_fence_init();
     }
     __syncthreads();
@@ -135,7 +159,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             head = at + need;
             return at;
         };
-        auto fill = [&](RingStage &sh, const TileHdr2 &cur, int32_t tile, uint32_t at, int k) {
+        auto fill = [&](RingStage &sh, const TileHdr2 &cur, int32_t tile, uint32_t at) {
             const uint32_t vr_bytes = 32u * (uint32_t)cur.np, ft_bytes = 32u * (uint32_t)max(cur.nfs, 0);
             sh.out_base0 = cur.out_base0;
             sh.nfs = cur.nfs;
@@ -146,15 +170,14 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             sh.slab_off = sh.vr_off + (int32_t)ring_round128(vr_bytes);
             sh.sl_off = sh.slab_off + (int32_t)ring_round128((uint32_t)cur.slab_bytes + VT_SLAB_SLACK);
             sh.sl_cap = max(cur.nfs, 0) * cur.lanes;
-            sh.overflow = 0;
+            sh.deep = tile_is_deep(cur.nfs, cur.np) ? 1 : 0;  // few bundles, long lists of slow columns
             sh.next_bundle = 0;
             sh.done = 0;
             sh.n_entries = 0;
             sh.closed = 0;
             sh.drain_total = 0;
-            sh.claim = ((uint32_t)k & 0xFFFu) << VR_CLAIM_GEN_SHIFT;
-            sh.cols_done = 0;
-            sh.pad1 = 0;
+            sh.next_col = 0;
+            sh.pad[0] = sh.pad[1] = 0;
         };
         for (int64_t base = (int64_t)blockIdx.x; base < n_tiles; base += (int64_t)WARP * gridDim.x) {
             const int64_t mine_t = base + (int64_t)lane * gridDim.x;
@@ -170,7 +193,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     const uint32_t at = allocate((uint32_t)tile_smem_need(cur.nfs, cur.np, cur.slab_bytes, cur.lanes));
                     const int s = k % n_stages;
                     RingStage sh;
-                    fill(sh, cur, (int32_t)t, at, k);
+                    fill(sh, cur, (int32_t)t, at);
                     shdr[s] = sh;
                     pipe_expect(full + s, slab_bytes + vr_bytes + ft_bytes);
                     if (slab_bytes > 0) tile_copy(smem + sh.slab_off, b.payload + cur.slab0, slab_bytes, full + s);
@@ -182,142 +205,47 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             }
             __syncwarp();
         }
-        if (lane == 0) {  // the end marker: the phase completes with this arrival alone
-            const uint32_t at = allocate(128u);
-            const int s = k % n_stages;
-            TileHdr2 cur;
-            cur.out_base0 = 0; cur.slab0 = 0; cur.slab_bytes = 0; cur.p0 = 0; cur.np = 0; cur.nfs = -1; cur.lanes = 1; cur.common_l = 0;
-            cur.per_bundle = 32; cur.n_bundles = 0;
-            RingStage sh;
-            fill(sh, cur, 0, at, k);
-            shdr[s] = sh;
-            pipe_expect(full + s, 0u);
-            pipe_commit(full + s);
-            k++;
+        if (lane == 0) {  // one end marker per group: the phase completes with this arrival alone
+            for (int g = 0; g < n_groups; g++) {
+                const uint32_t at = allocate(128u);
+                const int s = k % n_stages;
+                TileHdr2 cur;
+                cur.out_base0 = 0; cur.slab0 = 0; cur.slab_bytes = 0; cur.p0 = 0; cur.np = 0; cur.nfs = -1; cur.lanes = 1; cur.common_l = 0;
+                cur.per_bundle = 32; cur.n_bundles = 0;
+                RingStage sh;
+                fill(sh, cur, 0, at);
+                shdr[s] = sh;
+                pipe_expect(full + s, 0u);
+                pipe_commit(full + s);
+                k++;
+            }
         }
         return;
     }
 
+    RingCtx x;
+    x.b = &b; x.r = &r; x.gv = &gv; x.o = &o; x.rb = rb;
     // ---- voters
     const uint32_t mod4 = 0x01010101u * (uint32_t)(o.moderate_quality & 0xFF);
+    uint32_t pool_r = 0u, pool_re = 0u, pool_w = 0u, pool_we = 0u;  // this warp's reserved records / words of the slow-column queue
+    uint16_t *s_item = (uint16_t *)(smem + VR_OFF_ITEMS + 2 * VR_ITEMS * warp);
     const uint32_t sbase = smem_base(smem);
     // lane geometry and masks are kept across tiles while the tile shape (lanes per family side, usual record length) stays
     int cur_L = 0, cur_l = -1, S = 32, sub = 0, j = 0, col0 = 0;
     ChunkMasks cm_common = make_masks(0, 0, 0);
-    // ---- slow columns of closed tiles: work for any voter warp.  Lane 0 looks at the tiles dk .. k_hi-1 (the ones this warp has
-    // seen arrive, oldest first; dk moves past the tiles that are released or fully handed out), claims up to 32 columns of
-    // the first one that has any, and the warp extracts them, one thread per column.  Returns false when nothing could be claimed.
-    int dk = 0;  // (lane 0's)
-    auto help_drain = [&](int k_hi) -> bool {
-        int got_s = -1, c0 = 0, total = 0;
-        if (lane == 0) {
-            for (int t = dk; t < k_hi;) {
-                RingStage *h = shdr + (t % n_stages);
-                const uint32_t v = *(volatile uint32_t *)&h->claim;
-                if ((v >> VR_CLAIM_GEN_SHIFT) != ((uint32_t)t & 0xFFFu)) {  // the stage holds a later tile: tile t is extracted and released
-                    if (t == dk) dk++;
-                    t++;
-                    continue;
-                }
-                if (*(volatile int32_t *)&h->closed == 0) {  // bundles of the tile are still being voted
-                    t++;
-                    continue;
-                }
-                __threadfence_block();
-                const uint32_t tot = (uint32_t)*(volatile int32_t *)&h->drain_total, c = v & VR_CLAIM_COL_MASK;
-                if (c >= tot) {  // every column of the tile is handed out
-                    if (t == dk) dk++;
-                    t++;
-                    continue;
-                }
-                if (atomicCAS(&h->claim, v, v + (uint32_t)WARP) != v) continue;  // the word moved: look at the tile again
-                if (c + (uint32_t)WARP >= tot) atomicAdd(drain_pending, -1);      // these were the tile's last columns
-                got_s = t % n_stages; c0 = (int)c; total = (int)tot;
-                break;
-            }
-        }
-        got_s = __shfl_sync(FULL, got_s, 0);
-        if (got_s < 0) return false;
-        c0 = __shfl_sync(FULL, c0, 0);
-        total = __shfl_sync(FULL, total, 0);
-        __syncwarp();
-        RingStage *h = shdr + got_s;
-        const int idx = c0 + lane;
-        FsTile ft;
-        ft.m = 0;
-        int col = 0;
-        if (idx < total) {
-            const uint32_t *s_list = (const uint32_t *)(smem + h->sl_off), *s_pf = s_list + h->sl_cap;
-            int lo = 0, hi = h->n_entries - 1;
-            while (lo < hi) {  // the first entry whose inclusive column count exceeds idx
-                const int mid = (lo + hi) >> 1;
-                if ((int)s_pf[mid] > idx) hi = mid;
-                else lo = mid + 1;
-            }
-            const uint32_t code = s_list[lo];
-            uint32_t mask = code & 0xFFFFu;
-            const int rank = idx - ((int)s_pf[lo] - __popc(mask));
-            for (int q = 0; q < rank; q++) mask &= mask - 1u;
-            const int bit = __ffs((int)mask) - 1;  // bit 8 * w + i of the mask = column 8 * w + 7 - i of the lane's sixteen
-            col = VT_CHUNK * (int)((code >> 16) & 31u) + (bit & 8) + 7 - (bit & 7);
-            ft = ((const FsTile *)(smem + h->ft_off))[code >> 21];
-        }
-        // queue space for the warp's columns: records of one size (the largest family side among them), one atomic
-        const uint32_t n_cols = (uint32_t)min(WARP, total - c0), stride = slow_rec_words(__reduce_max_sync(FULL, (int)ft.m)), W = n_cols * stride;
-        unsigned long long base64 = ~0ull;
-        if (lane == 0 && (uint32_t)*(volatile unsigned long long *)sq.count < sq.cap_words)  // (a full queue is not counted further)
-            base64 = atomicAdd(sq.count, ((unsigned long long)n_cols << 32) | W);
-        base64 = __shfl_sync(FULL, base64, 0);
-        const uint32_t r0 = (uint32_t)(base64 >> 32), w0 = (uint32_t)base64;
-        if (base64 != ~0ull && (unsigned long long)r0 + n_cols <= sq.cap_recs && (unsigned long long)w0 + W <= sq.cap_words) {
-            if (idx < total) {
-                const uint32_t wofs = w0 + (uint32_t)lane * stride;
-                sq.index[r0 + (uint32_t)lane] = wofs;
-                slow_extract_column(sq.words + wofs, ft, smem + h->slab_off + 4 * (int)ft.cbase4, (const VoteRead *)(smem + h->vr_off) + ft.ent0,
-                                    h->out_base0 + 4 * (int64_t)ft.out4, col);
-            }
-        } else {
-            // no room: what was reserved stays unused, and the generic kernel redoes the whole tile from the payload (it runs
-            // after slow_columns_kernel and vote_rollback_kernel)
-            if (base64 != ~0ull && idx < total && (unsigned long long)r0 + (uint32_t)lane < sq.cap_recs) sq.index[r0 + (uint32_t)lane] = VQ_INVALID;
-            if (lane == 0 && atomicExch(&h->overflow, 1) == 0) {
-                ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~h->tile;
-                GCB_COUNT(1, 1);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            const int n = min(WARP, total - c0);
-            __threadfence_block();
-            if (atomicAdd(&h->cols_done, n) + n == total) pipe_arrive(empty + got_s);  // the tile's last slow column: the tile is released
-        }
-        pipe_progress();
-        return true;
-    };
-    auto drain_is_pending = [&]() -> bool {
-        int p = 0;
-        if (lane == 0) p = *(volatile int32_t *)drain_pending;
-        return __shfl_sync(FULL, p, 0) > 0;
-    };
-    // tile k lives in slot k % n_stages
-    int k = 0;
-    for (;; k++) {
+    // this warp's group and the group's tiles: k = group, group + G, ...; tile k lives in slot k % n_stages
+    const int group = (warp - 1) % n_groups;
+    for (int k = group;; k += n_groups) {
         const int s = k % n_stages;
         const uint32_t par = (uint32_t)((k / n_stages) & 1);
         GCB_TRACE(100 + s);
-        // wait for the tile; slow columns of earlier tiles are extracted meanwhile
-        for (;;) {  // (lane 0 polls for the warp: the branch below holds collectives)
-            int here = 0;
-            if (lane == 0) here = pipe_try_wait(full + s, par, 500u) ? 1 : 0;
-            if (__shfl_sync(FULL, here, 0)) break;
-            if (!(drain_is_pending() && help_drain(k))) pipe_relax(20u);
-        }
-        pipe_wait(full + s, par, 200u);  // every lane observes the completed phase itself (returns at once)
+        pipe_wait(full + s, par, 1000u);
         RingStage *sh = shdr + s;
         const int nfs = sh->nfs;
         if (nfs < 0) break;
         GCB_TRACE(400 + s);
         const int nb = sh->n_bundles;
+        const bool deep = sh->deep != 0;
         int bundle = nb;
         if (lane == 0 && *(volatile int32_t *)&sh->next_bundle < nb) bundle = atomicAdd(&sh->next_bundle, 1);  // (no atomic on a drained tile)
         bundle = __shfl_sync(FULL, bundle, 0);
@@ -488,36 +416,128 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     if (sb0 < sbytes) *(uint32_t *)(out + qbytes + sb0) = bswap32(tbe0 & cm.kn0);
                     if (sb0 + 4 < sbytes) *(uint32_t *)(out + qbytes + sb0 + 4) = bswap32(tbe1 & cm.kn1);
                 }
-                // ---- slow columns: one list entry per lane that found any (family side << 21 | lane of the family side << 16 |
-                // column mask) in the tile's own list
+                // ---- slow columns: one list entry per lane that found any
                 const uint32_t mask16 = nib_flags_to_byte(slow0) | (nib_flags_to_byte(slow1) << 8);
                 const unsigned bal = __ballot_sync(FULL, mask16 != 0u);
-                if (bal != 0u) {
-                    int at = 0;
-                    if (lane == 0) at = atomicAdd(&sh->n_entries, __popc(bal));
-                    at = __shfl_sync(FULL, at, 0);
-                    if (mask16 != 0u) s_list[at + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)f << 21) | ((uint32_t)j << 16) | mask16;
+                if (deep) {
+                    // the stage's own list (family side << 21 | lane of the family side << 16 | column mask) ...
+                    if (bal != 0u) {
+                        int at = 0;
+                        if (lane == 0) at = atomicAdd(&sh->n_entries, __popc(bal));
+                        at = __shfl_sync(FULL, at, 0);
+                        if (mask16 != 0u) s_list[at + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)f << 21) | ((uint32_t)j << 16) | mask16;
+                    }
+                    // ... and the warp that finishes the tile's last bundle closes the tile
+                    __syncwarp();
+                    int fin = 0;
+                    if (lane == 0) {
+                        __threadfence_block();
+                        fin = atomicAdd(&sh->done, 1) + 1;
+                    }
+                    fin = __shfl_sync(FULL, fin, 0);
+                    closer = fin == nb;
+                } else if (bal != 0u) {
+                    // ... or a record per slow column in the global queue: records of one size per bundle, from the warp's own
+                    // pool of reserved queue space
+                    const uint32_t T = (uint32_t)__reduce_add_sync(FULL, __popc(mask16)), rw = slow_rec_words(mmax), W = T * rw;
+                    if (pool_r + T > pool_re || pool_w + W > pool_we) {
+                        // a new pool (one 64-bit atomic: records << 32 | words); what is left of the old one stays unused
+                        for (uint32_t i = pool_r + (uint32_t)lane; i < pool_re; i += WARP) sq.index[i] = VQ_INVALID;
+                        const uint32_t need_r = T > VQ_POOL_RECS ? T : VQ_POOL_RECS, need_w = W > VQ_POOL_WORDS ? W : VQ_POOL_WORDS;
+                        unsigned long long base64 = 0ull;
+                        if (lane == 0) base64 = atomicAdd(sq.count, ((unsigned long long)need_r << 32) | need_w);
+                        base64 = __shfl_sync(FULL, base64, 0);
+                        const uint32_t r0 = (uint32_t)(base64 >> 32), w0 = (uint32_t)base64;
+                        if ((unsigned long long)r0 + need_r <= sq.cap_recs && (unsigned long long)w0 + need_w <= sq.cap_words) {
+                            pool_r = r0; pool_re = r0 + need_r;
+                            pool_w = w0; pool_we = w0 + need_w;
+                        } else {  // the queue is full: the reserved index entries are marked unused, the pool stays empty
+                            for (uint32_t i = r0 + (uint32_t)lane; i < r0 + need_r && i < sq.cap_recs; i += WARP) sq.index[i] = VQ_INVALID;
+                            pool_r = pool_re = pool_w = pool_we = 0u;
+                        }
+                    }
+                    if (pool_r + T > pool_re) {
+                        // no queue space: the generic kernel redoes the whole tile from the payload (it runs after
+                        // slow_columns_kernel and vote_rollback_kernel)
+                        if (lane == 0 && atomicExch(&sh->closed, 1) == 0) {
+                            ws.generic_tiles[atomicAdd(ws.generic_count, 1)] = ~sh->tile;
+                            GCB_COUNT(1, 1);
+                        }
+                    } else {
+                        // rounds of at most VR_ITEMS columns: every lane lists one of its columns per ballot, then eight lanes per
+                        // column write the column's entries, one lane per read (a lane that writes its own columns alone keeps
+                        // the other lanes waiting: slow columns are rare, the warp has two or three lanes with any)
+                        uint32_t mk = mask16, emitted = 0u;
+                        while (emitted < T) {
+                            uint32_t listed = 0u;
+                            while (listed + WARP <= (uint32_t)VR_ITEMS) {
+                                const unsigned lb = __ballot_sync(FULL, mk != 0u);
+                                if (lb == 0u) break;
+                                if (mk != 0u) {
+                                    const int bit = __ffs((int)mk) - 1;  // bit 8 * w + i of the mask = column 8 * w + 7 - i of the lane's sixteen
+                                    mk &= mk - 1u;
+                                    s_item[listed + __popc(lb & ((1u << lane) - 1u))] = (uint16_t)((sub << 9) | (col0 + (bit & 8) + 7 - (bit & 7)));
+                                }
+                                listed += __popc(lb);
+                            }
+                            __syncwarp();
+                            const int g = lane / VR_GROUP, gl = lane % VR_GROUP;
+                            for (uint32_t i = (uint32_t)g; i < listed; i += WARP / VR_GROUP) {
+                                const uint32_t code = s_item[i], wofs = pool_w + (emitted + i) * rw;
+                                const int col = (int)(code & 511u);
+                                const FsTile fti = s_ft[bundle * S + (int)(code >> 9)];
+                                const uint8_t *cbp = smem + off_slab + 4 * (int)fti.cbase4;
+                                const VoteRead *ents = s_vr + fti.ent0;
+                                uint32_t *rec = sq.words + wofs;
+                                const int mi = (int)fti.m;
+                                if (gl == 0) {
+                                    sq.index[pool_r + emitted + i] = wofs;
+                                    slow_write_header(rec, fti, col, sh->out_base0 + 4 * (int64_t)fti.out4);
+                                }
+                                if ((fti.flags & FS_UNIFORM) && col < (int)fti.len) {
+                                    // the column's place in pair.cpp:121-170 is the same for every read of a uniform family
+                                    const VoteRead tvi = ents[fti.tmpl_k];
+                                    const bool info = tvi.ov_len != VR_NO_OVERLAP_INFO;
+                                    const int kq = col - (int)tvi.ov_own, mp = (int)tvi.ov_mate + kq;
+                                    const bool inwin = info && kq >= 0 && kq < (int)tvi.ov_len;
+                                    const bool mvalid = inwin && mp >= 0 && mp < (int)tvi.mate_l;
+                                    const uint32_t tag = ((!info ? SE_NO_INFO : !inwin ? SE_PLAIN : mvalid ? SE_MATE : SE_NO_MATE_BASE) << 24) | SE_VOTES;
+                                    const int soff = GCB_ALIGN4(fti.l_out) + (col >> 1), nsh = (col & 1) ? 0 : 4;
+                                    const int mpi = mvalid ? mp : 0;
+                                    const int msoff = GCB_ALIGN4(tvi.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
+                                    for (int e = gl; e < mi; e += VR_GROUP) {
+                                        const uint32_t w = *(const uint32_t *)(ents + e);  // own_off4 | mate_off4 << 16
+                                        uint32_t ent = 0u;
+                                        if ((w & 0xFFFFu) != VR_NO_VOTE) {
+                                            const uint8_t *p = cbp + 4 * (int)(w & 0xFFFFu);
+                                            ent = (uint32_t)p[col] | ((((uint32_t)p[soff] >> nsh) & 0xFu) << 16) | tag;
+                                            if (mvalid) {
+                                                const uint8_t *q = cbp + 4 * (int)(w >> 16);
+                                                ent |= ((uint32_t)q[mpi] << 8) | ((((uint32_t)q[msoff] >> mnsh) & 0xFu) << 20);
+                                            }
+                                        }
+                                        rec[SR_HDR_WORDS + e] = ent;
+                                    }
+                                } else {
+                                    for (int e = gl; e < mi; e += VR_GROUP) rec[SR_HDR_WORDS + e] = slow_entry(cbp, ents[e], col);
+                                }
+                            }
+                            __syncwarp();
+                            emitted += listed;
+                        }
+                        pool_r += T;
+                        pool_w += W;
+                    }
                 }
-                // the warp that finishes the tile's last bundle closes the tile; every warp takes its next bundle
-                __syncwarp();
-                int fin = 0;
-                if (lane == 0) {
-                    __threadfence_block();  // the entries above, and the record's words in global memory, before the count
-                    fin = atomicAdd(&sh->done, 1) + 1;
-                    bundle = atomicAdd(&sh->next_bundle, 1);
-                }
-                fin = __shfl_sync(FULL, fin, 0);
+                if (lane == 0) bundle = atomicAdd(&sh->next_bundle, 1);
                 bundle = __shfl_sync(FULL, bundle, 0);
-                closer = closer || fin == nb;
                 pipe_progress();
             } while (bundle < nb);
         }
         if (closer) {
-            // every bundle of the tile is done: prefix sums of the entries' column counts, then the list is open to every warp
+            // every bundle of the (deep) tile is done: prefix sums of the entries' column counts, then the list is open to every warp
             __threadfence_block();
-            int n = 0;
-            if (lane == 0) n = *(volatile int32_t *)&sh->n_entries;
-            n = __shfl_sync(FULL, n, 0);
+            const int n = *(volatile int32_t *)&sh->n_entries;
             uint32_t *s_list = (uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap;
             int run = 0;
             for (int base = 0; base < n; base += WARP) {
@@ -532,22 +552,49 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             }
             __syncwarp();
             if (lane == 0) {
-                if (run == 0) {
-                    pipe_arrive(empty + s);  // no slow column: the extra arrival is the closing warp's
-                } else {
-                    sh->drain_total = run;
-                    __threadfence_block();
-                    *(volatile int32_t *)&sh->closed = 1;
-                    atomicAdd(drain_pending, 1);
+                sh->drain_total = run;
+                __threadfence_block();
+                *(volatile int32_t *)&sh->closed = 1;
+            }
+        }
+        if (deep) {
+            // every voter warp waits for the tile to be closed and then decides slow columns, 32 at a time, one thread per
+            // column, straight from the staged slab: a deep tile has hundreds of them and nothing else for the warps to do
+            while (*(volatile int32_t *)&sh->closed == 0) pipe_relax(100u);
+            __threadfence_block();
+            const int total = *(volatile int32_t *)&sh->drain_total, n = *(volatile int32_t *)&sh->n_entries;
+            const uint32_t *s_list = (const uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap;
+            const int ft_off = sh->ft_off, vr_off = sh->vr_off, slab_off = sh->slab_off;
+            const int64_t out_base0 = sh->out_base0;
+            for (;;) {
+                int c0 = 0;
+                if (lane == 0) c0 = atomicAdd(&sh->next_col, WARP);
+                c0 = __shfl_sync(FULL, c0, 0);
+                if (c0 >= total) break;
+                const int idx = c0 + lane;
+                if (idx < total) {
+                    int lo = 0, hi = n - 1;
+                    while (lo < hi) {  // the first entry whose inclusive column count exceeds idx
+                        const int mid = (lo + hi) >> 1;
+                        if ((int)s_pf[mid] > idx) hi = mid;
+                        else lo = mid + 1;
+                    }
+                    const uint32_t code = s_list[lo];
+                    uint32_t mask = code & 0xFFFFu;
+                    const int rank = idx - ((int)s_pf[lo] - __popc(mask));
+                    for (int q = 0; q < rank; q++) mask &= mask - 1u;
+                    const int bit = __ffs((int)mask) - 1;
+                    const int col = VT_CHUNK * (int)((code >> 16) & 31u) + (bit & 8) + 7 - (bit & 7);
+                    ring_slow_column(x, ft_off, vr_off, slab_off, out_base0, (int)(code >> 21), col);
                 }
+                __syncwarp();
+                pipe_progress();
             }
         }
         __syncwarp();
         if (lane == 0) pipe_arrive(empty + s);
-        if (drain_is_pending()) help_drain(k + 1);  // one chunk between two tiles keeps the stream of tiles going
     }
-    // no more tiles: what is left to decide (a warp that closes a tile after this point comes by here itself)
-    while (help_drain(k)) {}
+    for (uint32_t i = pool_r + (uint32_t)lane; i < pool_re; i += WARP) sq.index[i] = VQ_INVALID;  // what is left of the warp's pool
 #undef GCB_LDS32
 }
 

@@ -380,14 +380,19 @@ GCB_DEV ChunkMasks make_masks(int l_out, int len, int col0) {
 // ------------------------------------------------------------------------------------------------
 // One WARP per tile, 32 pair positions per pass: the tile's bookkeeping, once per batch.  The live family sides are
 // compacted with ballots (no shared memory, no CTA barrier); many tiles per SM keep their chains of dependent loads
-// (directory -> side modes -> family-side descriptors -> cluster offsets) in flight at once.
+// (directory -> side modes -> family-side descriptors -> cluster offsets) in flight at once.  `max_need`: the largest
+// shared-memory allocation a tile of this view takes in the vote kernel.
+GCB_HD bool tile_is_deep(int32_t nfs, int32_t np) { return nfs > 0 && 2 * np >= 24 * nfs; }  // 24 pairs or more per family side on average
 GCB_HD int32_t tile_smem_need(int32_t nfs, int32_t np, int32_t slab_bytes, int32_t lanes) {
-    // family-side list, VoteRead table, slab + slack, the slow-column list and the list's prefix sums (one entry per family side and lane)
-    return ((32 * nfs + 127) & ~127) + ((32 * np + 127) & ~127) + ((slab_bytes + VT_SLAB_SLACK + 127) & ~127) + ((8 * nfs * lanes + 127) & ~127);
+    // family-side list, VoteRead table, slab + slack; a deep tile also its slow-column list and the list's prefix sums (one entry
+    // per family side and lane)
+    return ((32 * nfs + 127) & ~127) + ((32 * np + 127) & ~127) + ((slab_bytes + VT_SLAB_SLACK + 127) & ~127) +
+           (tile_is_deep(nfs, np) ? ((8 * nfs * lanes + 127) & ~127) : 0);
 }
 
 __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b, ResultView r, Workspace ws, int32_t slab_cap, int32_t arena,
-                                                                      TileHdr2 *hdr, FsTile *fs_tiles, int32_t n_tiles, int32_t force_generic) {
+                                                                      TileHdr2 *hdr, FsTile *fs_tiles, int32_t *max_need, int32_t n_tiles,
+                                                                      int32_t force_generic) {
     const int lane = lane_id();
     const int tile = (int)(blockIdx.x * (VS_PREP_THREADS / WARP) + (threadIdx.x >> 5));
     if (tile >= n_tiles || batch_is_malformed(ws.error_flag)) return;
@@ -489,6 +494,7 @@ __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b
             h.common_l = common;
             h.per_bundle = 32 / lmax;
             h.n_bundles = ((int32_t)total + h.per_bundle - 1) / h.per_bundle;
+            atomicMax(max_need, need);
             GCB_COUNT(0, 1);
         }
         hdr[tile] = h;
