@@ -9,6 +9,7 @@
 
 #include <new>
 
+#include "k_cluster_stats.cuh"
 #include "k_duplex.cuh"
 #include "k_group_select.cuh"
 #include "k_score_vote.cuh"
@@ -44,6 +45,7 @@ struct gcb_ctx {
     DevBuf w_vr, w_fs, w_gtiles, w_gcount;
     DevBuf w_fstiles, w_thdr2, w_need;   // the tiles' compact family-side lists, their headers, the largest tile's shared-memory need (per chunk)
     DevBuf w_rb_list, w_rb_count;        // rollback candidates (per chunk: one counter)
+    DevBuf w_stats;                      // gcb_cluster_stats accumulator (cluster_stats_kernel)
     DevBuf w_sq_count, w_sq_words, w_sq_index;  // slow-column queue (per chunk: one counter)
     int64_t slow_queue_bytes = 0;        // 0 = sized from the payload
     uint32_t sq_cap_words = 0, sq_cap_recs = 0;
@@ -176,6 +178,11 @@ int reserve_workspace(gcb_ctx *ctx, int64_t n_pairs, int64_t n_clusters, int64_t
     GCB_RES(w_need, 4 * GCB_MAX_CHUNKS);
     GCB_RES(w_rb_list, 2 * n_pairs * 4);
     GCB_RES(w_rb_count, 4 * GCB_MAX_CHUNKS);
+    if (!ctx->w_stats.p) {
+        GCB_RES(w_stats, sizeof(gcb_cluster_stats));
+        GCB_CUDA(ctx, cudaMemsetAsync(ctx->w_stats.p, 0, sizeof(gcb_cluster_stats), ctx->stream));
+        GCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // (the first batch may run on a caller's stream)
+    }
     {   // slow-column queue: a clean shallow library queues about 0.08 bytes per payload byte, a noisy one of depth 30 (1 % errors:
         // a third of its columns are slow) about 1.5, a vote whose every column is slow (options outside fast_path_implied) about
         // 4; deep families never use it (their tiles are decided in place); tiles whose columns do not fit are redone by the
@@ -343,6 +350,11 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         GCB_LAUNCH(duplex_kernel, dim3((unsigned)((2 * (int64_t)nc + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream, b, r, ws,
                    ctx->opt);
         ctx->launches++;
+        // ... and the Stats side effects of the clusters' verdicts
+        const unsigned stats_grid = (unsigned)((nc + STATS_THREADS - 1) / STATS_THREADS);
+        GCB_LAUNCH(cluster_stats_kernel, dim3(stats_grid < 4u * 148u ? stats_grid : 4u * 148u), dim3(STATS_THREADS), 0, stream, b, r, ws,
+                   (unsigned long long *)ctx->w_stats.p);
+        ctx->launches++;
     }
     GCB_CUDA(ctx, cudaGetLastError());
     return GCB_OK;
@@ -418,7 +430,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
     DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
-                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_need, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->w_sq_count, &ctx->w_sq_words, &ctx->w_sq_index,  &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
+                     &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_need, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->w_stats, &ctx->w_sq_count, &ctx->w_sq_words, &ctx->w_sq_index,  &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
                      &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status, &ctx->f_text, &ctx->f_anchor, &ctx->f_cnt, &ctx->f_hpos, &ctx->f_hbase,
                      &ctx->f_flag, &ctx->f_coff, &ctx->f_out};
@@ -797,6 +809,17 @@ int gcb_set_debug(gcb_ctx *ctx, int key, int value) {
 int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes) {
     if (!ctx || bytes < 0) return GCB_ERR_ARG;
     ctx->slow_queue_bytes = bytes;
+    return GCB_OK;
+}
+
+int gcb_get_cluster_stats(gcb_ctx *ctx, gcb_cluster_stats *out, int reset) {
+    if (!ctx || !out) return GCB_ERR_ARG;
+    memset(out, 0, sizeof *out);
+    if (!ctx->w_stats.p) return GCB_OK;  // nothing processed yet
+    GCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    GCB_CUDA(ctx, cudaMemcpyAsync(out, ctx->w_stats.p, sizeof *out, cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) GCB_CUDA(ctx, cudaMemsetAsync(ctx->w_stats.p, 0, sizeof *out, ctx->stream));
+    GCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return GCB_OK;
 }
 

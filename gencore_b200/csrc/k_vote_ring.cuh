@@ -33,7 +33,13 @@
 
 namespace gcb {
 
-constexpr int VR_THREADS = 512;    // warp 0 produces, fifteen warps vote (128 registers per thread)
+#ifndef GCB_VR_THREADS
+#define GCB_VR_THREADS 512
+#endif
+#ifndef GCB_VR_UNROLL
+#define GCB_VR_UNROLL 0  // read-loop unrolling: 0 = the compiler's choice
+#endif
+constexpr int VR_THREADS = GCB_VR_THREADS;  // warp 0 produces, fifteen warps vote (128 registers per thread)
 constexpr int VR_WARPS = VR_THREADS / WARP;
 constexpr int VR_VOTERS = VR_WARPS - 1;
 constexpr int VR_MAX_STAGES = 16;  // tiles in flight (barrier pairs and stage headers); their bytes come from one ring-buffer arena
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     // the batch's largest tile (tile_prep2_kernel measured it) decides how the voters are organised: small tiles -> many in
     // flight -> three groups of five warps; tiles that fill the arena -> all fifteen warps on every tile
     const int32_t largest = (int32_t)ring_round128((uint32_t)max(*max_need, 128));
-    const int n_groups = arena_bytes >= 6 * largest ? VR_GROUPS : 1, wpg = VR_VOTERS / n_groups;
+    const int n_groups = (arena_bytes >= 6 * largest && VR_VOTERS % VR_GROUPS == 0) ? VR_GROUPS : 1, wpg = VR_VOTERS / n_groups;
     const int n_stages = VR_MAX_STAGES;
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
@@ -317,6 +323,11 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     const uint32_t a0 = lds32<0>(qt + mdelta), c0 = lds32<4>(qt + mdelta), e0 = lds32<8>(qt + mdelta);  // its mate's
                     uint32_t d0 = 0u, d1 = 0u, da = 0u, dc = 0u, de = 0u;
                     uint32_t ea = sbase + (uint32_t)ento;
+#if GCB_VR_UNROLL == 1
+#pragma unroll 1
+#elif GCB_VR_UNROLL == 2
+#pragma unroll 2
+#endif
                     for (int e = 0; e < mmax; e += 2, ea += 32) {
                         uint32_t xa = lds16<0>(ea), xb = lds16<16>(ea);
                         xa = (e < m && xa != VR_NO_VOTE) ? xa : xt;  // reads that do not vote are replaced by the template's own

@@ -24,7 +24,7 @@ DEFAULT_LIB = os.path.join(HERE, "csrc", "libgencore_b200.so")
 # every symbol include/gencore_b200.h declares
 ABI_SYMBOLS = ["gcb_abi_version", "gcb_default_options", "gcb_create", "gcb_destroy", "gcb_last_error", "gcb_set_reference",
                "gcb_set_reference_device", "gcb_consensus_batch", "gcb_consensus_batch_device", "gcb_batch_status",
-               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_debug", "gcb_set_slow_queue_bytes", "gcb_pack_fasta", "gcb_host_alloc", "gcb_host_free"]
+               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_debug", "gcb_set_slow_queue_bytes", "gcb_get_cluster_stats", "gcb_pack_fasta", "gcb_host_alloc", "gcb_host_free"]
 
 
 class EngineError(RuntimeError):
@@ -34,7 +34,7 @@ class EngineError(RuntimeError):
 
 
 def load_library(path: Optional[str] = None) -> C.CDLL:
-    path = path or DEFAULT_LIB
+    path = path or os.environ.get("GENCORE_B200_LIB") or DEFAULT_LIB  # (the variable: measuring a differently built library)
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} is missing: build it with `python -m gencore_b200.build` (there is no CPU fallback)")
     lib = C.CDLL(path)
@@ -59,6 +59,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gcb_extract_umi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.gcb_set_slow_queue_bytes.restype = C.c_int
     lib.gcb_set_slow_queue_bytes.argtypes = [C.c_void_p, C.c_int64]
+    lib.gcb_get_cluster_stats.restype = C.c_int
+    lib.gcb_get_cluster_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.gcb_pack_fasta.restype = C.c_int
     lib.gcb_pack_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
@@ -177,6 +179,17 @@ class ConsensusEngine:
     def set_slow_queue_bytes(self, nbytes: int) -> None:
         """Bytes of the slow-column queue (tuning / tests: tiles whose columns do not fit are voted by the generic kernel)."""
         self._check(self.lib.gcb_set_slow_queue_bytes(self._ctx, nbytes))
+
+    def cluster_stats(self, reset: bool = True):
+        """What Cluster::clusterByUMI added to preStats / postStats for every cluster processed since the last reset
+        (gcb_cluster_stats, summed on the device): a hoststats.ClusterStats."""
+        from .hoststats import MAX_SUPPORTING_READS, ClusterStats
+        raw = np.zeros(10 + MAX_SUPPORTING_READS, np.int64)
+        self._check(self.lib.gcb_get_cluster_stats(self._ctx, raw.ctypes.data, 1 if reset else 0))
+        v = [int(x) for x in raw[:10]]
+        return ClusterStats(pre_cluster=v[0], pre_multi_cluster=v[1], pre_molecule=v[2], pre_molecule_se=v[3], pre_molecule_pe=v[4],
+                            pre_uncounted=v[5], pre_hist=raw[10:].copy(), post_cluster=v[6], post_multi_cluster=v[7], post_sscs=v[8],
+                            post_dcs=v[9])
 
     def batch_status(self, stream: int = 0) -> int:
         return self.lib.gcb_batch_status(self._ctx, C.c_void_p(stream))

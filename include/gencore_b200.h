@@ -236,6 +236,19 @@ int gcb_set_debug(gcb_ctx *ctx, int key, int value);
  * Tiles whose slow columns do not fit are voted by the generic kernel; results do not depend on it. */
 int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes);
 
+/* What Cluster::clusterByUMI adds to preStats and postStats (cluster.cpp:102,136,143,157,161,172,176,184-186 calling
+ * Stats::addCluster / addMolecule / addSSCS / addDCS, stats.cpp:122-141), summed on the device over every cluster this context
+ * has processed with GCB_STAGE_DUPLEX since the last reset.  The counters are additive: ranks sum them with one all-reduce. */
+#define GCB_MAX_SUPPORTING_READS 100 /* stats.h:15 */
+typedef struct gcb_cluster_stats {
+    int64_t pre_cluster, pre_multi_cluster;                              /* preStats->addCluster */
+    int64_t pre_molecule, pre_molecule_se, pre_molecule_pe, pre_uncounted; /* preStats->addMolecule; uncounted: >= 100 supporting reads */
+    int64_t post_cluster, post_multi_cluster, post_sscs, post_dcs;       /* postStats->addCluster / addSSCS / addDCS */
+    int64_t pre_hist[GCB_MAX_SUPPORTING_READS];                          /* Stats::mSupportingHistgram */
+} gcb_cluster_stats;
+/* Waits for the context's stream, copies the counters to *out and, with reset != 0, zeroes them. */
+int gcb_get_cluster_stats(gcb_ctx *ctx, gcb_cluster_stats *out, int reset);
+
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t gcb_launch_count(const gcb_ctx *ctx);
 

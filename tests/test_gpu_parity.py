@@ -92,6 +92,22 @@ def test_lanes_per_cluster_do_not_change_results(engine_cls, oracle, name, lanes
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} lanes {lanes}")
 
 
+@pytest.mark.parametrize("name", ["cfg2_40k", "cfg3_40k", "cfg4_40k", "ragged_duplex_5_big", "edge_strict", "deep_1100"])
+def test_cluster_stats_kernel_matches_the_host_replay(engine_cls, name):
+    """cluster_stats_kernel (gcb_get_cluster_stats) against hoststats, the replay pinned to the reference's Stats in tests/parity.py."""
+    import dataclasses
+    from gencore_b200.hoststats import stats_from_result
+    batch, genome, opt = dict(CASES)[name]()
+    with engine_cls(opt, 0) as eng:
+        eng.set_reference(genome)
+        eng.set_chunk_bytes(1 << 20)
+        res = eng.cluster_by_umi(batch)
+        got = eng.cluster_stats()
+    want = stats_from_result(batch, res)
+    for f in dataclasses.fields(got):
+        assert np.array_equal(getattr(got, f.name), getattr(want, f.name)), (name, f.name, getattr(got, f.name), getattr(want, f.name))
+
+
 @pytest.mark.parametrize("qbytes", [1 << 14, 1 << 20])
 @pytest.mark.parametrize("name", ["cfg2_40k", "ragged_duplex_5_big", "cfg4_40k", "edge_strict", "deep50_noisy_40k"])
 def test_slow_queue_overflow_does_not_change_results(engine_cls, oracle, name, qbytes):

@@ -117,6 +117,35 @@ def test_lanes_per_cluster_do_not_change_results(simt_lib, oracle, name, lanes):
     assert_results_equal(batch, res, oracle.consensus(batch, genome, opt), f"{name} lanes {lanes}")
 
 
+def assert_stats_equal(a, b, what):
+    import dataclasses
+    import numpy as np
+    for f in dataclasses.fields(a):
+        x, y = getattr(a, f.name), getattr(b, f.name)
+        assert np.array_equal(x, y), f"{what}: {f.name} {x} vs {y}"
+
+
+@pytest.mark.parametrize("name", ["golden_cfg2_600", "golden_cfg3_600", "golden_cfg4_600", "edge_default", "edge_strict", "ragged_duplex_2",
+                                  "deep_1100", "empty", "cfg3_1500"])
+def test_cluster_stats_kernel_matches_the_host_replay(simt_lib, name):
+    """cluster_stats_kernel: the Stats side effects of clusterByUMI (cluster.cpp:102-186) summed on the device; hoststats is the
+    numpy replay that tests/parity.py::assert_matches_reference pins against the reference's own Stats objects."""
+    from gencore_b200.engine import ConsensusEngine
+    from gencore_b200.hoststats import stats_from_result
+    batch, genome, opt = dict(CASES)[name]()
+    with ConsensusEngine(opt, 0, lib_path=simt_lib) as eng:
+        eng.set_reference(genome)
+        eng.set_chunk_bytes(1 << 15)  # several chunks: the counters are sums
+        res = eng.cluster_by_umi(batch)
+        got = eng.cluster_stats()
+        assert_stats_equal(got, stats_from_result(batch, res), name)
+        # the reset worked, and two batches add up
+        eng.cluster_by_umi(batch)
+        eng.cluster_by_umi(batch)
+        twice = eng.cluster_stats()
+    assert twice.pre_molecule == 2 * got.pre_molecule and twice.post_sscs == 2 * got.post_sscs and (twice.pre_hist == 2 * got.pre_hist).all()
+
+
 @pytest.mark.parametrize("what", ["slab_misaligned", "pair_off_not_monotone", "data_off_unaligned", "cigar_out_of_range", "record_outside_slab"])
 def test_malformed_batches_are_refused(simt_lib, what):
     """A batch that breaks a documented precondition comes back as GCB_ERR_MALFORMED (no fault, no hang)."""
