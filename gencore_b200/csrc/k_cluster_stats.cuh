@@ -13,12 +13,17 @@ constexpr int STATS_THREADS = 256;
 enum { ST_PRE_CLUSTER = 0, ST_PRE_MULTI, ST_PRE_MOLECULE, ST_PRE_SE, ST_PRE_PE, ST_PRE_UNCOUNTED, ST_POST_CLUSTER, ST_POST_MULTI, ST_POST_SSCS,
        ST_POST_DCS, ST_HIST0 };
 
-GCB_DEV void stats_add(unsigned long long *acc, int k, int v) {
+GCB_DEV void stats_add(int *cta_counters, int k, int v) {  // (the CTA's share: shared memory, flushed once per CTA)
     const int s = __reduce_add_sync(FULL, v);
-    if (lane_id() == 0 && s != 0) atomicAdd(acc + k, (unsigned long long)s);
+    if (lane_id() == 0 && s != 0) atomicAdd(cta_counters + k, s);
 }
 
 __global__ void __launch_bounds__(STATS_THREADS) cluster_stats_kernel(BatchView b, ResultView r, Workspace ws, unsigned long long *acc) {
+    __shared__ int s_cnt[ST_HIST0 + GCB_MAX_SUPPORTING_READS];  // the CTA's share of the counters and of Stats::mSupportingHistgram (a few
+                                                                // hot words: thousands of global atomics on them would serialise)
+    int *s_hist = s_cnt + ST_HIST0;
+    for (int i = (int)threadIdx.x; i < ST_HIST0 + GCB_MAX_SUPPORTING_READS; i += (int)blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
     if (batch_is_malformed(ws.error_flag)) return;
     const int n_round = (b.n_clusters + WARP - 1) / WARP * WARP;  // whole warps take part in the reductions
     for (int c = (int)(blockIdx.x * blockDim.x + threadIdx.x); c < n_round; c += (int)(gridDim.x * blockDim.x)) {
@@ -36,7 +41,7 @@ __global__ void __launch_bounds__(STATS_THREADS) cluster_stats_kernel(BatchView 
                     int supporting = gr->merge_reads;
                     if (gr->duplex_partner >= 0) supporting += g0[gr->duplex_partner].merge_reads;  // cluster.cpp:136,157
                     if (gr->tmpl_read[0] >= 0 && gr->tmpl_read[1] >= 0) pe++;
-                    if ((unsigned)supporting < (unsigned)GCB_MAX_SUPPORTING_READS) atomicAdd(acc + ST_HIST0 + supporting, 1ull);  // stats.cpp:124-127
+                    if ((unsigned)supporting < (unsigned)GCB_MAX_SUPPORTING_READS) atomicAdd(&s_hist[supporting], 1);  // stats.cpp:124-127
                     else uncounted++;
                 }
                 if (st == GCB_GROUP_SSCS) sscs++;
@@ -44,17 +49,20 @@ __global__ void __launch_bounds__(STATS_THREADS) cluster_stats_kernel(BatchView 
             }
             kept = sscs + dcs;
         }
-        stats_add(acc, ST_PRE_CLUSTER, have ? 1 : 0);
-        stats_add(acc, ST_PRE_MULTI, pre_multi);
-        stats_add(acc, ST_PRE_MOLECULE, mol);
-        stats_add(acc, ST_PRE_PE, pe);
-        stats_add(acc, ST_PRE_SE, mol - pe);
-        stats_add(acc, ST_PRE_UNCOUNTED, uncounted);
-        stats_add(acc, ST_POST_CLUSTER, kept > 0 ? 1 : 0);  // cluster.cpp:184-186
-        stats_add(acc, ST_POST_MULTI, kept > 1 ? 1 : 0);
-        stats_add(acc, ST_POST_SSCS, sscs);
-        stats_add(acc, ST_POST_DCS, dcs);
+        stats_add(s_cnt, ST_PRE_CLUSTER, have ? 1 : 0);
+        stats_add(s_cnt, ST_PRE_MULTI, pre_multi);
+        stats_add(s_cnt, ST_PRE_MOLECULE, mol);
+        stats_add(s_cnt, ST_PRE_PE, pe);
+        stats_add(s_cnt, ST_PRE_SE, mol - pe);
+        stats_add(s_cnt, ST_PRE_UNCOUNTED, uncounted);
+        stats_add(s_cnt, ST_POST_CLUSTER, kept > 0 ? 1 : 0);  // cluster.cpp:184-186
+        stats_add(s_cnt, ST_POST_MULTI, kept > 1 ? 1 : 0);
+        stats_add(s_cnt, ST_POST_SSCS, sscs);
+        stats_add(s_cnt, ST_POST_DCS, dcs);
     }
+    __syncthreads();
+    for (int i = (int)threadIdx.x; i < ST_HIST0 + GCB_MAX_SUPPORTING_READS; i += (int)blockDim.x)
+        if (s_cnt[i] != 0) atomicAdd(acc + i, (unsigned long long)s_cnt[i]);
 }
 
 }  // namespace gcb

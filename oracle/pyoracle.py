@@ -25,7 +25,7 @@ REF_BIN = os.path.join(HERE, "_ref", "gencore")
 
 def build(port: bool = True, ref: bool = True) -> None:
     """make -C oracle (the ref target is a no-op when /root/reference is absent)."""
-    targets = (["port"] if port else []) + (["ref"] if ref else [])
+    targets = (["port"] if port else []) + (["ref", "bridge"] if ref else [])  # bridge: the reference bound to the C ABI (integration/)
     subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
 
 
