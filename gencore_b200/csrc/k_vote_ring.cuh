@@ -122,7 +122,11 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     // the batch's largest tile (tile_prep2_kernel measured it) decides how the voters are organised: small tiles -> many in
     // flight -> three groups of five warps; tiles that fill the arena -> all fifteen warps on every tile
     const int32_t largest = (int32_t)ring_round128((uint32_t)max(*max_need, 128));
+    #ifdef GCB_VR_FORCE_GROUPS
+    const int n_groups = (arena_bytes >= GCB_VR_FORCE_GROUPS * largest && VR_VOTERS % VR_GROUPS == 0) ? VR_GROUPS : 1, wpg = VR_VOTERS / n_groups;
+#else
     const int n_groups = (arena_bytes >= 6 * largest && VR_VOTERS % VR_GROUPS == 0) ? VR_GROUPS : 1, wpg = VR_VOTERS / n_groups;
+#endif
     const int n_stages = VR_MAX_STAGES;
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {

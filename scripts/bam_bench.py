@@ -1,6 +1,7 @@
 """BAM-to-BAM wall time of the host pipeline (gencore_b200/bin/gencore_b200 + libgencore_b200.so on cuda:0) next to the
-unmodified reference binary (oracle/_ref/gencore, one core) on the same synthetic cfg2-shaped BAM; checks the outputs
-match.  Not the bench.py metric (that is the hot path behind the C ABI): this is the whole tool, BGZF included."""
+unmodified reference binary (oracle/_ref/gencore, one core) and to the reference bound to the C ABI (oracle/_ref/gencore_bridged,
+integration/gcbbridge.h: the reference's own host code, the engine for Cluster::clusterByUMI) on the same synthetic cfg2-shaped
+BAM; checks the outputs match.  Not the bench.py metric (that is the hot path behind the C ABI): this is the whole tool, BGZF included."""
 import dataclasses, json, os, subprocess, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -17,16 +18,22 @@ with tempfile.TemporaryDirectory() as td:
     n_rec = bamfile.batch_to_bam(bam, batch, genome)
     res = {}
     for tag, cmd in (("reference", [pyoracle.REF_BIN, "-i", bam, "-o", os.path.join(td, "ref.bam"), "-r", fa, "-j", os.path.join(td, "r.json"), "-h", os.path.join(td, "r.html")]),
+                     ("bridged", [os.path.join(os.path.dirname(pyoracle.REF_BIN), "gencore_bridged"), "-i", bam, "-o", os.path.join(td, "bridged.bam"), "-r", fa,
+                                  "-j", os.path.join(td, "b.json"), "-h", os.path.join(td, "b.html")]),
                      ("b200", [gbuild.build_cli(), "-i", bam, "-o", os.path.join(td, "b200.bam"), "-r", fa])):
+        if not os.path.exists(cmd[0]):
+            continue
         best = None
         for rep in range(2):
             t = time.perf_counter()
-            p = subprocess.run(cmd, capture_output=True, text=True, cwd=td)
+            p = subprocess.run(cmd, capture_output=True, text=True, cwd=td, env=dict(os.environ, GENCORE_B200_ENGINE=gbuild.LIB))
             dt = time.perf_counter() - t
             assert p.returncode == 0, p.stderr[-1500:]
             best = dt if best is None else min(best, dt)
         res[tag] = best
     n_out = bamfile.assert_same_bam(os.path.join(td, "ref.bam"), os.path.join(td, "b200.bam"))
+    if "bridged" in res:
+        assert bamfile.assert_same_bam(os.path.join(td, "ref.bam"), os.path.join(td, "bridged.bam")) == n_out
     print(json.dumps({"what": "BAM-to-BAM wall time, cfg2 shape", "pairs": n_pairs, "records_in": n_rec, "records_out": n_out, "identical_output": True,
-                      "reference_s": res["reference"], "b200_s": res["b200"], "reference_pairs_per_s": n_pairs / res["reference"],
-                      "b200_pairs_per_s": n_pairs / res["b200"], "bam_bytes": os.path.getsize(bam)}))
+                      "reference_s": res["reference"], "bridged_reference_s": res.get("bridged"), "b200_s": res["b200"],
+                      "reference_pairs_per_s": n_pairs / res["reference"], "b200_pairs_per_s": n_pairs / res["b200"], "bam_bytes": os.path.getsize(bam)}))

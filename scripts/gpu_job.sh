@@ -1,6 +1,6 @@
 #!/bin/bash
-# One gpurun call of round 2: parity tests, the bench line, other shapes, a launch list and an ncu capture of the ring kernel.
-#   gpurun --timeout 2400 -- 'bash scripts/gpu_job.sh <tag> [tests|notests]'
+# One gpurun call of round 2: parity tests, the bench line, other shapes, a launch list, ncu captures of the main kernels, the BAM-to-BAM tools.
+#   gpurun --timeout 2400 -- 'bash scripts/gpu_job.sh <tag> [tests|notests] [full]'
 tag=${1:-r2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi_$tag.txt 2>&1
@@ -17,3 +17,12 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 4
   python bench.py --steps 2 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/launches_$tag.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:vote_ring -s 3 -c 1 -o gpurun_out/prof_ring_$tag \
   python bench.py --steps 1 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/ncu_ring_$tag.log 2>&1
+if [ "${3:-}" = "full" ]; then
+  for k in select_template slow_columns umi_group duplex_kernel tile_prep2; do
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -o gpurun_out/prof_${k}_$tag \
+      python bench.py --steps 1 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/ncu_${k}_$tag.log 2>&1
+  done
+  timeout 600 python scripts/bam_bench.py 300000 > gpurun_out/bam_bench_$tag.json 2> gpurun_out/bam_bench_$tag.err
+  cat gpurun_out/bam_bench_$tag.json
+fi
+ls -la gpurun_out | tail -5
