@@ -253,44 +253,57 @@ GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const Genome
         const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
         const int mpi = mvalid ? mp : 0;
         const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
-        // eight reads at a time, in two waves of independent loads (where their records lie, then their bytes): a column decided
-        // from global memory waits for two round trips per eight reads instead of two per read
-        for (int e0 = 0; e0 < m; e0 += 8) {
-            uint32_t w[8], x[8];
+        // eight reads at a time, in two waves of independent loads (where their records lie, then their bytes)
+        auto walk = [&](auto &acc) {
+            for (int e0 = 0; e0 < m; e0 += 8) {
+                uint32_t w[8], x[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) w[u] = e0 + u < m ? *(const uint32_t *)(ents + e0 + u) : (uint32_t)VR_NO_VOTE;  // own_off4 | mate_off4 << 16
+                for (int u = 0; u < 8; u++) w[u] = e0 + u < m ? *(const uint32_t *)(ents + e0 + u) : (uint32_t)VR_NO_VOTE;  // own_off4 | mate_off4 << 16
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                x[u] = 0u;
-                if ((w[u] & 0xFFFFu) != VR_NO_VOTE) {
-                    const uint8_t *rec = cb + 4 * (int)(w[u] & 0xFFFFu);
-                    x[u] = (uint32_t)rec[col] | ((uint32_t)rec[soff] << 8);
-                    if (mvalid) {
-                        const uint8_t *mrec = cb + 4 * (int)(w[u] >> 16);
-                        x[u] |= ((uint32_t)mrec[mpi] << 16) | ((uint32_t)mrec[msoff] << 24);
+                for (int u = 0; u < 8; u++) {
+                    x[u] = 0u;
+                    if ((w[u] & 0xFFFFu) != VR_NO_VOTE) {
+                        const uint8_t *rec = cb + 4 * (int)(w[u] & 0xFFFFu);
+                        x[u] = (uint32_t)rec[col] | ((uint32_t)rec[soff] << 8);
+                        if (mvalid) {
+                            const uint8_t *mrec = cb + 4 * (int)(w[u] >> 16);
+                            x[u] |= ((uint32_t)mrec[mpi] << 16) | ((uint32_t)mrec[msoff] << 24);
+                        }
                     }
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                if ((w[u] & 0xFFFFu) == VR_NO_VOTE) continue;
-                int ql = (int)(x[u] & 0xFFu);
-                const int base = (int)((x[u] >> (8 + nsh)) & 0xFu);
-                int score;
-                if (mvalid) {
-                    const int mql = (int)((x[u] >> 16) & 0xFFu);
-                    const int mbase = (int)((x[u] >> (24 + mnsh)) & 0xFu);
-                    const int lq = side == 0 ? ql : mql, rq = side == 0 ? mql : ql;
-                    const bool mine = side == 0 ? lq >= rq : !(lq >= rq);
-                    const int s_match = sc8(tab.q2s((ql + mql) / 2) + 4);                        // pair.cpp:147-152
-                    const int s_mis = mine ? sc8(tab.q2s(lq >= rq ? lq - rq : rq - lq) - 3) : 0;  // pair.cpp:153-169
-                    score = base == mbase ? s_match : s_mis;
-                    ql = base == mbase ? ql : max(0, ql - mql);
-                } else {
-                    score = plain ? tab.q2s(ql) : tab.sm;
+                for (int u = 0; u < 8; u++) {
+                    if ((w[u] & 0xFFFFu) == VR_NO_VOTE) continue;
+                    int ql = (int)(x[u] & 0xFFu);
+                    const int base = (int)((x[u] >> (8 + nsh)) & 0xFu);
+                    int score;
+                    if (mvalid) {
+                        // pair.cpp:147-169 with one qual2score: of the mean quality when the mates agree (+4), of the difference
+                        // when they do not (-3 for the better read, nothing for the other, whose quality is rewritten)
+                        const int mql = (int)((x[u] >> 16) & 0xFFu);
+                        const int mbase = (int)((x[u] >> (24 + mnsh)) & 0xFu);
+                        const bool match = base == mbase, ge = ql >= mql;
+                        const bool mine = side == 0 ? ge : (mql < ql);  // left read wins ties
+                        const int sc = tab.q2s(match ? (ql + mql) >> 1 : ge ? ql - mql : mql - ql);
+                        score = match ? sc8(sc + 4) : mine ? sc8(sc - 3) : 0;
+                        ql = match ? ql : max(0, ql - mql);
+                    } else {
+                        score = plain ? tab.q2s(ql) : tab.sm;
+                    }
+                    acc.add(base, ql, score);
                 }
-                bins.add(base, ql, score);
             }
+        };
+        // most slow columns show two codes: a two-bin histogram first, the three-bin one when a third code turns up
+        Bins2 two;
+        two.init();
+        walk(two);
+        if (!two.overflow) {
+            bins.b0 = two.bA; bins.c0 = two.cA; bins.s0 = two.sA; bins.q0 = two.qA; bins.x0 = two.xA;
+            bins.b1 = two.bB; bins.c1 = two.cB; bins.s1 = two.sB; bins.q1 = two.qB; bins.x1 = two.xB;
+            bins.total = two.total;
+        } else {
+            walk(bins);
         }
     } else {
         for (int e = 0; e < m; e++) {

@@ -79,6 +79,10 @@ constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MA
 constexpr int VR_OFF_HDR = 16 * VR_MAX_STAGES;                   // RingStage[VR_MAX_STAGES]
 constexpr int VR_OFF_HCACHE = VR_OFF_HDR + 96 * VR_MAX_STAGES;   // TileHdr2[32]: the producer's next tiles
 constexpr int VR_ITEMS = 64;       // slow columns of one bundle that are emitted per round
+#ifndef GCB_VR_DEEP_CHUNK
+#define GCB_VR_DEEP_CHUNK 32
+#endif
+constexpr int VR_DEEP_CHUNK = GCB_VR_DEEP_CHUNK;  // slow columns of a deep tile a warp takes at a time (a tile has a few hundred for fifteen warps)
 #ifndef GCB_VR_GROUP
 #define GCB_VR_GROUP 4
 #endif
@@ -592,11 +596,11 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             const int64_t out_base0 = sh->out_base0;
             for (;;) {
                 int c0 = 0;
-                if (lane == 0) c0 = atomicAdd(&sh->next_col, WARP);
+                if (lane == 0) c0 = atomicAdd(&sh->next_col, VR_DEEP_CHUNK);
                 c0 = __shfl_sync(FULL, c0, 0);
                 if (c0 >= total) break;
                 const int idx = c0 + lane;
-                if (idx < total) {
+                if (lane < VR_DEEP_CHUNK && idx < total) {
                     int lo = 0, hi = n - 1;
                     while (lo < hi) {  // the first entry whose inclusive column count exceeds idx
                         const int mid = (lo + hi) >> 1;

@@ -382,7 +382,10 @@ GCB_DEV ChunkMasks make_masks(int l_out, int len, int col0) {
 // compacted with ballots (no shared memory, no CTA barrier); many tiles per SM keep their chains of dependent loads
 // (directory -> side modes -> family-side descriptors -> cluster offsets) in flight at once.  `max_need`: the largest
 // shared-memory allocation a tile of this view takes in the vote kernel.
-GCB_HD bool tile_is_deep(int32_t nfs, int32_t np) { return nfs > 0 && 2 * np >= 24 * nfs; }  // 24 pairs or more per family side on average
+#ifndef GCB_VT_DEEP
+#define GCB_VT_DEEP 24
+#endif
+GCB_HD bool tile_is_deep(int32_t nfs, int32_t np) { return nfs > 0 && 2 * np >= GCB_VT_DEEP * nfs; }  // 24 pairs or more per family side on average
 GCB_HD int32_t tile_smem_need(int32_t nfs, int32_t np, int32_t slab_bytes, int32_t lanes) {
     // family-side list, VoteRead table, slab + slack; a deep tile also its slow-column list and the list's prefix sums (one entry
     // per family side and lane)
