@@ -19,6 +19,7 @@ GCB_DEV void stats_add(int *cta_counters, int k, int v) {  // (the CTA's share: 
 }
 
 __global__ void __launch_bounds__(STATS_THREADS) cluster_stats_kernel(BatchView b, ResultView r, Workspace ws, unsigned long long *acc) {
+    GCB_GRID_DEP();
     __shared__ int s_cnt[ST_HIST0 + GCB_MAX_SUPPORTING_READS];  // the CTA's share of the counters and of Stats::mSupportingHistgram (a few
                                                                 // hot words: thousands of global atomics on them would serialise)
     int *s_hist = s_cnt + ST_HIST0;

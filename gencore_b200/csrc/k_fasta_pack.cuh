@@ -71,6 +71,7 @@ GCB_DEV int64_t fa_block_scan(int64_t v, int64_t *s_warp, int64_t &block_total) 
 
 // K1: the last line start of every block
 __global__ void __launch_bounds__(FA_THREADS) fa_anchor_kernel(FaView v, int64_t *blk_anchor) {
+    GCB_GRID_DEP();
     __shared__ int64_t s_warp[FA_THREADS / WARP];
     const int64_t q0 = (int64_t)blockIdx.x * FA_BLOCK + (int64_t)threadIdx.x * FA_PER_THREAD;
     int64_t a = -1;
@@ -94,6 +95,7 @@ GCB_DEV int64_t fa_shift_right(int64_t incl, int64_t id) {
 // K2 / K4: exclusive scan of the block aggregates, one CTA (nv values per block, interleaved); totals behind the last block
 template <typename Op>
 __global__ void __launch_bounds__(FA_THREADS) fa_scan_kernel(int64_t *blk, int64_t n_blocks, int nv) {
+    GCB_GRID_DEP();
     __shared__ int64_t s_warp[FA_THREADS / WARP];
     for (int j = 0; j < nv; j++) {
         int64_t carry = Op::id();
@@ -158,6 +160,7 @@ GCB_DEV int64_t fa_thread_anchor(const FaView &v, int64_t q0, int64_t blk_in, in
 
 // K3: bases and headers of every block
 __global__ void __launch_bounds__(FA_THREADS) fa_count_kernel(FaView v, const int64_t *blk_anchor_in, int64_t *blk_cnt) {
+    GCB_GRID_DEP();
     __shared__ int64_t s_warp[FA_THREADS / WARP];
     const int64_t q0 = (int64_t)blockIdx.x * FA_BLOCK + (int64_t)threadIdx.x * FA_PER_THREAD;
     const int64_t anchor = fa_thread_anchor(v, q0, blk_anchor_in[blockIdx.x], s_warp);
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(FA_THREADS) fa_count_kernel(FaView v, const in
 // reference reads as something else (">\n", ">>", '>' as the last byte)
 __global__ void __launch_bounds__(FA_THREADS) fa_header_kernel(FaView v, const int64_t *blk_anchor_in, const int64_t *blk_cnt_in, int64_t *hdr_pos,
                                                                int64_t *hdr_base, int32_t max_contigs, int32_t *flag) {
+    GCB_GRID_DEP();
     __shared__ int64_t s_warp[FA_THREADS / WARP];
     const int64_t q0 = (int64_t)blockIdx.x * FA_BLOCK + (int64_t)threadIdx.x * FA_PER_THREAD;
     const int64_t anchor = fa_thread_anchor(v, q0, blk_anchor_in[blockIdx.x], s_warp);
@@ -201,6 +205,7 @@ __global__ void __launch_bounds__(FA_THREADS) fa_header_kernel(FaView v, const i
 // K6: the nibbles.  out32: the packed genome as 32-bit words, zeroed; contig_off: byte offset of every contig in it
 __global__ void __launch_bounds__(FA_THREADS) fa_pack_kernel(FaView v, const int64_t *blk_anchor_in, const int64_t *blk_cnt_in, const int64_t *hdr_base,
                                                              const int64_t *contig_off, int32_t n_contigs, uint32_t *out32) {
+    GCB_GRID_DEP();
     __shared__ int64_t s_warp[FA_THREADS / WARP];
     const int64_t q0 = (int64_t)blockIdx.x * FA_BLOCK + (int64_t)threadIdx.x * FA_PER_THREAD;
     const int64_t anchor = fa_thread_anchor(v, q0, blk_anchor_in[blockIdx.x], s_warp);

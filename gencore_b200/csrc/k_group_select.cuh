@@ -99,6 +99,7 @@ GCB_DEV int umit_diff(const UmiT<NW> &a, const UmiT<NW> &b) {  // Cluster::umiDi
 template <int NW, int GS>
 __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, ResultView r, Workspace ws, int32_t window_shift,
                                                                    int32_t n_tiles) {
+    GCB_GRID_DEP();
     const Grp<GS> g;
     const int lane = g.gl;
     const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (WARP / GS) + (lane_id() / GS);
@@ -660,6 +661,7 @@ GCB_DEV bool select_cluster_fast(const Grp<GS> &g, const BatchView &b, const Res
 // group.cpp:68-134 per family of the cluster + the per-pair overlap windows of pair.cpp:103-119
 template <int GS>
 __global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o) {
+    GCB_GRID_DEP();
     const Grp<GS> g;
     const int lane = g.gl;
     const int c = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (WARP / GS) + (lane_id() / GS);
@@ -846,6 +848,7 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = SCAN_BLOCK / SCAN_THREADS;
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_local_kernel(Workspace ws, int32_t n_clusters) {
+    GCB_GRID_DEP();
     __shared__ int64_t warp_tot[SCAN_THREADS / WARP];
     const int lane = lane_id(), warp = (int)(threadIdx.x >> 5);
     const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
@@ -875,6 +878,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_local_kernel(Workspace ws, 
 // `carry_in`: bytes emitted by the views that precede this one in out_payload (NULL = none)
 __global__ void __launch_bounds__(WARP) scan_blocks_kernel(Workspace ws, int32_t n_blocks, int64_t *out_bytes, int64_t out_capacity,
                                                            const int64_t *carry_in) {
+    GCB_GRID_DEP();
     const int lane = lane_id();
     int64_t carry = carry_in ? *carry_in : 0;
     for (int base = 0; base < n_blocks; base += WARP) {

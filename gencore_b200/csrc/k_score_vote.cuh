@@ -437,6 +437,7 @@ GCB_DEV void vote_family_side(const BatchView &b, const ResultView &r, const Wor
 }
 
 __global__ void __launch_bounds__(VOTE_THREADS) score_vote_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o) {
+    GCB_GRID_DEP();
     GCB_DYN_SMEM(smem);
     if (batch_is_malformed(ws.error_flag)) return;
     uint64_t *bar = (uint64_t *)smem;

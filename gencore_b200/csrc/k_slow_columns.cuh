@@ -227,6 +227,13 @@ GCB_DEV void finish_column(const BatchView &b, const ResultView &r, const Genome
     out[col] = (uint8_t)new_qual;
 }
 
+#ifndef GCB_DC_UNROLL
+#define GCB_DC_UNROLL 2  // (8: 2.20 ms, 4 and 2: 1.91 ms on the cfg4 shape: the smaller code wins)
+#endif
+#ifndef GCB_DC_TWO
+#define GCB_DC_TWO 0     // 1: two-bin histogram in the uniform walk, the general loop when a third code turns up (3.2 ms on the cfg4
+                         // shape against 1.9: with 50 reads at 1 % errors some lane of nearly every warp sees a third code)
+#endif
 // One column of a family side from its VoteRead entries `ents` and its cluster's slab `cb` (shared or global memory).
 GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const GenomeView &gv, const gcb_options &o, const RollbackList &rb,
                            const SlowSide &fs, const uint8_t *cb, const VoteRead *ents, uint8_t *out, int col) {
@@ -244,7 +251,12 @@ GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const Genome
     Bins3 bins;
     bins.init();
     const int m = fs.m;
+    bool general = true;
     if (fs.flags & FS_UNIFORM) {
+#if GCB_DC_TWO
+        Bins2 two;  // most slow columns show two codes
+        two.init();
+#endif
         const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
         const int k = col - (int)tv.ov_own, mp = (int)tv.ov_mate + k;
         const bool inwin = info && k >= 0 && k < (int)tv.ov_len;
@@ -253,59 +265,63 @@ GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const Genome
         const int soff = qbytes + (col >> 1), nsh = (col & 1) ? 0 : 4;
         const int mpi = mvalid ? mp : 0;
         const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
-        // eight reads at a time, in two waves of independent loads (where their records lie, then their bytes)
-        auto walk = [&](auto &acc) {
-            for (int e0 = 0; e0 < m; e0 += 8) {
-                uint32_t w[8], x[8];
+        // GCB_DC_UNROLL reads at a time, in two waves of independent loads (where their records lie, then their bytes).  ONE walk:
+        // a second instantiation (two-bin histogram first, three-bin on overflow) doubles the code of a function every voter
+        // warp of a deep tile enters, and measured 4.6 ms against 2.4 on the cfg4 shape (profiles/r03_notes.md).
+        for (int e0 = 0; e0 < m; e0 += GCB_DC_UNROLL) {
+            uint32_t w[GCB_DC_UNROLL], x[GCB_DC_UNROLL];
 #pragma unroll
-                for (int u = 0; u < 8; u++) w[u] = e0 + u < m ? *(const uint32_t *)(ents + e0 + u) : (uint32_t)VR_NO_VOTE;  // own_off4 | mate_off4 << 16
+            for (int u = 0; u < GCB_DC_UNROLL; u++) w[u] = e0 + u < m ? *(const uint32_t *)(ents + e0 + u) : (uint32_t)VR_NO_VOTE;  // own_off4 | mate_off4 << 16
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    x[u] = 0u;
-                    if ((w[u] & 0xFFFFu) != VR_NO_VOTE) {
-                        const uint8_t *rec = cb + 4 * (int)(w[u] & 0xFFFFu);
-                        x[u] = (uint32_t)rec[col] | ((uint32_t)rec[soff] << 8);
-                        if (mvalid) {
-                            const uint8_t *mrec = cb + 4 * (int)(w[u] >> 16);
-                            x[u] |= ((uint32_t)mrec[mpi] << 16) | ((uint32_t)mrec[msoff] << 24);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    if ((w[u] & 0xFFFFu) == VR_NO_VOTE) continue;
-                    int ql = (int)(x[u] & 0xFFu);
-                    const int base = (int)((x[u] >> (8 + nsh)) & 0xFu);
-                    int score;
+            for (int u = 0; u < GCB_DC_UNROLL; u++) {
+                x[u] = 0u;
+                if ((w[u] & 0xFFFFu) != VR_NO_VOTE) {
+                    const uint8_t *rec = cb + 4 * (int)(w[u] & 0xFFFFu);
+                    x[u] = (uint32_t)rec[col] | ((uint32_t)rec[soff] << 8);
                     if (mvalid) {
-                        // pair.cpp:147-169 with one qual2score: of the mean quality when the mates agree (+4), of the difference
-                        // when they do not (-3 for the better read, nothing for the other, whose quality is rewritten)
-                        const int mql = (int)((x[u] >> 16) & 0xFFu);
-                        const int mbase = (int)((x[u] >> (24 + mnsh)) & 0xFu);
-                        const bool match = base == mbase, ge = ql >= mql;
-                        const bool mine = side == 0 ? ge : (mql < ql);  // left read wins ties
-                        const int sc = tab.q2s(match ? (ql + mql) >> 1 : ge ? ql - mql : mql - ql);
-                        score = match ? sc8(sc + 4) : mine ? sc8(sc - 3) : 0;
-                        ql = match ? ql : max(0, ql - mql);
-                    } else {
-                        score = plain ? tab.q2s(ql) : tab.sm;
+                        const uint8_t *mrec = cb + 4 * (int)(w[u] >> 16);
+                        x[u] |= ((uint32_t)mrec[mpi] << 16) | ((uint32_t)mrec[msoff] << 24);
                     }
-                    acc.add(base, ql, score);
                 }
             }
-        };
-        // most slow columns show two codes: a two-bin histogram first, the three-bin one when a third code turns up
-        Bins2 two;
-        two.init();
-        walk(two);
-        if (!two.overflow) {
+#pragma unroll
+            for (int u = 0; u < GCB_DC_UNROLL; u++) {
+                if ((w[u] & 0xFFFFu) == VR_NO_VOTE) continue;
+                int ql = (int)(x[u] & 0xFFu);
+                const int base = (int)((x[u] >> (8 + nsh)) & 0xFu);
+                int score;
+                if (mvalid) {
+                    // pair.cpp:147-169 with one qual2score: of the mean quality when the mates agree (+4), of the difference
+                    // when they do not (-3 for the better read, nothing for the other, whose quality is rewritten)
+                    const int mql = (int)((x[u] >> 16) & 0xFFu);
+                    const int mbase = (int)((x[u] >> (24 + mnsh)) & 0xFu);
+                    const bool match = base == mbase, ge = ql >= mql;
+                    const bool mine = side == 0 ? ge : (mql < ql);  // left read wins ties
+                    const int sc = tab.q2s(match ? (ql + mql) >> 1 : ge ? ql - mql : mql - ql);
+                    score = match ? sc8(sc + 4) : mine ? sc8(sc - 3) : 0;
+                    ql = match ? ql : max(0, ql - mql);
+                } else {
+                    score = plain ? tab.q2s(ql) : tab.sm;
+                }
+#if GCB_DC_TWO
+                two.add(base, ql, score);
+#else
+                bins.add(base, ql, score);
+#endif
+            }
+        }
+#if GCB_DC_TWO
+        general = two.overflow;  // a third code: the general loop below builds the three-bin histogram
+        if (!general) {
             bins.b0 = two.bA; bins.c0 = two.cA; bins.s0 = two.sA; bins.q0 = two.qA; bins.x0 = two.xA;
             bins.b1 = two.bB; bins.c1 = two.cB; bins.s1 = two.sB; bins.q1 = two.qB; bins.x1 = two.xB;
             bins.total = two.total;
-        } else {
-            walk(bins);
         }
-    } else {
+#else
+        general = false;
+#endif
+    }
+    if (general) {
         for (int e = 0; e < m; e++) {
             int base, qual, score;
             if (fetch_vote(cb, ents[e], col, side, tab, base, qual, score)) bins.add(base, qual, score);
@@ -375,6 +391,7 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
 
 __global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o,
                                                                        SlowQueue sq, RollbackList rb) {
+    GCB_GRID_DEP();
     if (batch_is_malformed(ws.error_flag)) return;
     const uint32_t reserved = (uint32_t)(*sq.count >> 32), total = reserved < sq.cap_recs ? reserved : sq.cap_recs;
     const ScoreTab tab(o);

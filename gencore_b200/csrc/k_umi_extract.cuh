@@ -24,6 +24,7 @@ constexpr uint8_t UMI_TOO_LONG = 1;  // the UMI has more than 16*umi_words chara
 
 __global__ void __launch_bounds__(UMI_EXTRACT_THREADS) umi_extract_kernel(const char *names, const int64_t *name_off, int32_t n, UmiPrefix prefix,
                                                                           int32_t umi_words, uint64_t *out, uint8_t *status) {
+    GCB_GRID_DEP();
     const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (i >= n) return;
     const char *q = names + name_off[i];

@@ -116,6 +116,7 @@ __device__ __noinline__ void ring_slow_column(const RingCtx &x, int ft_off, int 
 __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o, int32_t implied,
                                                                    const TileHdr2 *hdr, const FsTile *fs_tiles, SlowQueue sq, RollbackList rb,
                                                                    int32_t n_tiles, int32_t arena_bytes, const int32_t *max_need) {
+    GCB_GRID_DEP();
     GCB_DYN_SMEM(smem);
     if (batch_is_malformed(ws.error_flag)) return;  // (every thread of the grid sees the same flag: the kernels that raise it have finished)
     uint64_t *full = (uint64_t *)(smem + VR_OFF_FULL);

@@ -396,6 +396,7 @@ GCB_HD int32_t tile_smem_need(int32_t nfs, int32_t np, int32_t slab_bytes, int32
 __global__ void __launch_bounds__(VS_PREP_THREADS) tile_prep2_kernel(BatchView b, ResultView r, Workspace ws, int32_t slab_cap, int32_t arena,
                                                                       TileHdr2 *hdr, FsTile *fs_tiles, int32_t *max_need, int32_t n_tiles,
                                                                       int32_t force_generic) {
+    GCB_GRID_DEP();
     const int lane = lane_id();
     const int tile = (int)(blockIdx.x * (VS_PREP_THREADS / WARP) + (threadIdx.x >> 5));
     if (tile >= n_tiles || batch_is_malformed(ws.error_flag)) return;
@@ -530,6 +531,7 @@ GCB_DEV void rollback_family_side(const BatchView &b, const ResultView &r, const
 
 __global__ void __launch_bounds__(VQ_FINAL_THREADS) vote_rollback_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o, RollbackList rb,
                                                                          int32_t p0, int32_t p1) {
+    GCB_GRID_DEP();
     if (batch_is_malformed(ws.error_flag)) return;
     const int n = *rb.count;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
