@@ -263,6 +263,36 @@ class ShapeRun:
         self.d2h = int(self.pr.pair_group.nbytes + self.pr.cluster_n_groups.nbytes + self.pr.groups.nbytes + 8 + 4 + int(self.pr.out_bytes[0]))
         return sec
 
+    def copy_ceiling(self, steps, barrier):
+        """seconds per step of the copies of e2e() ALONE: the same bytes host -> device from the same page-locked buffers on one
+        stream, the same bytes device -> host on another, no kernel.  With every rank doing it at once this is the ceiling the
+        box's host memory system and PCIe fabric put on `e2e` at this N."""
+        torch = self.torch
+        ins = [t for t in self.pb._pinned]
+        outs = [t for t in self.pr._pinned]
+        d_in = [torch.empty(t.numel(), dtype=torch.uint8, device=self.dev) for t in ins]
+        used = int(self.pr.out_bytes[0])
+        # (the result's record buffer is copied up to the bytes the batch produced, as gcb_consensus_batch does)
+        d_out = [torch.empty(t.numel(), dtype=torch.uint8, device=self.dev) for t in outs]
+        sizes_out = [min(t.numel(), used) if t.numel() >= self.cap else t.numel() for t in outs]
+        s_in, s_out = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
+
+        def step():
+            with torch.cuda.stream(s_in):
+                for h, d in zip(ins, d_in):
+                    d.copy_(h, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                for h, d, n in zip(outs, d_out, sizes_out):
+                    h[:n].copy_(d[:n], non_blocking=True)
+        for _ in range(2):
+            step()
+        barrier()
+        t = time.perf_counter()
+        for _ in range(steps):
+            step()
+        barrier()
+        return (time.perf_counter() - t) / steps
+
     def check_window(self, opt, n_clusters=3000):
         """After the timed region: a window of the timed batch against the oracle, bit for bit (the checker, never the thing measured)."""
         from gencore_b200.shard import slice_batch
@@ -279,7 +309,10 @@ class ShapeRun:
     def roofline(self, stage_ms, peak):
         vote_ms = float(stage_ms[3])
         whole_ms = float(stage_ms[2] + stage_ms[3] + stage_ms[4])
-        return vote_ms, whole_ms, self.alg["total"] / (vote_ms * 1e-3) / 1e9 / peak, self.alg["total"] / (whole_ms * 1e-3) / 1e9 / peak
+        # the ring kernel reads every read and writes every record; the reference slices are read by slow_columns_kernel, which
+        # belongs to the whole vote
+        ring_bytes = self.alg["reads_in"] + self.alg["consensus_out"]
+        return vote_ms, whole_ms, ring_bytes / (vote_ms * 1e-3) / 1e9 / peak, self.alg["total"] / (whole_ms * 1e-3) / 1e9 / peak
 
     def free(self):
         self.db = self.dr = self.pb = self.pr = None
@@ -335,6 +368,31 @@ def strong_scaling_leg(args, eng, torch, dist, dev, rank, world, barrier):
             "result_sha256": h.hexdigest(), "steps": args.strong_steps}
 
 
+def pin_to_gpu_numa_node(torch, local):
+    """Binds this rank's threads (and so its first-touch page-locked staging buffers) to the CPUs of the NUMA node its GPU hangs
+    off: with N ranks uploading at once the host's memory system is the shared resource (round 1: 44 GB/s per GPU alone, 16 GB/s
+    each at N = 8).  Returns what was done for the JSON line; never fails the run."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "the platform reports no NUMA node for the GPU"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return {"numa_node": node, "note": "none of the node's CPUs is available to this process"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:  # (containers without /sys, older torch: run unpinned)
+        return {"numa_node": None, "note": f"not pinned: {type(e).__name__}"}
+
+
 def b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -349,6 +407,7 @@ def b200_arm(args):
         raise SystemExit("bench.py: no CUDA device (the consensus engine has no CPU path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = pin_to_gpu_numa_node(torch, local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # (NCCL prints its version banner on stdout, which carries the one JSON line)
@@ -399,6 +458,11 @@ def b200_arm(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     clocks_e2e = sampler.stop() if sampler else None
+    ceil_s = run.copy_ceiling(max(3, args.steps), barrier)
+    if world > 1:
+        tt = torch.tensor([ceil_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ceil_s = float(tt.item())
     if args.host_sweep and rank == 0:  # tuning aid: end-to-end time by kind of host memory for the batch, to stderr
         from gencore_b200.device import pinned_copy
         for label, kw in (("torch pinned", None), ("gcb_host_alloc", dict(lib=eng.lib)), ("gcb_host_alloc write-combined", dict(lib=eng.lib, write_combined=True))):
@@ -477,12 +541,16 @@ def b200_arm(args):
                        "parity": parity},
             "roofline": {"bound": "hbm", "kernel": VOTE_KERNEL, "achieved": frac * peak, "peak": peak, "unit": "GB/s", "frac": frac,
                          "peak_source": peak_src, "traffic": args.traffic if args.traffic is not None else (measured_traffic(VOTE_KERNEL) if args.pairs == 1_000_000 else None),
-                         "algorithmic_bytes": alg, "kernel_ms": vote_ms,
+                         "algorithmic_bytes": {"reads_in": alg["reads_in"], "consensus_out": alg["consensus_out"], "reference_in": 0,
+                                               "total": alg["reads_in"] + alg["consensus_out"]}, "kernel_ms": vote_ms,
                          "timed": "CUDA events around every launch of %s on the launching stream, mean over the timed region" % VOTE_KERNEL,
-                         "whole_vote": {"kernels": "every launch of the vote (tile_prep2_kernel, %s, vote_rollback_kernel, score_vote_kernel)" % VOTE_KERNEL,
+                         "whole_vote": {"kernels": "every launch of the vote (tile_prep2_kernel, %s, slow_columns_kernel, vote_rollback_kernel, score_vote_kernel)" % VOTE_KERNEL,
                                         "ms": whole_ms, "algorithmic_bytes": alg["total"], "achieved": whole_frac * peak, "frac": whole_frac}},
             "e2e": {"value": args.pairs * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000 * e2e_s,
-                    "pairs_per_step_per_gpu": args.pairs, "steps": max(3, args.steps)},
+                    "pairs_per_step_per_gpu": args.pairs, "steps": max(3, args.steps), "host_affinity": affinity,
+                    "copy_ceiling": {"value": args.pairs * world / ceil_s, "unit": UNIT, "ms_per_step": 1000 * ceil_s,
+                                     "h2d_gb_per_s_per_gpu": h2d / ceil_s / 1e9, "frac_of_ceiling": ceil_s / e2e_s,
+                                     "what": "the same H2D and D2H bytes from the same page-locked buffers on two streams, no kernel, every rank at once"}},
             "gpu_launches": int(launches),
             "clocks": clocks, "clocks_e2e": clocks_e2e,
         }
