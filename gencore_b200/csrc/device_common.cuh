@@ -249,7 +249,19 @@ GCB_HD UmiParts umi_split(const Umi &u) {
     }
     return p;
 }
+// true when the code holds a '_' field: without one util.h:59-88 split() yields a single part and isDuplex is false
+// (cluster.cpp:246-258), so the pairing loop can skip the split of every UMI of a single-strand library
+GCB_HD bool umi_has_separator(const Umi &u) {
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < GCB_MAX_UMI_WORDS; k++) {
+        const uint64_t y = u.w[k] ^ 0x5555555555555555ull;  // a zero nibble of y is a '_' field
+        any = any || (((y - 0x1111111111111111ull) & ~y & 0x8888888888888888ull) != 0ull);
+    }
+    return any;
+}
 GCB_HD bool umi_is_duplex(const Umi &a, const Umi &b) {
+    if (!umi_has_separator(a) || !umi_has_separator(b)) return false;
     UmiParts pa = umi_split(a), pb = umi_split(b);
     if (pa.n != 2 || pb.n != 2) return false;
     int a0 = pa.e0 - pa.b0, a1 = pa.e1 - pa.b1, c0 = pb.e0 - pb.b0, c1 = pb.e1 - pb.b1;
