@@ -8,11 +8,13 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "k_cluster_stats.cuh"
 #include "k_duplex.cuh"
 #include "k_group_select.cuh"
 #include "k_score_vote.cuh"
+#include "k_stat_depth.cuh"
 #include "k_fasta_pack.cuh"
 #include "k_umi_extract.cuh"
 #include "k_vote_ring.cuh"
@@ -56,6 +58,7 @@ struct gcb_ctx {
     // device mirror of a host batch / result (gcb_consensus_batch)
     DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
     DevBuf d_pair_group, d_ngroups, d_groups, d_out, d_out_bytes;
+    DevBuf s_tid, s_pos, s_len, s_off, s_depth;  // gcb_stat_depth
     DevBuf u_names, u_off, u_out, u_status;  // gcb_extract_umi
     DevBuf f_text, f_anchor, f_cnt, f_hpos, f_hbase, f_flag, f_coff, f_out;  // gcb_pack_fasta
     // gcb_consensus_batch pipelines chunks of clusters: copies in, kernels and copies out run on three streams
@@ -432,7 +435,7 @@ void gcb_destroy(gcb_ctx *ctx) {
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
                      &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_need, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->w_stats, &ctx->w_sq_count, &ctx->w_sq_words, &ctx->w_sq_index,  &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
                      &ctx->d_reads, &ctx->d_cigar, &ctx->d_payload, &ctx->d_pair_group, &ctx->d_ngroups, &ctx->d_groups,
-                     &ctx->d_out, &ctx->d_out_bytes, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status, &ctx->f_text, &ctx->f_anchor, &ctx->f_cnt, &ctx->f_hpos, &ctx->f_hbase,
+                     &ctx->d_out, &ctx->d_out_bytes, &ctx->s_tid, &ctx->s_pos, &ctx->s_len, &ctx->s_off, &ctx->s_depth, &ctx->u_names, &ctx->u_off, &ctx->u_out, &ctx->u_status, &ctx->f_text, &ctx->f_anchor, &ctx->f_cnt, &ctx->f_hpos, &ctx->f_hbase,
                      &ctx->f_flag, &ctx->f_coff, &ctx->f_out};
     for (DevBuf *b : all) release(*b);
     for (int k = 0; k < GCB_MAX_CHUNKS; k++) {
@@ -809,6 +812,39 @@ int gcb_set_debug(gcb_ctx *ctx, int key, int value) {
 int gcb_set_slow_queue_bytes(gcb_ctx *ctx, int64_t bytes) {
     if (!ctx || bytes < 0) return GCB_ERR_ARG;
     ctx->slow_queue_bytes = bytes;
+    return GCB_OK;
+}
+
+int gcb_stat_depth(gcb_ctx *ctx, const int32_t *tid, const int32_t *pos, const int32_t *l_qseq, int64_t n, int32_t coverage_step,
+                   const int64_t *target_len, int32_t n_targets, int64_t *depth) {
+    if (!ctx || n < 0 || coverage_step <= 0 || n_targets < 0 || (n > 0 && (!tid || !pos || !l_qseq)) || (n_targets > 0 && (!target_len || !depth)))
+        return fail(ctx, GCB_ERR_ARG, "gcb_stat_depth: bad argument");
+    if (n == 0 || n_targets == 0) return GCB_OK;
+    std::vector<int64_t> off((size_t)n_targets + 1, 0);
+    for (int32_t t = 0; t < n_targets; t++) {
+        if (target_len[t] < 0) return fail(ctx, GCB_ERR_ARG, "gcb_stat_depth: negative target length");
+        off[(size_t)t + 1] = off[(size_t)t] + 1 + target_len[t] / coverage_step;  // stats.cpp:43
+    }
+    const size_t bins = (size_t)off[(size_t)n_targets];
+    GCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = reserve(ctx, ctx->s_tid, (size_t)n * 4)) != GCB_OK || (rc = reserve(ctx, ctx->s_pos, (size_t)n * 4)) != GCB_OK ||
+        (rc = reserve(ctx, ctx->s_len, (size_t)n * 4)) != GCB_OK || (rc = reserve(ctx, ctx->s_off, off.size() * 8)) != GCB_OK ||
+        (rc = reserve(ctx, ctx->s_depth, bins * 8)) != GCB_OK)
+        return rc;
+    cudaStream_t st = ctx->stream;
+    GCB_CUDA(ctx, cudaMemcpyAsync(ctx->s_tid.p, tid, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    GCB_CUDA(ctx, cudaMemcpyAsync(ctx->s_pos.p, pos, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    GCB_CUDA(ctx, cudaMemcpyAsync(ctx->s_len.p, l_qseq, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    GCB_CUDA(ctx, cudaMemcpyAsync(ctx->s_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+    GCB_CUDA(ctx, cudaMemcpyAsync(ctx->s_depth.p, depth, bins * 8, cudaMemcpyHostToDevice, st));
+    GCB_LAUNCH(stat_depth_kernel, dim3((unsigned)((n + DEPTH_THREADS - 1) / DEPTH_THREADS)), dim3(DEPTH_THREADS), 0, st, (const int32_t *)ctx->s_tid.p,
+               (const int32_t *)ctx->s_pos.p, (const int32_t *)ctx->s_len.p, n, coverage_step, (const int64_t *)ctx->s_off.p, n_targets,
+               (unsigned long long *)ctx->s_depth.p);
+    ctx->launches++;
+    GCB_CUDA(ctx, cudaGetLastError());
+    GCB_CUDA(ctx, cudaMemcpyAsync(depth, ctx->s_depth.p, bins * 8, cudaMemcpyDeviceToHost, st));
+    GCB_CUDA(ctx, cudaStreamSynchronize(st));
     return GCB_OK;
 }
 

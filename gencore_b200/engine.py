@@ -24,7 +24,7 @@ DEFAULT_LIB = os.path.join(HERE, "csrc", "libgencore_b200.so")
 # every symbol include/gencore_b200.h declares
 ABI_SYMBOLS = ["gcb_abi_version", "gcb_default_options", "gcb_create", "gcb_destroy", "gcb_last_error", "gcb_set_reference",
                "gcb_set_reference_device", "gcb_consensus_batch", "gcb_consensus_batch_device", "gcb_batch_status",
-               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_debug", "gcb_set_slow_queue_bytes", "gcb_get_cluster_stats", "gcb_pack_fasta", "gcb_host_alloc", "gcb_host_free"]
+               "gcb_launch_count", "gcb_set_chunk_bytes", "gcb_extract_umi", "gcb_set_debug", "gcb_set_slow_queue_bytes", "gcb_get_cluster_stats", "gcb_stat_depth", "gcb_pack_fasta", "gcb_host_alloc", "gcb_host_free"]
 
 
 class EngineError(RuntimeError):
@@ -61,6 +61,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.gcb_set_slow_queue_bytes.argtypes = [C.c_void_p, C.c_int64]
     lib.gcb_get_cluster_stats.restype = C.c_int
     lib.gcb_get_cluster_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.gcb_stat_depth.restype = C.c_int
+    lib.gcb_stat_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     lib.gcb_pack_fasta.restype = C.c_int
     lib.gcb_pack_fasta.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
@@ -190,6 +192,18 @@ class ConsensusEngine:
         return ClusterStats(pre_cluster=v[0], pre_multi_cluster=v[1], pre_molecule=v[2], pre_molecule_se=v[3], pre_molecule_pe=v[4],
                             pre_uncounted=v[5], pre_hist=raw[10:].copy(), post_cluster=v[6], post_multi_cluster=v[7], post_sscs=v[8],
                             post_dcs=v[9])
+
+    def stat_depth(self, tid, pos, l_qseq, target_len, coverage_step: int = 10000, depth=None):
+        """Stats::statDepth over reads (stats.cpp:56-83): returns the concatenated per-contig depth bins (int64), added to `depth`
+        when one is given."""
+        tid, pos, l_qseq = (np.ascontiguousarray(a, np.int32) for a in (tid, pos, l_qseq))
+        target_len = np.ascontiguousarray(target_len, np.int64)
+        bins = int((1 + target_len // coverage_step).sum())
+        out = np.zeros(bins, np.int64) if depth is None else np.ascontiguousarray(depth, np.int64)
+        assert len(out) == bins
+        self._check(self.lib.gcb_stat_depth(self._ctx, tid.ctypes.data, pos.ctypes.data, l_qseq.ctypes.data, len(tid), coverage_step,
+                                            target_len.ctypes.data, len(target_len), out.ctypes.data))
+        return out
 
     def batch_status(self, stream: int = 0) -> int:
         return self.lib.gcb_batch_status(self._ctx, C.c_void_p(stream))

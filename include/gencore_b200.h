@@ -249,6 +249,15 @@ typedef struct gcb_cluster_stats {
 /* Waits for the context's stream, copies the counters to *out and, with reset != 0, zeroes them. */
 int gcb_get_cluster_stats(gcb_ctx *ctx, gcb_cluster_stats *out, int reset);
 
+/* Stats::statDepth (stats.cpp:56-83, called by Stats::addRead for every mapped read) over n reads given as host arrays of
+ * core.tid / core.pos / core.l_qseq: ADDS every read's bases to depth[bin_off[tid] + k], k-th bin of `coverage_step` bases of
+ * contig tid (Options::coverageStep, 10000 by default), where bin_off[t] = sum over earlier contigs of 1 + target_len / step
+ * (Stats::makeGenomeDepthBuf, stats.cpp:40-46).  `depth` is a host array of bin_off[n_targets] counters (zero them for a
+ * fresh Stats object; they are additive over batches and over ranks).  The rules of the reference hold bit for bit: reads with
+ * tid outside [0, n_targets) or ending in or beyond the contig's last bin are not counted. */
+int gcb_stat_depth(gcb_ctx *ctx, const int32_t *tid, const int32_t *pos, const int32_t *l_qseq, int64_t n, int32_t coverage_step,
+                   const int64_t *target_len, int32_t n_targets, int64_t *depth);
+
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 int64_t gcb_launch_count(const gcb_ctx *ctx);
 
