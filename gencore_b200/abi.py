@@ -193,9 +193,12 @@ class Batch:
         return b
 
     def max_cluster_bytes(self) -> int:
-        if self.n_clusters == 0:
-            return 0
-        return int(min(np.diff(self.cluster_slab_bounds()).max(), 2**31 - 1))
+        """gcb_batch.max_cluster_bytes: a property of the packed batch (whoever packs it knows it); computed once per object."""
+        cached = self.__dict__.get("_max_cluster_bytes")
+        if cached is None:
+            cached = 0 if self.n_clusters == 0 else int(min(np.diff(self.cluster_slab_bounds()).max(), 2**31 - 1))
+            self.__dict__["_max_cluster_bytes"] = cached
+        return cached
 
     def algorithmic_bytes(self) -> dict:
         """SURVEY §8(d) payload-only byte counts for the vote kernel (input side)."""

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <new>
 #include <vector>
@@ -54,6 +55,8 @@ struct gcb_ctx {
     int ring_window_shift = 0;           // 0 = chosen by plan_tiles; 14 / 15 = forced (tuning)
     int group_lanes = 0;                 // lanes per cluster in umi_group / select_template (0 = by mean cluster size)
     int force_generic = 0;               // tests: every tile goes to the generic kernel
+    int trace_e2e = 0;                   // gcb_set_debug key 6: gcb_consensus_batch prints where its time goes (stderr)
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     int n_sms = 148;
     // device mirror of a host batch / result (gcb_consensus_batch)
     DevBuf d_pair_off, d_cref, d_cflags, d_umi, d_reads, d_cigar, d_payload;
@@ -62,7 +65,7 @@ struct gcb_ctx {
     DevBuf u_names, u_off, u_out, u_status;  // gcb_extract_umi
     DevBuf f_text, f_anchor, f_cnt, f_hpos, f_hbase, f_flag, f_coff, f_out;  // gcb_pack_fasta
     // gcb_consensus_batch pipelines chunks of clusters: copies in, kernels and copies out run on three streams
-    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaStream_t h2d = nullptr, d2h = nullptr, d2h_out = nullptr;  // (d2h_out: the consensus records, whose sizes the host learns chunk by chunk)
     cudaEvent_t ev_in[GCB_MAX_CHUNKS] = {nullptr}, ev_done[GCB_MAX_CHUNKS] = {nullptr}, ev_out[GCB_MAX_CHUNKS] = {nullptr};
     int64_t *h_totals = nullptr;  // pinned: cumulative consensus bytes after every chunk
     int32_t *h_flag = nullptr;    // pinned: the device error flag
@@ -406,6 +409,7 @@ int gcb_create(const gcb_options *opt, int device, gcb_ctx **out) {
     }
     bool ok = cudaStreamCreateWithFlags(&ctx->h2d, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->d2h, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->d2h_out, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->h_totals, 8 * (GCB_MAX_CHUNKS + 1)) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->h_flag, 8) == cudaSuccess;
     for (int k = 0; ok && k < GCB_MAX_CHUNKS; k++)
@@ -431,6 +435,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     if (ctx->h2d) cudaStreamSynchronize(ctx->h2d);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->d2h) cudaStreamSynchronize(ctx->d2h);
+    if (ctx->d2h_out) cudaStreamSynchronize(ctx->d2h_out);
     DevBuf *all[] = {&ctx->g_packed, &ctx->g_off, &ctx->g_len, &ctx->w_members, &ctx->w_group_off, &ctx->w_scratch, &ctx->w_rrp,
                      &ctx->w_flags, &ctx->w_mode, &ctx->w_hasumi, &ctx->w_overlap, &ctx->w_slab, &ctx->w_cob, &ctx->w_coo,
                      &ctx->w_scan, &ctx->w_err, &ctx->w_tiles, &ctx->w_vr, &ctx->w_fs, &ctx->w_gtiles, &ctx->w_gcount, &ctx->w_fstiles, &ctx->w_thdr2, &ctx->w_need, &ctx->w_rb_list, &ctx->w_rb_count, &ctx->w_stats, &ctx->w_sq_count, &ctx->w_sq_words, &ctx->w_sq_index,  &ctx->d_pair_off, &ctx->d_cref, &ctx->d_cflags, &ctx->d_umi,
@@ -447,6 +452,7 @@ void gcb_destroy(gcb_ctx *ctx) {
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     if (ctx->h2d) cudaStreamDestroy(ctx->h2d);
     if (ctx->d2h) cudaStreamDestroy(ctx->d2h);
+    if (ctx->d2h_out) cudaStreamDestroy(ctx->d2h_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -528,6 +534,7 @@ int gcb_consensus_batch(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *hr) {
         cudaStreamSynchronize(ctx->h2d);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->d2h);
+        cudaStreamSynchronize(ctx->d2h_out);
     }
     return rc;
 }
@@ -630,6 +637,12 @@ static int consensus_batch_host(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *h
     Workspace ws;
     if ((rc = reserve_workspace(ctx, hb->n_pairs, hb->n_clusters, (hb->payload_bytes + plan.window - 1) / plan.window, hb->payload_bytes, ws)) != GCB_OK) return rc;
     cudaStream_t sc = ctx->stream, sin = ctx->h2d, sout = ctx->d2h;
+    struct timespec ts0, ts1, ts2, ts3;
+    if (ctx->trace_e2e) {
+        if (!ctx->ev_t0) { cudaEventCreate(&ctx->ev_t0); cudaEventCreate(&ctx->ev_t1); }
+        clock_gettime(CLOCK_MONOTONIC, &ts0);
+        cudaEventRecord(ctx->ev_t0, sin);
+    }
     GCB_CUDA(ctx, cudaMemsetAsync(ws.error_flag, 0, 4, sc));
     for (int k = 0; k < K; k++) {
         const ViewRange &v = view[k];
@@ -659,18 +672,35 @@ static int consensus_batch_host(gcb_ctx *ctx, const gcb_batch *hb, gcb_result *h
         GCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_totals + k, d_totals + k, 8, cudaMemcpyDeviceToHost, sout));
         GCB_CUDA(ctx, cudaEventRecord(ctx->ev_out[k], sout));
     }
-    // consensus records: the size of every chunk's share is known only on the device
+    if (ctx->trace_e2e) {
+        cudaEventRecord(ctx->ev_t1, sin);
+        clock_gettime(CLOCK_MONOTONIC, &ts1);
+    }
+    // consensus records: the size of every chunk's share is known only on the device.  They leave on a stream of their own: on
+    // `sout` they would queue behind the result rows of EVERY chunk (enqueued above) and all 57 MB per million pairs would
+    // cross after the last chunk (measured: 1.15 ms of 11.5).  ev_out[k] implies the chunk's kernels are done.
+    cudaStream_t srec = ctx->d2h_out;
     int64_t done = 0;
     for (int k = 0; k < K; k++) {
         GCB_CUDA(ctx, cudaEventSynchronize(ctx->ev_out[k]));
         int64_t upto = ctx->h_totals[k];
         if (upto > hr->out_capacity) upto = hr->out_capacity;  // (the error flag below reports it)
-        if (upto > done) GCB_CUDA(ctx, cudaMemcpyAsync(hr->out_payload + done, dr.out_payload + done, (size_t)(upto - done), cudaMemcpyDeviceToHost, sout));
+        if (upto > done) GCB_CUDA(ctx, cudaMemcpyAsync(hr->out_payload + done, dr.out_payload + done, (size_t)(upto - done), cudaMemcpyDeviceToHost, srec));
         if (upto > done) done = upto;
     }
+    if (ctx->trace_e2e) clock_gettime(CLOCK_MONOTONIC, &ts2);
     GCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_flag, ws.error_flag, 4, cudaMemcpyDeviceToHost, sout));
     GCB_CUDA(ctx, cudaStreamSynchronize(sout));
+    GCB_CUDA(ctx, cudaStreamSynchronize(srec));
     GCB_CUDA(ctx, cudaStreamSynchronize(sc));
+    if (ctx->trace_e2e) {
+        clock_gettime(CLOCK_MONOTONIC, &ts3);
+        float h2d_ms = 0.f;
+        cudaEventElapsedTime(&h2d_ms, ctx->ev_t0, ctx->ev_t1);
+        auto ms = [](const timespec &a, const timespec &b) { return (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6; };
+        fprintf(stderr, "gcb_consensus_batch: %d chunks; enqueue %.3f ms, last chunk's results at %.3f ms, done at %.3f ms; the copy-in stream was busy %.3f ms\n",
+                K, ms(ts0, ts1), ms(ts0, ts2), ms(ts0, ts3), (double)h2d_ms);
+    }
     *hr->out_bytes = ctx->h_totals[K - 1];
     const int32_t flag = *ctx->h_flag;
     if (flag != GCB_OK) return fail(ctx, flag, flag == GCB_ERR_CAPACITY ? "out_payload too small" : "malformed batch");
@@ -805,6 +835,7 @@ int gcb_set_debug(gcb_ctx *ctx, int key, int value) {
     if (key == 2) ctx->ring_window_shift = (value == 14 || value == 15) ? value : 0;  // tuning only: same results
     else if (key == 3) ctx->group_lanes = value;                                      // tuning only: same results
     else if (key == 5) ctx->force_generic = value != 0;                               // tests: the generic kernel votes every tile
+    else if (key == 6) ctx->trace_e2e = value != 0;                                   // measurement: gcb_consensus_batch's timeline on stderr
     else return GCB_ERR_ARG;
     return GCB_OK;
 }

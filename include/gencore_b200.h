@@ -229,7 +229,8 @@ void gcb_host_free(void *p);
 
 /* Tuning / test aid; results never depend on it.  key 2 = force the vote's tile window (14 or 15 = log2 bytes, 0 = automatic),
  * key 3 = lanes per cluster in umi_group_kernel / select_template_kernel (8, 16, 32; 0 = by mean cluster size),
- * key 5 = non-zero: every tile is voted by the generic kernel (score_vote_kernel) instead of the ring kernel. */
+ * key 5 = non-zero: every tile is voted by the generic kernel (score_vote_kernel) instead of the ring kernel,
+ * key 6 = non-zero: gcb_consensus_batch prints its timeline (enqueue, copy-in stream, results) on stderr. */
 int gcb_set_debug(gcb_ctx *ctx, int key, int value);
 
 /* Tuning knob: bytes of the slow-column queue between vote_ring_kernel and slow_columns_kernel (0 = sized from the payload).
