@@ -230,10 +230,6 @@ GCB_DEV void finish_column(const BatchView &b, const ResultView &r, const Genome
 #ifndef GCB_DC_UNROLL
 #define GCB_DC_UNROLL 2  // (8: 2.20 ms, 4 and 2: 1.91 ms on the cfg4 shape: the smaller code wins)
 #endif
-#ifndef GCB_DC_TWO
-#define GCB_DC_TWO 0     // 1: two-bin histogram in the uniform walk, the general loop when a third code turns up (3.2 ms on the cfg4
-                         // shape against 1.9: with 50 reads at 1 % errors some lane of nearly every warp sees a third code)
-#endif
 // One column of a family side from its VoteRead entries `ents` and its cluster's slab `cb` (shared or global memory).
 GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const GenomeView &gv, const gcb_options &o, const RollbackList &rb,
                            const SlowSide &fs, const uint8_t *cb, const VoteRead *ents, uint8_t *out, int col) {
@@ -250,13 +246,11 @@ GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const Genome
     }
     Bins3 bins;
     bins.init();
+    const int obase = base_at(cb + 4 * (int)tv.own_off4 + qbytes, col);  // the record's base before the vote: the template's own
+    bins.seed(obase);
     const int m = fs.m;
     bool general = true;
     if (fs.flags & FS_UNIFORM) {
-#if GCB_DC_TWO
-        Bins2 two;  // most slow columns show two codes
-        two.init();
-#endif
         const bool info = tv.ov_len != VR_NO_OVERLAP_INFO;
         const int k = col - (int)tv.ov_own, mp = (int)tv.ov_mate + k;
         const bool inwin = info && k >= 0 && k < (int)tv.ov_len;
@@ -267,7 +261,8 @@ GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const Genome
         const int msoff = GCB_ALIGN4(tv.mate_l) + (mpi >> 1), mnsh = (mpi & 1) ? 0 : 4;
         // GCB_DC_UNROLL reads at a time, in two waves of independent loads (where their records lie, then their bytes).  ONE walk:
         // a second instantiation (two-bin histogram first, three-bin on overflow) doubles the code of a function every voter
-        // warp of a deep tile enters, and measured 4.6 ms against 2.4 on the cfg4 shape (profiles/r03_notes.md).
+        // warp of a deep tile enters, and measured 4.6 ms against 2.4 on the cfg4 shape; a two-bin walk that falls back to the
+        // general loop 3.2 ms (with 50 reads at 1 % errors some lane of nearly every warp sees a third code): profiles/r03_notes.md.
         for (int e0 = 0; e0 < m; e0 += GCB_DC_UNROLL) {
             uint32_t w[GCB_DC_UNROLL], x[GCB_DC_UNROLL];
 #pragma unroll
@@ -303,23 +298,10 @@ GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const Genome
                 } else {
                     score = plain ? tab.q2s(ql) : tab.sm;
                 }
-#if GCB_DC_TWO
-                two.add(base, ql, score);
-#else
                 bins.add(base, ql, score);
-#endif
             }
         }
-#if GCB_DC_TWO
-        general = two.overflow;  // a third code: the general loop below builds the three-bin histogram
-        if (!general) {
-            bins.b0 = two.bA; bins.c0 = two.cA; bins.s0 = two.sA; bins.q0 = two.qA; bins.x0 = two.xA;
-            bins.b1 = two.bB; bins.c1 = two.cB; bins.s1 = two.sB; bins.q1 = two.qB; bins.x1 = two.xB;
-            bins.total = two.total;
-        }
-#else
         general = false;
-#endif
     }
     if (general) {
         for (int e = 0; e < m; e++) {
@@ -327,7 +309,7 @@ GCB_DEV void decide_column(const BatchView &b, const ResultView &r, const Genome
             if (fetch_vote(cb, ents[e], col, side, tab, base, qual, score)) bins.add(base, qual, score);
         }
     }
-    finish_column(b, r, gv, o, rb, fs, out, col, bins, base_at(cb + 4 * (int)tv.own_off4 + qbytes, col), [&](auto &&f) {
+    finish_column(b, r, gv, o, rb, fs, out, col, bins, obase, [&](auto &&f) {
         for (int e = 0; e < m; e++) {
             int base, qual, score;
             if (fetch_ent(cb, ents[e], col, side, o, base, qual, score)) f(base, qual, score, e == fs.tmpl_k);
@@ -370,18 +352,21 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
             }
         }
     };
+    const int obase = (int)((ents[fs.tmpl_k] >> 16) & 0xFu);  // the record's base before the vote: the template's own
     Bins2 two;
     two.init();
+    two.seed(obase);
     walk(two);
     if (!two.overflow) {
         bins.b0 = two.bA; bins.c0 = two.cA; bins.s0 = two.sA; bins.q0 = two.qA; bins.x0 = two.xA;
         bins.b1 = two.bB; bins.c1 = two.cB; bins.s1 = two.sB; bins.q1 = two.qB; bins.x1 = two.xB;
         bins.total = two.total;
     } else {
+        bins.seed(obase);
         walk(bins);
     }
     // the record's base before the vote: the template's own (pair.cpp rewrites qualities, never bases)
-    finish_column(b, r, gv, o, rb, fs, out, col, bins, (int)((ents[fs.tmpl_k] >> 16) & 0xFu), [&](auto &&f) {
+    finish_column(b, r, gv, o, rb, fs, out, col, bins, obase, [&](auto &&f) {
         for (int e = 0; e < n; e++) {
             int base, qual, score;
             if (slow_decode(tab, ents[e], side, base, qual, score)) f(base, qual, score, e == fs.tmpl_k);

@@ -310,10 +310,17 @@ struct Bins3 {
         total = 0;
         overflow = false;
     }
+    // bin 0 may be SEEDED with a code nobody has shown yet (the template's base: the code most reads of a column show); an empty
+    // bin takes part in the top-2 selection exactly as the code would without a bin — with (0, 0, code)
+    GCB_DEV void seed(int base) { b0 = base; }
     GCB_DEV void add(int base, int qual, int score) {
         total += score;
+        if (base == b0) {  // the usual read: five instructions instead of forty (a branch: the threads of a warp mostly agree)
+            c0++; s0 += score; q0 += qual; x0 = max(x0, qual);
+            return;
+        }
         // the bin that holds the code, else the first free one
-        const bool h0 = b0 == base, h1 = b1 == base, h2 = b2 == base;
+        const bool h0 = false, h1 = b1 == base, h2 = b2 == base;
         const bool hit = h0 || h1 || h2;
         const bool u0 = h0 || (!hit && b0 < 0);
         const bool u1 = h1 || (!hit && b0 >= 0 && b1 < 0);
@@ -344,9 +351,14 @@ struct Bins2 {
         cA = cB = sA = sB = qA = qB = xA = xB = total = 0;
         overflow = false;
     }
+    GCB_DEV void seed(int base) { bA = base; }  // (see Bins3::seed)
     GCB_DEV void add(int base, int qual, int score) {
         total += score;
-        const bool uA = bA < 0 || bA == base;
+        if (base == bA) {
+            cA++; sA += score; qA += qual; xA = max(xA, qual);
+            return;
+        }
+        const bool uA = bA < 0;
         const bool uB = !uA && (bB < 0 || bB == base);
         overflow = overflow || !(uA || uB);
         bA = uA ? base : bA; cA += uA ? 1 : 0; sA += uA ? score : 0; qA += uA ? qual : 0; xA = max(xA, uA ? qual : 0);
