@@ -79,10 +79,7 @@ GCB_DEV int duplex_merge_staged(uint8_t *rec1, int len1, uint8_t *rec2, int len2
 
 // Two threads per cluster: both walk the stack (same decisions), each merges one side of a strand pair's consensus records
 // (the walk over a record is sequential, the two sides are independent), thread 0 writes the verdicts.
-#ifndef GCB_DUPLEX_MIN_CTAS
-#define GCB_DUPLEX_MIN_CTAS 1
-#endif
-__global__ void __launch_bounds__(DUPLEX_THREADS, GCB_DUPLEX_MIN_CTAS) duplex_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o) {
+__global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o) {
     GCB_GRID_DEP();
     __shared__ uint32_t s_stage[DUPLEX_THREADS][2][DUPLEX_STAGE_WORDS];
     const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);

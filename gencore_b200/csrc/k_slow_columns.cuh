@@ -374,10 +374,7 @@ GCB_DEV void slow_record(const BatchView &b, const ResultView &r, const GenomeVi
     });
 }
 
-#ifndef GCB_SLOW_MIN_CTAS
-#define GCB_SLOW_MIN_CTAS 1
-#endif
-__global__ void __launch_bounds__(VQ_SLOW_THREADS, GCB_SLOW_MIN_CTAS) slow_columns_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o,
+__global__ void __launch_bounds__(VQ_SLOW_THREADS) slow_columns_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o,
                                                                        SlowQueue sq, RollbackList rb) {
     GCB_GRID_DEP();
     if (batch_is_malformed(ws.error_flag)) return;

@@ -40,11 +40,6 @@ namespace gcb {
 #define GCB_VR_UNROLL 1  // read-loop unrolling (0 = the compiler's choice, which unrolls seven times: 0.198 ms against 0.180 for the
                          // rolled loop on the BASELINE shape — the kernel waits for instructions, not for data; profiles/r03_notes.md)
 #endif
-#if defined(GCB_VR_HINTS) && !defined(GCB_SIMT_CHECK)
-#define VR_RARE(x) __builtin_expect(!!(x), 0)  // block placement: the rare paths out of the way of the instruction fetch
-#else
-#define VR_RARE(x) (x)
-#endif
 constexpr int VR_THREADS = GCB_VR_THREADS;  // warp 0 produces, fifteen warps vote (128 registers per thread)
 constexpr int VR_WARPS = VR_THREADS / WARP;
 constexpr int VR_VOTERS = VR_WARPS - 1;
@@ -127,11 +122,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     // the batch's largest tile (tile_prep2_kernel measured it) decides how the voters are organised: small tiles -> many in
     // flight -> three groups of five warps; tiles that fill the arena -> all fifteen warps on every tile
     const int32_t largest = (int32_t)ring_round128((uint32_t)max(*max_need, 128));
-    #ifdef GCB_VR_FORCE_GROUPS
-    const int n_groups = (arena_bytes >= GCB_VR_FORCE_GROUPS * largest && VR_VOTERS % VR_GROUPS == 0) ? VR_GROUPS : 1, wpg = VR_VOTERS / n_groups;
-#else
     const int n_groups = (arena_bytes >= 6 * largest && VR_VOTERS % VR_GROUPS == 0) ? VR_GROUPS : 1, wpg = VR_VOTERS / n_groups;
-#endif
     const int n_stages = VR_MAX_STAGES;
     if (tid == 0) {
         for (int s = 0; s < n_stages; s++) {
@@ -275,7 +266,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         bundle = __shfl_sync(FULL, bundle, 0);
         bool closer = false;
         if (bundle < nb) {
-            if (VR_RARE(sh->lanes != cur_L)) {  // a lane owns sixteen columns; a family side takes L lanes, a bundle 32 / L family sides
+            if (sh->lanes != cur_L) {  // a lane owns sixteen columns; a family side takes L lanes, a bundle 32 / L family sides
                 cur_L = sh->lanes;
                 S = (int)((32u * ((65535u / (unsigned)cur_L) + 1u)) >> 16);
                 sub = (int)(((unsigned)lane * ((65535u / (unsigned)cur_L) + 1u)) >> 16);  // lane / L
@@ -283,7 +274,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 col0 = VT_CHUNK * j;
                 cur_l = -1;
             }
-            if (VR_RARE(sh->common_l != cur_l)) {  // the masks of the tile's usual record length
+            if (sh->common_l != cur_l) {  // the masks of the tile's usual record length
                 cur_l = sh->common_l;
                 cm_common = make_masks(cur_l, cur_l, col0);
             }
@@ -315,12 +306,12 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     if (sb0 + 4 < sbytes) tbe1 = bswap32(GCB_LDS32(trec + qbytes + sb0 + 4));
                 }
                 ChunkMasks cm = cm_common;
-                if (VR_RARE(l_out != cur_l || len != l_out)) cm = make_masks(l_out, len, col0);
+                if (l_out != cur_l || len != l_out) cm = make_masks(l_out, len, col0);
                 if (mine && j == 0 && ft.mode != SIDE_COPY) GCB_COUNT((ft.flags & FS_UNIFORM) ? 4 : 5, 1);
                 // per-column maxima live in 16-bit lanes (VIMNMX3.U16x2 is native, a per-byte maximum is seven instructions):
                 // mo[k] tracks bytes 1 and 3 of quality word k in the high byte of each half, me[k] bytes 0 and 2 (word << 8)
                 uint32_t mo[4] = {0u, 0u, 0u, 0u}, me[4] = {0u, 0u, 0u, 0u}, dis0 = 0u, dis1 = 0u;
-                if (!VR_RARE(!(ft.flags & FS_UNIFORM))) {
+                if (ft.flags & FS_UNIFORM) {
                     // hoisted geometry: every voter is read at the template's columns and meets its mate at the same offset,
                     // and every mate's record lies at the same distance from its read's record
                     const int xw = (int)tv.ov_own - col0;   // first column of the lane inside the overlap window
@@ -448,7 +439,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 // ---- slow columns: one list entry per lane that found any
                 const uint32_t mask16 = nib_flags_to_byte(slow0) | (nib_flags_to_byte(slow1) << 8);
                 const unsigned bal = __ballot_sync(FULL, mask16 != 0u);
-                if (VR_RARE(deep)) {
+                if (deep) {
                     // the stage's own list (family side << 21 | lane of the family side << 16 | column mask) ...
                     if (bal != 0u) {
                         int at = 0;
@@ -469,7 +460,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     // ... or a record per slow column in the global queue: records of one size per bundle, from the warp's own
                     // pool of reserved queue space
                     const uint32_t T = (uint32_t)__reduce_add_sync(FULL, __popc(mask16)), rw = slow_rec_words(mmax), W = T * rw;
-                    if (VR_RARE(pool_r + T > pool_re || pool_w + W > pool_we)) {
+                    if (pool_r + T > pool_re || pool_w + W > pool_we) {
                         // a new pool (one 64-bit atomic: records << 32 | words); what is left of the old one stays unused
                         for (uint32_t i = pool_r + (uint32_t)lane; i < pool_re; i += WARP) sq.index[i] = VQ_INVALID;
                         const uint32_t need_r = T > VQ_POOL_RECS ? T : VQ_POOL_RECS, need_w = W > VQ_POOL_WORDS ? W : VQ_POOL_WORDS;
@@ -485,7 +476,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                             pool_r = pool_re = pool_w = pool_we = 0u;
                         }
                     }
-                    if (VR_RARE(pool_r + T > pool_re)) {
+                    if (pool_r + T > pool_re) {
                         // no queue space: the generic kernel redoes the whole tile from the payload (it runs after
                         // slow_columns_kernel and vote_rollback_kernel)
                         if (lane == 0 && atomicExch(&sh->closed, 1) == 0) {
@@ -563,7 +554,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 pipe_progress();
             } while (bundle < nb);
         }
-        if (VR_RARE(closer)) {
+        if (closer) {
             // every bundle of the (deep) tile is done: prefix sums of the entries' column counts, then the list is open to every warp
             __threadfence_block();
             const int n = *(volatile int32_t *)&sh->n_entries;
@@ -586,10 +577,10 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 *(volatile int32_t *)&sh->closed = 1;
             }
         }
-        if (VR_RARE(deep)) {
+        if (deep) {
             // every voter warp waits for the tile to be closed and then decides slow columns, 32 at a time, one thread per
             // column, straight from the staged slab: a deep tile has hundreds of them and nothing else for the warps to do
-            while (*(volatile int32_t *)&sh->closed == 0) pipe_relax(100u);
+            while (*(volatile int32_t *)&sh->closed == 0) pipe_relax(400u);  // (thirteen warps poll while two vote; the length of the nap does not matter: 100 to 1000 ns measured)
             __threadfence_block();
             const int total = *(volatile int32_t *)&sh->drain_total, n = *(volatile int32_t *)&sh->n_entries;
             const uint32_t *s_list = (const uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap;

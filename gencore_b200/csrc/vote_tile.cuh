@@ -319,8 +319,12 @@ struct Bins3 {
             c0++; s0 += score; q0 += qual; x0 = max(x0, qual);
             return;
         }
+        if (base == b1) {  // (a slow column usually shows two codes: the general update is left with the first sight of a code)
+            c1++; s1 += score; q1 += qual; x1 = max(x1, qual);
+            return;
+        }
         // the bin that holds the code, else the first free one
-        const bool h0 = false, h1 = b1 == base, h2 = b2 == base;
+        const bool h0 = false, h1 = false, h2 = b2 == base;
         const bool hit = h0 || h1 || h2;
         const bool u0 = h0 || (!hit && b0 < 0);
         const bool u1 = h1 || (!hit && b0 >= 0 && b1 < 0);
@@ -356,6 +360,10 @@ struct Bins2 {
         total += score;
         if (base == bA) {
             cA++; sA += score; qA += qual; xA = max(xA, qual);
+            return;
+        }
+        if (base == bB) {
+            cB++; sB += score; qB += qual; xB = max(xB, qual);
             return;
         }
         const bool uA = bA < 0;
