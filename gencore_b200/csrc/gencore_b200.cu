@@ -353,7 +353,7 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         }
     }
     if (stages & GCB_STAGE_DUPLEX) {
-        GCB_LAUNCH(duplex_kernel, dim3((unsigned)((2 * (int64_t)nc + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream, b, r, ws,
+        GCB_LAUNCH(duplex_kernel, dim3((unsigned)((DUPLEX_GS * (int64_t)nc + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream, b, r, ws,
                    ctx->opt);
         ctx->launches++;
         // ... and the Stats side effects of the clusters' verdicts

@@ -539,25 +539,55 @@ GCB_DEV bool select_cluster_fast(const Grp<GS> &g, const BatchView &b, const Res
         v[side] = w;
     }
     if (!g.all(!act || fits)) return false;
-    // every family: its members are the lanes whose pair_group names it, in lane (= map) order
-    bool same = true;
-    for (int gi = 0; gi < G; gi++) {
-        const unsigned fm = g.ballot(gid == gi);
-        if (fm == 0u) return false;  // (cannot happen: every family has a pair)
-        const int first = __ffs((int)fm) - 1 + g.base;
-        const bool mem = gid == gi;
-        // (every lane of the group takes part in every shuffle)
-        const int fl = __shfl_sync(g.mask, L_l, first), fp = __shfl_sync(g.mask, L_pos, first), gl_ = __shfl_sync(g.mask, R_l, first),
-                  gp = __shfl_sync(g.mask, R_pos, first);
-        const uint32_t fc = __shfl_sync(g.mask, L_cig, first), gc = __shfl_sync(g.mask, R_cig, first);
-        same = same && (!mem || (L_l == fl && L_pos == fp && L_cig == fc && R_l == gl_ && R_pos == gp && R_cig == gc));
+    // every family: its members are the lanes whose pair_group names it, in lane (= map) order.  Everything below is
+    // lane-parallel but for one short loop over the families (a loop in which one lane writes a family's rows while the others
+    // wait was half of this kernel's instructions).
+    const unsigned fm = __match_any_sync(g.mask, gid) >> g.base;  // this lane's family (the idle lanes form one of their own)
+    const int first = __ffs((int)fm) - 1, src = first + g.base;
+    const int m = __popc(fm), rank = __popc(fm & ((1u << lane) - 1u));
+    const bool is_first = act && lane == first;
+    const unsigned firsts = g.ballot(is_first);
+    // (cannot fail: umi_group_kernel numbers the families 0 .. G-1 and every family has a pair)
+    if (!g.all(!act || (gid >= 0 && gid < G)) || __popc(firsts) != G) return false;
+    {
+        const int fl = __shfl_sync(g.mask, L_l, src), fp = __shfl_sync(g.mask, L_pos, src), gl_ = __shfl_sync(g.mask, R_l, src),
+                  gp = __shfl_sync(g.mask, R_pos, src);
+        const uint32_t fc = __shfl_sync(g.mask, L_cig, src), gc = __shfl_sync(g.mask, R_cig, src);
+        const bool same = !act || (L_l == fl && L_pos == fp && L_cig == fc && R_l == gl_ && R_pos == gp && R_cig == gc);
+        if (!g.all(same)) return false;
     }
-    if (!g.all(same)) return false;
+    // FS_UNIFORM per family side ((same length, no shift: given) every member has the template's overlap window and the same
+    // distance from its record to its mate's): three words per side compared with the first member's
+    bool uni[2];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const VoteRead &x = v[side];
+        const bool ovl = x.ov_len > 0;
+        const uint32_t k1 = (uint32_t)(uint16_t)x.ov_len | (ovl ? (uint32_t)(uint16_t)x.ov_own << 16 : 0u);
+        const uint32_t k2 = ovl ? ((uint32_t)(uint16_t)x.ov_mate | (uint32_t)(uint16_t)x.mate_l << 16) : 0u;
+        const uint32_t k3 = ovl ? (uint32_t)(uint16_t)(x.mate_off4 - x.own_off4) : 0u;
+        const bool u = k1 == __shfl_sync(g.mask, k1, src) && k2 == __shfl_sync(g.mask, k2, src) && k3 == __shfl_sync(g.mask, k3, src);
+        uni[side] = (g.ballot(act && !u) & fm) == 0u;
+    }
+    // where the family's members and its consensus records begin: sums over the families created before it (umi_group_kernel
+    // numbers them in creation order; pairs in the high byte, record bytes — at most 32 * 2 * 48 KB — below)
+    const uint32_t own_sum = is_first ? ((uint32_t)m << 24) + (uint32_t)(record_bytes(L_l) + record_bytes(R_l)) : 0u;
+    uint32_t excl = 0u, total = 0u;
+    for (int gi = 0; gi < G; gi++) {
+        const unsigned f = g.ballot(is_first && gid == gi);  // exactly one lane
+        const uint32_t sgi = __shfl_sync(g.mask, own_sum, __ffs((int)f) - 1 + g.base);
+        if (gid > gi) excl += sgi;
+        total += sgi;
+    }
+    const int mb = p0 + (int)(excl >> 24);
+    const int64_t orel0 = (int64_t)(excl & 0xFFFFFFu);
 
     // ---- the cluster is of the usual kind: write what select_template_kernel's general path would
     if (act) {
         ws.overlap[pair] = ov;
         *(uint16_t *)(ws.vote_flags + 2 * pair) = (uint16_t)(VOTE_PARTICIPATES | (VOTE_PARTICIPATES << 8));
+        ws.vote_reads[2 * (int64_t)mb + rank] = v[0];
+        ws.vote_reads[2 * (int64_t)mb + m + rank] = v[1];
     }
     if (lane >= G && act) {  // slots that hold no family
         *(uint16_t *)(ws.side_mode + 2 * pair) = (uint16_t)(SIDE_NONE | (SIDE_NONE << 8));
@@ -565,98 +595,63 @@ GCB_DEV bool select_cluster_fast(const Grp<GS> &g, const BatchView &b, const Res
 #pragma unroll
         for (int q = 0; q < (int)(sizeof(gcb_group_result) / 8); q++) row[q] = make_int2(0, 0);
     }
-    const int contig = b.cluster_ref[c];
-    int64_t out_rel = 0;
-    int mb = p0;  // families lie in `members` in creation order
-    for (int gi = 0; gi < G; gi++) {
-        const unsigned fm = g.ballot(gid == gi);
-        const int m = __popc(fm), first = __ffs((int)fm) - 1 + g.base;
-        const bool mem = gid == gi;
-        const int rank = __popc(fm & ((1u << lane) - 1u));
-        // the template's entries (the family's first pair), for the uniformity test of group.cpp's FS_UNIFORM shortcut
-        uint32_t w0[4], w1[4], t0[4], t1[4];
-        memcpy(w0, &v[0], 16);
-        memcpy(w1, &v[1], 16);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            t0[q] = __shfl_sync(g.mask, w0[q], first);
-            t1[q] = __shfl_sync(g.mask, w1[q], first);
-        }
-        VoteRead tv[2];
-        memcpy(&tv[0], t0, 16);
-        memcpy(&tv[1], t1, 16);
-        bool uni[2];
+    if (is_first) {  // the family's result row and its two family-side descriptors
+        const int contig = b.cluster_ref[c];
+        const int slot = p0 + gid;
+        const int left = 2 * (int)pair, right = left + 1;
+        gcb_group_result gr;
+        gr.tmpl_read[0] = left;
+        gr.tmpl_read[1] = right;
+        gr.qname_donor[0] = gr.qname_donor[1] = -1;
+        int name_slot;
+        if (L_lqn <= R_lqn) { gr.qname_donor[1] = left; name_slot = left; }  // group.cpp:114-123
+        else { gr.qname_donor[0] = right; name_slot = right; }
+        gr.diff[0] = gr.diff[1] = 0;
+        gr.mismatch_inc[0] = gr.mismatch_inc[1] = 0;
+        gr.merge_reads = m;
+        gr.reverse_merge_reads = 0;
+        gr.status = 0;
+        gr.duplex_partner = -1;
+        gr.duplex_diff = 0;
+        gr.umi_pair = name_slot / 2;
+        int64_t orel = orel0;
 #pragma unroll
         for (int side = 0; side < 2; side++) {
-            const VoteRead &x = v[side], &t = tv[side];
-            // (same length, no shift: given) same overlap window and the same distance from a read's record to its mate's
-            const bool u = !mem || (x.ov_len == t.ov_len && (x.ov_len <= 0 || (x.ov_own == t.ov_own && x.ov_mate == t.ov_mate && x.mate_l == t.mate_l &&
-                                                                                (uint16_t)(x.mate_off4 - x.own_off4) == (uint16_t)(t.mate_off4 - t.own_off4))));
-            uni[side] = g.all(u);
-        }
-        if (mem) {
-            ws.vote_reads[2 * (int64_t)mb + rank] = v[0];
-            ws.vote_reads[2 * (int64_t)mb + m + rank] = v[1];
-        }
-        if (lane + g.base == first) {
-            const int slot = p0 + gi;
-            const int left = 2 * (int)pair, right = left + 1;
-            gcb_group_result gr;
-            gr.tmpl_read[0] = left;
-            gr.tmpl_read[1] = right;
-            gr.qname_donor[0] = gr.qname_donor[1] = -1;
-            int name_slot;
-            if (L_lqn <= R_lqn) { gr.qname_donor[1] = left; name_slot = left; }  // group.cpp:114-123
-            else { gr.qname_donor[0] = right; name_slot = right; }
-            gr.diff[0] = gr.diff[1] = 0;
-            gr.mismatch_inc[0] = gr.mismatch_inc[1] = 0;
-            gr.merge_reads = m;
-            gr.reverse_merge_reads = 0;
-            gr.status = 0;
-            gr.duplex_partner = -1;
-            gr.duplex_diff = 0;
-            gr.umi_pair = name_slot / 2;
-            int64_t orel = out_rel;
-#pragma unroll
-            for (int side = 0; side < 2; side++) {
-                const int l_out = side == 0 ? L_l : R_l, pos = side == 0 ? L_pos : R_pos, isize = side == 0 ? L_isize : R_isize;
-                const uint32_t cg = side == 0 ? L_cig : R_cig;
-                FsDesc fd = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, 0};
-                fd.c = c;
-                if (isize != 0 && gv.packed4 && contig >= 0 && contig < gv.n_contigs) {  // group.cpp:362-367 + reference.cpp:33-71
-                    const int64_t span = (int64_t)get_ref_offset(&cg, 1, l_out - 1) + 1;
-                    if ((int64_t)pos + span < gv.contig_len[contig]) {
-                        fd.flags |= FS_REF_OK;
-                        fd.ref_nib0 = 2 * gv.contig_off[contig] + pos;
-                    }
+            const int l_out = side == 0 ? L_l : R_l, pos = side == 0 ? L_pos : R_pos, isize = side == 0 ? L_isize : R_isize;
+            const uint32_t cg = side == 0 ? L_cig : R_cig;
+            FsDesc fd = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, 0};
+            fd.c = c;
+            if (isize != 0 && gv.packed4 && contig >= 0 && contig < gv.n_contigs) {  // group.cpp:362-367 + reference.cpp:33-71
+                const int64_t span = (int64_t)get_ref_offset(&cg, 1, l_out - 1) + 1;
+                if ((int64_t)pos + span < gv.contig_len[contig]) {
+                    fd.flags |= FS_REF_OK;
+                    fd.ref_nib0 = 2 * gv.contig_off[contig] + pos;
                 }
-                const int op = cig_op(cg);
-                if (query_consum(op) && ref_consum(op) && cig_len(cg) >= l_out) fd.flags |= FS_SIMPLE_CIGAR;
-                if (uni[side]) fd.flags |= FS_UNIFORM;
-                gr.out_off[side] = orel;  // cluster-relative; the vote rebases it after the scan
-                fd.mb = mb;
-                fd.m = (uint16_t)m;
-                fd.l_out = (uint16_t)l_out;
-                fd.len = (uint16_t)l_out;
-                fd.tmpl_k = 0;
-                fd.mode = SIDE_LEFT;
-                fd.out_rel = (uint32_t)orel;
-                if (orel > 0xFFFFFFFFll) fd.flags |= FS_NOFIT;
-                orel += record_bytes(l_out);
-                ws.fs_desc[2 * (int64_t)slot + side] = fd;
             }
-            *(uint16_t *)(ws.side_mode + 2 * (int64_t)slot) = (uint16_t)(SIDE_LEFT | (SIDE_LEFT << 8));
-            r.groups[slot] = gr;
+            const int op = cig_op(cg);
+            if (query_consum(op) && ref_consum(op) && cig_len(cg) >= l_out) fd.flags |= FS_SIMPLE_CIGAR;
+            if (uni[side]) fd.flags |= FS_UNIFORM;
+            gr.out_off[side] = orel;  // cluster-relative; the vote rebases it after the scan
+            fd.mb = mb;
+            fd.m = (uint16_t)m;
+            fd.l_out = (uint16_t)l_out;
+            fd.len = (uint16_t)l_out;
+            fd.tmpl_k = 0;
+            fd.mode = SIDE_LEFT;
+            fd.out_rel = (uint32_t)orel;
+            orel += record_bytes(l_out);
+            ws.fs_desc[2 * (int64_t)slot + side] = fd;
         }
-        out_rel += record_bytes(__shfl_sync(g.mask, L_l, first)) + record_bytes(__shfl_sync(g.mask, R_l, first));
-        mb += m;
+        *(uint16_t *)(ws.side_mode + 2 * (int64_t)slot) = (uint16_t)(SIDE_LEFT | (SIDE_LEFT << 8));
+        r.groups[slot] = gr;
     }
     if (lane == 0) {
-        ws.cluster_out_bytes[c] = out_rel;
+        ws.cluster_out_bytes[c] = (int64_t)(total & 0xFFFFFFu);
         GCB_COUNT(6, 1);
     }
     return true;
 }
+
 
 // group.cpp:68-134 per family of the cluster + the per-pair overlap windows of pair.cpp:103-119
 template <int GS>

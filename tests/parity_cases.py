@@ -105,7 +105,9 @@ def small_cases():
     out += [(f"{n}_1500", (lambda n=n: fixed_case(n, 1500))) for n in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5")]
     out += [("cfg2_6000", lambda: fixed_case("cfg2", 6000)),           # many tiles per CTA: the ring's stages are used again and again
             ("deep30_noisy", lambda: noisy_deep_case(1500, 30, 0.01)),
-            ("deep300_noisy", lambda: noisy_deep_case(1500, 300, 0.003))]  # clusters of ~130 KB: one tile fills the ring kernel's arena
+            ("deep300_noisy", lambda: noisy_deep_case(1500, 300, 0.003)),  # clusters of ~130 KB: one tile fills the ring kernel's arena
+            # many molecules per coordinate pair: more strand families per cluster than duplex_kernel gives lanes to one
+            ("cfg3_crowded", lambda: fixed_case("cfg3", 1500, contig_len=340, depth=3.0, err=0.01, insert_sigma=0.5))]
     return out
 
 

@@ -354,6 +354,16 @@ inline unsigned __ballot_sync(unsigned mask, int pred) {
         if ((mask >> i) & 1u) r |= (unsigned)(x[i] & 1) << i;
     return r;
 }
+template <typename T>
+inline unsigned __match_any_sync(unsigned mask, T v) {
+    simt::check_full(mask);
+    const uint64_t mine = simt::to_bits(v);
+    const uint64_t *x = simt::exchange(mine, mask);
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++)
+        if (((mask >> i) & 1u) && x[i] == mine) r |= 1u << i;
+    return r;
+}
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
 inline int __reduce_add_sync(unsigned mask, int v) {
