@@ -273,6 +273,28 @@ GCB_HD bool umi_is_duplex(const Umi &a, const Umi &b) {
     return true;
 }
 
+// The two strand forms of a UMI for Cluster::isDuplex: `canon` = part 0, '_', part 1 and `swapped` = part 1, '_', part 0 when
+// split() yields exactly two parts (returns false otherwise).  a and b are duplex partners iff canon(a) == swapped(b): the
+// parts hold no '_', so the strings are equal iff the parts are, crosswise.  Computed once per family by duplex_kernel
+// instead of two splits per candidate.
+GCB_HD void umi_put(Umi &u, int k, int f) { u.w[k >> 4] |= (uint64_t)f << (60 - 4 * (k & 15)); }
+GCB_HD bool umi_strand_forms(const Umi &u, Umi &canon, Umi &swapped) {
+#pragma unroll
+    for (int k = 0; k < GCB_MAX_UMI_WORDS; k++) canon.w[k] = swapped.w[k] = 0ull;
+    if (!umi_has_separator(u)) return false;
+    const UmiParts p = umi_split(u);
+    if (p.n != 2) return false;
+    int k = 0;
+    for (int q = p.b0; q < p.e0; q++) umi_put(canon, k++, umi_field(u, q));
+    umi_put(canon, k++, UMI_UNDERSCORE);
+    for (int q = p.b1; q < p.e1; q++) umi_put(canon, k++, umi_field(u, q));
+    k = 0;
+    for (int q = p.b1; q < p.e1; q++) umi_put(swapped, k++, umi_field(u, q));
+    umi_put(swapped, k++, UMI_UNDERSCORE);
+    for (int q = p.b0; q < p.e0; q++) umi_put(swapped, k++, umi_field(u, q));
+    return true;
+}
+
 // ---- sequence helpers ------------------------------------------------------------------------
 GCB_HD int base_at(const uint8_t *seq, int i) {  // bam_get_seq nibble order
     uint8_t b = seq[i >> 1];

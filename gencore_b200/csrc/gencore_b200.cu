@@ -900,6 +900,13 @@ void gcb_simt_counters(int64_t *out, int reset) {
         if (reset) g_simt_counters[k] = 0;
     }
 }
+// tests only: Cluster::isDuplex on two encoded UMIs, by the literal split (bit 0) and by the strand forms duplex_kernel compares (bit 1)
+int gcb_simt_is_duplex(const uint64_t *a, const uint64_t *b, int nw) {
+    const Umi ua = umi_load(a, nw), ub = umi_load(b, nw);
+    Umi ca, sa, cb, sb;
+    const bool ta = umi_strand_forms(ua, ca, sa), tb = umi_strand_forms(ub, cb, sb);
+    return (umi_is_duplex(ua, ub) ? 1 : 0) | ((ta && tb && umi_equal(ca, sb)) ? 2 : 0);
+}
 #endif
 
 }  // extern "C"

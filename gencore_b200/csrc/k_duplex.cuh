@@ -81,18 +81,56 @@ GCB_DEV int duplex_merge_staged(uint8_t *rec1, int len1, uint8_t *rec2, int len2
     return diff;
 }
 
-// The first differing byte of the two sequences' first `nbytes` bytes, found by the group's lanes together, a word per lane
-// and step (0x7FFFFFFF: none).  The records are 4-byte aligned and padded to whole words.
+// The first byte at or after `from` in which the two sequences' first `nbytes` bytes differ, found by the group's lanes
+// together, a word per lane and step (0x7FFFFFFF: none).  The records are 4-byte aligned and padded to whole words.
 template <int GS>
-GCB_DEV int first_diff_byte(const Grp<GS> &g, const uint8_t *seq1, const uint8_t *seq2, int nbytes) {
+GCB_DEV int first_diff_byte(const Grp<GS> &g, const uint8_t *seq1, const uint8_t *seq2, int nbytes, int from) {
     int k0 = 0x7FFFFFFF;
-    for (int w = g.gl; 4 * w < nbytes && k0 == 0x7FFFFFFF; w += GS) {
+    for (int w = (from >> 2) + g.gl; 4 * w < nbytes && k0 == 0x7FFFFFFF; w += GS) {
         uint32_t x = ((const uint32_t *)seq1)[w] ^ ((const uint32_t *)seq2)[w];
-        const int rem = nbytes - 4 * w;
+        const int rem = nbytes - 4 * w, skip = from - 4 * w;
         if (rem < 4) x &= (1u << (8 * rem)) - 1u;
+        if (skip > 0) x &= ~((1u << (8 * skip)) - 1u);  // (skip <= 3: only in the first word)
         if (x != 0u) k0 = 4 * w + ((__ffs((int)x) - 1) >> 3);
     }
     return g.min_of(k0);
+}
+
+// cluster.cpp:200-244 by a group of lanes: equal bytes only move the walk on by two positions, whatever its parity, so the
+// lanes look for the next differing byte together and lane 0 runs the reference's loop literally inside that byte (one or
+// two positions; its writes change this byte alone, which the walk then leaves).  Returns the differing positions.
+template <int GS>
+GCB_DEV int duplex_merge_group(const Grp<GS> &g, uint8_t *rec1, int len1, uint8_t *rec2, int len2) {
+    const int len = min(len1, len2), nbytes = (len + 1) >> 1;
+    uint8_t *qual1 = rec1, *qual2 = rec2;
+    uint8_t *seq1 = rec1 + GCB_ALIGN4(len1), *seq2 = rec2 + GCB_ALIGN4(len2);
+    int diff = 0, i = 0;
+    for (;;) {
+        const int kb = first_diff_byte(g, seq1, seq2, nbytes, i >> 1);
+        if (kb == 0x7FFFFFFF) break;
+        if (kb > (i >> 1)) i = 2 * kb + (i & 1);
+        if (g.gl == 0) {
+            for (; i < len && (i >> 1) == kb; i++) {
+                const uint8_t a = seq1[i >> 1], c = seq2[i >> 1];
+                if (a == c) {
+                    i++;
+                    continue;
+                }
+                const int b1 = (i & 1) ? (a & 0xF) : (a >> 4), b2 = (i & 1) ? (c & 0xF) : (c >> 4);
+                if (base_letter(b1) != base_letter(b2)) {
+                    diff++;
+                    qual1[i] = 0;
+                    qual2[i] = 0;
+                    const uint8_t m = (i & 1) ? 0x0F : 0xF0;
+                    seq1[i >> 1] = (uint8_t)(a | m);
+                    seq2[i >> 1] = (uint8_t)(c | m);
+                }
+            }
+        }
+        i = __shfl_sync(g.mask, i, g.base);
+        if (i >= len) break;
+    }
+    return __shfl_sync(g.mask, diff, g.base);
 }
 
 // The reference's loop over the stack for one cluster by two threads (side = 0 / 1): both walk the stack (same decisions),
@@ -202,16 +240,18 @@ __global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, Res
         tmpl[0] = row->tmpl_read[0]; tmpl[1] = row->tmpl_read[1];
         out_off[0] = row->out_off[0]; out_off[1] = row->out_off[1];
     }
-    const Umi u = umi_load(b.umi + (int64_t)(umi_pair >= 0 ? umi_pair : 0) * nw, umi_pair >= 0 ? nw : 0);
+    Umi canon, swapped;  // cluster.cpp:246-258 isDuplex(a, b) <=> canon(a) == swapped(b)
+    const bool two = umi_strand_forms(umi_load(b.umi + (int64_t)(umi_pair >= 0 ? umi_pair : 0) * nw, umi_pair >= 0 ? nw : 0), canon, swapped);
     unsigned alive = (1u << G) - 1u;
     int status = GCB_GROUP_DROPPED, partner = -1, ddiff = 0, rev = 0;
     while (alive != 0u) {
         const int g1 = 31 - __clz((int)alive);  // cluster.cpp:119-121: the back of the stack
         alive &= ~(1u << g1);
-        Umi u1;
+        Umi c1;
 #pragma unroll
-        for (int k = 0; k < GCB_MAX_UMI_WORDS; k++) u1.w[k] = __shfl_sync(g.mask, u.w[k], g.base + g1);
-        const bool match = ((alive >> lane) & 1u) != 0u && umi_is_duplex(u1, u);
+        for (int k = 0; k < GCB_MAX_UMI_WORDS; k++) c1.w[k] = __shfl_sync(g.mask, canon.w[k], g.base + g1);
+        const bool two1 = __shfl_sync(g.mask, (int)two, g.base + g1) != 0;
+        const bool match = ((alive >> lane) & 1u) != 0u && two && two1 && umi_equal(c1, swapped);
         const unsigned bal = g.ballot(match);
         const int mr1 = __shfl_sync(g.mask, merge_reads, g.base + g1);
         if (bal == 0u) {
@@ -229,14 +269,8 @@ __global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, Res
             const int l1 = b.reads[t1].l_qseq, l2 = b.reads[t2].l_qseq;
             if (o1 + record_bytes(l1) > r.out_capacity || o2 + record_bytes(l2) > r.out_capacity) continue;
             uint8_t *rec1 = r.out_payload + o1, *rec2 = r.out_payload + o2;
-            const int len = min(l1, l2);
             diff += l1 > l2 ? l1 - l2 : l2 - l1;
-            const int k0 = first_diff_byte(g, rec1 + GCB_ALIGN4(l1), rec2 + GCB_ALIGN4(l2), (len + 1) >> 1);
-            if (k0 != 0x7FFFFFFF) {
-                int d = 0;
-                if (lane == 0) d = duplex_walk(rec1, l1, rec2, l2, 2 * k0);
-                diff += __shfl_sync(g.mask, d, g.base);
-            }
+            diff += duplex_merge_group(g, rec1, l1, rec2, l2);
         }
         const int mr2 = __shfl_sync(g.mask, merge_reads, g.base + g2);
         if (lane == g1) {

@@ -263,6 +263,25 @@ GCB_DEV VoteRead make_vote_read(const BatchView &b, const Workspace &ws, int64_t
     return v;
 }
 
+// BamUtil::isPartOf (bamutil.cpp:204-255) on CIGARs of at most four ops held in registers
+GCB_DEV uint32_t cig_sel4(const uint32_t (&a)[4], int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
+GCB_DEV bool is_part_of4(const uint32_t (&cp)[4], int np, const uint32_t (&cw)[4], int nw, bool is_left) {
+    if (nw < np) return false;
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (i < np && ok) {
+            const uint32_t vp = cig_sel4(cp, is_left ? i : np - i - 1), vw = cig_sel4(cw, is_left ? i : nw - i - 1);
+            if (cig_op(vp) != cig_op(vw) || cig_len(vp) > cig_len(vw)) ok = false;
+            else if (cig_len(vp) < cig_len(vw) && i != np - 1) {
+                if (i != np - 2) ok = false;
+                else if (cig_op(cig_sel4(cp, is_left ? i + 1 : np - i - 2)) != OP_HARD_CLIP) ok = false;
+            }
+        }
+    }
+    return ok;
+}
+
 template <int GS>
 GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Workspace &ws, const gcb_options &o, int mb, int m, int side, int slot,
                                int64_t slab0) {
@@ -318,7 +337,71 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
     }
     bool leftReadMode = true;
     int best_cnt = m, best_k = 0;
-    if (!same) {
+    // The family in registers (at most GS pairs, CIGARs of at most four ops): lane k holds read k's length, position and CIGAR,
+    // and the O(m^2) containment counts of group.cpp:196-233 exchange them by shuffle.  From global memory every comparison is
+    // a chain of dependent loads (members -> descriptor -> CIGAR): half of this kernel's time on a library of ragged reads.
+    bool staged = !same && m <= GS;
+    uint32_t cg[4] = {0u, 0u, 0u, 0u};
+    int nc = 0, my_l = 0, my_pos = 0;
+    bool have_me = false;
+    if (staged) {
+        if (lane < m) {
+            const gcb_read_desc rd = b.reads[GCB_SLOT(lane)];
+            have_me = rd.l_qseq >= 0;
+            if (have_me) {
+                my_l = rd.l_qseq;
+                my_pos = rd.pos;
+                nc = rd.n_cigar;
+                if (nc <= 4) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (q < nc) cg[q] = b.cigar[rd.cigar_off + q];
+                }
+            }
+        }
+        staged = !g.any(nc > 4);
+    }
+    if (staged) {
+        leftReadMode = isLeft;
+        int rrp = 0;  // BamUtil::getRightRefPos (bamutil.cpp:379-383)
+        if (!isLeft) {  // group.cpp:177-194: every right read starts at the same position => left-aligned columns
+            const int lo = g.min_of(have_me ? my_pos : 0x7FFFFFFF), hi = g.max_of(have_me ? my_pos : -0x7FFFFFFF);
+            if (lo >= hi) leftReadMode = true;  // all equal, or no read at all
+            int rl = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) rl += cig_len(cg[q]) * ref_consum(cig_op(cg[q]));  // (absent ops are 0M)
+            rrp = my_pos < 0 ? -1 : my_pos + rl;
+        }
+        // group.cpp:196-233: containedBy[i] = 1 + #{j : read i is part of read j}
+        int cnt = 0;
+        for (int j = 0; j < m; j++) {
+            const int src = g.base + j;
+            const bool hj = __shfl_sync(g.mask, (int)have_me, src) != 0;
+            const int nj = __shfl_sync(g.mask, nc, src), rj = __shfl_sync(g.mask, rrp, src);
+            uint32_t cj[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) cj[q] = __shfl_sync(g.mask, cg[q], src);
+            if (j == lane || !have_me || !hj || (!isLeft && rrp != rj)) continue;
+            if (is_part_of4(cg, nc, cj, nj, leftReadMode)) cnt++;
+        }
+        cnt = have_me ? cnt + 1 : 0;
+        const int first_big = g.min_of((have_me && m > thr && cnt >= m / 2) ? lane : 0x7FFFFFFF);  // group.cpp:231-232: the scan stops there
+        // group.cpp:235-261: most contained, ties -> strictly shorter read, else first in map order
+        int best_len = 0;
+        best_cnt = -1;
+        best_k = 0x7FFFFFFF;
+        if (lane < m) {
+            best_cnt = lane > first_big ? 0 : cnt;
+            best_len = my_l;
+            best_k = lane;
+        }
+        for (int off = GS / 2; off > 0; off >>= 1) {
+            const int oc = g.shfl_xor(best_cnt, off), ol = g.shfl_xor(best_len, off), ok = g.shfl_xor(best_k, off);
+            if (oc > best_cnt || (oc == best_cnt && (ol < best_len || (ol == best_len && ok < best_k)))) {
+                best_cnt = oc; best_len = ol; best_k = ok;
+            }
+        }
+    } else if (!same) {
         leftReadMode = isLeft;
         if (!isLeft) {  // group.cpp:177-194: every right read starts at the same position => left-aligned columns
             int lo = 0x7FFFFFFF, hi = -0x7FFFFFFF;

@@ -177,3 +177,35 @@ def test_malformed_batches_are_refused(simt_lib, what):
         # the context stays usable
         res = eng.cluster_by_umi(batch)
     assert int(res.out_bytes[0]) > 0
+
+
+def test_duplex_strand_forms_match_is_duplex(simt_lib, oracle):
+    """duplex_kernel compares precomputed strand forms (device_common.cuh umi_strand_forms) instead of splitting both UMIs per
+    candidate: the same verdict as the literal split and as the oracle's Cluster::isDuplex on the reference's vectors, on
+    split() corner cases and on random strings."""
+    import random
+    import numpy as np
+    from gencore_b200.abi import encode_umi
+    from test_oracle_kat import ISDUPLEX_EXTRA, ISDUPLEX_KAT
+    lib = ctypes.CDLL(simt_lib)
+    lib.gcb_simt_is_duplex.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    rng = random.Random(5)
+    pairs = [(a.replace('B', 'C'), b.replace('B', 'C')) for a, b in [(a, b) for a, b, _ in ISDUPLEX_KAT] + list(ISDUPLEX_EXTRA)]  # ('B' has no code)
+    for _ in range(3000):
+        a = "".join(rng.choice("ACGT__") for _ in range(rng.randint(0, 9)))
+        if rng.random() < 0.5 and "_" in a:  # a true partner, or a near one
+            parts = a.split("_")
+            b = "_".join(reversed(parts)) if rng.random() < 0.7 else "_".join(parts[1:] + parts[:1])
+        else:
+            b = "".join(rng.choice("ACGT__") for _ in range(rng.randint(0, 9)))
+        pairs.append((a, b))
+    n_true = 0
+    for nw in (1, 2, 4):
+        for a, b in pairs:
+            ca, cb = np.ascontiguousarray(encode_umi(a, nw)), np.ascontiguousarray(encode_umi(b, nw))
+            for x, y, sx, sy in ((ca, cb, a, b), (cb, ca, b, a)):
+                got = lib.gcb_simt_is_duplex(x.ctypes.data, y.ctypes.data, nw)
+                want = bool(oracle.is_duplex(sx, sy))
+                assert got == (3 if want else 0), (sx, sy, got, want)
+                n_true += want
+    assert n_true > 100
