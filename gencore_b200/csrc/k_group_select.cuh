@@ -263,21 +263,17 @@ GCB_DEV VoteRead make_vote_read(const BatchView &b, const Workspace &ws, int64_t
     return v;
 }
 
-// BamUtil::isPartOf (bamutil.cpp:204-255) on CIGARs of at most four ops held in registers
-GCB_DEV uint32_t cig_sel4(const uint32_t (&a)[4], int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
-GCB_DEV bool is_part_of4(const uint32_t (&cp)[4], int np, const uint32_t (&cw)[4], int nw, bool is_left) {
-    if (nw < np) return false;
-    bool ok = true;
+// BamUtil::isPartOf (bamutil.cpp:204-255) on CIGARs of at most four ops held in registers IN COMPARISON ORDER: first op first
+// for left-aligned columns, last op first otherwise (so that every index below is a constant after unrolling)
+GCB_DEV bool is_part_of4(const uint32_t (&cp)[4], int np, const uint32_t (&cw)[4], int nw) {
+    bool ok = nw >= np;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        if (i < np && ok) {
-            const uint32_t vp = cig_sel4(cp, is_left ? i : np - i - 1), vw = cig_sel4(cw, is_left ? i : nw - i - 1);
-            if (cig_op(vp) != cig_op(vw) || cig_len(vp) > cig_len(vw)) ok = false;
-            else if (cig_len(vp) < cig_len(vw) && i != np - 1) {
-                if (i != np - 2) ok = false;
-                else if (cig_op(cig_sel4(cp, is_left ? i + 1 : np - i - 2)) != OP_HARD_CLIP) ok = false;
-            }
-        }
+        const uint32_t vp = cp[i], vw = cw[i];
+        bool fine = cig_op(vp) == cig_op(vw) && cig_len(vp) <= cig_len(vw);
+        // a shorter op is allowed in the last place, or in the last but one before a hard clip
+        if (cig_len(vp) < cig_len(vw) && i != np - 1) fine = fine && i == np - 2 && cig_op(cp[(i + 1) & 3]) == OP_HARD_CLIP;  // (i == np - 2 implies i < 3)
+        ok = ok && (i >= np || fine);
     }
     return ok;
 }
@@ -373,16 +369,18 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
             rrp = my_pos < 0 ? -1 : my_pos + rl;
         }
         // group.cpp:196-233: containedBy[i] = 1 + #{j : read i is part of read j}
+        uint32_t co[4];  // the CIGAR in comparison order
+#pragma unroll
+        for (int q = 0; q < 4; q++) co[q] = leftReadMode ? cg[q] : (nc - 1 - q == 0 ? cg[0] : nc - 1 - q == 1 ? cg[1] : nc - 1 - q == 2 ? cg[2] : nc - 1 - q == 3 ? cg[3] : 0u);
+        const int meta = nc | (have_me ? 0x100 : 0);
         int cnt = 0;
         for (int j = 0; j < m; j++) {
             const int src = g.base + j;
-            const bool hj = __shfl_sync(g.mask, (int)have_me, src) != 0;
-            const int nj = __shfl_sync(g.mask, nc, src), rj = __shfl_sync(g.mask, rrp, src);
+            const int mj = __shfl_sync(g.mask, meta, src), rj = isLeft ? 0 : __shfl_sync(g.mask, rrp, src);
             uint32_t cj[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) cj[q] = __shfl_sync(g.mask, cg[q], src);
-            if (j == lane || !have_me || !hj || (!isLeft && rrp != rj)) continue;
-            if (is_part_of4(cg, nc, cj, nj, leftReadMode)) cnt++;
+            for (int q = 0; q < 4; q++) cj[q] = __shfl_sync(g.mask, co[q], src);
+            if (j != lane && have_me && (mj & 0x100) && (isLeft || rrp == rj) && is_part_of4(co, nc, cj, mj & 0xFF)) cnt++;
         }
         cnt = have_me ? cnt + 1 : 0;
         const int first_big = g.min_of((have_me && m > thr && cnt >= m / 2) ? lane : 0x7FFFFFFF);  // group.cpp:231-232: the scan stops there

@@ -107,7 +107,7 @@ def small_cases():
             ("deep30_noisy", lambda: noisy_deep_case(1500, 30, 0.01)),
             ("deep300_noisy", lambda: noisy_deep_case(1500, 300, 0.003)),  # clusters of ~130 KB: one tile fills the ring kernel's arena
             # many molecules per coordinate pair: more strand families per cluster than duplex_kernel gives lanes to one
-            ("cfg3_crowded", lambda: fixed_case("cfg3", 1500, contig_len=340, depth=3.0, err=0.01, insert_sigma=0.5))]
+            ("cfg3_crowded", lambda: fixed_case("cfg3", 1500, contig_len=245, depth=2.0, err=0.01, insert_sigma=0.5))]
     return out
 
 
