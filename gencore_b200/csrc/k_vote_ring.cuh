@@ -23,9 +23,8 @@
 //                     the queued columns at full occupancy.  A full queue hands the tile to the generic kernel.  The ring
 //                     never waits for a slow column.  (Measured alternatives, profiles/r03_notes.md.)
 //   deep tiles        (24 pairs or more per family side on average: few bundles, hundreds of slow columns per tile) keep
-//                     their list in the stage; when every warp has arrived on the slot's `listed` barrier the group's first warp
-//                     closes the list (prefix sums of the entries' column counts, then the `closed` barrier), and ALL voter
-//                     warps of the tile then decide the columns, 32 at a time, one
+//                     their list in the stage; the warp that finishes the tile's last bundle closes it (prefix sums of the
+//                     entries' column counts), and ALL voter warps of the tile then decide the columns, 32 at a time, one
 //                     thread per column, straight from the staged slab — a deep tile has nothing else for them to do, and
 //                     its reads never cross HBM a second time.
 #pragma once
@@ -60,22 +59,19 @@ struct __align__(16) RingStage {  // shared memory; the first part is written by
     int32_t deep;          // the tile's slow columns are decided here, by all the voter warps together (see the header)
     // the voters' part
     int32_t next_bundle;   // atomic: next bundle to hand out
-    int32_t unused0;
+    int32_t done;          // atomic: bundles finished
     int32_t n_entries;     // atomic: slow-column list entries
-    int32_t closed;        // the tile was handed to the generic kernel (the slow-column queue was full)
+    int32_t closed;        // deep tiles: the list is complete and its prefix sums are written
     int32_t drain_total;   // deep tiles: slow columns of the tile
     int32_t next_col;      // deep tiles, atomic: next slow column to decide
-    int32_t deep_par;      // deep tiles: the phase parity of the slot's `listed` / `closed` barriers for this tile (written by the producer)
-    int32_t pad;
+    int32_t pad[2];
 };
 static_assert(sizeof(RingStage) == 96, "stage header size");
 
 // shared-memory map: [barriers][stage headers][producer's header cache][arena]
 constexpr int VR_OFF_FULL = 0;                                   // uint64[VR_MAX_STAGES]
 constexpr int VR_OFF_EMPTY = 8 * VR_MAX_STAGES;                  // uint64[VR_MAX_STAGES]
-constexpr int VR_OFF_LISTED = 16 * VR_MAX_STAGES;                // uint64[VR_MAX_STAGES]  deep tiles: every voter warp has written its slow-column list entries
-constexpr int VR_OFF_CLOSED = 24 * VR_MAX_STAGES;                // uint64[VR_MAX_STAGES]  deep tiles: the list's prefix sums are written
-constexpr int VR_OFF_HDR = 32 * VR_MAX_STAGES;                   // RingStage[VR_MAX_STAGES]
+constexpr int VR_OFF_HDR = 16 * VR_MAX_STAGES;                   // RingStage[VR_MAX_STAGES]
 constexpr int VR_OFF_HCACHE = VR_OFF_HDR + 96 * VR_MAX_STAGES;   // TileHdr2[32]: the producer's next tiles
 constexpr int VR_ITEMS = 64;       // slow columns of one bundle that are emitted per round
 #ifndef GCB_VR_DEEP_CHUNK
@@ -120,7 +116,6 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
     if (batch_is_malformed(ws.error_flag)) return;  // (every thread of the grid sees the same flag: the kernels that raise it have finished)
     uint64_t *full = (uint64_t *)(smem + VR_OFF_FULL);
     uint64_t *empty = (uint64_t *)(smem + VR_OFF_EMPTY);
-    uint64_t *listed = (uint64_t *)(smem + VR_OFF_LISTED), *closed_bar = (uint64_t *)(smem + VR_OFF_CLOSED);
     RingStage *shdr = (RingStage *)(smem + VR_OFF_HDR);
 #define GCB_LDS32(off) (*(const uint32_t *)(smem + (off)))
     const int tid = (int)threadIdx.x, lane = lane_id(), warp = tid >> 5;
@@ -133,8 +128,6 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         for (int s = 0; s < n_stages; s++) {
             pipe_init(full + s, 1);
             pipe_init(empty + s, wpg);  // every voter warp of the tile's group arrives once when it leaves the tile
-            pipe_init(listed + s, wpg);  // (deep tiles only: the phases of these two count the deep tiles the slot has held)
-            pipe_init(closed_bar + s, 1);
         }
         pipe_fence_init();
     }
@@ -149,7 +142,6 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         // slot k % n_stages (barriers, header) once the tile that used it before is released
         int k_tail = 0;
         uint32_t head = 0u, off_of[VR_MAX_STAGES];
-        uint32_t deep_phase = 0u;  // bit s: parity of the deep tiles slot s has held
         auto release_oldest = [&]() {
             const int s = k_tail % n_stages, use = k_tail / n_stages;
             GCB_TRACE(200 + s);
@@ -195,13 +187,12 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
             sh.sl_cap = max(cur.nfs, 0) * cur.lanes;
             sh.deep = tile_is_deep(cur.nfs, cur.np) ? 1 : 0;  // few bundles, long lists of slow columns
             sh.next_bundle = 0;
-            sh.unused0 = 0;
+            sh.done = 0;
             sh.n_entries = 0;
             sh.closed = 0;
             sh.drain_total = 0;
             sh.next_col = 0;
-            sh.deep_par = 0;
-            sh.pad = 0;
+            sh.pad[0] = sh.pad[1] = 0;
         };
         for (int64_t base = (int64_t)blockIdx.x; base < n_tiles; base += (int64_t)WARP * gridDim.x) {
             const int64_t mine_t = base + (int64_t)lane * gridDim.x;
@@ -218,10 +209,6 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                     const int s = k % n_stages;
                     RingStage sh;
                     fill(sh, cur, (int32_t)t, at);
-                    if (sh.deep) {
-                        sh.deep_par = (int32_t)((deep_phase >> s) & 1u);
-                        deep_phase ^= 1u << s;
-                    }
                     shdr[s] = sh;
                     pipe_expect(full + s, slab_bytes + vr_bytes + ft_bytes);
                     if (slab_bytes > 0) tile_copy(smem + sh.slab_off, b.payload + cur.slab0, slab_bytes, full + s);
@@ -277,6 +264,7 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
         int bundle = nb;
         if (lane == 0 && *(volatile int32_t *)&sh->next_bundle < nb) bundle = atomicAdd(&sh->next_bundle, 1);  // (no atomic on a drained tile)
         bundle = __shfl_sync(FULL, bundle, 0);
+        bool closer = false;
         if (bundle < nb) {
             if (sh->lanes != cur_L) {  // a lane owns sixteen columns; a family side takes L lanes, a bundle 32 / L family sides
                 cur_L = sh->lanes;
@@ -459,6 +447,15 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                         at = __shfl_sync(FULL, at, 0);
                         if (mask16 != 0u) s_list[at + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)f << 21) | ((uint32_t)j << 16) | mask16;
                     }
+                    // ... and the warp that finishes the tile's last bundle closes the tile
+                    __syncwarp();
+                    int fin = 0;
+                    if (lane == 0) {
+                        __threadfence_block();
+                        fin = atomicAdd(&sh->done, 1) + 1;
+                    }
+                    fin = __shfl_sync(FULL, fin, 0);
+                    closer = fin == nb;
                 } else if (bal != 0u) {
                     // ... or a record per slow column in the global queue: records of one size per bundle, from the warp's own
                     // pool of reserved queue space
@@ -557,38 +554,35 @@ __global__ void __launch_bounds__(VR_THREADS, 1) vote_ring_kernel(BatchView b, R
                 pipe_progress();
             } while (bundle < nb);
         }
-        if (deep) {
-            // Every voter warp of the tile arrives on `listed` when it has no bundle left (its list entries are written); the
-            // group's first warp then writes the prefix sums of the entries' column counts and completes `closed`; every warp waits
-            // for that and decides slow columns, 32 at a time, one thread per column, straight from the staged slab: a deep tile
-            // has hundreds of them and nothing else for the warps to do.  (Barrier objects, not flags and fences: the orderings
-            // are the memory model's, and compute-sanitizer's racecheck can see them.)
-            const uint32_t dpar = (uint32_t)sh->deep_par;
-            __syncwarp();
-            if (lane == 0) pipe_arrive(listed + s);
-            if ((warp - 1) / n_groups == 0) {
-                pipe_wait(listed + s, dpar, 1000u);
-                const int n = sh->n_entries;
-                uint32_t *s_list = (uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap;
-                int run = 0;
-                for (int base = 0; base < n; base += WARP) {
-                    const int i = base + lane;
-                    int incl = i < n ? __popc(s_list[i] & 0xFFFFu) : 0;
-                    for (int off = 1; off < WARP; off <<= 1) {
-                        const int v = __shfl_up_sync(FULL, incl, off);
-                        if (lane >= off) incl += v;
-                    }
-                    if (i < n) s_pf[i] = (uint32_t)(run + incl);
-                    run += __shfl_sync(FULL, incl, WARP - 1);
+        if (closer) {
+            // every bundle of the (deep) tile is done: prefix sums of the entries' column counts, then the list is open to every warp
+            __threadfence_block();
+            const int n = *(volatile int32_t *)&sh->n_entries;
+            uint32_t *s_list = (uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap;
+            int run = 0;
+            for (int base = 0; base < n; base += WARP) {
+                const int i = base + lane;
+                int incl = i < n ? __popc(s_list[i] & 0xFFFFu) : 0;
+                for (int off = 1; off < WARP; off <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, off);
+                    if (lane >= off) incl += v;
                 }
-                __syncwarp();
-                if (lane == 0) {
-                    sh->drain_total = run;
-                    pipe_arrive(closed_bar + s);
-                }
+                if (i < n) s_pf[i] = (uint32_t)(run + incl);
+                run += __shfl_sync(FULL, incl, WARP - 1);
             }
-            while (!pipe_try_wait(closed_bar + s, dpar, 1000u)) pipe_relax(400u);  // (fourteen warps wait while one or two vote; the length of the nap does not matter: 100 to 1000 ns measured)
-            const int total = sh->drain_total, n = sh->n_entries;
+            __syncwarp();
+            if (lane == 0) {
+                sh->drain_total = run;
+                __threadfence_block();
+                *(volatile int32_t *)&sh->closed = 1;
+            }
+        }
+        if (deep) {
+            // every voter warp waits for the tile to be closed and then decides slow columns, 32 at a time, one thread per
+            // column, straight from the staged slab: a deep tile has hundreds of them and nothing else for the warps to do
+            while (*(volatile int32_t *)&sh->closed == 0) pipe_relax(400u);  // (thirteen warps poll while two vote; the length of the nap does not matter: 100 to 1000 ns measured)
+            __threadfence_block();
+            const int total = *(volatile int32_t *)&sh->drain_total, n = *(volatile int32_t *)&sh->n_entries;
             const uint32_t *s_list = (const uint32_t *)(smem + sh->sl_off), *s_pf = s_list + sh->sl_cap;
             const int ft_off = sh->ft_off, vr_off = sh->vr_off, slab_off = sh->slab_off;
             const int64_t out_base0 = sh->out_base0;
