@@ -353,8 +353,10 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         }
     }
     if (stages & GCB_STAGE_DUPLEX) {
-        GCB_LAUNCH(duplex_kernel, dim3((unsigned)((DUPLEX_GS * (int64_t)nc + DUPLEX_THREADS - 1) / DUPLEX_THREADS)), dim3(DUPLEX_THREADS), 0, stream, b, r, ws,
-                   ctx->opt);
+        const int gs_dup = (int64_t)(v.p1 - v.p0) / nc <= 12 ? 8 : 16;  // lanes per cluster = families it pairs up in registers
+        const dim3 grid_dup((unsigned)((gs_dup * (int64_t)nc + DUPLEX_THREADS - 1) / DUPLEX_THREADS));
+        if (gs_dup == 8) GCB_LAUNCH(duplex_kernel<8>, grid_dup, dim3(DUPLEX_THREADS), 0, stream, b, r, ws, ctx->opt);
+        else GCB_LAUNCH(duplex_kernel<16>, grid_dup, dim3(DUPLEX_THREADS), 0, stream, b, r, ws, ctx->opt);
         ctx->launches++;
         // ... and the Stats side effects of the clusters' verdicts
         const unsigned stats_grid = (unsigned)((nc + STATS_THREADS - 1) / STATS_THREADS);

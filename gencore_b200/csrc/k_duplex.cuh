@@ -1,6 +1,6 @@
 // k_duplex.cuh — the tail of Cluster::clusterByUMI (cluster.cpp:102-188): duplex partner search,
 // Cluster::duplexMerge / duplexMergeBam (cluster.cpp:190-244) on the consensus records the vote
-// kernel wrote, and the SSCS / DCS / dropped verdict of every family.  Sixteen lanes per cluster, a family
+// kernel wrote, and the SSCS / DCS / dropped verdict of every family.  Eight or sixteen lanes per cluster, a family
 // per lane (duplex_kernel below); the partner search is a sequential stack walk in the reference and its order decides
 // who pairs up.
 #pragma once
@@ -200,12 +200,14 @@ GCB_DEV void duplex_cluster_pairwise(const BatchView &b, const ResultView &r, co
     }
 }
 
-// DUPLEX_GS lanes per cluster (sixteen), lane i holds family i (its UMI, its sizes, where its consensus records lie).  The stack of
+// DUPLEX_GS lanes per cluster (eight or sixteen), lane i holds family i (its UMI, its sizes, where its consensus records lie).  The stack of
 // cluster.cpp:119-168 keeps the families in creation order, so it is a bit mask: the popped family is its highest bit, the
 // partner the lowest bit whose UMI is the swap — every lane tests its own family, one ballot finds the partner.  The merge
 // (cluster.cpp:200-244) is a walk whose outcome depends on its own writes, but only from the first differing byte on: the
 // lanes find that byte together (a word each), and only strand pairs that differ anywhere are walked, by one lane, from there.
-constexpr int DUPLEX_GS = 16;  // (clusters with more families take the two-lane walk: rare, and slow)
+// (Clusters with more families than lanes take the two-lane walk: rare, and slow — the host gives sixteen lanes to batches of
+// larger clusters: 0.154 -> 0.056 ms on the cfg4 shape, where a few clusters in a thousand have nine or more families.)
+template <int DUPLEX_GS>
 __global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, ResultView r, Workspace ws, gcb_options o) {
     GCB_GRID_DEP();
     __shared__ uint32_t s_stage[DUPLEX_THREADS / DUPLEX_GS][2][2][DUPLEX_STAGE_WORDS];

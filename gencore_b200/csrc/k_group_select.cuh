@@ -263,21 +263,6 @@ GCB_DEV VoteRead make_vote_read(const BatchView &b, const Workspace &ws, int64_t
     return v;
 }
 
-// BamUtil::isPartOf (bamutil.cpp:204-255) on CIGARs of at most four ops held in registers IN COMPARISON ORDER: first op first
-// for left-aligned columns, last op first otherwise (so that every index below is a constant after unrolling)
-GCB_DEV bool is_part_of4(const uint32_t (&cp)[4], int np, const uint32_t (&cw)[4], int nw) {
-    bool ok = nw >= np;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t vp = cp[i], vw = cw[i];
-        bool fine = cig_op(vp) == cig_op(vw) && cig_len(vp) <= cig_len(vw);
-        // a shorter op is allowed in the last place, or in the last but one before a hard clip
-        if (cig_len(vp) < cig_len(vw) && i != np - 1) fine = fine && i == np - 2 && cig_op(cp[(i + 1) & 3]) == OP_HARD_CLIP;  // (i == np - 2 implies i < 3)
-        ok = ok && (i >= np || fine);
-    }
-    return ok;
-}
-
 template <int GS>
 GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Workspace &ws, const gcb_options &o, int mb, int m, int side, int slot,
                                int64_t slab0) {
@@ -333,73 +318,7 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
     }
     bool leftReadMode = true;
     int best_cnt = m, best_k = 0;
-    // The family in registers (at most GS pairs, CIGARs of at most four ops): lane k holds read k's length, position and CIGAR,
-    // and the O(m^2) containment counts of group.cpp:196-233 exchange them by shuffle.  From global memory every comparison is
-    // a chain of dependent loads (members -> descriptor -> CIGAR): half of this kernel's time on a library of ragged reads.
-    bool staged = !same && m <= GS;
-    uint32_t cg[4] = {0u, 0u, 0u, 0u};
-    int nc = 0, my_l = 0, my_pos = 0;
-    bool have_me = false;
-    if (staged) {
-        if (lane < m) {
-            const gcb_read_desc rd = b.reads[GCB_SLOT(lane)];
-            have_me = rd.l_qseq >= 0;
-            if (have_me) {
-                my_l = rd.l_qseq;
-                my_pos = rd.pos;
-                nc = rd.n_cigar;
-                if (nc <= 4) {
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        if (q < nc) cg[q] = b.cigar[rd.cigar_off + q];
-                }
-            }
-        }
-        staged = !g.any(nc > 4);
-    }
-    if (staged) {
-        leftReadMode = isLeft;
-        int rrp = 0;  // BamUtil::getRightRefPos (bamutil.cpp:379-383)
-        if (!isLeft) {  // group.cpp:177-194: every right read starts at the same position => left-aligned columns
-            const int lo = g.min_of(have_me ? my_pos : 0x7FFFFFFF), hi = g.max_of(have_me ? my_pos : -0x7FFFFFFF);
-            if (lo >= hi) leftReadMode = true;  // all equal, or no read at all
-            int rl = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) rl += cig_len(cg[q]) * ref_consum(cig_op(cg[q]));  // (absent ops are 0M)
-            rrp = my_pos < 0 ? -1 : my_pos + rl;
-        }
-        // group.cpp:196-233: containedBy[i] = 1 + #{j : read i is part of read j}
-        uint32_t co[4];  // the CIGAR in comparison order
-#pragma unroll
-        for (int q = 0; q < 4; q++) co[q] = leftReadMode ? cg[q] : (nc - 1 - q == 0 ? cg[0] : nc - 1 - q == 1 ? cg[1] : nc - 1 - q == 2 ? cg[2] : nc - 1 - q == 3 ? cg[3] : 0u);
-        const int meta = nc | (have_me ? 0x100 : 0);
-        int cnt = 0;
-        for (int j = 0; j < m; j++) {
-            const int src = g.base + j;
-            const int mj = __shfl_sync(g.mask, meta, src), rj = isLeft ? 0 : __shfl_sync(g.mask, rrp, src);
-            uint32_t cj[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) cj[q] = __shfl_sync(g.mask, co[q], src);
-            if (j != lane && have_me && (mj & 0x100) && (isLeft || rrp == rj) && is_part_of4(co, nc, cj, mj & 0xFF)) cnt++;
-        }
-        cnt = have_me ? cnt + 1 : 0;
-        const int first_big = g.min_of((have_me && m > thr && cnt >= m / 2) ? lane : 0x7FFFFFFF);  // group.cpp:231-232: the scan stops there
-        // group.cpp:235-261: most contained, ties -> strictly shorter read, else first in map order
-        int best_len = 0;
-        best_cnt = -1;
-        best_k = 0x7FFFFFFF;
-        if (lane < m) {
-            best_cnt = lane > first_big ? 0 : cnt;
-            best_len = my_l;
-            best_k = lane;
-        }
-        for (int off = GS / 2; off > 0; off >>= 1) {
-            const int oc = g.shfl_xor(best_cnt, off), ol = g.shfl_xor(best_len, off), ok = g.shfl_xor(best_k, off);
-            if (oc > best_cnt || (oc == best_cnt && (ol < best_len || (ol == best_len && ok < best_k)))) {
-                best_cnt = oc; best_len = ol; best_k = ok;
-            }
-        }
-    } else if (!same) {
+    if (!same) {
         leftReadMode = isLeft;
         if (!isLeft) {  // group.cpp:177-194: every right read starts at the same position => left-aligned columns
             int lo = 0x7FFFFFFF, hi = -0x7FFFFFFF;
