@@ -147,6 +147,57 @@ __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, R
         }
     }
 
+    if (n <= GS) {
+        // The usual cluster in registers, a pair per lane: the multiplicity of a pair's UMI is the population of a match mask,
+        // the round's top UMI comes from word-wise minimum reductions, the unassigned pairs are a bit mask.  (The loops below
+        // re-read every UMI of the cluster from memory for every pair and every round.)
+        const bool act = lane < n;
+        const unsigned actmask = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+        UmiT<NW> u;
+#pragma unroll
+        for (int k = 0; k < NW; k++) u.w[k] = act ? umi[(int64_t)lane * NW + k] : 0ull;
+        unsigned eq = actmask;
+#pragma unroll
+        for (int k = 0; k < NW; k++) eq &= __match_any_sync(g.mask, u.w[k]) >> g.base;
+        const int cnt = __popc(eq);  // cluster.cpp:57-65
+        const bool has_umi = g.any(act && (u.w[0] >> 60) != 0);
+        if (lane == 0) ws.cluster_has_umi[c] = has_umi ? 1 : 0;
+        unsigned un = actmask;  // the pairs no family has absorbed yet
+        int gi = 0, filled = 0, mine = -1;
+        while (un != 0u) {  // cluster.cpp:66-100
+            const bool cand = ((un >> lane) & 1u) != 0u;
+            const int top = g.max_of(cand ? cnt : -1);
+            bool in = cand && cnt == top;  // of the most frequent UMIs, the first in string order
+            UmiT<NW> best;
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                const unsigned hi = (unsigned)(u.w[k] >> 32), lo = (unsigned)u.w[k];
+                const unsigned mh = __reduce_min_sync(g.mask, in ? hi : 0xFFFFFFFFu);
+                in = in && hi == mh;
+                const unsigned ml = __reduce_min_sync(g.mask, in ? lo : 0xFFFFFFFFu);
+                in = in && lo == ml;
+                best.w[k] = ((uint64_t)mh << 32) | ml;
+            }
+            const bool absorb = cand && umit_diff<NW>(u, best) <= thr;
+            const unsigned m = g.ballot(absorb);
+            if (absorb) {
+                ws.members[p0 + filled + __popc(m & ((1u << lane) - 1u))] = p0 + lane;
+                mine = gi;
+            }
+            if (lane == 0) ws.group_off[p0 + gi] = p0 + filled;
+            if (m == 0u) {  // cannot happen (the top UMI is within 0 of itself); never spin on bad input
+                if (lane == 0) raise_error(ws.error_flag, GCB_ERR_MALFORMED);
+                break;
+            }
+            filled += __popc(m);
+            un &= ~m;
+            gi++;
+        }
+        if (act) r.pair_group[p0 + lane] = mine;
+        if (lane == 0) r.cluster_n_groups[c] = gi;
+        return;
+    }
+
     // multiplicity of every pair's UMI inside the cluster (cluster.cpp:57-65)
     bool has = false;
     for (int i = lane; i < n; i += GS) {

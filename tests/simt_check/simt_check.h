@@ -391,6 +391,23 @@ inline int __reduce_max_sync(unsigned mask, int v) {
     return r;
 }
 
+inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
+    simt::check_full(mask);
+    const uint64_t *x = simt::exchange(simt::to_bits(v), mask);
+    unsigned r = 0xFFFFFFFFu;
+    for (int i = 0; i < 32; i++)
+        if ((mask >> i) & 1u) r = std::min(r, simt::from_bits<unsigned>(x[i]));
+    return r;
+}
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+    simt::check_full(mask);
+    const uint64_t *x = simt::exchange(simt::to_bits(v), mask);
+    unsigned r = 0u;
+    for (int i = 0; i < 32; i++)
+        if ((mask >> i) & 1u) r = std::max(r, simt::from_bits<unsigned>(x[i]));
+    return r;
+}
+
 template <typename T>
 inline T __ldg(const T *p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
