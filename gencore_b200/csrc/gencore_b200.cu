@@ -263,11 +263,12 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         }
         return GCB_OK;
     }
-    // umi_group_kernel / select_template_kernel give GS lanes to a cluster: 8 while clusters are small, a whole warp when deep
+    // umi_group_kernel / select_template_kernel give GS lanes to a cluster and keep a cluster of at most GS pairs in registers:
+    // wide enough for most of the batch's clusters to take that path
     int gs = ctx->group_lanes;
     if (gs != 8 && gs != 16 && gs != 32) {
         const int64_t avg = (int64_t)(v.p1 - v.p0) / nc;
-        gs = avg <= 12 ? 8 : avg <= 24 ? 16 : 32;
+        gs = avg <= 4 ? 8 : avg <= 12 ? 16 : 32;
     }
     const int clusters_per_cta = (GROUP_THREADS / WARP) * (WARP / gs);
     const unsigned grid_clusters = (unsigned)((nc + clusters_per_cta - 1) / clusters_per_cta);
