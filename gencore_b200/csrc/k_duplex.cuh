@@ -233,14 +233,16 @@ __global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, Res
         return;
     }
     const bool fam = lane < G;
-    int umi_pair = -1, merge_reads = 0, tmpl[2] = {-1, -1};
+    int umi_pair = -1, merge_reads = 0, tlen[2] = {-1, -1};  // tlen: l_qseq of the family's template on either side, -1 = no record
     long long out_off[2] = {0, 0};
     if (fam) {
         const gcb_group_result *row = gr + lane;
         umi_pair = row->umi_pair;
         merge_reads = row->merge_reads;
-        tmpl[0] = row->tmpl_read[0]; tmpl[1] = row->tmpl_read[1];
+        const int t0 = row->tmpl_read[0], t1 = row->tmpl_read[1];
         out_off[0] = row->out_off[0]; out_off[1] = row->out_off[1];
+        if (t0 >= 0) tlen[0] = b.reads[t0].l_qseq;  // (loaded once per family, not once per merge: the loop below is a chain of dependent loads as it is)
+        if (t1 >= 0) tlen[1] = b.reads[t1].l_qseq;
     }
     Umi canon, swapped;  // cluster.cpp:246-258 isDuplex(a, b) <=> canon(a) == swapped(b)
     const bool two = umi_strand_forms(umi_load(b.umi + (int64_t)(umi_pair >= 0 ? umi_pair : 0) * nw, umi_pair >= 0 ? nw : 0), canon, swapped);
@@ -265,10 +267,9 @@ __global__ void __launch_bounds__(DUPLEX_THREADS) duplex_kernel(BatchView b, Res
         int diff = 0;  // Cluster::duplexMerge, cluster.cpp:190-198
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-            const int t1 = __shfl_sync(g.mask, tmpl[s], g.base + g1), t2 = __shfl_sync(g.mask, tmpl[s], g.base + g2);
+            const int l1 = __shfl_sync(g.mask, tlen[s], g.base + g1), l2 = __shfl_sync(g.mask, tlen[s], g.base + g2);
             const long long o1 = __shfl_sync(g.mask, out_off[s], g.base + g1), o2 = __shfl_sync(g.mask, out_off[s], g.base + g2);
-            if (t1 < 0 || t2 < 0) continue;
-            const int l1 = b.reads[t1].l_qseq, l2 = b.reads[t2].l_qseq;
+            if (l1 < 0 || l2 < 0) continue;
             if (o1 + record_bytes(l1) > r.out_capacity || o2 + record_bytes(l2) > r.out_capacity) continue;
             uint8_t *rec1 = r.out_payload + o1, *rec2 = r.out_payload + o2;
             diff += l1 > l2 ? l1 - l2 : l2 - l1;
