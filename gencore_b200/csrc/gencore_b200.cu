@@ -354,7 +354,8 @@ int launch_stages(gcb_ctx *ctx, const gcb_batch &batch, const gcb_result &result
         }
     }
     if (stages & GCB_STAGE_DUPLEX) {
-        const int gs_dup = (int64_t)(v.p1 - v.p0) / nc <= 12 ? 8 : 16;  // lanes per cluster = families it pairs up in registers
+        // lanes per cluster = families it pairs up in registers (the tuning knob of the other two kernels applies here too)
+        const int gs_dup = ctx->group_lanes == 8 ? 8 : (ctx->group_lanes == 16 || ctx->group_lanes == 32) ? 16 : (int64_t)(v.p1 - v.p0) / nc <= 12 ? 8 : 16;
         const dim3 grid_dup((unsigned)((gs_dup * (int64_t)nc + DUPLEX_THREADS - 1) / DUPLEX_THREADS));
         if (gs_dup == 8) GCB_LAUNCH(duplex_kernel<8>, grid_dup, dim3(DUPLEX_THREADS), 0, stream, b, r, ws, ctx->opt);
         else GCB_LAUNCH(duplex_kernel<16>, grid_dup, dim3(DUPLEX_THREADS), 0, stream, b, r, ws, ctx->opt);

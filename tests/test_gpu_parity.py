@@ -81,7 +81,7 @@ def test_small_tile_window_matches_oracle(engine_cls, oracle, name, thunk):
 
 @pytest.mark.parametrize("lanes", [8, 16, 32])
 @pytest.mark.parametrize("name", ["cfg2_40k", "cfg4_40k", "edge_default", "ragged_duplex_5_big", "ragged_single_4_big", "deep_1100", "low_complexity",
-                                  "wide_umi_3", "cfg3_40k", "tiny_reads", "cfg5_40k"])
+                                  "wide_umi_3", "cfg3_40k", "tiny_reads", "cfg5_40k", "cfg3_crowded"])
 def test_lanes_per_cluster_do_not_change_results(engine_cls, oracle, name, lanes):
     """umi_group_kernel / select_template_kernel with 8, 16 or 32 lanes per cluster."""
     batch, genome, opt = dict(CASES)[name]()

@@ -108,7 +108,7 @@ def test_slow_queue_overflow_does_not_change_results(simt_lib, oracle, name, qby
 
 
 @pytest.mark.parametrize("name,lanes", [(n, l) for n in ["golden_cfg2_600", "golden_cfg4_600", "edge_default", "ragged_duplex_2", "ragged_single_1",
-                                                         "low_complexity", "wide_umi_3", "cfg3_1500", "tiny_reads", "cfg5_1500"] for l in [8, 16, 32]] +
+                                                         "low_complexity", "wide_umi_3", "cfg3_1500", "tiny_reads", "cfg5_1500", "cfg3_crowded"] for l in [8, 16, 32]] +
                          [("deep_1100", 8)])
 def test_lanes_per_cluster_do_not_change_results(simt_lib, oracle, name, lanes):
     """umi_group_kernel / select_template_kernel with 8, 16 or 32 lanes per cluster (groups of a warp work on different clusters)."""
