@@ -107,6 +107,14 @@ __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, R
     const int p0 = b.cluster_pair_off[c], p1 = b.cluster_pair_off[c + 1], n = p1 - p0;
     const int thr = b.cluster_flags[c] >> GCB_CLUSTER_UMI_THR_SHIFT;
     const uint64_t *umi = b.umi + (int64_t)p0 * NW;
+    // a cluster of at most GS pairs is grouped in registers, a pair per lane: its UMIs are requested here, together with the
+    // descriptors the checks below read (the kernel waits for loads, not for instructions)
+    UmiT<NW> u;
+    {
+        const bool pre = lane < n && n <= GS && p0 >= 0 && p1 <= b.n_pairs;
+#pragma unroll
+        for (int k = 0; k < NW; k++) u.w[k] = pre ? umi[(int64_t)lane * NW + k] : 0ull;
+    }
     {   // preconditions: monotone pair offsets inside the batch; the cluster's slab 16-byte aligned, after the previous cluster's,
         // inside this view's payload
         bool bad = p0 < 0 || p1 < p0 || p1 > b.n_pairs;
@@ -153,9 +161,6 @@ __global__ void __launch_bounds__(GROUP_THREADS) umi_group_kernel(BatchView b, R
         // re-read every UMI of the cluster from memory for every pair and every round.)
         const bool act = lane < n;
         const unsigned actmask = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
-        UmiT<NW> u;
-#pragma unroll
-        for (int k = 0; k < NW; k++) u.w[k] = act ? umi[(int64_t)lane * NW + k] : 0ull;
         unsigned eq = actmask;
 #pragma unroll
         for (int k = 0; k < NW; k++) eq &= __match_any_sync(g.mask, u.w[k]) >> g.base;
@@ -520,13 +525,14 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
 // Returns false (nothing written) when the cluster is not of that kind.
 template <int GS>
 GCB_DEV bool select_cluster_fast(const Grp<GS> &g, const BatchView &b, const ResultView &r, const Workspace &ws, const GenomeView &gv, int c, int p0,
-                                 int n, int G) {
+                                 int n, int G, int gid, int64_t contig_len, int64_t contig_off) {
     const int lane = g.gl;
     const bool act = lane < n;
     const int64_t pair = p0 + (act ? lane : 0);
     const uint4 *dp = (const uint4 *)(b.reads + 2 * pair);
     const uint4 l0 = dp[0], l1 = dp[1], r0 = dp[2], r1 = dp[3];  // gcb_read_desc: {data_off lo, hi, l_qseq, pos} {isize, cigar_off, n_cigar | l_qname << 16, -}
-    const int gid = act ? r.pair_group[pair] : -1;
+    // (gid = the pair's family, contig_len / contig_off = the cluster's contig in the packed genome, contig_len < 0: none — loaded by
+    // the caller together with the descriptors: this kernel waits for loads, and these were the ends of two dependent chains)
     const int64_t slab0 = ws.slab_off[c];
     const int L_l = (int)l0.z, L_pos = (int)l0.w, L_isize = (int)l1.x, L_ncig = (int)(l1.z & 0xFFFFu), L_lqn = (int)(l1.z >> 16);
     const int R_l = (int)r0.z, R_pos = (int)r0.w, R_isize = (int)r1.x, R_ncig = (int)(r1.z & 0xFFFFu), R_lqn = (int)(r1.z >> 16);
@@ -647,7 +653,6 @@ GCB_DEV bool select_cluster_fast(const Grp<GS> &g, const BatchView &b, const Res
         for (int q = 0; q < (int)(sizeof(gcb_group_result) / 8); q++) row[q] = make_int2(0, 0);
     }
     if (is_first) {  // the family's result row and its two family-side descriptors
-        const int contig = b.cluster_ref[c];
         const int slot = p0 + gid;
         const int left = 2 * (int)pair, right = left + 1;
         gcb_group_result gr;
@@ -672,11 +677,11 @@ GCB_DEV bool select_cluster_fast(const Grp<GS> &g, const BatchView &b, const Res
             const uint32_t cg = side == 0 ? L_cig : R_cig;
             FsDesc fd = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, 0};
             fd.c = c;
-            if (isize != 0 && gv.packed4 && contig >= 0 && contig < gv.n_contigs) {  // group.cpp:362-367 + reference.cpp:33-71
+            if (isize != 0 && contig_len >= 0) {  // group.cpp:362-367 + reference.cpp:33-71
                 const int64_t span = (int64_t)get_ref_offset(&cg, 1, l_out - 1) + 1;
-                if ((int64_t)pos + span < gv.contig_len[contig]) {
+                if ((int64_t)pos + span < contig_len) {
                     fd.flags |= FS_REF_OK;
-                    fd.ref_nib0 = 2 * gv.contig_off[contig] + pos;
+                    fd.ref_nib0 = 2 * contig_off + pos;
                 }
             }
             const int op = cig_op(cg);
@@ -715,6 +720,11 @@ __global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(Batc
     const int p0 = b.cluster_pair_off[c], p1 = b.cluster_pair_off[c + 1], n = p1 - p0;
     const int G = r.cluster_n_groups[c];
     const bool crossContig = (b.cluster_flags[c] & GCB_CLUSTER_CROSS_CONTIG) != 0;
+    // what select_cluster_fast needs besides the descriptors, requested here so that the loads travel together
+    const int contig0 = b.cluster_ref[c];
+    const bool ref0 = gv.packed4 && contig0 >= 0 && contig0 < gv.n_contigs;
+    const int64_t contig_len0 = ref0 ? gv.contig_len[contig0] : -1, contig_off0 = ref0 ? gv.contig_off[contig0] : 0;
+    const int gid0 = (n <= GS && lane < n) ? r.pair_group[p0 + lane] : -1;
     {   // preconditions of the cluster's reads (see read_desc_ok)
         const int64_t lo = ws.slab_off[c], hi = ws.slab_off[c + 1];
         bool bad = false;
@@ -730,7 +740,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(Batc
             return;
         }
     }
-    if (n > 0 && n <= GS && !crossContig && select_cluster_fast<GS>(g, b, r, ws, gv, c, p0, n, G)) return;
+    if (n > 0 && n <= GS && !crossContig && select_cluster_fast<GS>(g, b, r, ws, gv, c, p0, n, G, gid0, contig_len0, contig_off0)) return;
 
     for (int i = lane; i < n; i += GS) {
         const int64_t pair = p0 + i;
@@ -830,8 +840,8 @@ __global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(Batc
                 ws.side_mode[2 * (int64_t)slot + 1] = SIDE_NONE;
             }
             g.sync();
-            ch[0] = side_select<GS>(g, b, ws, o, mb, m, 0, slot, slab0);
-            ch[1] = side_select<GS>(g, b, ws, o, mb, m, 1, slot, slab0);
+#pragma unroll 1  // (one copy of side_select: the kernel is 88 KB of code, and on ragged libraries it waits for instructions)
+            for (int s = 0; s < 2; s++) ch[s] = side_select<GS>(g, b, ws, o, mb, m, s, slot, slab0);
             const int left = ch[0].out, right = ch[1].out;
             gr.tmpl_read[0] = left;
             gr.tmpl_read[1] = right;
