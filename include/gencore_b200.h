@@ -41,6 +41,7 @@
 #ifndef GENCORE_B200_H
 #define GENCORE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
