@@ -55,6 +55,9 @@ struct ResultView {  // gcb_result with device pointers
 };
 
 constexpr int GROUP_THREADS = 128;  // 4 clusters per CTA
+#ifndef GCB_SELECT_MINB
+#define GCB_SELECT_MINB 12  // CTAs per SM select_template_kernel is compiled for (42 registers a thread)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // UMIs of NW 64-bit words held in registers (the kernel is instantiated for 1, 2 and GCB_MAX_UMI_WORDS words:
@@ -525,14 +528,13 @@ GCB_DEV SideChoice side_select(const Grp<GS> &g, const BatchView &b, const Works
 // Returns false (nothing written) when the cluster is not of that kind.
 template <int GS>
 GCB_DEV bool select_cluster_fast(const Grp<GS> &g, const BatchView &b, const ResultView &r, const Workspace &ws, const GenomeView &gv, int c, int p0,
-                                 int n, int G, int gid, int64_t contig_len, int64_t contig_off) {
+                                 int n, int G) {
     const int lane = g.gl;
     const bool act = lane < n;
     const int64_t pair = p0 + (act ? lane : 0);
     const uint4 *dp = (const uint4 *)(b.reads + 2 * pair);
     const uint4 l0 = dp[0], l1 = dp[1], r0 = dp[2], r1 = dp[3];  // gcb_read_desc: {data_off lo, hi, l_qseq, pos} {isize, cigar_off, n_cigar | l_qname << 16, -}
-    // (gid = the pair's family, contig_len / contig_off = the cluster's contig in the packed genome, contig_len < 0: none — loaded by
-    // the caller together with the descriptors: this kernel waits for loads, and these were the ends of two dependent chains)
+    const int gid = act ? r.pair_group[pair] : -1;
     const int64_t slab0 = ws.slab_off[c];
     const int L_l = (int)l0.z, L_pos = (int)l0.w, L_isize = (int)l1.x, L_ncig = (int)(l1.z & 0xFFFFu), L_lqn = (int)(l1.z >> 16);
     const int R_l = (int)r0.z, R_pos = (int)r0.w, R_isize = (int)r1.x, R_ncig = (int)(r1.z & 0xFFFFu), R_lqn = (int)(r1.z >> 16);
@@ -653,6 +655,7 @@ GCB_DEV bool select_cluster_fast(const Grp<GS> &g, const BatchView &b, const Res
         for (int q = 0; q < (int)(sizeof(gcb_group_result) / 8); q++) row[q] = make_int2(0, 0);
     }
     if (is_first) {  // the family's result row and its two family-side descriptors
+        const int contig = b.cluster_ref[c];
         const int slot = p0 + gid;
         const int left = 2 * (int)pair, right = left + 1;
         gcb_group_result gr;
@@ -677,11 +680,11 @@ GCB_DEV bool select_cluster_fast(const Grp<GS> &g, const BatchView &b, const Res
             const uint32_t cg = side == 0 ? L_cig : R_cig;
             FsDesc fd = {0, 0, 0, 0, 0, SIDE_NONE, 0, 0, 0, 0, 0};
             fd.c = c;
-            if (isize != 0 && contig_len >= 0) {  // group.cpp:362-367 + reference.cpp:33-71
+            if (isize != 0 && gv.packed4 && contig >= 0 && contig < gv.n_contigs) {  // group.cpp:362-367 + reference.cpp:33-71
                 const int64_t span = (int64_t)get_ref_offset(&cg, 1, l_out - 1) + 1;
-                if ((int64_t)pos + span < contig_len) {
+                if ((int64_t)pos + span < gv.contig_len[contig]) {
                     fd.flags |= FS_REF_OK;
-                    fd.ref_nib0 = 2 * contig_off + pos;
+                    fd.ref_nib0 = 2 * gv.contig_off[contig] + pos;
                 }
             }
             const int op = cig_op(cg);
@@ -711,7 +714,7 @@ GCB_DEV bool select_cluster_fast(const Grp<GS> &g, const BatchView &b, const Res
 
 // group.cpp:68-134 per family of the cluster + the per-pair overlap windows of pair.cpp:103-119
 template <int GS>
-__global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o) {
+__global__ void __launch_bounds__(GROUP_THREADS, GCB_SELECT_MINB) select_template_kernel(BatchView b, ResultView r, Workspace ws, GenomeView gv, gcb_options o) {
     GCB_GRID_DEP();
     const Grp<GS> g;
     const int lane = g.gl;
@@ -720,11 +723,6 @@ __global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(Batc
     const int p0 = b.cluster_pair_off[c], p1 = b.cluster_pair_off[c + 1], n = p1 - p0;
     const int G = r.cluster_n_groups[c];
     const bool crossContig = (b.cluster_flags[c] & GCB_CLUSTER_CROSS_CONTIG) != 0;
-    // what select_cluster_fast needs besides the descriptors, requested here so that the loads travel together
-    const int contig0 = b.cluster_ref[c];
-    const bool ref0 = gv.packed4 && contig0 >= 0 && contig0 < gv.n_contigs;
-    const int64_t contig_len0 = ref0 ? gv.contig_len[contig0] : -1, contig_off0 = ref0 ? gv.contig_off[contig0] : 0;
-    const int gid0 = (n <= GS && lane < n) ? r.pair_group[p0 + lane] : -1;
     {   // preconditions of the cluster's reads (see read_desc_ok)
         const int64_t lo = ws.slab_off[c], hi = ws.slab_off[c + 1];
         bool bad = false;
@@ -740,7 +738,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 12) select_template_kernel(Batc
             return;
         }
     }
-    if (n > 0 && n <= GS && !crossContig && select_cluster_fast<GS>(g, b, r, ws, gv, c, p0, n, G, gid0, contig_len0, contig_off0)) return;
+    if (n > 0 && n <= GS && !crossContig && select_cluster_fast<GS>(g, b, r, ws, gv, c, p0, n, G)) return;
 
     for (int i = lane; i < n; i += GS) {
         const int64_t pair = p0 + i;
