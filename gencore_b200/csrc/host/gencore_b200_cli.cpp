@@ -20,6 +20,7 @@
 #include <deque>
 #include <future>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <set>
@@ -418,6 +419,10 @@ struct Cli {
     gcb_options opt;
     int umi_diff_threshold = 1;  // -d properReadsUmiDiffThreshold; unproper reads use 0 (options.cpp:12-13)
     int device = 0;
+    // (not reference flags) one input over several processes / GPUs: `--shard i/N` keeps only the clusters whose (contig, left)
+    // falls into the i-th of N equal windows of the concatenated contigs; `--merge` joins the shards' outputs
+    int shard_index = 0, shard_count = 1;
+    std::vector<std::string> merge_inputs;
 };
 
 // ---------------------------------------------------------------------------------------------- the engine (C ABI, dlopen)
@@ -546,6 +551,21 @@ struct Pipeline {
     long tick = 0;
     std::string prefix;
     std::future<void> engine_ready;
+    std::vector<int64_t> lin_off;  // --shard: first coordinate of every contig in the concatenation of the header's contigs
+    int64_t lin_total = 0;
+
+    // --shard i/N: a cluster belongs to the window its (contig, left) falls into, a read whose mate is unmapped to the window of
+    // its own position.  Clusters are independent (gencore.cpp:76, cluster.cpp:55), and whether one is flushed at a tick depends
+    // only on its own key and on the read that ticks (see add_to_proper_cluster), so a process that COUNTS every clustered read
+    // of the input but KEEPS only its own window's reads flushes its clusters at the same ticks, with the same UMI threshold
+    // (Q18), as the unsharded run.
+    bool mine(int tid, int left) const {
+        if (cli.shard_count <= 1) return true;
+        const int64_t len = hdr.lens[(size_t)tid];
+        const int64_t x = lin_off[(size_t)tid] + std::min<int64_t>(std::max<int64_t>(left, 0), std::max<int64_t>(len - 1, 0));
+        const int owner = lin_total > 0 ? (int)std::min<int64_t>(x * cli.shard_count / lin_total, cli.shard_count - 1) : 0;
+        return owner == cli.shard_index;
+    }
 
     // ---- output side (gencore.cpp:83-160)
     void write_bam(Rec *r) { write_record(out, *r); }
@@ -603,7 +623,7 @@ struct Pipeline {
         jobs.push_back(std::move(j));
     }
     void add_to_proper_cluster(Rec *b) {  // gencore.cpp:295-390
-        const int tid = b->tid;
+        const int tid = b->tid, bpos = b->pos;
         int left = b->pos;
         long right;
         if (b->mtid == b->tid && abs(b->mpos - b->pos) < 100000) {
@@ -611,6 +631,10 @@ struct Pipeline {
             right = (long)left + abs(b->isize) - 1;
         } else {
             if (b->mtid < 0) {
+                if (!mine(tid, b->pos)) {
+                    delete b;
+                    return;
+                }
                 Event e;
                 e.kind = Event::PASS;
                 e.rec = b;
@@ -619,7 +643,8 @@ struct Pipeline {
             }
             right = -1L * (long)hdr.lens[(size_t)b->tid] * (long)(b->mtid + 1) + (long)b->mpos;
         }
-        add_read(clusters[tid][left][right], b);
+        if (mine(tid, left)) add_read(clusters[tid][left][right], b);
+        else delete b;  // (another shard's read: it still counts for the tick)
         tick++;
         if (tick % 10000 != 0) return;
         // the tick flush: every cluster the sorted input can no longer add to
@@ -637,13 +662,13 @@ struct Pipeline {
             }
             processed = hdr.lens[(size_t)i1->first];
             for (auto i2 = i1->second.begin(); i2 != i1->second.end();) {
-                if (i1->first == tid && i2->first >= b->pos) {
+                if (i1->first == tid && i2->first >= bpos) {
                     if (processed > i2->first) processed = i2->first;
                     need_break = true;
                     break;
                 }
                 for (auto i3 = i2->second.begin(); i3 != i2->second.end();) {
-                    if (i1->first == tid && i3->first >= b->pos) break;
+                    if (i1->first == tid && i3->first >= bpos) break;
                     take_jobs(e.jobs, i1->first, i3->first, cli.umi_diff_threshold, false, i3->second);
                     i3 = i2->second.erase(i3);
                 }
@@ -922,6 +947,10 @@ void Pipeline::run() {
     hdr = read_header(in);
     if (hdr.names.empty()) die("this SAM file has no header");
     write_header(out, hdr);
+    for (int32_t l : hdr.lens) {
+        lin_off.push_back(lin_total);
+        lin_total += std::max<int64_t>(l, 1);
+    }
     prefix = cli.umi_prefix;
     bool first = true;
     int last_tid = -1, last_pos = -1;
@@ -978,6 +1007,43 @@ void Pipeline::run() {
     eng.destroy(eng.ctx);
 }
 
+// --merge: the outputs of the N processes of one sharded run joined into one BAM in the order of the reference's output set
+// (gencore.h:19-47; records tied on all five fields keep shard order).  Every shard's output is in that order already.
+void merge_shards(const Cli &cli) {
+    unsigned hw = std::thread::hardware_concurrency();
+    WorkerPool pool((int)std::max(2u, std::min(hw ? hw - 1 : 4u, 16u)));
+    const size_t n = cli.merge_inputs.size();
+    std::vector<std::unique_ptr<BgzfReader>> in(n);
+    std::vector<Rec> head(n);
+    std::vector<bool> live(n, false);
+    BgzfWriter out;
+    out.pool = &pool;
+    out.fp = cli.output == "-" ? stdout : fopen(cli.output.c_str(), "wb");
+    if (!out.fp) die("failed to open output " + cli.output);
+    for (size_t k = 0; k < n; k++) {
+        in[k].reset(new BgzfReader());
+        in[k]->pool = &pool;
+        in[k]->fp = fopen(cli.merge_inputs[k].c_str(), "rb");
+        if (!in[k]->fp) die("failed to open " + cli.merge_inputs[k]);
+        BamHeader h = read_header(*in[k]);
+        if (k == 0) write_header(out, h);
+        live[k] = read_record(*in[k], head[k]);
+        head[k].serial = k;  // ties: the lower shard first
+    }
+    OutComp less;
+    for (;;) {
+        int best = -1;
+        for (size_t k = 0; k < n; k++)
+            if (live[k] && (best < 0 || less(&head[k], &head[(size_t)best]))) best = (int)k;
+        if (best < 0) break;
+        write_record(out, head[(size_t)best]);
+        live[(size_t)best] = read_record(*in[(size_t)best], head[(size_t)best]);
+        head[(size_t)best].serial = (uint64_t)best;
+    }
+    out.close();
+    for (size_t k = 0; k < n; k++) fclose(in[k]->fp);
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -1020,10 +1086,22 @@ int main(int argc, char **argv) {
         else if (a == "--no_duplex") c.opt.disable_duplex = 1;
         else if (a == "--engine") c.engine = need("engine");   // (not a reference flag) the C-ABI library to load
         else if (a == "--device") c.device = atoi(need("device").c_str());
+        else if (a == "--shard") {  // (not a reference flag) i/N: this process takes the i-th of N coordinate windows
+            const std::string v = need("shard");
+            if (sscanf(v.c_str(), "%d/%d", &c.shard_index, &c.shard_count) != 2 || c.shard_count < 1 || c.shard_index < 0 || c.shard_index >= c.shard_count)
+                die("--shard wants i/N with 0 <= i < N");
+        } else if (a == "--merge") {  // (not a reference flag) every remaining argument is a shard's output; -o names the result
+            while (i + 1 < argc) c.merge_inputs.push_back(argv[++i]);
+            if (c.merge_inputs.empty()) die("--merge wants the shards' BAM files");
+        }
         else if (a == "-b" || a == "--bed" || a == "-j" || a == "--json" || a == "-h" || a == "--html" || a == "--coverage_sampling" ||
                  a == "--quit_after_contig") need(a.c_str());  // reports and debugging aids are not part of this tool
         else if (a == "--debug") {}
         else die("unrecognized option: " + a);
+    }
+    if (!c.merge_inputs.empty()) {
+        merge_shards(c);
+        return 0;
     }
     // Options::validate (options.cpp:42-111), the checks that touch these fields
     if (c.ref.empty()) die("need option: --ref");

@@ -82,3 +82,61 @@ def test_bam_pipeline_matches_reference_binary_cuda(tmp_path, name, n_pairs, fla
     fa, bam, n_in = _make_inputs(tmp_path, name, n_pairs)
     n_out = _run_both(tmp_path, fa, bam, flags, gbuild.build())
     assert 0 < n_out < n_in
+
+
+def _run_sharded(tmp_path, fa, bam, flags, engine_lib, n_shards):
+    """One input over n_shards processes (`--shard i/N`: a window of the concatenated contigs each, every process counts all
+    clustered reads so that the 10 000-read ticks and the threshold rule Q18 fall where they fall in one process), the shards'
+    outputs joined by `--merge`: the result must be the reference binary's output."""
+    if not pyoracle.reference_available():
+        pytest.skip("oracle/_ref/gencore is not built")
+    ref_out, merged = str(tmp_path / "ref.bam"), str(tmp_path / "merged.bam")
+    r = subprocess.run([pyoracle.REF_BIN, "-i", bam, "-o", ref_out, "-r", fa, "-j", str(tmp_path / "r.json"), "-h", str(tmp_path / "r.html")] + flags,
+                       capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    cli = gbuild.build_cli()
+    parts, counts = [], []
+    for i in range(n_shards):
+        part = str(tmp_path / f"shard{i}.bam")
+        m = subprocess.run([cli, "-i", bam, "-o", part, "-r", fa, "--engine", engine_lib, "--shard", f"{i}/{n_shards}"] + flags,
+                           capture_output=True, text=True, cwd=str(tmp_path))
+        assert m.returncode == 0, m.stderr[-2000:]
+        parts.append(part)
+        counts.append(len(bamfile.bam_records(part)[1]))
+    m = subprocess.run([cli, "-o", merged, "--merge"] + parts, capture_output=True, text=True, cwd=str(tmp_path))
+    assert m.returncode == 0, m.stderr[-2000:]
+    n = bamfile.assert_same_bam(ref_out, merged)
+    assert sum(counts) == n
+    return n, counts
+
+
+@pytest.mark.parametrize("name,n_pairs,flags,n_shards", [("cfg2", 6000, [], 2),          # crosses the tick: flushed clusters use -d, the rest 0
+                                                         ("cfg3", 7000, [], 3),          # duplex, two contigs over three windows
+                                                         ("cfg4", 3000, ["-s", "2"], 2)])
+def test_sharded_bam_pipeline_matches_reference_binary_simt(tmp_path, name, n_pairs, flags, n_shards):
+    import build as simt_build
+    fa, bam, n_in = _make_inputs(tmp_path, name, n_pairs)
+    n_out, counts = _run_sharded(tmp_path, fa, bam, flags, simt_build.build(), n_shards)
+    assert 0 < n_out < n_in
+    assert sum(1 for c in counts if c > 0) >= 2  # (more than one window has reads)
+
+
+def test_sharded_bam_pipeline_ragged_simt(tmp_path):
+    """Pass-through reads (mate unmapped), unmapped and secondary records, clips and indels over four windows."""
+    import build as simt_build
+    fa, bam, n_in = _make_ragged_inputs(tmp_path, 13, "duplex")
+    n_out, counts = _run_sharded(tmp_path, fa, bam, [], simt_build.build(), 4)
+    assert 0 < n_out < n_in
+
+
+def test_shard_flag_is_validated(tmp_path):
+    cli = gbuild.build_cli()
+    m = subprocess.run([cli, "-i", "x.bam", "-o", "y.bam", "-r", "z.fa", "--shard", "2/2"], capture_output=True, text=True)
+    assert m.returncode != 0 and "--shard" in m.stderr
+
+
+@pytest.mark.gpu
+def test_sharded_bam_pipeline_matches_reference_binary_cuda(tmp_path):
+    fa, bam, n_in = _make_inputs(tmp_path, "cfg2", 60_000)
+    n_out, counts = _run_sharded(tmp_path, fa, bam, [], gbuild.build(), 2)
+    assert 0 < n_out < n_in and min(counts) > 0
