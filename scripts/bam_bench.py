@@ -32,8 +32,18 @@ with tempfile.TemporaryDirectory() as td:
             best = dt if best is None else min(best, dt)
         res[tag] = best
     n_out = bamfile.assert_same_bam(os.path.join(td, "ref.bam"), os.path.join(td, "b200.bam"))
+    # the same input over two processes on this GPU (--shard 0/2, 1/2) and the merge: scripts/sharded_bam.py
+    sharded = None
+    for rep in range(2):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sharded_bam.py"), "-n", "2", "--gpus", "1", "-i", bam, "-o", os.path.join(td, "sharded.bam"),
+                            "-r", fa, "--engine", gbuild.LIB], capture_output=True, text=True, cwd=td)
+        assert p.returncode == 0, p.stderr[-1500:]
+        line = json.loads(p.stdout.strip().splitlines()[-1])
+        sharded = line if sharded is None or line["total_s"] < sharded["total_s"] else sharded
+    assert bamfile.assert_same_bam(os.path.join(td, "ref.bam"), os.path.join(td, "sharded.bam")) == n_out
     if "bridged" in res:
         assert bamfile.assert_same_bam(os.path.join(td, "ref.bam"), os.path.join(td, "bridged.bam")) == n_out
     print(json.dumps({"what": "BAM-to-BAM wall time, cfg2 shape", "pairs": n_pairs, "records_in": n_rec, "records_out": n_out, "identical_output": True,
                       "reference_s": res["reference"], "bridged_reference_s": res.get("bridged"), "b200_s": res["b200"],
-                      "reference_pairs_per_s": n_pairs / res["reference"], "b200_pairs_per_s": n_pairs / res["b200"], "bam_bytes": os.path.getsize(bam)}))
+                      "reference_pairs_per_s": n_pairs / res["reference"], "b200_pairs_per_s": n_pairs / res["b200"], "bam_bytes": os.path.getsize(bam),
+                      "b200_two_shards_one_gpu": sharded}))

@@ -140,3 +140,21 @@ def test_sharded_bam_pipeline_matches_reference_binary_cuda(tmp_path):
     fa, bam, n_in = _make_inputs(tmp_path, "cfg2", 60_000)
     n_out, counts = _run_sharded(tmp_path, fa, bam, [], gbuild.build(), 2)
     assert 0 < n_out < n_in and min(counts) > 0
+
+
+def test_sharded_bam_script_simt(tmp_path):
+    """scripts/sharded_bam.py: the shards as concurrent processes, then the merge."""
+    import json
+    import build as simt_build
+    if not pyoracle.reference_available():
+        pytest.skip("oracle/_ref/gencore is not built")
+    fa, bam, n_in = _make_inputs(tmp_path, "cfg3", 4000)
+    ref_out, out = str(tmp_path / "ref.bam"), str(tmp_path / "sharded.bam")
+    r = subprocess.run([pyoracle.REF_BIN, "-i", bam, "-o", ref_out, "-r", fa, "-j", str(tmp_path / "r.json"), "-h", str(tmp_path / "r.html")],
+                       capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    script = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "sharded_bam.py")
+    m = subprocess.run([sys.executable, script, "-n", "3", "-i", bam, "-o", out, "-r", fa, "--engine", simt_build.build()], capture_output=True, text=True)
+    assert m.returncode == 0, m.stderr[-2000:]
+    assert json.loads(m.stdout.strip().splitlines()[-1])["shards"] == 3
+    assert bamfile.assert_same_bam(ref_out, out) > 0
