@@ -592,8 +592,7 @@ struct Pipeline {
             write_bam(r);
             delete r;
         }
-        out_set.clear();
-        out_set_cleared = true;
+        out_set.clear();  // (mOutSetCleared is the reading side's flag: Pipeline::run sets it when it logs the event)
     }
 
     // ---- input side
@@ -709,12 +708,44 @@ struct Pipeline {
         log.push_back(std::move(e));
     }
 
-    // ---- the engine call over every pending CLUSTERS event, then the replay of the log
-    void run_and_replay();
+    // ---- the engine call over every CLUSTERS event of a batch of the log, then the replay of that batch.  Two threads: the
+    // one that reads and keys (clusters, tick, log, pending_pairs, serial, out_set_cleared) hands whole batches of the log to
+    // the one that packs, calls the engine, replays and writes (out_set, watermark, out, eng, genome): the next 200 000 pairs
+    // are parsed and clustered while the engine and the writer work on the current ones.
+    std::mutex q_mu;
+    std::condition_variable q_cv;
+    std::deque<std::vector<Event>> q;
+    bool q_closed = false;
+    void submit_log() {
+        std::vector<Event> batch;
+        batch.swap(log);
+        pending_pairs = 0;
+        {
+            std::unique_lock<std::mutex> l(q_mu);
+            q_cv.wait(l, [this] { return q.size() < 2; });  // (a batch holds its reads: at most two wait)
+            q.push_back(std::move(batch));
+        }
+        q_cv.notify_all();
+    }
+    void consume_batches() {
+        for (;;) {
+            std::vector<Event> batch;
+            {
+                std::unique_lock<std::mutex> l(q_mu);
+                q_cv.wait(l, [this] { return !q.empty() || q_closed; });
+                if (q.empty()) return;
+                batch = std::move(q.front());
+                q.pop_front();
+            }
+            q_cv.notify_all();
+            run_and_replay(batch);
+        }
+    }
+    void run_and_replay(std::vector<Event> &log);
     void run();
 };
 
-void Pipeline::run_and_replay() {
+void Pipeline::run_and_replay(std::vector<Event> &log) {
     double t0 = now_s();
     if (engine_ready.valid()) {
         engine_ready.get();
@@ -917,8 +948,6 @@ void Pipeline::run_and_replay() {
     // the records that did not become a consensus were deleted with their Pair
     for (size_t s = 0; s < slot_rec.size(); s++)
         if (slot_rec[s] && !consumed[s]) delete slot_rec[s];
-    log.clear();
-    pending_pairs = 0;
     lap("replay + write", t0);
 }
 
@@ -954,6 +983,7 @@ void Pipeline::run() {
     prefix = cli.umi_prefix;
     bool first = true;
     int last_tid = -1, last_pos = -1;
+    std::thread consumer([this] { consume_batches(); });
     double t_read = now_s();
     Rec *b = new Rec();
     while (read_record(in, *b)) {
@@ -986,7 +1016,7 @@ void Pipeline::run() {
         b = new Rec();
         if (pending_pairs >= 200000) {
             lap("read + key", t_read);
-            run_and_replay();
+            submit_log();
             t_read = now_s();
         }
     }
@@ -999,7 +1029,13 @@ void Pipeline::run() {
     Event e;  // ~Gencore: outputOutSet
     e.kind = Event::CLEAR_OUTSET;
     log.push_back(std::move(e));
-    run_and_replay();
+    submit_log();
+    {
+        std::lock_guard<std::mutex> l(q_mu);
+        q_closed = true;
+    }
+    q_cv.notify_all();
+    consumer.join();
     double t_close = now_s();
     out.close();
     lap("flush output", t_close);
