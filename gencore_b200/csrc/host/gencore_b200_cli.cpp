@@ -34,11 +34,12 @@ namespace {
 double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-const bool g_timing = getenv("GCB_TIMING") != nullptr;  // per-phase wall times on stderr
+const bool g_timing = getenv("GCB_TIMING") != nullptr;  // per-phase wall times on stderr (and when the phase ended, since the start of main)
+const double g_t_start = now_s();
 void lap(const char *what, double &t0) {
     if (!g_timing) return;
     const double t = now_s();
-    fprintf(stderr, "[timing] %-28s %8.3f s\n", what, t - t0);
+    fprintf(stderr, "[timing] %-28s %8.3f s   (at %7.3f)\n", what, t - t0, t - g_t_start);
     t0 = t;
 }
 
@@ -1041,6 +1042,7 @@ void Pipeline::run() {
     lap("flush output", t_close);
     if (in.fp != stdin) fclose(in.fp);
     eng.destroy(eng.ctx);
+    lap("gcb_destroy", t_close);
 }
 
 // --merge: the outputs of the N processes of one sharded run joined into one BAM in the order of the reference's output set
@@ -1153,5 +1155,14 @@ int main(int argc, char **argv) {
     if (c.opt.moderate_quality > c.opt.high_quality) die("moderate_qual cannot be greater than high_qual");
     if (c.opt.duplex_mismatch_threshold < 0 || c.opt.duplex_mismatch_threshold > 10) die("duplex_diff_threshold cannot be negative or greater than 10");
     p.run();
+    double t_end = g_t_start;
+    lap("main, before exit", t_end);
+    // every output is written and closed: leave without the teardown of the CUDA context and of the runtime's exit handlers
+    // (GCB_FAST_EXIT=0: the ordinary way out)
+    const char *fe = getenv("GCB_FAST_EXIT");
+    if (!fe || strcmp(fe, "0") != 0) {
+        fflush(nullptr);
+        _exit(0);
+    }
     return 0;
 }

@@ -10,6 +10,7 @@ from gencore_b200 import build as gbuild, synth
 from oracle import pyoracle
 
 n_pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 300_000
+only_b200 = "--only-b200" in sys.argv  # the tool's own timeline (GCB_TIMING lines on stderr), nothing compared
 cfg = dataclasses.replace(synth.CONFIGS["cfg2"], contig_len=20_000_000)
 with tempfile.TemporaryDirectory() as td:
     batch, genome, contigs = synth.make_fixed_batch(cfg, seed=20261019, n_pairs=n_pairs, with_qnames=True)
@@ -21,7 +22,7 @@ with tempfile.TemporaryDirectory() as td:
                      ("bridged", [os.path.join(os.path.dirname(pyoracle.REF_BIN), "gencore_bridged"), "-i", bam, "-o", os.path.join(td, "bridged.bam"), "-r", fa,
                                   "-j", os.path.join(td, "b.json"), "-h", os.path.join(td, "b.html")]),
                      ("b200", [gbuild.build_cli(), "-i", bam, "-o", os.path.join(td, "b200.bam"), "-r", fa])):
-        if not os.path.exists(cmd[0]):
+        if not os.path.exists(cmd[0]) or (only_b200 and tag != "b200"):
             continue
         best = None
         for rep in range(2):
@@ -33,6 +34,17 @@ with tempfile.TemporaryDirectory() as td:
             assert p.returncode == 0, p.stderr[-1500:]
             best = dt if best is None else min(best, dt)
         res[tag] = best
+    if only_b200:
+        cmd = [gbuild.build_cli(), "-i", bam, "-o", os.path.join(td, "b200.bam"), "-r", fa]
+        for fast in ("0", "1"):
+            for rep in range(2):
+                t = time.perf_counter()
+                p = subprocess.run(cmd, capture_output=True, text=True, cwd=td, env=dict(os.environ, GENCORE_B200_ENGINE=gbuild.LIB, GCB_TIMING="1", GCB_FAST_EXIT=fast))
+                dt = time.perf_counter() - t
+                sys.stderr.write("== GCB_FAST_EXIT=%s, wall %.3f s\n%s" % (fast, dt, p.stderr))
+                res["b200_fast_exit_" + fast] = min(res.get("b200_fast_exit_" + fast, 1e9), dt)
+        print(json.dumps(dict(res, pairs=n_pairs)))
+        sys.exit(0)
     n_out = bamfile.assert_same_bam(os.path.join(td, "ref.bam"), os.path.join(td, "b200.bam"))
     # the same input over two processes on this GPU (--shard 0/2, 1/2) and the merge: scripts/sharded_bam.py
     sharded = None
