@@ -709,45 +709,83 @@ struct Pipeline {
         log.push_back(std::move(e));
     }
 
-    // ---- the engine call over every CLUSTERS event of a batch of the log, then the replay of that batch.  Two threads: the
+    // ---- the engine call over every CLUSTERS event of a batch of the log, then the replay of that batch.  Three threads: the
     // one that reads and keys (clusters, tick, log, pending_pairs, serial, out_set_cleared) hands whole batches of the log to
-    // the one that packs, calls the engine, replays and writes (out_set, watermark, out, eng, genome): the next 200 000 pairs
-    // are parsed and clustered while the engine and the writer work on the current ones.
-    std::mutex q_mu;
-    std::condition_variable q_cv;
-    std::deque<std::vector<Event>> q;
-    bool q_closed = false;
+    // the one that packs them and calls the engine (eng, genome, prefix), which hands the batch and its results to the one that
+    // replays and writes (out_set, watermark, out).  Batches go through in order, so the sequence of outputs is that of one
+    // thread; the next 200 000 pairs are parsed and clustered while the engine works on the current ones and the writer on
+    // the ones before.
+    struct Packed {  // a batch of the log after the engine call: what the replay needs
+        std::vector<Event> log;
+        std::vector<int32_t> cpo, n_groups;
+        std::vector<gcb_group_result> groups;
+        std::vector<uint8_t> out_payload;
+        std::vector<uint64_t> umi;
+        std::vector<const Rec *> slot_rec;  // read slot -> record
+        int umi_words = 2;
+        int32_t n_pairs = 0;
+    };
+    template <typename T>
+    struct Channel {  // a bounded queue between two stages (a batch holds its reads: at most two wait)
+        std::mutex mu;
+        std::condition_variable cv;
+        std::deque<T> q;
+        bool closed = false;
+        void push(T &&v) {
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cv.wait(l, [this] { return q.size() < 2; });
+                q.push_back(std::move(v));
+            }
+            cv.notify_all();
+        }
+        bool pop(T &v) {
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cv.wait(l, [this] { return !q.empty() || closed; });
+                if (q.empty()) return false;
+                v = std::move(q.front());
+                q.pop_front();
+            }
+            cv.notify_all();
+            return true;
+        }
+        void close() {
+            {
+                std::lock_guard<std::mutex> l(mu);
+                closed = true;
+            }
+            cv.notify_all();
+        }
+    };
+    Channel<std::vector<Event>> to_engine;
+    Channel<std::unique_ptr<Packed>> to_writer;
     void submit_log() {
         std::vector<Event> batch;
         batch.swap(log);
         pending_pairs = 0;
-        {
-            std::unique_lock<std::mutex> l(q_mu);
-            q_cv.wait(l, [this] { return q.size() < 2; });  // (a batch holds its reads: at most two wait)
-            q.push_back(std::move(batch));
-        }
-        q_cv.notify_all();
+        to_engine.push(std::move(batch));
     }
-    void consume_batches() {
-        for (;;) {
-            std::vector<Event> batch;
-            {
-                std::unique_lock<std::mutex> l(q_mu);
-                q_cv.wait(l, [this] { return !q.empty() || q_closed; });
-                if (q.empty()) return;
-                batch = std::move(q.front());
-                q.pop_front();
-            }
-            q_cv.notify_all();
-            run_and_replay(batch);
-        }
+    void engine_stage() {
+        std::vector<Event> batch;
+        while (to_engine.pop(batch)) to_writer.push(pack_and_run(std::move(batch)));
+        to_writer.close();
     }
-    void run_and_replay(std::vector<Event> &log);
+    void writer_stage() {
+        std::unique_ptr<Packed> pk;
+        while (to_writer.pop(pk)) replay(*pk);
+    }
+    std::unique_ptr<Packed> pack_and_run(std::vector<Event> &&batch);
+    void replay(Packed &pk);
     void run();
 };
 
-void Pipeline::run_and_replay(std::vector<Event> &log) {
+std::unique_ptr<Pipeline::Packed> Pipeline::pack_and_run(std::vector<Event> &&batch) {
     double t0 = now_s();
+    std::unique_ptr<Packed> pkp(new Packed());
+    Packed &pk = *pkp;
+    pk.log = std::move(batch);
+    std::vector<Event> &log = pk.log;
     if (engine_ready.valid()) {
         engine_ready.get();
         lap("wait for engine start-up", t0);
@@ -757,12 +795,13 @@ void Pipeline::run_and_replay(std::vector<Event> &log) {
         }
     }
     // 1. pack (gencore_b200.h "Encoding conventions")
-    std::vector<int32_t> cpo = {0}, cref;
+    std::vector<int32_t> &cpo = pk.cpo, cref;
+    cpo.push_back(0);
     std::vector<uint8_t> cflags;
     std::vector<gcb_read_desc> reads;
     std::vector<uint32_t> cigar;
     std::vector<uint8_t> payload;
-    std::vector<const Rec *> slot_rec;  // read slot -> record
+    std::vector<const Rec *> &slot_rec = pk.slot_rec;
     std::string names;
     std::vector<int64_t> name_off = {0};
     for (Event &e : log) {
@@ -811,11 +850,15 @@ void Pipeline::run_and_replay(std::vector<Event> &log) {
     payload.resize((payload.size() + 15) & ~(size_t)15, 0);
     lap("pack batch", t0);
     const int32_t n_pairs = (int32_t)(reads.size() / 2), n_clusters = (int32_t)cref.size();
-    std::vector<int32_t> pair_group((size_t)n_pairs + 1), n_groups((size_t)n_clusters + 1);
-    std::vector<gcb_group_result> groups((size_t)n_pairs + 1);
-    std::vector<uint8_t> out_payload(payload.size() + 16);
-    std::vector<uint64_t> umi;
-    int umi_words = 2;
+    std::vector<int32_t> pair_group((size_t)n_pairs + 1), &n_groups = pk.n_groups;
+    n_groups.assign((size_t)n_clusters + 1, 0);
+    std::vector<gcb_group_result> &groups = pk.groups;
+    groups.resize((size_t)n_pairs + 1);
+    std::vector<uint8_t> &out_payload = pk.out_payload;
+    out_payload.resize(payload.size() + 16);
+    std::vector<uint64_t> &umi = pk.umi;
+    int &umi_words = pk.umi_words;
+    pk.n_pairs = n_pairs;
     if (n_pairs > 0) {
         // 2. UMIs of every read (gcb_extract_umi = BamUtil::getUMI on the GPU), then Pair::setLeft / setRight (pair.cpp:188-216)
         std::vector<uint64_t> read_umi;
@@ -875,7 +918,20 @@ void Pipeline::run_and_replay(std::vector<Event> &log) {
         eng.check(eng.consensus_batch(eng.ctx, &b, &res), "gcb_consensus_batch");
         lap("gcb_consensus_batch", t0);
     }
-    // 4. replay: what the loops around clusterByUMI do with the returned pairs (gencore.cpp:355-360, 409-414)
+    return pkp;
+}
+
+// 4. replay: what the loops around clusterByUMI do with the returned pairs (gencore.cpp:355-360, 409-414)
+void Pipeline::replay(Packed &pk) {
+    double t0 = now_s();
+    std::vector<Event> &log = pk.log;
+    const std::vector<int32_t> &cpo = pk.cpo, &n_groups = pk.n_groups;
+    const std::vector<gcb_group_result> &groups = pk.groups;
+    const std::vector<uint8_t> &out_payload = pk.out_payload;
+    const std::vector<uint64_t> &umi = pk.umi;
+    const std::vector<const Rec *> &slot_rec = pk.slot_rec;
+    const int umi_words = pk.umi_words;
+    const int32_t n_pairs = pk.n_pairs;
     int32_t c = 0;
     std::vector<char> consumed((size_t)2 * n_pairs + 1, 0);
     for (Event &e : log) {
@@ -984,7 +1040,9 @@ void Pipeline::run() {
     prefix = cli.umi_prefix;
     bool first = true;
     int last_tid = -1, last_pos = -1;
-    std::thread consumer([this] { consume_batches(); });
+    // pairs per engine call; GCB_BATCH_PAIRS: smaller batches for tests of the hand-over between the three threads
+    const size_t batch_pairs = getenv("GCB_BATCH_PAIRS") ? (size_t)std::max(1L, atol(getenv("GCB_BATCH_PAIRS"))) : (size_t)200000;
+    std::thread engine_thread([this] { engine_stage(); }), writer_thread([this] { writer_stage(); });
     double t_read = now_s();
     Rec *b = new Rec();
     while (read_record(in, *b)) {
@@ -1015,7 +1073,7 @@ void Pipeline::run() {
         b->serial = serial++;
         add_to_proper_cluster(b);
         b = new Rec();
-        if (pending_pairs >= 200000) {
+        if (pending_pairs >= batch_pairs) {
             lap("read + key", t_read);
             submit_log();
             t_read = now_s();
@@ -1031,12 +1089,9 @@ void Pipeline::run() {
     e.kind = Event::CLEAR_OUTSET;
     log.push_back(std::move(e));
     submit_log();
-    {
-        std::lock_guard<std::mutex> l(q_mu);
-        q_closed = true;
-    }
-    q_cv.notify_all();
-    consumer.join();
+    to_engine.close();
+    engine_thread.join();
+    writer_thread.join();
     double t_close = now_s();
     out.close();
     lap("flush output", t_close);

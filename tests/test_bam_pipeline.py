@@ -158,3 +158,15 @@ def test_sharded_bam_script_simt(tmp_path):
     assert m.returncode == 0, m.stderr[-2000:]
     assert json.loads(m.stdout.strip().splitlines()[-1])["shards"] == 3
     assert bamfile.assert_same_bam(ref_out, out) > 0
+
+
+@pytest.mark.parametrize("name,n_pairs,batch", [("cfg2", 12000, 1500), ("cfg3", 7000, 500)])
+def test_bam_pipeline_many_batches_simt(tmp_path, monkeypatch, name, n_pairs, batch):
+    """The tool hands batches of its event log from the reading thread to the engine thread to the writing thread: with a small
+    batch (GCB_BATCH_PAIRS) an input goes through in many batches, tick flushes and watermarks in between, and must come out
+    as from the reference binary."""
+    import build as simt_build
+    monkeypatch.setenv("GCB_BATCH_PAIRS", str(batch))
+    fa, bam, n_in = _make_inputs(tmp_path, name, n_pairs)
+    n_out = _run_both(tmp_path, fa, bam, [], simt_build.build())
+    assert 0 < n_out < n_in
