@@ -726,15 +726,16 @@ struct Pipeline {
         int32_t n_pairs = 0;
     };
     template <typename T>
-    struct Channel {  // a bounded queue between two stages (a batch holds its reads: at most two wait)
+    struct Channel {  // a bounded queue between two stages (a batch holds its reads)
         std::mutex mu;
         std::condition_variable cv;
         std::deque<T> q;
+        size_t cap = 2;
         bool closed = false;
         void push(T &&v) {
             {
                 std::unique_lock<std::mutex> l(mu);
-                cv.wait(l, [this] { return q.size() < 2; });
+                cv.wait(l, [this] { return q.size() < cap; });
                 q.push_back(std::move(v));
             }
             cv.notify_all();
@@ -1042,6 +1043,7 @@ void Pipeline::run() {
     int last_tid = -1, last_pos = -1;
     // pairs per engine call; GCB_BATCH_PAIRS: smaller batches for tests of the hand-over between the three threads
     const size_t batch_pairs = getenv("GCB_BATCH_PAIRS") ? (size_t)std::max(1L, atol(getenv("GCB_BATCH_PAIRS"))) : (size_t)200000;
+    to_engine.cap = 6;  // (the reader does not stop while the CUDA context starts up: 1 to 4 s on the B200 boxes, six batches ~ 1.7 GB of reads)
     std::thread engine_thread([this] { engine_stage(); }), writer_thread([this] { writer_stage(); });
     double t_read = now_s();
     Rec *b = new Rec();
@@ -1096,6 +1098,16 @@ void Pipeline::run() {
     out.close();
     lap("flush output", t_close);
     if (in.fp != stdin) fclose(in.fp);
+    // every output is written and closed: leave without gcb_destroy and without the teardown of the CUDA context and of the
+    // runtime's exit handlers (measured on the B200 boxes: gcb_destroy 0.01 to 1.8 s, the exit handlers 0.3 to 1.3 s);
+    // GCB_FAST_EXIT=0: the ordinary way out
+    const char *fe = getenv("GCB_FAST_EXIT");
+    if (!fe || strcmp(fe, "0") != 0) {
+        double t_end = g_t_start;
+        lap("main, before exit", t_end);
+        fflush(nullptr);
+        _exit(0);
+    }
     eng.destroy(eng.ctx);
     lap("gcb_destroy", t_close);
 }
@@ -1212,12 +1224,5 @@ int main(int argc, char **argv) {
     p.run();
     double t_end = g_t_start;
     lap("main, before exit", t_end);
-    // every output is written and closed: leave without the teardown of the CUDA context and of the runtime's exit handlers
-    // (GCB_FAST_EXIT=0: the ordinary way out)
-    const char *fe = getenv("GCB_FAST_EXIT");
-    if (!fe || strcmp(fe, "0") != 0) {
-        fflush(nullptr);
-        _exit(0);
-    }
     return 0;
 }
