@@ -323,7 +323,8 @@ bool read_record(BgzfReader &in, Rec &r) {
     if (got == 0) return false;
     if (got != 4) die("truncated BAM record");
     const uint32_t block = le32(b4);
-    std::vector<uint8_t> d(block);
+    static thread_local std::vector<uint8_t> d;  // (one buffer for every record a thread reads: no allocation, no zero fill)
+    if (d.size() < block) d.resize(block);
     if (block < 32 || in.read(d.data(), block) != block) die("truncated BAM record");
     r.tid = (int32_t)le32(&d[0]);
     r.pos = (int32_t)le32(&d[4]);
@@ -348,7 +349,7 @@ bool read_record(BgzfReader &in, Rec &r) {
     off += (size_t)(r.l_seq + 1) / 2;
     r.qual.assign(d.begin() + (long)off, d.begin() + (long)(off + (size_t)r.l_seq));
     off += (size_t)r.l_seq;
-    r.aux.assign(d.begin() + (long)off, d.end());
+    r.aux.assign(d.begin() + (long)off, d.begin() + (long)block);
     return true;
 }
 
@@ -603,14 +604,12 @@ struct Pipeline {
         return k;
     }
     void add_read(PairMap &pm, Rec *r) {  // Cluster::addRead, cluster.cpp:260-273
-        auto it = pm.find(map_key(*r));
-        if (it != pm.end()) {
-            delete it->second.right;  // Pair::setRight destroys a previous mRight (Q25)
-            it->second.right = r;
-        } else {
-            PairRec p;
-            p.left = r;
-            pm[map_key(*r)] = p;
+        PairRec fresh;
+        fresh.left = r;
+        auto ins = pm.emplace(map_key(*r), fresh);  // (one key, one walk of the map)
+        if (!ins.second) {
+            delete ins.first->second.right;  // Pair::setRight destroys a previous mRight (Q25)
+            ins.first->second.right = r;
         }
     }
     static void take_jobs(std::vector<ClusterJob> &jobs, int tid, long right, int thr, bool passthrough, PairMap &pm) {
