@@ -170,3 +170,14 @@ def test_bam_pipeline_many_batches_simt(tmp_path, monkeypatch, name, n_pairs, ba
     fa, bam, n_in = _make_inputs(tmp_path, name, n_pairs)
     n_out = _run_both(tmp_path, fa, bam, [], simt_build.build())
     assert 0 < n_out < n_in
+
+
+def test_sharded_bam_pipeline_many_windows_simt(tmp_path):
+    """More windows than the input has busy regions: shards that keep nothing write a header-only BAM and the merge still yields
+    the reference's output; one shard of one is the unsharded tool."""
+    import build as simt_build
+    fa, bam, n_in = _make_inputs(tmp_path, "cfg1", 800)
+    n_out, counts = _run_sharded(tmp_path, fa, bam, [], simt_build.build(), 16)
+    assert 0 < n_out < n_in
+    n_one, counts_one = _run_sharded(tmp_path, fa, bam, [], simt_build.build(), 1)
+    assert n_one == n_out and counts_one == [n_out]
