@@ -723,6 +723,14 @@ struct Pipeline {
         std::vector<const Rec *> slot_rec;  // read slot -> record
         int umi_words = 2;
         int32_t n_pairs = 0;
+        // the packed batch (gencore_b200.h "Encoding conventions"), used by the engine stage only
+        std::vector<int32_t> ctid;  // the clusters' tids (the engine stage maps them to contigs of the FASTA once that is loaded)
+        std::vector<uint8_t> cflags;
+        std::vector<gcb_read_desc> reads;
+        std::vector<uint32_t> cigar;
+        std::vector<uint8_t> payload;
+        std::string names;
+        std::vector<int64_t> name_off;
     };
     template <typename T>
     struct Channel {  // a bounded queue between two stages (a batch holds its reads)
@@ -758,52 +766,54 @@ struct Pipeline {
             cv.notify_all();
         }
     };
-    Channel<std::vector<Event>> to_engine;
-    Channel<std::unique_ptr<Packed>> to_writer;
+    Channel<std::vector<Event>> to_pack;
+    Channel<std::unique_ptr<Packed>> to_engine, to_writer;
     void submit_log() {
         std::vector<Event> batch;
         batch.swap(log);
         pending_pairs = 0;
-        to_engine.push(std::move(batch));
+        to_pack.push(std::move(batch));
+    }
+    void pack_stage() {
+        std::vector<Event> batch;
+        while (to_pack.pop(batch)) to_engine.push(pack(std::move(batch)));
+        to_engine.close();
     }
     void engine_stage() {
-        std::vector<Event> batch;
-        while (to_engine.pop(batch)) to_writer.push(pack_and_run(std::move(batch)));
+        std::unique_ptr<Packed> pk;
+        while (to_engine.pop(pk)) {
+            run_engine(*pk);
+            to_writer.push(std::move(pk));
+        }
         to_writer.close();
     }
     void writer_stage() {
         std::unique_ptr<Packed> pk;
         while (to_writer.pop(pk)) replay(*pk);
     }
-    std::unique_ptr<Packed> pack_and_run(std::vector<Event> &&batch);
+    std::unique_ptr<Packed> pack(std::vector<Event> &&batch);
+    void run_engine(Packed &pk);
     void replay(Packed &pk);
     void run();
 };
 
-std::unique_ptr<Pipeline::Packed> Pipeline::pack_and_run(std::vector<Event> &&batch) {
+// 1. pack (gencore_b200.h "Encoding conventions"): needs no engine, so it runs while the CUDA context starts up
+std::unique_ptr<Pipeline::Packed> Pipeline::pack(std::vector<Event> &&batch) {
     double t0 = now_s();
     std::unique_ptr<Packed> pkp(new Packed());
     Packed &pk = *pkp;
     pk.log = std::move(batch);
     std::vector<Event> &log = pk.log;
-    if (engine_ready.valid()) {
-        engine_ready.get();
-        lap("wait for engine start-up", t0);
-        for (const std::string &n : hdr.names) {
-            auto it = genome.index.find(n);
-            tid_to_contig.push_back(it == genome.index.end() ? -1 : it->second);
-        }
-    }
-    // 1. pack (gencore_b200.h "Encoding conventions")
-    std::vector<int32_t> &cpo = pk.cpo, cref;
+    std::vector<int32_t> &cpo = pk.cpo, &ctid = pk.ctid;
     cpo.push_back(0);
-    std::vector<uint8_t> cflags;
-    std::vector<gcb_read_desc> reads;
-    std::vector<uint32_t> cigar;
-    std::vector<uint8_t> payload;
+    std::vector<uint8_t> &cflags = pk.cflags;
+    std::vector<gcb_read_desc> &reads = pk.reads;
+    std::vector<uint32_t> &cigar = pk.cigar;
+    std::vector<uint8_t> &payload = pk.payload;
     std::vector<const Rec *> &slot_rec = pk.slot_rec;
-    std::string names;
-    std::vector<int64_t> name_off = {0};
+    std::string &names = pk.names;
+    std::vector<int64_t> &name_off = pk.name_off;
+    name_off.push_back(0);
     for (Event &e : log) {
         if (e.kind != Event::CLUSTERS) continue;
         for (ClusterJob &j : e.jobs) {
@@ -843,13 +853,36 @@ std::unique_ptr<Pipeline::Packed> Pipeline::pack_and_run(std::vector<Event> &&ba
                 }
             }
             cpo.push_back((int32_t)(reads.size() / 2));
-            cref.push_back(j.tid >= 0 && (size_t)j.tid < tid_to_contig.size() ? tid_to_contig[(size_t)j.tid] : -1);
+            ctid.push_back(j.tid);
             cflags.push_back((uint8_t)((j.right < 0 ? GCB_CLUSTER_CROSS_CONTIG : 0) | (j.thr << GCB_CLUSTER_UMI_THR_SHIFT)));
         }
     }
     payload.resize((payload.size() + 15) & ~(size_t)15, 0);
+    pk.n_pairs = (int32_t)(reads.size() / 2);
     lap("pack batch", t0);
-    const int32_t n_pairs = (int32_t)(reads.size() / 2), n_clusters = (int32_t)cref.size();
+    return pkp;
+}
+
+// 2.-3. the engine over a packed batch: UMIs, then Cluster::clusterByUMI for every cluster
+void Pipeline::run_engine(Packed &pk) {
+    double t0 = now_s();
+    if (engine_ready.valid()) {
+        engine_ready.get();
+        lap("wait for engine start-up", t0);
+        for (const std::string &n : hdr.names) {
+            auto it = genome.index.find(n);
+            tid_to_contig.push_back(it == genome.index.end() ? -1 : it->second);
+        }
+    }
+    std::vector<int32_t> &cpo = pk.cpo, cref;
+    for (int32_t t : pk.ctid) cref.push_back(t >= 0 && (size_t)t < tid_to_contig.size() ? tid_to_contig[(size_t)t] : -1);
+    std::vector<uint8_t> &cflags = pk.cflags;
+    std::vector<gcb_read_desc> &reads = pk.reads;
+    std::vector<uint32_t> &cigar = pk.cigar;
+    std::vector<uint8_t> &payload = pk.payload;
+    const std::string &names = pk.names;
+    const std::vector<int64_t> &name_off = pk.name_off;
+    const int32_t n_pairs = pk.n_pairs, n_clusters = (int32_t)cref.size();
     std::vector<int32_t> pair_group((size_t)n_pairs + 1), &n_groups = pk.n_groups;
     n_groups.assign((size_t)n_clusters + 1, 0);
     std::vector<gcb_group_result> &groups = pk.groups;
@@ -858,7 +891,6 @@ std::unique_ptr<Pipeline::Packed> Pipeline::pack_and_run(std::vector<Event> &&ba
     out_payload.resize(payload.size() + 16);
     std::vector<uint64_t> &umi = pk.umi;
     int &umi_words = pk.umi_words;
-    pk.n_pairs = n_pairs;
     if (n_pairs > 0) {
         // 2. UMIs of every read (gcb_extract_umi = BamUtil::getUMI on the GPU), then Pair::setLeft / setRight (pair.cpp:188-216)
         std::vector<uint64_t> read_umi;
@@ -918,7 +950,10 @@ std::unique_ptr<Pipeline::Packed> Pipeline::pack_and_run(std::vector<Event> &&ba
         eng.check(eng.consensus_batch(eng.ctx, &b, &res), "gcb_consensus_batch");
         lap("gcb_consensus_batch", t0);
     }
-    return pkp;
+    // (the packed batch is not needed again: the replay reads the log, the results and the records)
+    std::vector<uint8_t>().swap(payload);
+    std::vector<gcb_read_desc>().swap(reads);
+    std::string().swap(pk.names);
 }
 
 // 4. replay: what the loops around clusterByUMI do with the returned pairs (gencore.cpp:355-360, 409-414)
@@ -1042,8 +1077,8 @@ void Pipeline::run() {
     int last_tid = -1, last_pos = -1;
     // pairs per engine call; GCB_BATCH_PAIRS: smaller batches for tests of the hand-over between the three threads
     const size_t batch_pairs = getenv("GCB_BATCH_PAIRS") ? (size_t)std::max(1L, atol(getenv("GCB_BATCH_PAIRS"))) : (size_t)200000;
-    to_engine.cap = 6;  // (the reader does not stop while the CUDA context starts up: 1 to 4 s on the B200 boxes, six batches ~ 1.7 GB of reads)
-    std::thread engine_thread([this] { engine_stage(); }), writer_thread([this] { writer_stage(); });
+    to_engine.cap = 6;  // (reader and packer do not stop while the CUDA context starts up: 1 to 4 s on the B200 boxes; six batches ~ 2.3 GB of reads and payload)
+    std::thread pack_thread([this] { pack_stage(); }), engine_thread([this] { engine_stage(); }), writer_thread([this] { writer_stage(); });
     double t_read = now_s();
     Rec *b = new Rec();
     while (read_record(in, *b)) {
@@ -1090,7 +1125,8 @@ void Pipeline::run() {
     e.kind = Event::CLEAR_OUTSET;
     log.push_back(std::move(e));
     submit_log();
-    to_engine.close();
+    to_pack.close();
+    pack_thread.join();
     engine_thread.join();
     writer_thread.join();
     double t_close = now_s();
