@@ -393,6 +393,20 @@ def pin_to_gpu_numa_node(torch, local):
         return {"numa_node": None, "note": f"not pinned: {type(e).__name__}"}
 
 
+def bam_to_bam_leg(pairs=300_000, timeout_s=150):
+    """Not the metric: the whole tools, sorted BAM in / consensus BAM out, on one synthetic cfg2-shaped BAM (scripts/bam_bench.py in a
+    process of its own: the stock reference binary on one core, the reference bound to the C ABI, gencore_b200/bin/gencore_b200, the
+    same as two --shard processes plus --merge; outputs compared record by record).  A failure is reported, it does not cost the line."""
+    import subprocess
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bam_bench.py"), str(pairs)], capture_output=True, text=True, timeout=timeout_s)
+        if p.returncode != 0:
+            return {"error": p.stderr.strip().splitlines()[-1][:300] if p.stderr.strip() else "exit %d" % p.returncode}
+        return json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+
 def b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -563,6 +577,8 @@ def b200_arm(args):
             line["cpu_baseline"] = {"value": pairs / float(np.mean(per_rep)), "unit": UNIT, "cores": 1, "kind": kind,
                                     "sample": f"{pairs} pairs of the cfg2 workload x {args.cpu_reps} repetitions, time inside "
                                               f"Cluster::clusterByUMI on one core ({float(np.sum(per_rep)):.1f} s of CPU work)"}
+        if world == 1 and not args.no_bam:
+            line["bam_to_bam"] = bam_to_bam_leg()
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
@@ -586,6 +602,7 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=400_000, help="cpu_baseline sample size (one core)")
     ap.add_argument("--cpu-reps", type=int, default=10, help="cpu_baseline repetitions of the sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bam", action="store_true", help="skip the `bam_to_bam` block (the whole tools on one synthetic BAM, N = 1 only)")
     ap.add_argument("--window-shift", type=int, default=0, help="tuning aid: log2 of the vote's tile window (14 or 15; 0 = automatic)")
     ap.add_argument("--group-lanes", type=int, default=0, help="tuning aid: lanes per cluster in umi_group / select_template (8, 16, 32; 0 = automatic)")
     ap.add_argument("--host-sweep", action="store_true", help="tuning aid: end-to-end times by kind of host memory, to stderr")

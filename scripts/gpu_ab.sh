@@ -28,4 +28,4 @@ tail -3 gpurun_out/pytest_$tag.log
 timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 tail -c 600 gpurun_out/bench_$tag.json
 timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 40 --csv --log-file gpurun_out/launches_$tag.csv \
-  python bench.py --steps 2 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/launches_$tag.log 2>&1
+  python bench.py --steps 2 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong --no-bam > gpurun_out/launches_$tag.log 2>&1

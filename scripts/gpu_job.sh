@@ -14,13 +14,13 @@ tail -c 3000 gpurun_out/bench_$tag.json
 timeout 900 python scripts/shape_perf.py cfg1 cfg3 cfg4 cfg5 cfg2:1000000:14 deep:30:0.01 deep:30:0.003 deep:50:0.003 > gpurun_out/shapes_$tag.log 2>&1
 cat gpurun_out/shapes_$tag.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 40 --csv --log-file gpurun_out/launches_$tag.csv \
-  python bench.py --steps 2 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/launches_$tag.log 2>&1
+  python bench.py --steps 2 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong --no-bam > gpurun_out/launches_$tag.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:vote_ring -s 3 -c 1 -o gpurun_out/prof_ring_$tag \
-  python bench.py --steps 1 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/ncu_ring_$tag.log 2>&1
+  python bench.py --steps 1 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong --no-bam > gpurun_out/ncu_ring_$tag.log 2>&1
 if [ "${3:-}" = "full" ]; then
   for k in select_template slow_columns umi_group duplex_kernel tile_prep2; do
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -o gpurun_out/prof_${k}_$tag \
-      python bench.py --steps 1 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong > gpurun_out/ncu_${k}_$tag.log 2>&1
+      python bench.py --steps 1 --warmup 3 --inner 1 --no-cpu-baseline --no-configs --no-strong --no-bam > gpurun_out/ncu_${k}_$tag.log 2>&1
   done
   timeout 600 python scripts/bam_bench.py 300000 > gpurun_out/bam_bench_$tag.json 2> gpurun_out/bam_bench_$tag.err
   cat gpurun_out/bam_bench_$tag.json
