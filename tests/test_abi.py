@@ -51,3 +51,14 @@ def test_missing_library_fails_loudly(tmp_path):
     from gencore_b200.engine import ConsensusEngine
     with pytest.raises(FileNotFoundError):
         ConsensusEngine(lib_path=str(tmp_path / "nope.so"))
+
+
+def test_header_is_self_contained_c(tmp_path):
+    """include/gencore_b200.h compiles on its own as C and as C++ (a missing <stddef.h> once broke the oracle's build on a fresh tree)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "only_header.c"
+    src.write_text('#include "gencore_b200.h"\nint main(void) { return 0; }\n')
+    for cc, lang in (("gcc", "c"), ("g++", "c++")):
+        p = subprocess.run([cc, "-x", lang, "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), str(src)], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
